@@ -1,0 +1,101 @@
+/*
+ * cemk.h -- C ABI of libcemk.so, the sm_100a CUDA library behind the drop-in `cem_planner`.
+ *
+ * The reference exposes this path only as a Python class (there is no FFI in the reference); each
+ * entry point below replaces one jitted method of `cem_planner`
+ * (reference sampling_based_planner/mjx_planner.py) and is what a ctypes / JAX-FFI / cffi binding of
+ * that class would call.  Conventions:
+ *   - every function returns 0 on success, a negative cemk_status otherwise; nothing throws;
+ *     cemk_last_error() returns a static description of the last failure on the calling thread;
+ *   - all buffers are caller-owned DEVICE pointers (float32 / int32, row-major, shapes as in the
+ *     reference method), kernels are enqueued on `stream` (a cudaStream_t passed as void*) and the
+ *     call returns without synchronising;
+ *   - one handle per device, not thread-safe per handle;
+ *   - B = num_batch (samples on this GPU), T = num_steps, NV = 66 = num_dof(6) * 11 coefficients.
+ */
+#ifndef CEMK_H
+#define CEMK_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cemk_handle cemk_handle;
+
+enum cemk_status {
+  CEMK_OK = 0,
+  CEMK_ERR_ARG = -1,      /* bad argument (null pointer, size out of range) */
+  CEMK_ERR_CUDA = -2,     /* a CUDA runtime call failed */
+  CEMK_ERR_MODEL = -3     /* model table has the wrong size / unsupported topology */
+};
+
+int cemk_version(void);
+const char* cemk_last_error(void);
+/* sizeof(KModel) this library was built with (host bindings assert their mirror matches). */
+int cemk_sizeof_kmodel(void);
+
+/* `kmodel`: host pointer to a KModel (csrc/kmodel.h; built by manipulator_mujoco_b200/kmodel.py from
+ * the compiled MJCF).  Replaces mjx.put_model / put_data in cem_planner.__init__ (mjx_planner.py:100-107). */
+int cemk_create(const void* kmodel, int kmodel_bytes, int device, cemk_handle** out);
+int cemk_destroy(cemk_handle* h);
+/* Update the rollout snapshot (qpos0 / warm0 / qvel0 of the KModel) after construction. */
+int cemk_set_model(cemk_handle* h, const void* kmodel, int kmodel_bytes);
+
+/* Per-horizon constants, host pointers, float32:
+ *   G [3][T][11] = Pdot, Pddot, P (bernstein_coeff_ordern_new, mjx_planner.py:40);
+ *   Kpp [11][11], Kpe [11][5] = per-DOF blocks of Q_inv (mjx_planner.py:166-172, block diagonal per DOF);
+ *   N [11][11] = sum_c G_c^T G_c;  bounds = v_max, a_max, p_max (mjx_planner.py:84-86). */
+int cemk_set_horizon(cemk_handle* h, int T, const float* G, const float* Kpp, const float* Kpe, const float* N,
+                     const float* bounds3);
+
+/* compute_xi_samples (mjx_planner.py:313-316) with the standard-normal draws injected:
+ *   xi[B][66] = mean[66] + z[B][66] . chol(cov[66][66] + 0.003 I)^T.   `chol_ws` [66*66] scratch. */
+int cemk_sample(cemk_handle* h, int B, const float* z, const float* mean, const float* cov, float* chol_ws, float* xi,
+                void* stream);
+
+/* compute_projection_filter (mjx_planner.py:234-249) + Bernstein evaluation (mjx_planner.py:348):
+ *   xi[B][66], state_term[B][30] -> xi_f[B][66]; thetadot[B][6*T] (index dof*T + t) when non-null. */
+int cemk_project(cemk_handle* h, int B, int maxiter_projection, const float* xi, const float* state_term, float* xi_f,
+                 float* thetadot, void* stream);
+
+/* compute_rollout_batch + compute_cost_batch fused (mjx_planner.py:251-303):
+ *   thetadot[B][6T], q0[6], v0[6], target_pos[3], target_rot[4] (device) ->
+ *   theta[B][6T] (post-step joint angles, dof-major), cost4[B][4] = (cost, cost_g, cost_r, cost_c).
+ *   Optional per-step dumps (pass NULL to skip): eef_pos[B][T][3], eef_rot[B][T][4],
+ *   collision[B][T][nslot_robot] (pre-step, mjx_planner.py:259-261), qacc[B][T][12],
+ *   flags[B] (bit 0: more than 32 simultaneously active contacts, extra ones dropped). */
+int cemk_rollout_cost(cemk_handle* h, int B, int T, const float* thetadot, const float* q0, const float* v0,
+                      const float* target_pos, const float* target_rot, float w_pos, float w_rot, float w_col,
+                      float* theta, float* cost4, float* eef_pos, float* eef_rot, float* collision, float* qacc,
+                      int* flags, void* stream);
+
+/* compute_cost_batch alone (mjx_planner.py:277-303), per-sample targets as in the reference method:
+ *   eef_pos[B][T][3], eef_rot[B][T][4], collision[B][T][nslot], target_pos[B][3], target_rot[B][4] -> cost4[B][4]. */
+int cemk_cost_batch(cemk_handle* h, int B, int T, int nslot, const float* eef_pos, const float* eef_rot,
+                    const float* collision, const float* target_pos, const float* target_rot, float w_pos, float w_rot,
+                    float w_col, float* cost4, void* stream);
+
+/* compute_ellite_samples (mjx_planner.py:306-310): stable ascending argsort of cost (NaN last, ties
+ * by lower index).  cost is read with stride `cost_stride` floats.  keys_ws: [n_pow2] uint64 scratch
+ * (n_pow2 = next power of two >= n).  idx_base is added to every index (global sample index of this
+ * shard).  Outputs: idx_sorted[n] (int32, global indices), and when k > 0 the k best rows gathered:
+ * xi_elite[k][66] from xi[n][66] (local rows), cost_elite[k]. */
+int cemk_argsort_topk(cemk_handle* h, int n, const float* cost, int cost_stride, int idx_base, unsigned long long* keys_ws,
+                      int* idx_sorted, int k, const float* xi, float* xi_elite, float* cost_elite, void* stream);
+
+/* Merge of per-GPU elite lists after the NCCL all-gather: n candidates (cost[n], gidx[n] global
+ * sample indices, xi[n][66]); selects the k best by (cost, global index).  keys_ws as above. */
+int cemk_merge_elites(cemk_handle* h, int n, const float* cost, const int* gidx, const float* xi, unsigned long long* keys_ws,
+                      int k, float* xi_elite, float* cost_elite, int* gidx_elite, void* stream);
+
+/* compute_mean_cov (mjx_planner.py:326-335): k elites -> mean_out[66], cov_out[66][66]. */
+int cemk_mean_cov(cemk_handle* h, int k, const float* cost_elite, const float* xi_elite, const float* mean_prev,
+                  const float* cov_prev, float lamda, float alpha_mean, float alpha_cov, float* mean_out, float* cov_out,
+                  void* stream);
+
+/* Number of kernels this library has launched since cemk_create (bench.py's gpu_launches). */
+long long cemk_launch_count(cemk_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

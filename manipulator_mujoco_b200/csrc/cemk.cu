@@ -1,0 +1,489 @@
+// cemk.cu -- sm_100a kernels + the C ABI declared in include/cemk.h.
+//
+// Kernels (one per stage of cem_planner.cem_iter, reference mjx_planner.py:337-362):
+//   k_chol66 / k_sample      compute_xi_samples            (:313-316)
+//   k_project                compute_projection_filter + A_thetadot @ xi   (:181-249, :348)
+//   k_rollout                vmap(scan(mjx.step)) + compute_cost_batch     (:251-303)   <- hot kernel
+//   k_cost_batch             compute_cost_batch on materialised trajectories (:277-303)
+//   k_make_keys / k_bitonic* / k_finish_sort      compute_ellite_samples   (:306-310)
+//   k_mean_cov               compute_mean_cov                              (:326-335)
+// The rollout core lives in rollout_core.h (shared with the CPU emulation used by the no-GPU tests).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/cemk.h"
+#include "rollout_core.h"
+
+#define NVAR 66
+#define NCOEF 11
+#define ROLLOUT_WARPS 4
+
+static thread_local char g_err[256] = "";
+static int set_err(int code, const char* msg) { snprintf(g_err, sizeof g_err, "%s", msg); return code; }
+static int cuda_err(cudaError_t e, const char* where) {
+  snprintf(g_err, sizeof g_err, "%s: %s", where, cudaGetErrorString(e));
+  return CEMK_ERR_CUDA;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_err(e_, #call); } while (0)
+
+struct cemk_handle {
+  int device;
+  KModel* d_model;
+  int T;
+  float* d_G;      // [3][T][11]
+  float* d_K;      // Kpp[121] Kpe[55] N[121] bounds[3]
+  long long launches;
+};
+
+// ---------------------------------------------------------------------------------------------- rollout
+struct RolloutBatch {
+  int B, T;
+  const float* thetadot; const float* q0; const float* v0; const float* target_pos; const float* target_rot;
+  float w_pos, w_rot, w_col;
+  float* theta; float* cost4; float* eef_pos; float* eef_rot; float* collision; float* qacc; int* flags;
+};
+
+__global__ void __launch_bounds__(ROLLOUT_WARPS * 32) k_rollout(const KModel* __restrict__ gm, RolloutBatch a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  KModel* sm = reinterpret_cast<KModel*>(smem_raw);
+  WarpSmem* ws = reinterpret_cast<WarpSmem*>(smem_raw + ((sizeof(KModel) + 15) & ~size_t(15)));
+  {
+    const int* src = reinterpret_cast<const int*>(gm);
+    int* dst = reinterpret_cast<int*>(sm);
+    for (int i = threadIdx.x; i < (int)(sizeof(KModel) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5;
+  const int s = blockIdx.x * ROLLOUT_WARPS + warp;
+  if (s >= a.B) return;
+  Warp W;
+  W.lane = threadIdx.x & 31;
+  RolloutArgs A;
+  const size_t row = (size_t)s * KM_NL * a.T;
+  A.T = a.T;
+  A.thetadot = a.thetadot + row;
+  A.q0 = a.q0; A.v0 = a.v0; A.target_pos = a.target_pos; A.target_rot = a.target_rot;
+  A.w_pos = a.w_pos; A.w_rot = a.w_rot; A.w_col = a.w_col;
+  A.theta = a.theta + row;
+  A.cost4 = a.cost4 + (size_t)s * 4;
+  A.eef_pos = a.eef_pos ? a.eef_pos + (size_t)s * a.T * 3 : nullptr;
+  A.eef_rot = a.eef_rot ? a.eef_rot + (size_t)s * a.T * 4 : nullptr;
+  A.collision = a.collision ? a.collision + (size_t)s * a.T * sm->nslot_robot : nullptr;
+  A.qacc_dbg = a.qacc ? a.qacc + (size_t)s * a.T * KM_NV : nullptr;
+  A.flags = a.flags ? a.flags + s : nullptr;
+  rollout_sample(W, *sm, ws[warp], A);
+}
+
+// ---------------------------------------------------------------------------------------------- sampling
+// L = chol(cov + 0.003 I), lower, row-major [66][66]; one CTA.
+__global__ void __launch_bounds__(256) k_chol66(const float* __restrict__ cov, float* __restrict__ L) {
+  __shared__ float A[NVAR][NVAR + 1];
+  for (int e = threadIdx.x; e < NVAR * NVAR; e += blockDim.x) {
+    int i = e / NVAR, j = e % NVAR;
+    A[i][j] = cov[e] + (i == j ? 0.003f : 0.f);
+  }
+  __syncthreads();
+  for (int j = 0; j < NVAR; ++j) {
+    const float d = sqrtf(A[j][j]);
+    __syncthreads();
+    for (int i = j + threadIdx.x; i < NVAR; i += blockDim.x) A[i][j] = (i == j) ? d : A[i][j] / d;
+    __syncthreads();
+    const int n = NVAR - j - 1;
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+      int i = j + 1 + e / n, k = j + 1 + e % n;
+      if (k <= i) A[i][k] -= A[i][j] * A[k][j];
+    }
+    __syncthreads();
+  }
+  for (int e = threadIdx.x; e < NVAR * NVAR; e += blockDim.x) {
+    int i = e / NVAR, j = e % NVAR;
+    L[e] = j <= i ? A[i][j] : 0.f;
+  }
+}
+// xi[b][i] = mean[i] + sum_{j<=i} L[i][j] z[b][j]
+__global__ void __launch_bounds__(256) k_sample(int B, const float* __restrict__ z, const float* __restrict__ mean,
+                                                const float* __restrict__ L, float* __restrict__ xi) {
+  __shared__ float sL[NVAR][NVAR + 1];
+  __shared__ float sz[4][NVAR];
+  for (int e = threadIdx.x; e < NVAR * NVAR; e += blockDim.x) sL[e / NVAR][e % NVAR] = L[e];
+  const int b0 = blockIdx.x * 4;
+  for (int e = threadIdx.x; e < 4 * NVAR; e += blockDim.x) {
+    int b = b0 + e / NVAR;
+    sz[e / NVAR][e % NVAR] = b < B ? z[(size_t)b * NVAR + e % NVAR] : 0.f;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 4 * NVAR; e += blockDim.x) {
+    int bl = e / NVAR, i = e % NVAR, b = b0 + bl;
+    if (b >= B) continue;
+    float s = 0.f;
+    for (int j = 0; j <= i; ++j) s += sL[i][j] * sz[bl][j];
+    xi[(size_t)b * NVAR + i] = mean[i] + s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- projection
+// One thread per (sample, dof).  Q_inv of the reference is block diagonal per DOF, and the slack /
+// multiplier updates collapse to (see DESIGN.md "projection filter"):
+//   u_c   = G_c x                       c in {velocity, acceleration, position}
+//   r     = sum_c G_c^T clip(u_c, -b_c, b_c)
+//   Lam  -= N x - r                     (sum of the three multipliers; they only ever appear summed)
+//   x'    = Kpp (Lam + xi + N x + r) + Kpe b_eq
+// which is the reference iteration with s and res eliminated.
+__global__ void __launch_bounds__(128) k_project(int B, int T, int iters, const float* __restrict__ G, const float* __restrict__ Kc,
+                                                 const float* __restrict__ xi, const float* __restrict__ state_term,
+                                                 float* __restrict__ xi_f, float* __restrict__ thetadot) {
+  extern __shared__ float sm[];
+  float* sG = sm;                        // [3][T][11]
+  float* sK = sm + 3 * T * NCOEF;        // Kpp[121] Kpe[55] N[121] bounds[3]
+  for (int e = threadIdx.x; e < 3 * T * NCOEF; e += blockDim.x) sG[e] = G[e];
+  for (int e = threadIdx.x; e < 300; e += blockDim.x) sK[e] = Kc[e];
+  __syncthreads();
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= B * 6) return;
+  const int b = gid / 6, d = gid % 6;
+  const float* Kpp = sK; const float* Kpe = sK + 121; const float* Nm = sK + 176; const float* bnd = sK + 297;
+  float x[NCOEF], lam[NCOEF], xs[NCOEF], beq[5], cst[NCOEF];
+#pragma unroll
+  for (int k = 0; k < NCOEF; ++k) { xs[k] = xi[(size_t)b * NVAR + d * NCOEF + k]; lam[k] = 0.f; x[k] = 0.f; }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) beq[k] = state_term[(size_t)b * 30 + k * 6 + d];
+#pragma unroll
+  for (int i = 0; i < NCOEF; ++i) { float s = 0.f; for (int k = 0; k < 5; ++k) s += Kpe[i * 5 + k] * beq[k]; cst[i] = s; }
+  float nx[NCOEF], r[NCOEF];
+#pragma unroll
+  for (int k = 0; k < NCOEF; ++k) { nx[k] = 0.f; r[k] = 0.f; }
+  for (int it = 0; it < iters; ++it) {
+    float rhs[NCOEF];
+#pragma unroll
+    for (int k = 0; k < NCOEF; ++k) rhs[k] = lam[k] + xs[k] + nx[k] + r[k];
+#pragma unroll
+    for (int i = 0; i < NCOEF; ++i) { float s = cst[i]; for (int k = 0; k < NCOEF; ++k) s += Kpp[i * NCOEF + k] * rhs[k]; x[i] = s; }
+#pragma unroll
+    for (int i = 0; i < NCOEF; ++i) { float s = 0.f; for (int k = 0; k < NCOEF; ++k) s += Nm[i * NCOEF + k] * x[k]; nx[i] = s; r[i] = 0.f; }
+    for (int c = 0; c < 3; ++c) {
+      const float bc = bnd[c];
+      const float* Gc = sG + c * T * NCOEF;
+      for (int t = 0; t < T; ++t) {
+        const float* g = Gc + t * NCOEF;
+        float u = 0.f;
+#pragma unroll
+        for (int k = 0; k < NCOEF; ++k) u += g[k] * x[k];
+        u = fminf(fmaxf(u, -bc), bc);
+#pragma unroll
+        for (int k = 0; k < NCOEF; ++k) r[k] += g[k] * u;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NCOEF; ++k) lam[k] -= nx[k] - r[k];
+  }
+#pragma unroll
+  for (int k = 0; k < NCOEF; ++k) xi_f[(size_t)b * NVAR + d * NCOEF + k] = x[k];
+  if (thetadot) {
+    const float* Gv = sG;    // Pdot
+    float* out = thetadot + (size_t)b * 6 * T + (size_t)d * T;
+    for (int t = 0; t < T; ++t) {
+      float u = 0.f;
+#pragma unroll
+      for (int k = 0; k < NCOEF; ++k) u += Gv[t * NCOEF + k] * x[k];
+      out[t] = u;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- standalone cost
+__global__ void __launch_bounds__(128) k_cost_batch(int B, int T, int nslot, const float* __restrict__ eef_pos, const float* __restrict__ eef_rot,
+                                                    const float* __restrict__ collision, const float* __restrict__ tpos, const float* __restrict__ trot,
+                                                    float w_pos, float w_rot, float w_col, float* __restrict__ cost4) {
+  const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (s >= B) return;
+  float cg = 0.f, cr = 0.f, cc = 0.f;
+  const float* tp = tpos + (size_t)s * 3; const float* tq = trot + (size_t)s * 4;
+  const float tn = rsqrtf(tq[0] * tq[0] + tq[1] * tq[1] + tq[2] * tq[2] + tq[3] * tq[3]);
+  for (int t = lane; t < T; t += 32) {
+    const float* p = eef_pos + ((size_t)s * T + t) * 3; const float* q = eef_rot + ((size_t)s * T + t) * 4;
+    float dx = p[0] - tp[0], dy = p[1] - tp[1], dz = p[2] - tp[2];
+    cg += sqrtf(dx * dx + dy * dy + dz * dz);
+    float qn = rsqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    float dp = fabsf((q[0] * tq[0] + q[1] * tq[1] + q[2] * tq[2] + q[3] * tq[3]) * qn * tn);
+    cr += 2.f * acosf(fminf(fmaxf(dp, -1.f), 1.f));
+  }
+  for (int k = lane; k < nslot; k += 32) {
+    float prev = 0.f;
+    for (int t = 0; t < T; ++t) {
+      float c = collision[((size_t)s * T + t) * nslot + k];
+      if (c < 0.f) cc += 1.f;
+      if (t > 0) cc += fmaxf((1.f - 0.005f) * prev - c, 0.f);
+      prev = c;
+    }
+  }
+  for (int o = 16; o; o >>= 1) { cg += __shfl_xor_sync(0xffffffffu, cg, o); cr += __shfl_xor_sync(0xffffffffu, cr, o); cc += __shfl_xor_sync(0xffffffffu, cc, o); }
+  if (lane == 0) {
+    float* o4 = cost4 + (size_t)s * 4;
+    o4[0] = w_pos * cg + w_rot * cr + w_col * cc; o4[1] = cg; o4[2] = cr; o4[3] = cc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- argsort / top-k
+__device__ __forceinline__ unsigned int float_order(float f) {
+  if (f != f) return 0xffffffffu;                       // NaN sorts last (jnp.argsort)
+  unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__global__ void k_make_keys(int n, int npow2, const float* __restrict__ cost, int stride, unsigned long long* __restrict__ keys) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npow2) return;
+  keys[i] = i < n ? (((unsigned long long)float_order(cost[(size_t)i * stride]) << 32) | (unsigned int)i) : ~0ull;
+}
+#define SORT_BLK 4096    // keys per CTA held in shared memory (32 KB)
+// all stages with partner distance < SORT_BLK for merge size k; kfirst: run the full local sort (k = 2..SORT_BLK)
+__global__ void __launch_bounds__(1024) k_bitonic_local(unsigned long long* __restrict__ keys, int npow2, int k_outer, int full) {
+  __shared__ unsigned long long s[SORT_BLK];
+  const int base = blockIdx.x * SORT_BLK;
+  const int cnt = npow2 < SORT_BLK ? npow2 : SORT_BLK;
+  for (int e = threadIdx.x; e < cnt; e += blockDim.x) s[e] = keys[base + e];
+  __syncthreads();
+  for (int k = full ? 2 : k_outer; k <= (full ? cnt : k_outer); k <<= 1) {
+    for (int j = (k >> 1) < cnt ? (k >> 1) : (cnt >> 1); j > 0; j >>= 1) {
+      for (int e = threadIdx.x; e < cnt / 2; e += blockDim.x) {
+        const int i = 2 * e - (e & (j - 1));            // index with bit j clear
+        const int p = i + j;
+        const bool up = (((base + i) & k) == 0);
+        unsigned long long a = s[i], b = s[p];
+        if ((a > b) == up) { s[i] = b; s[p] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int e = threadIdx.x; e < cnt; e += blockDim.x) keys[base + e] = s[e];
+}
+__global__ void k_bitonic_global(unsigned long long* __restrict__ keys, int npow2, int k, int j) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= npow2 / 2) return;
+  const int i = 2 * e - (e & (j - 1));
+  const int p = i + j;
+  const bool up = ((i & k) == 0);
+  unsigned long long a = keys[i], b = keys[p];
+  if ((a > b) == up) { keys[i] = b; keys[p] = a; }
+}
+__global__ void k_finish_sort(int n, const unsigned long long* __restrict__ keys, int idx_base, int* __restrict__ idx_sorted, int k,
+                              const float* __restrict__ cost, int stride, const float* __restrict__ xi, float* __restrict__ xi_elite,
+                              float* __restrict__ cost_elite, const int* __restrict__ aux_in, int* __restrict__ aux_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx_sorted && i < n) idx_sorted[i] = (int)(unsigned int)(keys[i] & 0xffffffffull) + idx_base;
+  if (i < k * NVAR) {
+    const int e = i / NVAR, c = i % NVAR;
+    const int src = (int)(unsigned int)(keys[e] & 0xffffffffull);
+    xi_elite[i] = xi[(size_t)src * NVAR + c];
+    if (c == 0) {
+      cost_elite[e] = cost[(size_t)src * stride];
+      if (aux_out) aux_out[e] = aux_in[src];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- mean / covariance
+// grid = 66 CTAs (one covariance row each); fixed summation order => bit-identical on every rank.
+__global__ void __launch_bounds__(128) k_mean_cov(int k, const float* __restrict__ cost, const float* __restrict__ xi, const float* __restrict__ mean_prev,
+                                                  const float* __restrict__ cov_prev, float lamda, float am, float ac,
+                                                  float* __restrict__ mean_out, float* __restrict__ cov_out) {
+  __shared__ float red[128];
+  __shared__ float smean[NVAR];
+  __shared__ float s_cmin, s_sumw;
+  const int tid = threadIdx.x, row = blockIdx.x;
+  float v = INFINITY;
+  for (int i = tid; i < k; i += 128) v = fminf(v, cost[i]);
+  red[tid] = v; __syncthreads();
+  for (int o = 64; o; o >>= 1) { if (tid < o) red[tid] = fminf(red[tid], red[tid + o]); __syncthreads(); }
+  if (tid == 0) s_cmin = red[0];
+  __syncthreads();
+  const float cmin = s_cmin, il = 1.f / lamda;
+  float sw = 0.f;
+  for (int i = tid; i < k; i += 128) sw += expf(-il * (cost[i] - cmin));
+  red[tid] = sw; __syncthreads();
+  for (int o = 64; o; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
+  if (tid == 0) s_sumw = red[0];
+  __syncthreads();
+  const float sumw = s_sumw;
+  if (tid < NVAR) {
+    float s = 0.f;
+    for (int i = 0; i < k; ++i) s += expf(-il * (cost[i] - cmin)) * xi[(size_t)i * NVAR + tid];
+    float mnew = (1.f - am) * mean_prev[tid] + am * (s / sumw);
+    smean[tid] = mnew;
+    if (row == 0) mean_out[tid] = mnew;
+  }
+  __syncthreads();
+  if (tid < NVAR) {
+    const float mr = smean[row], mj = smean[tid];
+    float s = 0.f;
+    for (int i = 0; i < k; ++i) {
+      float w = expf(-il * (cost[i] - cmin));
+      s += w * (xi[(size_t)i * NVAR + row] - mr) * (xi[(size_t)i * NVAR + tid] - mj);
+    }
+    cov_out[row * NVAR + tid] = (1.f - ac) * cov_prev[row * NVAR + tid] + ac * (s / sumw) + (row == tid ? 0.0001f : 0.f);
+  }
+}
+
+// ================================================================================================ C ABI
+extern "C" {
+
+int cemk_version(void) { return 1; }
+const char* cemk_last_error(void) { return g_err; }
+int cemk_sizeof_kmodel(void) { return (int)sizeof(KModel); }
+
+int cemk_create(const void* kmodel, int kmodel_bytes, int device, cemk_handle** out) {
+  if (!kmodel || !out) return set_err(CEMK_ERR_ARG, "cemk_create: null argument");
+  if (kmodel_bytes != (int)sizeof(KModel)) return set_err(CEMK_ERR_MODEL, "cemk_create: KModel size mismatch");
+  const KModel* km = (const KModel*)kmodel;
+  if (km->nl != KM_NL || km->ncap > KM_MAXCAP || km->nsbox > KM_MAXSBOX || km->nrpair > KM_MAXRPAIR || km->nbpair > KM_MAXBPAIR)
+    return set_err(CEMK_ERR_MODEL, "cemk_create: unsupported topology");
+  CK(cudaSetDevice(device));
+  cemk_handle* h = new cemk_handle();
+  h->device = device; h->T = 0; h->d_G = nullptr; h->d_K = nullptr; h->launches = 0;
+  CK(cudaMalloc(&h->d_model, sizeof(KModel)));
+  CK(cudaMemcpy(h->d_model, kmodel, sizeof(KModel), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&h->d_K, 300 * sizeof(float)));
+  const size_t smem = ((sizeof(KModel) + 15) & ~size_t(15)) + ROLLOUT_WARPS * sizeof(WarpSmem);
+  CK(cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  *out = h;
+  return CEMK_OK;
+}
+int cemk_destroy(cemk_handle* h) {
+  if (!h) return CEMK_OK;
+  cudaSetDevice(h->device);
+  cudaFree(h->d_model); cudaFree(h->d_G); cudaFree(h->d_K);
+  delete h;
+  return CEMK_OK;
+}
+int cemk_set_model(cemk_handle* h, const void* kmodel, int kmodel_bytes) {
+  if (!h || !kmodel) return set_err(CEMK_ERR_ARG, "cemk_set_model: null argument");
+  if (kmodel_bytes != (int)sizeof(KModel)) return set_err(CEMK_ERR_MODEL, "cemk_set_model: KModel size mismatch");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpy(h->d_model, kmodel, sizeof(KModel), cudaMemcpyHostToDevice));
+  return CEMK_OK;
+}
+int cemk_set_horizon(cemk_handle* h, int T, const float* G, const float* Kpp, const float* Kpe, const float* N, const float* bounds3) {
+  if (!h || !G || !Kpp || !Kpe || !N || !bounds3) return set_err(CEMK_ERR_ARG, "cemk_set_horizon: null argument");
+  if (T < 2 || T > 1024) return set_err(CEMK_ERR_ARG, "cemk_set_horizon: T out of range [2, 1024]");
+  CK(cudaSetDevice(h->device));
+  if (h->d_G) { CK(cudaFree(h->d_G)); h->d_G = nullptr; }
+  CK(cudaMalloc(&h->d_G, sizeof(float) * 3 * T * NCOEF));
+  CK(cudaMemcpy(h->d_G, G, sizeof(float) * 3 * T * NCOEF, cudaMemcpyHostToDevice));
+  float kc[300];
+  memcpy(kc, Kpp, 121 * 4); memcpy(kc + 121, Kpe, 55 * 4); memcpy(kc + 176, N, 121 * 4); memcpy(kc + 297, bounds3, 12);
+  CK(cudaMemcpy(h->d_K, kc, sizeof kc, cudaMemcpyHostToDevice));
+  h->T = T;
+  const int smem = (3 * T * NCOEF + 300) * (int)sizeof(float);
+  CK(cudaFuncSetAttribute(k_project, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  return CEMK_OK;
+}
+
+int cemk_sample(cemk_handle* h, int B, const float* z, const float* mean, const float* cov, float* chol_ws, float* xi, void* stream) {
+  if (!h || !z || !mean || !cov || !chol_ws || !xi || B <= 0) return set_err(CEMK_ERR_ARG, "cemk_sample: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  k_chol66<<<1, 256, 0, st>>>(cov, chol_ws);
+  k_sample<<<(B + 3) / 4, 256, 0, st>>>(B, z, mean, chol_ws, xi);
+  h->launches += 2;
+  CK(cudaPeekAtLastError());
+  return CEMK_OK;
+}
+
+int cemk_project(cemk_handle* h, int B, int iters, const float* xi, const float* state_term, float* xi_f, float* thetadot, void* stream) {
+  if (!h || !xi || !state_term || !xi_f || B <= 0 || iters < 1) return set_err(CEMK_ERR_ARG, "cemk_project: bad argument");
+  if (!h->d_G) return set_err(CEMK_ERR_ARG, "cemk_project: cemk_set_horizon has not been called");
+  const int T = h->T, smem = (3 * T * NCOEF + 300) * (int)sizeof(float);
+  k_project<<<(B * 6 + 127) / 128, 128, smem, (cudaStream_t)stream>>>(B, T, iters, h->d_G, h->d_K, xi, state_term, xi_f, thetadot);
+  h->launches += 1;
+  CK(cudaPeekAtLastError());
+  return CEMK_OK;
+}
+
+int cemk_rollout_cost(cemk_handle* h, int B, int T, const float* thetadot, const float* q0, const float* v0, const float* target_pos,
+                      const float* target_rot, float w_pos, float w_rot, float w_col, float* theta, float* cost4, float* eef_pos,
+                      float* eef_rot, float* collision, float* qacc, int* flags, void* stream) {
+  if (!h || !thetadot || !q0 || !v0 || !target_pos || !target_rot || !theta || !cost4 || B <= 0 || T <= 0)
+    return set_err(CEMK_ERR_ARG, "cemk_rollout_cost: bad argument");
+  RolloutBatch a;
+  a.B = B; a.T = T; a.thetadot = thetadot; a.q0 = q0; a.v0 = v0; a.target_pos = target_pos; a.target_rot = target_rot;
+  a.w_pos = w_pos; a.w_rot = w_rot; a.w_col = w_col;
+  a.theta = theta; a.cost4 = cost4; a.eef_pos = eef_pos; a.eef_rot = eef_rot; a.collision = collision; a.qacc = qacc; a.flags = flags;
+  const size_t smem = ((sizeof(KModel) + 15) & ~size_t(15)) + ROLLOUT_WARPS * sizeof(WarpSmem);
+  k_rollout<<<(B + ROLLOUT_WARPS - 1) / ROLLOUT_WARPS, ROLLOUT_WARPS * 32, smem, (cudaStream_t)stream>>>(h->d_model, a);
+  h->launches += 1;
+  CK(cudaPeekAtLastError());
+  return CEMK_OK;
+}
+
+int cemk_cost_batch(cemk_handle* h, int B, int T, int nslot, const float* eef_pos, const float* eef_rot, const float* collision,
+                    const float* target_pos, const float* target_rot, float w_pos, float w_rot, float w_col, float* cost4, void* stream) {
+  if (!h || !eef_pos || !eef_rot || !collision || !target_pos || !target_rot || !cost4 || B <= 0 || T <= 0 || nslot <= 0)
+    return set_err(CEMK_ERR_ARG, "cemk_cost_batch: bad argument");
+  k_cost_batch<<<(B * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(B, T, nslot, eef_pos, eef_rot, collision, target_pos, target_rot, w_pos, w_rot, w_col, cost4);
+  h->launches += 1;
+  CK(cudaPeekAtLastError());
+  return CEMK_OK;
+}
+
+static int sort_keys(cemk_handle* h, int npow2, unsigned long long* keys, cudaStream_t st) {
+  const int nblk = npow2 > SORT_BLK ? npow2 / SORT_BLK : 1;
+  k_bitonic_local<<<nblk, 1024, 0, st>>>(keys, npow2, 0, 1);
+  h->launches += 1;
+  for (int k = 2 * SORT_BLK; k <= npow2; k <<= 1) {
+    for (int j = k >> 1; j >= SORT_BLK; j >>= 1) {
+      k_bitonic_global<<<(npow2 / 2 + 255) / 256, 256, 0, st>>>(keys, npow2, k, j);
+      h->launches += 1;
+    }
+    k_bitonic_local<<<nblk, 1024, 0, st>>>(keys, npow2, k, 0);
+    h->launches += 1;
+  }
+  return CEMK_OK;
+}
+static int next_pow2(int n) { int p = 1; while (p < n) p <<= 1; return p; }
+
+int cemk_argsort_topk(cemk_handle* h, int n, const float* cost, int cost_stride, int idx_base, unsigned long long* keys_ws,
+                      int* idx_sorted, int k, const float* xi, float* xi_elite, float* cost_elite, void* stream) {
+  if (!h || !cost || !keys_ws || n <= 0 || k < 0 || k > n || cost_stride < 1) return set_err(CEMK_ERR_ARG, "cemk_argsort_topk: bad argument");
+  if (k > 0 && (!xi || !xi_elite || !cost_elite)) return set_err(CEMK_ERR_ARG, "cemk_argsort_topk: elite buffers missing");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int np2 = next_pow2(n);
+  k_make_keys<<<(np2 + 255) / 256, 256, 0, st>>>(n, np2, cost, cost_stride, keys_ws);
+  h->launches += 1;
+  sort_keys(h, np2, keys_ws, st);
+  const int work = n > k * NVAR ? n : k * NVAR;
+  k_finish_sort<<<(work + 255) / 256, 256, 0, st>>>(n, keys_ws, idx_base, idx_sorted, k, cost, cost_stride, xi, xi_elite, cost_elite, nullptr, nullptr);
+  h->launches += 1;
+  CK(cudaPeekAtLastError());
+  return CEMK_OK;
+}
+
+int cemk_merge_elites(cemk_handle* h, int n, const float* cost, const int* gidx, const float* xi, unsigned long long* keys_ws, int k,
+                      float* xi_elite, float* cost_elite, int* gidx_elite, void* stream) {
+  if (!h || !cost || !gidx || !xi || !keys_ws || !xi_elite || !cost_elite || !gidx_elite || n <= 0 || k <= 0 || k > n)
+    return set_err(CEMK_ERR_ARG, "cemk_merge_elites: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int np2 = next_pow2(n);
+  // candidate rows arrive rank-major and (cost, index)-sorted within a rank, so the row number breaks
+  // cost ties exactly like the global sample index does
+  k_make_keys<<<(np2 + 255) / 256, 256, 0, st>>>(n, np2, cost, 1, keys_ws);
+  h->launches += 1;
+  sort_keys(h, np2, keys_ws, st);
+  k_finish_sort<<<(k * NVAR + 255) / 256, 256, 0, st>>>(0, keys_ws, 0, nullptr, k, cost, 1, xi, xi_elite, cost_elite, gidx, gidx_elite);
+  h->launches += 1;
+  CK(cudaPeekAtLastError());
+  return CEMK_OK;
+}
+
+int cemk_mean_cov(cemk_handle* h, int k, const float* cost_elite, const float* xi_elite, const float* mean_prev, const float* cov_prev,
+                  float lamda, float alpha_mean, float alpha_cov, float* mean_out, float* cov_out, void* stream) {
+  if (!h || !cost_elite || !xi_elite || !mean_prev || !cov_prev || !mean_out || !cov_out || k <= 0)
+    return set_err(CEMK_ERR_ARG, "cemk_mean_cov: bad argument");
+  k_mean_cov<<<NVAR, 128, 0, (cudaStream_t)stream>>>(k, cost_elite, xi_elite, mean_prev, cov_prev, lamda, alpha_mean, alpha_cov, mean_out, cov_out);
+  h->launches += 1;
+  CK(cudaPeekAtLastError());
+  return CEMK_OK;
+}
+
+long long cemk_launch_count(cemk_handle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

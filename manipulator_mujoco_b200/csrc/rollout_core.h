@@ -1,0 +1,1094 @@
+// rollout_core.h -- one warp rolls one CEM sample through the whole horizon.
+//
+// Replaces, for the planner scene, the reference's `vmap(scan(mjx.step))` + `vmap(compute_cost_single)`
+// (reference sampling_based_planner/mjx_planner.py:251-303): forward kinematics, joint-space
+// inertia, bias forces, primitive-geom narrow phase, MJX's soft-constraint Newton step with its
+// bracketed line search, semi-implicit Euler, and the per-sample cost accumulated on the fly so the
+// [B,T,187] distance tensor is never materialised.
+//
+// Formulation notes (all mathematically equivalent to the MJX algorithm restated in
+// oracle/mjstep.c; only rounding differs):
+//   * spatial vectors are [rot; lin] in world axes about the fixed point m.refpt (MJX uses the
+//     subtree COM of the kinematic tree root; any fixed point gives the same joint-space result);
+//   * gravity is dropped from the robot's recursive Newton-Euler pass because every robot body has
+//     gravcomp = 1, so `qfrc_gravcomp - qfrc_bias(gravity)` cancels identically;
+//   * the free box has its COM at the body origin and a principal-axis inertia, so its mass matrix
+//     is constant and diagonal and its bias is  [-m g ; w x I w];
+//   * only rows of active constraints (dist < 0, limit violated) are built: MJX multiplies the
+//     Jacobian of every inactive row by zero, which leaves H, grad and the line search untouched;
+//   * capsule-box uses the closed form for rectangular faces of `_clip_edge_to_planes`.
+//
+// Written against warp_dsl.h so that tests/emu can single-step it on the CPU.
+#pragma once
+#include "kmodel.h"
+#include "warp_dsl.h"
+
+#define NCMAX 32                          // max simultaneously active contacts per sample
+#define NROWMAX (KM_NL + 4 * NCMAX)
+#define MJ_MINVAL 1e-15f
+#define MJ_MINIMP 0.0001f
+#define MJ_MAXIMP 0.9999f
+
+struct LaneRegs {
+  float prevd[KM_NPASS][2];   // previous-step distance of this lane's robot slots
+  float curd[KM_NPASS][2];
+  float cost_c;               // this lane's share of cost_c
+  int nact, off;              // active contacts this lane will emit, and where
+  int actmask;                // bit (2*pass + slot)
+  float acc[9];               // line-search partial sums
+  float f0, f1, f2;
+};
+
+struct WarpSmem {
+  float qpos[16], qvel[12], warm[12];
+  float lpos[KM_NL][4], lquat[KM_NL][4], lmat[KM_NL][12];
+  float cdof[KM_NL][8], cinert[KM_NL][12], crb[KM_NL][12];
+  float cvel[KM_NL][8], cdofdot[KM_NL][8], cfrc[KM_NL][8];
+  float capA[KM_MAXCAP][4], capB[KM_MAXCAP][4];
+  float bmat[12];
+  float M[KM_NV][KM_NV], H[KM_NV][KM_NV];
+  float fs[12], as[12], qacc[12], Ma[12], grad[12], search[12], mv[12];
+  int ncon, nrow, nlim, flags;
+  float bstage[KM_MAXBPAIR][4][4];    // free-box pair candidates: pos3, dist
+  float bnrm[KM_MAXBPAIR][4];
+  float cgeo[NCMAX][16];              // pos3 n3 t1 3 t2 3 dist invw link1 link2
+  float cJ[NCMAX][36];                // Jn[12] Jt1[12] Jt2[12] (tangents pre-multiplied by mu)
+  float rD[NROWMAX], rAref[NROWMAX], rJaref[NROWMAX], rJv[NROWMAX], rJs[NROWMAX];
+  int limdof[KM_NL];
+  float limsign[KM_NL];
+};
+
+typedef WarpCtx<LaneRegs> Warp;
+
+// ------------------------------------------------------------------------------------------ vec3
+KFN float dot3(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+KFN void cross3(float* r, const float* a, const float* b) {
+  float x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+KFN void sub3(float* r, const float* a, const float* b) { r[0] = a[0] - b[0]; r[1] = a[1] - b[1]; r[2] = a[2] - b[2]; }
+KFN void add3(float* r, const float* a, const float* b) { r[0] = a[0] + b[0]; r[1] = a[1] + b[1]; r[2] = a[2] + b[2]; }
+KFN void madd3(float* r, const float* a, const float* b, float s) { r[0] = a[0] + s * b[0]; r[1] = a[1] + s * b[1]; r[2] = a[2] + s * b[2]; }
+KFN void copy3(float* r, const float* a) { r[0] = a[0]; r[1] = a[1]; r[2] = a[2]; }
+KFN float normalize3(float* a) {
+  float n = sqrtf(dot3(a, a));
+  if (n > 0.f) { float i = 1.f / n; a[0] *= i; a[1] *= i; a[2] *= i; } else { a[0] = a[1] = a[2] = 0.f; }
+  return n;
+}
+KFN void mat_vec(float* r, const float* m, const float* v) {      // row-major 3x3
+  float x = m[0] * v[0] + m[1] * v[1] + m[2] * v[2], y = m[3] * v[0] + m[4] * v[1] + m[5] * v[2], z = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+KFN void matT_vec(float* r, const float* m, const float* v) {
+  float x = m[0] * v[0] + m[3] * v[1] + m[6] * v[2], y = m[1] * v[0] + m[4] * v[1] + m[7] * v[2], z = m[2] * v[0] + m[5] * v[1] + m[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+KFN void quat_mul(float* r, const float* a, const float* b) {
+  float w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  float x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  float y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  float z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  r[0] = w; r[1] = x; r[2] = y; r[3] = z;
+}
+KFN void quat_to_mat(float* m, const float* q) {
+  float w = q[0], x = q[1], y = q[2], z = q[3];
+  m[0] = w * w + x * x - y * y - z * z; m[1] = 2.f * (x * y - w * z);         m[2] = 2.f * (x * z + w * y);
+  m[3] = 2.f * (x * y + w * z);         m[4] = w * w - x * x + y * y - z * z; m[5] = 2.f * (y * z - w * x);
+  m[6] = 2.f * (x * z - w * y);         m[7] = 2.f * (y * z + w * x);         m[8] = w * w - x * x - y * y + z * z;
+}
+// MJX math.make_frame: tangents for a unit normal (rows t1, t2)
+KFN void make_tangents(const float* n, float* t1, float* t2) {
+  float b[3] = {0.f, 0.f, 0.f};
+  if (n[1] > -0.5f && n[1] < 0.5f) b[1] = 1.f; else b[2] = 1.f;
+  float s = dot3(n, b);
+  madd3(b, b, n, -s);
+  normalize3(b);
+  copy3(t1, b);
+  cross3(t2, n, b);
+}
+// spatial algebra (BD.2, BD.4)
+KFN void mul_inert(float* r, const float* i, const float* v) {
+  r[0] = i[0] * v[0] + i[3] * v[1] + i[4] * v[2] - i[8] * v[4] + i[7] * v[5];
+  r[1] = i[3] * v[0] + i[1] * v[1] + i[5] * v[2] + i[8] * v[3] - i[6] * v[5];
+  r[2] = i[4] * v[0] + i[5] * v[1] + i[2] * v[2] - i[7] * v[3] + i[6] * v[4];
+  r[3] = i[8] * v[1] - i[7] * v[2] + i[9] * v[3];
+  r[4] = i[6] * v[2] - i[8] * v[0] + i[9] * v[4];
+  r[5] = i[7] * v[0] - i[6] * v[1] + i[9] * v[5];
+}
+KFN float dot6(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5]; }
+KFN void cross_motion(float* r, const float* v, const float* s) {
+  float a[3], b[3], c[3];
+  cross3(a, v, s); cross3(b, v, s + 3); cross3(c, v + 3, s);
+  r[0] = a[0]; r[1] = a[1]; r[2] = a[2]; r[3] = b[0] + c[0]; r[4] = b[1] + c[1]; r[5] = b[2] + c[2];
+}
+KFN void cross_force(float* r, const float* v, const float* f) {
+  float a[3], b[3], c[3];
+  cross3(a, v, f); cross3(b, v + 3, f + 3); cross3(c, v, f + 3);
+  r[0] = a[0] + b[0]; r[1] = a[1] + b[1]; r[2] = a[2] + b[2]; r[3] = c[0]; r[4] = c[1]; r[5] = c[2];
+}
+
+// ------------------------------------------------------------------------------------------ colliders
+// MJX math.closest_segment_point_and_dist
+KFN float closest_segment_point(float* res, const float* a, const float* b, const float* pt) {
+  float ab[3], ap[3], d[3];
+  sub3(ab, b, a); sub3(ap, pt, a);
+  float t = dot3(ap, ab) / (dot3(ab, ab) + 1e-6f);
+  t = fminf(fmaxf(t, 0.f), 1.f);
+  madd3(res, a, ab, t);
+  sub3(d, pt, res);
+  return dot3(d, d);
+}
+// MJX math.closest_segment_to_segment_points
+KFN void closest_seg_seg(float* besta, float* bestb, const float* a0, const float* a1, const float* b0, const float* b1) {
+  float da[3], db[3], amid[3], bmid[3], tr[3];
+  sub3(da, a1, a0); sub3(db, b1, b0);
+  float ha = 0.5f * normalize3(da), hb = 0.5f * normalize3(db);
+  madd3(amid, a0, da, ha); madd3(bmid, b0, db, hb);
+  sub3(tr, amid, bmid);
+  float dd = dot3(da, db), dat = dot3(da, tr), dbt = dot3(db, tr);
+  float ta = (-dat + dd * dbt) / (1.f - dd * dd + 1e-6f);
+  float tb = dbt + ta * dd;
+  ta = fminf(fmaxf(ta, -ha), ha);
+  tb = fminf(fmaxf(tb, -hb), hb);
+  madd3(besta, amid, da, ta); madd3(bestb, bmid, db, tb);
+  float na[3], nb[3];
+  float d1 = closest_segment_point(na, a0, a1, bestb);
+  float d2 = closest_segment_point(nb, b0, b1, besta);
+  if (d1 < d2) copy3(besta, na); else copy3(bestb, nb);
+}
+
+struct Contact2 { float dist[2], pos[2][3], nrm[2][3]; };
+
+// plane (geom1) vs capsule (geom2); A = centre + axis*hl is slot 0 (MJX plane_capsule offset order)
+template <bool FULL>
+KFN void plane_capsule(const float* ppos, const float* pn, const float* A, const float* B, float r, Contact2& c) {
+  float t[3];
+  sub3(t, B, ppos); c.dist[0] = dot3(t, pn) - r;
+  sub3(t, A, ppos); c.dist[1] = dot3(t, pn) - r;
+  if (FULL) {
+    madd3(c.pos[0], B, pn, -(r + 0.5f * c.dist[0]));
+    madd3(c.pos[1], A, pn, -(r + 0.5f * c.dist[1]));
+    copy3(c.nrm[0], pn); copy3(c.nrm[1], pn);
+  }
+}
+// capsule_capsule -> sphere_sphere on the closest segment points
+template <bool FULL>
+KFN void capsule_capsule(const float* a0, const float* a1, float r1, const float* b0, const float* b1, float r2, Contact2& c) {
+  float pa[3], pb[3], n[3];
+  closest_seg_seg(pa, pb, a0, a1, b0, b1);
+  sub3(n, pb, pa);
+  float dn = normalize3(n);
+  if (dn == 0.f) { n[0] = 1.f; n[1] = 0.f; n[2] = 0.f; }
+  c.dist[0] = dn - (r1 + r2);
+  c.dist[1] = 1.f;
+  if (FULL) { madd3(c.pos[0], pa, n, r1 + 0.5f * c.dist[0]); copy3(c.nrm[0], n); }
+}
+// capsule (geom1) vs box (geom2), MJX capsule_convex with rectangular faces; see header note.
+template <bool FULL>
+KFN void capsule_box(const float* A, const float* B, float r, const float* bpos, const float* bmat, const float* bsize, Contact2& c) {
+  float t[3], a[3], b[3];
+  sub3(t, A, bpos); matT_vec(a, bmat, t);
+  sub3(t, B, bpos); matT_vec(b, bmat, t);
+  // best face: argmax over (+x,-x,+y,-y,+z,-z) of min over end points of the signed face distance
+  float bests = fminf(a[0], b[0]) - bsize[0]; int bk = 0; float sg = 1.f;
+  { float s = -fmaxf(a[0], b[0]) - bsize[0]; if (s > bests) { bests = s; sg = -1.f; } }
+  { float s = fminf(a[1], b[1]) - bsize[1]; if (s > bests) { bests = s; bk = 1; sg = 1.f; } }
+  { float s = -fmaxf(a[1], b[1]) - bsize[1]; if (s > bests) { bests = s; bk = 1; sg = -1.f; } }
+  { float s = fminf(a[2], b[2]) - bsize[2]; if (s > bests) { bests = s; bk = 2; sg = 1.f; } }
+  { float s = -fmaxf(a[2], b[2]) - bsize[2]; if (s > bests) { bests = s; bk = 2; sg = -1.f; } }
+  // cyclic permutation into (k, u, w) coordinates without dynamic indexing
+  float ak, au, aw, bk_, bu, bw, sk, su, sw;
+  if (bk == 0)      { ak = a[0]; au = a[1]; aw = a[2]; bk_ = b[0]; bu = b[1]; bw = b[2]; sk = bsize[0]; su = bsize[1]; sw = bsize[2]; }
+  else if (bk == 1) { ak = a[1]; au = a[2]; aw = a[0]; bk_ = b[1]; bu = b[2]; bw = b[0]; sk = bsize[1]; su = bsize[2]; sw = bsize[0]; }
+  else              { ak = a[2]; au = a[0]; aw = a[1]; bk_ = b[2]; bu = b[0]; bw = b[1]; sk = bsize[2]; su = bsize[0]; sw = bsize[1]; }
+  // clip the segment (parameter 0..1 from a to b) against the four side planes
+  float t0 = 0.f, t1 = 1.f; bool both = false;
+  {
+    const float Lu = 2.f * sw, Lw = 2.f * su;      // length of the edge each side plane is built on
+#define CEMK_CLIP(pa, pb, s, tau, L) { \
+      float na_ = ((tau) * (pa) - (s)) * (L), nb_ = ((tau) * (pb) - (s)) * (L); \
+      bool fa = na_ > 1e-6f, fb = nb_ > 1e-6f; \
+      float den = (tau) * ((pb) - (pa)) * (L); \
+      float tt = (-na_) / (den + (den == 0.f ? 1e-6f : 0.f)); \
+      tt = fminf(fmaxf(tt, 0.f), 1.f); \
+      if (fa) t0 = fmaxf(t0, tt); \
+      if (fb) t1 = fminf(t1, tt); \
+      both = both || (fa && fb); }
+    CEMK_CLIP(au, bu, su, -1.f, Lu)
+    CEMK_CLIP(aw, bw, sw, -1.f, Lw)
+    CEMK_CLIP(au, bu, su, 1.f, Lu)
+    CEMK_CLIP(aw, bw, sw, 1.f, Lw)
+#undef CEMK_CLIP
+  }
+  bool mask = !both;
+  if (!mask) { t0 = 0.f; t1 = 1.f; }
+  {
+    float dk = bk_ - ak, du = bu - au, dw = bw - aw;
+    if ((t1 - t0) * (dk * dk + du * du + dw * dw) < 0.f) mask = false;
+  }
+  float h0 = sg * (ak + t0 * (bk_ - ak)) - r - sk, h1 = sg * (ak + t1 * (bk_ - ak)) - r - sk;
+  c.dist[0] = mask ? h0 : 1.f;
+  c.dist[1] = mask ? h1 : 1.f;
+  float lp[2][3], ln[2][3];     // contact point / normal in (k,u,w) box coordinates
+  if (FULL) {
+    lp[0][0] = sg * (sk + 0.5f * h0); lp[0][1] = au + t0 * (bu - au); lp[0][2] = aw + t0 * (bw - aw);
+    lp[1][0] = sg * (sk + 0.5f * h1); lp[1][1] = au + t1 * (bu - au); lp[1][2] = aw + t1 * (bw - aw);
+    ln[0][0] = -sg; ln[0][1] = 0.f; ln[0][2] = 0.f;
+    ln[1][0] = -sg; ln[1][1] = 0.f; ln[1][2] = 0.f;
+  }
+  // shallow edge contact: an edge of the face closer than r to the segment replaces slot 0.
+  // Every edge lies in the face plane, so nothing to do when the segment stays >= r away from it.
+  float ha = sg * ak - sk, hb = sg * bk_ - sk;
+  float hmin = (ha * hb <= 0.f) ? 0.f : fminf(fabsf(ha), fabsf(hb));
+  if (hmin < r) {
+    // face polygon, counter-clockwise seen from outside; edge i runs from V[i-1] to V[i]
+    float fu[4] = {-su, su, su, -su}, fw[4] = {-sw, -sw, sw, sw};
+    if (sg < 0.f) { fu[0] = -su; fw[0] = sw; fu[1] = su; fw[1] = sw; fu[2] = su; fw[2] = -sw; fu[3] = -su; fw[3] = -sw; }
+    float pa[3] = {ak, au, aw}, pb[3] = {bk_, bu, bw};
+    float bd = 0.f, bec[3] = {0.f, 0.f, 0.f}, bcc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int ip = (i + 3) & 3;
+      float e0[3] = {sg * sk, fu[ip], fw[ip]}, e1[3] = {sg * sk, fu[i], fw[i]}, ec[3], cc[3], df[3];
+      closest_seg_seg(ec, cc, e0, e1, pa, pb);
+      sub3(df, ec, cc);
+      float d2 = dot3(df, df);
+      if (i == 0 || d2 < bd) { bd = d2; copy3(bec, ec); copy3(bcc, cc); }
+    }
+    float eax[3];
+    sub3(eax, bcc, bec);
+    float ed = normalize3(eax);
+    float epen = r - ed;
+    if (epen > 0.f) {
+      c.dist[0] = -epen;
+      if (FULL) {
+        for (int q = 0; q < 3; ++q) { lp[0][q] = 0.5f * (bec[q] + bcc[q] - eax[q] * r); ln[0][q] = -eax[q]; }
+      }
+    }
+  }
+  if (FULL) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      float p[3], n[3];
+      if (bk == 0)      { p[0] = lp[j][0]; p[1] = lp[j][1]; p[2] = lp[j][2]; n[0] = ln[j][0]; n[1] = ln[j][1]; n[2] = ln[j][2]; }
+      else if (bk == 1) { p[1] = lp[j][0]; p[2] = lp[j][1]; p[0] = lp[j][2]; n[1] = ln[j][0]; n[2] = ln[j][1]; n[0] = ln[j][2]; }
+      else              { p[2] = lp[j][0]; p[0] = lp[j][1]; p[1] = lp[j][2]; n[2] = ln[j][0]; n[0] = ln[j][1]; n[1] = ln[j][2]; }
+      float w[3];
+      mat_vec(w, bmat, p); add3(c.pos[j], w, bpos);
+      mat_vec(c.nrm[j], bmat, n);
+      normalize3(c.nrm[j]);
+    }
+  }
+}
+
+// ---- free-box colliders (lane-serial, rarely past the bounding-sphere test) -------------------
+// 4-point manifold selection of MJX _manifold_points, with the oracle's distinct-point tie rule
+KFN void manifold_points(int n, float poly[][3], const bool* mask, const float* nrm, int* idx) {
+  float dm[16];
+  for (int i = 0; i < n; ++i) dm[i] = mask[i] ? 0.f : -1e6f;
+  int a = 0;
+  for (int i = 1; i < n; ++i) if (dm[i] > dm[a]) a = i;
+  int b = 0; float bv = 0.f;
+  for (int i = 0; i < n; ++i) { float t[3]; sub3(t, poly[a], poly[i]); float v = dot3(t, t) + dm[i]; if (i == 0 || v > bv) { bv = v; b = i; } }
+  float ab[3], t[3];
+  sub3(t, poly[a], poly[b]); cross3(ab, nrm, t);
+  int c = 0; float cv = 0.f;
+  for (int i = 0; i < n; ++i) { float ap[3]; sub3(ap, poly[a], poly[i]); float v = fabsf(dot3(ap, ab)) + dm[i]; if (i == 0 || v > cv) { cv = v; c = i; } }
+  float ac[3], bc[3];
+  sub3(t, poly[a], poly[c]); cross3(ac, nrm, t);
+  sub3(t, poly[b], poly[c]); cross3(bc, nrm, t);
+  int dsel = 0; float dv = 0.f;
+  for (int i = 0; i < n; ++i) {
+    float bp[3], ap[3];
+    sub3(bp, poly[b], poly[i]); sub3(ap, poly[a], poly[i]);
+    float v = fmaxf(fabsf(dot3(bp, bc)), fabsf(dot3(ap, ac))) + dm[i] - ((i == a || i == b || i == c) ? 2e6f : 0.f);
+    if (i == 0 || v > dv) { dv = v; dsel = i; }
+  }
+  idx[0] = a; idx[1] = b; idx[2] = c; idx[3] = dsel;
+}
+KFN void box_face(const float* s, int f, float v[4][3], float* n) {
+  int k = f >> 1, u = (k + 1) % 3, w = (k + 2) % 3;
+  float sg = (f & 1) ? -1.f : 1.f;
+  n[0] = n[1] = n[2] = 0.f; n[k] = sg;
+  const float su[4] = {-1.f, 1.f, 1.f, -1.f}, sw[4] = {-1.f, -1.f, 1.f, 1.f};
+  for (int i = 0; i < 4; ++i) {
+    int ii = (f & 1) ? 3 - i : i;
+    v[i][k] = sg * s[k]; v[i][u] = su[ii] * s[u]; v[i][w] = sw[ii] * s[w];
+  }
+}
+// plane (geom1) vs free box: out[k] = pos3, dist; normal = plane normal.  Only penetrating
+// vertices matter (these slots never enter the cost), see oracle plane_box.
+KFN int plane_box(const float* ppos, const float* pn, const float* bpos, const float* bmat, const float* bs, float out[4][4]) {
+  float v[8][3], sup[8], t[3], pl[3], n[3], smax = -1e30f;
+  bool mask[8]; int idx[4];
+  sub3(t, ppos, bpos); matT_vec(pl, bmat, t); matT_vec(n, bmat, pn);
+  for (int i = 0; i < 8; ++i) {
+    v[i][0] = (i & 4 ? 1.f : -1.f) * bs[0]; v[i][1] = (i & 2 ? 1.f : -1.f) * bs[1]; v[i][2] = (i & 1 ? 1.f : -1.f) * bs[2];
+    sub3(t, pl, v[i]); sup[i] = dot3(t, n); smax = fmaxf(smax, sup[i]);
+  }
+  float thr = fmaxf(0.f, smax - 1e-3f);
+  for (int i = 0; i < 8; ++i) mask[i] = sup[i] > thr;
+  manifold_points(8, v, mask, n, idx);
+  int nact = 0;
+  for (int k = 0; k < 4; ++k) {
+    bool uniq = true;
+    for (int q = 0; q < k; ++q) if (idx[q] == idx[k]) uniq = false;
+    float w[3];
+    mat_vec(w, bmat, v[idx[k]]); add3(w, w, bpos);
+    float d = uniq ? -sup[idx[k]] : 1.f;
+    madd3(out[k], w, pn, -0.5f * d);
+    out[k][3] = d;
+    nact += d < 0.f;
+  }
+  return nact;
+}
+KFN int clip_poly_halfplane(int n, float in[][3], float out[][3], const float* pp, const float* pn) {
+  int m = 0;
+  for (int i = 0; i < n; ++i) {
+    const float* a = in[i]; const float* b = in[(i + 1) % n];
+    float ta[3], tb[3];
+    sub3(ta, a, pp); sub3(tb, b, pp);
+    float da = dot3(ta, pn), db = dot3(tb, pn);
+    if (da <= 0.f) { copy3(out[m], a); ++m; }
+    if ((da < 0.f && db > 0.f) || (da > 0.f && db < 0.f)) {
+      float s = da / (da - db), ab[3];
+      sub3(ab, b, a); madd3(out[m], a, ab, s); ++m;
+    }
+  }
+  return m;
+}
+// static box (geom1) vs free box (geom2): SAT over 15 axes, then clipped face manifold or a single
+// edge-edge contact.  out[k] = pos3, dist; nrm = contact normal (geom1 -> geom2), world frame.
+KFN int box_box(const float* p1, const float* m1, const float* s1, const float* p2, const float* m2, const float* s2, float out[4][4], float* nrm) {
+  float t[3], c[3], R[9];
+  sub3(t, p1, p2); matT_vec(c, m2, t);
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R[3 * i + j] = m2[i] * m1[j] + m2[3 + i] * m1[3 + j] + m2[6 + i] * m1[6 + j];
+  float A[3][3];
+  for (int i = 0; i < 3; ++i) { A[i][0] = R[i]; A[i][1] = R[3 + i]; A[i][2] = R[6 + i]; }
+  float bestsep = -1e30f; int besttype = -1, bi = 0, bj = 0; float bestn[3] = {0.f, 0.f, 1.f};
+  for (int type = 0; type < 3; ++type) for (int i = 0; i < 3; ++i) for (int j = 0; j < (type == 2 ? 3 : 1); ++j) {
+    float ax[3] = {0.f, 0.f, 0.f};
+    if (type == 0) ax[i] = 1.f; else if (type == 1) copy3(ax, A[i]);
+    else { float e2[3] = {0.f, 0.f, 0.f}; e2[j] = 1.f; cross3(ax, A[i], e2); if (normalize3(ax) < 1e-6f) continue; }
+    float r1 = 0.f, r2 = 0.f;
+    for (int k = 0; k < 3; ++k) { r1 += s1[k] * fabsf(dot3(A[k], ax)); r2 += s2[k] * fabsf(ax[k]); }
+    float dc = dot3(c, ax);
+    float cmp = fabsf(dc) - r1 - r2 - (type == 2 ? 1e-6f : 0.f);
+    if (cmp > bestsep) {
+      bestsep = cmp; besttype = type; bi = i; bj = j;
+      float sgn = dc > 0.f ? -1.f : 1.f;
+      bestn[0] = ax[0] * sgn; bestn[1] = ax[1] * sgn; bestn[2] = ax[2] * sgn;
+    }
+  }
+  for (int k = 0; k < 4; ++k) { out[k][0] = out[k][1] = out[k][2] = 0.f; out[k][3] = 1.f; }
+  mat_vec(nrm, m2, bestn);
+  normalize3(nrm);
+  if (bestsep > 0.f) return 0;                 // separated: no slot can be active
+  if (besttype == 2) {
+    float e1c[3], e2c[3] = {0.f, 0.f, 0.f};
+    copy3(e1c, c);
+    for (int k = 0; k < 3; ++k) if (k != bi) { float sgn = dot3(A[k], bestn) > 0.f ? 1.f : -1.f; madd3(e1c, e1c, A[k], sgn * s1[k]); }
+    for (int k = 0; k < 3; ++k) if (k != bj) e2c[k] = (bestn[k] > 0.f ? -1.f : 1.f) * s2[k];
+    float a0[3], a1[3], b0[3], b1[3], pa[3], pb[3], e2[3] = {0.f, 0.f, 0.f};
+    e2[bj] = 1.f;
+    madd3(a0, e1c, A[bi], -s1[bi]); madd3(a1, e1c, A[bi], s1[bi]);
+    madd3(b0, e2c, e2, -s2[bj]); madd3(b1, e2c, e2, s2[bj]);
+    closest_seg_seg(pa, pb, a0, a1, b0, b1);
+    float mid[3] = {0.5f * (pa[0] + pb[0]), 0.5f * (pa[1] + pb[1]), 0.5f * (pa[2] + pb[2])}, w[3], df[3];
+    mat_vec(w, m2, mid); add3(out[0], w, p2);
+    sub3(df, pb, pa);
+    out[0][3] = dot3(df, bestn);
+    return out[0][3] < 0.f;
+  }
+  float rc[3], Rr[9], rs[3], is[3], nref[3];
+  bool swap = besttype == 1;
+  if (!swap) {
+    copy3(rc, c); for (int k = 0; k < 9; ++k) Rr[k] = R[k];
+    copy3(rs, s2); copy3(is, s1); nref[0] = -bestn[0]; nref[1] = -bestn[1]; nref[2] = -bestn[2];
+  } else {
+    float mc[3] = {-c[0], -c[1], -c[2]};
+    matT_vec(rc, R, mc);
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Rr[3 * i + j] = R[3 * j + i];
+    copy3(rs, s1); copy3(is, s2);
+    matT_vec(nref, R, bestn);
+  }
+  int k = 0; for (int q = 1; q < 3; ++q) if (fabsf(nref[q]) > fabsf(nref[k])) k = q;
+  int rf = 2 * k + (nref[k] > 0.f ? 0 : 1);
+  float rface[4][3], rn[3];
+  box_face(rs, rf, rface, rn);
+  int inf = 0; float mind = 1e30f;
+  for (int f = 0; f < 6; ++f) {
+    int kk = f >> 1; float sgn = (f & 1) ? -1.f : 1.f;
+    float fn[3] = {sgn * Rr[kk], sgn * Rr[3 + kk], sgn * Rr[6 + kk]};
+    float dd = dot3(fn, rn);
+    if (dd < mind) { mind = dd; inf = f; }
+  }
+  float iface[4][3], itmp[3], poly[16][3], poly2[16][3];
+  box_face(is, inf, iface, itmp);
+  for (int i = 0; i < 4; ++i) { mat_vec(poly[i], Rr, iface[i]); add3(poly[i], poly[i], rc); }
+  int np = 4;
+  for (int i = 0; i < 4 && np > 0; ++i) {
+    float e[3], en[3];
+    sub3(e, rface[i], rface[(i + 3) % 4]);
+    cross3(en, e, rn); normalize3(en);
+    np = clip_poly_halfplane(np, poly, poly2, rface[i], en);
+    for (int q = 0; q < np; ++q) copy3(poly[q], poly2[q]);
+  }
+  if (np == 0) return 0;
+  float pref[16][3], depth[16]; bool mask[16]; int idx[4];
+  for (int i = 0; i < np; ++i) {
+    float tt[3]; sub3(tt, poly[i], rface[0]);
+    float h = dot3(tt, rn);
+    depth[i] = -h; mask[i] = h < 0.f;
+    madd3(pref[i], poly[i], rn, -h);
+  }
+  manifold_points(np, pref, mask, rn, idx);
+  int nact = 0;
+  for (int q = 0; q < 4; ++q) {
+    int i = idx[q]; bool uniq = true;
+    for (int z = 0; z < q; ++z) if (idx[z] == i) uniq = false;
+    if (!mask[i] || !uniq) continue;
+    float w[3];
+    if (swap) { float u[3]; mat_vec(u, R, pref[i]); add3(u, u, c); mat_vec(w, m2, u); }
+    else mat_vec(w, m2, pref[i]);
+    add3(out[q], w, p2);
+    out[q][3] = -depth[i];
+    ++nact;
+  }
+  return nact;
+}
+
+// ------------------------------------------------------------------------------------------ constraints
+// MJX constraint._kbi + row regulariser (BD.8)
+KFN void row_params(const KModel& m, float pos, float invw, float vel, float& D, float& aref) {
+  float tc = fmaxf(m.solref[0], 2.f * m.dt), dr = m.solref[1];
+  float dmin = fminf(fmaxf(m.solimp[0], MJ_MINIMP), MJ_MAXIMP), dmax = fminf(fmaxf(m.solimp[1], MJ_MINIMP), MJ_MAXIMP);
+  float width = fmaxf(m.solimp[2], MJ_MINVAL), mid = fminf(fmaxf(m.solimp[3], MJ_MINIMP), MJ_MAXIMP), power = fmaxf(m.solimp[4], 1.f);
+  float k = 1.f / (dmax * dmax * tc * tc * dr * dr), b = 2.f / (dmax * tc);
+  if (m.solref[0] <= 0.f) k = -m.solref[0] / (dmax * dmax);
+  if (m.solref[1] <= 0.f) b = -m.solref[1] / dmax;
+  float x = fabsf(pos) / width, y;
+  if (x < mid) y = powf(x, power) / powf(mid, power - 1.f);
+  else y = 1.f - powf(1.f - x, power) / powf(1.f - mid, power - 1.f);
+  float imp = fminf(fmaxf(dmin + y * (dmax - dmin), dmin), dmax);
+  if (x > 1.f) imp = dmax;
+  float R = fmaxf(invw * (1.f - imp) / imp, MJ_MINVAL);
+  D = 1.f / R;
+  aref = -b * vel - k * imp * pos;
+}
+// translational Jacobian column of world point p on `link` (0..5 robot link, 6 free box, <0 static)
+KFN void jac_col(const KModel& m, const WarpSmem& S, const float* p, int link, int d, float* col) {
+  col[0] = col[1] = col[2] = 0.f;
+  if (link < 0) return;
+  if (d < KM_NL) {
+    if (link >= KM_NL || d > link) return;
+    float off[3], t[3];
+    sub3(off, p, m.refpt);
+    cross3(t, S.cdof[d], off);
+    add3(col, S.cdof[d] + 3, t);
+  } else {
+    if (link != KM_NL) return;
+    int k = d - KM_NL;
+    if (k < 3) { col[k] = 1.f; return; }
+    k -= 3;
+    float r[3] = {S.bmat[k], S.bmat[3 + k], S.bmat[6 + k]}, off[3];
+    sub3(off, p, S.qpos + KM_NL);
+    cross3(col, r, off);
+  }
+}
+// J_r . v for constraint row r
+KFN float row_dot(const WarpSmem& S, int r, const float* v) {
+  if (r < S.nlim) return S.limsign[r] * v[S.limdof[r]];
+  int c = (r - S.nlim) >> 2, q = (r - S.nlim) & 3;
+  const float* Jn = S.cJ[c]; const float* Jt = S.cJ[c] + (q < 2 ? 12 : 24);
+  float sn = 0.f, st = 0.f;
+#pragma unroll
+  for (int d = 0; d < KM_NV; ++d) { sn += Jn[d] * v[d]; st += Jt[d] * v[d]; }
+  return (q & 1) ? sn - st : sn + st;
+}
+KFN float row_J(const WarpSmem& S, int r, int d) {
+  if (r < S.nlim) return S.limdof[r] == d ? S.limsign[r] : 0.f;
+  int c = (r - S.nlim) >> 2, q = (r - S.nlim) & 3;
+  float jn = S.cJ[c][d], jt = S.cJ[c][(q < 2 ? 12 : 24) + d];
+  return (q & 1) ? jn - jt : jn + jt;
+}
+
+struct LSPoint { float alpha, cost, d0, d1; };
+KFN bool in_bracket(const LSPoint& x, const LSPoint& y) {
+  return ((x.d0 < y.d0) && (y.d0 < 0.f)) || ((x.d0 > y.d0) && (y.d0 > 0.f));
+}
+// evaluate the 1-D piecewise quadratic at up to three step sizes at once (BD.10)
+KFN void ls_eval(Warp& W, const WarpSmem& S, const float* qg, int n, const float* alpha, LSPoint* out) {
+  LANES(W, R)
+    for (int k = 0; k < 9; ++k) R.acc[k] = 0.f;
+    for (int r = lane; r < S.nrow; r += 32) {
+      float ja = S.rJaref[r], jv = S.rJv[r], D = S.rD[r];
+      float q0 = 0.5f * D * ja * ja, q1 = D * jv * ja, q2 = 0.5f * D * jv * jv;
+      for (int k = 0; k < n; ++k) if (ja + alpha[k] * jv < 0.f) { R.acc[3 * k] += q0; R.acc[3 * k + 1] += q1; R.acc[3 * k + 2] += q2; }
+    }
+  END_LANES
+  for (int k = 0; k < n; ++k) {
+    float q0 = qg[0] + warp_sum(W, [&](int, LaneRegs& R) { return R.acc[3 * k]; });
+    float q1 = qg[1] + warp_sum(W, [&](int, LaneRegs& R) { return R.acc[3 * k + 1]; });
+    float q2 = qg[2] + warp_sum(W, [&](int, LaneRegs& R) { return R.acc[3 * k + 2]; });
+    float a = alpha[k];
+    out[k].alpha = a;
+    out[k].cost = a * a * q2 + a * q1 + q0;
+    out[k].d0 = 2.f * a * q2 + q1;
+    out[k].d1 = 2.f * q2 + (q2 == 0.f ? MJ_MINVAL : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ one forward()
+// Inputs: S.qpos, S.qvel, S.warm.  Outputs: S.qacc (= new warm start), per-lane R.curd, link frames.
+KFN void step_forward(Warp& W, const KModel& m, WarpSmem& S) {
+  // ---- P1: serial joint chain (uniform) ----
+  {
+    float pq[4] = {m.base_quat[0], m.base_quat[1], m.base_quat[2], m.base_quat[3]};
+    float pp[3] = {m.base_pos[0], m.base_pos[1], m.base_pos[2]}, pm[9];
+    quat_to_mat(pm, pq);
+    USYNC();
+    for (int i = 0; i < KM_NL; ++i) {
+      float p[3], q[4], t[3], qj[4], mat[9];
+      mat_vec(t, pm, m.l_pos[i]); add3(p, pp, t);
+      quat_mul(q, pq, m.l_quat[i]);
+      float ang = 0.5f * S.qpos[i], sn, cs;
+      sincosf(ang, &sn, &cs);
+      qj[0] = cs; qj[1] = sn * m.l_axis[i][0]; qj[2] = sn * m.l_axis[i][1]; qj[3] = sn * m.l_axis[i][2];
+      quat_mul(q, q, qj);
+      quat_to_mat(mat, q);
+      UNIFORM_WRITE(W) {
+        copy3(S.lpos[i], p);
+        for (int k = 0; k < 4; ++k) S.lquat[i][k] = q[k];
+        for (int k = 0; k < 9; ++k) S.lmat[i][k] = mat[k];
+      } END_UNIFORM_WRITE
+      copy3(pp, p);
+      for (int k = 0; k < 4; ++k) pq[k] = q[k];
+      for (int k = 0; k < 9; ++k) pm[k] = mat[k];
+    }
+  }
+  // ---- P2: per-link spatial quantities, capsule end points, box frame ----
+  LANES(W, R)
+    if (lane < KM_NL) {
+      const int i = lane;
+      float a[3], off[3], com[3], d[3], t[3];
+      mat_vec(a, S.lmat[i], m.l_axis[i]);
+      sub3(off, m.refpt, S.lpos[i]);
+      copy3(S.cdof[i], a);
+      cross3(S.cdof[i] + 3, a, off);
+      mat_vec(t, S.lmat[i], m.l_com[i]); add3(com, S.lpos[i], t);
+      sub3(d, com, m.refpt);
+      const float* I = m.l_inertia[i]; const float* Rm = S.lmat[i];
+      float ms = I[6];
+      // T = R I R^T, I symmetric (xx yy zz xy xz yz)
+      float RI[9];
+      for (int r = 0; r < 3; ++r) {
+        RI[3 * r + 0] = Rm[3 * r] * I[0] + Rm[3 * r + 1] * I[3] + Rm[3 * r + 2] * I[4];
+        RI[3 * r + 1] = Rm[3 * r] * I[3] + Rm[3 * r + 1] * I[1] + Rm[3 * r + 2] * I[5];
+        RI[3 * r + 2] = Rm[3 * r] * I[4] + Rm[3 * r + 1] * I[5] + Rm[3 * r + 2] * I[2];
+      }
+      float T00 = RI[0] * Rm[0] + RI[1] * Rm[1] + RI[2] * Rm[2];
+      float T11 = RI[3] * Rm[3] + RI[4] * Rm[4] + RI[5] * Rm[5];
+      float T22 = RI[6] * Rm[6] + RI[7] * Rm[7] + RI[8] * Rm[8];
+      float T01 = RI[0] * Rm[3] + RI[1] * Rm[4] + RI[2] * Rm[5];
+      float T02 = RI[0] * Rm[6] + RI[1] * Rm[7] + RI[2] * Rm[8];
+      float T12 = RI[3] * Rm[6] + RI[4] * Rm[7] + RI[5] * Rm[8];
+      float* ci = S.cinert[i];
+      ci[0] = T00 + ms * (d[1] * d[1] + d[2] * d[2]);
+      ci[1] = T11 + ms * (d[0] * d[0] + d[2] * d[2]);
+      ci[2] = T22 + ms * (d[0] * d[0] + d[1] * d[1]);
+      ci[3] = T01 - ms * d[0] * d[1];
+      ci[4] = T02 - ms * d[0] * d[2];
+      ci[5] = T12 - ms * d[1] * d[2];
+      ci[6] = ms * d[0]; ci[7] = ms * d[1]; ci[8] = ms * d[2]; ci[9] = ms;
+    } else if (lane >= 8 && lane < 8 + m.ncap) {
+      const int j = lane - 8, L = m.cap_link[j];
+      float cpos[3], ax[3], t[3];
+      mat_vec(t, S.lmat[L], m.cap_pos[j]); add3(cpos, S.lpos[L], t);
+      mat_vec(ax, S.lmat[L], m.cap_axis[j]);
+      madd3(S.capA[j], cpos, ax, -m.cap_hl[j]);
+      madd3(S.capB[j], cpos, ax, m.cap_hl[j]);
+    } else if (lane == 24 && m.has_box) {
+      float* q = S.qpos + KM_NL + 3;
+      float inv = 1.f / sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+      q[0] *= inv; q[1] *= inv; q[2] *= inv; q[3] *= inv;
+      quat_to_mat(S.bmat, q);
+    }
+  END_LANES
+  // ---- P3: composite inertias; link velocities and cdof_dot (BD.3, BD.4) ----
+  LANES(W, R)
+    if (lane < KM_NL) {
+      for (int k = 0; k < 10; ++k) { float s = 0.f; for (int b = lane; b < KM_NL; ++b) s += S.cinert[b][k]; S.crb[lane][k] = s; }
+    } else if (lane >= 8 && lane < 8 + KM_NL) {
+      const int i = lane - 8;
+      float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int b = 0; b < i; ++b) for (int k = 0; k < 6; ++k) v[k] += S.cdof[b][k] * S.qvel[b];
+      cross_motion(S.cdofdot[i], v, S.cdof[i]);
+      for (int k = 0; k < 6; ++k) S.cvel[i][k] = v[k] + S.cdof[i][k] * S.qvel[i];
+    }
+  END_LANES
+  // ---- P4: robot inertia matrix entries; per-link bias wrench (BD.3, BD.5 without gravity) ----
+  LANES(W, R)
+    if (lane < 21) {
+      int i = 0, j = lane;
+      while (j > i) { j -= i + 1; ++i; }        // lane -> (i, j), j <= i
+      float buf[6];
+      mul_inert(buf, S.crb[i], S.cdof[i]);
+      float v = dot6(S.cdof[j], buf);
+      if (i == j) v += m.l_armature[i];
+      S.M[i][j] = v; S.M[j][i] = v;
+    } else if (lane >= 24 && lane < 24 + KM_NL) {
+      const int i = lane - 24;
+      float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, f[6], t[6], t2[6];
+      for (int b = 0; b <= i; ++b) for (int k = 0; k < 6; ++k) acc[k] += S.cdofdot[b][k] * S.qvel[b];
+      mul_inert(f, S.cinert[i], acc);
+      mul_inert(t, S.cinert[i], S.cvel[i]);
+      cross_force(t2, S.cvel[i], t);
+      for (int k = 0; k < 6; ++k) S.cfrc[i][k] = f[k] + t2[k];
+    }
+  END_LANES
+  // ---- P5: qfrc_smooth ----
+  LANES(W, R)
+    if (lane < KM_NL) {
+      float f[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int b = lane; b < KM_NL; ++b) for (int k = 0; k < 6; ++k) f[k] += S.cfrc[b][k];
+      S.fs[lane] = -dot6(S.cdof[lane], f) - m.l_damping[lane] * S.qvel[lane];
+    } else if (lane < KM_NV) {
+      const int k = lane - KM_NL;
+      const float* w = S.qvel + KM_NL + 3;
+      if (k < 3) S.fs[lane] = m.fb_mass * m.grav[k] - m.fb_damping * S.qvel[lane];
+      else {
+        float Iw[3] = {m.fb_inertia[0] * w[0], m.fb_inertia[1] * w[1], m.fb_inertia[2] * w[2]}, g[3];
+        cross3(g, w, Iw);
+        S.fs[lane] = -g[k - 3] - m.fb_damping * S.qvel[lane];
+      }
+    }
+  END_LANES
+  // ---- P6: qacc_smooth = M^-1 qfrc_smooth (6x6 Cholesky, uniform; box block is diagonal) ----
+  {
+    float L[KM_NL][KM_NL], y[KM_NL], x[KM_NL];
+    USYNC();
+#pragma unroll
+    for (int i = 0; i < KM_NL; ++i) {
+#pragma unroll
+      for (int j = 0; j <= i; ++j) {
+        float s = S.M[i][j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
+        L[i][j] = (i == j) ? sqrtf(s) : s / L[j][j];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < KM_NL; ++i) { float s = S.fs[i]; for (int k = 0; k < i; ++k) s -= L[i][k] * y[k]; y[i] = s / L[i][i]; }
+#pragma unroll
+    for (int i = KM_NL - 1; i >= 0; --i) { float s = y[i]; for (int k = i + 1; k < KM_NL; ++k) s -= L[k][i] * x[k]; x[i] = s / L[i][i]; }
+    UNIFORM_WRITE(W) {
+      for (int i = 0; i < KM_NL; ++i) S.as[i] = x[i];
+      for (int k = 0; k < 3; ++k) { S.as[KM_NL + k] = S.fs[KM_NL + k] / m.fb_mass; S.as[KM_NL + 3 + k] = S.fs[KM_NL + 3 + k] / m.fb_inertia[k]; }
+    } END_UNIFORM_WRITE
+  }
+  // ---- N1: narrow phase, distances only ----
+  LANES(W, R)
+    R.nact = 0; R.actmask = 0;
+#pragma unroll
+    for (int p = 0; p < KM_NPASS; ++p) {
+      const int e = p * 32 + lane;
+      const int ty = m.rp_type[e];
+      Contact2 c; c.dist[0] = 1.f; c.dist[1] = 1.f;
+      if (ty == KP_CAP_BOX) {
+        const int a = m.rp_a[e], b = m.rp_b[e];
+        if (b < m.nsbox) capsule_box<false>(S.capA[a], S.capB[a], m.cap_r[a], m.sb_pos[b], m.sb_mat[b], m.sb_size[b], c);
+        else capsule_box<false>(S.capA[a], S.capB[a], m.cap_r[a], S.qpos + KM_NL, S.bmat, m.fb_size, c);
+      } else if (ty == KP_CAP_CAP) {
+        const int a = m.rp_a[e], b = m.rp_b[e];
+        capsule_capsule<false>(S.capA[a], S.capB[a], m.cap_r[a], S.capA[b], S.capB[b], m.cap_r[b], c);
+      } else if (ty == KP_PLANE_CAP) {
+        const int b = m.rp_b[e];
+        plane_capsule<false>(m.plane_pos, m.plane_n, S.capA[b], S.capB[b], m.cap_r[b], c);
+      }
+      R.curd[p][0] = c.dist[0]; R.curd[p][1] = c.dist[1];
+      if (ty != KP_NONE) {
+        if (c.dist[0] < 0.f) { R.nact++; R.actmask |= 1 << (2 * p); }
+        if (ty != KP_CAP_CAP && c.dist[1] < 0.f) { R.nact++; R.actmask |= 1 << (2 * p + 1); }
+      }
+    }
+    // free-box pairs: full contact generation into the staging area (rarely past the sphere test)
+    if (m.has_box && lane < m.nbpair) {
+      const int ty = m.bp_type[lane], a = m.bp_a[lane];
+      const float* bp = S.qpos + KM_NL;
+      const float rb = sqrtf(m.fb_size[0] * m.fb_size[0] + m.fb_size[1] * m.fb_size[1] + m.fb_size[2] * m.fb_size[2]);
+      int n = 0;
+      for (int k = 0; k < 4; ++k) S.bstage[lane][k][3] = 1.f;
+      if (ty == KB_PLANE_BOX) {
+        float t[3]; sub3(t, bp, m.plane_pos);
+        if (dot3(t, m.plane_n) < rb) { n = plane_box(m.plane_pos, m.plane_n, bp, S.bmat, m.fb_size, S.bstage[lane]); copy3(S.bnrm[lane], m.plane_n); }
+      } else {
+        float t[3]; sub3(t, bp, m.sb_pos[a]);
+        const float ra = sqrtf(m.sb_size[a][0] * m.sb_size[a][0] + m.sb_size[a][1] * m.sb_size[a][1] + m.sb_size[a][2] * m.sb_size[a][2]);
+        if (dot3(t, t) < (ra + rb) * (ra + rb)) {
+          if (ty == KB_BOX_BOX) n = box_box(m.sb_pos[a], m.sb_mat[a], m.sb_size[a], bp, S.bmat, m.fb_size, S.bstage[lane], S.bnrm[lane]);
+          else n = box_box(bp, S.bmat, m.fb_size, m.sb_pos[a], m.sb_mat[a], m.sb_size[a], S.bstage[lane], S.bnrm[lane]);
+        }
+      }
+      R.nact += n;
+    }
+  END_LANES
+  const int ncon_all = warp_excl_scan(W, [](int, LaneRegs& R) { return R.nact; }, [](int, LaneRegs& R, int o) { R.off = o; });
+  const int ncon = ncon_all < NCMAX ? ncon_all : NCMAX;
+  // ---- N2: full contact records for the active slots (divergent, rare) ----
+  LANES(W, R)
+    if (R.nact > 0) {
+      int o = R.off;
+      // t1 == nullptr: MJX make_frame tangents; plane-capsule supplies its own first tangent
+      auto emit = [&](const float* pos, const float* n, const float* t1, float dist, float invw, int l1, int l2) {
+        if (o < NCMAX) {
+          float* g = S.cgeo[o];
+          copy3(g, pos); copy3(g + 3, n);
+          if (t1) { copy3(g + 6, t1); cross3(g + 9, n, t1); }
+          else make_tangents(n, g + 6, g + 9);
+          g[12] = dist; g[13] = invw; g[14] = (float)l1; g[15] = (float)l2;
+        }
+        ++o;
+      };
+#pragma unroll
+      for (int p = 0; p < KM_NPASS; ++p) {
+        if (!((R.actmask >> (2 * p)) & 3)) continue;
+        const int e = p * 32 + lane, ty = m.rp_type[e], a = m.rp_a[e], b = m.rp_b[e];
+        Contact2 c;
+        float invw; int l1, l2;
+        float pt1[3]; const float* t1 = nullptr;
+        if (ty == KP_CAP_BOX) {
+          if (b < m.nsbox) { capsule_box<true>(S.capA[a], S.capB[a], m.cap_r[a], m.sb_pos[b], m.sb_mat[b], m.sb_size[b], c); invw = m.cap_invw[a]; l2 = -1; }
+          else { capsule_box<true>(S.capA[a], S.capB[a], m.cap_r[a], S.qpos + KM_NL, S.bmat, m.fb_size, c); invw = m.cap_invw[a] + m.fb_invw; l2 = KM_NL; }
+          l1 = m.cap_link[a];
+        } else if (ty == KP_CAP_CAP) {
+          capsule_capsule<true>(S.capA[a], S.capB[a], m.cap_r[a], S.capA[b], S.capB[b], m.cap_r[b], c);
+          invw = m.cap_invw[a] + m.cap_invw[b]; l1 = m.cap_link[a]; l2 = m.cap_link[b];
+        } else {
+          plane_capsule<true>(m.plane_pos, m.plane_n, S.capA[b], S.capB[b], m.cap_r[b], c);
+          invw = m.cap_invw[b]; l1 = -1; l2 = m.cap_link[b];
+          // MJX plane_capsule: first tangent = capsule axis projected on the plane
+          float ax[3];
+          sub3(ax, S.capB[b], S.capA[b]); normalize3(ax);
+          madd3(pt1, ax, m.plane_n, -dot3(m.plane_n, ax));
+          if (normalize3(pt1) < 0.5f) {
+            pt1[0] = 0.f;
+            if (m.plane_n[1] > -0.5f && m.plane_n[1] < 0.5f) { pt1[1] = 1.f; pt1[2] = 0.f; } else { pt1[1] = 0.f; pt1[2] = 1.f; }
+          }
+          t1 = pt1;
+        }
+        if ((R.actmask >> (2 * p)) & 1) emit(c.pos[0], c.nrm[0], t1, c.dist[0], invw, l1, l2);
+        if ((R.actmask >> (2 * p + 1)) & 1) emit(c.pos[1], c.nrm[1], t1, c.dist[1], invw, l1, l2);
+      }
+      if (m.has_box && lane < m.nbpair) {
+        const bool sw = m.bp_type[lane] == KB_BOX_BOX_SWAP;
+        for (int k = 0; k < 4; ++k) if (S.bstage[lane][k][3] < 0.f) emit(S.bstage[lane][k], S.bnrm[lane], nullptr, S.bstage[lane][k][3], m.fb_invw, sw ? KM_NL : -1, sw ? -1 : KM_NL);
+      }
+    }
+  END_LANES
+  // ---- C1: joint-limit rows ----
+  LANES(W, R)
+    R.nact = 0;
+    if (lane < KM_NL && m.l_limited[lane]) {
+      float q = S.qpos[lane], dlo = q - m.l_lo[lane], dhi = m.l_hi[lane] - q;
+      float pos = fminf(dlo, dhi) - m.l_margin[lane];
+      R.f0 = pos; R.f1 = dlo < dhi ? 1.f : -1.f;
+      R.nact = pos < 0.f;
+    }
+  END_LANES
+  const int nlim = warp_excl_scan(W, [](int, LaneRegs& R) { return R.nact; }, [](int, LaneRegs& R, int o) { R.off = o; });
+  UNIFORM_WRITE(W) { S.ncon = ncon; S.nlim = nlim; S.nrow = nlim + 4 * ncon; if (ncon_all > NCMAX) S.flags |= 1; } END_UNIFORM_WRITE
+  const int nrow = nlim + 4 * ncon;
+  if (nrow == 0) {
+    LANES(W, R)
+      if (lane < KM_NV) { S.qacc[lane] = S.as[lane]; S.warm[lane] = S.as[lane]; }
+    END_LANES
+    return;
+  }
+  LANES(W, R)
+    if (R.nact) {
+      const int r = R.off;
+      S.limdof[r] = lane; S.limsign[r] = R.f1;
+      float D, aref;
+      row_params(m, R.f0, m.l_invw[lane], R.f1 * S.qvel[lane], D, aref);
+      S.rD[r] = D; S.rAref[r] = aref;
+    }
+  END_LANES
+  // ---- C2: contact Jacobians in the contact frame: Jn, mu*Jt1, mu*Jt2 ----
+  LANES(W, R)
+    const int d = lane & 15;
+    if (d < KM_NV) {
+      for (int c = lane >> 4; c < ncon; c += 2) {
+        const float* g = S.cgeo[c];
+        float c1[3], c2[3], df[3];
+        jac_col(m, S, g, (int)g[14], d, c1);
+        jac_col(m, S, g, (int)g[15], d, c2);
+        sub3(df, c2, c1);
+        S.cJ[c][d] = dot3(g + 3, df);
+        S.cJ[c][12 + d] = m.mu * dot3(g + 6, df);
+        S.cJ[c][24 + d] = m.mu * dot3(g + 9, df);
+      }
+    }
+  END_LANES
+  // ---- C3: contact row parameters (4 pyramid edges share pos and D) ----
+  LANES(W, R)
+    for (int c = lane; c < ncon; c += 32) {
+      const float* g = S.cgeo[c];
+      float w = g[13];
+      w = w + m.mu * m.mu * w;
+      w = w * 2.f * m.mu * m.mu / m.impratio;
+      for (int q = 0; q < 4; ++q) {
+        const int r = nlim + 4 * c + q;
+        float vel = row_dot(S, r, S.qvel), D, aref;
+        row_params(m, g[12], w, vel, D, aref);
+        S.rD[r] = D; S.rAref[r] = aref;
+      }
+    }
+  END_LANES
+  // ---- S1: warm start vs smooth start (B.6) ----
+  LANES(W, R)
+    float cw = 0.f, cs = 0.f;
+    for (int r = lane; r < nrow; r += 32) {
+      float jw = row_dot(S, r, S.warm) - S.rAref[r], js = row_dot(S, r, S.as) - S.rAref[r];
+      S.rJaref[r] = jw; S.rJs[r] = js;
+      if (jw < 0.f) cw += 0.5f * S.rD[r] * jw * jw;
+      if (js < 0.f) cs += 0.5f * S.rD[r] * js * js;
+    }
+    R.f0 = cw; R.f1 = cs; R.f2 = 0.f;
+    if (lane < KM_NV) {
+      float ma = 0.f;
+      for (int k = 0; k < KM_NV; ++k) ma += S.M[lane][k] * S.warm[k];
+      S.Ma[lane] = ma;
+      R.f2 = 0.5f * (ma - S.fs[lane]) * (S.warm[lane] - S.as[lane]);
+    }
+  END_LANES
+  const float gauss_w = warp_sum(W, [](int, LaneRegs& R) { return R.f2; });
+  const float cost_w = warp_sum(W, [](int, LaneRegs& R) { return R.f0; }) + gauss_w;
+  const float cost_s = warp_sum(W, [](int, LaneRegs& R) { return R.f1; });
+  const bool use_warm = cost_w < cost_s;
+#ifdef CEMK_EMU_DEBUG
+  printf("[emu] nrow %d nlim %d ncon %d cost_w %.9g cost_s %.9g use_warm %d\n", nrow, nlim, ncon, cost_w, cost_s, (int)use_warm);
+#endif
+  const float gauss = use_warm ? gauss_w : 0.f;
+  LANES(W, R)
+    if (!use_warm) {
+      for (int r = lane; r < nrow; r += 32) S.rJaref[r] = S.rJs[r];
+      if (lane < KM_NV) {
+        float ma = 0.f;
+        for (int k = 0; k < KM_NV; ++k) ma += S.M[lane][k] * S.as[k];
+        S.Ma[lane] = ma;
+      }
+    }
+    if (lane < KM_NV) S.qacc[lane] = use_warm ? S.warm[lane] : S.as[lane];
+  END_LANES
+  // ---- S3: gradient and Hessian over the active rows (BD.9) ----
+  LANES(W, R)
+    if (lane < KM_NV) {
+      float fc = 0.f;
+      for (int r = 0; r < nrow; ++r) { float ja = S.rJaref[r]; if (ja < 0.f) fc += row_J(S, r, lane) * (-S.rD[r] * ja); }
+      S.grad[lane] = S.Ma[lane] - S.fs[lane] - fc;
+    }
+    for (int e = lane; e < KM_NV * (KM_NV + 1) / 2; e += 32) {
+      int i = 0, j = e;
+      while (j > i) { j -= i + 1; ++i; }
+      float h = S.M[i][j];
+      for (int r = 0; r < nlim; ++r) if (S.rJaref[r] < 0.f && S.limdof[r] == i && i == j) h += S.rD[r];
+      for (int c = 0; c < ncon; ++c) {
+        const float* J = S.cJ[c];
+        const int r0 = nlim + 4 * c;
+        float w0 = S.rJaref[r0] < 0.f ? S.rD[r0] : 0.f, w1 = S.rJaref[r0 + 1] < 0.f ? S.rD[r0 + 1] : 0.f;
+        float w2 = S.rJaref[r0 + 2] < 0.f ? S.rD[r0 + 2] : 0.f, w3 = S.rJaref[r0 + 3] < 0.f ? S.rD[r0 + 3] : 0.f;
+        float ni = J[i], nj = J[j], ai = J[12 + i], aj = J[12 + j], bi = J[24 + i], bj = J[24 + j];
+        h += w0 * (ni + ai) * (nj + aj) + w1 * (ni - ai) * (nj - aj) + w2 * (ni + bi) * (nj + bj) + w3 * (ni - bi) * (nj - bj);
+      }
+      S.H[i][j] = h;
+    }
+  END_LANES
+  // ---- S4: Cholesky of H (lower, in place), search = -H^-1 grad ----
+  for (int j = 0; j < KM_NV; ++j) {
+    USYNC();
+    const float dj = sqrtf(S.H[j][j]);
+    LANES(W, R)
+      if (lane > j && lane < KM_NV) S.H[lane][j] = S.H[lane][j] / dj;
+      if (lane == j) S.H[j][j] = dj;
+    END_LANES
+    LANES(W, R)
+      // trailing update H[i][k] -= L[i][j] L[k][j], j < k <= i
+      for (int e = lane; e < KM_NV * (KM_NV + 1) / 2; e += 32) {
+        int i = 0, k = e;
+        while (k > i) { k -= i + 1; ++i; }
+        if (k > j) S.H[i][k] -= S.H[i][j] * S.H[k][j];
+      }
+    END_LANES
+  }
+  {
+    float y[KM_NV], x[KM_NV];
+    USYNC();
+#pragma unroll
+    for (int i = 0; i < KM_NV; ++i) { float s = S.grad[i]; for (int k = 0; k < i; ++k) s -= S.H[i][k] * y[k]; y[i] = s / S.H[i][i]; }
+#pragma unroll
+    for (int i = KM_NV - 1; i >= 0; --i) { float s = y[i]; for (int k = i + 1; k < KM_NV; ++k) s -= S.H[k][i] * x[k]; x[i] = s / S.H[i][i]; }
+    UNIFORM_WRITE(W) { for (int i = 0; i < KM_NV; ++i) S.search[i] = -x[i]; } END_UNIFORM_WRITE
+  }
+  // ---- S5: line search (BD.10) ----
+  LANES(W, R)
+    R.f0 = R.f1 = R.f2 = 0.f;
+    if (lane < KM_NV) {
+      float mv = 0.f;
+      for (int k = 0; k < KM_NV; ++k) mv += S.M[lane][k] * S.search[k];
+      S.mv[lane] = mv;
+      float s = S.search[lane];
+      R.f0 = s * s; R.f1 = s * S.Ma[lane] - s * S.fs[lane]; R.f2 = 0.5f * s * mv;
+    }
+    for (int r = lane; r < nrow; r += 32) S.rJv[r] = row_dot(S, r, S.search);
+  END_LANES
+  float qg[3];
+  const float snorm = sqrtf(warp_sum(W, [](int, LaneRegs& R) { return R.f0; }));
+  qg[0] = gauss;
+  qg[1] = warp_sum(W, [](int, LaneRegs& R) { return R.f1; });
+  qg[2] = warp_sum(W, [](int, LaneRegs& R) { return R.f2; });
+  const float gtol = m.tolerance * m.ls_tolerance * snorm * m.meaninertia * (float)KM_NV;
+  LSPoint p0, lo, hi;
+  { float a0 = 0.f; ls_eval(W, S, qg, 1, &a0, &p0); }
+  { float a1 = p0.alpha - p0.d0 / p0.d1; ls_eval(W, S, qg, 1, &a1, &lo); }
+  if (lo.d0 < p0.d0) { hi = p0; } else { hi = lo; lo = p0; }
+  bool swapped = true;
+  for (int it = 0; it < m.ls_iterations; ++it) {
+    bool done = !swapped;
+    done = done || ((lo.d0 < 0.f) && (lo.d0 > -gtol));
+    done = done || ((hi.d0 > 0.f) && (hi.d0 < gtol));
+    if (done) break;
+    float al[3] = {lo.alpha - lo.d0 / lo.d1, hi.alpha - hi.d0 / hi.d1, 0.5f * (lo.alpha + hi.alpha)};
+    LSPoint pt[3];
+    ls_eval(W, S, qg, 3, al, pt);
+    const LSPoint lo_next = pt[0], hi_next = pt[1], mid = pt[2];
+    bool s1 = in_bracket(lo, lo_next); if (s1) lo = lo_next;
+    bool s2 = in_bracket(lo, mid);     if (s2) lo = mid;
+    bool s3 = in_bracket(lo, hi_next); if (s3) lo = hi_next;
+    bool s4 = in_bracket(hi, hi_next); if (s4) hi = hi_next;
+    bool s5 = in_bracket(hi, mid);     if (s5) hi = mid;
+    bool s6 = in_bracket(hi, lo_next); if (s6) hi = lo_next;
+    swapped = s1 || s2 || s3 || s4 || s5 || s6;
+#ifdef CEMK_EMU_DEBUG
+    printf("[emu]  it %d cand %.7g %.7g %.7g -> lo a %.7g d0 %.5g  hi a %.7g d0 %.5g swaps %d%d%d%d%d%d\n", it, al[0], al[1], al[2], lo.alpha, lo.d0, hi.alpha, hi.d0, s1, s2, s3, s4, s5, s6);
+#endif
+  }
+  const bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
+#ifdef CEMK_EMU_DEBUG
+  printf("[emu] p0 cost %.9g d0 %.6g d1 %.6g | lo a %.7g cost %.9g d0 %.6g | hi a %.7g cost %.9g d0 %.6g | gtol %.3g\n", p0.cost, p0.d0, p0.d1, lo.alpha, lo.cost, lo.d0, hi.alpha, hi.cost, hi.d0, gtol);
+#endif
+  const float alpha = improved ? (lo.cost < hi.cost ? lo.alpha : hi.alpha) : 0.f;
+  LANES(W, R)
+    if (lane < KM_NV) {
+      float a = S.qacc[lane] + alpha * S.search[lane];
+      S.qacc[lane] = a; S.warm[lane] = a;
+    }
+  END_LANES
+}
+
+// B.8: semi-implicit Euler with eulerdamp disabled
+KFN void step_euler(Warp& W, const KModel& m, WarpSmem& S) {
+  LANES(W, R)
+    if (lane < KM_NV) {
+      float v = S.qvel[lane] + m.dt * S.qacc[lane];
+      S.qvel[lane] = v;
+      if (lane < KM_NL + 3) S.qpos[lane] += m.dt * v;
+    }
+  END_LANES
+  LANES(W, R)
+    if (lane == 0 && m.has_box) {
+      float v[3] = {S.qvel[KM_NL + 3], S.qvel[KM_NL + 4], S.qvel[KM_NL + 5]};
+      float nrm = normalize3(v), ang = 0.5f * m.dt * nrm, sn, cs;
+      sincosf(ang, &sn, &cs);
+      float qr[4] = {cs, sn * v[0], sn * v[1], sn * v[2]}, qn[4];
+      float* q = S.qpos + KM_NL + 3;
+      quat_mul(qn, q, qr);
+      float inv = 1.f / sqrtf(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3]);
+      q[0] = qn[0] * inv; q[1] = qn[1] * inv; q[2] = qn[2] * inv; q[3] = qn[3] * inv;
+    }
+  END_LANES
+}
+
+// ------------------------------------------------------------------------------------------ rollout + cost
+struct RolloutArgs {
+  int T;
+  const float* thetadot;      // this sample's [NL][T]
+  const float* q0; const float* v0;
+  const float* target_pos; const float* target_rot;     // uniform target (compute_cem tiles it, :380-381)
+  float w_pos, w_rot, w_col;
+  float* theta;               // [NL][T] post-step joint angles
+  float* cost4;               // cost, cost_g, cost_r, cost_c
+  float* eef_pos; float* eef_rot; float* collision;     // optional per-step dumps [T][3], [T][4], [T][nslot]
+  float* qacc_dbg;            // optional [T][12]
+  int* flags;
+};
+
+KFN void rollout_sample(Warp& W, const KModel& m, WarpSmem& S, const RolloutArgs& A) {
+  LANES(W, R)
+    if (lane < KM_NQ) S.qpos[lane] = lane < KM_NL ? A.q0[lane] : m.qpos0[lane];
+    if (lane < KM_NV) { S.qvel[lane] = lane < KM_NL ? A.v0[lane] : m.qvel0[lane]; S.warm[lane] = m.warm0[lane]; }
+    for (int e = lane; e < KM_NV * KM_NV; e += 32) {
+      int i = e / KM_NV, j = e % KM_NV;
+      float v = 0.f;
+      if (i == j && i >= KM_NL) v = (i < KM_NL + 3) ? m.fb_mass : m.fb_inertia[i - KM_NL - 3];
+      S.M[i][j] = v;
+    }
+    if (lane == 0) S.flags = 0;
+    R.cost_c = 0.f;
+  END_LANES
+  float tq[4] = {A.target_rot[0], A.target_rot[1], A.target_rot[2], A.target_rot[3]};
+  {
+    float inv = 1.f / sqrtf(tq[0] * tq[0] + tq[1] * tq[1] + tq[2] * tq[2] + tq[3] * tq[3]);
+    tq[0] *= inv; tq[1] *= inv; tq[2] *= inv; tq[3] *= inv;
+  }
+  float cost_g = 0.f, cost_r = 0.f;
+  for (int t = 0; t < A.T; ++t) {
+    LANES(W, R)
+      if (lane < KM_NL) S.qvel[lane] = A.thetadot[lane * A.T + t];       // mjx_planner.py:254
+    END_LANES
+    step_forward(W, m, S);
+    // pre-step observations (mjx_planner.py:259-261) and running cost (:277-296)
+    {
+      float tcp[3], tv[3], eq[4];
+      USYNC();
+      mat_vec(tv, S.lmat[KM_NL - 1], m.tcp_pos); add3(tcp, S.lpos[KM_NL - 1], tv);
+      quat_mul(eq, S.lquat[KM_NL - 1], m.hande_quat);
+      float d[3]; sub3(d, tcp, A.target_pos);
+      cost_g += sqrtf(dot3(d, d));
+      float inv = 1.f / sqrtf(eq[0] * eq[0] + eq[1] * eq[1] + eq[2] * eq[2] + eq[3] * eq[3]);
+      float dp = fabsf((eq[0] * tq[0] + eq[1] * tq[1] + eq[2] * tq[2] + eq[3] * tq[3]) * inv);
+      dp = fminf(fmaxf(dp, -1.f), 1.f);
+      cost_r += 2.f * acosf(dp);
+      LANES(W, R)
+        if (A.eef_pos && lane < 3) A.eef_pos[t * 3 + lane] = tcp[lane];
+        if (A.eef_rot && lane < 4) A.eef_rot[t * 4 + lane] = eq[lane];
+        if (A.qacc_dbg && lane < KM_NV) A.qacc_dbg[t * KM_NV + lane] = S.qacc[lane];
+#pragma unroll
+        for (int p = 0; p < KM_NPASS; ++p) {
+          const int e = p * 32 + lane, ty = m.rp_type[e];
+          if (ty == KP_NONE) continue;
+          const int ns = ty == KP_CAP_CAP ? 1 : 2;
+          for (int k = 0; k < ns; ++k) {
+            float c = R.curd[p][k];
+            if (c < 0.f) R.cost_c += 1.f;
+            if (t > 0) R.cost_c += fmaxf((1.f - 0.005f) * R.prevd[p][k] - c, 0.f);
+            R.prevd[p][k] = c;
+            if (A.collision) A.collision[(size_t)t * m.nslot_robot + m.rp_slot[e] + k] = c;
+          }
+        }
+      END_LANES
+    }
+    step_euler(W, m, S);
+    LANES(W, R)
+      if (lane < KM_NL) A.theta[lane * A.T + t] = S.qpos[lane];
+    END_LANES
+  }
+  const float cost_c = warp_sum(W, [](int, LaneRegs& R) { return R.cost_c; });
+  LANES(W, R)
+    if (lane == 0) {
+      A.cost4[0] = A.w_pos * cost_g + A.w_rot * cost_r + A.w_col * cost_c;
+      A.cost4[1] = cost_g; A.cost4[2] = cost_r; A.cost4[3] = cost_c;
+      if (A.flags) *A.flags = S.flags;
+    }
+  END_LANES
+}

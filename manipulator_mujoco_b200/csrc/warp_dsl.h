@@ -1,0 +1,78 @@
+// warp_dsl.h -- a tiny "one warp = one sample" programming layer.
+//
+// The rollout core (rollout_core.h) is written once against these macros and compiled twice:
+//   * by nvcc for sm_100a, where a LANES block is the body executed by each of the 32 lanes of the
+//     warp that owns the sample, per-lane state lives in registers, collectives are warp shuffles
+//     and every block is fenced by __syncwarp();
+//   * by g++ with -DCEMK_EMU (tests/emu, no-GPU unit tests only), where a LANES block is a plain
+//     `for (lane = 0..31)` loop over an array of per-lane register structs.  This is a debugging
+//     aid for kernel logic in a container without a GPU; it is never used by the product path.
+//
+// Rules the core follows so both builds mean the same thing:
+//   1. inside one LANES block a lane reads only shared scratch written in *earlier* blocks (or by
+//      itself) and writes only locations no other lane touches in that block;
+//   2. code outside LANES blocks is warp-uniform (every lane computes the same scalars); shared
+//      scratch is written there only through UNIFORM_WRITE, which is fenced on both sides.
+#pragma once
+#include <math.h>
+
+#ifdef CEMK_EMU
+#include <cstring>
+#define KFN static inline
+#define LANES(W, R) for (int lane = 0; lane < 32; ++lane) { auto& R = (W).regs[lane]; (void)R;
+#define END_LANES }
+#define UNIFORM_WRITE(W) if (true)
+#define END_UNIFORM_WRITE
+#define USYNC()
+#define KRSQRT(x) (1.0f / sqrtf(x))
+#else
+#define KFN __device__ __forceinline__
+#define LANES(W, R) { __syncwarp(); const int lane = (W).lane; auto& R = (W).regs; (void)R;
+#define END_LANES } __syncwarp();
+#define UNIFORM_WRITE(W) __syncwarp(); if ((W).lane == 0)
+#define END_UNIFORM_WRITE __syncwarp();
+#define USYNC() __syncwarp()
+#define KRSQRT(x) rsqrtf(x)
+#endif
+
+template <class LR>
+struct WarpCtx {
+#ifdef CEMK_EMU
+  LR regs[32];
+#else
+  LR regs;
+  int lane;
+#endif
+};
+
+// sum over lanes of f(lane, regs); result is warp-uniform
+template <class W, class F>
+KFN float warp_sum(W& w, F f) {
+#ifdef CEMK_EMU
+  float s = 0.f;
+  for (int l = 0; l < 32; ++l) s += f(l, w.regs[l]);
+  return s;
+#else
+  float v = f(w.lane, w.regs);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+#endif
+}
+
+// exclusive prefix sum of small non-negative ints; set(lane, regs, offset) receives each lane's
+// offset; returns the warp total
+template <class W, class G, class S>
+KFN int warp_excl_scan(W& w, G get, S set) {
+#ifdef CEMK_EMU
+  int run = 0;
+  for (int l = 0; l < 32; ++l) { int v = get(l, w.regs[l]); set(l, w.regs[l], run); run += v; }
+  return run;
+#else
+  int v = get(w.lane, w.regs), inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (w.lane >= o) inc += t; }
+  set(w.lane, w.regs, inc - v);
+  return __shfl_sync(0xffffffffu, inc, 31);
+#endif
+}

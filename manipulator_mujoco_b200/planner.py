@@ -1,0 +1,523 @@
+"""Drop-in ``cem_planner`` for the UR5e + Hand-E scene, backed by libcemk.so (sm_100a CUDA).
+
+Mirrors the public surface of the reference class (``sampling_based_planner/mjx_planner.py:17-406``):
+same constructor keywords, same attribute names read by ``mpc_planner.py`` (``nvar``, ``model``,
+``data``, ``tcp_id``, ``hande_id``) and the notebooks, the same per-iteration methods with the
+same argument order and shapes, and ``compute_cem`` returning the same 9-tuple.  JAX arrays become
+torch CUDA tensors; the small results of ``compute_cem`` come back as numpy arrays because the
+caller feeds them straight to ``np.mean`` / ``np.round`` (``mpc_planner.py:178,185``).
+
+There is no CPU path: constructing the planner without a CUDA device or without libcemk.so raises.
+
+Reference quirks kept on purpose: elites are taken from the *unprojected*
+samples (:357); the PRNG key never advances across ``compute_cem`` calls (:80,:388) so the same
+standard-normal draws are reused every tick; the covariance restarts at 10*I every call (:386);
+``theta`` is the post-step joint angle while ``eef_pos`` / ``eef_rot`` / ``collision`` are pre-step.
+``jax.random`` is replaced by a counter-keyed torch generator (JAX's threefry stream cannot be
+reproduced here; parity tests inject samples instead).
+
+Multi-GPU (extension): pass ``process_group``; ``num_batch`` is then the global
+batch, each rank rolls out ``num_batch / world`` samples, keeps its local top-k and one NCCL
+all-gather merges the elite lists so every rank computes the identical mean / covariance.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from .bernstein import bernstein_coeff_ordern_new
+from .kmodel import KModel, build_kmodel
+from .mjcf import ModelConsts, host_kinematics, load_model
+
+_VP = C.c_void_p
+
+
+def _ptr(t):
+    return None if t is None else _VP(t.data_ptr())
+
+
+class _Named:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+class _ModelView:
+    """Stand-in for the ``mujoco.MjModel`` attributes the callers touch (mpc_planner.py:109-124,231)."""
+
+    def __init__(self, mc: ModelConsts, timestep):
+        self._mc = mc
+        self.opt = _Named(timestep=timestep)
+        self.nq, self.nv, self.nbody, self.ngeom = mc.nq, mc.nv, mc.nbody, mc.ngeom
+        self._body_pos = mc.body_pos.copy()
+        self._body_quat = mc.body_quat.copy()
+
+    def body(self, name=None):
+        i = self._mc.body_id(name)
+        return _Named(id=i, name=name, pos=self._body_pos[i], quat=self._body_quat[i])
+
+    def site(self, name=None):
+        return _Named(id=self._mc.site_id(name), name=name)
+
+    def geom(self, name=None):
+        return _Named(id=self._mc.geom_id(name), name=name)
+
+
+class _DataView:
+    """Stand-in for ``mujoco.MjData``: qpos/qvel/qacc plus kinematics refreshed by ``forward()``."""
+
+    def __init__(self, mc: ModelConsts):
+        self._mc = mc
+        self.qpos = mc.qpos0.copy()
+        self.qvel = np.zeros(mc.nv)
+        self.qacc = np.zeros(mc.nv)
+        self.forward()
+
+    def forward(self):
+        xpos, xquat, xmat = host_kinematics(self._mc, self.qpos)
+        self.xpos, self.xquat, self.xmat = xpos, xquat, xmat
+        sb = self._mc.site_body
+        self.site_xpos = np.array([xpos[b] + xmat[b] @ p for b, p in zip(sb, self._mc.site_pos)])
+
+
+class cem_planner:
+
+    def __init__(self, num_dof=None, num_batch=None, num_steps=None, timestep=None, maxiter_cem=None, num_elite=None,
+                 w_pos=None, w_rot=None, w_col=None, maxiter_projection=None, *, model_path=None, device=None,
+                 process_group=None, seed=0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("cem_planner needs a CUDA device (B200 / sm_100a); there is no CPU fallback")
+        self._lib = _lib.load()
+        if num_dof != 6:
+            raise NotImplementedError("the rollout kernel is built for the 6-DOF UR5e chain (num_dof=6)")
+        self.num_dof = num_dof
+        self.num_batch = num_batch
+        self.t = timestep
+        self.num = num_steps
+        self.num_elite = num_elite
+        self.cost_weights = {'w_pos': w_pos, 'w_rot': w_rot, 'w_col': w_col}
+        self.maxiter_projection = maxiter_projection
+        self.maxiter_cem = maxiter_cem
+
+        # ---- distributed layout: samples are sharded contiguously by rank ----
+        self.process_group = process_group
+        if process_group is not None:
+            import torch.distributed as dist
+            self._dist = dist
+            self.world = dist.get_world_size(process_group)
+            self.rank = dist.get_rank(process_group)
+        else:
+            self._dist, self.world, self.rank = None, 1, 0
+        if num_batch % self.world:
+            raise ValueError("num_batch must be divisible by the number of ranks")
+        self.num_batch_local = num_batch // self.world
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        dev = self.device
+
+        # ---- basis and constraint matrices (mjx_planner.py:34-76) ----
+        self.t_fin = self.num * self.t
+        tot_time = np.linspace(0, self.t_fin, self.num)
+        self.tot_time = tot_time
+        tc = tot_time.reshape(self.num, 1)
+        self.P, self.Pdot, self.Pddot = bernstein_coeff_ordern_new(10, tc[0], tc[-1], tc)
+        f32 = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32, device=dev)
+        self.P_jax, self.Pdot_jax, self.Pddot_jax = f32(self.P), f32(self.Pdot), f32(self.Pddot)
+        self.nvar_single = self.P.shape[1]
+        self.nvar = self.nvar_single * self.num_dof
+        self.A_projection = torch.eye(self.nvar, device=dev)
+        self.rho_ineq = 1.0
+        self.rho_projection = 1.0
+        A_v_ineq, A_v = self.get_A_v()
+        A_a_ineq, A_a = self.get_A_a()
+        A_p_ineq, A_p = self.get_A_p()
+        A_eq = self.get_A_eq()
+        self._np = dict(A_v_ineq=A_v_ineq, A_a_ineq=A_a_ineq, A_p_ineq=A_p_ineq)
+        Q_inv = self.get_Q_inv(A_eq)
+        A_theta, A_thetadot, A_thetaddot = self.get_A_traj()
+        self.A_v_ineq, self.A_v = f32(A_v_ineq), f32(A_v)
+        self.A_a_ineq, self.A_a = f32(A_a_ineq), f32(A_a)
+        self.A_p_ineq, self.A_p = f32(A_p_ineq), f32(A_p)
+        self.A_eq, self.Q_inv = f32(A_eq), f32(Q_inv)
+        self.A_theta, self.A_thetadot, self.A_thetaddot = f32(A_theta), f32(A_thetadot), f32(A_thetaddot)
+
+        self.key = 0                       # counter-based stand-in for jax.random.PRNGKey(0) (:80)
+        self._seed = int(seed)
+        self.v_max = 0.8
+        self.a_max = 1.8
+        self.p_max = 180 * np.pi / 180
+        self.l_1 = self.l_2 = self.l_3 = 1.0
+        self.ellite_num = int(self.num_elite * self.num_batch)
+        self.alpha_mean = 0.6
+        self.alpha_cov = 0.6
+        self.lamda = 10
+        self.g = 10
+
+        # ---- model (mjx_planner.py:100-121) ----
+        self.model_path = model_path if model_path is not None else "<packaged ur5e_hande_mjx/scene.xml constants>"
+        self._mc = load_model(model_path)
+        self.model = _ModelView(self._mc, self.t)
+        self.data = _DataView(self._mc)
+        km, info = build_kmodel(self._mc, self.t)
+        self.mjx_model = km
+        self.geom_ids = np.array([self._mc.geom_id(f'robot_{i}') for i in range(10)])
+        mask = np.zeros(self._mc.ncon, dtype=bool)
+        for (g1, g2), a, n in zip(self._mc.pair_geom, self._mc.pair_slotadr, self._mc.pair_nslot):
+            if g1 in self.geom_ids or g2 in self.geom_ids:
+                mask[a:a + n] = True
+        self.mask = torch.as_tensor(mask, device=dev)
+        self.nslot = int(mask.sum())
+        self.hande_id = self.model.body(name="hande").id
+        self.tcp_id = self.model.site(name="tcp").id
+
+        h = _VP()
+        _lib.check(self._lib.cemk_create(C.byref(km), C.sizeof(km), dev.index or 0, C.byref(h)), self._lib)
+        self._h = h
+        self._set_horizon(Q_inv)
+        # mjx.forward at qpos0 (:107): its qacc becomes the first warm start of every rollout
+        self.mjx_data = self._initial_forward()
+
+        self._z_cache = {}
+        self._ws = {}
+        self.print_info()
+
+    # ------------------------------------------------------------------ constants (mjx_planner.py:142-172)
+    def get_A_traj(self):
+        I = np.identity(self.num_dof)
+        return np.kron(I, self.P), np.kron(I, self.Pdot), np.kron(I, self.Pddot)
+
+    def get_A_p(self):
+        A_p = np.vstack((self.P, -self.P))
+        return np.kron(np.identity(self.num_dof), A_p), A_p
+
+    def get_A_v(self):
+        A_v = np.vstack((self.Pdot, -self.Pdot))
+        return np.kron(np.identity(self.num_dof), A_v), A_v
+
+    def get_A_a(self):
+        A_a = np.vstack((self.Pddot, -self.Pddot))
+        return np.kron(np.identity(self.num_dof), A_a), A_a
+
+    def get_A_eq(self):
+        return np.kron(np.identity(self.num_dof),
+                       np.vstack((self.P[0], self.Pdot[0], self.Pddot[0], self.Pdot[-1], self.Pddot[-1])))
+
+    def get_Q_inv(self, A_eq):
+        # the reference forms the cost block from float32 arrays and inverts the KKT matrix in float64
+        r = lambda a: a.astype(np.float32).astype(np.float64)
+        Av, Aa, Ap = r(self._np["A_v_ineq"]), r(self._np["A_a_ineq"]), r(self._np["A_p_ineq"])
+        Q = (np.identity(self.nvar) + self.rho_ineq * Av.T @ Av + self.rho_ineq * Aa.T @ Aa
+             + self.rho_ineq * Ap.T @ Ap).astype(np.float32).astype(np.float64)
+        ne = A_eq.shape[0]
+        return np.linalg.inv(np.vstack((np.hstack((Q, A_eq.T)), np.hstack((A_eq, np.zeros((ne, ne)))))))
+
+    def _set_horizon(self, Q_inv):
+        """Per-DOF blocks of Q_inv (block diagonal: every DOF solves the same 11-variable problem)."""
+        n1, nd, nv = self.nvar_single, self.num_dof, self.nvar
+        Kpp = Q_inv[:n1, :n1]
+        Kpe = Q_inv[:n1, nv:nv + 5]
+        # verify the structure the kernel relies on
+        scale = np.abs(Q_inv).max()
+        for d in range(nd):
+            blk = Q_inv[d * n1:(d + 1) * n1]
+            if (np.abs(blk[:, d * n1:(d + 1) * n1] - Kpp).max() > 1e-6 * scale
+                    or np.abs(blk[:, nv + 5 * d:nv + 5 * d + 5] - Kpe).max() > 1e-6 * scale):
+                raise RuntimeError("Q_inv is not block diagonal per DOF")
+        off = Q_inv[:n1, n1:nv]
+        if np.abs(off).max() > 1e-6 * scale:
+            raise RuntimeError("Q_inv couples different DOFs")
+        G = np.stack((self.Pdot, self.Pddot, self.P)).astype(np.float32)
+        Gd = G.astype(np.float64)
+        N = sum(Gd[c].T @ Gd[c] for c in range(3))
+        c32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+        G, Kpp, Kpe, N = c32(G), c32(Kpp), c32(Kpe), c32(N)
+        bnd = c32([self.v_max, self.a_max, self.p_max])
+        hp = lambda a: a.ctypes.data_as(_VP)
+        _lib.check(self._lib.cemk_set_horizon(self._h, self.num, hp(G), hp(Kpp), hp(Kpe), hp(N), hp(bnd)), self._lib)
+
+    def _initial_forward(self):
+        """One forward at qpos0 with zero velocity: qacc -> KModel.warm0 (mjx_planner.py:107)."""
+        dev = self.device
+        z6 = torch.zeros(6, device=dev)
+        q0 = torch.as_tensor(self._mc.qpos0[:6], dtype=torch.float32, device=dev)
+        td = torch.zeros(1, 6, device=dev)
+        theta = torch.empty(1, 6, device=dev)
+        cost4 = torch.empty(1, 4, device=dev)
+        qacc = torch.empty(1, 1, 12, device=dev)
+        tp = torch.zeros(3, device=dev)
+        tr = torch.tensor([1.0, 0, 0, 0], device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(self._lib.cemk_rollout_cost(self._h, 1, 1, _ptr(td), _ptr(q0), _ptr(z6), _ptr(tp), _ptr(tr), 0.0, 0.0, 0.0,
+                                               _ptr(theta), _ptr(cost4), None, None, None, _ptr(qacc), None, _VP(st)), self._lib)
+        warm = qacc[0, 0].cpu().numpy()
+        for i in range(12):
+            self.mjx_model.warm0[i] = float(warm[i])
+        _lib.check(self._lib.cemk_set_model(self._h, C.byref(self.mjx_model), C.sizeof(self.mjx_model)), self._lib)
+        return dict(qpos=self._mc.qpos0.copy(), qvel=np.zeros(12), qacc=warm.copy(), qacc_warmstart=warm.copy())
+
+    def print_info(self):
+        if self.rank == 0:
+            print(
+                f'\n Default backend: cuda ({torch.cuda.get_device_name(self.device)})'
+                f'\n Model path: {self.model_path}',
+                f'\n Timestep: {self.t}',
+                f'\n CEM Iter: {self.maxiter_cem}',
+                f'\n Number of batches: {self.num_batch}',
+                f'\n Number of steps per trajectory: {self.num}',
+                f'\n Time per trajectory: {self.t_fin}',
+            )
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.cemk_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _t(self, a, shape=None):
+        t = torch.as_tensor(np.asarray(a) if not torch.is_tensor(a) else a, dtype=torch.float32, device=self.device)
+        t = t.contiguous()
+        return t if shape is None else t.reshape(shape)
+
+    def _stream(self):
+        return _VP(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _buf(self, name, shape, dtype=torch.float32):
+        key = (name, tuple(shape), dtype)
+        b = self._ws.get(key)
+        if b is None:
+            b = torch.empty(shape, dtype=dtype, device=self.device)
+            self._ws[key] = b
+        return b
+
+    def _normal(self, key):
+        """Standard normal draws for PRNG counter ``key``: rows [rank*Bl, (rank+1)*Bl) of a [B, nvar]
+        table that depends only on (seed, key), so results do not depend on the number of GPUs."""
+        z = self._z_cache.get(key)
+        if z is None:
+            g = torch.Generator(device=self.device)
+            g.manual_seed((self._seed * 1000003 + int(key)) & 0x7FFFFFFFFFFFFFFF)
+            full = torch.randn(self.num_batch, self.nvar, generator=g, device=self.device, dtype=torch.float32)
+            lo = self.rank * self.num_batch_local
+            z = full[lo:lo + self.num_batch_local].contiguous()
+            self._z_cache[key] = z
+        return z
+
+    # ------------------------------------------------------------------ per-iteration methods
+    def compute_boundary_vec_single(self, state_term):
+        st = self._t(state_term)
+        return st.reshape(5, self.num_dof).T.reshape(self.num_dof * 5)
+
+    def compute_boundary_vec_batch(self, state_term):
+        st = self._t(state_term)
+        return st.reshape(-1, 5, self.num_dof).transpose(1, 2).reshape(-1, self.num_dof * 5)
+
+    def compute_xi_samples(self, key, xi_mean, xi_cov):
+        """mjx_planner.py:313-316.  ``key`` is the integer PRNG counter; returns (xi_samples, new key)."""
+        key = int(key) + 1                                   # key, subkey = split(key); sample with key
+        z = self._normal(key)
+        B = z.shape[0]
+        xi = torch.empty(B, self.nvar, device=self.device)
+        ws = self._buf("chol", (self.nvar * self.nvar,))
+        _lib.check(self._lib.cemk_sample(self._h, B, _ptr(z), _ptr(self._t(xi_mean)), _ptr(self._t(xi_cov)), _ptr(ws),
+                                         _ptr(xi), self._stream()), self._lib)
+        return xi, key
+
+    def _project(self, xi_samples, state_term, want_thetadot):
+        xi = self._t(xi_samples)
+        st = self._t(state_term)
+        B = xi.shape[0]
+        xi_f = torch.empty(B, self.nvar, device=self.device)
+        thetadot = torch.empty(B, self.num_dof * self.num, device=self.device) if want_thetadot else None
+        _lib.check(self._lib.cemk_project(self._h, B, int(self.maxiter_projection), _ptr(xi), _ptr(st), _ptr(xi_f),
+                                          _ptr(thetadot), self._stream()), self._lib)
+        return xi_f, thetadot
+
+    def compute_projection_filter(self, xi_samples, state_term):
+        """mjx_planner.py:234-249 -> primal_sol [B, nvar]."""
+        return self._project(xi_samples, state_term, False)[0]
+
+    def _rollout(self, thetadot, init_pos, init_vel, target_pos, target_rot, dumps):
+        td = self._t(thetadot)
+        B, T = td.shape[0], self.num
+        dev = self.device
+        theta = torch.empty(B, self.num_dof * T, device=dev)
+        cost4 = torch.empty(B, 4, device=dev)
+        eef_pos = torch.empty(B, T, 3, device=dev) if dumps else None
+        eef_rot = torch.empty(B, T, 4, device=dev) if dumps else None
+        collision = torch.empty(B, T, self.nslot, device=dev) if dumps else None
+        flags = self._buf("flags", (B,), torch.int32)
+        w = self.cost_weights
+        _lib.check(self._lib.cemk_rollout_cost(
+            self._h, B, T, _ptr(td), _ptr(self._t(init_pos)), _ptr(self._t(init_vel)), _ptr(self._t(target_pos)),
+            _ptr(self._t(target_rot)), float(w['w_pos']), float(w['w_rot']), float(w['w_col']), _ptr(theta), _ptr(cost4),
+            _ptr(eef_pos), _ptr(eef_rot), _ptr(collision), None, _ptr(flags), self._stream()), self._lib)
+        return theta, cost4, eef_pos, eef_rot, collision
+
+    def compute_rollout_batch(self, thetadot, init_pos, init_vel):
+        """mjx_planner.py:123,266-274 -> theta [B,6T], eef_pos [B,T,3], eef_rot [B,T,4], collision [B,T,187]."""
+        tp = torch.zeros(3, device=self.device)
+        tr = torch.tensor([1.0, 0, 0, 0], device=self.device)
+        theta, _c, eef_pos, eef_rot, collision = self._rollout(thetadot, init_pos, init_vel, tp, tr, True)
+        return theta, eef_pos, eef_rot, collision
+
+    def compute_cost_batch(self, thetadot, eef_pos, eef_rot, collision, target_pos, target_rot):
+        """mjx_planner.py:124,277-303 (thetadot is unused there too) -> cost, cost_g, cost_r, cost_c [B]."""
+        ep, er, col = self._t(eef_pos), self._t(eef_rot), self._t(collision)
+        B, T, ns = col.shape
+        tp, tr = self._t(target_pos).reshape(-1, 3), self._t(target_rot).reshape(-1, 4)
+        if tp.shape[0] == 1:
+            tp, tr = tp.expand(B, 3).contiguous(), tr.expand(B, 4).contiguous()
+        cost4 = torch.empty(B, 4, device=self.device)
+        w = self.cost_weights
+        _lib.check(self._lib.cemk_cost_batch(self._h, B, T, ns, _ptr(ep), _ptr(er), _ptr(col), _ptr(tp), _ptr(tr),
+                                             float(w['w_pos']), float(w['w_rot']), float(w['w_col']), _ptr(cost4),
+                                             self._stream()), self._lib)
+        return cost4[:, 0], cost4[:, 1], cost4[:, 2], cost4[:, 3]
+
+    def _argsort_topk(self, cost, stride, n, k, xi, idx_base=0, want_idx=True):
+        np2 = 1 << max(0, (n - 1).bit_length())
+        keys = self._buf("keys", (np2,), torch.int64)
+        idx = torch.empty(n, dtype=torch.int32, device=self.device) if want_idx else None
+        xi_e = torch.empty(k, self.nvar, device=self.device)
+        cost_e = torch.empty(k, device=self.device)
+        _lib.check(self._lib.cemk_argsort_topk(self._h, n, _ptr(cost), stride, idx_base, _ptr(keys), _ptr(idx), k, _ptr(xi),
+                                               _ptr(xi_e), _ptr(cost_e), self._stream()), self._lib)
+        return xi_e, idx, cost_e
+
+    def compute_ellite_samples(self, cost_batch, xi_filtered):
+        """mjx_planner.py:306-310 -> xi_ellite [k,nvar], idx_ellite [B] (stable argsort), cost_ellite [k]."""
+        cost = self._t(cost_batch)
+        xi = self._t(xi_filtered)
+        n = cost.shape[0]
+        k = min(self.ellite_num, n)
+        return self._argsort_topk(cost, 1, n, k, xi)
+
+    def comp_prod(self, diffs, d):
+        diffs = self._t(diffs)
+        return d * torch.outer(diffs, diffs)
+
+    def compute_mean_cov(self, cost_ellite, mean_control_prev, cov_control_prev, xi_ellite):
+        """mjx_planner.py:326-335."""
+        ce, xe = self._t(cost_ellite), self._t(xi_ellite)
+        mean = torch.empty(self.nvar, device=self.device)
+        cov = torch.empty(self.nvar, self.nvar, device=self.device)
+        _lib.check(self._lib.cemk_mean_cov(self._h, ce.shape[0], _ptr(ce), _ptr(xe), _ptr(self._t(mean_control_prev)),
+                                           _ptr(self._t(cov_control_prev)), float(self.lamda), float(self.alpha_mean),
+                                           float(self.alpha_cov), _ptr(mean), _ptr(cov), self._stream()), self._lib)
+        return mean, cov
+
+    # ------------------------------------------------------------------ elite selection across GPUs
+    def _select_elites(self, cost4, xi_samples):
+        """Local top-k, then (multi-GPU) one all-gather + merge.  Returns xi_e [k,nvar], cost_e [k], gidx_e [k]|None."""
+        Bl = self.num_batch_local
+        k = self.ellite_num
+        kl = min(k, Bl)
+        base = self.rank * Bl
+        xi_e, idx, cost_e = self._argsort_topk(cost4, 4, Bl, kl, xi_samples, idx_base=base)
+        if self.world == 1:
+            return xi_e, cost_e, idx[:kl]
+        dist = self._dist
+        pack = torch.empty(kl, self.nvar + 2, device=self.device)
+        pack[:, :self.nvar] = xi_e
+        pack[:, self.nvar] = cost_e
+        pack[:, self.nvar + 1] = idx[:kl].to(torch.float32)      # global index < 2^24: exact in float32
+        gathered = torch.empty(self.world * kl, self.nvar + 2, device=self.device)
+        dist.all_gather_into_tensor(gathered, pack, group=self.process_group)
+        n = self.world * kl
+        g_cost = gathered[:, self.nvar].contiguous()
+        g_idx = gathered[:, self.nvar + 1].to(torch.int32).contiguous()
+        g_xi = gathered[:, :self.nvar].contiguous()
+        np2 = 1 << max(0, (n - 1).bit_length())
+        keys = self._buf("keys_merge", (np2,), torch.int64)
+        xi_m = torch.empty(k, self.nvar, device=self.device)
+        cost_m = torch.empty(k, device=self.device)
+        gidx_m = torch.empty(k, dtype=torch.int32, device=self.device)
+        _lib.check(self._lib.cemk_merge_elites(self._h, n, _ptr(g_cost), _ptr(g_idx), _ptr(g_xi), _ptr(keys), k, _ptr(xi_m),
+                                               _ptr(cost_m), _ptr(gidx_m), self._stream()), self._lib)
+        return xi_m, cost_m, gidx_m
+
+    # ------------------------------------------------------------------ cem_iter / compute_cem (mjx_planner.py:337-406)
+    def cem_iter(self, carry, _):
+        init_pos, init_vel, target_pos, target_rot, xi_mean, xi_cov, key, state_term = carry
+        xi_mean_prev, xi_cov_prev = xi_mean, xi_cov
+        xi_samples, key = self.compute_xi_samples(key, xi_mean, xi_cov)
+        xi_filtered, thetadot = self._project(xi_samples, state_term, True)
+        tp = self._t(target_pos).reshape(-1, 3)[0]
+        tr = self._t(target_rot).reshape(-1, 4)[0]
+        theta, cost4, _, _, _ = self._rollout(thetadot, init_pos, init_vel, tp, tr, False)
+        xi_ellite, cost_ellite, gidx = self._select_elites(cost4, xi_samples)
+        xi_mean, xi_cov = self.compute_mean_cov(cost_ellite, xi_mean_prev, xi_cov_prev, xi_ellite)
+        self._last_elite = (cost_ellite, gidx)
+        carry = (init_pos, init_vel, target_pos, target_rot, xi_mean, xi_cov, key, state_term)
+        return carry, (cost4[:, 0], cost4[:, 1], cost4[:, 2], cost4[:, 3], thetadot, theta)
+
+    def compute_cem(self, xi_mean, init_pos=np.array([1.5, -1.8, 1.75, -1.25, -1.6, 0]), init_vel=np.zeros(6),
+                    init_acc=np.zeros(6), target_pos=np.zeros(3), target_rot=np.zeros(4)):
+        dev = self.device
+        Bl, T, nd = self.num_batch_local, self.num, self.num_dof
+        # one packed host->device copy for the per-tick inputs
+        host = np.concatenate([np.asarray(xi_mean.detach().cpu() if torch.is_tensor(xi_mean) else xi_mean, dtype=np.float32).reshape(-1),
+                               np.asarray(init_pos, dtype=np.float32).reshape(-1), np.asarray(init_vel, dtype=np.float32).reshape(-1),
+                               np.asarray(init_acc, dtype=np.float32).reshape(-1), np.asarray(target_pos, dtype=np.float32).reshape(-1),
+                               np.asarray(target_rot, dtype=np.float32).reshape(-1)])
+        pin = self._ws.get("pin_in")
+        if pin is None:
+            pin = torch.empty(host.size, dtype=torch.float32).pin_memory()
+            self._ws["pin_in"] = pin
+        pin.copy_(torch.from_numpy(host))
+        d_in = self._buf("d_in", (host.size,))
+        d_in.copy_(pin, non_blocking=True)
+        nv = self.nvar
+        xi_mean_d = d_in[:nv]
+        q0, v0, a0 = d_in[nv:nv + 6], d_in[nv + 6:nv + 12], d_in[nv + 12:nv + 18]
+        tp, tr = d_in[nv + 18:nv + 21], d_in[nv + 21:nv + 25]
+        z6 = torch.zeros(6, device=dev)
+        state_row = torch.cat([q0, v0, a0, z6, z6])
+        state_term = state_row.unsqueeze(0).expand(Bl, 30).contiguous()                    # :374-384
+        xi_cov = 10 * torch.eye(nv, device=dev)                                            # :386
+        key = self.key + 1                                                                 # :388
+        carry = (q0, v0, tp, tr, xi_mean_d, xi_cov, key, state_term)
+        thetadot_all = torch.empty(self.maxiter_cem, Bl, nd * T, device=dev)
+        theta_all = torch.empty(self.maxiter_cem, Bl, nd * T, device=dev)
+        cost_min = torch.empty(self.maxiter_cem, device=dev)
+        last = None
+        for i in range(self.maxiter_cem):                                                  # :390-392
+            carry, out = self.cem_iter(carry, None)
+            thetadot_all[i].copy_(out[4])
+            theta_all[i].copy_(out[5])
+            cost_min[i] = self._last_elite[0][0]                                           # min over the (global) batch
+            last = out
+        # :395-402  best sample of the last iteration = head of the (merged) sorted list
+        gbest = self._last_elite[1][0:1].to(torch.int64)
+        lo = self.rank * Bl
+        if self.world == 1:
+            li = gbest
+            best = torch.cat([last[4][li].reshape(-1), last[5][li].reshape(-1), last[1][li], last[2][li], last[3][li]])
+        else:
+            li = (gbest - lo).clamp(0, Bl - 1)
+            own = ((gbest >= lo) & (gbest < lo + Bl)).to(torch.float32)
+            best = torch.cat([last[4][li].reshape(-1), last[5][li].reshape(-1), last[1][li], last[2][li], last[3][li]]) * own
+            self._dist.all_reduce(best, group=self.process_group)
+        out_d = torch.cat([cost_min, best, carry[4]])
+        pout = self._ws.get("pin_out")
+        if pout is None or pout.numel() != out_d.numel():
+            pout = torch.empty(out_d.numel(), dtype=torch.float32).pin_memory()
+            self._ws["pin_out"] = pout
+        pout.copy_(out_d, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        res = pout.numpy().copy()
+        m = self.maxiter_cem
+        cost = res[:m]
+        best_vels = res[m:m + nd * T].reshape(nd, T).T.copy()
+        best_traj = res[m + nd * T:m + 2 * nd * T].reshape(nd, T).T.copy()
+        o = m + 2 * nd * T
+        best_cost_g, best_cost_r, best_cost_c = res[o], res[o + 1], res[o + 2]
+        xi_mean_out = res[o + 3:o + 3 + nv].copy()
+        self.h2d_bytes = host.size * 4
+        self.d2h_bytes = out_d.numel() * 4
+        return cost, best_cost_g, best_cost_r, best_cost_c, best_vels, best_traj, xi_mean_out, thetadot_all, theta_all

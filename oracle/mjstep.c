@@ -22,6 +22,7 @@
 #include <math.h>
 #include <string.h>
 #include <stdlib.h>
+#include <stdio.h>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -999,8 +1000,14 @@ static void linesearch(const omodel *m, odata *d, sctx *c) {
     int s5 = in_bracket(hi, mid);     if (s5) hi = mid;
     int s6 = in_bracket(hi, lo_next); if (s6) hi = lo_next;
     swap = s1 | s2 | s3 | s4 | s5 | s6;
+#ifdef ORACLE_DEBUG
+    printf("[ora]  it %d cand %.7g %.7g %.7g -> lo a %.7g d0 %.5g  hi a %.7g d0 %.5g swaps %d%d%d%d%d%d\n", it, (double)lo_next.alpha, (double)hi_next.alpha, (double)mid.alpha, (double)lo.alpha, (double)lo.d0, (double)hi.alpha, (double)hi.d0, s1, s2, s3, s4, s5, s6);
+#endif
   }
   int improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
+#ifdef ORACLE_DEBUG
+  printf("[ora] p0 cost %.9g d0 %.6g d1 %.6g | lo a %.7g cost %.9g d0 %.6g | hi a %.7g cost %.9g d0 %.6g | gtol %.3g\n", (double)p0.cost, (double)p0.d0, (double)p0.d1, (double)lo.alpha, (double)lo.cost, (double)lo.d0, (double)hi.alpha, (double)hi.cost, (double)hi.d0, (double)gtol);
+#endif
   real alpha = lo.cost < hi.cost ? lo.alpha : hi.alpha;
   if (improved) {
     for (int i = 0; i < nv; i++) { c->qacc[i] += c->search[i] * alpha; c->Ma[i] += mv[i] * alpha; }
@@ -1015,6 +1022,9 @@ static void solve(const omodel *m, odata *d) {
   ctx_create(m, d, c, d->qacc_warmstart);
   ctx_create(m, d, c2, d->qacc_smooth);
   const real *start = c->cost < c2->cost ? d->qacc_warmstart : d->qacc_smooth;
+#ifdef ORACLE_DEBUG
+  printf("[ora] nefc %d cost_w %.9g cost_s %.9g use_warm %d\n", d->nefc, (double)c->cost, (double)c2->cost, (int)(c->cost < c2->cost));
+#endif
   real q0[MAXV];
   memcpy(q0, start, sizeof(real) * nv);
   ctx_create(m, d, c, q0);

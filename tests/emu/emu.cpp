@@ -1,0 +1,43 @@
+// tests/emu/emu.cpp -- CPU single-stepping harness for the rollout core (NO-GPU UNIT TESTS ONLY).
+//
+// Compiles manipulator_mujoco_b200/csrc/rollout_core.h with -DCEMK_EMU, where each LANES block
+// becomes a loop over 32 per-lane register structs (see warp_dsl.h).  It exists so the kernel's
+// indexing / physics logic can be checked against the oracle in a container without a GPU.
+// Nothing in the package imports it; the product path is the CUDA build in csrc/cemk.cu.
+#define CEMK_EMU 1
+#include "../../manipulator_mujoco_b200/csrc/rollout_core.h"
+#include <cstdlib>
+#include <new>
+
+extern "C" int emu_sizeof_kmodel() { return (int)sizeof(KModel); }
+
+extern "C" int emu_rollout(const KModel* m, int B, int T, const float* thetadot, const float* q0, const float* v0,
+                           const float* tpos, const float* trot, float w_pos, float w_rot, float w_col,
+                           float* theta, float* cost4, float* eef_pos, float* eef_rot, float* collision,
+                           float* qacc_dbg, int* flags) {
+#pragma omp parallel
+  {
+    Warp* W = new Warp();
+    WarpSmem* S = new WarpSmem();
+#pragma omp for schedule(dynamic, 4)
+    for (int s = 0; s < B; ++s) {
+      memset((void*)W, 0, sizeof(Warp));
+      memset((void*)S, 0, sizeof(WarpSmem));
+      RolloutArgs A;
+      A.T = T;
+      A.thetadot = thetadot + (size_t)s * KM_NL * T;
+      A.q0 = q0; A.v0 = v0; A.target_pos = tpos; A.target_rot = trot;
+      A.w_pos = w_pos; A.w_rot = w_rot; A.w_col = w_col;
+      A.theta = theta + (size_t)s * KM_NL * T;
+      A.cost4 = cost4 + (size_t)s * 4;
+      A.eef_pos = eef_pos ? eef_pos + (size_t)s * T * 3 : nullptr;
+      A.eef_rot = eef_rot ? eef_rot + (size_t)s * T * 4 : nullptr;
+      A.collision = collision ? collision + (size_t)s * T * m->nslot_robot : nullptr;
+      A.qacc_dbg = qacc_dbg ? qacc_dbg + (size_t)s * T * KM_NV : nullptr;
+      A.flags = flags ? flags + s : nullptr;
+      rollout_sample(*W, *m, *S, A);
+    }
+    delete W; delete S;
+  }
+  return 0;
+}
