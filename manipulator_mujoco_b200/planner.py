@@ -323,8 +323,10 @@ class cem_planner:
         B = z.shape[0]
         xi = torch.empty(B, self.nvar, device=self.device)
         ws = self._buf("chol", (self.nvar * self.nvar,))
-        _lib.check(self._lib.cemk_sample(self._h, B, _ptr(z), _ptr(self._t(xi_mean)), _ptr(self._t(xi_cov)), _ptr(ws),
-                                         _ptr(xi), self._stream()), self._lib)
+        mean, cov = self._t(xi_mean), self._t(xi_cov)
+        _lib.check(self._lib.cemk_sample(self._h, B, _ptr(z), _ptr(mean), _ptr(cov), _ptr(ws), _ptr(xi), self._stream()),
+                   self._lib)
+        self._keep_s = (mean, cov)
         return xi, key
 
     def _project(self, xi_samples, state_term, want_thetadot):
@@ -352,10 +354,14 @@ class cem_planner:
         collision = torch.empty(B, T, self.nslot, device=dev) if dumps else None
         flags = self._buf("flags", (B,), torch.int32)
         w = self.cost_weights
+        # keep every converted argument referenced until the launch is enqueued (a temporary tensor
+        # would hand its storage to the next allocation before the kernel reads it)
+        q0, v0, tp, tr = self._t(init_pos), self._t(init_vel), self._t(target_pos), self._t(target_rot)
         _lib.check(self._lib.cemk_rollout_cost(
-            self._h, B, T, _ptr(td), _ptr(self._t(init_pos)), _ptr(self._t(init_vel)), _ptr(self._t(target_pos)),
-            _ptr(self._t(target_rot)), float(w['w_pos']), float(w['w_rot']), float(w['w_col']), _ptr(theta), _ptr(cost4),
-            _ptr(eef_pos), _ptr(eef_rot), _ptr(collision), None, _ptr(flags), self._stream()), self._lib)
+            self._h, B, T, _ptr(td), _ptr(q0), _ptr(v0), _ptr(tp), _ptr(tr), float(w['w_pos']), float(w['w_rot']),
+            float(w['w_col']), _ptr(theta), _ptr(cost4), _ptr(eef_pos), _ptr(eef_rot), _ptr(collision), None, _ptr(flags),
+            self._stream()), self._lib)
+        self._keep = (td, q0, v0, tp, tr)
         return theta, cost4, eef_pos, eef_rot, collision
 
     def compute_rollout_batch(self, thetadot, init_pos, init_vel):
@@ -406,9 +412,11 @@ class cem_planner:
         ce, xe = self._t(cost_ellite), self._t(xi_ellite)
         mean = torch.empty(self.nvar, device=self.device)
         cov = torch.empty(self.nvar, self.nvar, device=self.device)
-        _lib.check(self._lib.cemk_mean_cov(self._h, ce.shape[0], _ptr(ce), _ptr(xe), _ptr(self._t(mean_control_prev)),
-                                           _ptr(self._t(cov_control_prev)), float(self.lamda), float(self.alpha_mean),
-                                           float(self.alpha_cov), _ptr(mean), _ptr(cov), self._stream()), self._lib)
+        mp, cp = self._t(mean_control_prev), self._t(cov_control_prev)
+        _lib.check(self._lib.cemk_mean_cov(self._h, ce.shape[0], _ptr(ce), _ptr(xe), _ptr(mp), _ptr(cp), float(self.lamda),
+                                           float(self.alpha_mean), float(self.alpha_cov), _ptr(mean), _ptr(cov),
+                                           self._stream()), self._lib)
+        self._keep_m = (ce, xe, mp, cp)
         return mean, cov
 
     # ------------------------------------------------------------------ elite selection across GPUs

@@ -1147,3 +1147,26 @@ int oracle_rollout(const omodel *m, int B, int T, int ndof, const double *thetad
 
 int oracle_sizeof_model(void) { return (int)sizeof(omodel); }
 int oracle_real_bytes(void) { return (int)sizeof(real); }
+
+/* ------------------------------------------------------------------ isolated colliders for unit tests
+ * type: 0 plane-capsule, 1 capsule-capsule, 2 capsule-box, 3 plane-box, 4 box-box.
+ * pos/mat: world pose (mat row-major), size: mujoco size triple.  Outputs up to 4 slots. */
+int oracle_collide(int type, const double *p1, const double *m1, const double *s1, const double *p2, const double *m2,
+                   const double *s2, double *dist, double *pos, double *frame) {
+  real P1[3], M1[9], S1[3], P2[3], M2[9], S2[3], d[4] = {1, 1, 1, 1}, ps[4][3], fr[4][9];
+  memset(ps, 0, sizeof ps); memset(fr, 0, sizeof fr);
+  for (int k = 0; k < 3; k++) { P1[k] = (real)p1[k]; P2[k] = (real)p2[k]; S1[k] = (real)s1[k]; S2[k] = (real)s2[k]; }
+  for (int k = 0; k < 9; k++) { M1[k] = (real)m1[k]; M2[k] = (real)m2[k]; }
+  int n = 0;
+  if (type == 0) { plane_capsule(P1, M1, P2, M2, S2, d, ps, fr); n = 2; }
+  else if (type == 1) { capsule_capsule(P1, M1, S1, P2, M2, S2, d, ps, fr); n = 1; }
+  else if (type == 2) { capsule_box(P1, M1, S1, P2, M2, S2, d, ps, fr); n = 2; }
+  else if (type == 3) { plane_box(P1, M1, P2, M2, S2, d, ps, fr); n = 4; }
+  else if (type == 4) { box_box(P1, M1, S1, P2, M2, S2, d, ps, fr); n = 4; }
+  for (int i = 0; i < n; i++) {
+    dist[i] = d[i];
+    for (int k = 0; k < 3; k++) pos[3*i+k] = ps[i][k];
+    for (int k = 0; k < 9; k++) frame[9*i+k] = fr[i][k];
+  }
+  return n;
+}

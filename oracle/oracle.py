@@ -183,3 +183,18 @@ class Oracle:
         if want_state:
             return theta, eef_pos, eef_rot, collision, qpos_out, qacc_out
         return theta, eef_pos, eef_rot, collision
+
+
+def collide(kind, p1, m1, s1, p2, m2, s2, dtype="f64"):
+    """Run one oracle collider in isolation (unit tests).  kind: plane_capsule, capsule_capsule,
+    capsule_box, plane_box, box_box.  Returns dist [n], pos [n,3], frame [n,3,3]."""
+    libs = build()
+    lib = C.CDLL(libs[0] if dtype == "f64" else libs[1])
+    code = ["plane_capsule", "capsule_capsule", "capsule_box", "plane_box", "box_box"].index(kind)
+    a = lambda x, n: np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1)[:n] if np.size(x) >= n
+                                          else np.concatenate([np.asarray(x, dtype=np.float64).reshape(-1), np.zeros(n - np.size(x))]))
+    P1, M1, S1, P2, M2, S2 = a(p1, 3), a(m1, 9), a(s1, 3), a(p2, 3), a(m2, 9), a(s2, 3)
+    dist, pos, frame = np.zeros(4), np.zeros(12), np.zeros(36)
+    p = lambda x: x.ctypes.data_as(C.c_void_p)
+    n = lib.oracle_collide(code, p(P1), p(M1), p(S1), p(P2), p(M2), p(S2), p(dist), p(pos), p(frame))
+    return dist[:n].copy(), pos.reshape(4, 3)[:n].copy(), frame.reshape(4, 3, 3)[:n].copy()

@@ -1,0 +1,70 @@
+"""What pins the oracle to the real reference stack: FK, recorded MuJoCo data,
+and physical invariants.  Parity with MJX contact/solver arithmetic itself is UNPINNED (no MJX here)."""
+import os
+
+import numpy as np
+
+from conftest import GOLDEN, Q0
+
+
+def test_fk_pins(mc, oracle64):
+    q = mc.qpos0.copy()
+    q[:6] = Q0
+    f = oracle64.forward(q, np.zeros(12))
+    np.testing.assert_allclose(f["site_tcp"], [0.04936, -0.10358, 0.90439], atol=1e-5)
+    np.testing.assert_allclose(f["xquat"][mc.body_id("hande")], [0.08889, 0.72357, 0.67677, 0.10259], atol=1e-5)
+
+
+def test_mass_matrix_matches_independent_host_formula(mc, oracle64):
+    """CRBA (oracle, MuJoCo cinert formulation) vs sum_b J^T diag(m, I) J (mjcf.host_mass_matrix)."""
+    from manipulator_mujoco_b200.mjcf import host_mass_matrix
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        q = mc.qpos0.copy()
+        q[:6] = rng.uniform(-2, 2, 6)
+        M, _, _ = host_mass_matrix(mc, q)
+        np.testing.assert_allclose(oracle64.forward(q, np.zeros(12))["M"], M, atol=1e-12)
+
+
+def test_gravcomp_cancels_gravity_bias(mc, oracle64):
+    q = mc.qpos0.copy()
+    q[:6] = Q0
+    f = oracle64.forward(q, np.zeros(12))
+    np.testing.assert_allclose(f["qfrc_passive"][:6], f["qfrc_bias"][:6], atol=1e-12)
+    np.testing.assert_allclose(f["qacc"][:6], 0, atol=1e-12)
+    np.testing.assert_allclose(f["qacc"][6:], [0, 0, -9.81, 0, 0, 0], atol=1e-12)     # box in free fall
+
+
+def test_recorded_closed_loop_run_kat(mc, oracle64):
+    """data/theta.csv, data/thetadot.csv: 897 ticks of the reference's C-MuJoCo plant at dt = 0.05.
+    theta[k+1] = theta[k] + dt*(thetadot[k+1] + dt*qacc); with the oracle's qacc the residual drops
+    from 4.5e-4 (no dynamics) to < 2e-5 rad, median < 5e-7."""
+    d = np.load(os.path.join(GOLDEN, "closed_loop_kat.npz"))
+    th, td = d["theta"], d["thetadot"].astype(np.float64)
+    dt = 0.05
+    qbox = mc.qpos0[6:].copy()
+    qbox[2] = 0.445
+    r0, r1 = [], []
+    for k in range(0, 896, 3):
+        v = np.zeros(12)
+        v[:6] = td[k + 1]
+        qacc = oracle64.forward(np.concatenate([th[k], qbox]), v)["qacc"][:6]
+        r0.append(np.abs(th[k + 1] - th[k] - dt * td[k + 1]).max())
+        r1.append(np.abs(th[k + 1] - th[k] - dt * (td[k + 1] + dt * qacc)).max())
+    r0, r1 = np.array(r0), np.array(r1)
+    assert r0.max() > 3e-4
+    assert r1.max() < 2e-5 and np.median(r1) < 5e-7
+    assert (r1 < r0).mean() > 0.98
+
+
+def test_box_settles_on_table(mc, oracle64):
+    """target_0 drops 5.5 cm and rests with the analytic soft-contact penetration
+    m g / (16 D k imp) = 1.2 mm, untilted."""
+    T = 60
+    th, ep, er, col, qp, qa = oracle64.rollout(np.zeros((1, 6 * T)), Q0, np.zeros(6), want_state=True)
+    z = qp[0, :, 8]
+    assert abs(z[-1] - (0.425 + 0.02 - 0.00123)) < 5e-5
+    np.testing.assert_allclose(qp[0, -1, 9:13], [0, 1, 0, 0], atol=1e-9)
+    np.testing.assert_allclose(qp[0, -1, 6:8], [-0.3, -0.3], atol=1e-9)
+    assert np.abs(qa[0, :, :6]).max() < 1e-9          # robot untouched (gravcomp)
+    assert np.abs(th.reshape(6, T) - Q0[:, None]).max() < 1e-9
