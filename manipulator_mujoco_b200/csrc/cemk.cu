@@ -56,13 +56,21 @@ __global__ void __launch_bounds__(ROLLOUT_WARPS * 32) k_rollout(const KModel* __
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5;
-  const int s = blockIdx.x * ROLLOUT_WARPS + warp;
-  if (s >= a.B) return;
+  int s = blockIdx.x * ROLLOUT_WARPS + warp;
+  const bool live = s < a.B;
+  if (!live) {
+#ifdef CEMK_STEP_SYNC
+    s = a.B - 1;            // padding warp: keeps the CTA's per-step barrier count uniform, writes nothing
+#else
+    return;
+#endif
+  }
   Warp W;
   W.lane = threadIdx.x & 31;
   RolloutArgs A;
   const size_t row = (size_t)s * KM_NL * a.T;
   A.T = a.T;
+  A.live = live;
   A.thetadot = a.thetadot + row;
   A.q0 = a.q0; A.v0 = a.v0; A.target_pos = a.target_pos; A.target_rot = a.target_rot;
   A.w_pos = a.w_pos; A.w_rot = a.w_rot; A.w_col = a.w_col;

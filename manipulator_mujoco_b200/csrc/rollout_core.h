@@ -30,12 +30,10 @@
 #define MJ_MAXIMP 0.9999f
 
 struct LaneRegs {
-  float prevd[KM_NPASS][2];   // previous-step distance of this lane's robot slots
-  float curd[KM_NPASS][2];
   float cost_c;               // this lane's share of cost_c
   int nact, off;              // active contacts this lane will emit, and where
   int actmask;                // bit (2*pass + slot)
-  float acc[9];               // line-search partial sums
+  float acc[9];               // line-search partial sums (compile-time indices only)
   float f0, f1, f2;
 };
 
@@ -49,6 +47,7 @@ struct WarpSmem {
   float M[KM_NV][KM_NV], H[KM_NV][KM_NV];
   float fs[12], as[12], qacc[12], Ma[12], grad[12], search[12], mv[12];
   int ncon, nrow, nlim, flags;
+  float prevd[KM_NPASS * 2][32];      // previous-step distance of every lane's robot slots
   float bstage[KM_MAXBPAIR][4][4];    // free-box pair candidates: pos3, dist
   float bnrm[KM_MAXBPAIR][4];
   float cgeo[NCMAX][16];              // pos3 n3 t1 3 t2 3 dist invw link1 link2
@@ -96,6 +95,29 @@ KFN void quat_to_mat(float* m, const float* q) {
   m[3] = 2.f * (x * y + w * z);         m[4] = w * w - x * x + y * y - z * z; m[5] = 2.f * (y * z - w * x);
   m[6] = 2.f * (x * z - w * y);         m[7] = 2.f * (y * z + w * x);         m[8] = w * w - x * x - y * y + z * z;
 }
+// sin/cos for |x| up to a few hundred: Cody-Waite reduction to [-pi/4, pi/4] + minimax polynomials
+// (max error 7e-8 absolute for |x| <= 8, as good as sinf/cosf).  Replaces sincosf, whose slow path drags a large local-memory
+// Payne-Hanek routine into the kernel.
+KFN void k_sincos(float x, float* sn, float* cs) {
+  const float k = rintf(x * 0.636619772367581343f);
+  float r = fmaf(k, -1.5707963705062866f, x);          // pi/2 split in three float32 pieces
+  r = fmaf(k, 4.371138828673793e-08f, r);
+  r = fmaf(k, 1.7763568394002505e-15f, r);
+  const float r2 = r * r;
+  float sp = fmaf(r2, 2.724990382407328e-06f, -0.00019840086439758365f);
+  sp = fmaf(sp, r2, 0.008333331873528407f);
+  sp = fmaf(sp, r2, -0.16666666663842697f);
+  sp = fmaf(sp * r2, r, r);
+  float cp = fmaf(r2, -2.1011874848372744e-08f, 2.452856854478212e-05f);
+  cp = fmaf(cp, r2, -0.0013888048639039594f);
+  cp = fmaf(cp, r2, 0.041666660194519124f);
+  cp = fmaf(cp, r2, -0.5f);
+  cp = fmaf(cp, r2, 1.f);
+  const int q = (int)k;
+  const float s0 = (q & 1) ? cp : sp, c0 = (q & 1) ? sp : cp;
+  *sn = (q & 2) ? -s0 : s0;
+  *cs = ((q + 1) & 2) ? -c0 : c0;
+}
 // MJX math.make_frame: tangents for a unit normal (rows t1, t2)
 KFN void make_tangents(const float* n, float* t1, float* t2) {
   float b[3] = {0.f, 0.f, 0.f};
@@ -128,6 +150,10 @@ KFN void cross_force(float* r, const float* v, const float* f) {
 }
 
 // ------------------------------------------------------------------------------------------ colliders
+// Code-size note: the first build inlined every collider into four unrolled passes (670 KB of SASS)
+// and spent 80 % of its issue slots waiting on instruction fetch (profiles/r1a).  Colliders are now
+// real functions (KNOINLINE) called from rolled loops.
+
 // MJX math.closest_segment_point_and_dist
 KFN float closest_segment_point(float* res, const float* a, const float* b, const float* pt) {
   float ab[3], ap[3], d[3];
@@ -138,9 +164,13 @@ KFN float closest_segment_point(float* res, const float* a, const float* b, cons
   sub3(d, pt, res);
   return dot3(d, d);
 }
-// MJX math.closest_segment_to_segment_points
-KFN void closest_seg_seg(float* besta, float* bestb, const float* a0, const float* a1, const float* b0, const float* b1) {
+// MJX math.closest_segment_to_segment_points; res = besta(3), bestb(3)
+struct SegPair { float a[3], b[3]; };
+KNOINLINE SegPair closest_seg_seg(float a0x, float a0y, float a0z, float a1x, float a1y, float a1z,
+                                  float b0x, float b0y, float b0z, float b1x, float b1y, float b1z) {
+  const float a0[3] = {a0x, a0y, a0z}, a1[3] = {a1x, a1y, a1z}, b0[3] = {b0x, b0y, b0z}, b1[3] = {b1x, b1y, b1z};
   float da[3], db[3], amid[3], bmid[3], tr[3];
+  SegPair r;
   sub3(da, a1, a0); sub3(db, b1, b0);
   float ha = 0.5f * normalize3(da), hb = 0.5f * normalize3(db);
   madd3(amid, a0, da, ha); madd3(bmid, b0, db, hb);
@@ -150,16 +180,21 @@ KFN void closest_seg_seg(float* besta, float* bestb, const float* a0, const floa
   float tb = dbt + ta * dd;
   ta = fminf(fmaxf(ta, -ha), ha);
   tb = fminf(fmaxf(tb, -hb), hb);
-  madd3(besta, amid, da, ta); madd3(bestb, bmid, db, tb);
+  madd3(r.a, amid, da, ta); madd3(r.b, bmid, db, tb);
   float na[3], nb[3];
-  float d1 = closest_segment_point(na, a0, a1, bestb);
-  float d2 = closest_segment_point(nb, b0, b1, besta);
-  if (d1 < d2) copy3(besta, na); else copy3(bestb, nb);
+  float d1 = closest_segment_point(na, a0, a1, r.b);
+  float d2 = closest_segment_point(nb, b0, b1, r.a);
+  if (d1 < d2) copy3(r.a, na); else copy3(r.b, nb);
+  return r;
+}
+KFN SegPair closest_seg_seg_v(const float* a0, const float* a1, const float* b0, const float* b1) {
+  return closest_seg_seg(a0[0], a0[1], a0[2], a1[0], a1[1], a1[2], b0[0], b0[1], b0[2], b1[0], b1[1], b1[2]);
 }
 
 struct Contact2 { float dist[2], pos[2][3], nrm[2][3]; };
+struct Dist2 { float d0, d1; };
 
-// plane (geom1) vs capsule (geom2); A = centre + axis*hl is slot 0 (MJX plane_capsule offset order)
+// plane (geom1) vs capsule (geom2); B = centre + axis*hl is slot 0 (MJX plane_capsule offset order)
 template <bool FULL>
 KFN void plane_capsule(const float* ppos, const float* pn, const float* A, const float* B, float r, Contact2& c) {
   float t[3];
@@ -174,14 +209,14 @@ KFN void plane_capsule(const float* ppos, const float* pn, const float* A, const
 // capsule_capsule -> sphere_sphere on the closest segment points
 template <bool FULL>
 KFN void capsule_capsule(const float* a0, const float* a1, float r1, const float* b0, const float* b1, float r2, Contact2& c) {
-  float pa[3], pb[3], n[3];
-  closest_seg_seg(pa, pb, a0, a1, b0, b1);
-  sub3(n, pb, pa);
+  SegPair sp = closest_seg_seg_v(a0, a1, b0, b1);
+  float n[3];
+  sub3(n, sp.b, sp.a);
   float dn = normalize3(n);
   if (dn == 0.f) { n[0] = 1.f; n[1] = 0.f; n[2] = 0.f; }
   c.dist[0] = dn - (r1 + r2);
   c.dist[1] = 1.f;
-  if (FULL) { madd3(c.pos[0], pa, n, r1 + 0.5f * c.dist[0]); copy3(c.nrm[0], n); }
+  if (FULL) { madd3(c.pos[0], sp.a, n, r1 + 0.5f * c.dist[0]); copy3(c.nrm[0], n); }
 }
 // capsule (geom1) vs box (geom2), MJX capsule_convex with rectangular faces; see header note.
 template <bool FULL>
@@ -241,19 +276,20 @@ KFN void capsule_box(const float* A, const float* B, float r, const float* bpos,
   float ha = sg * ak - sk, hb = sg * bk_ - sk;
   float hmin = (ha * hb <= 0.f) ? 0.f : fminf(fabsf(ha), fabsf(hb));
   if (hmin < r) {
-    // face polygon, counter-clockwise seen from outside; edge i runs from V[i-1] to V[i]
-    float fu[4] = {-su, su, su, -su}, fw[4] = {-sw, -sw, sw, sw};
-    if (sg < 0.f) { fu[0] = -su; fw[0] = sw; fu[1] = su; fw[1] = sw; fu[2] = su; fw[2] = -sw; fu[3] = -su; fw[3] = -sw; }
-    float pa[3] = {ak, au, aw}, pb[3] = {bk_, bu, bw};
     float bd = 0.f, bec[3] = {0.f, 0.f, 0.f}, bcc[3] = {0.f, 0.f, 0.f};
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 4; ++i) {
-      int ip = (i + 3) & 3;
-      float e0[3] = {sg * sk, fu[ip], fw[ip]}, e1[3] = {sg * sk, fu[i], fw[i]}, ec[3], cc[3], df[3];
-      closest_seg_seg(ec, cc, e0, e1, pa, pb);
-      sub3(df, ec, cc);
+      // face polygon counter-clockwise seen from outside (reversed for the negative face);
+      // edge i runs from V[i-1] to V[i]
+      const int ip = (i + 3) & 3;
+      const int vi = sg < 0.f ? 3 - i : i, vp = sg < 0.f ? 3 - ip : ip;
+      const float u1 = (vi == 1 || vi == 2) ? su : -su, w1 = vi >= 2 ? sw : -sw;
+      const float u0 = (vp == 1 || vp == 2) ? su : -su, w0 = vp >= 2 ? sw : -sw;
+      SegPair sp = closest_seg_seg(sg * sk, u0, w0, sg * sk, u1, w1, ak, au, aw, bk_, bu, bw);
+      float df[3];
+      sub3(df, sp.a, sp.b);
       float d2 = dot3(df, df);
-      if (i == 0 || d2 < bd) { bd = d2; copy3(bec, ec); copy3(bcc, cc); }
+      if (i == 0 || d2 < bd) { bd = d2; copy3(bec, sp.a); copy3(bcc, sp.b); }
     }
     float eax[3];
     sub3(eax, bcc, bec);
@@ -279,6 +315,12 @@ KFN void capsule_box(const float* A, const float* B, float r, const float* bpos,
       normalize3(c.nrm[j]);
     }
   }
+}
+KNOINLINE Dist2 capsule_box_dist(const float* A, const float* B, float r, const float* bpos, const float* bmat, const float* bsize) {
+  Contact2 c;
+  capsule_box<false>(A, B, r, bpos, bmat, bsize, c);
+  Dist2 d; d.d0 = c.dist[0]; d.d1 = c.dist[1];
+  return d;
 }
 
 // ---- free-box colliders (lane-serial, rarely past the bounding-sphere test) -------------------
@@ -318,7 +360,7 @@ KFN void box_face(const float* s, int f, float v[4][3], float* n) {
 }
 // plane (geom1) vs free box: out[k] = pos3, dist; normal = plane normal.  Only penetrating
 // vertices matter (these slots never enter the cost), see oracle plane_box.
-KFN int plane_box(const float* ppos, const float* pn, const float* bpos, const float* bmat, const float* bs, float out[4][4]) {
+KNOINLINE int plane_box(const float* ppos, const float* pn, const float* bpos, const float* bmat, const float* bs, float out[4][4]) {
   float v[8][3], sup[8], t[3], pl[3], n[3], smax = -1e30f;
   bool mask[8]; int idx[4];
   sub3(t, ppos, bpos); matT_vec(pl, bmat, t); matT_vec(n, bmat, pn);
@@ -357,16 +399,21 @@ KFN int clip_poly_halfplane(int n, float in[][3], float out[][3], const float* p
   }
   return m;
 }
-// static box (geom1) vs free box (geom2): SAT over 15 axes, then clipped face manifold or a single
-// edge-edge contact.  out[k] = pos3, dist; nrm = contact normal (geom1 -> geom2), world frame.
-KFN int box_box(const float* p1, const float* m1, const float* s1, const float* p2, const float* m2, const float* s2, float out[4][4], float* nrm) {
+// box (geom1) vs box (geom2): SAT over 15 axes, then clipped face manifold or a single edge-edge
+// contact.  out[k] = pos3, dist; nrm = contact normal (geom1 -> geom2), world frame.
+KNOINLINE int box_box(const float* p1, const float* m1, const float* s1, const float* p2, const float* m2, const float* s2, float out[4][4], float* nrm) {
   float t[3], c[3], R[9];
   sub3(t, p1, p2); matT_vec(c, m2, t);
   for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R[3 * i + j] = m2[i] * m1[j] + m2[3 + i] * m1[3 + j] + m2[6 + i] * m1[6 + j];
   float A[3][3];
   for (int i = 0; i < 3; ++i) { A[i][0] = R[i]; A[i][1] = R[3 + i]; A[i][2] = R[6 + i]; }
   float bestsep = -1e30f; int besttype = -1, bi = 0, bj = 0; float bestn[3] = {0.f, 0.f, 1.f};
-  for (int type = 0; type < 3; ++type) for (int i = 0; i < 3; ++i) for (int j = 0; j < (type == 2 ? 3 : 1); ++j) {
+#pragma unroll 1
+  for (int type = 0; type < 3; ++type)
+#pragma unroll 1
+    for (int i = 0; i < 3; ++i)
+#pragma unroll 1
+      for (int j = 0; j < (type == 2 ? 3 : 1); ++j) {
     float ax[3] = {0.f, 0.f, 0.f};
     if (type == 0) ax[i] = 1.f; else if (type == 1) copy3(ax, A[i]);
     else { float e2[3] = {0.f, 0.f, 0.f}; e2[j] = 1.f; cross3(ax, A[i], e2); if (normalize3(ax) < 1e-6f) continue; }
@@ -389,14 +436,14 @@ KFN int box_box(const float* p1, const float* m1, const float* s1, const float* 
     copy3(e1c, c);
     for (int k = 0; k < 3; ++k) if (k != bi) { float sgn = dot3(A[k], bestn) > 0.f ? 1.f : -1.f; madd3(e1c, e1c, A[k], sgn * s1[k]); }
     for (int k = 0; k < 3; ++k) if (k != bj) e2c[k] = (bestn[k] > 0.f ? -1.f : 1.f) * s2[k];
-    float a0[3], a1[3], b0[3], b1[3], pa[3], pb[3], e2[3] = {0.f, 0.f, 0.f};
+    float a0[3], a1[3], b0[3], b1[3], e2[3] = {0.f, 0.f, 0.f};
     e2[bj] = 1.f;
     madd3(a0, e1c, A[bi], -s1[bi]); madd3(a1, e1c, A[bi], s1[bi]);
     madd3(b0, e2c, e2, -s2[bj]); madd3(b1, e2c, e2, s2[bj]);
-    closest_seg_seg(pa, pb, a0, a1, b0, b1);
-    float mid[3] = {0.5f * (pa[0] + pb[0]), 0.5f * (pa[1] + pb[1]), 0.5f * (pa[2] + pb[2])}, w[3], df[3];
+    SegPair sp = closest_seg_seg_v(a0, a1, b0, b1);
+    float mid[3] = {0.5f * (sp.a[0] + sp.b[0]), 0.5f * (sp.a[1] + sp.b[1]), 0.5f * (sp.a[2] + sp.b[2])}, w[3], df[3];
     mat_vec(w, m2, mid); add3(out[0], w, p2);
-    sub3(df, pb, pa);
+    sub3(df, sp.b, sp.a);
     out[0][3] = dot3(df, bestn);
     return out[0][3] < 0.f;
   }
@@ -427,6 +474,7 @@ KFN int box_box(const float* p1, const float* m1, const float* s1, const float* 
   box_face(is, inf, iface, itmp);
   for (int i = 0; i < 4; ++i) { mat_vec(poly[i], Rr, iface[i]); add3(poly[i], poly[i], rc); }
   int np = 4;
+#pragma unroll 1
   for (int i = 0; i < 4 && np > 0; ++i) {
     float e[3], en[3];
     sub3(e, rface[i], rface[(i + 3) % 4]);
@@ -459,6 +507,7 @@ KFN int box_box(const float* p1, const float* m1, const float* s1, const float* 
 }
 
 // ------------------------------------------------------------------------------------------ constraints
+KFN float pow_pos(float x, float p) { return p == 2.f ? x * x : (p == 1.f ? x : powf(x, p)); }
 // MJX constraint._kbi + row regulariser (BD.8)
 KFN void row_params(const KModel& m, float pos, float invw, float vel, float& D, float& aref) {
   float tc = fmaxf(m.solref[0], 2.f * m.dt), dr = m.solref[1];
@@ -468,8 +517,8 @@ KFN void row_params(const KModel& m, float pos, float invw, float vel, float& D,
   if (m.solref[0] <= 0.f) k = -m.solref[0] / (dmax * dmax);
   if (m.solref[1] <= 0.f) b = -m.solref[1] / dmax;
   float x = fabsf(pos) / width, y;
-  if (x < mid) y = powf(x, power) / powf(mid, power - 1.f);
-  else y = 1.f - powf(1.f - x, power) / powf(1.f - mid, power - 1.f);
+  if (x < mid) y = pow_pos(x, power) / pow_pos(mid, power - 1.f);
+  else y = 1.f - pow_pos(1.f - x, power) / pow_pos(1.f - mid, power - 1.f);
   float imp = fminf(fmaxf(dmin + y * (dmax - dmin), dmin), dmax);
   if (x > 1.f) imp = dmax;
   float R = fmaxf(invw * (1.f - imp) / imp, MJ_MINVAL);
@@ -517,43 +566,110 @@ struct LSPoint { float alpha, cost, d0, d1; };
 KFN bool in_bracket(const LSPoint& x, const LSPoint& y) {
   return ((x.d0 < y.d0) && (y.d0 < 0.f)) || ((x.d0 > y.d0) && (y.d0 > 0.f));
 }
-// evaluate the 1-D piecewise quadratic at up to three step sizes at once (BD.10)
-KFN void ls_eval(Warp& W, const WarpSmem& S, const float* qg, int n, const float* alpha, LSPoint* out) {
-  LANES(W, R)
-    for (int k = 0; k < 9; ++k) R.acc[k] = 0.f;
-    for (int r = lane; r < S.nrow; r += 32) {
-      float ja = S.rJaref[r], jv = S.rJv[r], D = S.rD[r];
-      float q0 = 0.5f * D * ja * ja, q1 = D * jv * ja, q2 = 0.5f * D * jv * jv;
-      for (int k = 0; k < n; ++k) if (ja + alpha[k] * jv < 0.f) { R.acc[3 * k] += q0; R.acc[3 * k + 1] += q1; R.acc[3 * k + 2] += q2; }
+
+// emit the full contact records (position, frame) of one lane's active robot slots; rare path
+KNOINLINE void emit_robot_contacts(const KModel& m, WarpSmem& S, int lane, int actmask, int o) {
+#pragma unroll 1
+  for (int p = 0; p < KM_NPASS; ++p) {
+    const int bits = (actmask >> (2 * p)) & 3;
+    if (!bits) continue;
+    const int e = p * 32 + lane, ty = m.rp_type[e], a = m.rp_a[e], b = m.rp_b[e];
+    Contact2 c;
+    float invw; int l1, l2;
+    float pt1[3]; bool own_t1 = false;
+    if (ty == KP_CAP_BOX) {
+      const bool st = b < m.nsbox;
+      capsule_box<true>(S.capA[a], S.capB[a], m.cap_r[a], st ? m.sb_pos[b] : S.qpos + KM_NL, st ? m.sb_mat[b] : S.bmat,
+                        st ? m.sb_size[b] : m.fb_size, c);
+      invw = m.cap_invw[a] + (st ? 0.f : m.fb_invw); l1 = m.cap_link[a]; l2 = st ? -1 : KM_NL;
+    } else if (ty == KP_CAP_CAP) {
+      capsule_capsule<true>(S.capA[a], S.capB[a], m.cap_r[a], S.capA[b], S.capB[b], m.cap_r[b], c);
+      invw = m.cap_invw[a] + m.cap_invw[b]; l1 = m.cap_link[a]; l2 = m.cap_link[b];
+    } else {
+      plane_capsule<true>(m.plane_pos, m.plane_n, S.capA[b], S.capB[b], m.cap_r[b], c);
+      invw = m.cap_invw[b]; l1 = -1; l2 = m.cap_link[b];
+      // MJX plane_capsule: first tangent = capsule axis projected on the plane
+      float ax[3];
+      sub3(ax, S.capB[b], S.capA[b]); normalize3(ax);
+      madd3(pt1, ax, m.plane_n, -dot3(m.plane_n, ax));
+      if (normalize3(pt1) < 0.5f) {
+        pt1[0] = 0.f;
+        if (m.plane_n[1] > -0.5f && m.plane_n[1] < 0.5f) { pt1[1] = 1.f; pt1[2] = 0.f; } else { pt1[1] = 0.f; pt1[2] = 1.f; }
+      }
+      own_t1 = true;
     }
-  END_LANES
-  for (int k = 0; k < n; ++k) {
-    float q0 = qg[0] + warp_sum(W, [&](int, LaneRegs& R) { return R.acc[3 * k]; });
-    float q1 = qg[1] + warp_sum(W, [&](int, LaneRegs& R) { return R.acc[3 * k + 1]; });
-    float q2 = qg[2] + warp_sum(W, [&](int, LaneRegs& R) { return R.acc[3 * k + 2]; });
-    float a = alpha[k];
-    out[k].alpha = a;
-    out[k].cost = a * a * q2 + a * q1 + q0;
-    out[k].d0 = 2.f * a * q2 + q1;
-    out[k].d1 = 2.f * q2 + (q2 == 0.f ? MJ_MINVAL : 0.f);
+#pragma unroll 1
+    for (int k = 0; k < 2; ++k) {
+      if (!((bits >> k) & 1)) continue;
+      if (o < NCMAX) {
+        float* g = S.cgeo[o];
+        copy3(g, c.pos[k]); copy3(g + 3, c.nrm[k]);
+        if (own_t1) { copy3(g + 6, pt1); cross3(g + 9, c.nrm[k], pt1); }
+        else make_tangents(c.nrm[k], g + 6, g + 9);
+        g[12] = c.dist[k]; g[13] = invw; g[14] = (float)l1; g[15] = (float)l2;
+      }
+      ++o;
+    }
+  }
+}
+// free-box pairs of one lane: full contact generation into the staging area; returns #active
+KNOINLINE int box_pair_contacts(const KModel& m, WarpSmem& S, int lane) {
+  const int ty = m.bp_type[lane], a = m.bp_a[lane];
+  const float* bp = S.qpos + KM_NL;
+  const float rb = sqrtf(m.fb_size[0] * m.fb_size[0] + m.fb_size[1] * m.fb_size[1] + m.fb_size[2] * m.fb_size[2]);
+  int n = 0;
+  for (int k = 0; k < 4; ++k) S.bstage[lane][k][3] = 1.f;
+  if (ty == KB_PLANE_BOX) {
+    float t[3]; sub3(t, bp, m.plane_pos);
+    if (dot3(t, m.plane_n) < rb) { n = plane_box(m.plane_pos, m.plane_n, bp, S.bmat, m.fb_size, S.bstage[lane]); copy3(S.bnrm[lane], m.plane_n); }
+  } else {
+    float t[3]; sub3(t, bp, m.sb_pos[a]);
+    const float ra = sqrtf(m.sb_size[a][0] * m.sb_size[a][0] + m.sb_size[a][1] * m.sb_size[a][1] + m.sb_size[a][2] * m.sb_size[a][2]);
+    if (dot3(t, t) < (ra + rb) * (ra + rb)) {
+      if (ty == KB_BOX_BOX) n = box_box(m.sb_pos[a], m.sb_mat[a], m.sb_size[a], bp, S.bmat, m.fb_size, S.bstage[lane], S.bnrm[lane]);
+      else n = box_box(bp, S.bmat, m.fb_size, m.sb_pos[a], m.sb_mat[a], m.sb_size[a], S.bstage[lane], S.bnrm[lane]);
+    }
+  }
+  return n;
+}
+KNOINLINE void emit_box_contacts(const KModel& m, WarpSmem& S, int lane, int o) {
+  const bool sw = m.bp_type[lane] == KB_BOX_BOX_SWAP;
+#pragma unroll 1
+  for (int k = 0; k < 4; ++k) {
+    if (!(S.bstage[lane][k][3] < 0.f)) continue;
+    if (o < NCMAX) {
+      float* g = S.cgeo[o];
+      copy3(g, S.bstage[lane][k]); copy3(g + 3, S.bnrm[lane]);
+      make_tangents(S.bnrm[lane], g + 6, g + 9);
+      g[12] = S.bstage[lane][k][3]; g[13] = m.fb_invw; g[14] = sw ? (float)KM_NL : -1.f; g[15] = sw ? -1.f : (float)KM_NL;
+    }
+    ++o;
   }
 }
 
+// per-step observation / cost hooks of the narrow phase
+struct StepIO {
+  bool first;                 // t == 0: no previous distance yet
+  float* collision_row;       // optional dump of this step's robot-slot distances [nslot_robot]
+};
+
 // ------------------------------------------------------------------------------------------ one forward()
-// Inputs: S.qpos, S.qvel, S.warm.  Outputs: S.qacc (= new warm start), per-lane R.curd, link frames.
-KFN void step_forward(Warp& W, const KModel& m, WarpSmem& S) {
+// Inputs: S.qpos, S.qvel, S.warm.  Outputs: S.qacc (= new warm start), link frames, and the
+// collision-cost contribution of this step added to R.cost_c (mjx_planner.py:287-296).
+KFN void step_forward(Warp& W, const KModel& m, WarpSmem& S, const StepIO& io) {
   // ---- P1: serial joint chain (uniform) ----
   {
     float pq[4] = {m.base_quat[0], m.base_quat[1], m.base_quat[2], m.base_quat[3]};
     float pp[3] = {m.base_pos[0], m.base_pos[1], m.base_pos[2]}, pm[9];
     quat_to_mat(pm, pq);
     USYNC();
+#pragma unroll 1
     for (int i = 0; i < KM_NL; ++i) {
       float p[3], q[4], t[3], qj[4], mat[9];
       mat_vec(t, pm, m.l_pos[i]); add3(p, pp, t);
       quat_mul(q, pq, m.l_quat[i]);
-      float ang = 0.5f * S.qpos[i], sn, cs;
-      sincosf(ang, &sn, &cs);
+      float sn, cs;
+      k_sincos(0.5f * S.qpos[i], &sn, &cs);
       qj[0] = cs; qj[1] = sn * m.l_axis[i][0]; qj[2] = sn * m.l_axis[i][1]; qj[3] = sn * m.l_axis[i][2];
       quat_mul(q, q, qj);
       quat_to_mat(mat, q);
@@ -580,7 +696,6 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmem& S) {
       sub3(d, com, m.refpt);
       const float* I = m.l_inertia[i]; const float* Rm = S.lmat[i];
       float ms = I[6];
-      // T = R I R^T, I symmetric (xx yy zz xy xz yz)
       float RI[9];
       for (int r = 0; r < 3; ++r) {
         RI[3 * r + 0] = Rm[3 * r] * I[0] + Rm[3 * r + 1] * I[3] + Rm[3 * r + 2] * I[4];
@@ -660,7 +775,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmem& S) {
       else {
         float Iw[3] = {m.fb_inertia[0] * w[0], m.fb_inertia[1] * w[1], m.fb_inertia[2] * w[2]}, g[3];
         cross3(g, w, Iw);
-        S.fs[lane] = -g[k - 3] - m.fb_damping * S.qvel[lane];
+        S.fs[lane] = -(k == 3 ? g[0] : (k == 4 ? g[1] : g[2])) - m.fb_damping * S.qvel[lane];
       }
     }
   END_LANES
@@ -687,51 +802,50 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmem& S) {
       for (int k = 0; k < 3; ++k) { S.as[KM_NL + k] = S.fs[KM_NL + k] / m.fb_mass; S.as[KM_NL + 3 + k] = S.fs[KM_NL + 3 + k] / m.fb_inertia[k]; }
     } END_UNIFORM_WRITE
   }
-  // ---- N1: narrow phase, distances only ----
+  // ---- N1: narrow phase (distances only) + collision cost of this step ----
   LANES(W, R)
-    R.nact = 0; R.actmask = 0;
-#pragma unroll
+    int nact = 0, actmask = 0;
+    float cc = 0.f;
+#pragma unroll 1
     for (int p = 0; p < KM_NPASS; ++p) {
       const int e = p * 32 + lane;
       const int ty = m.rp_type[e];
-      Contact2 c; c.dist[0] = 1.f; c.dist[1] = 1.f;
+      if (ty == KP_NONE) continue;
+      const int a = m.rp_a[e], b = m.rp_b[e];
+      float d0, d1 = 1.f;
       if (ty == KP_CAP_BOX) {
-        const int a = m.rp_a[e], b = m.rp_b[e];
-        if (b < m.nsbox) capsule_box<false>(S.capA[a], S.capB[a], m.cap_r[a], m.sb_pos[b], m.sb_mat[b], m.sb_size[b], c);
-        else capsule_box<false>(S.capA[a], S.capB[a], m.cap_r[a], S.qpos + KM_NL, S.bmat, m.fb_size, c);
+        const bool st = b < m.nsbox;
+        Dist2 d = capsule_box_dist(S.capA[a], S.capB[a], m.cap_r[a], st ? m.sb_pos[b] : S.qpos + KM_NL, st ? m.sb_mat[b] : S.bmat,
+                                   st ? m.sb_size[b] : m.fb_size);
+        d0 = d.d0; d1 = d.d1;
       } else if (ty == KP_CAP_CAP) {
-        const int a = m.rp_a[e], b = m.rp_b[e];
+        Contact2 c;
         capsule_capsule<false>(S.capA[a], S.capB[a], m.cap_r[a], S.capA[b], S.capB[b], m.cap_r[b], c);
-      } else if (ty == KP_PLANE_CAP) {
-        const int b = m.rp_b[e];
-        plane_capsule<false>(m.plane_pos, m.plane_n, S.capA[b], S.capB[b], m.cap_r[b], c);
-      }
-      R.curd[p][0] = c.dist[0]; R.curd[p][1] = c.dist[1];
-      if (ty != KP_NONE) {
-        if (c.dist[0] < 0.f) { R.nact++; R.actmask |= 1 << (2 * p); }
-        if (ty != KP_CAP_CAP && c.dist[1] < 0.f) { R.nact++; R.actmask |= 1 << (2 * p + 1); }
-      }
-    }
-    // free-box pairs: full contact generation into the staging area (rarely past the sphere test)
-    if (m.has_box && lane < m.nbpair) {
-      const int ty = m.bp_type[lane], a = m.bp_a[lane];
-      const float* bp = S.qpos + KM_NL;
-      const float rb = sqrtf(m.fb_size[0] * m.fb_size[0] + m.fb_size[1] * m.fb_size[1] + m.fb_size[2] * m.fb_size[2]);
-      int n = 0;
-      for (int k = 0; k < 4; ++k) S.bstage[lane][k][3] = 1.f;
-      if (ty == KB_PLANE_BOX) {
-        float t[3]; sub3(t, bp, m.plane_pos);
-        if (dot3(t, m.plane_n) < rb) { n = plane_box(m.plane_pos, m.plane_n, bp, S.bmat, m.fb_size, S.bstage[lane]); copy3(S.bnrm[lane], m.plane_n); }
+        d0 = c.dist[0];
       } else {
-        float t[3]; sub3(t, bp, m.sb_pos[a]);
-        const float ra = sqrtf(m.sb_size[a][0] * m.sb_size[a][0] + m.sb_size[a][1] * m.sb_size[a][1] + m.sb_size[a][2] * m.sb_size[a][2]);
-        if (dot3(t, t) < (ra + rb) * (ra + rb)) {
-          if (ty == KB_BOX_BOX) n = box_box(m.sb_pos[a], m.sb_mat[a], m.sb_size[a], bp, S.bmat, m.fb_size, S.bstage[lane], S.bnrm[lane]);
-          else n = box_box(bp, S.bmat, m.fb_size, m.sb_pos[a], m.sb_mat[a], m.sb_size[a], S.bstage[lane], S.bnrm[lane]);
-        }
+        Contact2 c;
+        plane_capsule<false>(m.plane_pos, m.plane_n, S.capA[b], S.capB[b], m.cap_r[b], c);
+        d0 = c.dist[0]; d1 = c.dist[1];
       }
-      R.nact += n;
+      const int ns = ty == KP_CAP_CAP ? 1 : 2;
+      // cost_c (mjx_planner.py:287-296): sum max(0, (1-y) c_t - c_{t+1}) + #(c < 0), y = 0.005
+      if (d0 < 0.f) { ++nact; actmask |= 1 << (2 * p); cc += 1.f; }
+      if (!io.first) cc += fmaxf((1.f - 0.005f) * S.prevd[2 * p][lane] - d0, 0.f);
+      S.prevd[2 * p][lane] = d0;
+      if (ns == 2) {
+        if (d1 < 0.f) { ++nact; actmask |= 1 << (2 * p + 1); cc += 1.f; }
+        if (!io.first) cc += fmaxf((1.f - 0.005f) * S.prevd[2 * p + 1][lane] - d1, 0.f);
+        S.prevd[2 * p + 1][lane] = d1;
+      }
+      if (io.collision_row) {
+        io.collision_row[m.rp_slot[e]] = d0;
+        if (ns == 2) io.collision_row[m.rp_slot[e] + 1] = d1;
+      }
     }
+    R.cost_c += cc;
+    R.actmask = actmask;
+    if (m.has_box && lane < m.nbpair) nact += box_pair_contacts(m, S, lane);
+    R.nact = nact;
   END_LANES
   const int ncon_all = warp_excl_scan(W, [](int, LaneRegs& R) { return R.nact; }, [](int, LaneRegs& R, int o) { R.off = o; });
   const int ncon = ncon_all < NCMAX ? ncon_all : NCMAX;
@@ -739,51 +853,11 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmem& S) {
   LANES(W, R)
     if (R.nact > 0) {
       int o = R.off;
-      // t1 == nullptr: MJX make_frame tangents; plane-capsule supplies its own first tangent
-      auto emit = [&](const float* pos, const float* n, const float* t1, float dist, float invw, int l1, int l2) {
-        if (o < NCMAX) {
-          float* g = S.cgeo[o];
-          copy3(g, pos); copy3(g + 3, n);
-          if (t1) { copy3(g + 6, t1); cross3(g + 9, n, t1); }
-          else make_tangents(n, g + 6, g + 9);
-          g[12] = dist; g[13] = invw; g[14] = (float)l1; g[15] = (float)l2;
-        }
-        ++o;
-      };
-#pragma unroll
-      for (int p = 0; p < KM_NPASS; ++p) {
-        if (!((R.actmask >> (2 * p)) & 3)) continue;
-        const int e = p * 32 + lane, ty = m.rp_type[e], a = m.rp_a[e], b = m.rp_b[e];
-        Contact2 c;
-        float invw; int l1, l2;
-        float pt1[3]; const float* t1 = nullptr;
-        if (ty == KP_CAP_BOX) {
-          if (b < m.nsbox) { capsule_box<true>(S.capA[a], S.capB[a], m.cap_r[a], m.sb_pos[b], m.sb_mat[b], m.sb_size[b], c); invw = m.cap_invw[a]; l2 = -1; }
-          else { capsule_box<true>(S.capA[a], S.capB[a], m.cap_r[a], S.qpos + KM_NL, S.bmat, m.fb_size, c); invw = m.cap_invw[a] + m.fb_invw; l2 = KM_NL; }
-          l1 = m.cap_link[a];
-        } else if (ty == KP_CAP_CAP) {
-          capsule_capsule<true>(S.capA[a], S.capB[a], m.cap_r[a], S.capA[b], S.capB[b], m.cap_r[b], c);
-          invw = m.cap_invw[a] + m.cap_invw[b]; l1 = m.cap_link[a]; l2 = m.cap_link[b];
-        } else {
-          plane_capsule<true>(m.plane_pos, m.plane_n, S.capA[b], S.capB[b], m.cap_r[b], c);
-          invw = m.cap_invw[b]; l1 = -1; l2 = m.cap_link[b];
-          // MJX plane_capsule: first tangent = capsule axis projected on the plane
-          float ax[3];
-          sub3(ax, S.capB[b], S.capA[b]); normalize3(ax);
-          madd3(pt1, ax, m.plane_n, -dot3(m.plane_n, ax));
-          if (normalize3(pt1) < 0.5f) {
-            pt1[0] = 0.f;
-            if (m.plane_n[1] > -0.5f && m.plane_n[1] < 0.5f) { pt1[1] = 1.f; pt1[2] = 0.f; } else { pt1[1] = 0.f; pt1[2] = 1.f; }
-          }
-          t1 = pt1;
-        }
-        if ((R.actmask >> (2 * p)) & 1) emit(c.pos[0], c.nrm[0], t1, c.dist[0], invw, l1, l2);
-        if ((R.actmask >> (2 * p + 1)) & 1) emit(c.pos[1], c.nrm[1], t1, c.dist[1], invw, l1, l2);
+      if (R.actmask) {
+        emit_robot_contacts(m, S, lane, R.actmask, o);
+        o += KPOPC((unsigned)R.actmask);
       }
-      if (m.has_box && lane < m.nbpair) {
-        const bool sw = m.bp_type[lane] == KB_BOX_BOX_SWAP;
-        for (int k = 0; k < 4; ++k) if (S.bstage[lane][k][3] < 0.f) emit(S.bstage[lane][k], S.bnrm[lane], nullptr, S.bstage[lane][k][3], m.fb_invw, sw ? KM_NL : -1, sw ? -1 : KM_NL);
-      }
+      if (m.has_box && lane < m.nbpair) emit_box_contacts(m, S, lane, o);
     }
   END_LANES
   // ---- C1: joint-limit rows ----
@@ -818,6 +892,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmem& S) {
   LANES(W, R)
     const int d = lane & 15;
     if (d < KM_NV) {
+#pragma unroll 1
       for (int c = lane >> 4; c < ncon; c += 2) {
         const float* g = S.cgeo[c];
         float c1[3], c2[3], df[3];
@@ -830,24 +905,23 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmem& S) {
       }
     }
   END_LANES
-  // ---- C3: contact row parameters (4 pyramid edges share pos and D) ----
+  // ---- C3: contact row parameters (the 4 pyramid edges share pos and D) ----
   LANES(W, R)
-    for (int c = lane; c < ncon; c += 32) {
-      const float* g = S.cgeo[c];
+#pragma unroll 1
+    for (int r = nlim + lane; r < nrow; r += 32) {
+      const float* g = S.cgeo[(r - nlim) >> 2];
       float w = g[13];
       w = w + m.mu * m.mu * w;
       w = w * 2.f * m.mu * m.mu / m.impratio;
-      for (int q = 0; q < 4; ++q) {
-        const int r = nlim + 4 * c + q;
-        float vel = row_dot(S, r, S.qvel), D, aref;
-        row_params(m, g[12], w, vel, D, aref);
-        S.rD[r] = D; S.rAref[r] = aref;
-      }
+      float vel = row_dot(S, r, S.qvel), D, aref;
+      row_params(m, g[12], w, vel, D, aref);
+      S.rD[r] = D; S.rAref[r] = aref;
     }
   END_LANES
   // ---- S1: warm start vs smooth start (B.6) ----
   LANES(W, R)
     float cw = 0.f, cs = 0.f;
+#pragma unroll 1
     for (int r = lane; r < nrow; r += 32) {
       float jw = row_dot(S, r, S.warm) - S.rAref[r], js = row_dot(S, r, S.as) - S.rAref[r];
       S.rJaref[r] = jw; S.rJs[r] = js;
@@ -885,14 +959,17 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmem& S) {
   LANES(W, R)
     if (lane < KM_NV) {
       float fc = 0.f;
+#pragma unroll 1
       for (int r = 0; r < nrow; ++r) { float ja = S.rJaref[r]; if (ja < 0.f) fc += row_J(S, r, lane) * (-S.rD[r] * ja); }
       S.grad[lane] = S.Ma[lane] - S.fs[lane] - fc;
     }
+#pragma unroll 1
     for (int e = lane; e < KM_NV * (KM_NV + 1) / 2; e += 32) {
       int i = 0, j = e;
       while (j > i) { j -= i + 1; ++i; }
       float h = S.M[i][j];
       for (int r = 0; r < nlim; ++r) if (S.rJaref[r] < 0.f && S.limdof[r] == i && i == j) h += S.rD[r];
+#pragma unroll 1
       for (int c = 0; c < ncon; ++c) {
         const float* J = S.cJ[c];
         const int r0 = nlim + 4 * c;
@@ -904,7 +981,8 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmem& S) {
       S.H[i][j] = h;
     }
   END_LANES
-  // ---- S4: Cholesky of H (lower, in place), search = -H^-1 grad ----
+  // ---- S4: Cholesky of H (lower, in place), then search = -H^-1 grad with lane i owning row i ----
+#pragma unroll 1
   for (int j = 0; j < KM_NV; ++j) {
     USYNC();
     const float dj = sqrtf(S.H[j][j]);
@@ -914,6 +992,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmem& S) {
     END_LANES
     LANES(W, R)
       // trailing update H[i][k] -= L[i][j] L[k][j], j < k <= i
+#pragma unroll 1
       for (int e = lane; e < KM_NV * (KM_NV + 1) / 2; e += 32) {
         int i = 0, k = e;
         while (k > i) { k -= i + 1; ++i; }
@@ -921,15 +1000,28 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmem& S) {
       }
     END_LANES
   }
-  {
-    float y[KM_NV], x[KM_NV];
-    USYNC();
-#pragma unroll
-    for (int i = 0; i < KM_NV; ++i) { float s = S.grad[i]; for (int k = 0; k < i; ++k) s -= S.H[i][k] * y[k]; y[i] = s / S.H[i][i]; }
-#pragma unroll
-    for (int i = KM_NV - 1; i >= 0; --i) { float s = y[i]; for (int k = i + 1; k < KM_NV; ++k) s -= S.H[k][i] * x[k]; x[i] = s / S.H[i][i]; }
-    UNIFORM_WRITE(W) { for (int i = 0; i < KM_NV; ++i) S.search[i] = -x[i]; } END_UNIFORM_WRITE
+  LANES(W, R)
+    R.f0 = lane < KM_NV ? S.grad[lane] : 0.f;
+  END_LANES
+#pragma unroll 1
+  for (int k = 0; k < KM_NV; ++k) {            // forward substitution L y = grad
+    const float yk = warp_bcast(W, k, [&](int l, LaneRegs& R) { return R.f0 / S.H[l < KM_NV ? l : 0][l < KM_NV ? l : 0]; });
+    LANES(W, R)
+      if (lane == k) R.f0 = yk;
+      else if (lane > k && lane < KM_NV) R.f0 -= S.H[lane][k] * yk;
+    END_LANES
   }
+#pragma unroll 1
+  for (int k = KM_NV - 1; k >= 0; --k) {       // back substitution L^T x = y
+    const float xk = warp_bcast(W, k, [&](int l, LaneRegs& R) { return R.f0 / S.H[l < KM_NV ? l : 0][l < KM_NV ? l : 0]; });
+    LANES(W, R)
+      if (lane == k) R.f0 = xk;
+      else if (lane < k) R.f0 -= S.H[k][lane] * xk;
+    END_LANES
+  }
+  LANES(W, R)
+    if (lane < KM_NV) S.search[lane] = -R.f0;
+  END_LANES
   // ---- S5: line search (BD.10) ----
   LANES(W, R)
     R.f0 = R.f1 = R.f2 = 0.f;
@@ -940,6 +1032,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmem& S) {
       float s = S.search[lane];
       R.f0 = s * s; R.f1 = s * S.Ma[lane] - s * S.fs[lane]; R.f2 = 0.5f * s * mv;
     }
+#pragma unroll 1
     for (int r = lane; r < nrow; r += 32) S.rJv[r] = row_dot(S, r, S.search);
   END_LANES
   float qg[3];
@@ -948,19 +1041,54 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmem& S) {
   qg[1] = warp_sum(W, [](int, LaneRegs& R) { return R.f1; });
   qg[2] = warp_sum(W, [](int, LaneRegs& R) { return R.f2; });
   const float gtol = m.tolerance * m.ls_tolerance * snorm * m.meaninertia * (float)KM_NV;
+  // One rolled loop evaluates the piecewise quadratic at three step sizes per trip:
+  //   trip -2: p0 = point(0); trip -1: lo = point(-p0.d0/p0.d1); trips 0..ls_iterations-1: MJX bracket update.
   LSPoint p0, lo, hi;
-  { float a0 = 0.f; ls_eval(W, S, qg, 1, &a0, &p0); }
-  { float a1 = p0.alpha - p0.d0 / p0.d1; ls_eval(W, S, qg, 1, &a1, &lo); }
-  if (lo.d0 < p0.d0) { hi = p0; } else { hi = lo; lo = p0; }
+  p0.alpha = p0.cost = p0.d0 = 0.f; p0.d1 = 1.f; lo = p0; hi = p0;
   bool swapped = true;
-  for (int it = 0; it < m.ls_iterations; ++it) {
-    bool done = !swapped;
-    done = done || ((lo.d0 < 0.f) && (lo.d0 > -gtol));
-    done = done || ((hi.d0 > 0.f) && (hi.d0 < gtol));
-    if (done) break;
-    float al[3] = {lo.alpha - lo.d0 / lo.d1, hi.alpha - hi.d0 / hi.d1, 0.5f * (lo.alpha + hi.alpha)};
+#pragma unroll 1
+  for (int it = -2; it < m.ls_iterations; ++it) {
+    float al0, al1, al2;
+    if (it == -2) { al0 = al1 = al2 = 0.f; }
+    else if (it == -1) { al0 = al1 = al2 = p0.alpha - p0.d0 / p0.d1; }
+    else {
+      bool done = !swapped;
+      done = done || ((lo.d0 < 0.f) && (lo.d0 > -gtol));
+      done = done || ((hi.d0 > 0.f) && (hi.d0 < gtol));
+      if (done) break;
+      al0 = lo.alpha - lo.d0 / lo.d1; al1 = hi.alpha - hi.d0 / hi.d1; al2 = 0.5f * (lo.alpha + hi.alpha);
+    }
+    LANES(W, R)
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+#pragma unroll 1
+      for (int r = lane; r < nrow; r += 32) {
+        const float ja = S.rJaref[r], jv = S.rJv[r], D = S.rD[r];
+        const float q0 = 0.5f * D * ja * ja, q1 = D * jv * ja, q2 = 0.5f * D * jv * jv;
+        if (ja + al0 * jv < 0.f) { a0 += q0; a1 += q1; a2 += q2; }
+        if (ja + al1 * jv < 0.f) { b0 += q0; b1 += q1; b2 += q2; }
+        if (ja + al2 * jv < 0.f) { c0 += q0; c1 += q1; c2 += q2; }
+      }
+      R.acc[0] = a0; R.acc[1] = a1; R.acc[2] = a2; R.acc[3] = b0; R.acc[4] = b1; R.acc[5] = b2; R.acc[6] = c0; R.acc[7] = c1; R.acc[8] = c2;
+    END_LANES
     LSPoint pt[3];
-    ls_eval(W, S, qg, 3, al, pt);
+    const float als[3] = {al0, al1, al2};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (it < 0 && k > 0) { pt[k] = pt[0]; continue; }
+      const float q0 = qg[0] + warp_sum(W, [&](int, LaneRegs& R) { return R.acc[3 * k]; });
+      const float q1 = qg[1] + warp_sum(W, [&](int, LaneRegs& R) { return R.acc[3 * k + 1]; });
+      const float q2 = qg[2] + warp_sum(W, [&](int, LaneRegs& R) { return R.acc[3 * k + 2]; });
+      const float a = als[k];
+      pt[k].alpha = a;
+      pt[k].cost = a * a * q2 + a * q1 + q0;
+      pt[k].d0 = 2.f * a * q2 + q1;
+      pt[k].d1 = 2.f * q2 + (q2 == 0.f ? MJ_MINVAL : 0.f);
+    }
+    if (it == -2) { p0 = pt[0]; continue; }
+    if (it == -1) {
+      if (pt[0].d0 < p0.d0) { lo = pt[0]; hi = p0; } else { hi = pt[0]; lo = p0; }
+      continue;
+    }
     const LSPoint lo_next = pt[0], hi_next = pt[1], mid = pt[2];
     bool s1 = in_bracket(lo, lo_next); if (s1) lo = lo_next;
     bool s2 = in_bracket(lo, mid);     if (s2) lo = mid;
@@ -970,7 +1098,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmem& S) {
     bool s6 = in_bracket(hi, lo_next); if (s6) hi = lo_next;
     swapped = s1 || s2 || s3 || s4 || s5 || s6;
 #ifdef CEMK_EMU_DEBUG
-    printf("[emu]  it %d cand %.7g %.7g %.7g -> lo a %.7g d0 %.5g  hi a %.7g d0 %.5g swaps %d%d%d%d%d%d\n", it, al[0], al[1], al[2], lo.alpha, lo.d0, hi.alpha, hi.d0, s1, s2, s3, s4, s5, s6);
+    printf("[emu]  it %d cand %.7g %.7g %.7g -> lo a %.7g d0 %.5g  hi a %.7g d0 %.5g swaps %d%d%d%d%d%d\n", it, al0, al1, al2, lo.alpha, lo.d0, hi.alpha, hi.d0, s1, s2, s3, s4, s5, s6);
 #endif
   }
   const bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
@@ -998,8 +1126,8 @@ KFN void step_euler(Warp& W, const KModel& m, WarpSmem& S) {
   LANES(W, R)
     if (lane == 0 && m.has_box) {
       float v[3] = {S.qvel[KM_NL + 3], S.qvel[KM_NL + 4], S.qvel[KM_NL + 5]};
-      float nrm = normalize3(v), ang = 0.5f * m.dt * nrm, sn, cs;
-      sincosf(ang, &sn, &cs);
+      float nrm = normalize3(v), sn, cs;
+      k_sincos(0.5f * m.dt * nrm, &sn, &cs);
       float qr[4] = {cs, sn * v[0], sn * v[1], sn * v[2]}, qn[4];
       float* q = S.qpos + KM_NL + 3;
       quat_mul(qn, q, qr);
@@ -1012,6 +1140,7 @@ KFN void step_euler(Warp& W, const KModel& m, WarpSmem& S) {
 // ------------------------------------------------------------------------------------------ rollout + cost
 struct RolloutArgs {
   int T;
+  bool live;                  // false: padding warp of the last CTA (computes, writes nothing)
   const float* thetadot;      // this sample's [NL][T]
   const float* q0; const float* v0;
   const float* target_pos; const float* target_rot;     // uniform target (compute_cem tiles it, :380-381)
@@ -1042,12 +1171,17 @@ KFN void rollout_sample(Warp& W, const KModel& m, WarpSmem& S, const RolloutArgs
     tq[0] *= inv; tq[1] *= inv; tq[2] *= inv; tq[3] *= inv;
   }
   float cost_g = 0.f, cost_r = 0.f;
+#pragma unroll 1
   for (int t = 0; t < A.T; ++t) {
+    STEP_ALIGN();
     LANES(W, R)
       if (lane < KM_NL) S.qvel[lane] = A.thetadot[lane * A.T + t];       // mjx_planner.py:254
     END_LANES
-    step_forward(W, m, S);
-    // pre-step observations (mjx_planner.py:259-261) and running cost (:277-296)
+    StepIO io;
+    io.first = t == 0;
+    io.collision_row = (A.collision && A.live) ? A.collision + (size_t)t * m.nslot_robot : nullptr;
+    step_forward(W, m, S, io);
+    // pre-step observations (mjx_planner.py:259-261) and running cost (:277-285)
     {
       float tcp[3], tv[3], eq[4];
       USYNC();
@@ -1059,33 +1193,22 @@ KFN void rollout_sample(Warp& W, const KModel& m, WarpSmem& S, const RolloutArgs
       float dp = fabsf((eq[0] * tq[0] + eq[1] * tq[1] + eq[2] * tq[2] + eq[3] * tq[3]) * inv);
       dp = fminf(fmaxf(dp, -1.f), 1.f);
       cost_r += 2.f * acosf(dp);
-      LANES(W, R)
-        if (A.eef_pos && lane < 3) A.eef_pos[t * 3 + lane] = tcp[lane];
-        if (A.eef_rot && lane < 4) A.eef_rot[t * 4 + lane] = eq[lane];
-        if (A.qacc_dbg && lane < KM_NV) A.qacc_dbg[t * KM_NV + lane] = S.qacc[lane];
-#pragma unroll
-        for (int p = 0; p < KM_NPASS; ++p) {
-          const int e = p * 32 + lane, ty = m.rp_type[e];
-          if (ty == KP_NONE) continue;
-          const int ns = ty == KP_CAP_CAP ? 1 : 2;
-          for (int k = 0; k < ns; ++k) {
-            float c = R.curd[p][k];
-            if (c < 0.f) R.cost_c += 1.f;
-            if (t > 0) R.cost_c += fmaxf((1.f - 0.005f) * R.prevd[p][k] - c, 0.f);
-            R.prevd[p][k] = c;
-            if (A.collision) A.collision[(size_t)t * m.nslot_robot + m.rp_slot[e] + k] = c;
-          }
-        }
-      END_LANES
+      if (A.live && (A.eef_pos || A.eef_rot || A.qacc_dbg)) {
+        LANES(W, R)
+          if (A.eef_pos && lane < 3) A.eef_pos[t * 3 + lane] = lane == 0 ? tcp[0] : (lane == 1 ? tcp[1] : tcp[2]);
+          if (A.eef_rot && lane < 4) A.eef_rot[t * 4 + lane] = lane == 0 ? eq[0] : (lane == 1 ? eq[1] : (lane == 2 ? eq[2] : eq[3]));
+          if (A.qacc_dbg && lane < KM_NV) A.qacc_dbg[t * KM_NV + lane] = S.qacc[lane];
+        END_LANES
+      }
     }
     step_euler(W, m, S);
     LANES(W, R)
-      if (lane < KM_NL) A.theta[lane * A.T + t] = S.qpos[lane];
+      if (A.live && lane < KM_NL) A.theta[lane * A.T + t] = S.qpos[lane];
     END_LANES
   }
   const float cost_c = warp_sum(W, [](int, LaneRegs& R) { return R.cost_c; });
   LANES(W, R)
-    if (lane == 0) {
+    if (lane == 0 && A.live) {
       A.cost4[0] = A.w_pos * cost_g + A.w_rot * cost_r + A.w_col * cost_c;
       A.cost4[1] = cost_g; A.cost4[2] = cost_r; A.cost4[3] = cost_c;
       if (A.flags) *A.flags = S.flags;

@@ -19,20 +19,30 @@
 #ifdef CEMK_EMU
 #include <cstring>
 #define KFN static inline
+#define KNOINLINE static
+#define STEP_ALIGN()
 #define LANES(W, R) for (int lane = 0; lane < 32; ++lane) { auto& R = (W).regs[lane]; (void)R;
 #define END_LANES }
 #define UNIFORM_WRITE(W) if (true)
 #define END_UNIFORM_WRITE
 #define USYNC()
 #define KRSQRT(x) (1.0f / sqrtf(x))
+#define KPOPC(x) __builtin_popcount(x)
 #else
 #define KFN __device__ __forceinline__
+#define KNOINLINE __device__ __noinline__
+#ifdef CEMK_STEP_SYNC
+#define STEP_ALIGN() __syncthreads()     // keep the warps of a CTA on the same code (instruction-cache locality)
+#else
+#define STEP_ALIGN()
+#endif
 #define LANES(W, R) { __syncwarp(); const int lane = (W).lane; auto& R = (W).regs; (void)R;
 #define END_LANES } __syncwarp();
 #define UNIFORM_WRITE(W) __syncwarp(); if ((W).lane == 0)
 #define END_UNIFORM_WRITE __syncwarp();
 #define USYNC() __syncwarp()
 #define KRSQRT(x) rsqrtf(x)
+#define KPOPC(x) __popc(x)
 #endif
 
 template <class LR>
@@ -74,5 +84,15 @@ KFN int warp_excl_scan(W& w, G get, S set) {
   for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (w.lane >= o) inc += t; }
   set(w.lane, w.regs, inc - v);
   return __shfl_sync(0xffffffffu, inc, 31);
+#endif
+}
+
+// value of f(src, regs[src]) broadcast to every lane
+template <class W, class F>
+KFN float warp_bcast(W& w, int src, F f) {
+#ifdef CEMK_EMU
+  return f(src, w.regs[src]);
+#else
+  return __shfl_sync(0xffffffffu, f(w.lane, w.regs), src);
 #endif
 }

@@ -25,6 +25,7 @@ extern "C" int emu_rollout(const KModel* m, int B, int T, const float* thetadot,
       memset((void*)S, 0, sizeof(WarpSmem));
       RolloutArgs A;
       A.T = T;
+      A.live = true;
       A.thetadot = thetadot + (size_t)s * KM_NL * T;
       A.q0 = q0; A.v0 = v0; A.target_pos = tpos; A.target_rot = trot;
       A.w_pos = w_pos; A.w_rot = w_rot; A.w_col = w_col;
