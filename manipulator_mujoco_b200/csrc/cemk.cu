@@ -18,7 +18,12 @@
 
 #define NVAR 66
 #define NCOEF 11
-#define ROLLOUT_WARPS 4
+#ifndef ROLLOUT_WARPS
+#define ROLLOUT_WARPS 16      // samples (warps) per CTA; they step in lockstep (STEP_ALIGN) to share the instruction cache
+#endif
+#ifndef ROLLOUT_MINB
+#define ROLLOUT_MINB 1
+#endif
 
 static thread_local char g_err[256] = "";
 static int set_err(int code, const char* msg) { snprintf(g_err, sizeof g_err, "%s", msg); return code; }
@@ -35,6 +40,7 @@ struct cemk_handle {
   float* d_G;      // [3][T][11]
   float* d_K;      // Kpp[121] Kpe[55] N[121] bounds[3]
   long long launches;
+  int* d_flags; int flags_cap;   // per-sample overflow flags when the caller passes none
 };
 
 // ---------------------------------------------------------------------------------------------- rollout
@@ -45,18 +51,25 @@ struct RolloutBatch {
   float* theta; float* cost4; float* eef_pos; float* eef_rot; float* collision; float* qacc; int* flags;
 };
 
-__global__ void __launch_bounds__(ROLLOUT_WARPS * 32) k_rollout(const KModel* __restrict__ gm, RolloutBatch a) {
+// NC = capacity of the per-sample active-contact list, WARPS = samples per CTA.  The fast
+// instantiation (NC = 16) covers every sample; samples that ever needed more contacts set flag bit 0
+// and are recomputed from scratch by the big instantiation (NC = 48, one warp per CTA, ONLY_FLAGGED).
+template <int NC, int WARPS, bool ONLY_FLAGGED>
+__global__ void __launch_bounds__(WARPS * 32, ROLLOUT_MINB) k_rollout(const KModel* __restrict__ gm, RolloutBatch a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   KModel* sm = reinterpret_cast<KModel*>(smem_raw);
-  WarpSmem* ws = reinterpret_cast<WarpSmem*>(smem_raw + ((sizeof(KModel) + 15) & ~size_t(15)));
+  WarpSmemT<NC>* ws = reinterpret_cast<WarpSmemT<NC>*>(smem_raw + ((sizeof(KModel) + 15) & ~size_t(15)));
+  const int warp = threadIdx.x >> 5;
+  int s = blockIdx.x * WARPS + warp;
+  if (ONLY_FLAGGED) {
+    if (s >= a.B || !(a.flags[s] & 1)) return;            // WARPS == 1: the whole CTA leaves together
+  }
   {
     const int* src = reinterpret_cast<const int*>(gm);
     int* dst = reinterpret_cast<int*>(sm);
     for (int i = threadIdx.x; i < (int)(sizeof(KModel) / 4); i += blockDim.x) dst[i] = src[i];
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5;
-  int s = blockIdx.x * ROLLOUT_WARPS + warp;
   const bool live = s < a.B;
   if (!live) {
 #ifdef CEMK_STEP_SYNC
@@ -80,9 +93,11 @@ __global__ void __launch_bounds__(ROLLOUT_WARPS * 32) k_rollout(const KModel* __
   A.eef_rot = a.eef_rot ? a.eef_rot + (size_t)s * a.T * 4 : nullptr;
   A.collision = a.collision ? a.collision + (size_t)s * a.T * sm->nslot_robot : nullptr;
   A.qacc_dbg = a.qacc ? a.qacc + (size_t)s * a.T * KM_NV : nullptr;
-  A.flags = a.flags ? a.flags + s : nullptr;
-  rollout_sample(W, *sm, ws[warp], A);
+  A.flags = a.flags + s;
+  rollout_sample<NC>(W, *sm, ws[warp], A);
 }
+template <int NC, int WARPS>
+static size_t rollout_smem() { return ((sizeof(KModel) + 15) & ~size_t(15)) + WARPS * sizeof(WarpSmemT<NC>); }
 
 // ---------------------------------------------------------------------------------------------- sampling
 // L = chol(cov + 0.003 I), lower, row-major [66][66]; one CTA.
@@ -348,19 +363,21 @@ int cemk_create(const void* kmodel, int kmodel_bytes, int device, cemk_handle** 
     return set_err(CEMK_ERR_MODEL, "cemk_create: unsupported topology");
   CK(cudaSetDevice(device));
   cemk_handle* h = new cemk_handle();
-  h->device = device; h->T = 0; h->d_G = nullptr; h->d_K = nullptr; h->launches = 0;
+  h->device = device; h->T = 0; h->d_G = nullptr; h->d_K = nullptr; h->launches = 0; h->d_flags = nullptr; h->flags_cap = 0;
   CK(cudaMalloc(&h->d_model, sizeof(KModel)));
   CK(cudaMemcpy(h->d_model, kmodel, sizeof(KModel), cudaMemcpyHostToDevice));
   CK(cudaMalloc(&h->d_K, 300 * sizeof(float)));
-  const size_t smem = ((sizeof(KModel) + 15) & ~size_t(15)) + ROLLOUT_WARPS * sizeof(WarpSmem);
-  CK(cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(k_rollout<KM_NC_FAST, ROLLOUT_WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)rollout_smem<KM_NC_FAST, ROLLOUT_WARPS>()));
+  CK(cudaFuncSetAttribute(k_rollout<KM_NC_BIG, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)rollout_smem<KM_NC_BIG, 1>()));
   *out = h;
   return CEMK_OK;
 }
 int cemk_destroy(cemk_handle* h) {
   if (!h) return CEMK_OK;
   cudaSetDevice(h->device);
-  cudaFree(h->d_model); cudaFree(h->d_G); cudaFree(h->d_K);
+  cudaFree(h->d_model); cudaFree(h->d_G); cudaFree(h->d_K); cudaFree(h->d_flags);
   delete h;
   return CEMK_OK;
 }
@@ -412,13 +429,25 @@ int cemk_rollout_cost(cemk_handle* h, int B, int T, const float* thetadot, const
                       float* eef_rot, float* collision, float* qacc, int* flags, void* stream) {
   if (!h || !thetadot || !q0 || !v0 || !target_pos || !target_rot || !theta || !cost4 || B <= 0 || T <= 0)
     return set_err(CEMK_ERR_ARG, "cemk_rollout_cost: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!flags) {
+    if (h->flags_cap < B) {
+      CK(cudaSetDevice(h->device));
+      if (h->d_flags) CK(cudaFree(h->d_flags));
+      CK(cudaMalloc(&h->d_flags, sizeof(int) * B));
+      h->flags_cap = B;
+    }
+    flags = h->d_flags;
+  }
   RolloutBatch a;
   a.B = B; a.T = T; a.thetadot = thetadot; a.q0 = q0; a.v0 = v0; a.target_pos = target_pos; a.target_rot = target_rot;
   a.w_pos = w_pos; a.w_rot = w_rot; a.w_col = w_col;
   a.theta = theta; a.cost4 = cost4; a.eef_pos = eef_pos; a.eef_rot = eef_rot; a.collision = collision; a.qacc = qacc; a.flags = flags;
-  const size_t smem = ((sizeof(KModel) + 15) & ~size_t(15)) + ROLLOUT_WARPS * sizeof(WarpSmem);
-  k_rollout<<<(B + ROLLOUT_WARPS - 1) / ROLLOUT_WARPS, ROLLOUT_WARPS * 32, smem, (cudaStream_t)stream>>>(h->d_model, a);
-  h->launches += 1;
+  k_rollout<KM_NC_FAST, ROLLOUT_WARPS, false><<<(B + ROLLOUT_WARPS - 1) / ROLLOUT_WARPS, ROLLOUT_WARPS * 32,
+                                                rollout_smem<KM_NC_FAST, ROLLOUT_WARPS>(), st>>>(h->d_model, a);
+  // samples whose active-contact list overflowed the fast capacity are recomputed with the big one
+  k_rollout<KM_NC_BIG, 1, true><<<B, 32, rollout_smem<KM_NC_BIG, 1>(), st>>>(h->d_model, a);
+  h->launches += 2;
   CK(cudaPeekAtLastError());
   return CEMK_OK;
 }

@@ -23,8 +23,8 @@
 #include "kmodel.h"
 #include "warp_dsl.h"
 
-#define NCMAX 32                          // max simultaneously active contacts per sample
-#define NROWMAX (KM_NL + 4 * NCMAX)
+#define KM_NC_FAST 24                     // active-contact capacity of the fast kernel
+#define KM_NC_BIG 48                      // capacity of the re-run kernel for samples that overflowed
 #define MJ_MINVAL 1e-15f
 #define MJ_MINIMP 0.0001f
 #define MJ_MAXIMP 0.9999f
@@ -33,26 +33,37 @@ struct LaneRegs {
   float cost_c;               // this lane's share of cost_c
   int nact, off;              // active contacts this lane will emit, and where
   int actmask;                // bit (2*pass + slot)
+  int tri;                    // three packed (i, j) pairs of the lower triangle this lane owns (4 bits each)
   float acc[9];               // line-search partial sums (compile-time indices only)
+  float h[KM_NV];             // row `lane` of the Newton Hessian / its Cholesky factor
   float f0, f1, f2;
 };
 
-struct WarpSmem {
+// Per-warp scratch in shared memory.  Two unions reuse space between phases that never overlap:
+// the spatial-dynamics arrays (P2-P5) vs the constraint rows (C1-S5), and the free-box contact
+// staging (N1-N2) vs the contact Jacobians (C2-S5).
+template <int NC>
+struct WarpSmemT {
+  static constexpr int NROW = KM_NL + 4 * NC;
   float qpos[16], qvel[12], warm[12];
   float lpos[KM_NL][4], lquat[KM_NL][4], lmat[KM_NL][12];
-  float cdof[KM_NL][8], cinert[KM_NL][12], crb[KM_NL][12];
-  float cvel[KM_NL][8], cdofdot[KM_NL][8], cfrc[KM_NL][8];
+  float cdof[KM_NL][8];
   float capA[KM_MAXCAP][4], capB[KM_MAXCAP][4];
   float bmat[12];
-  float M[KM_NV][KM_NV], H[KM_NV][KM_NV];
+  float Mr[KM_NL][KM_NL];             // robot block of the joint-space inertia (box block is constant, diagonal)
+  float H[KM_NV][KM_NV];
   float fs[12], as[12], qacc[12], Ma[12], grad[12], search[12], mv[12];
   int ncon, nrow, nlim, flags;
   float prevd[KM_NPASS * 2][32];      // previous-step distance of every lane's robot slots
-  float bstage[KM_MAXBPAIR][4][4];    // free-box pair candidates: pos3, dist
-  float bnrm[KM_MAXBPAIR][4];
-  float cgeo[NCMAX][16];              // pos3 n3 t1 3 t2 3 dist invw link1 link2
-  float cJ[NCMAX][36];                // Jn[12] Jt1[12] Jt2[12] (tangents pre-multiplied by mu)
-  float rD[NROWMAX], rAref[NROWMAX], rJaref[NROWMAX], rJv[NROWMAX], rJs[NROWMAX];
+  union {
+    struct { float cinert[KM_NL][12], crb[KM_NL][12], cvel[KM_NL][8], cdofdot[KM_NL][8], cfrc[KM_NL][8]; };
+    struct { float rD[NROW], rAref[NROW], rJaref[NROW], rJv[NROW], rJs[NROW]; };
+  };
+  float cgeo[NC][16];                 // pos3 n3 t1 3 t2 3 dist invw link1 link2
+  union {
+    float cJ[NC][36];                 // Jn[12] Jt1[12] Jt2[12] (tangents pre-multiplied by mu)
+    struct { float bstage[KM_MAXBPAIR][4][4], bnrm[KM_MAXBPAIR][4]; };   // free-box pair candidates: pos3, dist
+  };
   int limdof[KM_NL];
   float limsign[KM_NL];
 };
@@ -525,8 +536,21 @@ KFN void row_params(const KModel& m, float pos, float invw, float vel, float& D,
   D = 1.f / R;
   aref = -b * vel - k * imp * pos;
 }
+// (M v)[d] and M[i][j] with the constant diagonal free-box block
+template <int NC>
+KFN float mul_M(const KModel& m, const WarpSmemT<NC>& S, int d, const float* v) {
+  if (d < KM_NL) { float s = 0.f; for (int k = 0; k < KM_NL; ++k) s += S.Mr[d][k] * v[k]; return s; }
+  return (d < KM_NL + 3 ? m.fb_mass : (d == KM_NL + 3 ? m.fb_inertia[0] : (d == KM_NL + 4 ? m.fb_inertia[1] : m.fb_inertia[2]))) * v[d];
+}
+template <int NC>
+KFN float M_entry(const KModel& m, const WarpSmemT<NC>& S, int i, int j) {
+  if (i < KM_NL) return j < KM_NL ? S.Mr[i][j] : 0.f;
+  if (i != j) return 0.f;
+  return i < KM_NL + 3 ? m.fb_mass : (i == KM_NL + 3 ? m.fb_inertia[0] : (i == KM_NL + 4 ? m.fb_inertia[1] : m.fb_inertia[2]));
+}
 // translational Jacobian column of world point p on `link` (0..5 robot link, 6 free box, <0 static)
-KFN void jac_col(const KModel& m, const WarpSmem& S, const float* p, int link, int d, float* col) {
+template <int NC>
+KFN void jac_col(const KModel& m, const WarpSmemT<NC>& S, const float* p, int link, int d, float* col) {
   col[0] = col[1] = col[2] = 0.f;
   if (link < 0) return;
   if (d < KM_NL) {
@@ -546,7 +570,8 @@ KFN void jac_col(const KModel& m, const WarpSmem& S, const float* p, int link, i
   }
 }
 // J_r . v for constraint row r
-KFN float row_dot(const WarpSmem& S, int r, const float* v) {
+template <int NC>
+KFN float row_dot(const WarpSmemT<NC>& S, int r, const float* v) {
   if (r < S.nlim) return S.limsign[r] * v[S.limdof[r]];
   int c = (r - S.nlim) >> 2, q = (r - S.nlim) & 3;
   const float* Jn = S.cJ[c]; const float* Jt = S.cJ[c] + (q < 2 ? 12 : 24);
@@ -555,7 +580,8 @@ KFN float row_dot(const WarpSmem& S, int r, const float* v) {
   for (int d = 0; d < KM_NV; ++d) { sn += Jn[d] * v[d]; st += Jt[d] * v[d]; }
   return (q & 1) ? sn - st : sn + st;
 }
-KFN float row_J(const WarpSmem& S, int r, int d) {
+template <int NC>
+KFN float row_J(const WarpSmemT<NC>& S, int r, int d) {
   if (r < S.nlim) return S.limdof[r] == d ? S.limsign[r] : 0.f;
   int c = (r - S.nlim) >> 2, q = (r - S.nlim) & 3;
   float jn = S.cJ[c][d], jt = S.cJ[c][(q < 2 ? 12 : 24) + d];
@@ -568,7 +594,8 @@ KFN bool in_bracket(const LSPoint& x, const LSPoint& y) {
 }
 
 // emit the full contact records (position, frame) of one lane's active robot slots; rare path
-KNOINLINE void emit_robot_contacts(const KModel& m, WarpSmem& S, int lane, int actmask, int o) {
+template <int NC>
+KNOINLINE void emit_robot_contacts(const KModel& m, WarpSmemT<NC>& S, int lane, int actmask, int o) {
 #pragma unroll 1
   for (int p = 0; p < KM_NPASS; ++p) {
     const int bits = (actmask >> (2 * p)) & 3;
@@ -601,7 +628,7 @@ KNOINLINE void emit_robot_contacts(const KModel& m, WarpSmem& S, int lane, int a
 #pragma unroll 1
     for (int k = 0; k < 2; ++k) {
       if (!((bits >> k) & 1)) continue;
-      if (o < NCMAX) {
+      if (o < NC) {
         float* g = S.cgeo[o];
         copy3(g, c.pos[k]); copy3(g + 3, c.nrm[k]);
         if (own_t1) { copy3(g + 6, pt1); cross3(g + 9, c.nrm[k], pt1); }
@@ -613,7 +640,8 @@ KNOINLINE void emit_robot_contacts(const KModel& m, WarpSmem& S, int lane, int a
   }
 }
 // free-box pairs of one lane: full contact generation into the staging area; returns #active
-KNOINLINE int box_pair_contacts(const KModel& m, WarpSmem& S, int lane) {
+template <int NC>
+KNOINLINE int box_pair_contacts(const KModel& m, WarpSmemT<NC>& S, int lane) {
   const int ty = m.bp_type[lane], a = m.bp_a[lane];
   const float* bp = S.qpos + KM_NL;
   const float rb = sqrtf(m.fb_size[0] * m.fb_size[0] + m.fb_size[1] * m.fb_size[1] + m.fb_size[2] * m.fb_size[2]);
@@ -632,12 +660,13 @@ KNOINLINE int box_pair_contacts(const KModel& m, WarpSmem& S, int lane) {
   }
   return n;
 }
-KNOINLINE void emit_box_contacts(const KModel& m, WarpSmem& S, int lane, int o) {
+template <int NC>
+KNOINLINE void emit_box_contacts(const KModel& m, WarpSmemT<NC>& S, int lane, int o) {
   const bool sw = m.bp_type[lane] == KB_BOX_BOX_SWAP;
 #pragma unroll 1
   for (int k = 0; k < 4; ++k) {
     if (!(S.bstage[lane][k][3] < 0.f)) continue;
-    if (o < NCMAX) {
+    if (o < NC) {
       float* g = S.cgeo[o];
       copy3(g, S.bstage[lane][k]); copy3(g + 3, S.bnrm[lane]);
       make_tangents(S.bnrm[lane], g + 6, g + 9);
@@ -656,7 +685,8 @@ struct StepIO {
 // ------------------------------------------------------------------------------------------ one forward()
 // Inputs: S.qpos, S.qvel, S.warm.  Outputs: S.qacc (= new warm start), link frames, and the
 // collision-cost contribution of this step added to R.cost_c (mjx_planner.py:287-296).
-KFN void step_forward(Warp& W, const KModel& m, WarpSmem& S, const StepIO& io) {
+template <int NC>
+KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& io) {
   // ---- P1: serial joint chain (uniform) ----
   {
     float pq[4] = {m.base_quat[0], m.base_quat[1], m.base_quat[2], m.base_quat[3]};
@@ -751,7 +781,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmem& S, const StepIO& io) {
       mul_inert(buf, S.crb[i], S.cdof[i]);
       float v = dot6(S.cdof[j], buf);
       if (i == j) v += m.l_armature[i];
-      S.M[i][j] = v; S.M[j][i] = v;
+      S.Mr[i][j] = v; S.Mr[j][i] = v;
     } else if (lane >= 24 && lane < 24 + KM_NL) {
       const int i = lane - 24;
       float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, f[6], t[6], t2[6];
@@ -787,7 +817,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmem& S, const StepIO& io) {
     for (int i = 0; i < KM_NL; ++i) {
 #pragma unroll
       for (int j = 0; j <= i; ++j) {
-        float s = S.M[i][j];
+        float s = S.Mr[i][j];
 #pragma unroll
         for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
         L[i][j] = (i == j) ? sqrtf(s) : s / L[j][j];
@@ -844,20 +874,20 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmem& S, const StepIO& io) {
     }
     R.cost_c += cc;
     R.actmask = actmask;
-    if (m.has_box && lane < m.nbpair) nact += box_pair_contacts(m, S, lane);
+    if (m.has_box && lane < m.nbpair) nact += box_pair_contacts<NC>(m, S, lane);
     R.nact = nact;
   END_LANES
   const int ncon_all = warp_excl_scan(W, [](int, LaneRegs& R) { return R.nact; }, [](int, LaneRegs& R, int o) { R.off = o; });
-  const int ncon = ncon_all < NCMAX ? ncon_all : NCMAX;
+  const int ncon = ncon_all < NC ? ncon_all : NC;
   // ---- N2: full contact records for the active slots (divergent, rare) ----
   LANES(W, R)
     if (R.nact > 0) {
       int o = R.off;
       if (R.actmask) {
-        emit_robot_contacts(m, S, lane, R.actmask, o);
+        emit_robot_contacts<NC>(m, S, lane, R.actmask, o);
         o += KPOPC((unsigned)R.actmask);
       }
-      if (m.has_box && lane < m.nbpair) emit_box_contacts(m, S, lane, o);
+      if (m.has_box && lane < m.nbpair) emit_box_contacts<NC>(m, S, lane, o);
     }
   END_LANES
   // ---- C1: joint-limit rows ----
@@ -871,7 +901,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmem& S, const StepIO& io) {
     }
   END_LANES
   const int nlim = warp_excl_scan(W, [](int, LaneRegs& R) { return R.nact; }, [](int, LaneRegs& R, int o) { R.off = o; });
-  UNIFORM_WRITE(W) { S.ncon = ncon; S.nlim = nlim; S.nrow = nlim + 4 * ncon; if (ncon_all > NCMAX) S.flags |= 1; } END_UNIFORM_WRITE
+  UNIFORM_WRITE(W) { S.ncon = ncon; S.nlim = nlim; S.nrow = nlim + 4 * ncon; if (ncon_all > NC) S.flags |= 1; } END_UNIFORM_WRITE
   const int nrow = nlim + 4 * ncon;
   if (nrow == 0) {
     LANES(W, R)
@@ -930,8 +960,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmem& S, const StepIO& io) {
     }
     R.f0 = cw; R.f1 = cs; R.f2 = 0.f;
     if (lane < KM_NV) {
-      float ma = 0.f;
-      for (int k = 0; k < KM_NV; ++k) ma += S.M[lane][k] * S.warm[k];
+      float ma = mul_M<NC>(m, S, lane, S.warm);
       S.Ma[lane] = ma;
       R.f2 = 0.5f * (ma - S.fs[lane]) * (S.warm[lane] - S.as[lane]);
     }
@@ -948,9 +977,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmem& S, const StepIO& io) {
     if (!use_warm) {
       for (int r = lane; r < nrow; r += 32) S.rJaref[r] = S.rJs[r];
       if (lane < KM_NV) {
-        float ma = 0.f;
-        for (int k = 0; k < KM_NV; ++k) ma += S.M[lane][k] * S.as[k];
-        S.Ma[lane] = ma;
+        S.Ma[lane] = mul_M<NC>(m, S, lane, S.as);
       }
     }
     if (lane < KM_NV) S.qacc[lane] = use_warm ? S.warm[lane] : S.as[lane];
@@ -963,53 +990,60 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmem& S, const StepIO& io) {
       for (int r = 0; r < nrow; ++r) { float ja = S.rJaref[r]; if (ja < 0.f) fc += row_J(S, r, lane) * (-S.rD[r] * ja); }
       S.grad[lane] = S.Ma[lane] - S.fs[lane] - fc;
     }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int i = (R.tri >> (8 * q)) & 15, j = (R.tri >> (8 * q + 4)) & 15;
+      if (i < KM_NV) {
+        float h = M_entry<NC>(m, S, i, j);
+        for (int r = 0; r < nlim; ++r) if (S.rJaref[r] < 0.f && S.limdof[r] == i && i == j) h += S.rD[r];
 #pragma unroll 1
-    for (int e = lane; e < KM_NV * (KM_NV + 1) / 2; e += 32) {
-      int i = 0, j = e;
-      while (j > i) { j -= i + 1; ++i; }
-      float h = S.M[i][j];
-      for (int r = 0; r < nlim; ++r) if (S.rJaref[r] < 0.f && S.limdof[r] == i && i == j) h += S.rD[r];
-#pragma unroll 1
-      for (int c = 0; c < ncon; ++c) {
-        const float* J = S.cJ[c];
-        const int r0 = nlim + 4 * c;
-        float w0 = S.rJaref[r0] < 0.f ? S.rD[r0] : 0.f, w1 = S.rJaref[r0 + 1] < 0.f ? S.rD[r0 + 1] : 0.f;
-        float w2 = S.rJaref[r0 + 2] < 0.f ? S.rD[r0 + 2] : 0.f, w3 = S.rJaref[r0 + 3] < 0.f ? S.rD[r0 + 3] : 0.f;
-        float ni = J[i], nj = J[j], ai = J[12 + i], aj = J[12 + j], bi = J[24 + i], bj = J[24 + j];
-        h += w0 * (ni + ai) * (nj + aj) + w1 * (ni - ai) * (nj - aj) + w2 * (ni + bi) * (nj + bj) + w3 * (ni - bi) * (nj - bj);
+        for (int c = 0; c < ncon; ++c) {
+          const float* J = S.cJ[c];
+          const int r0 = nlim + 4 * c;
+          float w0 = S.rJaref[r0] < 0.f ? S.rD[r0] : 0.f, w1 = S.rJaref[r0 + 1] < 0.f ? S.rD[r0 + 1] : 0.f;
+          float w2 = S.rJaref[r0 + 2] < 0.f ? S.rD[r0 + 2] : 0.f, w3 = S.rJaref[r0 + 3] < 0.f ? S.rD[r0 + 3] : 0.f;
+          float ni = J[i], nj = J[j], ai = J[12 + i], aj = J[12 + j], bi = J[24 + i], bj = J[24 + j];
+          h += w0 * (ni + ai) * (nj + aj) + w1 * (ni - ai) * (nj - aj) + w2 * (ni + bi) * (nj + bj) + w3 * (ni - bi) * (nj - bj);
+        }
+        S.H[i][j] = h;
       }
-      S.H[i][j] = h;
     }
   END_LANES
-  // ---- S4: Cholesky of H (lower, in place), then search = -H^-1 grad with lane i owning row i ----
-#pragma unroll 1
+  // ---- S4: Cholesky of H with lane i holding row i in registers (shuffles, no shared-memory
+  //      round trips), then search = -H^-1 grad ----
+  LANES(W, R)
+#pragma unroll
+    for (int k = 0; k < KM_NV; ++k) R.h[k] = (lane < KM_NV && k <= lane) ? S.H[lane][k] : 0.f;
+  END_LANES
+#pragma unroll
   for (int j = 0; j < KM_NV; ++j) {
-    USYNC();
-    const float dj = sqrtf(S.H[j][j]);
-    LANES(W, R)
-      if (lane > j && lane < KM_NV) S.H[lane][j] = S.H[lane][j] / dj;
-      if (lane == j) S.H[j][j] = dj;
-    END_LANES
-    LANES(W, R)
-      // trailing update H[i][k] -= L[i][j] L[k][j], j < k <= i
-#pragma unroll 1
-      for (int e = lane; e < KM_NV * (KM_NV + 1) / 2; e += 32) {
-        int i = 0, k = e;
-        while (k > i) { k -= i + 1; ++i; }
-        if (k > j) S.H[i][k] -= S.H[i][j] * S.H[k][j];
-      }
-    END_LANES
+    const float dj = sqrtf(warp_bcast(W, j, [&](int, LaneRegs& R) { return R.h[j]; }));
+    const float idj = 1.f / dj;
+    RLANES(W, R)
+      R.h[j] = (lane == j) ? dj : R.h[j] * idj;          // column j of L (rows > j), diagonal
+    END_RLANES
+#pragma unroll
+    for (int k = j + 1; k < KM_NV; ++k) {
+      const float lkj = warp_bcast(W, k, [&](int, LaneRegs& R) { return R.h[j]; });
+      RLANES(W, R)
+        if (lane >= k) R.h[k] -= R.h[j] * lkj;
+      END_RLANES
+    }
   }
   LANES(W, R)
+    if (lane < KM_NV) {
+#pragma unroll
+      for (int k = 0; k < KM_NV; ++k) if (k <= lane) S.H[lane][k] = R.h[k];
+    }
     R.f0 = lane < KM_NV ? S.grad[lane] : 0.f;
   END_LANES
-#pragma unroll 1
+#pragma unroll
   for (int k = 0; k < KM_NV; ++k) {            // forward substitution L y = grad
-    const float yk = warp_bcast(W, k, [&](int l, LaneRegs& R) { return R.f0 / S.H[l < KM_NV ? l : 0][l < KM_NV ? l : 0]; });
-    LANES(W, R)
+    const float yk = warp_bcast(W, k, [&](int, LaneRegs& R) { return R.f0 / R.h[k]; });
+    RLANES(W, R)
       if (lane == k) R.f0 = yk;
-      else if (lane > k && lane < KM_NV) R.f0 -= S.H[lane][k] * yk;
-    END_LANES
+      else if (lane > k) R.f0 -= R.h[k] * yk;
+    END_RLANES
   }
 #pragma unroll 1
   for (int k = KM_NV - 1; k >= 0; --k) {       // back substitution L^T x = y
@@ -1026,8 +1060,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmem& S, const StepIO& io) {
   LANES(W, R)
     R.f0 = R.f1 = R.f2 = 0.f;
     if (lane < KM_NV) {
-      float mv = 0.f;
-      for (int k = 0; k < KM_NV; ++k) mv += S.M[lane][k] * S.search[k];
+      float mv = mul_M<NC>(m, S, lane, S.search);
       S.mv[lane] = mv;
       float s = S.search[lane];
       R.f0 = s * s; R.f1 = s * S.Ma[lane] - s * S.fs[lane]; R.f2 = 0.5f * s * mv;
@@ -1115,7 +1148,8 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmem& S, const StepIO& io) {
 }
 
 // B.8: semi-implicit Euler with eulerdamp disabled
-KFN void step_euler(Warp& W, const KModel& m, WarpSmem& S) {
+template <int NC>
+KFN void step_euler(Warp& W, const KModel& m, WarpSmemT<NC>& S) {
   LANES(W, R)
     if (lane < KM_NV) {
       float v = S.qvel[lane] + m.dt * S.qacc[lane];
@@ -1152,15 +1186,20 @@ struct RolloutArgs {
   int* flags;
 };
 
-KFN void rollout_sample(Warp& W, const KModel& m, WarpSmem& S, const RolloutArgs& A) {
+template <int NC>
+KFN void rollout_sample(Warp& W, const KModel& m, WarpSmemT<NC>& S, const RolloutArgs& A) {
   LANES(W, R)
     if (lane < KM_NQ) S.qpos[lane] = lane < KM_NL ? A.q0[lane] : m.qpos0[lane];
     if (lane < KM_NV) { S.qvel[lane] = lane < KM_NL ? A.v0[lane] : m.qvel0[lane]; S.warm[lane] = m.warm0[lane]; }
-    for (int e = lane; e < KM_NV * KM_NV; e += 32) {
-      int i = e / KM_NV, j = e % KM_NV;
-      float v = 0.f;
-      if (i == j && i >= KM_NL) v = (i < KM_NL + 3) ? m.fb_mass : m.fb_inertia[i - KM_NL - 3];
-      S.M[i][j] = v;
+    {
+      // the three lower-triangle entries (i, j) this lane owns: e = lane, lane + 32, lane + 64 (78 in total)
+      int tri = 0;
+      for (int q = 0; q < 3; ++q) {
+        int e = lane + 32 * q, i = 0, j = e;
+        if (e < KM_NV * (KM_NV + 1) / 2) { while (j > i) { j -= i + 1; ++i; } } else { i = 15; j = 15; }
+        tri |= (i | (j << 4)) << (8 * q);
+      }
+      R.tri = tri;
     }
     if (lane == 0) S.flags = 0;
     R.cost_c = 0.f;
@@ -1180,7 +1219,7 @@ KFN void rollout_sample(Warp& W, const KModel& m, WarpSmem& S, const RolloutArgs
     StepIO io;
     io.first = t == 0;
     io.collision_row = (A.collision && A.live) ? A.collision + (size_t)t * m.nslot_robot : nullptr;
-    step_forward(W, m, S, io);
+    step_forward<NC>(W, m, S, io);
     // pre-step observations (mjx_planner.py:259-261) and running cost (:277-285)
     {
       float tcp[3], tv[3], eq[4];
@@ -1201,7 +1240,7 @@ KFN void rollout_sample(Warp& W, const KModel& m, WarpSmem& S, const RolloutArgs
         END_LANES
       }
     }
-    step_euler(W, m, S);
+    step_euler<NC>(W, m, S);
     LANES(W, R)
       if (A.live && lane < KM_NL) A.theta[lane * A.T + t] = S.qpos[lane];
     END_LANES

@@ -23,6 +23,8 @@
 #define STEP_ALIGN()
 #define LANES(W, R) for (int lane = 0; lane < 32; ++lane) { auto& R = (W).regs[lane]; (void)R;
 #define END_LANES }
+#define RLANES(W, R) LANES(W, R)
+#define END_RLANES }
 #define UNIFORM_WRITE(W) if (true)
 #define END_UNIFORM_WRITE
 #define USYNC()
@@ -38,6 +40,9 @@
 #endif
 #define LANES(W, R) { __syncwarp(); const int lane = (W).lane; auto& R = (W).regs; (void)R;
 #define END_LANES } __syncwarp();
+// register-only lane block: touches no shared scratch, so no fences
+#define RLANES(W, R) { const int lane = (W).lane; auto& R = (W).regs; (void)R; (void)lane;
+#define END_RLANES }
 #define UNIFORM_WRITE(W) __syncwarp(); if ((W).lane == 0)
 #define END_UNIFORM_WRITE __syncwarp();
 #define USYNC() __syncwarp()

@@ -14,15 +14,17 @@ extern "C" int emu_sizeof_kmodel() { return (int)sizeof(KModel); }
 extern "C" int emu_rollout(const KModel* m, int B, int T, const float* thetadot, const float* q0, const float* v0,
                            const float* tpos, const float* trot, float w_pos, float w_rot, float w_col,
                            float* theta, float* cost4, float* eef_pos, float* eef_rot, float* collision,
-                           float* qacc_dbg, int* flags) {
+                           float* qacc_dbg, int* flags, int nc) {
 #pragma omp parallel
   {
     Warp* W = new Warp();
-    WarpSmem* S = new WarpSmem();
+    WarpSmemT<KM_NC_FAST>* S = new WarpSmemT<KM_NC_FAST>();
+    WarpSmemT<KM_NC_BIG>* Sb = new WarpSmemT<KM_NC_BIG>();
 #pragma omp for schedule(dynamic, 4)
     for (int s = 0; s < B; ++s) {
       memset((void*)W, 0, sizeof(Warp));
-      memset((void*)S, 0, sizeof(WarpSmem));
+      memset((void*)S, 0, sizeof(*S));
+      memset((void*)Sb, 0, sizeof(*Sb));
       RolloutArgs A;
       A.T = T;
       A.live = true;
@@ -36,9 +38,9 @@ extern "C" int emu_rollout(const KModel* m, int B, int T, const float* thetadot,
       A.collision = collision ? collision + (size_t)s * T * m->nslot_robot : nullptr;
       A.qacc_dbg = qacc_dbg ? qacc_dbg + (size_t)s * T * KM_NV : nullptr;
       A.flags = flags ? flags + s : nullptr;
-      rollout_sample(*W, *m, *S, A);
+      if (nc <= KM_NC_FAST) rollout_sample<KM_NC_FAST>(*W, *m, *S, A); else rollout_sample<KM_NC_BIG>(*W, *m, *Sb, A);
     }
-    delete W; delete S;
+    delete W; delete S; delete Sb;
   }
   return 0;
 }
