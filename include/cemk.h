@@ -43,9 +43,8 @@ int cemk_set_model(cemk_handle* h, const void* kmodel, int kmodel_bytes);
 /* Per-horizon constants, host pointers, float32:
  *   G [3][T][11] = Pdot, Pddot, P (bernstein_coeff_ordern_new, mjx_planner.py:40);
  *   Kpp [11][11], Kpe [11][5] = per-DOF blocks of Q_inv (mjx_planner.py:166-172, block diagonal per DOF);
- *   N [11][11] = sum_c G_c^T G_c;  bounds = v_max, a_max, p_max (mjx_planner.py:84-86). */
-int cemk_set_horizon(cemk_handle* h, int T, const float* G, const float* Kpp, const float* Kpe, const float* N,
-                     const float* bounds3);
+ *   bounds = v_max, a_max, p_max (mjx_planner.py:84-86). */
+int cemk_set_horizon(cemk_handle* h, int T, const float* G, const float* Kpp, const float* Kpe, const float* bounds3);
 
 /* compute_xi_samples (mjx_planner.py:313-316) with the standard-normal draws injected:
  *   xi[B][66] = mean[66] + z[B][66] . chol(cov[66][66] + 0.003 I)^T.   `chol_ws` [66*66] scratch. */
@@ -62,7 +61,8 @@ int cemk_project(cemk_handle* h, int B, int maxiter_projection, const float* xi,
  *   theta[B][6T] (post-step joint angles, dof-major), cost4[B][4] = (cost, cost_g, cost_r, cost_c).
  *   Optional per-step dumps (pass NULL to skip): eef_pos[B][T][3], eef_rot[B][T][4],
  *   collision[B][T][nslot_robot] (pre-step, mjx_planner.py:259-261), qacc[B][T][12],
- *   flags[B] (bit 0: more than 32 simultaneously active contacts, extra ones dropped). */
+ *   flags[B] (bit 0: more than 48 simultaneously active contacts even in the re-run kernel, extra ones
+ *   dropped; samples exceeding the fast kernel's capacity of 24 are transparently recomputed). */
 int cemk_rollout_cost(cemk_handle* h, int B, int T, const float* thetadot, const float* q0, const float* v0,
                       const float* target_pos, const float* target_rot, float w_pos, float w_rot, float w_col,
                       float* theta, float* cost4, float* eef_pos, float* eef_rot, float* collision, float* qacc,

@@ -39,7 +39,7 @@ _SIGS = {
     "cemk_create": ([_vp, _i, _i, C.POINTER(_vp)], _i),
     "cemk_destroy": ([_vp], _i),
     "cemk_set_model": ([_vp, _vp, _i], _i),
-    "cemk_set_horizon": ([_vp, _i, _vp, _vp, _vp, _vp, _vp], _i),
+    "cemk_set_horizon": ([_vp, _i, _vp, _vp, _vp, _vp], _i),
     "cemk_sample": ([_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "cemk_project": ([_vp, _i, _i, _vp, _vp, _vp, _vp, _vp], _i),
     "cemk_rollout_cost": ([_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),

@@ -38,7 +38,7 @@ struct cemk_handle {
   KModel* d_model;
   int T;
   float* d_G;      // [3][T][11]
-  float* d_K;      // Kpp[121] Kpe[55] N[121] bounds[3]
+  float* d_K;      // Kpp[121] Kpe[55] bounds[3]
   long long launches;
   int* d_flags; int flags_cap;   // per-sample overflow flags when the caller passes none
 };
@@ -147,44 +147,42 @@ __global__ void __launch_bounds__(256) k_sample(int B, const float* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------- projection
-// One thread per (sample, dof).  Q_inv of the reference is block diagonal per DOF, and the slack /
-// multiplier updates collapse to (see DESIGN.md "projection filter"):
-//   u_c   = G_c x                       c in {velocity, acceleration, position}
-//   r     = sum_c G_c^T clip(u_c, -b_c, b_c)
-//   Lam  -= N x - r                     (sum of the three multipliers; they only ever appear summed)
-//   x'    = Kpp (Lam + xi + N x + r) + Kpe b_eq
-// which is the reference iteration with s and res eliminated.
+// One thread per (sample, dof).  Q_inv of the reference is block diagonal per DOF, and with
+// A_c = [G_c; -G_c] the slack / residual / multiplier updates of mjx_planner.py:196-223 collapse to
+//   u_c   = G_c x                                  c in {velocity, acceleration, position}
+//   e_c   = u_c - clip(u_c, -b_c, b_c)             (= res+ - res-; exactly 0 inside the bounds)
+//   h_c   = u_c + clip(u_c, -b_c, b_c)             (= (b - s+) - (b - s-))
+//   Lam  -= sum_c G_c^T e_c                        (the three multipliers only ever appear summed)
+//   x'    = Kpp (Lam + xi + sum_c G_c^T h_c) + Kpe b_eq
+// i.e. the reference iteration with s and res eliminated.  e_c is formed per time step *before* the
+// transpose product -- forming G^T G x - G^T clip(.) instead cancels catastrophically in float32
+// (|G^T G| ~ 1e6 at T = 16).
 __global__ void __launch_bounds__(128) k_project(int B, int T, int iters, const float* __restrict__ G, const float* __restrict__ Kc,
                                                  const float* __restrict__ xi, const float* __restrict__ state_term,
                                                  float* __restrict__ xi_f, float* __restrict__ thetadot) {
   extern __shared__ float sm[];
   float* sG = sm;                        // [3][T][11]
-  float* sK = sm + 3 * T * NCOEF;        // Kpp[121] Kpe[55] N[121] bounds[3]
+  float* sK = sm + 3 * T * NCOEF;        // Kpp[121] Kpe[55] bounds[3]
   for (int e = threadIdx.x; e < 3 * T * NCOEF; e += blockDim.x) sG[e] = G[e];
-  for (int e = threadIdx.x; e < 300; e += blockDim.x) sK[e] = Kc[e];
+  for (int e = threadIdx.x; e < 179; e += blockDim.x) sK[e] = Kc[e];
   __syncthreads();
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= B * 6) return;
   const int b = gid / 6, d = gid % 6;
-  const float* Kpp = sK; const float* Kpe = sK + 121; const float* Nm = sK + 176; const float* bnd = sK + 297;
-  float x[NCOEF], lam[NCOEF], xs[NCOEF], beq[5], cst[NCOEF];
+  const float* Kpp = sK; const float* Kpe = sK + 121; const float* bnd = sK + 176;
+  float x[NCOEF], lam[NCOEF], xs[NCOEF], beq[5], cst[NCOEF], rh[NCOEF], re[NCOEF];
 #pragma unroll
-  for (int k = 0; k < NCOEF; ++k) { xs[k] = xi[(size_t)b * NVAR + d * NCOEF + k]; lam[k] = 0.f; x[k] = 0.f; }
+  for (int k = 0; k < NCOEF; ++k) { xs[k] = xi[(size_t)b * NVAR + d * NCOEF + k]; lam[k] = 0.f; x[k] = 0.f; rh[k] = 0.f; }
 #pragma unroll
   for (int k = 0; k < 5; ++k) beq[k] = state_term[(size_t)b * 30 + k * 6 + d];
 #pragma unroll
   for (int i = 0; i < NCOEF; ++i) { float s = 0.f; for (int k = 0; k < 5; ++k) s += Kpe[i * 5 + k] * beq[k]; cst[i] = s; }
-  float nx[NCOEF], r[NCOEF];
-#pragma unroll
-  for (int k = 0; k < NCOEF; ++k) { nx[k] = 0.f; r[k] = 0.f; }
   for (int it = 0; it < iters; ++it) {
     float rhs[NCOEF];
 #pragma unroll
-    for (int k = 0; k < NCOEF; ++k) rhs[k] = lam[k] + xs[k] + nx[k] + r[k];
+    for (int k = 0; k < NCOEF; ++k) { rhs[k] = lam[k] + xs[k] + rh[k]; rh[k] = 0.f; re[k] = 0.f; }
 #pragma unroll
     for (int i = 0; i < NCOEF; ++i) { float s = cst[i]; for (int k = 0; k < NCOEF; ++k) s += Kpp[i * NCOEF + k] * rhs[k]; x[i] = s; }
-#pragma unroll
-    for (int i = 0; i < NCOEF; ++i) { float s = 0.f; for (int k = 0; k < NCOEF; ++k) s += Nm[i * NCOEF + k] * x[k]; nx[i] = s; r[i] = 0.f; }
     for (int c = 0; c < 3; ++c) {
       const float bc = bnd[c];
       const float* Gc = sG + c * T * NCOEF;
@@ -193,13 +191,14 @@ __global__ void __launch_bounds__(128) k_project(int B, int T, int iters, const 
         float u = 0.f;
 #pragma unroll
         for (int k = 0; k < NCOEF; ++k) u += g[k] * x[k];
-        u = fminf(fmaxf(u, -bc), bc);
+        const float cl = fminf(fmaxf(u, -bc), bc);
+        const float e = u - cl, h = u + cl;
 #pragma unroll
-        for (int k = 0; k < NCOEF; ++k) r[k] += g[k] * u;
+        for (int k = 0; k < NCOEF; ++k) { re[k] += g[k] * e; rh[k] += g[k] * h; }
       }
     }
 #pragma unroll
-    for (int k = 0; k < NCOEF; ++k) lam[k] -= nx[k] - r[k];
+    for (int k = 0; k < NCOEF; ++k) lam[k] -= re[k];
   }
 #pragma unroll
   for (int k = 0; k < NCOEF; ++k) xi_f[(size_t)b * NVAR + d * NCOEF + k] = x[k];
@@ -366,7 +365,7 @@ int cemk_create(const void* kmodel, int kmodel_bytes, int device, cemk_handle** 
   h->device = device; h->T = 0; h->d_G = nullptr; h->d_K = nullptr; h->launches = 0; h->d_flags = nullptr; h->flags_cap = 0;
   CK(cudaMalloc(&h->d_model, sizeof(KModel)));
   CK(cudaMemcpy(h->d_model, kmodel, sizeof(KModel), cudaMemcpyHostToDevice));
-  CK(cudaMalloc(&h->d_K, 300 * sizeof(float)));
+  CK(cudaMalloc(&h->d_K, 179 * sizeof(float)));
   CK(cudaFuncSetAttribute(k_rollout<KM_NC_FAST, ROLLOUT_WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)rollout_smem<KM_NC_FAST, ROLLOUT_WARPS>()));
   CK(cudaFuncSetAttribute(k_rollout<KM_NC_BIG, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -388,18 +387,18 @@ int cemk_set_model(cemk_handle* h, const void* kmodel, int kmodel_bytes) {
   CK(cudaMemcpy(h->d_model, kmodel, sizeof(KModel), cudaMemcpyHostToDevice));
   return CEMK_OK;
 }
-int cemk_set_horizon(cemk_handle* h, int T, const float* G, const float* Kpp, const float* Kpe, const float* N, const float* bounds3) {
-  if (!h || !G || !Kpp || !Kpe || !N || !bounds3) return set_err(CEMK_ERR_ARG, "cemk_set_horizon: null argument");
+int cemk_set_horizon(cemk_handle* h, int T, const float* G, const float* Kpp, const float* Kpe, const float* bounds3) {
+  if (!h || !G || !Kpp || !Kpe || !bounds3) return set_err(CEMK_ERR_ARG, "cemk_set_horizon: null argument");
   if (T < 2 || T > 1024) return set_err(CEMK_ERR_ARG, "cemk_set_horizon: T out of range [2, 1024]");
   CK(cudaSetDevice(h->device));
   if (h->d_G) { CK(cudaFree(h->d_G)); h->d_G = nullptr; }
   CK(cudaMalloc(&h->d_G, sizeof(float) * 3 * T * NCOEF));
   CK(cudaMemcpy(h->d_G, G, sizeof(float) * 3 * T * NCOEF, cudaMemcpyHostToDevice));
-  float kc[300];
-  memcpy(kc, Kpp, 121 * 4); memcpy(kc + 121, Kpe, 55 * 4); memcpy(kc + 176, N, 121 * 4); memcpy(kc + 297, bounds3, 12);
+  float kc[179];
+  memcpy(kc, Kpp, 121 * 4); memcpy(kc + 121, Kpe, 55 * 4); memcpy(kc + 176, bounds3, 12);
   CK(cudaMemcpy(h->d_K, kc, sizeof kc, cudaMemcpyHostToDevice));
   h->T = T;
-  const int smem = (3 * T * NCOEF + 300) * (int)sizeof(float);
+  const int smem = (3 * T * NCOEF + 179) * (int)sizeof(float);
   CK(cudaFuncSetAttribute(k_project, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   return CEMK_OK;
 }
@@ -417,7 +416,7 @@ int cemk_sample(cemk_handle* h, int B, const float* z, const float* mean, const 
 int cemk_project(cemk_handle* h, int B, int iters, const float* xi, const float* state_term, float* xi_f, float* thetadot, void* stream) {
   if (!h || !xi || !state_term || !xi_f || B <= 0 || iters < 1) return set_err(CEMK_ERR_ARG, "cemk_project: bad argument");
   if (!h->d_G) return set_err(CEMK_ERR_ARG, "cemk_project: cemk_set_horizon has not been called");
-  const int T = h->T, smem = (3 * T * NCOEF + 300) * (int)sizeof(float);
+  const int T = h->T, smem = (3 * T * NCOEF + 179) * (int)sizeof(float);
   k_project<<<(B * 6 + 127) / 128, 128, smem, (cudaStream_t)stream>>>(B, T, iters, h->d_G, h->d_K, xi, state_term, xi_f, thetadot);
   h->launches += 1;
   CK(cudaPeekAtLastError());

@@ -28,7 +28,7 @@ import os
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, parallel
 from .bernstein import bernstein_coeff_ordern_new
 from .kmodel import KModel, build_kmodel
 from .mjcf import ModelConsts, host_kinematics, load_model
@@ -228,14 +228,11 @@ class cem_planner:
         off = Q_inv[:n1, n1:nv]
         if np.abs(off).max() > 1e-6 * scale:
             raise RuntimeError("Q_inv couples different DOFs")
-        G = np.stack((self.Pdot, self.Pddot, self.P)).astype(np.float32)
-        Gd = G.astype(np.float64)
-        N = sum(Gd[c].T @ Gd[c] for c in range(3))
         c32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
-        G, Kpp, Kpe, N = c32(G), c32(Kpp), c32(Kpe), c32(N)
+        G, Kpp, Kpe = c32(np.stack((self.Pdot, self.Pddot, self.P))), c32(Kpp), c32(Kpe)
         bnd = c32([self.v_max, self.a_max, self.p_max])
         hp = lambda a: a.ctypes.data_as(_VP)
-        _lib.check(self._lib.cemk_set_horizon(self._h, self.num, hp(G), hp(Kpp), hp(Kpe), hp(N), hp(bnd)), self._lib)
+        _lib.check(self._lib.cemk_set_horizon(self._h, self.num, hp(G), hp(Kpp), hp(Kpe), hp(bnd)), self._lib)
 
     def _initial_forward(self):
         """One forward at qpos0 with zero velocity: qacc -> KModel.warm0 (mjx_planner.py:107)."""
@@ -429,17 +426,9 @@ class cem_planner:
         xi_e, idx, cost_e = self._argsort_topk(cost4, 4, Bl, kl, xi_samples, idx_base=base)
         if self.world == 1:
             return xi_e, cost_e, idx[:kl]
-        dist = self._dist
-        pack = torch.empty(kl, self.nvar + 2, device=self.device)
-        pack[:, :self.nvar] = xi_e
-        pack[:, self.nvar] = cost_e
-        pack[:, self.nvar + 1] = idx[:kl].to(torch.float32)      # global index < 2^24: exact in float32
-        gathered = torch.empty(self.world * kl, self.nvar + 2, device=self.device)
-        dist.all_gather_into_tensor(gathered, pack, group=self.process_group)
+        gathered = parallel.gather_elites(parallel.pack_elites(xi_e, cost_e, idx[:kl]), self.world, self.process_group)
         n = self.world * kl
-        g_cost = gathered[:, self.nvar].contiguous()
-        g_idx = gathered[:, self.nvar + 1].to(torch.int32).contiguous()
-        g_xi = gathered[:, :self.nvar].contiguous()
+        g_cost, g_idx, g_xi = parallel.split_gathered(gathered)
         np2 = 1 << max(0, (n - 1).bit_length())
         keys = self._buf("keys_merge", (np2,), torch.int64)
         xi_m = torch.empty(k, self.nvar, device=self.device)

@@ -1,0 +1,44 @@
+"""Build + call the CPU emulation build of the rollout core (tests/emu/emu.cpp).  Test infrastructure."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "tests", "_emu_build", "libcemk_emu.so")
+SRCS = [os.path.join(ROOT, "tests", "emu", "emu.cpp")] + [os.path.join(ROOT, "manipulator_mujoco_b200", "csrc", n)
+                                                          for n in ("rollout_core.h", "warp_dsl.h", "kmodel.h")]
+
+
+def build():
+    if os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(s) for s in SRCS):
+        return OUT
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([cxx, "-O2", "-fPIC", "-shared", "-fopenmp", "-std=c++17", "-Wno-unknown-pragmas", "-o", OUT, SRCS[0]],
+                   check=True, capture_output=True)
+    return OUT
+
+
+class Emu:
+    def __init__(self, km):
+        from manipulator_mujoco_b200.kmodel import KModel
+        self.lib = C.CDLL(build())
+        assert self.lib.emu_sizeof_kmodel() == C.sizeof(KModel)
+        self.km = km
+
+    def rollout(self, td, q0, v0, tpos, trot, w=(20.0, 3.0, 80.0), nc=48, km=None):
+        km = km or self.km
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+        td = f(td)
+        B, T = td.shape[0], td.shape[1] // 6
+        q0, v0, tpos, trot = f(q0), f(v0), f(tpos), f(trot)
+        out = dict(theta=np.zeros((B, 6 * T), np.float32), cost4=np.zeros((B, 4), np.float32), eef_pos=np.zeros((B, T, 3), np.float32),
+                   eef_rot=np.zeros((B, T, 4), np.float32), collision=np.zeros((B, T, km.nslot_robot), np.float32),
+                   qacc=np.zeros((B, T, 12), np.float32), flags=np.zeros(B, np.int32))
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        self.lib.emu_rollout(C.byref(km), B, T, p(td), p(q0), p(v0), p(tpos), p(trot), C.c_float(w[0]), C.c_float(w[1]), C.c_float(w[2]),
+                             p(out["theta"]), p(out["cost4"]), p(out["eef_pos"]), p(out["eef_rot"]), p(out["collision"]), p(out["qacc"]),
+                             p(out["flags"]), int(nc))
+        return out

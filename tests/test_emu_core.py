@@ -1,0 +1,84 @@
+"""The rollout kernel's source (csrc/rollout_core.h), compiled for the CPU by tests/emu, against the
+oracle.  Catches indexing / physics mistakes in the kernel logic without a GPU; the real parity
+tests (tests/test_gpu_*.py) run the CUDA build on the B200."""
+import copy
+
+import numpy as np
+import pytest
+
+from conftest import Q0, TARGET_POS, TARGET_ROT, planner_inputs
+from emu_util import Emu
+
+
+@pytest.fixture(scope="module")
+def emu(mc, oracle64):
+    from manipulator_mujoco_b200.kmodel import build_kmodel
+    km, _ = build_kmodel(mc, 0.05, warm0=oracle64.initial_warmstart())
+    return Emu(km)
+
+
+def test_short_rollout_matches_oracle(emu, oracle64):
+    pr, z, xi, st, xif, td = planner_inputs(16, 64)
+    out = emu.rollout(td, Q0, np.zeros(6), TARGET_POS, TARGET_ROT)
+    oth, oep, oer, ocol = oracle64.rollout(td, Q0, np.zeros(6))
+    th, ot = out["theta"].reshape(64, 6, 16), oth.reshape(64, 6, 16)
+    assert np.abs(th[:, :, :4] - ot[:, :, :4]).max() < 2e-6           # before the box lands: well conditioned
+    assert np.abs(out["eef_pos"][:, :5] - oep[:, :5]).max() < 2e-6
+    assert np.abs(out["theta"] - oth).max() < 5e-4                    # after: line-search branch noise
+    assert (np.abs(out["collision"] - ocol) > 1e-3).mean() < 1e-4
+    oc = pr.compute_cost_batch(oep, oer, ocol, TARGET_POS, TARGET_ROT)
+    np.testing.assert_allclose(out["cost4"][:, 1], oc[1], rtol=2e-4)
+    np.testing.assert_allclose(out["cost4"][:, 2], oc[2], rtol=2e-4, atol=1e-4)
+    np.testing.assert_allclose(out["cost4"][:, 0], 20 * out["cost4"][:, 1] + 3 * out["cost4"][:, 2] + 80 * out["cost4"][:, 3], rtol=1e-5)
+    assert out["flags"].max() == 0
+
+
+def test_teacher_forced_steps_on_contact_states(emu, oracle64, oracle32):
+    """Single steps from states of a long oracle rollout where the robot is in contact.
+    Narrow phase must agree to rounding.  The solver output qacc must agree wherever the reference
+    algorithm itself is precision-stable (float32 and float64 builds of the oracle agree)."""
+    T, B = 100, 96
+    pr, z, xi, st, xif, td = planner_inputs(T, B, seed=1)
+    oth, oep, oer, ocol, oqp, oqa = oracle64.rollout(td, Q0, np.zeros(6), want_state=True)
+    has = np.where((ocol < 0).any(axis=(1, 2)))[0]
+    assert len(has) >= 10
+    warm0 = oracle64.initial_warmstart()
+    n = stable = 0
+    worst_col = 0.0
+    for s in has[:24]:
+        qvbox = np.zeros(6)
+        for t in range(T):
+            qpos = np.concatenate([Q0, oracle64.mc.qpos0[6:]]) if t == 0 else oqp[s, t - 1]
+            warm = warm0 if t == 0 else oqa[s, t - 1]
+            qvel = np.zeros(12)
+            qvel[6:] = qvbox
+            qvel[:6] = td[s].reshape(6, T)[:, t]
+            qvbox = qvbox + 0.05 * oqa[s, t, 6:]
+            if not (ocol[s, t] < 0).any() or t % 3:
+                continue
+            r64, r32 = oracle64.forward(qpos, qvel, warm), oracle32.forward(qpos, qvel, warm)
+            km = copy.copy(emu.km)
+            for i in range(13):
+                km.qpos0[i] = qpos[i]
+            for i in range(12):
+                km.warm0[i], km.qvel0[i] = warm[i], qvel[i]
+            out = emu.rollout(qvel[:6].reshape(1, 6), qpos[:6], qvel[:6], TARGET_POS, TARGET_ROT, km=km)
+            worst_col = max(worst_col, np.abs(out["collision"][0, 0] - r64["con_dist"][oracle64.mask]).max())
+            scale = max(1.0, np.abs(r64["qacc"]).max())
+            n += 1
+            if np.abs(r32["qacc"] - r64["qacc"]).max() < 1e-3 * scale:
+                stable += 1
+                assert np.abs(out["qacc"][0, 0] - r64["qacc"]).max() < 2e-2 * scale, (s, t)
+    assert n > 50 and stable > 0.3 * n
+    assert worst_col < 1e-5
+
+
+def test_contact_capacity_variants_agree(emu):
+    """NC = 24 (fast kernel) and NC = 48 (re-run kernel) are the same code: identical results
+    whenever nothing overflows."""
+    pr, z, xi, st, xif, td = planner_inputs(30, 32, seed=2)
+    a = emu.rollout(td, Q0, np.zeros(6), TARGET_POS, TARGET_ROT, nc=24)
+    b = emu.rollout(td, Q0, np.zeros(6), TARGET_POS, TARGET_ROT, nc=48)
+    assert a["flags"].max() == 0
+    np.testing.assert_array_equal(a["theta"], b["theta"])
+    np.testing.assert_array_equal(a["cost4"], b["cost4"])
