@@ -21,6 +21,9 @@
 #ifndef ROLLOUT_WARPS
 #define ROLLOUT_WARPS 16      // samples (warps) per CTA; they step in lockstep (STEP_ALIGN) to share the instruction cache
 #endif
+#ifndef ROLLOUT_WARPS_ALT
+#define ROLLOUT_WARPS_ALT 14  // alternative CTA size picked when it quantises better onto the SMs
+#endif
 #ifndef ROLLOUT_MINB
 #define ROLLOUT_MINB 1
 #endif
@@ -40,10 +43,13 @@ struct cemk_handle {
   float* d_G;      // [3][T][11]
   float* d_K;      // Kpp[121] Kpe[55] bounds[3]
   long long launches;
-  int* d_flags; int flags_cap;   // per-sample overflow flags when the caller passes none
+  int* d_flags; int flags_cap; int num_sms;   // per-sample overflow flags when the caller passes none
 };
 
 // ---------------------------------------------------------------------------------------------- rollout
+#ifdef CEMK_PHASE_TIMING
+__device__ unsigned long long g_phase[16];
+#endif
 struct RolloutBatch {
   int B, T;
   const float* thetadot; const float* q0; const float* v0; const float* target_pos; const float* target_rot;
@@ -80,6 +86,10 @@ __global__ void __launch_bounds__(WARPS * 32, ROLLOUT_MINB) k_rollout(const KMod
   }
   Warp W;
   W.lane = threadIdx.x & 31;
+#ifdef CEMK_PHASE_TIMING
+  W.phase = 14; W.t0 = clock64();
+  for (int i = 0; i < 16; ++i) W.ph[i] = 0;
+#endif
   RolloutArgs A;
   const size_t row = (size_t)s * KM_NL * a.T;
   A.T = a.T;
@@ -95,6 +105,10 @@ __global__ void __launch_bounds__(WARPS * 32, ROLLOUT_MINB) k_rollout(const KMod
   A.qacc_dbg = a.qacc ? a.qacc + (size_t)s * a.T * KM_NV : nullptr;
   A.flags = a.flags + s;
   rollout_sample<NC>(W, *sm, ws[warp], A);
+#ifdef CEMK_PHASE_TIMING
+  PHASE(W, 15);
+  if (W.lane == 0 && !ONLY_FLAGGED) for (int i = 0; i < 16; ++i) atomicAdd(&g_phase[i], (unsigned long long)W.ph[i]);
+#endif
 }
 template <int NC, int WARPS>
 static size_t rollout_smem() { return ((sizeof(KModel) + 15) & ~size_t(15)) + WARPS * sizeof(WarpSmemT<NC>); }
@@ -363,11 +377,14 @@ int cemk_create(const void* kmodel, int kmodel_bytes, int device, cemk_handle** 
   CK(cudaSetDevice(device));
   cemk_handle* h = new cemk_handle();
   h->device = device; h->T = 0; h->d_G = nullptr; h->d_K = nullptr; h->launches = 0; h->d_flags = nullptr; h->flags_cap = 0;
+  { cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device)); h->num_sms = prop.multiProcessorCount; }
   CK(cudaMalloc(&h->d_model, sizeof(KModel)));
   CK(cudaMemcpy(h->d_model, kmodel, sizeof(KModel), cudaMemcpyHostToDevice));
   CK(cudaMalloc(&h->d_K, 179 * sizeof(float)));
   CK(cudaFuncSetAttribute(k_rollout<KM_NC_FAST, ROLLOUT_WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)rollout_smem<KM_NC_FAST, ROLLOUT_WARPS>()));
+  CK(cudaFuncSetAttribute(k_rollout<KM_NC_FAST, ROLLOUT_WARPS_ALT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)rollout_smem<KM_NC_FAST, ROLLOUT_WARPS_ALT>()));
   CK(cudaFuncSetAttribute(k_rollout<KM_NC_BIG, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)rollout_smem<KM_NC_BIG, 1>()));
   *out = h;
@@ -442,8 +459,15 @@ int cemk_rollout_cost(cemk_handle* h, int B, int T, const float* thetadot, const
   a.B = B; a.T = T; a.thetadot = thetadot; a.q0 = q0; a.v0 = v0; a.target_pos = target_pos; a.target_rot = target_rot;
   a.w_pos = w_pos; a.w_rot = w_rot; a.w_col = w_col;
   a.theta = theta; a.cost4 = cost4; a.eef_pos = eef_pos; a.eef_rot = eef_rot; a.collision = collision; a.qacc = qacc; a.flags = flags;
-  k_rollout<KM_NC_FAST, ROLLOUT_WARPS, false><<<(B + ROLLOUT_WARPS - 1) / ROLLOUT_WARPS, ROLLOUT_WARPS * 32,
-                                                rollout_smem<KM_NC_FAST, ROLLOUT_WARPS>(), st>>>(h->d_model, a);
+  // CTA size: 16 or 14 samples, whichever wastes fewer SM slots in the last wave (one CTA per SM is resident)
+  const int nsm = h->num_sms > 0 ? h->num_sms : 148;
+  auto waste = [&](int w) { const int ctas = (B + w - 1) / w; const int waves = (ctas + nsm - 1) / nsm; return (double)waves * nsm * w / (double)B; };
+  if (waste(ROLLOUT_WARPS_ALT) + 0.02 < waste(ROLLOUT_WARPS))
+    k_rollout<KM_NC_FAST, ROLLOUT_WARPS_ALT, false><<<(B + ROLLOUT_WARPS_ALT - 1) / ROLLOUT_WARPS_ALT, ROLLOUT_WARPS_ALT * 32,
+                                                      rollout_smem<KM_NC_FAST, ROLLOUT_WARPS_ALT>(), st>>>(h->d_model, a);
+  else
+    k_rollout<KM_NC_FAST, ROLLOUT_WARPS, false><<<(B + ROLLOUT_WARPS - 1) / ROLLOUT_WARPS, ROLLOUT_WARPS * 32,
+                                                  rollout_smem<KM_NC_FAST, ROLLOUT_WARPS>(), st>>>(h->d_model, a);
   // samples whose active-contact list overflowed the fast capacity are recomputed with the big one
   k_rollout<KM_NC_BIG, 1, true><<<B, 32, rollout_smem<KM_NC_BIG, 1>(), st>>>(h->d_model, a);
   h->launches += 2;
@@ -521,5 +545,15 @@ int cemk_mean_cov(cemk_handle* h, int k, const float* cost_elite, const float* x
 }
 
 long long cemk_launch_count(cemk_handle* h) { return h ? h->launches : 0; }
+
+#ifdef CEMK_PHASE_TIMING
+/* debug builds only: copy out and clear the per-phase clock table */
+int cemk_debug_phase_clocks(unsigned long long* out16) {
+  unsigned long long z[16] = {0};
+  if (cudaMemcpyFromSymbol(out16, g_phase, sizeof z) != cudaSuccess) return CEMK_ERR_CUDA;
+  if (cudaMemcpyToSymbol(g_phase, z, sizeof z) != cudaSuccess) return CEMK_ERR_CUDA;
+  return CEMK_OK;
+}
+#endif
 
 }  // extern "C"

@@ -23,6 +23,9 @@
 #include "kmodel.h"
 #include "warp_dsl.h"
 
+#ifndef CEMK_SYNC_EVERY
+#define CEMK_SYNC_EVERY 1                   // env-steps between two CTA-wide re-alignments (STEP_ALIGN)
+#endif
 #define KM_NC_FAST 24                     // active-contact capacity of the fast kernel
 #define KM_NC_BIG 48                      // capacity of the re-run kernel for samples that overflowed
 #define MJ_MINVAL 1e-15f
@@ -34,6 +37,7 @@ struct LaneRegs {
   int nact, off;              // active contacts this lane will emit, and where
   int actmask;                // bit (2*pass + slot)
   int tri;                    // three packed (i, j) pairs of the lower triangle this lane owns (4 bits each)
+  float td;                   // next step's commanded joint velocity (lanes < 6), prefetched one step ahead
   float acc[9];               // line-search partial sums (compile-time indices only)
   float h[KM_NV];             // row `lane` of the Newton Hessian / its Cholesky factor
   float f0, f1, f2;
@@ -62,7 +66,10 @@ struct WarpSmemT {
   float cgeo[NC][16];                 // pos3 n3 t1 3 t2 3 dist invw link1 link2
   union {
     float cJ[NC][36];                 // Jn[12] Jt1[12] Jt2[12] (tangents pre-multiplied by mu)
-    struct { float bstage[KM_MAXBPAIR][4][4], bnrm[KM_MAXBPAIR][4]; };   // free-box pair candidates: pos3, dist
+    struct {                          // free-box pair candidates (pos3, dist) + scratch of the cooperative box-box
+      float bstage[KM_MAXBPAIR][4][4], bnrm[KM_MAXBPAIR][4];
+      float bbR[12], bbc[4], bbsz[2][4], bbrf[4][4], bben[4][4], bbpoly[2][8][4], bbpref[8][4];
+    };
   };
   int limdof[KM_NL];
   float limsign[KM_NL];
@@ -284,9 +291,12 @@ KFN void capsule_box(const float* A, const float* B, float r, const float* bpos,
   }
   // shallow edge contact: an edge of the face closer than r to the segment replaces slot 0.
   // Every edge lies in the face plane, so nothing to do when the segment stays >= r away from it.
+  // ... nor when both end points lie inside the face rectangle shrunk by r (the shrunk rectangle is
+  // convex, so every point of the segment is then >= r from every edge).
   float ha = sg * ak - sk, hb = sg * bk_ - sk;
   float hmin = (ha * hb <= 0.f) ? 0.f : fminf(fabsf(ha), fabsf(hb));
-  if (hmin < r) {
+  const bool interior = fmaxf(fabsf(au), fabsf(bu)) < su - r && fmaxf(fabsf(aw), fabsf(bw)) < sw - r;
+  if (hmin < r && !interior) {
     float bd = 0.f, bec[3] = {0.f, 0.f, 0.f}, bcc[3] = {0.f, 0.f, 0.f};
 #pragma unroll 1
     for (int i = 0; i < 4; ++i) {
@@ -395,123 +405,251 @@ KNOINLINE int plane_box(const float* ppos, const float* pn, const float* bpos, c
   }
   return nact;
 }
-KFN int clip_poly_halfplane(int n, float in[][3], float out[][3], const float* pp, const float* pn) {
-  int m = 0;
-  for (int i = 0; i < n; ++i) {
-    const float* a = in[i]; const float* b = in[(i + 1) % n];
-    float ta[3], tb[3];
-    sub3(ta, a, pp); sub3(tb, b, pp);
-    float da = dot3(ta, pn), db = dot3(tb, pn);
-    if (da <= 0.f) { copy3(out[m], a); ++m; }
-    if ((da < 0.f && db > 0.f) || (da > 0.f && db < 0.f)) {
-      float s = da / (da - db), ab[3];
-      sub3(ab, b, a); madd3(out[m], a, ab, s); ++m;
+// Warp-cooperative box (geom1) vs box (geom2).  Same algorithm, axis order and tie rules as the
+// oracle's box_box (SAT over face2 x3, face1 x3, edge x edge 3x3; clipped face
+// manifold reduced by the 4-point rule, or one edge-edge contact), with the 15 axes, the polygon edges
+// and the polygon vertices spread over lanes: the resting target_0 / table pair is evaluated every
+// step, and the scalar version on one lane was 30 % of all issued warp instructions (profiles/r1c).
+// Must be called by the whole warp.  Writes S.bstage[slot][k] = pos3, dist (dist = 1: unused) and
+// S.bnrm[slot]; returns the number of active contacts.
+template <int NC>
+KFN int box_box_warp(Warp& W, WarpSmemT<NC>& S, int slot, const float* p1, const float* m1, const float* s1,
+                     const float* p2, const float* m2, const float* s2) {
+  LANES(W, R)
+    if (lane < 9) { const int i = lane / 3, j = lane % 3; S.bbR[lane] = m2[i] * m1[j] + m2[3 + i] * m1[3 + j] + m2[6 + i] * m1[6 + j]; }
+    else if (lane < 12) { const int i = lane - 9; S.bbc[i] = m2[i] * (p1[0] - p2[0]) + m2[3 + i] * (p1[1] - p2[1]) + m2[6 + i] * (p1[2] - p2[2]); }
+    else if (lane < 16) { float* o = S.bstage[slot][lane - 12]; o[0] = o[1] = o[2] = 0.f; o[3] = 1.f; }
+  END_LANES
+  // ---- separating axes, one per lane ----
+  LANES(W, R)
+    float cmp = -INFINITY, a0 = 0.f, a1 = 0.f, a2 = 1.f, sgn = 1.f;
+    if (lane < 15) {
+      const float* Rm = S.bbR; const float* c = S.bbc;
+      bool ok = true;
+      if (lane < 3) { a0 = lane == 0 ? 1.f : 0.f; a1 = lane == 1 ? 1.f : 0.f; a2 = lane == 2 ? 1.f : 0.f; }
+      else if (lane < 6) { const int i = lane - 3; a0 = Rm[i]; a1 = Rm[3 + i]; a2 = Rm[6 + i]; }
+      else {
+        const int i = (lane - 6) / 3, j = (lane - 6) % 3;
+        const float x = Rm[i], y = Rm[3 + i], z = Rm[6 + i];
+        if (j == 0) { a0 = 0.f; a1 = z; a2 = -y; } else if (j == 1) { a0 = -z; a1 = 0.f; a2 = x; } else { a0 = y; a1 = -x; a2 = 0.f; }
+        const float n = sqrtf(a0 * a0 + a1 * a1 + a2 * a2);
+        if (n > 0.f) { const float in = 1.f / n; a0 *= in; a1 *= in; a2 *= in; } else { a0 = a1 = a2 = 0.f; }
+        ok = !(n < 1e-6f);
+      }
+      float r1 = 0.f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) r1 += s1[k] * fabsf(Rm[k] * a0 + Rm[3 + k] * a1 + Rm[6 + k] * a2);
+      const float r2 = s2[0] * fabsf(a0) + s2[1] * fabsf(a1) + s2[2] * fabsf(a2);
+      const float dc = c[0] * a0 + c[1] * a1 + c[2] * a2;
+      if (ok) cmp = fabsf(dc) - r1 - r2 - (lane >= 6 ? 1e-6f : 0.f);
+      sgn = dc > 0.f ? -1.f : 1.f;          // contact normal points from box 1 (at c) to box 2 (origin)
     }
+    R.f0 = cmp; R.f1 = a0 * sgn; R.f2 = a1 * sgn; R.acc[0] = a2 * sgn;
+  END_LANES
+  const int bl = warp_argmax_first(W, [](int, LaneRegs& R) { return R.f0; });
+  const float bestsep = warp_bcast(W, bl, [](int, LaneRegs& R) { return R.f0; });
+  if (bestsep > 0.f) return 0;               // separated: no slot can be active
+  const float bn[3] = {warp_bcast(W, bl, [](int, LaneRegs& R) { return R.f1; }), warp_bcast(W, bl, [](int, LaneRegs& R) { return R.f2; }),
+                       warp_bcast(W, bl, [](int, LaneRegs& R) { return R.acc[0]; })};
+  {
+    float nw[3];
+    mat_vec(nw, m2, bn);
+    normalize3(nw);
+    UNIFORM_WRITE(W) { copy3(S.bnrm[slot], nw); } END_UNIFORM_WRITE
   }
-  return m;
-}
-// box (geom1) vs box (geom2): SAT over 15 axes, then clipped face manifold or a single edge-edge
-// contact.  out[k] = pos3, dist; nrm = contact normal (geom1 -> geom2), world frame.
-KNOINLINE int box_box(const float* p1, const float* m1, const float* s1, const float* p2, const float* m2, const float* s2, float out[4][4], float* nrm) {
-  float t[3], c[3], R[9];
-  sub3(t, p1, p2); matT_vec(c, m2, t);
-  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R[3 * i + j] = m2[i] * m1[j] + m2[3 + i] * m1[3 + j] + m2[6 + i] * m1[6 + j];
-  float A[3][3];
-  for (int i = 0; i < 3; ++i) { A[i][0] = R[i]; A[i][1] = R[3 + i]; A[i][2] = R[6 + i]; }
-  float bestsep = -1e30f; int besttype = -1, bi = 0, bj = 0; float bestn[3] = {0.f, 0.f, 1.f};
-#pragma unroll 1
-  for (int type = 0; type < 3; ++type)
-#pragma unroll 1
-    for (int i = 0; i < 3; ++i)
-#pragma unroll 1
-      for (int j = 0; j < (type == 2 ? 3 : 1); ++j) {
-    float ax[3] = {0.f, 0.f, 0.f};
-    if (type == 0) ax[i] = 1.f; else if (type == 1) copy3(ax, A[i]);
-    else { float e2[3] = {0.f, 0.f, 0.f}; e2[j] = 1.f; cross3(ax, A[i], e2); if (normalize3(ax) < 1e-6f) continue; }
-    float r1 = 0.f, r2 = 0.f;
-    for (int k = 0; k < 3; ++k) { r1 += s1[k] * fabsf(dot3(A[k], ax)); r2 += s2[k] * fabsf(ax[k]); }
-    float dc = dot3(c, ax);
-    float cmp = fabsf(dc) - r1 - r2 - (type == 2 ? 1e-6f : 0.f);
-    if (cmp > bestsep) {
-      bestsep = cmp; besttype = type; bi = i; bj = j;
-      float sgn = dc > 0.f ? -1.f : 1.f;
-      bestn[0] = ax[0] * sgn; bestn[1] = ax[1] * sgn; bestn[2] = ax[2] * sgn;
+  float Rm[9], c[3];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) Rm[k] = S.bbR[k];
+  c[0] = S.bbc[0]; c[1] = S.bbc[1]; c[2] = S.bbc[2];
+  if (bl >= 6) {
+    // ---- edge-edge: closest points of the two support edges (uniform, rare) ----
+    const int bi = (bl - 6) / 3, bj = (bl - 6) % 3;
+    float e1c[3] = {c[0], c[1], c[2]}, e2c[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float Ak[3] = {Rm[k], Rm[3 + k], Rm[6 + k]};
+      if (k != bi) { const float sg = dot3(Ak, bn) > 0.f ? 1.f : -1.f; madd3(e1c, e1c, Ak, sg * s1[k]); }
+      if (k != bj) e2c[k] = (bn[k] > 0.f ? -1.f : 1.f) * s2[k];
     }
-  }
-  for (int k = 0; k < 4; ++k) { out[k][0] = out[k][1] = out[k][2] = 0.f; out[k][3] = 1.f; }
-  mat_vec(nrm, m2, bestn);
-  normalize3(nrm);
-  if (bestsep > 0.f) return 0;                 // separated: no slot can be active
-  if (besttype == 2) {
-    float e1c[3], e2c[3] = {0.f, 0.f, 0.f};
-    copy3(e1c, c);
-    for (int k = 0; k < 3; ++k) if (k != bi) { float sgn = dot3(A[k], bestn) > 0.f ? 1.f : -1.f; madd3(e1c, e1c, A[k], sgn * s1[k]); }
-    for (int k = 0; k < 3; ++k) if (k != bj) e2c[k] = (bestn[k] > 0.f ? -1.f : 1.f) * s2[k];
-    float a0[3], a1[3], b0[3], b1[3], e2[3] = {0.f, 0.f, 0.f};
-    e2[bj] = 1.f;
-    madd3(a0, e1c, A[bi], -s1[bi]); madd3(a1, e1c, A[bi], s1[bi]);
+    const float Ab[3] = {S.bbR[bi], S.bbR[3 + bi], S.bbR[6 + bi]}, e2[3] = {bj == 0 ? 1.f : 0.f, bj == 1 ? 1.f : 0.f, bj == 2 ? 1.f : 0.f};
+    float a0[3], a1[3], b0[3], b1[3];
+    madd3(a0, e1c, Ab, -s1[bi]); madd3(a1, e1c, Ab, s1[bi]);
     madd3(b0, e2c, e2, -s2[bj]); madd3(b1, e2c, e2, s2[bj]);
     SegPair sp = closest_seg_seg_v(a0, a1, b0, b1);
-    float mid[3] = {0.5f * (sp.a[0] + sp.b[0]), 0.5f * (sp.a[1] + sp.b[1]), 0.5f * (sp.a[2] + sp.b[2])}, w[3], df[3];
-    mat_vec(w, m2, mid); add3(out[0], w, p2);
+    const float mid[3] = {0.5f * (sp.a[0] + sp.b[0]), 0.5f * (sp.a[1] + sp.b[1]), 0.5f * (sp.a[2] + sp.b[2])};
+    float w[3], df[3];
+    mat_vec(w, m2, mid); add3(w, w, p2);
     sub3(df, sp.b, sp.a);
-    out[0][3] = dot3(df, bestn);
-    return out[0][3] < 0.f;
+    const float d = dot3(df, bn);
+    UNIFORM_WRITE(W) { copy3(S.bstage[slot][0], w); S.bstage[slot][0][3] = d; } END_UNIFORM_WRITE
+    return d < 0.f ? 1 : 0;
   }
-  float rc[3], Rr[9], rs[3], is[3], nref[3];
-  bool swap = besttype == 1;
+  // ---- face-face: reference face on the box owning the axis, incident face on the other ----
+  const bool swap = bl >= 3;                   // reference = box 1
+  float rc[3], Rr[9], nref[3];
   if (!swap) {
-    copy3(rc, c); for (int k = 0; k < 9; ++k) Rr[k] = R[k];
-    copy3(rs, s2); copy3(is, s1); nref[0] = -bestn[0]; nref[1] = -bestn[1]; nref[2] = -bestn[2];
+    copy3(rc, c);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Rr[k] = Rm[k];
+    nref[0] = -bn[0]; nref[1] = -bn[1]; nref[2] = -bn[2];
   } else {
-    float mc[3] = {-c[0], -c[1], -c[2]};
-    matT_vec(rc, R, mc);
-    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Rr[3 * i + j] = R[3 * j + i];
-    copy3(rs, s1); copy3(is, s2);
-    matT_vec(nref, R, bestn);
+    const float mc[3] = {-c[0], -c[1], -c[2]};
+    matT_vec(rc, Rm, mc);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) Rr[3 * i + j] = Rm[3 * j + i];
+    matT_vec(nref, Rm, bn);
   }
-  int k = 0; for (int q = 1; q < 3; ++q) if (fabsf(nref[q]) > fabsf(nref[k])) k = q;
-  int rf = 2 * k + (nref[k] > 0.f ? 0 : 1);
-  float rface[4][3], rn[3];
-  box_face(rs, rf, rface, rn);
+  const float* rs = swap ? s1 : s2; const float* is = swap ? s2 : s1;
+  int rk = 0;
+  if (fabsf(nref[1]) > fabsf(nref[0])) rk = 1;
+  if (fabsf(nref[2]) > fabsf(rk == 0 ? nref[0] : nref[1])) rk = 2;
+  const float rsg = (rk == 0 ? nref[0] : (rk == 1 ? nref[1] : nref[2])) > 0.f ? 1.f : -1.f;
+  const float rn[3] = {rk == 0 ? rsg : 0.f, rk == 1 ? rsg : 0.f, rk == 2 ? rsg : 0.f};
+  // incident face: most anti-parallel to rn (first minimum over +x,-x,+y,-y,+z,-z of the incident box)
   int inf = 0; float mind = 1e30f;
+#pragma unroll
   for (int f = 0; f < 6; ++f) {
-    int kk = f >> 1; float sgn = (f & 1) ? -1.f : 1.f;
-    float fn[3] = {sgn * Rr[kk], sgn * Rr[3 + kk], sgn * Rr[6 + kk]};
-    float dd = dot3(fn, rn);
+    const int kk = f >> 1; const float sg = (f & 1) ? -1.f : 1.f;
+    const float dd = sg * (Rr[kk] * rn[0] + Rr[3 + kk] * rn[1] + Rr[6 + kk] * rn[2]);
     if (dd < mind) { mind = dd; inf = f; }
   }
-  float iface[4][3], itmp[3], poly[16][3], poly2[16][3];
-  box_face(is, inf, iface, itmp);
-  for (int i = 0; i < 4; ++i) { mat_vec(poly[i], Rr, iface[i]); add3(poly[i], poly[i], rc); }
-  int np = 4;
+  // box face f = 2*axis + (0:+, 1:-), vertices counter-clockwise seen from outside:
+  // in-plane signs (u, w) = (-,-),(+,-),(+,+),(-,+) for +k, reversed for -k  (u = k+1, w = k+2 cyclic)
+  LANES(W, R)
+    if (lane < 8) {
+      const bool ref = lane < 4;
+      const int i = lane & 3;
+      const int k = ref ? rk : (inf >> 1);
+      const float sg = ref ? rsg : ((inf & 1) ? -1.f : 1.f);
+      const float* sz = ref ? rs : is;
+      const int ii = sg < 0.f ? 3 - i : i;
+      const float su = (ii == 1 || ii == 2) ? 1.f : -1.f, sw = ii >= 2 ? 1.f : -1.f;
+      const int u = (k + 1) % 3, w = (k + 2) % 3;
+      float v[3];
+      v[0] = k == 0 ? sg * sz[0] : (u == 0 ? su * sz[0] : sw * sz[0]);
+      v[1] = k == 1 ? sg * sz[1] : (u == 1 ? su * sz[1] : sw * sz[1]);
+      v[2] = k == 2 ? sg * sz[2] : (u == 2 ? su * sz[2] : sw * sz[2]);
+      if (ref) copy3(S.bbrf[i], v);
+      else { float t[3]; mat_vec(t, Rr, v); add3(S.bbpoly[0][i], t, rc); }
+    }
+  END_LANES
+  LANES(W, R)
+    if (lane < 4) {                            // outward side-plane normals of the reference face
+      float e[3], en[3];
+      sub3(e, S.bbrf[lane], S.bbrf[(lane + 3) & 3]);
+      cross3(en, e, rn); normalize3(en);
+      copy3(S.bben[lane], en);
+    }
+  END_LANES
+  // ---- Sutherland-Hodgman against the four side planes, polygon edges on lanes; output slots by
+  //      ballot (each edge emits its start vertex if inside, then the crossing point) ----
+  int np = 4, cur = 0;
+  // common case (a box resting on a larger one): every incident vertex is inside every side plane,
+  // so clipping would return the polygon unchanged -- 16 tests on 16 lanes and one ballot
+  const unsigned outside = warp_ballot(W, [&](int l, LaneRegs&) {
+    if (l >= 16) return false;
+    float t[3];
+    sub3(t, S.bbpoly[0][l & 3], S.bbrf[l >> 2]);
+    return dot3(t, S.bben[l >> 2]) > 0.f;
+  });
 #pragma unroll 1
-  for (int i = 0; i < 4 && np > 0; ++i) {
-    float e[3], en[3];
-    sub3(e, rface[i], rface[(i + 3) % 4]);
-    cross3(en, e, rn); normalize3(en);
-    np = clip_poly_halfplane(np, poly, poly2, rface[i], en);
-    for (int q = 0; q < np; ++q) copy3(poly[q], poly2[q]);
+  for (int i = 0; i < 4 && np > 0 && outside != 0u; ++i) {
+    LANES(W, R)
+      R.actmask = 0; R.f0 = 0.f;
+      if (lane < np) {
+        const float* a = S.bbpoly[cur][lane]; const float* b = S.bbpoly[cur][lane + 1 == np ? 0 : lane + 1];
+        float ta[3], tb[3];
+        sub3(ta, a, S.bbrf[i]); sub3(tb, b, S.bbrf[i]);
+        const float da = dot3(ta, S.bben[i]), db = dot3(tb, S.bben[i]);
+        const bool keep = da <= 0.f, cross = (da < 0.f && db > 0.f) || (da > 0.f && db < 0.f);
+        R.actmask = (keep ? 1 : 0) | (cross ? 2 : 0);
+        R.f0 = cross ? da / (da - db) : 0.f;
+      }
+    END_LANES
+    const unsigned mk = warp_ballot(W, [](int, LaneRegs& R) { return (R.actmask & 1) != 0; });
+    const unsigned mx = warp_ballot(W, [](int, LaneRegs& R) { return (R.actmask & 2) != 0; });
+    LANES(W, R)
+      if (lane < np && R.actmask) {
+        const float* a = S.bbpoly[cur][lane]; const float* b = S.bbpoly[cur][lane + 1 == np ? 0 : lane + 1];
+        const unsigned below = (1u << lane) - 1u;
+        int o = KPOPC(mk & below) + KPOPC(mx & below);
+        if (R.actmask & 1) { copy3(S.bbpoly[cur ^ 1][o], a); ++o; }
+        if (R.actmask & 2) { float ab[3]; sub3(ab, b, a); madd3(S.bbpoly[cur ^ 1][o], a, ab, R.f0); }
+      }
+    END_LANES
+    np = KPOPC(mk) + KPOPC(mx); cur ^= 1;
   }
   if (np == 0) return 0;
-  float pref[16][3], depth[16]; bool mask[16]; int idx[4];
-  for (int i = 0; i < np; ++i) {
-    float tt[3]; sub3(tt, poly[i], rface[0]);
-    float h = dot3(tt, rn);
-    depth[i] = -h; mask[i] = h < 0.f;
-    madd3(pref[i], poly[i], rn, -h);
+  // ---- penetrating vertices projected on the reference face; 4-point manifold ----
+  LANES(W, R)
+    R.f0 = -1e6f; R.actmask = 0;
+    if (lane < np) {
+      float tt[3];
+      sub3(tt, S.bbpoly[cur][lane], S.bbrf[0]);
+      const float h = dot3(tt, rn);
+      madd3(S.bbpref[lane], S.bbpoly[cur][lane], rn, -h);
+      S.bbpref[lane][3] = h;
+      R.actmask = h < 0.f;
+      R.f0 = h < 0.f ? 0.f : -1e6f;            // dm
+    }
+  END_LANES
+  if (np <= 4) {
+    // With at most four vertices MJX's 4-point rule returns exactly the penetrating ones (every
+    // later pick prefers a not-yet-chosen vertex); emit them in polygon order.
+    const unsigned pen = warp_ballot(W, [&](int l, LaneRegs& R) { return l < np && R.actmask != 0; });
+    LANES(W, R)
+      if (pen & (1u << lane)) {
+        const int q = KPOPC(pen & ((1u << lane) - 1u));
+        float w[3];
+        if (swap) { float u[3]; mat_vec(u, Rm, S.bbpref[lane]); add3(u, u, c); mat_vec(w, m2, u); }
+        else mat_vec(w, m2, S.bbpref[lane]);
+        add3(w, w, p2);
+        copy3(S.bstage[slot][q], w); S.bstage[slot][q][3] = S.bbpref[lane][3];
+      }
+    END_LANES
+    return KPOPC(pen);
   }
-  manifold_points(np, pref, mask, rn, idx);
+  // lanes >= np must never win: give them -inf in every argmax
+  const int ia = warp_argmax_first8(W, [&](int l, LaneRegs& R) { return l < np ? R.f0 : -INFINITY; });
+  LANES(W, R)
+    R.f1 = -INFINITY;
+    if (lane < np) { float t[3]; sub3(t, S.bbpref[ia], S.bbpref[lane]); R.f1 = dot3(t, t) + R.f0; }
+  END_LANES
+  const int ib = warp_argmax_first8(W, [](int, LaneRegs& R) { return R.f1; });
+  float ab[3];
+  { float t[3]; sub3(t, S.bbpref[ia], S.bbpref[ib]); cross3(ab, rn, t); }
+  LANES(W, R)
+    R.f1 = -INFINITY;
+    if (lane < np) { float ap[3]; sub3(ap, S.bbpref[ia], S.bbpref[lane]); R.f1 = fabsf(dot3(ap, ab)) + R.f0; }
+  END_LANES
+  const int ic = warp_argmax_first8(W, [](int, LaneRegs& R) { return R.f1; });
+  float ac[3], bc[3];
+  { float t[3]; sub3(t, S.bbpref[ia], S.bbpref[ic]); cross3(ac, rn, t); sub3(t, S.bbpref[ib], S.bbpref[ic]); cross3(bc, rn, t); }
+  LANES(W, R)
+    R.f1 = -INFINITY;
+    if (lane < np) {
+      float bp[3], ap[3];
+      sub3(bp, S.bbpref[ib], S.bbpref[lane]); sub3(ap, S.bbpref[ia], S.bbpref[lane]);
+      R.f1 = fmaxf(fabsf(dot3(bp, bc)), fabsf(dot3(ap, ac))) + R.f0 - ((lane == ia || lane == ib || lane == ic) ? 2e6f : 0.f);
+    }
+  END_LANES
+  const int id = warp_argmax_first8(W, [](int, LaneRegs& R) { return R.f1; });
+  const int idx[4] = {ia, ib, ic, id};
   int nact = 0;
+#pragma unroll
   for (int q = 0; q < 4; ++q) {
-    int i = idx[q]; bool uniq = true;
-    for (int z = 0; z < q; ++z) if (idx[z] == i) uniq = false;
-    if (!mask[i] || !uniq) continue;
+    bool uniq = true;
+#pragma unroll
+    for (int z = 0; z < q; ++z) if (idx[z] == idx[q]) uniq = false;
+    const float h = S.bbpref[idx[q]][3];
+    if (!(h < 0.f) || !uniq) continue;
     float w[3];
-    if (swap) { float u[3]; mat_vec(u, R, pref[i]); add3(u, u, c); mat_vec(w, m2, u); }
-    else mat_vec(w, m2, pref[i]);
-    add3(out[q], w, p2);
-    out[q][3] = -depth[i];
+    if (swap) { float u[3]; mat_vec(u, Rm, S.bbpref[idx[q]]); add3(u, u, c); mat_vec(w, m2, u); }
+    else mat_vec(w, m2, S.bbpref[idx[q]]);
+    add3(w, w, p2);
+    UNIFORM_WRITE(W) { copy3(S.bstage[slot][q], w); S.bstage[slot][q][3] = h; } END_UNIFORM_WRITE
     ++nact;
   }
   return nact;
@@ -588,6 +726,64 @@ KFN float row_J(const WarpSmemT<NC>& S, int r, int d) {
   return (q & 1) ? jn - jt : jn + jt;
 }
 
+// Dense 6x6 SPD solve in registers, executed redundantly by every lane (uniform): for matrices this
+// small a straight-line Cholesky beats a lane-distributed one, whose ~50 dependent shuffles cost more
+// than the arithmetic (measured: profiles/README.md).  A: lower triangle read with row stride `ld`.
+struct Vec6 { float v[6]; };
+KNOINLINE Vec6 chol_solve6(const float* A, int ld, const float* rhs) {
+  float L[6][6], y[6];
+  Vec6 x;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+#pragma unroll
+    for (int j = 0; j <= i; ++j) {
+      float s = A[i * ld + j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
+      if (i == j) { const float d = sqrtf(s); L[i][i] = 1.f / d; }    // store the reciprocal of the diagonal
+      else L[i][j] = s * L[j][j];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { float s = rhs[i]; for (int k = 0; k < i; ++k) s -= L[i][k] * y[k]; y[i] = s * L[i][i]; }
+#pragma unroll
+  for (int i = 5; i >= 0; --i) { float s = y[i]; for (int k = i + 1; k < 6; ++k) s -= L[k][i] * x.v[k]; x.v[i] = s * L[i][i]; }
+  return x;
+}
+
+// Cholesky solve with one matrix row per lane, all in registers.  N = 12: lanes 0..11 hold the
+// rows of one 12x12 SPD matrix (R.h[k] = A[lane][k], k <= lane).  N = 6: two independent 6x6 systems
+// at once, rows of the first on lanes 0..5 and of the second on lanes 6..11 (R.h[k] = A[lane][base+k]).
+// In: R.h, R.f0 = right-hand side.  Out: R.f0 = A^-1 rhs (R.h = Cholesky factor, lower).
+template <int N>
+KFN void chol_solve_rows(Warp& W) {
+  static_assert(N == 6 || N == 12, "N");
+  auto base = [](int l) { return (N == 6 && l >= 6 && l < 12) ? 6 : 0; };
+  auto loc = [&](int l) { return l - base(l); };
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    warp_shfl_each(W, [&](int, LaneRegs& R) { return R.h[j]; }, [&](int l) { return base(l) + j; },
+                   [&](int l, LaneRegs& R, float d) { const float dj = sqrtf(d); R.h[j] = (loc(l) == j) ? dj : R.h[j] / dj; });
+#pragma unroll
+    for (int k = j + 1; k < N; ++k)
+      warp_shfl_each(W, [&](int, LaneRegs& R) { return R.h[j]; }, [&](int l) { return base(l) + k; },
+                     [&](int l, LaneRegs& R, float lkj) { if (loc(l) >= k) R.h[k] -= R.h[j] * lkj; });
+  }
+#pragma unroll
+  for (int k = 0; k < N; ++k)                  // forward substitution L y = rhs
+    warp_shfl_each(W, [&](int, LaneRegs& R) { return R.f0 / R.h[k]; }, [&](int l) { return base(l) + k; },
+                   [&](int l, LaneRegs& R, float yk) { if (loc(l) == k) R.f0 = yk; else if (loc(l) > k) R.f0 -= R.h[k] * yk; });
+#pragma unroll
+  for (int k = N - 1; k >= 0; --k) {           // back substitution L^T x = y, column k of L^T lives in lane base+k
+    warp_shfl_each(W, [&](int, LaneRegs& R) { return R.f0 / R.h[k]; }, [&](int l) { return base(l) + k; },
+                   [&](int l, LaneRegs& R, float xk) { R.f1 = xk; if (loc(l) == k) R.f0 = xk; });
+#pragma unroll
+    for (int i = 0; i < k; ++i)
+      warp_shfl_each(W, [&](int, LaneRegs& R) { return R.h[i] * R.f1; }, [&](int l) { return base(l) + k; },
+                     [&](int l, LaneRegs& R, float p) { if (loc(l) == i) R.f0 -= p; });
+  }
+}
+
 struct LSPoint { float alpha, cost, d0, d1; };
 KFN bool in_bracket(const LSPoint& x, const LSPoint& y) {
   return ((x.d0 < y.d0) && (y.d0 < 0.f)) || ((x.d0 > y.d0) && (y.d0 > 0.f));
@@ -639,43 +835,6 @@ KNOINLINE void emit_robot_contacts(const KModel& m, WarpSmemT<NC>& S, int lane, 
     }
   }
 }
-// free-box pairs of one lane: full contact generation into the staging area; returns #active
-template <int NC>
-KNOINLINE int box_pair_contacts(const KModel& m, WarpSmemT<NC>& S, int lane) {
-  const int ty = m.bp_type[lane], a = m.bp_a[lane];
-  const float* bp = S.qpos + KM_NL;
-  const float rb = sqrtf(m.fb_size[0] * m.fb_size[0] + m.fb_size[1] * m.fb_size[1] + m.fb_size[2] * m.fb_size[2]);
-  int n = 0;
-  for (int k = 0; k < 4; ++k) S.bstage[lane][k][3] = 1.f;
-  if (ty == KB_PLANE_BOX) {
-    float t[3]; sub3(t, bp, m.plane_pos);
-    if (dot3(t, m.plane_n) < rb) { n = plane_box(m.plane_pos, m.plane_n, bp, S.bmat, m.fb_size, S.bstage[lane]); copy3(S.bnrm[lane], m.plane_n); }
-  } else {
-    float t[3]; sub3(t, bp, m.sb_pos[a]);
-    const float ra = sqrtf(m.sb_size[a][0] * m.sb_size[a][0] + m.sb_size[a][1] * m.sb_size[a][1] + m.sb_size[a][2] * m.sb_size[a][2]);
-    if (dot3(t, t) < (ra + rb) * (ra + rb)) {
-      if (ty == KB_BOX_BOX) n = box_box(m.sb_pos[a], m.sb_mat[a], m.sb_size[a], bp, S.bmat, m.fb_size, S.bstage[lane], S.bnrm[lane]);
-      else n = box_box(bp, S.bmat, m.fb_size, m.sb_pos[a], m.sb_mat[a], m.sb_size[a], S.bstage[lane], S.bnrm[lane]);
-    }
-  }
-  return n;
-}
-template <int NC>
-KNOINLINE void emit_box_contacts(const KModel& m, WarpSmemT<NC>& S, int lane, int o) {
-  const bool sw = m.bp_type[lane] == KB_BOX_BOX_SWAP;
-#pragma unroll 1
-  for (int k = 0; k < 4; ++k) {
-    if (!(S.bstage[lane][k][3] < 0.f)) continue;
-    if (o < NC) {
-      float* g = S.cgeo[o];
-      copy3(g, S.bstage[lane][k]); copy3(g + 3, S.bnrm[lane]);
-      make_tangents(S.bnrm[lane], g + 6, g + 9);
-      g[12] = S.bstage[lane][k][3]; g[13] = m.fb_invw; g[14] = sw ? (float)KM_NL : -1.f; g[15] = sw ? -1.f : (float)KM_NL;
-    }
-    ++o;
-  }
-}
-
 // per-step observation / cost hooks of the narrow phase
 struct StepIO {
   bool first;                 // t == 0: no previous distance yet
@@ -687,21 +846,27 @@ struct StepIO {
 // collision-cost contribution of this step added to R.cost_c (mjx_planner.py:287-296).
 template <int NC>
 KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& io) {
-  // ---- P1: serial joint chain (uniform) ----
+  PHASE(W, 1);
+  // ---- P1: joint chain.  Local link rotations (body quat x joint rotation) on six lanes, then the
+  //      serial composition down the chain in uniform code ----
+  LANES(W, R)
+    if (lane < KM_NL) {
+      float sn, cs, qj[4];
+      k_sincos(0.5f * S.qpos[lane], &sn, &cs);
+      qj[0] = cs; qj[1] = sn * m.l_axis[lane][0]; qj[2] = sn * m.l_axis[lane][1]; qj[3] = sn * m.l_axis[lane][2];
+      quat_mul(S.lquat[lane], m.l_quat[lane], qj);
+    }
+  END_LANES
   {
     float pq[4] = {m.base_quat[0], m.base_quat[1], m.base_quat[2], m.base_quat[3]};
     float pp[3] = {m.base_pos[0], m.base_pos[1], m.base_pos[2]}, pm[9];
     quat_to_mat(pm, pq);
-    USYNC();
 #pragma unroll 1
     for (int i = 0; i < KM_NL; ++i) {
-      float p[3], q[4], t[3], qj[4], mat[9];
+      float p[3], q[4], t[3], lq[4], mat[9];
+      lq[0] = S.lquat[i][0]; lq[1] = S.lquat[i][1]; lq[2] = S.lquat[i][2]; lq[3] = S.lquat[i][3];
       mat_vec(t, pm, m.l_pos[i]); add3(p, pp, t);
-      quat_mul(q, pq, m.l_quat[i]);
-      float sn, cs;
-      k_sincos(0.5f * S.qpos[i], &sn, &cs);
-      qj[0] = cs; qj[1] = sn * m.l_axis[i][0]; qj[2] = sn * m.l_axis[i][1]; qj[3] = sn * m.l_axis[i][2];
-      quat_mul(q, q, qj);
+      quat_mul(q, pq, lq);
       quat_to_mat(mat, q);
       UNIFORM_WRITE(W) {
         copy3(S.lpos[i], p);
@@ -713,6 +878,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
       for (int k = 0; k < 9; ++k) pm[k] = mat[k];
     }
   }
+  PHASE(W, 2);
   // ---- P2: per-link spatial quantities, capsule end points, box frame ----
   LANES(W, R)
     if (lane < KM_NL) {
@@ -760,19 +926,26 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
       quat_to_mat(S.bmat, q);
     }
   END_LANES
-  // ---- P3: composite inertias; link velocities and cdof_dot (BD.3, BD.4) ----
+  // ---- P3: composite inertias and link velocities, one (link, component) item per lane (BD.3, BD.4) ----
   LANES(W, R)
-    if (lane < KM_NL) {
-      for (int k = 0; k < 10; ++k) { float s = 0.f; for (int b = lane; b < KM_NL; ++b) s += S.cinert[b][k]; S.crb[lane][k] = s; }
-    } else if (lane >= 8 && lane < 8 + KM_NL) {
-      const int i = lane - 8;
-      float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int b = 0; b < i; ++b) for (int k = 0; k < 6; ++k) v[k] += S.cdof[b][k] * S.qvel[b];
-      cross_motion(S.cdofdot[i], v, S.cdof[i]);
-      for (int k = 0; k < 6; ++k) S.cvel[i][k] = v[k] + S.cdof[i][k] * S.qvel[i];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int e = lane + 32 * q;
+      if (e < KM_NL * 10) {
+        const int i = e / 10, k = e - 10 * i;
+        float s = 0.f;
+        for (int b = i; b < KM_NL; ++b) s += S.cinert[b][k];
+        S.crb[i][k] = s;
+      }
+      if (e < KM_NL * 6) {
+        const int i = e / 6, k = e - 6 * i;
+        float v = 0.f;
+        for (int b = 0; b <= i; ++b) v += S.cdof[b][k] * S.qvel[b];
+        S.cvel[i][k] = v;
+      }
     }
   END_LANES
-  // ---- P4: robot inertia matrix entries; per-link bias wrench (BD.3, BD.5 without gravity) ----
+  // ---- P4: robot inertia matrix entries (lanes 0-20), cdof_dot (lanes 24-29) ----
   LANES(W, R)
     if (lane < 21) {
       int i = 0, j = lane;
@@ -784,8 +957,16 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
       S.Mr[i][j] = v; S.Mr[j][i] = v;
     } else if (lane >= 24 && lane < 24 + KM_NL) {
       const int i = lane - 24;
+      if (i == 0) { for (int k = 0; k < 6; ++k) S.cdofdot[0][k] = 0.f; }
+      else cross_motion(S.cdofdot[i], S.cvel[i - 1], S.cdof[i]);
+    }
+  END_LANES
+  // ---- P4b: per-link bias wrench (BD.5 without gravity) ----
+  LANES(W, R)
+    if (lane < KM_NL) {
+      const int i = lane;
       float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, f[6], t[6], t2[6];
-      for (int b = 0; b <= i; ++b) for (int k = 0; k < 6; ++k) acc[k] += S.cdofdot[b][k] * S.qvel[b];
+      for (int b = 1; b <= i; ++b) for (int k = 0; k < 6; ++k) acc[k] += S.cdofdot[b][k] * S.qvel[b];
       mul_inert(f, S.cinert[i], acc);
       mul_inert(t, S.cinert[i], S.cvel[i]);
       cross_force(t2, S.cvel[i], t);
@@ -809,29 +990,18 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
       }
     }
   END_LANES
-  // ---- P6: qacc_smooth = M^-1 qfrc_smooth (6x6 Cholesky, uniform; box block is diagonal) ----
+  PHASE(W, 3);
+  // ---- P6: qacc_smooth = M^-1 qfrc_smooth (robot block by a uniform 6x6 Cholesky; box block is diagonal) ----
   {
-    float L[KM_NL][KM_NL], y[KM_NL], x[KM_NL];
     USYNC();
-#pragma unroll
-    for (int i = 0; i < KM_NL; ++i) {
-#pragma unroll
-      for (int j = 0; j <= i; ++j) {
-        float s = S.Mr[i][j];
-#pragma unroll
-        for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
-        L[i][j] = (i == j) ? sqrtf(s) : s / L[j][j];
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < KM_NL; ++i) { float s = S.fs[i]; for (int k = 0; k < i; ++k) s -= L[i][k] * y[k]; y[i] = s / L[i][i]; }
-#pragma unroll
-    for (int i = KM_NL - 1; i >= 0; --i) { float s = y[i]; for (int k = i + 1; k < KM_NL; ++k) s -= L[k][i] * x[k]; x[i] = s / L[i][i]; }
+    const Vec6 x = chol_solve6(&S.Mr[0][0], KM_NL, S.fs);
     UNIFORM_WRITE(W) {
-      for (int i = 0; i < KM_NL; ++i) S.as[i] = x[i];
+      for (int i = 0; i < KM_NL; ++i) S.as[i] = x.v[i];
       for (int k = 0; k < 3; ++k) { S.as[KM_NL + k] = S.fs[KM_NL + k] / m.fb_mass; S.as[KM_NL + 3 + k] = S.fs[KM_NL + 3 + k] / m.fb_inertia[k]; }
     } END_UNIFORM_WRITE
   }
+  PHASE_ALIGN(1);
+  PHASE(W, 4);
   // ---- N1: narrow phase (distances only) + collision cost of this step ----
   LANES(W, R)
     int nact = 0, actmask = 0;
@@ -873,23 +1043,74 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
       }
     }
     R.cost_c += cc;
-    R.actmask = actmask;
-    if (m.has_box && lane < m.nbpair) nact += box_pair_contacts<NC>(m, S, lane);
-    R.nact = nact;
+    R.h[0] = __int_as_float(actmask);          // parked: the cooperative box colliders below reuse the scratch fields
+    R.h[1] = __int_as_float(nact);
   END_LANES
-  const int ncon_all = warp_excl_scan(W, [](int, LaneRegs& R) { return R.nact; }, [](int, LaneRegs& R, int o) { R.off = o; });
-  const int ncon = ncon_all < NC ? ncon_all : NC;
-  // ---- N2: full contact records for the active slots (divergent, rare) ----
-  LANES(W, R)
-    if (R.nact > 0) {
-      int o = R.off;
-      if (R.actmask) {
-        emit_robot_contacts<NC>(m, S, lane, R.actmask, o);
-        o += KPOPC((unsigned)R.actmask);
+  PHASE_ALIGN(4);
+  PHASE(W, 5);
+  // free-box pairs: broad phase for all pairs at once (one lane per pair), then the cooperative
+  // narrow phase only for the pairs that pass
+  if (m.has_box) {
+    const float* bp = S.qpos + KM_NL;
+    LANES(W, R)
+      if (lane < 4 * m.nbpair) S.bstage[lane >> 2][lane & 3][3] = 1.f;
+    END_LANES
+    const unsigned cand = warp_ballot(W, [&](int q, LaneRegs&) {
+      if (q >= m.nbpair) return false;
+      if (m.bp_type[q] == KB_PLANE_BOX) {
+        const float rb = sqrtf(m.fb_size[0] * m.fb_size[0] + m.fb_size[1] * m.fb_size[1] + m.fb_size[2] * m.fb_size[2]);
+        float t[3]; sub3(t, bp, m.plane_pos);
+        return dot3(t, m.plane_n) < rb;
       }
-      if (m.has_box && lane < m.nbpair) emit_box_contacts<NC>(m, S, lane, o);
+      // world AABBs (extent_i = sum_j |R_ij| size_j); disjoint boxes cannot have an active slot
+      const int a = m.bp_a[q];
+      bool overlap = true;
+      for (int i = 0; i < 3; ++i) {
+        const float ea = fabsf(m.sb_mat[a][3 * i]) * m.sb_size[a][0] + fabsf(m.sb_mat[a][3 * i + 1]) * m.sb_size[a][1] + fabsf(m.sb_mat[a][3 * i + 2]) * m.sb_size[a][2];
+        const float eb = fabsf(S.bmat[3 * i]) * m.fb_size[0] + fabsf(S.bmat[3 * i + 1]) * m.fb_size[1] + fabsf(S.bmat[3 * i + 2]) * m.fb_size[2];
+        if (fabsf(bp[i] - m.sb_pos[a][i]) > ea + eb) overlap = false;
+      }
+      return overlap;
+    });
+#pragma unroll 1
+    for (unsigned rem = cand; rem != 0u; rem &= rem - 1u) {
+      const int q = KFFS(rem) - 1;
+      const int ty = m.bp_type[q], a = m.bp_a[q];
+      if (ty == KB_PLANE_BOX) {
+        LANES(W, R)
+          if (lane == q) { plane_box(m.plane_pos, m.plane_n, bp, S.bmat, m.fb_size, S.bstage[q]); copy3(S.bnrm[q], m.plane_n); }
+        END_LANES
+      } else if (ty == KB_BOX_BOX) box_box_warp<NC>(W, S, q, m.sb_pos[a], m.sb_mat[a], m.sb_size[a], bp, S.bmat, m.fb_size);
+      else box_box_warp<NC>(W, S, q, bp, S.bmat, m.fb_size, m.sb_pos[a], m.sb_mat[a], m.sb_size[a]);
+    }
+  }
+  LANES(W, R)
+    R.actmask = __float_as_int(R.h[0]);
+    R.nact = __float_as_int(R.h[1]);
+  END_LANES
+  // list positions: robot contacts first (lane-major), then the staged free-box contacts (pair-major)
+  const int nrob = warp_excl_scan(W, [](int, LaneRegs& R) { return R.nact; }, [](int, LaneRegs& R, int o) { R.off = o; });
+  const unsigned bmask = m.has_box ? warp_ballot(W, [&](int l, LaneRegs&) { return l < 4 * m.nbpair && S.bstage[l >> 2][l & 3][3] < 0.f; }) : 0u;
+  const int ncon_all = nrob + KPOPC(bmask);
+  const int ncon = ncon_all < NC ? ncon_all : NC;
+  PHASE(W, 6);
+  // ---- N2: full contact records for the active slots (divergent, rare for robot slots) ----
+  LANES(W, R)
+    if (R.nact > 0) emit_robot_contacts<NC>(m, S, lane, R.actmask, R.off);
+    if (bmask & (1u << lane)) {
+      const int o = nrob + KPOPC(bmask & ((1u << lane) - 1u)), q = lane >> 2;
+      if (o < NC) {
+        const bool sw = m.bp_type[q] == KB_BOX_BOX_SWAP;
+        float* g = S.cgeo[o];
+        const float* st = S.bstage[q][lane & 3];
+        copy3(g, st); copy3(g + 3, S.bnrm[q]);
+        make_tangents(S.bnrm[q], g + 6, g + 9);
+        g[12] = st[3]; g[13] = m.fb_invw; g[14] = sw ? (float)KM_NL : -1.f; g[15] = sw ? -1.f : (float)KM_NL;
+      }
     }
   END_LANES
+  PHASE_ALIGN(2);
+  PHASE(W, 7);
   // ---- C1: joint-limit rows ----
   LANES(W, R)
     R.nact = 0;
@@ -947,7 +1168,15 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
       row_params(m, g[12], w, vel, D, aref);
       S.rD[r] = D; S.rAref[r] = aref;
     }
+    // does any active contact join a robot link and the free box?  (then H is a full 12x12)
+    R.f2 = 0.f;
+    for (int c = lane; c < ncon; c += 32) {
+      const int l1 = (int)S.cgeo[c][14], l2 = (int)S.cgeo[c][15];
+      if ((l1 == KM_NL && l2 >= 0 && l2 < KM_NL) || (l2 == KM_NL && l1 >= 0 && l1 < KM_NL)) R.f2 = 1.f;
+    }
   END_LANES
+  const bool coupled = warp_sum(W, [](int, LaneRegs& R) { return R.f2; }) > 0.f;
+  PHASE(W, 8);
   // ---- S1: warm start vs smooth start (B.6) ----
   LANES(W, R)
     float cw = 0.f, cs = 0.f;
@@ -982,12 +1211,36 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
     }
     if (lane < KM_NV) S.qacc[lane] = use_warm ? S.warm[lane] : S.as[lane];
   END_LANES
+  PHASE(W, 9);
   // ---- S3: gradient and Hessian over the active rows (BD.9) ----
+  // per contact: the pyramid-edge weights w_q = D [Jaref_q < 0] and the force sums that multiply
+  // Jn, mu*Jt1, mu*Jt2; the contact position / frame slots of cgeo are dead after C2 and are reused.
+  LANES(W, R)
+#pragma unroll 1
+    for (int c = lane; c < ncon; c += 32) {
+      const int r0 = nlim + 4 * c;
+      float w[4], f[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const float ja = S.rJaref[r0 + q]; w[q] = ja < 0.f ? S.rD[r0 + q] : 0.f; f[q] = -w[q] * ja; }
+      float* g = S.cgeo[c];
+      const int l1 = (int)g[14], l2 = (int)g[15];
+      g[0] = f[0] + f[1] + f[2] + f[3]; g[1] = f[0] - f[1]; g[2] = f[2] - f[3];
+      g[3] = w[0]; g[4] = w[1]; g[5] = w[2]; g[6] = w[3];
+      g[7] = __int_as_float((((l1 >= 0 && l1 < KM_NL) || (l2 >= 0 && l2 < KM_NL)) ? 1 : 0) | ((l1 == KM_NL || l2 == KM_NL) ? 2 : 0));
+    }
+  END_LANES
   LANES(W, R)
     if (lane < KM_NV) {
+      const int myblk = lane < KM_NL ? 1 : 2;
       float fc = 0.f;
+      for (int r = 0; r < nlim; ++r) { const float ja = S.rJaref[r]; if (ja < 0.f && S.limdof[r] == lane) fc += S.limsign[r] * (-S.rD[r] * ja); }
 #pragma unroll 1
-      for (int r = 0; r < nrow; ++r) { float ja = S.rJaref[r]; if (ja < 0.f) fc += row_J(S, r, lane) * (-S.rD[r] * ja); }
+      for (int c = 0; c < ncon; ++c) {
+        const float* g = S.cgeo[c];
+        if (!(__float_as_int(g[7]) & myblk)) continue;
+        const float* J = S.cJ[c];
+        fc += J[lane] * g[0] + J[12 + lane] * g[1] + J[24 + lane] * g[2];
+      }
       S.grad[lane] = S.Ma[lane] - S.fs[lane] - fc;
     }
 #pragma unroll
@@ -995,67 +1248,43 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
       const int i = (R.tri >> (8 * q)) & 15, j = (R.tri >> (8 * q + 4)) & 15;
       if (i < KM_NV) {
         float h = M_entry<NC>(m, S, i, j);
+        const int need = (i < KM_NL ? 1 : 2) | (j < KM_NL ? 1 : 2);
         for (int r = 0; r < nlim; ++r) if (S.rJaref[r] < 0.f && S.limdof[r] == i && i == j) h += S.rD[r];
 #pragma unroll 1
         for (int c = 0; c < ncon; ++c) {
+          const float* g = S.cgeo[c];
+          if ((__float_as_int(g[7]) & need) != need) continue;
           const float* J = S.cJ[c];
-          const int r0 = nlim + 4 * c;
-          float w0 = S.rJaref[r0] < 0.f ? S.rD[r0] : 0.f, w1 = S.rJaref[r0 + 1] < 0.f ? S.rD[r0 + 1] : 0.f;
-          float w2 = S.rJaref[r0 + 2] < 0.f ? S.rD[r0 + 2] : 0.f, w3 = S.rJaref[r0 + 3] < 0.f ? S.rD[r0 + 3] : 0.f;
-          float ni = J[i], nj = J[j], ai = J[12 + i], aj = J[12 + j], bi = J[24 + i], bj = J[24 + j];
-          h += w0 * (ni + ai) * (nj + aj) + w1 * (ni - ai) * (nj - aj) + w2 * (ni + bi) * (nj + bj) + w3 * (ni - bi) * (nj - bj);
+          const float ni = J[i], nj = J[j], ai = J[12 + i], aj = J[12 + j], bi = J[24 + i], bj = J[24 + j];
+          h += g[3] * (ni + ai) * (nj + aj) + g[4] * (ni - ai) * (nj - aj) + g[5] * (ni + bi) * (nj + bj) + g[6] * (ni - bi) * (nj - bj);
         }
         S.H[i][j] = h;
       }
     }
   END_LANES
-  // ---- S4: Cholesky of H with lane i holding row i in registers (shuffles, no shared-memory
-  //      round trips), then search = -H^-1 grad ----
-  LANES(W, R)
-#pragma unroll
-    for (int k = 0; k < KM_NV; ++k) R.h[k] = (lane < KM_NV && k <= lane) ? S.H[lane][k] : 0.f;
-  END_LANES
-#pragma unroll
-  for (int j = 0; j < KM_NV; ++j) {
-    const float dj = sqrtf(warp_bcast(W, j, [&](int, LaneRegs& R) { return R.h[j]; }));
-    const float idj = 1.f / dj;
-    RLANES(W, R)
-      R.h[j] = (lane == j) ? dj : R.h[j] * idj;          // column j of L (rows > j), diagonal
-    END_RLANES
-#pragma unroll
-    for (int k = j + 1; k < KM_NV; ++k) {
-      const float lkj = warp_bcast(W, k, [&](int, LaneRegs& R) { return R.h[j]; });
-      RLANES(W, R)
-        if (lane >= k) R.h[k] -= R.h[j] * lkj;
-      END_RLANES
-    }
-  }
-  LANES(W, R)
-    if (lane < KM_NV) {
-#pragma unroll
-      for (int k = 0; k < KM_NV; ++k) if (k <= lane) S.H[lane][k] = R.h[k];
-    }
-    R.f0 = lane < KM_NV ? S.grad[lane] : 0.f;
-  END_LANES
-#pragma unroll
-  for (int k = 0; k < KM_NV; ++k) {            // forward substitution L y = grad
-    const float yk = warp_bcast(W, k, [&](int, LaneRegs& R) { return R.f0 / R.h[k]; });
-    RLANES(W, R)
-      if (lane == k) R.f0 = yk;
-      else if (lane > k) R.f0 -= R.h[k] * yk;
-    END_RLANES
-  }
-#pragma unroll 1
-  for (int k = KM_NV - 1; k >= 0; --k) {       // back substitution L^T x = y
-    const float xk = warp_bcast(W, k, [&](int l, LaneRegs& R) { return R.f0 / S.H[l < KM_NV ? l : 0][l < KM_NV ? l : 0]; });
+  PHASE(W, 10);
+  // ---- S4: search = -H^-1 grad, Cholesky with one row per lane in registers.  Robot and box
+  //      blocks only couple through a robot/box contact; otherwise the two 6x6 blocks are factorised
+  //      side by side (6 column steps instead of 12) ----
+  if (coupled) {
     LANES(W, R)
-      if (lane == k) R.f0 = xk;
-      else if (lane < k) R.f0 -= S.H[k][lane] * xk;
+#pragma unroll
+      for (int k = 0; k < KM_NV; ++k) R.h[k] = (lane < KM_NV && k <= lane) ? S.H[lane][k] : 0.f;
+      R.f0 = lane < KM_NV ? S.grad[lane] : 0.f;
     END_LANES
+    chol_solve_rows<12>(W);
+    LANES(W, R)
+      if (lane < KM_NV) S.search[lane] = -R.f0;
+    END_LANES
+  } else {
+    USYNC();
+    const Vec6 xr = chol_solve6(&S.H[0][0], KM_NV, S.grad);
+    const Vec6 xb = chol_solve6(&S.H[KM_NL][KM_NL], KM_NV, S.grad + KM_NL);
+    UNIFORM_WRITE(W) {
+      for (int i = 0; i < KM_NL; ++i) { S.search[i] = -xr.v[i]; S.search[KM_NL + i] = -xb.v[i]; }
+    } END_UNIFORM_WRITE
   }
-  LANES(W, R)
-    if (lane < KM_NV) S.search[lane] = -R.f0;
-  END_LANES
+  PHASE(W, 11);
   // ---- S5: line search (BD.10) ----
   LANES(W, R)
     R.f0 = R.f1 = R.f2 = 0.f;
@@ -1203,6 +1432,7 @@ KFN void rollout_sample(Warp& W, const KModel& m, WarpSmemT<NC>& S, const Rollou
     }
     if (lane == 0) S.flags = 0;
     R.cost_c = 0.f;
+    R.td = lane < KM_NL ? A.thetadot[lane * A.T] : 0.f;
   END_LANES
   float tq[4] = {A.target_rot[0], A.target_rot[1], A.target_rot[2], A.target_rot[3]};
   {
@@ -1212,14 +1442,20 @@ KFN void rollout_sample(Warp& W, const KModel& m, WarpSmemT<NC>& S, const Rollou
   float cost_g = 0.f, cost_r = 0.f;
 #pragma unroll 1
   for (int t = 0; t < A.T; ++t) {
-    STEP_ALIGN();
+    PHASE(W, 13);
+    if ((t % CEMK_SYNC_EVERY) == 0) { STEP_ALIGN(); }
+    PHASE(W, 0);
     LANES(W, R)
-      if (lane < KM_NL) S.qvel[lane] = A.thetadot[lane * A.T + t];       // mjx_planner.py:254
+      if (lane < KM_NL) {
+        S.qvel[lane] = R.td;                                             // mjx_planner.py:254
+        if (t + 1 < A.T) R.td = A.thetadot[lane * A.T + t + 1];          // consumed next step: latency hidden
+      }
     END_LANES
     StepIO io;
     io.first = t == 0;
     io.collision_row = (A.collision && A.live) ? A.collision + (size_t)t * m.nslot_robot : nullptr;
     step_forward<NC>(W, m, S, io);
+    PHASE(W, 12);
     // pre-step observations (mjx_planner.py:259-261) and running cost (:277-285)
     {
       float tcp[3], tv[3], eq[4];

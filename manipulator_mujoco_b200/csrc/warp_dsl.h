@@ -21,6 +21,7 @@
 #define KFN static inline
 #define KNOINLINE static
 #define STEP_ALIGN()
+#define PHASE_ALIGN(bit)
 #define LANES(W, R) for (int lane = 0; lane < 32; ++lane) { auto& R = (W).regs[lane]; (void)R;
 #define END_LANES }
 #define RLANES(W, R) LANES(W, R)
@@ -30,6 +31,9 @@
 #define USYNC()
 #define KRSQRT(x) (1.0f / sqrtf(x))
 #define KPOPC(x) __builtin_popcount(x)
+#define KFFS(x) __builtin_ffs((int)(x))
+static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
+static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
 #else
 #define KFN __device__ __forceinline__
 #define KNOINLINE __device__ __noinline__
@@ -37,6 +41,13 @@
 #define STEP_ALIGN() __syncthreads()     // keep the warps of a CTA on the same code (instruction-cache locality)
 #else
 #define STEP_ALIGN()
+#endif
+// optional extra CTA-wide re-alignments inside a step, selected by the bits of CEMK_PHASE_SYNC
+// (only at points every warp reaches)
+#if defined(CEMK_STEP_SYNC) && defined(CEMK_PHASE_SYNC)
+#define PHASE_ALIGN(bit) do { if ((CEMK_PHASE_SYNC) & (bit)) __syncthreads(); } while (0)
+#else
+#define PHASE_ALIGN(bit)
 #endif
 #define LANES(W, R) { __syncwarp(); const int lane = (W).lane; auto& R = (W).regs; (void)R;
 #define END_LANES } __syncwarp();
@@ -48,6 +59,7 @@
 #define USYNC() __syncwarp()
 #define KRSQRT(x) rsqrtf(x)
 #define KPOPC(x) __popc(x)
+#define KFFS(x) __ffs((int)(x))
 #endif
 
 template <class LR>
@@ -57,8 +69,19 @@ struct WarpCtx {
 #else
   LR regs;
   int lane;
+#ifdef CEMK_PHASE_TIMING
+  long long t0; int phase; long long ph[16];
+#endif
 #endif
 };
+
+// Debug build only (-DCEMK_PHASE_TIMING): per-phase SM-clock accounting of one warp's step, summed
+// into a global table by the kernel wrapper (tools/phase_timing.py).  No-op otherwise.
+#if !defined(CEMK_EMU) && defined(CEMK_PHASE_TIMING)
+#define PHASE(W, id) do { long long now_ = clock64(); (W).ph[(W).phase] += now_ - (W).t0; (W).t0 = now_; (W).phase = (id); } while (0)
+#else
+#define PHASE(W, id) do { } while (0)
+#endif
 
 // sum over lanes of f(lane, regs); result is warp-uniform
 template <class W, class F>
@@ -99,5 +122,68 @@ KFN float warp_bcast(W& w, int src, F f) {
   return f(src, w.regs[src]);
 #else
   return __shfl_sync(0xffffffffu, f(w.lane, w.regs), src);
+#endif
+}
+
+// lane index of the maximum of f(lane, regs) over all lanes; ties -> lowest lane ("first max");
+// lanes whose value is NaN never win against a number
+template <class W, class F>
+KFN int warp_argmax_first(W& w, F f) {
+#ifdef CEMK_EMU
+  int best = 0; float bv = f(0, w.regs[0]);
+  for (int l = 1; l < 32; ++l) { float v = f(l, w.regs[l]); if (v > bv || (bv != bv && v == v)) { bv = v; best = l; } }
+  return best;
+#else
+  float v = f(w.lane, w.regs); int idx = w.lane;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ov > v || (ov == v && oi < idx) || (v != v && ov == ov)) { v = ov; idx = oi; }
+  }
+  return idx;
+#endif
+}
+
+// per-lane-source shuffle: lane l receives get(src(l), regs[src(l)]) through set(l, regs[l], value)
+template <class W, class G, class SRC, class SET>
+KFN void warp_shfl_each(W& w, G get, SRC src, SET set) {
+#ifdef CEMK_EMU
+  float vals[32];
+  for (int l = 0; l < 32; ++l) vals[l] = get(l, w.regs[l]);
+  for (int l = 0; l < 32; ++l) set(l, w.regs[l], vals[src(l) & 31]);
+#else
+  const float v = __shfl_sync(0xffffffffu, get(w.lane, w.regs), src(w.lane));
+  set(w.lane, w.regs, v);
+#endif
+}
+
+// bit l of the result is set iff pred(l, regs[l]) holds
+template <class W, class F>
+KFN unsigned warp_ballot(W& w, F pred) {
+#ifdef CEMK_EMU
+  unsigned m = 0;
+  for (int l = 0; l < 32; ++l) if (pred(l, w.regs[l])) m |= 1u << l;
+  return m;
+#else
+  return __ballot_sync(0xffffffffu, pred(w.lane, w.regs));
+#endif
+}
+// warp_argmax_first restricted to lanes 0..7 (three exchange rounds); other lanes' values are ignored
+template <class W, class F>
+KFN int warp_argmax_first8(W& w, F f) {
+#ifdef CEMK_EMU
+  int best = 0; float bv = f(0, w.regs[0]);
+  for (int l = 1; l < 8; ++l) { float v = f(l, w.regs[l]); if (v > bv || (bv != bv && v == v)) { bv = v; best = l; } }
+  return best;
+#else
+  float v = f(w.lane, w.regs); int idx = w.lane;
+#pragma unroll
+  for (int o = 4; o; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ov > v || (ov == v && oi < idx) || (v != v && ov == ov)) { v = ov; idx = oi; }
+  }
+  return __shfl_sync(0xffffffffu, idx, 0);
 #endif
 }

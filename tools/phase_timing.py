@@ -1,0 +1,44 @@
+"""Per-phase share of k_rollout's time (SM clocks of one lane per warp, summed over warps).
+Builds a debug library with -DCEMK_PHASE_TIMING next to the normal one, runs one 4096 x 100 rollout.
+    python tools/phase_timing.py            (on a GPU box)"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from manipulator_mujoco_b200 import _lib  # noqa: E402
+
+dbg = os.path.join(ROOT, "manipulator_mujoco_b200", "libcemk_phase.so")
+cmd = ["nvcc"] + [f for f in _lib.NVCC_FLAGS] + ["-DCEMK_PHASE_TIMING", "-o", dbg, _lib.SRC[0]]
+subprocess.run(cmd, check=True)
+_lib.LIB_PATH = dbg
+import torch  # noqa: E402
+from manipulator_mujoco_b200 import cem_planner  # noqa: E402
+
+B, T = int(os.environ.get("B", 4096)), int(os.environ.get("T", 100))
+pl = cem_planner(num_dof=6, num_batch=B, num_steps=T, timestep=0.05, maxiter_cem=1, num_elite=0.05, w_pos=20.0, w_rot=3.0,
+                 w_col=80.0, maxiter_projection=10)
+q0 = np.array([1.5, -1.8, 1.75, -1.25, -1.6, 0.0])
+tp, tr = np.array([-0.3, -0.3, 0.5]), np.array([0.0, 1.0, 0.0, 0.0])
+lib = C.CDLL(dbg)
+buf = (C.c_ulonglong * 16)()
+for _ in range(2):
+    pl.compute_cem(np.zeros(66), q0, np.zeros(6), np.zeros(6), tp, tr)
+torch.cuda.synchronize()
+pl._lib.cemk_debug_phase_clocks(buf)
+pl.compute_cem(np.zeros(66), q0, np.zeros(6), np.zeros(6), tp, tr)
+torch.cuda.synchronize()
+pl._lib.cemk_debug_phase_clocks(buf)
+names = ["align-exit", "P1 FK chain", "P2-P5 dynamics", "P6 qacc_smooth", "N1 robot narrow phase + cost", "N1 free-box pairs", "N2 emit contacts",
+         "C1-C3 rows/Jacobians", "S1 warm/smooth", "S3 grad + H", "S4 Cholesky + solve", "S5 line search", "obs + euler", "step barrier wait",
+         "prologue", "epilogue"]
+v = np.array(list(buf), dtype=np.float64)
+print(f"k_rollout phase shares, B={B} T={T} (clock64 per warp, summed)")
+for n, x in sorted(zip(names, v), key=lambda t: -t[1]):
+    print(f"  {100 * x / v.sum():6.2f}%  {x / (B * T):9.0f} clk/env-step  {n}")
+print(f"  total {v.sum() / (B * T):.0f} clk per env-step per warp")
+os.remove(dbg)
