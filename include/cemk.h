@@ -92,6 +92,10 @@ int cemk_mean_cov(cemk_handle* h, int k, const float* cost_elite, const float* x
                   const float* cov_prev, float lamda, float alpha_mean, float alpha_cov, float* mean_out, float* cov_out,
                   void* stream);
 
+/* Calibration: measured FP32 FMA throughput (TFLOP/s, register operands) of the handle's device; synchronous.
+ * bench.py uses it as the measured denominator of the rollout kernel's FP32 roofline. */
+int cemk_fp32_fma_peak(cemk_handle* h, double* tflops);
+
 /* Number of kernels this library has launched since cemk_create (bench.py's gpu_launches). */
 long long cemk_launch_count(cemk_handle* h);
 

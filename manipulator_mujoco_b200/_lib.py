@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcemk.so")
 SRC = [os.path.join(_HERE, "csrc", n) for n in ("cemk.cu", "rollout_core.h", "warp_dsl.h", "kmodel.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-DCEMK_STEP_SYNC", "-DCEMK_PHASE_SYNC=2",
-              "-prec-div=false", "-prec-sqrt=false", "-shared", "-Xcompiler", "-fPIC"]
+              "-use_fast_math", "-shared", "-Xcompiler", "-fPIC"]
 
 
 def build_library(force=False, verbose=False):
@@ -47,6 +47,7 @@ _SIGS = {
     "cemk_argsort_topk": ([_vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp], _i),
     "cemk_merge_elites": ([_vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp], _i),
     "cemk_mean_cov": ([_vp, _i, _vp, _vp, _vp, _vp, _f, _f, _f, _vp, _vp, _vp], _i),
+    "cemk_fp32_fma_peak": ([_vp, C.POINTER(C.c_double)], _i),
     "cemk_launch_count": ([_vp], C.c_longlong),
 }
 EXPORTS = tuple(_SIGS)

@@ -361,6 +361,22 @@ __global__ void __launch_bounds__(128) k_mean_cov(int k, const float* __restrict
   }
 }
 
+// ---------------------------------------------------------------------------------------------- calibration
+// FP32 FMA throughput of this GPU under the kernel's own conditions (register operands, 8 independent
+// chains per thread): the measured denominator of the rollout kernel's FP32 roofline.
+__global__ void __launch_bounds__(256) k_fma_peak(float* out, int iters, float a, float b) {
+  float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+      x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
 // ================================================================================================ C ABI
 extern "C" {
 
@@ -545,6 +561,31 @@ int cemk_mean_cov(cemk_handle* h, int k, const float* cost_elite, const float* x
 }
 
 long long cemk_launch_count(cemk_handle* h) { return h ? h->launches : 0; }
+
+int cemk_fp32_fma_peak(cemk_handle* h, double* tflops) {
+  if (!h || !tflops) return set_err(CEMK_ERR_ARG, "cemk_fp32_fma_peak: null argument");
+  CK(cudaSetDevice(h->device));
+  const int nsm = h->num_sms > 0 ? h->num_sms : 148, blocks = nsm * 8, threads = 256, iters = 4096;
+  float* d = nullptr;
+  CK(cudaMalloc(&d, sizeof(float) * blocks * threads));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CK(cudaEventRecord(e0));
+    k_fma_peak<<<blocks, threads>>>(d, iters, 0.999f, 0.001f);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double fl = 2.0 * 8 * 16 * (double)iters * blocks * threads;
+    if (rep > 0 && fl / (ms * 1e-3) / 1e12 > best) best = fl / (ms * 1e-3) / 1e12;
+  }
+  h->launches += 5;
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  *tflops = best;
+  return CEMK_OK;
+}
 
 #ifdef CEMK_PHASE_TIMING
 /* debug builds only: copy out and clear the per-phase clock table */

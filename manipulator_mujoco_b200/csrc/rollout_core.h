@@ -337,7 +337,7 @@ KFN void capsule_box(const float* A, const float* B, float r, const float* bpos,
     }
   }
 }
-KNOINLINE Dist2 capsule_box_dist(const float* A, const float* B, float r, const float* bpos, const float* bmat, const float* bsize) {
+KFN Dist2 capsule_box_dist(const float* A, const float* B, float r, const float* bpos, const float* bmat, const float* bsize) {
   Contact2 c;
   capsule_box<false>(A, B, r, bpos, bmat, bsize, c);
   Dist2 d; d.d0 = c.dist[0]; d.d1 = c.dist[1];

@@ -260,11 +260,19 @@ def build_kmodel(mc: ModelConsts, timestep: float, robot_geom_names=None, tcp_si
         raise NotImplementedError("too many pairs")
     m.nrpair, m.nbpair, m.nslot_robot = len(rpairs), len(bpairs), slot
     # lanes of one pass should run the same collider: order by type (cap-box first)
-    order = sorted(range(len(rpairs)), key=lambda i: ({KP_CAP_BOX: 0, KP_CAP_CAP: 1, KP_PLANE_CAP: 2}[rpairs[i][0]], i))
+    # lanes of one 32-wide pass should run the same collider (a divergent pass pays for every collider
+    # present in it): capsule-box first, plane-capsule right behind, capsule-capsule on its own pass(es)
+    by = lambda ty: [i for i in range(len(rpairs)) if rpairs[i][0] == ty]
+    order = by(KP_CAP_BOX) + by(KP_PLANE_CAP)
+    pad = (-len(order)) % 32
+    if len(order) + pad + len(by(KP_CAP_CAP)) > MAXRPAIR:
+        pad = 0
+    order = order + [None] * pad + by(KP_CAP_CAP)
     for e in range(MAXRPAIR):
         m.rp_type[e] = KP_NONE
     for e, i in enumerate(order):
-        m.rp_type[e], m.rp_a[e], m.rp_b[e], m.rp_slot[e] = rpairs[i]
+        if i is not None:
+            m.rp_type[e], m.rp_a[e], m.rp_b[e], m.rp_slot[e] = rpairs[i]
     for e, (ty, a) in enumerate(bpairs):
         m.bp_type[e], m.bp_a[e] = ty, a
     _set(m.qpos0, mc.qpos0)
