@@ -71,6 +71,7 @@ struct WarpSmemT {
       float bbR[12], bbc[4], bbsz[2][4], bbrf[4][4], bben[4][4], bbpoly[2][8][4], bbpref[8][4];
     };
   };
+  float cd[2][NC][4];                 // per contact: Jn.v, mu*Jt1.v, mu*Jt2.v for up to two vectors v
   int limdof[KM_NL];
   float limsign[KM_NL];
 };
@@ -707,17 +708,6 @@ KFN void jac_col(const KModel& m, const WarpSmemT<NC>& S, const float* p, int li
     cross3(col, r, off);
   }
 }
-// J_r . v for constraint row r
-template <int NC>
-KFN float row_dot(const WarpSmemT<NC>& S, int r, const float* v) {
-  if (r < S.nlim) return S.limsign[r] * v[S.limdof[r]];
-  int c = (r - S.nlim) >> 2, q = (r - S.nlim) & 3;
-  const float* Jn = S.cJ[c]; const float* Jt = S.cJ[c] + (q < 2 ? 12 : 24);
-  float sn = 0.f, st = 0.f;
-#pragma unroll
-  for (int d = 0; d < KM_NV; ++d) { sn += Jn[d] * v[d]; st += Jt[d] * v[d]; }
-  return (q & 1) ? sn - st : sn + st;
-}
 template <int NC>
 KFN float row_J(const WarpSmemT<NC>& S, int r, int d) {
   if (r < S.nlim) return S.limdof[r] == d ? S.limsign[r] : 0.f;
@@ -729,6 +719,31 @@ KFN float row_J(const WarpSmemT<NC>& S, int r, int d) {
 // Dense 6x6 SPD solve in registers, executed redundantly by every lane (uniform): for matrices this
 // small a straight-line Cholesky beats a lane-distributed one, whose ~50 dependent shuffles cost more
 // than the arithmetic (measured: profiles/README.md).  A: lower triangle read with row stride `ld`.
+// The 4 pyramid rows of a contact are Jn +- mu*Jt1, Jn +- mu*Jt2: three dot products per contact (one
+// (contact, component) item per lane) give all four J_r . v.
+template <int NC>
+KFN void contact_dots(Warp& W, WarpSmemT<NC>& S, int ncon, const float* v0, const float* v1) {
+  LANES(W, R)
+#pragma unroll 1
+    for (int e = lane; e < 3 * ncon; e += 32) {
+      const int c = e / 3, k = e - 3 * c;
+      const float* J = S.cJ[c] + 12 * k;
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int d = 0; d < KM_NV; ++d) { s0 += J[d] * v0[d]; if (v1) s1 += J[d] * v1[d]; }
+      S.cd[0][c][k] = s0;
+      if (v1) S.cd[1][c][k] = s1;
+    }
+  END_LANES
+}
+template <int NC>
+KFN float row_val(const WarpSmemT<NC>& S, int set, int r, const float* v) {
+  if (r < S.nlim) return S.limsign[r] * v[S.limdof[r]];
+  const int c = (r - S.nlim) >> 2, q = (r - S.nlim) & 3;
+  const float dn = S.cd[set][c][0], dt = S.cd[set][c][q < 2 ? 1 : 2];
+  return (q & 1) ? dn - dt : dn + dt;
+}
+
 struct Vec6 { float v[6]; };
 KNOINLINE Vec6 chol_solve6(const float* A, int ld, const float* rhs) {
   float L[6][6], y[6];
@@ -1157,6 +1172,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
     }
   END_LANES
   // ---- C3: contact row parameters (the 4 pyramid edges share pos and D) ----
+  contact_dots<NC>(W, S, ncon, S.qvel, nullptr);
   LANES(W, R)
 #pragma unroll 1
     for (int r = nlim + lane; r < nrow; r += 32) {
@@ -1164,7 +1180,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
       float w = g[13];
       w = w + m.mu * m.mu * w;
       w = w * 2.f * m.mu * m.mu / m.impratio;
-      float vel = row_dot(S, r, S.qvel), D, aref;
+      float vel = row_val<NC>(S, 0, r, S.qvel), D, aref;
       row_params(m, g[12], w, vel, D, aref);
       S.rD[r] = D; S.rAref[r] = aref;
     }
@@ -1178,11 +1194,12 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
   const bool coupled = warp_sum(W, [](int, LaneRegs& R) { return R.f2; }) > 0.f;
   PHASE(W, 8);
   // ---- S1: warm start vs smooth start (B.6) ----
+  contact_dots<NC>(W, S, ncon, S.warm, S.as);
   LANES(W, R)
     float cw = 0.f, cs = 0.f;
 #pragma unroll 1
     for (int r = lane; r < nrow; r += 32) {
-      float jw = row_dot(S, r, S.warm) - S.rAref[r], js = row_dot(S, r, S.as) - S.rAref[r];
+      float jw = row_val<NC>(S, 0, r, S.warm) - S.rAref[r], js = row_val<NC>(S, 1, r, S.as) - S.rAref[r];
       S.rJaref[r] = jw; S.rJs[r] = js;
       if (jw < 0.f) cw += 0.5f * S.rD[r] * jw * jw;
       if (js < 0.f) cs += 0.5f * S.rD[r] * js * js;
@@ -1294,8 +1311,11 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
       float s = S.search[lane];
       R.f0 = s * s; R.f1 = s * S.Ma[lane] - s * S.fs[lane]; R.f2 = 0.5f * s * mv;
     }
+  END_LANES
+  contact_dots<NC>(W, S, ncon, S.search, nullptr);
+  LANES(W, R)
 #pragma unroll 1
-    for (int r = lane; r < nrow; r += 32) S.rJv[r] = row_dot(S, r, S.search);
+    for (int r = lane; r < nrow; r += 32) S.rJv[r] = row_val<NC>(S, 0, r, S.search);
   END_LANES
   float qg[3];
   const float snorm = sqrtf(warp_sum(W, [](int, LaneRegs& R) { return R.f0; }));

@@ -82,3 +82,41 @@ def test_contact_capacity_variants_agree(emu):
     assert a["flags"].max() == 0
     np.testing.assert_array_equal(a["theta"], b["theta"])
     np.testing.assert_array_equal(a["cost4"], b["cost4"])
+
+
+def test_robot_box_coupled_contact(emu, oracle64, oracle32, mc):
+    """States where a robot capsule touches the free box (target_0): the Hessian couples the robot
+    and box blocks (full 12x12 Cholesky path of the kernel)."""
+    rng = np.random.default_rng(5)
+    names = mc.geom_names
+    slots = []
+    for (g1, g2), a, n in zip(mc.pair_geom, mc.pair_slotadr, mc.pair_nslot):
+        if names[g2] == "target_0" and (names[g1] or "").startswith("robot_"):
+            slots += list(range(a, a + n))
+    found = checked = 0
+    for _ in range(200):
+        qr = Q0 + rng.normal(size=6) * 0.3
+        tcp = oracle64.forward(np.concatenate([qr, mc.qpos0[6:]]), np.zeros(12))["site_tcp"]
+        qbox = np.concatenate([tcp + rng.normal(size=3) * 0.01, [1.0, 0, 0, 0]])     # box floating at the tool tip
+        q = np.concatenate([qr, qbox])
+        v = np.zeros(12)
+        v[:6] = rng.normal(size=6) * 0.2
+        r64 = oracle64.forward(q, v)
+        if not (r64["con_dist"][slots] < 0).any():
+            continue
+        found += 1
+        r32 = oracle32.forward(q, v)
+        km = copy.copy(emu.km)
+        for i in range(13):
+            km.qpos0[i] = q[i]
+        for i in range(12):
+            km.warm0[i], km.qvel0[i] = 0.0, v[i]
+        out = emu.rollout(v[:6].reshape(1, 6), q[:6], v[:6], TARGET_POS, TARGET_ROT, km=km)
+        np.testing.assert_allclose(out["collision"][0, 0], r64["con_dist"][oracle64.mask], atol=1e-5)
+        scale = max(1.0, np.abs(r64["qacc"]).max())
+        if np.abs(r32["qacc"] - r64["qacc"]).max() < 1e-3 * scale:
+            checked += 1
+            assert np.abs(out["qacc"][0, 0] - r64["qacc"]).max() < 2e-2 * scale
+        if found >= 12:
+            break
+    assert found >= 5 and checked >= 2
