@@ -85,6 +85,16 @@ def cpu_rollout_baseline(nthreads, B, seed=0):
     return B * T / dt, dt
 
 
+def ncu_traffic(batch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_rollout launch from the committed
+    `ncu --set full` capture (profiles/), valid for the default 4096-sample workload only."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_final_k_rollout_metrics.json")) as f:
+            return float(json.load(f)["dram_traffic_bytes_per_launch"]) if batch == B_PER_GPU else None
+    except Exception:
+        return None
+
+
 def run_reference(args):
     """Reference arm: the CPU restatement of the path (oracle) on all host cores, same config."""
     rank = int(os.environ.get("RANK", "0"))
@@ -261,7 +271,7 @@ def main():
                 "h2d_bytes_per_step": int(pl.h2d_bytes), "d2h_bytes_per_step": int(pl.d2h_bytes)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "fp32", "kernel": "k_rollout", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-                     "frac": achieved / fp32_peak, "traffic": None,
+                     "frac": achieved / fp32_peak, "traffic": ncu_traffic(Bl),
                      "peak_source": "FP32 FMA throughput measured live by cemk_fp32_fma_peak (8 independent register chains/thread); "
                                     f"nominal {prop.multi_processor_count} SMs x 128 lanes x 2 x {sm_max} MHz = {fp32_nominal:.1f} TFLOP/s (MEASURED_PEAKS.json holds no FP32 figure)",
                      "peak_nominal": fp32_nominal,
