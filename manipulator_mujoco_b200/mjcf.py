@@ -455,6 +455,14 @@ def compile_mjcf(xml_path) -> ModelConsts:
             if key not in PAIR_SLOTS:
                 raise NotImplementedError(f"collision pair types {key}")
             pairs.append((key, g1, g2))
+    # <contact><exclude body1=.. body2=../> (the planner scene ships them commented out, scene.xml:27-45)
+    names = [b["name"] for b in bodies]
+    excl = set()
+    for c in root.findall("contact"):
+        for e in c.findall("exclude"):
+            b1, b2 = names.index(e.get("body1")), names.index(e.get("body2"))
+            excl.add((min(b1, b2), max(b1, b2)))
+    pairs = [p for p in pairs if (min(geoms[p[1]]["body"], geoms[p[2]]["body"]), max(geoms[p[1]]["body"], geoms[p[2]]["body"])) not in excl]
     pairs.sort(key=lambda p: (p[0], p[1], p[2]))
     pair_geom = np.array([[p[1], p[2]] for p in pairs], dtype=np.int32).reshape(-1, 2)
     pair_type = np.array([[p[0][0], p[0][1]] for p in pairs], dtype=np.int32).reshape(-1, 2)
@@ -615,6 +623,22 @@ def _set_const(mc: ModelConsts):
     mc.d["dof_invweight0"] = dof_invweight0
     mc.d["body_invweight0"] = body_invweight0
     mc.d["meaninertia"] = float(np.mean(np.diag(M))) if nv else 1.0
+
+
+def exclude_body_pairs(mc: ModelConsts, body_pairs) -> ModelConsts:
+    """Copy of a compiled model with the candidate pairs between the given body-name pairs removed,
+    i.e. what `<contact><exclude body1=... body2=.../>` does at compile time."""
+    ex = set()
+    for a, b in body_pairs:
+        i, j = mc.body_id(a), mc.body_id(b)
+        ex.add((min(i, j), max(i, j)))
+    keep = [k for k, (g1, g2) in enumerate(mc.pair_geom)
+            if (min(mc.geom_body[g1], mc.geom_body[g2]), max(mc.geom_body[g1], mc.geom_body[g2])) not in ex]
+    d = dict(mc.d)
+    d["pair_geom"], d["pair_type"], d["pair_nslot"] = mc.pair_geom[keep], mc.pair_type[keep], mc.pair_nslot[keep]
+    d["pair_slotadr"] = np.concatenate([[0], np.cumsum(d["pair_nslot"])[:-1]]).astype(np.int32)
+    d["ncon"] = int(d["pair_nslot"].sum())
+    return ModelConsts(d)
 
 
 DEFAULT_ASSET = os.path.join(os.path.dirname(__file__), "assets", "scene_a.json")

@@ -31,7 +31,7 @@ import torch
 from . import _lib, parallel
 from .bernstein import bernstein_coeff_ordern_new
 from .kmodel import KModel, build_kmodel
-from .mjcf import ModelConsts, host_kinematics, load_model
+from .mjcf import ModelConsts, exclude_body_pairs, host_kinematics, load_model
 
 _VP = C.c_void_p
 
@@ -87,7 +87,7 @@ class cem_planner:
 
     def __init__(self, num_dof=None, num_batch=None, num_steps=None, timestep=None, maxiter_cem=None, num_elite=None,
                  w_pos=None, w_rot=None, w_col=None, maxiter_projection=None, *, model_path=None, device=None,
-                 process_group=None, seed=0):
+                 process_group=None, seed=0, contact_exclude=None):
         if not torch.cuda.is_available():
             raise RuntimeError("cem_planner needs a CUDA device (B200 / sm_100a); there is no CPU fallback")
         self._lib = _lib.load()
@@ -158,6 +158,8 @@ class cem_planner:
         # ---- model (mjx_planner.py:100-121) ----
         self.model_path = model_path if model_path is not None else "<packaged ur5e_hande_mjx/scene.xml constants>"
         self._mc = load_model(model_path)
+        if contact_exclude:                 # [(body1, body2), ...] == MJCF <contact><exclude/> entries
+            self._mc = exclude_body_pairs(self._mc, contact_exclude)
         self.model = _ModelView(self._mc, self.t)
         self.data = _DataView(self._mc)
         km, info = build_kmodel(self._mc, self.t)

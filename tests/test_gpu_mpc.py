@@ -1,0 +1,33 @@
+"""Closed-loop MPC driver (reference mpc_planner.py call sites) on the GPU: BASELINE config 3 shape."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_closed_loop_reaches_first_target(tmp_path):
+    from manipulator_mujoco_b200.mpc_planner import run_cem_planner
+    res = run_cem_planner(num_dof=6, num_batch=1000, num_steps=16, num_elite=0.05, timestep=0.05, maxiter_cem=3,
+                          maxiter_projection=10, w_pos=20.0, w_rot=3.0, w_col=80.0, show_viewer=False, show_contact_points=False,
+                          initial_qpos=[1.5, -1.8, 1.75, -1.25, -1.6, 0], target_names=["target_0", "target_1", "target_2", "home"],
+                          cam_distance=4, position_threshold=0.05, rotation_threshold=0.1, save_data=True, data_dir=str(tmp_path),
+                          stop_at_final_target=True, max_ticks=120, verbose=False)
+    theta = np.array(res["theta"])
+    assert theta.shape[1] == 6 and np.isfinite(theta).all()
+    g = np.array(res["cost_g"])
+    assert np.isfinite(g).all()
+    # the planner drives the tool towards target_0: the per-tick goal cost of the best sample falls
+    assert g[:100].min() < 0.75 * g[0]
+    # joint velocities applied to the plant respect the projection filter's velocity bound (v_max = 0.8)
+    assert np.abs(np.array(res["thetadot"])).max() < 0.8 + 0.15
+    # real-time budget of the reference loop: one tick <= timestep = 50 ms (mpc_planner.py:231-233)
+    assert np.median(res["tick_ms"]) < 50.0
+    for name in ("costs", "thetadot", "theta", "cost_g", "cost_r", "cost_c"):
+        assert (tmp_path / f"{name}.csv").exists()
+
+
+def test_viewer_is_refused():
+    from manipulator_mujoco_b200.mpc_planner import run_cem_planner
+    with pytest.raises(NotImplementedError):
+        run_cem_planner(num_dof=6, num_batch=8, num_steps=8, num_elite=0.5, timestep=0.05, maxiter_cem=1, maxiter_projection=1,
+                        w_pos=1.0, w_rot=1.0, w_col=1.0, show_viewer=True, initial_qpos=[0] * 6, target_names=["target_0"])
