@@ -92,6 +92,10 @@ int cemk_mean_cov(cemk_handle* h, int k, const float* cost_elite, const float* x
                   const float* cov_prev, float lamda, float alpha_mean, float alpha_cov, float* mean_out, float* cov_out,
                   void* stream);
 
+/* Options.  "force_rerun" (0/1): recompute every sample with the big-capacity (48 contacts) rollout kernel,
+ * used by the tests to check that it agrees bit for bit with the fast kernel. */
+int cemk_set_option(cemk_handle* h, const char* name, int value);
+
 /* Calibration: measured FP32 FMA throughput (TFLOP/s, register operands) of the handle's device; synchronous.
  * bench.py uses it as the measured denominator of the rollout kernel's FP32 roofline. */
 int cemk_fp32_fma_peak(cemk_handle* h, double* tflops);

@@ -43,7 +43,8 @@ struct cemk_handle {
   float* d_G;      // [3][T][11]
   float* d_K;      // Kpp[121] Kpe[55] bounds[3]
   long long launches;
-  int* d_flags; int flags_cap; int num_sms;   // per-sample overflow flags when the caller passes none
+  int* d_flags; int flags_cap; int num_sms;
+  int force_rerun;               // debug option: recompute every sample with the big-capacity kernel   // per-sample overflow flags when the caller passes none
 };
 
 // ---------------------------------------------------------------------------------------------- rollout
@@ -392,7 +393,7 @@ int cemk_create(const void* kmodel, int kmodel_bytes, int device, cemk_handle** 
     return set_err(CEMK_ERR_MODEL, "cemk_create: unsupported topology");
   CK(cudaSetDevice(device));
   cemk_handle* h = new cemk_handle();
-  h->device = device; h->T = 0; h->d_G = nullptr; h->d_K = nullptr; h->launches = 0; h->d_flags = nullptr; h->flags_cap = 0;
+  h->device = device; h->T = 0; h->d_G = nullptr; h->d_K = nullptr; h->launches = 0; h->d_flags = nullptr; h->flags_cap = 0; h->force_rerun = 0;
   { cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device)); h->num_sms = prop.multiProcessorCount; }
   CK(cudaMalloc(&h->d_model, sizeof(KModel)));
   CK(cudaMemcpy(h->d_model, kmodel, sizeof(KModel), cudaMemcpyHostToDevice));
@@ -401,6 +402,8 @@ int cemk_create(const void* kmodel, int kmodel_bytes, int device, cemk_handle** 
                           (int)rollout_smem<KM_NC_FAST, ROLLOUT_WARPS>()));
   CK(cudaFuncSetAttribute(k_rollout<KM_NC_FAST, ROLLOUT_WARPS_ALT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)rollout_smem<KM_NC_FAST, ROLLOUT_WARPS_ALT>()));
+  CK(cudaFuncSetAttribute(k_rollout<KM_NC_FAST, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rollout_smem<KM_NC_FAST, 8>()));
+  CK(cudaFuncSetAttribute(k_rollout<KM_NC_FAST, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rollout_smem<KM_NC_FAST, 4>()));
   CK(cudaFuncSetAttribute(k_rollout<KM_NC_BIG, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)rollout_smem<KM_NC_BIG, 1>()));
   *out = h;
@@ -475,16 +478,19 @@ int cemk_rollout_cost(cemk_handle* h, int B, int T, const float* thetadot, const
   a.B = B; a.T = T; a.thetadot = thetadot; a.q0 = q0; a.v0 = v0; a.target_pos = target_pos; a.target_rot = target_rot;
   a.w_pos = w_pos; a.w_rot = w_rot; a.w_col = w_col;
   a.theta = theta; a.cost4 = cost4; a.eef_pos = eef_pos; a.eef_rot = eef_rot; a.collision = collision; a.qacc = qacc; a.flags = flags;
-  // CTA size: 16 or 14 samples, whichever wastes fewer SM slots in the last wave (one CTA per SM is resident)
+  // CTA size (samples per CTA; one CTA per SM is resident): batches that do not fill the GPU use small
+  // CTAs so every SM gets work (latency-bound regime, e.g. the closed-loop config B = 1000); otherwise
+  // 16 or 14, whichever wastes fewer SM slots in the last wave.
   const int nsm = h->num_sms > 0 ? h->num_sms : 148;
   auto waste = [&](int w) { const int ctas = (B + w - 1) / w; const int waves = (ctas + nsm - 1) / nsm; return (double)waves * nsm * w / (double)B; };
-  if (waste(ROLLOUT_WARPS_ALT) + 0.02 < waste(ROLLOUT_WARPS))
-    k_rollout<KM_NC_FAST, ROLLOUT_WARPS_ALT, false><<<(B + ROLLOUT_WARPS_ALT - 1) / ROLLOUT_WARPS_ALT, ROLLOUT_WARPS_ALT * 32,
-                                                      rollout_smem<KM_NC_FAST, ROLLOUT_WARPS_ALT>(), st>>>(h->d_model, a);
-  else
-    k_rollout<KM_NC_FAST, ROLLOUT_WARPS, false><<<(B + ROLLOUT_WARPS - 1) / ROLLOUT_WARPS, ROLLOUT_WARPS * 32,
-                                                  rollout_smem<KM_NC_FAST, ROLLOUT_WARPS>(), st>>>(h->d_model, a);
+#define CEMK_LAUNCH_ROLLOUT(W_) k_rollout<KM_NC_FAST, W_, false><<<(B + (W_) - 1) / (W_), (W_) * 32, rollout_smem<KM_NC_FAST, W_>(), st>>>(h->d_model, a)
+  if (B <= nsm * 4) CEMK_LAUNCH_ROLLOUT(4);
+  else if (B <= nsm * 8) CEMK_LAUNCH_ROLLOUT(8);
+  else if (waste(ROLLOUT_WARPS_ALT) + 0.02 < waste(ROLLOUT_WARPS)) CEMK_LAUNCH_ROLLOUT(ROLLOUT_WARPS_ALT);
+  else CEMK_LAUNCH_ROLLOUT(ROLLOUT_WARPS);
+#undef CEMK_LAUNCH_ROLLOUT
   // samples whose active-contact list overflowed the fast capacity are recomputed with the big one
+  if (h->force_rerun) CK(cudaMemsetAsync(flags, 1, sizeof(int) * B, st));      // 0x01010101: bit 0 set
   k_rollout<KM_NC_BIG, 1, true><<<B, 32, rollout_smem<KM_NC_BIG, 1>(), st>>>(h->d_model, a);
   h->launches += 2;
   CK(cudaPeekAtLastError());
@@ -561,6 +567,12 @@ int cemk_mean_cov(cemk_handle* h, int k, const float* cost_elite, const float* x
 }
 
 long long cemk_launch_count(cemk_handle* h) { return h ? h->launches : 0; }
+
+int cemk_set_option(cemk_handle* h, const char* name, int value) {
+  if (!h || !name) return set_err(CEMK_ERR_ARG, "cemk_set_option: null argument");
+  if (!strcmp(name, "force_rerun")) { h->force_rerun = value != 0; return CEMK_OK; }
+  return set_err(CEMK_ERR_ARG, "cemk_set_option: unknown option");
+}
 
 int cemk_fp32_fma_peak(cemk_handle* h, double* tflops) {
   if (!h || !tflops) return set_err(CEMK_ERR_ARG, "cemk_fp32_fma_peak: null argument");

@@ -183,6 +183,8 @@ class cem_planner:
 
         self._z_cache = {}
         self._ws = {}
+        self._graph, self._graph_out, self._eager_ticks = None, None, 0
+        self.use_cuda_graph = os.environ.get("CEMK_CUDA_GRAPH", "1") != "0"
         self.print_info()
 
     # ------------------------------------------------------------------ constants (mjx_planner.py:142-172)
@@ -455,23 +457,13 @@ class cem_planner:
         carry = (init_pos, init_vel, target_pos, target_rot, xi_mean, xi_cov, key, state_term)
         return carry, (cost4[:, 0], cost4[:, 1], cost4[:, 2], cost4[:, 3], thetadot, theta)
 
-    def compute_cem(self, xi_mean, init_pos=np.array([1.5, -1.8, 1.75, -1.25, -1.6, 0]), init_vel=np.zeros(6),
-                    init_acc=np.zeros(6), target_pos=np.zeros(3), target_rot=np.zeros(4)):
+    def _cem_device(self, pin, pout):
+        """Everything a planning tick does on the device: H2D of the packed inputs, maxiter_cem
+        iterations, best-sample extraction, D2H of the packed results (stream-ordered, no sync)."""
         dev = self.device
-        Bl, T, nd = self.num_batch_local, self.num, self.num_dof
-        # one packed host->device copy for the per-tick inputs
-        host = np.concatenate([np.asarray(xi_mean.detach().cpu() if torch.is_tensor(xi_mean) else xi_mean, dtype=np.float32).reshape(-1),
-                               np.asarray(init_pos, dtype=np.float32).reshape(-1), np.asarray(init_vel, dtype=np.float32).reshape(-1),
-                               np.asarray(init_acc, dtype=np.float32).reshape(-1), np.asarray(target_pos, dtype=np.float32).reshape(-1),
-                               np.asarray(target_rot, dtype=np.float32).reshape(-1)])
-        pin = self._ws.get("pin_in")
-        if pin is None:
-            pin = torch.empty(host.size, dtype=torch.float32).pin_memory()
-            self._ws["pin_in"] = pin
-        pin.copy_(torch.from_numpy(host))
-        d_in = self._buf("d_in", (host.size,))
+        Bl, T, nd, nv = self.num_batch_local, self.num, self.num_dof, self.nvar
+        d_in = self._buf("d_in", (pin.numel(),))
         d_in.copy_(pin, non_blocking=True)
-        nv = self.nvar
         xi_mean_d = d_in[:nv]
         q0, v0, a0 = d_in[nv:nv + 6], d_in[nv + 6:nv + 12], d_in[nv + 12:nv + 18]
         tp, tr = d_in[nv + 18:nv + 21], d_in[nv + 21:nv + 25]
@@ -489,7 +481,7 @@ class cem_planner:
             carry, out = self.cem_iter(carry, None)
             thetadot_all[i].copy_(out[4])
             theta_all[i].copy_(out[5])
-            cost_min[i] = self._last_elite[0][0]                                           # min over the (global) batch
+            cost_min[i:i + 1].copy_(self._last_elite[0][0:1])                              # min over the (global) batch
             last = out
         # :395-402  best sample of the last iteration = head of the (merged) sorted list
         gbest = self._last_elite[1][0:1].to(torch.int64)
@@ -503,14 +495,48 @@ class cem_planner:
             best = torch.cat([last[4][li].reshape(-1), last[5][li].reshape(-1), last[1][li], last[2][li], last[3][li]]) * own
             self._dist.all_reduce(best, group=self.process_group)
         out_d = torch.cat([cost_min, best, carry[4]])
-        pout = self._ws.get("pin_out")
-        if pout is None or pout.numel() != out_d.numel():
-            pout = torch.empty(out_d.numel(), dtype=torch.float32).pin_memory()
-            self._ws["pin_out"] = pout
         pout.copy_(out_d, non_blocking=True)
+        return thetadot_all, theta_all
+
+    def compute_cem(self, xi_mean, init_pos=np.array([1.5, -1.8, 1.75, -1.25, -1.6, 0]), init_vel=np.zeros(6),
+                    init_acc=np.zeros(6), target_pos=np.zeros(3), target_rot=np.zeros(4)):
+        dev = self.device
+        Bl, T, nd, nv = self.num_batch_local, self.num, self.num_dof, self.nvar
+        # one packed host->device copy for the per-tick inputs
+        host = np.concatenate([np.asarray(xi_mean.detach().cpu() if torch.is_tensor(xi_mean) else xi_mean, dtype=np.float32).reshape(-1),
+                               np.asarray(init_pos, dtype=np.float32).reshape(-1), np.asarray(init_vel, dtype=np.float32).reshape(-1),
+                               np.asarray(init_acc, dtype=np.float32).reshape(-1), np.asarray(target_pos, dtype=np.float32).reshape(-1),
+                               np.asarray(target_rot, dtype=np.float32).reshape(-1)])
+        pin = self._ws.get("pin_in")
+        if pin is None:
+            pin = torch.empty(host.size, dtype=torch.float32).pin_memory()
+            self._ws["pin_in"] = pin
+        pin.copy_(torch.from_numpy(host))
+        m = self.maxiter_cem
+        nout = m + 2 * nd * T + 3 + self.nvar
+        pout = self._ws.get("pin_out")
+        if pout is None or pout.numel() != nout:
+            pout = torch.empty(nout, dtype=torch.float32).pin_memory()
+            self._ws["pin_out"] = pout
+        # The device side of a tick is a fixed sequence of launches on fixed buffers: after two eager
+        # ticks (allocations, caches) it is captured once into a CUDA graph and replayed, which removes
+        # the per-launch CPU cost that dominates small batches (closed-loop config: 3 x 9 launches).
+        if self._graph is not None:
+            self._graph.replay()
+            thetadot_all, theta_all = self._graph_out
+        elif self.use_cuda_graph and self.world == 1 and self._eager_ticks >= 2:
+            torch.cuda.current_stream(dev).synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self._cem_device(pin, pout)
+            self._graph, self._graph_out = g, out
+            g.replay()
+            thetadot_all, theta_all = out
+        else:
+            thetadot_all, theta_all = self._cem_device(pin, pout)
+            self._eager_ticks += 1
         torch.cuda.current_stream(dev).synchronize()
         res = pout.numpy().copy()
-        m = self.maxiter_cem
         cost = res[:m]
         best_vels = res[m:m + nd * T].reshape(nd, T).T.copy()
         best_traj = res[m + nd * T:m + 2 * nd * T].reshape(nd, T).T.copy()
@@ -518,5 +544,7 @@ class cem_planner:
         best_cost_g, best_cost_r, best_cost_c = res[o], res[o + 1], res[o + 2]
         xi_mean_out = res[o + 3:o + 3 + nv].copy()
         self.h2d_bytes = host.size * 4
-        self.d2h_bytes = out_d.numel() * 4
+        self.d2h_bytes = nout * 4
+        if self._graph is not None:          # graph outputs are static buffers: hand out copies
+            thetadot_all, theta_all = thetadot_all.clone(), theta_all.clone()
         return cost, best_cost_g, best_cost_r, best_cost_c, best_vels, best_traj, xi_mean_out, thetadot_all, theta_all

@@ -61,3 +61,37 @@ def test_fused_cost_equals_standalone_cost(planner16):
     c = planner16.compute_cost_batch(td, ep, er, col, np.tile(TARGET_POS, (100, 1)), np.tile(TARGET_ROT, (100, 1)))
     for k in range(4):
         np.testing.assert_allclose(cost4[:, k].cpu().numpy(), c[k].cpu().numpy(), rtol=1e-5, atol=1e-5)
+
+
+def test_results_do_not_depend_on_batch_size_or_cta_variant():
+    """Samples are independent: the same sample must give bit-identical results whether it runs in a
+    batch of 100 (4-warp CTAs), 1000 (8-warp CTAs) or 2300 (14/16-warp CTAs, padded last CTA)."""
+    from manipulator_mujoco_b200 import cem_planner
+    T = 24
+    pr, z, xi, st, xif, td = planner_inputs(T, 2300, seed=9)
+    outs = {}
+    for B in (100, 1000, 2300):
+        pl = cem_planner(num_dof=6, num_batch=B, num_steps=T, timestep=0.05, maxiter_cem=1, num_elite=0.05,
+                         w_pos=20.0, w_rot=3.0, w_col=80.0, maxiter_projection=10)
+        theta, cost4, ep, er, col = pl._rollout(td[:B], Q0, np.zeros(6), TARGET_POS, TARGET_ROT, True)
+        outs[B] = (theta.cpu().numpy(), cost4.cpu().numpy(), col.cpu().numpy())
+    for B in (1000, 2300):
+        for a, b in zip(outs[100], outs[B]):
+            np.testing.assert_array_equal(a, b[:100])
+    np.testing.assert_array_equal(outs[1000][1], outs[2300][1][:1000])
+
+
+def test_big_capacity_kernel_agrees_with_fast_kernel():
+    """`force_rerun` recomputes every sample with the 48-contact instantiation (the overflow path)."""
+    from manipulator_mujoco_b200 import _lib, cem_planner
+    T, B = 60, 256
+    pl = cem_planner(num_dof=6, num_batch=B, num_steps=T, timestep=0.05, maxiter_cem=1, num_elite=0.05,
+                     w_pos=20.0, w_rot=3.0, w_col=80.0, maxiter_projection=10)
+    pr, z, xi, st, xif, td = planner_inputs(T, B, seed=11)
+    a = pl._rollout(td, Q0, np.zeros(6), TARGET_POS, TARGET_ROT, True)
+    assert int(pl._buf("flags", (B,), __import__("torch").int32).max()) == 0      # nothing overflowed 24 contacts
+    _lib.check(pl._lib.cemk_set_option(pl._h, b"force_rerun", 1), pl._lib)
+    b = pl._rollout(td, Q0, np.zeros(6), TARGET_POS, TARGET_ROT, True)
+    _lib.check(pl._lib.cemk_set_option(pl._h, b"force_rerun", 0), pl._lib)
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(x.cpu().numpy(), y.cpu().numpy())
