@@ -49,7 +49,7 @@ struct cemk_handle {
 
 // ---------------------------------------------------------------------------------------------- rollout
 #ifdef CEMK_PHASE_TIMING
-__device__ unsigned long long g_phase[16];
+__device__ unsigned long long g_phase[24];
 #endif
 struct RolloutBatch {
   int B, T;
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(WARPS * 32, ROLLOUT_MINB) k_rollout(const KMod
   W.lane = threadIdx.x & 31;
 #ifdef CEMK_PHASE_TIMING
   W.phase = 14; W.t0 = clock64();
-  for (int i = 0; i < 16; ++i) W.ph[i] = 0;
+  for (int i = 0; i < 24; ++i) W.ph[i] = 0;
 #endif
   RolloutArgs A;
   const size_t row = (size_t)s * KM_NL * a.T;
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(WARPS * 32, ROLLOUT_MINB) k_rollout(const KMod
   rollout_sample<NC>(W, *sm, ws[warp], A);
 #ifdef CEMK_PHASE_TIMING
   PHASE(W, 15);
-  if (W.lane == 0 && !ONLY_FLAGGED) for (int i = 0; i < 16; ++i) atomicAdd(&g_phase[i], (unsigned long long)W.ph[i]);
+  if (W.lane == 0 && !ONLY_FLAGGED) for (int i = 0; i < 24; ++i) atomicAdd(&g_phase[i], (unsigned long long)W.ph[i]);
 #endif
 }
 template <int NC, int WARPS>
@@ -601,9 +601,9 @@ int cemk_fp32_fma_peak(cemk_handle* h, double* tflops) {
 
 #ifdef CEMK_PHASE_TIMING
 /* debug builds only: copy out and clear the per-phase clock table */
-int cemk_debug_phase_clocks(unsigned long long* out16) {
-  unsigned long long z[16] = {0};
-  if (cudaMemcpyFromSymbol(out16, g_phase, sizeof z) != cudaSuccess) return CEMK_ERR_CUDA;
+int cemk_debug_phase_clocks(unsigned long long* out24) {
+  unsigned long long z[24] = {0};
+  if (cudaMemcpyFromSymbol(out24, g_phase, sizeof z) != cudaSuccess) return CEMK_ERR_CUDA;
   if (cudaMemcpyToSymbol(g_phase, z, sizeof z) != cudaSuccess) return CEMK_ERR_CUDA;
   return CEMK_OK;
 }

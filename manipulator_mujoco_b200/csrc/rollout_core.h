@@ -1124,6 +1124,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
       }
     }
   END_LANES
+  PHASE(W, 18);
   PHASE_ALIGN(2);
   PHASE(W, 7);
   // ---- C1: joint-limit rows ----
@@ -1154,6 +1155,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
       S.rD[r] = D; S.rAref[r] = aref;
     }
   END_LANES
+  PHASE(W, 16);
   // ---- C2: contact Jacobians in the contact frame: Jn, mu*Jt1, mu*Jt2 ----
   LANES(W, R)
     const int d = lane & 15;
@@ -1171,6 +1173,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
       }
     }
   END_LANES
+  PHASE(W, 17);
   // ---- C3: contact row parameters (the 4 pyramid edges share pos and D) ----
   contact_dots<NC>(W, S, ncon, S.qvel, nullptr);
   LANES(W, R)
@@ -1246,16 +1249,23 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
       g[7] = __int_as_float((((l1 >= 0 && l1 < KM_NL) || (l2 >= 0 && l2 < KM_NL)) ? 1 : 0) | ((l1 == KM_NL || l2 == KM_NL) ? 2 : 0));
     }
   END_LANES
+  // which contacts touch the robot block / the box block (ncon <= 32: one bit per contact); the loops
+  // below then visit only the contacts that can contribute (typically: 4 box contacts, no robot contact)
+  const unsigned mrob = warp_ballot(W, [&](int l, LaneRegs&) { return l < ncon && (__float_as_int(S.cgeo[l][7]) & 1); });
+  const unsigned mbox = warp_ballot(W, [&](int l, LaneRegs&) { return l < ncon && (__float_as_int(S.cgeo[l][7]) & 2); });
   LANES(W, R)
     if (lane < KM_NV) {
-      const int myblk = lane < KM_NL ? 1 : 2;
       float fc = 0.f;
       for (int r = 0; r < nlim; ++r) { const float ja = S.rJaref[r]; if (ja < 0.f && S.limdof[r] == lane) fc += S.limsign[r] * (-S.rD[r] * ja); }
 #pragma unroll 1
-      for (int c = 0; c < ncon; ++c) {
-        const float* g = S.cgeo[c];
-        if (!(__float_as_int(g[7]) & myblk)) continue;
-        const float* J = S.cJ[c];
+      for (unsigned rem = lane < KM_NL ? mrob : mbox; rem != 0u; rem &= rem - 1u) {
+        const int c = KFFS(rem) - 1;
+        const float* g = S.cgeo[c]; const float* J = S.cJ[c];
+        fc += J[lane] * g[0] + J[12 + lane] * g[1] + J[24 + lane] * g[2];
+      }
+#pragma unroll 1
+      for (int c = 32; c < ncon; ++c) {          // only the 48-contact re-run kernel can get here
+        const float* g = S.cgeo[c]; const float* J = S.cJ[c];
         fc += J[lane] * g[0] + J[12 + lane] * g[1] + J[24 + lane] * g[2];
       }
       S.grad[lane] = S.Ma[lane] - S.fs[lane] - fc;
@@ -1265,13 +1275,19 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
       const int i = (R.tri >> (8 * q)) & 15, j = (R.tri >> (8 * q + 4)) & 15;
       if (i < KM_NV) {
         float h = M_entry<NC>(m, S, i, j);
-        const int need = (i < KM_NL ? 1 : 2) | (j < KM_NL ? 1 : 2);
         for (int r = 0; r < nlim; ++r) if (S.rJaref[r] < 0.f && S.limdof[r] == i && i == j) h += S.rD[r];
+        // entry (i, j) only sees contacts that touch the blocks of both i and j
+        const unsigned sel = (i < KM_NL ? mrob : mbox) & (j < KM_NL ? mrob : mbox);
 #pragma unroll 1
-        for (int c = 0; c < ncon; ++c) {
-          const float* g = S.cgeo[c];
-          if ((__float_as_int(g[7]) & need) != need) continue;
-          const float* J = S.cJ[c];
+        for (unsigned rem = sel; rem != 0u; rem &= rem - 1u) {
+          const int c = KFFS(rem) - 1;
+          const float* g = S.cgeo[c]; const float* J = S.cJ[c];
+          const float ni = J[i], nj = J[j], ai = J[12 + i], aj = J[12 + j], bi = J[24 + i], bj = J[24 + j];
+          h += g[3] * (ni + ai) * (nj + aj) + g[4] * (ni - ai) * (nj - aj) + g[5] * (ni + bi) * (nj + bj) + g[6] * (ni - bi) * (nj - bj);
+        }
+#pragma unroll 1
+        for (int c = 32; c < ncon; ++c) {
+          const float* g = S.cgeo[c]; const float* J = S.cJ[c];
           const float ni = J[i], nj = J[j], ai = J[12 + i], aj = J[12 + j], bi = J[24 + i], bj = J[24 + j];
           h += g[3] * (ni + ai) * (nj + aj) + g[4] * (ni - ai) * (nj - aj) + g[5] * (ni + bi) * (nj + bj) + g[6] * (ni - bi) * (nj - bj);
         }
@@ -1323,6 +1339,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
   qg[1] = warp_sum(W, [](int, LaneRegs& R) { return R.f1; });
   qg[2] = warp_sum(W, [](int, LaneRegs& R) { return R.f2; });
   const float gtol = m.tolerance * m.ls_tolerance * snorm * m.meaninertia * (float)KM_NV;
+  PHASE(W, 19);
   // One rolled loop evaluates the piecewise quadratic at three step sizes per trip:
   //   trip -2: p0 = point(0); trip -1: lo = point(-p0.d0/p0.d1); trips 0..ls_iterations-1: MJX bracket update.
   LSPoint p0, lo, hi;
@@ -1352,14 +1369,13 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
       }
       R.acc[0] = a0; R.acc[1] = a1; R.acc[2] = a2; R.acc[3] = b0; R.acc[4] = b1; R.acc[5] = b2; R.acc[6] = c0; R.acc[7] = c1; R.acc[8] = c2;
     END_LANES
+    float sums[9];
+    warp_sum9(W, sums);
     LSPoint pt[3];
     const float als[3] = {al0, al1, al2};
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      if (it < 0 && k > 0) { pt[k] = pt[0]; continue; }
-      const float q0 = qg[0] + warp_sum(W, [&](int, LaneRegs& R) { return R.acc[3 * k]; });
-      const float q1 = qg[1] + warp_sum(W, [&](int, LaneRegs& R) { return R.acc[3 * k + 1]; });
-      const float q2 = qg[2] + warp_sum(W, [&](int, LaneRegs& R) { return R.acc[3 * k + 2]; });
+      const float q0 = qg[0] + sums[3 * k], q1 = qg[1] + sums[3 * k + 1], q2 = qg[2] + sums[3 * k + 2];
       const float a = als[k];
       pt[k].alpha = a;
       pt[k].cost = a * a * q2 + a * q1 + q0;

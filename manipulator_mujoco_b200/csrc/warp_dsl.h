@@ -70,7 +70,7 @@ struct WarpCtx {
   LR regs;
   int lane;
 #ifdef CEMK_PHASE_TIMING
-  long long t0; int phase; long long ph[16];
+  long long t0; int phase; long long ph[24];
 #endif
 #endif
 };
@@ -185,5 +185,48 @@ KFN int warp_argmax_first8(W& w, F f) {
     if (ov > v || (ov == v && oi < idx) || (v != v && ov == ov)) { v = ov; idx = oi; }
   }
   return __shfl_sync(0xffffffffu, idx, 0);
+#endif
+}
+
+// Sums of nine per-lane values (regs.acc[0..8]) over the warp, all nine results to every lane.
+// GPU: transposed butterfly -- each exchange round halves the number of values a lane still carries
+// (5+3+2+1+1 shuffles), then nine broadcasts: 21 shuffles instead of 45.
+template <class W>
+KFN void warp_sum9(W& w, float* out) {
+#ifdef CEMK_EMU
+  for (int k = 0; k < 9; ++k) { float s = 0.f; for (int l = 0; l < 32; ++l) s += w.regs[l].acc[k]; out[k] = s; }
+#else
+  const int lane = w.lane;
+  const bool hi = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+  float v[10];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) v[k] = w.regs.acc[k];
+  v[9] = 0.f;
+  float u[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const float recv = __shfl_xor_sync(0xffffffffu, hi ? v[k] : v[5 + k], 16);
+    u[k] = (hi ? v[5 + k] : v[k]) + recv;
+  }
+  float t[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float mine = h8 ? (k < 2 ? u[3 + k] : 0.f) : u[k];
+    const float send = h8 ? u[k] : (k < 2 ? u[3 + k] : 0.f);
+    t[k] = mine + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  float s2[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float mine = h4 ? (k < 1 ? t[2] : 0.f) : t[k];
+    const float send = h4 ? t[k] : (k < 1 ? t[2] : 0.f);
+    s2[k] = mine + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  float r = (h2 ? s2[1] : s2[0]) + __shfl_xor_sync(0xffffffffu, h2 ? s2[0] : s2[1], 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  // lane that ends up holding the total of original index k
+  out[0] = __shfl_sync(0xffffffffu, r, 0);  out[1] = __shfl_sync(0xffffffffu, r, 2);  out[2] = __shfl_sync(0xffffffffu, r, 4);
+  out[3] = __shfl_sync(0xffffffffu, r, 8);  out[4] = __shfl_sync(0xffffffffu, r, 10); out[5] = __shfl_sync(0xffffffffu, r, 16);
+  out[6] = __shfl_sync(0xffffffffu, r, 18); out[7] = __shfl_sync(0xffffffffu, r, 20); out[8] = __shfl_sync(0xffffffffu, r, 24);
 #endif
 }

@@ -25,7 +25,7 @@ pl = cem_planner(num_dof=6, num_batch=B, num_steps=T, timestep=0.05, maxiter_cem
 q0 = np.array([1.5, -1.8, 1.75, -1.25, -1.6, 0.0])
 tp, tr = np.array([-0.3, -0.3, 0.5]), np.array([0.0, 1.0, 0.0, 0.0])
 lib = C.CDLL(dbg)
-buf = (C.c_ulonglong * 16)()
+buf = (C.c_ulonglong * 24)()
 for _ in range(2):
     pl.compute_cem(np.zeros(66), q0, np.zeros(6), np.zeros(6), tp, tr)
 torch.cuda.synchronize()
@@ -34,8 +34,8 @@ pl.compute_cem(np.zeros(66), q0, np.zeros(6), np.zeros(6), tp, tr)
 torch.cuda.synchronize()
 pl._lib.cemk_debug_phase_clocks(buf)
 names = ["align-exit", "P1 FK chain", "P2-P5 dynamics", "P6 qacc_smooth", "N1 robot narrow phase + cost", "N1 free-box pairs", "N2 emit contacts",
-         "C1-C3 rows/Jacobians", "S1 warm/smooth", "S3 grad + H", "S4 Cholesky + solve", "S5 line search", "obs + euler", "step barrier wait",
-         "prologue", "epilogue"]
+         "phase-barrier wait + C1 limit rows", "S1 warm/smooth", "S3 grad + H", "S4 Cholesky + solve", "S5a line-search setup", "obs + euler", "step barrier wait",
+         "prologue", "epilogue", "C2 contact Jacobians", "C3 row parameters", "(issue of phase barrier)", "S5b line-search trips", "-", "-", "-", "-"]
 v = np.array(list(buf), dtype=np.float64)
 print(f"k_rollout phase shares, B={B} T={T} (clock64 per warp, summed)")
 for n, x in sorted(zip(names, v), key=lambda t: -t[1]):
