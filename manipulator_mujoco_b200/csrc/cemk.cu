@@ -21,9 +21,6 @@
 #ifndef ROLLOUT_WARPS
 #define ROLLOUT_WARPS 16      // samples (warps) per CTA; they step in lockstep (STEP_ALIGN) to share the instruction cache
 #endif
-#ifndef ROLLOUT_WARPS_ALT
-#define ROLLOUT_WARPS_ALT 14  // alternative CTA size picked when it quantises better onto the SMs
-#endif
 #ifndef ROLLOUT_MINB
 #define ROLLOUT_MINB 1
 #endif
@@ -44,7 +41,8 @@ struct cemk_handle {
   float* d_K;      // Kpp[121] Kpe[55] bounds[3]
   long long launches;
   int* d_flags; int flags_cap; int num_sms;
-  int force_rerun;               // debug option: recompute every sample with the big-capacity kernel   // per-sample overflow flags when the caller passes none
+  int force_rerun;               // debug option: recompute every sample with the big-capacity kernel
+  int cta_warps;                 // debug option: fixed number of samples per CTA (0 = balanced waves, see cemk_rollout_cost)
 };
 
 // ---------------------------------------------------------------------------------------------- rollout
@@ -56,6 +54,9 @@ struct RolloutBatch {
   const float* thetadot; const float* q0; const float* v0; const float* target_pos; const float* target_rot;
   float w_pos, w_rot, w_col;
   float* theta; float* cost4; float* eef_pos; float* eef_rot; float* collision; float* qacc; int* flags;
+  // CTA -> samples: the first n_hi CTAs run w_hi samples each, the others w_lo (both <= the launch width);
+  // warps beyond a CTA's share exit at once
+  int n_hi, w_hi, w_lo;
 };
 
 // NC = capacity of the per-sample active-contact list, WARPS = samples per CTA.  The fast
@@ -67,26 +68,26 @@ __global__ void __launch_bounds__(WARPS * 32, ROLLOUT_MINB) k_rollout(const KMod
   KModel* sm = reinterpret_cast<KModel*>(smem_raw);
   WarpSmemT<NC>* ws = reinterpret_cast<WarpSmemT<NC>*>(smem_raw + ((sizeof(KModel) + 15) & ~size_t(15)));
   const int warp = threadIdx.x >> 5;
-  int s = blockIdx.x * WARPS + warp;
+  const int cta = blockIdx.x;
+  const int share = cta < a.n_hi ? a.w_hi : a.w_lo;
+  const int base = cta < a.n_hi ? cta * a.w_hi : a.n_hi * a.w_hi + (cta - a.n_hi) * a.w_lo;
+  const int nlive = min(share, a.B - base);               // samples this CTA rolls out (<= 0: nothing left)
+  const int s = base + warp;
   if (ONLY_FLAGGED) {
     if (s >= a.B || !(a.flags[s] & 1)) return;            // WARPS == 1: the whole CTA leaves together
   }
+  if (nlive <= 0) return;
   {
     const int* src = reinterpret_cast<const int*>(gm);
     int* dst = reinterpret_cast<int*>(sm);
     for (int i = threadIdx.x; i < (int)(sizeof(KModel) / 4); i += blockDim.x) dst[i] = src[i];
   }
   __syncthreads();
-  const bool live = s < a.B;
-  if (!live) {
-#ifdef CEMK_STEP_SYNC
-    s = a.B - 1;            // padding warp: keeps the CTA's per-step barrier count uniform, writes nothing
-#else
-    return;
-#endif
-  }
+  if (warp >= nlive) return;                              // the live warps align on a named barrier of nlive * 32 threads
+  const bool live = true;
   Warp W;
   W.lane = threadIdx.x & 31;
+  W.nthr = nlive * 32;
 #ifdef CEMK_PHASE_TIMING
   W.phase = 14; W.t0 = clock64();
   for (int i = 0; i < 24; ++i) W.ph[i] = 0;
@@ -393,15 +394,13 @@ int cemk_create(const void* kmodel, int kmodel_bytes, int device, cemk_handle** 
     return set_err(CEMK_ERR_MODEL, "cemk_create: unsupported topology");
   CK(cudaSetDevice(device));
   cemk_handle* h = new cemk_handle();
-  h->device = device; h->T = 0; h->d_G = nullptr; h->d_K = nullptr; h->launches = 0; h->d_flags = nullptr; h->flags_cap = 0; h->force_rerun = 0;
+  h->device = device; h->T = 0; h->d_G = nullptr; h->d_K = nullptr; h->launches = 0; h->d_flags = nullptr; h->flags_cap = 0; h->force_rerun = 0; h->cta_warps = 0;
   { cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device)); h->num_sms = prop.multiProcessorCount; }
   CK(cudaMalloc(&h->d_model, sizeof(KModel)));
   CK(cudaMemcpy(h->d_model, kmodel, sizeof(KModel), cudaMemcpyHostToDevice));
   CK(cudaMalloc(&h->d_K, 179 * sizeof(float)));
   CK(cudaFuncSetAttribute(k_rollout<KM_NC_FAST, ROLLOUT_WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)rollout_smem<KM_NC_FAST, ROLLOUT_WARPS>()));
-  CK(cudaFuncSetAttribute(k_rollout<KM_NC_FAST, ROLLOUT_WARPS_ALT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)rollout_smem<KM_NC_FAST, ROLLOUT_WARPS_ALT>()));
   CK(cudaFuncSetAttribute(k_rollout<KM_NC_FAST, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rollout_smem<KM_NC_FAST, 8>()));
   CK(cudaFuncSetAttribute(k_rollout<KM_NC_FAST, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rollout_smem<KM_NC_FAST, 4>()));
   CK(cudaFuncSetAttribute(k_rollout<KM_NC_BIG, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -478,19 +477,41 @@ int cemk_rollout_cost(cemk_handle* h, int B, int T, const float* thetadot, const
   a.B = B; a.T = T; a.thetadot = thetadot; a.q0 = q0; a.v0 = v0; a.target_pos = target_pos; a.target_rot = target_rot;
   a.w_pos = w_pos; a.w_rot = w_rot; a.w_col = w_col;
   a.theta = theta; a.cost4 = cost4; a.eef_pos = eef_pos; a.eef_rot = eef_rot; a.collision = collision; a.qacc = qacc; a.flags = flags;
-  // CTA size (samples per CTA; one CTA per SM is resident): batches that do not fill the GPU use small
-  // CTAs so every SM gets work (latency-bound regime, e.g. the closed-loop config B = 1000); otherwise
-  // 16 or 14, whichever wastes fewer SM slots in the last wave.
+  // Samples per CTA.  One CTA is resident per SM and its warps step in lockstep, so the time of a wave
+  // grows with the warps per SM sub-partition (4 schedulers): shares are multiples of 4 where possible.
+  //  * B <= 4 SMs-worth: 4-warp CTAs of the 4-warp instantiation (more registers, latency-bound regime);
+  //  * one wave: every SM gets ceil(B / SMs) samples;
+  //  * several waves: the ceil(B / SMs) samples an SM has to run are split into `waves` shares counted in
+  //    quads, e.g. 4096 samples on 148 SMs = 28 per SM = one wave of 16 and one of 12 (a uniform 14 + 14
+  //    would load two of the four schedulers with 4 warps in both waves).
   const int nsm = h->num_sms > 0 ? h->num_sms : 148;
-  auto waste = [&](int w) { const int ctas = (B + w - 1) / w; const int waves = (ctas + nsm - 1) / nsm; return (double)waves * nsm * w / (double)B; };
-#define CEMK_LAUNCH_ROLLOUT(W_) k_rollout<KM_NC_FAST, W_, false><<<(B + (W_) - 1) / (W_), (W_) * 32, rollout_smem<KM_NC_FAST, W_>(), st>>>(h->d_model, a)
-  if (B <= nsm * 4) CEMK_LAUNCH_ROLLOUT(4);
-  else if (B <= nsm * 8) CEMK_LAUNCH_ROLLOUT(8);
-  else if (waste(ROLLOUT_WARPS_ALT) + 0.02 < waste(ROLLOUT_WARPS)) CEMK_LAUNCH_ROLLOUT(ROLLOUT_WARPS_ALT);
-  else CEMK_LAUNCH_ROLLOUT(ROLLOUT_WARPS);
+  int grid;
+#define CEMK_LAUNCH_ROLLOUT(W_) k_rollout<KM_NC_FAST, W_, false><<<grid, (W_) * 32, rollout_smem<KM_NC_FAST, W_>(), st>>>(h->d_model, a)
+  if (h->cta_warps > 0) {
+    const int w = h->cta_warps < ROLLOUT_WARPS ? h->cta_warps : ROLLOUT_WARPS;
+    a.n_hi = 0; a.w_hi = a.w_lo = w; grid = (B + w - 1) / w;
+    CEMK_LAUNCH_ROLLOUT(ROLLOUT_WARPS);
+  } else if (B <= nsm * 4) {
+    a.n_hi = 0; a.w_hi = a.w_lo = 4; grid = (B + 3) / 4;
+    CEMK_LAUNCH_ROLLOUT(4);
+  } else {
+    const int need = (B + nsm - 1) / nsm;                          // samples per SM
+    const int waves = (need + ROLLOUT_WARPS - 1) / ROLLOUT_WARPS;
+    if (waves == 1) {
+      a.n_hi = 0; a.w_hi = a.w_lo = need; grid = (B + need - 1) / need;
+      if (need <= 8) CEMK_LAUNCH_ROLLOUT(8); else CEMK_LAUNCH_ROLLOUT(ROLLOUT_WARPS);
+    } else {
+      const int quads = (need + 3) / 4, q_lo = quads / waves, r = quads % waves;
+      a.w_lo = 4 * q_lo; a.w_hi = 4 * (q_lo + (r ? 1 : 0)); a.n_hi = r * nsm;
+      const int rest = B - a.n_hi * a.w_hi;
+      grid = a.n_hi + (rest > 0 ? (rest + a.w_lo - 1) / a.w_lo : 0);
+      CEMK_LAUNCH_ROLLOUT(ROLLOUT_WARPS);
+    }
+  }
 #undef CEMK_LAUNCH_ROLLOUT
   // samples whose active-contact list overflowed the fast capacity are recomputed with the big one
   if (h->force_rerun) CK(cudaMemsetAsync(flags, 1, sizeof(int) * B, st));      // 0x01010101: bit 0 set
+  a.n_hi = 0; a.w_hi = a.w_lo = 1;
   k_rollout<KM_NC_BIG, 1, true><<<B, 32, rollout_smem<KM_NC_BIG, 1>(), st>>>(h->d_model, a);
   h->launches += 2;
   CK(cudaPeekAtLastError());
@@ -571,6 +592,7 @@ long long cemk_launch_count(cemk_handle* h) { return h ? h->launches : 0; }
 int cemk_set_option(cemk_handle* h, const char* name, int value) {
   if (!h || !name) return set_err(CEMK_ERR_ARG, "cemk_set_option: null argument");
   if (!strcmp(name, "force_rerun")) { h->force_rerun = value != 0; return CEMK_OK; }
+  if (!strcmp(name, "cta_warps")) { h->cta_warps = value > 0 ? value : 0; return CEMK_OK; }
   return set_err(CEMK_ERR_ARG, "cemk_set_option: unknown option");
 }
 

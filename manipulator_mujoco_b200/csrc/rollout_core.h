@@ -36,7 +36,7 @@ struct LaneRegs {
   float cost_c;               // this lane's share of cost_c
   int nact, off;              // active contacts this lane will emit, and where
   int actmask;                // bit (2*pass + slot)
-  int tri;                    // three packed (i, j) pairs of the lower triangle this lane owns (4 bits each)
+  int tri;                    // (i, j) of the 6x6 lower-triangle entry this lane owns, 4 bits each (lanes 0-20)
   float td;                   // next step's commanded joint velocity (lanes < 6), prefetched one step ahead
   float acc[9];               // line-search partial sums (compile-time indices only)
   float h[KM_NV];             // row `lane` of the Newton Hessian / its Cholesky factor
@@ -681,12 +681,6 @@ KFN float mul_M(const KModel& m, const WarpSmemT<NC>& S, int d, const float* v) 
   if (d < KM_NL) { float s = 0.f; for (int k = 0; k < KM_NL; ++k) s += S.Mr[d][k] * v[k]; return s; }
   return (d < KM_NL + 3 ? m.fb_mass : (d == KM_NL + 3 ? m.fb_inertia[0] : (d == KM_NL + 4 ? m.fb_inertia[1] : m.fb_inertia[2]))) * v[d];
 }
-template <int NC>
-KFN float M_entry(const KModel& m, const WarpSmemT<NC>& S, int i, int j) {
-  if (i < KM_NL) return j < KM_NL ? S.Mr[i][j] : 0.f;
-  if (i != j) return 0.f;
-  return i < KM_NL + 3 ? m.fb_mass : (i == KM_NL + 3 ? m.fb_inertia[0] : (i == KM_NL + 4 ? m.fb_inertia[1] : m.fb_inertia[2]));
-}
 // translational Jacobian column of world point p on `link` (0..5 robot link, 6 free box, <0 static)
 template <int NC>
 KFN void jac_col(const KModel& m, const WarpSmemT<NC>& S, const float* p, int link, int d, float* col) {
@@ -797,6 +791,29 @@ KFN void chol_solve_rows(Warp& W) {
       warp_shfl_each(W, [&](int, LaneRegs& R) { return R.h[i] * R.f1; }, [&](int l) { return base(l) + k; },
                      [&](int l, LaneRegs& R, float p) { if (loc(l) == i) R.f0 -= p; });
   }
+}
+
+// sum over the contacts in `sel` (bit c = contact c; contacts >= 32 exist only in the 48-contact re-run
+// kernel and are all visited) of the Hessian contribution of the four pyramid rows to entry (i, j)
+template <int NC>
+KFN float hess_contacts(const WarpSmemT<NC>& S, unsigned sel, int ncon, int i, int j) {
+  float h = 0.f;
+#pragma unroll 1
+  for (unsigned rem = sel; rem != 0u; rem &= rem - 1u) {
+    const int c = KFFS(rem) - 1;
+    const float* g = S.cgeo[c]; const float* J = S.cJ[c];
+    const float ni = J[i], nj = J[j], ai = J[12 + i], aj = J[12 + j], bi = J[24 + i], bj = J[24 + j];
+    h += g[3] * (ni + ai) * (nj + aj) + g[4] * (ni - ai) * (nj - aj) + g[5] * (ni + bi) * (nj + bj) + g[6] * (ni - bi) * (nj - bj);
+  }
+  if (NC > 32) {
+#pragma unroll 1
+    for (int c = 32; c < ncon; ++c) {
+      const float* g = S.cgeo[c]; const float* J = S.cJ[c];
+      const float ni = J[i], nj = J[j], ai = J[12 + i], aj = J[12 + j], bi = J[24 + i], bj = J[24 + j];
+      h += g[3] * (ni + ai) * (nj + aj) + g[4] * (ni - ai) * (nj - aj) + g[5] * (ni + bi) * (nj + bj) + g[6] * (ni - bi) * (nj - bj);
+    }
+  }
+  return h;
 }
 
 struct LSPoint { float alpha, cost, d0, d1; };
@@ -963,8 +980,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
   // ---- P4: robot inertia matrix entries (lanes 0-20), cdof_dot (lanes 24-29) ----
   LANES(W, R)
     if (lane < 21) {
-      int i = 0, j = lane;
-      while (j > i) { j -= i + 1; ++i; }        // lane -> (i, j), j <= i
+      const int i = R.tri & 15, j = (R.tri >> 4) & 15;
       float buf[6];
       mul_inert(buf, S.crb[i], S.cdof[i]);
       float v = dot6(S.cdof[j], buf);
@@ -1263,35 +1279,35 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
         const float* g = S.cgeo[c]; const float* J = S.cJ[c];
         fc += J[lane] * g[0] + J[12 + lane] * g[1] + J[24 + lane] * g[2];
       }
+      if (NC > 32) {
 #pragma unroll 1
-      for (int c = 32; c < ncon; ++c) {          // only the 48-contact re-run kernel can get here
-        const float* g = S.cgeo[c]; const float* J = S.cJ[c];
-        fc += J[lane] * g[0] + J[12 + lane] * g[1] + J[24 + lane] * g[2];
+        for (int c = 32; c < ncon; ++c) {        // only the 48-contact re-run kernel can get here
+          const float* g = S.cgeo[c]; const float* J = S.cJ[c];
+          fc += J[lane] * g[0] + J[12 + lane] * g[1] + J[24 + lane] * g[2];
+        }
       }
       S.grad[lane] = S.Ma[lane] - S.fs[lane] - fc;
     }
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const int i = (R.tri >> (8 * q)) & 15, j = (R.tri >> (8 * q + 4)) & 15;
-      if (i < KM_NV) {
-        float h = M_entry<NC>(m, S, i, j);
-        for (int r = 0; r < nlim; ++r) if (S.rJaref[r] < 0.f && S.limdof[r] == i && i == j) h += S.rD[r];
-        // entry (i, j) only sees contacts that touch the blocks of both i and j
-        const unsigned sel = (i < KM_NL ? mrob : mbox) & (j < KM_NL ? mrob : mbox);
+  END_LANES
+  // Hessian by blocks: lanes 0-20 own entry (i, j) of the 6x6 lower triangle and build it for the robot
+  // block and for the box block; the 36 robot/box cross entries exist only when a contact couples the two
+  // (otherwise the blocks are solved separately and the cross entries are never read).
+  LANES(W, R)
+    if (lane < 21) {
+      const int i = R.tri & 15, j = (R.tri >> 4) & 15;
+      float hr = S.Mr[i][j];
+      for (int r = 0; r < nlim; ++r) if (S.rJaref[r] < 0.f && S.limdof[r] == i && i == j) hr += S.rD[r];
+      hr += hess_contacts<NC>(S, mrob, ncon, i, j);
+      S.H[i][j] = hr;
+      float hb = i != j ? 0.f : (i < 3 ? m.fb_mass : (i == 3 ? m.fb_inertia[0] : (i == 4 ? m.fb_inertia[1] : m.fb_inertia[2])));
+      hb += hess_contacts<NC>(S, mbox, ncon, KM_NL + i, KM_NL + j);
+      S.H[KM_NL + i][KM_NL + j] = hb;
+    }
+    if (coupled) {
 #pragma unroll 1
-        for (unsigned rem = sel; rem != 0u; rem &= rem - 1u) {
-          const int c = KFFS(rem) - 1;
-          const float* g = S.cgeo[c]; const float* J = S.cJ[c];
-          const float ni = J[i], nj = J[j], ai = J[12 + i], aj = J[12 + j], bi = J[24 + i], bj = J[24 + j];
-          h += g[3] * (ni + ai) * (nj + aj) + g[4] * (ni - ai) * (nj - aj) + g[5] * (ni + bi) * (nj + bj) + g[6] * (ni - bi) * (nj - bj);
-        }
-#pragma unroll 1
-        for (int c = 32; c < ncon; ++c) {
-          const float* g = S.cgeo[c]; const float* J = S.cJ[c];
-          const float ni = J[i], nj = J[j], ai = J[12 + i], aj = J[12 + j], bi = J[24 + i], bj = J[24 + j];
-          h += g[3] * (ni + ai) * (nj + aj) + g[4] * (ni - ai) * (nj - aj) + g[5] * (ni + bi) * (nj + bj) + g[6] * (ni - bi) * (nj - bj);
-        }
-        S.H[i][j] = h;
+      for (int e = lane; e < KM_NL * KM_NL; e += 32) {
+        const int i = KM_NL + e / KM_NL, j = e % KM_NL;
+        S.H[i][j] = hess_contacts<NC>(S, mrob & mbox, ncon, i, j);
       }
     }
   END_LANES
@@ -1319,37 +1335,42 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
   }
   PHASE(W, 11);
   // ---- S5: line search (BD.10) ----
-  LANES(W, R)
-    R.f0 = R.f1 = R.f2 = 0.f;
-    if (lane < KM_NV) {
-      float mv = mul_M<NC>(m, S, lane, S.search);
-      S.mv[lane] = mv;
-      float s = S.search[lane];
-      R.f0 = s * s; R.f1 = s * S.Ma[lane] - s * S.fs[lane]; R.f2 = 0.5f * s * mv;
-    }
-  END_LANES
+  // J.search per row, the Gauss-term sums and the constraint sums of the starting point alpha = 0
+  // (MJX's p0) in one pass and one fused warp reduction
   contact_dots<NC>(W, S, ncon, S.search, nullptr);
   LANES(W, R)
+    float e0 = 0.f, e1 = 0.f, e2 = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    if (lane < KM_NV) {
+      const float mv = mul_M<NC>(m, S, lane, S.search), s = S.search[lane];
+      e0 = s * s; e1 = s * S.Ma[lane] - s * S.fs[lane]; e2 = 0.5f * s * mv;
+    }
 #pragma unroll 1
-    for (int r = lane; r < nrow; r += 32) S.rJv[r] = row_val<NC>(S, 0, r, S.search);
+    for (int r = lane; r < nrow; r += 32) {
+      const float jv = row_val<NC>(S, 0, r, S.search), ja = S.rJaref[r], D = S.rD[r];
+      S.rJv[r] = jv;
+      if (ja < 0.f) { a0 += 0.5f * D * ja * ja; a1 += D * jv * ja; a2 += 0.5f * D * jv * jv; }
+    }
+    R.acc[0] = e0; R.acc[1] = e1; R.acc[2] = e2; R.acc[3] = a0; R.acc[4] = a1; R.acc[5] = a2; R.acc[6] = R.acc[7] = R.acc[8] = 0.f;
   END_LANES
-  float qg[3];
-  const float snorm = sqrtf(warp_sum(W, [](int, LaneRegs& R) { return R.f0; }));
-  qg[0] = gauss;
-  qg[1] = warp_sum(W, [](int, LaneRegs& R) { return R.f1; });
-  qg[2] = warp_sum(W, [](int, LaneRegs& R) { return R.f2; });
-  const float gtol = m.tolerance * m.ls_tolerance * snorm * m.meaninertia * (float)KM_NV;
+  float qg[3], gtol;
+  LSPoint p0, lo, hi;
+  {
+    float sums[9];
+    warp_sum9(W, sums);
+    qg[0] = gauss; qg[1] = sums[1]; qg[2] = sums[2];
+    gtol = m.tolerance * m.ls_tolerance * sqrtf(sums[0]) * m.meaninertia * (float)KM_NV;
+    const float q2 = qg[2] + sums[5];
+    p0.alpha = 0.f; p0.cost = qg[0] + sums[3]; p0.d0 = qg[1] + sums[4]; p0.d1 = 2.f * q2 + (q2 == 0.f ? MJ_MINVAL : 0.f);
+    lo = p0; hi = p0;
+  }
   PHASE(W, 19);
   // One rolled loop evaluates the piecewise quadratic at three step sizes per trip:
-  //   trip -2: p0 = point(0); trip -1: lo = point(-p0.d0/p0.d1); trips 0..ls_iterations-1: MJX bracket update.
-  LSPoint p0, lo, hi;
-  p0.alpha = p0.cost = p0.d0 = 0.f; p0.d1 = 1.f; lo = p0; hi = p0;
+  //   trip -1: lo = point(-p0.d0/p0.d1); trips 0..ls_iterations-1: MJX bracket update.
   bool swapped = true;
 #pragma unroll 1
-  for (int it = -2; it < m.ls_iterations; ++it) {
+  for (int it = -1; it < m.ls_iterations; ++it) {
     float al0, al1, al2;
-    if (it == -2) { al0 = al1 = al2 = 0.f; }
-    else if (it == -1) { al0 = al1 = al2 = p0.alpha - p0.d0 / p0.d1; }
+    if (it == -1) { al0 = al1 = al2 = p0.alpha - p0.d0 / p0.d1; }
     else {
       bool done = !swapped;
       done = done || ((lo.d0 < 0.f) && (lo.d0 > -gtol));
@@ -1382,7 +1403,6 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
       pt[k].d0 = 2.f * a * q2 + q1;
       pt[k].d1 = 2.f * q2 + (q2 == 0.f ? MJ_MINVAL : 0.f);
     }
-    if (it == -2) { p0 = pt[0]; continue; }
     if (it == -1) {
       if (pt[0].d0 < p0.d0) { lo = pt[0]; hi = p0; } else { hi = pt[0]; lo = p0; }
       continue;
@@ -1457,14 +1477,10 @@ KFN void rollout_sample(Warp& W, const KModel& m, WarpSmemT<NC>& S, const Rollou
     if (lane < KM_NQ) S.qpos[lane] = lane < KM_NL ? A.q0[lane] : m.qpos0[lane];
     if (lane < KM_NV) { S.qvel[lane] = lane < KM_NL ? A.v0[lane] : m.qvel0[lane]; S.warm[lane] = m.warm0[lane]; }
     {
-      // the three lower-triangle entries (i, j) this lane owns: e = lane, lane + 32, lane + 64 (78 in total)
-      int tri = 0;
-      for (int q = 0; q < 3; ++q) {
-        int e = lane + 32 * q, i = 0, j = e;
-        if (e < KM_NV * (KM_NV + 1) / 2) { while (j > i) { j -= i + 1; ++i; } } else { i = 15; j = 15; }
-        tri |= (i | (j << 4)) << (8 * q);
-      }
-      R.tri = tri;
+      // the entry (i, j), j <= i, of a 6x6 lower triangle this lane owns (lanes 0-20)
+      int i = 0, j = lane;
+      if (lane < KM_NL * (KM_NL + 1) / 2) { while (j > i) { j -= i + 1; ++i; } } else { i = 15; j = 15; }
+      R.tri = i | (j << 4);
     }
     if (lane == 0) S.flags = 0;
     R.cost_c = 0.f;

@@ -38,14 +38,17 @@ static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); retur
 #define KFN __device__ __forceinline__
 #define KNOINLINE __device__ __noinline__
 #ifdef CEMK_STEP_SYNC
-#define STEP_ALIGN() __syncthreads()     // keep the warps of a CTA on the same code (instruction-cache locality)
+// keep the live warps of a CTA on the same code (instruction-cache locality).  Named barrier 1 with the
+// live thread count of this CTA (a CTA may run fewer samples than its launch width, see cemk_rollout_cost).
+#define CTA_ALIGN(W) asm volatile("bar.sync 1, %0;" :: "r"((W).nthr) : "memory")
+#define STEP_ALIGN() CTA_ALIGN(W)
 #else
 #define STEP_ALIGN()
 #endif
 // optional extra CTA-wide re-alignments inside a step, selected by the bits of CEMK_PHASE_SYNC
 // (only at points every warp reaches)
 #if defined(CEMK_STEP_SYNC) && defined(CEMK_PHASE_SYNC)
-#define PHASE_ALIGN(bit) do { if ((CEMK_PHASE_SYNC) & (bit)) __syncthreads(); } while (0)
+#define PHASE_ALIGN(bit) do { if ((CEMK_PHASE_SYNC) & (bit)) CTA_ALIGN(W); } while (0)
 #else
 #define PHASE_ALIGN(bit)
 #endif
@@ -69,6 +72,7 @@ struct WarpCtx {
 #else
   LR regs;
   int lane;
+  int nthr;          // live threads of this CTA (barrier width)
 #ifdef CEMK_PHASE_TIMING
   long long t0; int phase; long long ph[24];
 #endif
