@@ -170,8 +170,11 @@ def main():
     mean0 = torch.zeros(pl.nvar, device=dev)
     cov0 = 10 * torch.eye(pl.nvar, device=dev)
 
+    from manipulator_mujoco_b200 import jax_prng
+    key1 = jax_prng.split(pl.key)[0]                                   # compute_cem's key (mjx_planner.py:388)
+
     def device_step():
-        carry = (q0, z6, tp, tr, mean0, cov0, pl.key + 1, state_term)
+        carry = (q0, z6, tp, tr, mean0, cov0, key1, state_term)
         return pl.cem_iter(carry, None)
 
     def timed(fn, k, flush_l2=True):
@@ -226,7 +229,7 @@ def main():
     e2e_value = Bg * T * args.steps / (float(e2e_tot.item()) * 1e-3)
 
     # ---------------- dominant kernel alone: the fused rollout + cost ----------------
-    xi, _ = pl.compute_xi_samples(pl.key + 1, mean0, cov0)
+    xi, _ = pl.compute_xi_samples(key1, mean0, cov0)
     xi_f, thetadot = pl._project(xi, state_term, True)
 
     def rollout_only():

@@ -51,6 +51,13 @@ int cemk_set_horizon(cemk_handle* h, int T, const float* G, const float* Kpp, co
 int cemk_sample(cemk_handle* h, int B, const float* z, const float* mean, const float* cov, float* chol_ws, float* xi,
                 void* stream);
 
+/* The standard-normal draws of jax.random.multivariate_normal (mjx_planner.py:315; jax==0.5.3, requirements.txt:9):
+ *   out[i] = jax.random.normal(key, (total,), float32)[offset + i], i < count, for the raw threefry key
+ *   (key0, key1).  `original` = 0: jax_threefry_partitionable (default since jax 0.5), 1: the older layout.
+ *   A [B][66] table is total = B*66, row-major; a rank fills its rows with offset = first_row*66. */
+int cemk_jax_normal(cemk_handle* h, unsigned key0, unsigned key1, int original, unsigned total, unsigned offset,
+                    unsigned count, float* out, void* stream);
+
 /* compute_projection_filter (mjx_planner.py:234-249) + Bernstein evaluation (mjx_planner.py:348):
  *   xi[B][66], state_term[B][30] -> xi_f[B][66]; thetadot[B][6*T] (index dof*T + t) when non-null. */
 int cemk_project(cemk_handle* h, int B, int maxiter_projection, const float* xi, const float* state_term, float* xi_f,

@@ -162,6 +162,67 @@ __global__ void __launch_bounds__(256) k_sample(int B, const float* __restrict__
   }
 }
 
+// ---------------------------------------------------------------------------------------------- jax.random stream
+// Threefry-2x32 (20 rounds) as used by jax.random (jax/_src/prng.py, pinned jax==0.5.3 in the reference's
+// requirements.txt:9); known answers in tests/test_jax_prng.py.
+__device__ __forceinline__ void threefry2x32(uint32_t k0, uint32_t k1, uint32_t& x0, uint32_t& x1) {
+  const uint32_t ks[3] = {k0, k1, k0 ^ k1 ^ 0x1BD11BDAu};
+  x0 += ks[0]; x1 += ks[1];
+#define TF_R(r) { x0 += x1; x1 = (x1 << (r)) | (x1 >> (32 - (r))); x1 ^= x0; }
+#define TF_A TF_R(13) TF_R(15) TF_R(26) TF_R(6)
+#define TF_B TF_R(17) TF_R(29) TF_R(16) TF_R(24)
+  TF_A x0 += ks[1]; x1 += ks[2] + 1u;
+  TF_B x0 += ks[2]; x1 += ks[0] + 2u;
+  TF_A x0 += ks[0]; x1 += ks[1] + 3u;
+  TF_B x0 += ks[1]; x1 += ks[2] + 4u;
+  TF_A x0 += ks[2]; x1 += ks[0] + 5u;
+#undef TF_A
+#undef TF_B
+#undef TF_R
+}
+// XLA's float32 erf_inv (Giles' polynomial, xla/client/lib/math.cc ErfInv32)
+__device__ __forceinline__ float xla_erfinv32(float x) {
+  float w = -log1pf(-x * x);
+  const bool lt = w < 5.f;
+  w = lt ? w - 2.5f : __fsqrt_rn(w) - 3.f;
+  float p = lt ? 2.81022636e-08f : -0.000200214257f;
+  p = __fmaf_rn(p, w, lt ? 3.43273939e-07f : 0.000100950558f);
+  p = __fmaf_rn(p, w, lt ? -3.5233877e-06f : 0.00134934322f);
+  p = __fmaf_rn(p, w, lt ? -4.39150654e-06f : -0.00367342844f);
+  p = __fmaf_rn(p, w, lt ? 0.00021858087f : 0.00573950773f);
+  p = __fmaf_rn(p, w, lt ? -0.00125372503f : -0.0076224613f);
+  p = __fmaf_rn(p, w, lt ? -0.00417768164f : 0.00943887047f);
+  p = __fmaf_rn(p, w, lt ? 0.246640727f : 1.00167406f);
+  p = __fmaf_rn(p, w, lt ? 1.50140941f : 2.83297682f);
+  return fabsf(x) == 1.f ? x * INFINITY : p * x;
+}
+// out[i] = jax.random.normal(key, (total,), float32)[offset + i], i < count.
+//   bits -> uniform in [nextafter(-1, 0), 1): jax/_src/random.py _uniform;  normal = sqrt(2) erfinv(u): _normal_real.
+//   partitionable (jax >= 0.5 default): bits[e] = x0 ^ x1 of threefry(key, (0, e));
+//   original: counters iota(total) padded to even and split in halves, bits = out0 | out1 concatenated.
+__global__ void __launch_bounds__(256) k_jax_normal(uint32_t k0, uint32_t k1, int original, unsigned total, unsigned offset,
+                                                    unsigned count, float* __restrict__ out) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const unsigned e = offset + i;
+  uint32_t bits;
+  if (!original) {
+    uint32_t x0 = 0u, x1 = e;
+    threefry2x32(k0, k1, x0, x1);
+    bits = x0 ^ x1;
+  } else {
+    const unsigned half = (total + 1u) / 2u;
+    const unsigned j = e < half ? e : e - half;
+    uint32_t x0 = j, x1 = half + j < total ? half + j : 0u;
+    threefry2x32(k0, k1, x0, x1);
+    bits = e < half ? x0 : x1;
+  }
+  const float f = __uint_as_float((bits >> 9) | 0x3F800000u) - 1.f;
+  const float lo = -0.99999994f;                                  // nextafter(-1, 0)
+  const float u = fmaxf(lo, __fadd_rn(__fmul_rn(f, __fsub_rn(1.f, lo)), lo));
+  out[i] = 1.41421354f * xla_erfinv32(u);
+}
+
 // ---------------------------------------------------------------------------------------------- projection
 // One thread per (sample, dof).  Q_inv of the reference is block diagonal per DOF, and with
 // A_c = [G_c; -G_c] the slack / residual / multiplier updates of mjx_planner.py:196-223 collapse to
@@ -444,6 +505,15 @@ int cemk_sample(cemk_handle* h, int B, const float* z, const float* mean, const 
   k_chol66<<<1, 256, 0, st>>>(cov, chol_ws);
   k_sample<<<(B + 3) / 4, 256, 0, st>>>(B, z, mean, chol_ws, xi);
   h->launches += 2;
+  CK(cudaPeekAtLastError());
+  return CEMK_OK;
+}
+
+int cemk_jax_normal(cemk_handle* h, unsigned key0, unsigned key1, int original, unsigned total, unsigned offset, unsigned count,
+                    float* out, void* stream) {
+  if (!h || !out || count == 0 || offset > total || count > total - offset) return set_err(CEMK_ERR_ARG, "cemk_jax_normal: bad argument");
+  k_jax_normal<<<(count + 255) / 256, 256, 0, (cudaStream_t)stream>>>(key0, key1, original, total, offset, count, out);
+  h->launches += 1;
   CK(cudaPeekAtLastError());
   return CEMK_OK;
 }

@@ -13,8 +13,10 @@ Reference quirks kept on purpose: elites are taken from t
 samples (:357); the PRNG key never advances across ``compute_cem`` calls (:80,:388) so the same
 standard-normal draws are reused every tick; the covariance restarts at 10*I every call (:386);
 ``theta`` is the post-step joint angle while ``eef_pos`` / ``eef_rot`` / ``collision`` are pre-step.
-``jax.random`` is replaced by a counter-keyed torch generator (JAX's threefry stream cannot be
-reproduced here; parity tests inject samples instead).
+``jax.random`` is restated: ``key`` is raw threefry key data (``PRNGKey(0)`` = two zero words), the
+``split`` chain runs on the host (``jax_prng``) and the normal draws of ``multivariate_normal`` come
+from the device generator ``cemk_jax_normal`` (same counters, bit -> uniform -> erf_inv mapping as
+jax 0.5.3), so identical seeds give the reference's samples up to float32 rounding of the Cholesky.
 
 Multi-GPU (extension): pass ``process_group``; ``num_batch`` is then the global
 batch, each rank rolls out ``num_batch / world`` samples, keeps its local top-k and one NCCL
@@ -28,7 +30,7 @@ import os
 import numpy as np
 import torch
 
-from . import _lib, parallel
+from . import _lib, jax_prng, parallel
 from .bernstein import bernstein_coeff_ordern_new
 from .kmodel import KModel, build_kmodel
 from .mjcf import ModelConsts, exclude_body_pairs, host_kinematics, load_model
@@ -87,7 +89,7 @@ class cem_planner:
 
     def __init__(self, num_dof=None, num_batch=None, num_steps=None, timestep=None, maxiter_cem=None, num_elite=None,
                  w_pos=None, w_rot=None, w_col=None, maxiter_projection=None, *, model_path=None, device=None,
-                 process_group=None, seed=0, contact_exclude=None):
+                 process_group=None, seed=0, contact_exclude=None, threefry_partitionable=True):
         if not torch.cuda.is_available():
             raise RuntimeError("cem_planner needs a CUDA device (B200 / sm_100a); there is no CPU fallback")
         self._lib = _lib.load()
@@ -143,8 +145,10 @@ class cem_planner:
         self.A_eq, self.Q_inv = f32(A_eq), f32(Q_inv)
         self.A_theta, self.A_thetadot, self.A_thetaddot = f32(A_theta), f32(A_thetadot), f32(A_thetaddot)
 
-        self.key = 0                       # counter-based stand-in for jax.random.PRNGKey(0) (:80)
-        self._seed = int(seed)
+        # jax.random.PRNGKey(0) (:80) as raw threefry key data; `seed` is a keyword-only extension.
+        # threefry_partitionable selects the counter layout of jax >= 0.5 (the reference pins jax 0.5.3) or the older one.
+        self.key = jax_prng.PRNGKey(seed)
+        self._partitionable = bool(threefry_partitionable)
         self.v_max = 0.8
         self.a_max = 1.8
         self.p_max = 180 * np.pi / 180
@@ -296,16 +300,18 @@ class cem_planner:
         return b
 
     def _normal(self, key):
-        """Standard normal draws for PRNG counter ``key``: rows [rank*Bl, (rank+1)*Bl) of a [B, nvar]
-        table that depends only on (seed, key), so results do not depend on the number of GPUs."""
-        z = self._z_cache.get(key)
+        """jax.random.normal(key, (num_batch, nvar)) rows [rank*Bl, (rank+1)*Bl): the draws behind
+        jax.random.multivariate_normal (:315), generated on the device by cemk_jax_normal.  A function of
+        (key, global sample index) only, so results do not depend on the number of GPUs."""
+        k = jax_prng.as_key(key)
+        ck = (int(k[0]), int(k[1]))
+        z = self._z_cache.get(ck)
         if z is None:
-            g = torch.Generator(device=self.device)
-            g.manual_seed((self._seed * 1000003 + int(key)) & 0x7FFFFFFFFFFFFFFF)
-            full = torch.randn(self.num_batch, self.nvar, generator=g, device=self.device, dtype=torch.float32)
-            lo = self.rank * self.num_batch_local
-            z = full[lo:lo + self.num_batch_local].contiguous()
-            self._z_cache[key] = z
+            Bl, nv = self.num_batch_local, self.nvar
+            z = torch.empty(Bl, nv, device=self.device, dtype=torch.float32)
+            _lib.check(self._lib.cemk_jax_normal(self._h, ck[0], ck[1], 0 if self._partitionable else 1, self.num_batch * nv,
+                                                 self.rank * Bl * nv, Bl * nv, _ptr(z), self._stream()), self._lib)
+            self._z_cache[ck] = z
         return z
 
     # ------------------------------------------------------------------ per-iteration methods
@@ -318,8 +324,9 @@ class cem_planner:
         return st.reshape(-1, 5, self.num_dof).transpose(1, 2).reshape(-1, self.num_dof * 5)
 
     def compute_xi_samples(self, key, xi_mean, xi_cov):
-        """mjx_planner.py:313-316.  ``key`` is the integer PRNG counter; returns (xi_samples, new key)."""
-        key = int(key) + 1                                   # key, subkey = split(key); sample with key
+        """mjx_planner.py:313-316.  ``key``: raw threefry key data (2 x uint32, what jax.random.key_data
+        gives) or an integer seed; returns (xi_samples, new key)."""
+        key = jax_prng.split(key, 2, self._partitionable)[0]   # key, subkey = split(key); sample with key
         z = self._normal(key)
         B = z.shape[0]
         xi = torch.empty(B, self.nvar, device=self.device)
@@ -471,7 +478,7 @@ class cem_planner:
         state_row = torch.cat([q0, v0, a0, z6, z6])
         state_term = state_row.unsqueeze(0).expand(Bl, 30).contiguous()                    # :374-384
         xi_cov = 10 * torch.eye(nv, device=dev)                                            # :386
-        key = self.key + 1                                                                 # :388
+        key = jax_prng.split(self.key, 2, self._partitionable)[0]                          # :388
         carry = (q0, v0, tp, tr, xi_mean_d, xi_cov, key, state_term)
         thetadot_all = torch.empty(self.maxiter_cem, Bl, nd * T, device=dev)
         theta_all = torch.empty(self.maxiter_cem, Bl, nd * T, device=dev)

@@ -30,9 +30,10 @@ def test_sample(planner):
     A = rng.normal(size=(66, 66))
     cov = (A @ A.T / 66 + np.eye(66)).astype(np.float32)
     mean = rng.normal(size=66).astype(np.float32)
-    xi, key = planner.compute_xi_samples(5, mean, cov)
-    assert key == 6
-    z = planner._normal(6).cpu().numpy().astype(np.float64)
+    from manipulator_mujoco_b200 import jax_prng
+    xi, key = planner.compute_xi_samples(5, mean, cov)                 # integer seed = PRNGKey(5)
+    np.testing.assert_array_equal(key, jax_prng.split(jax_prng.PRNGKey(5))[0])
+    z = planner._normal(key).cpu().numpy().astype(np.float64)
     L = np.linalg.cholesky(cov.astype(np.float64) + 0.003 * np.eye(66))
     np.testing.assert_allclose(xi.cpu().numpy(), mean + z @ L.T, rtol=0, atol=2e-5)
     # same key -> same draws (the reference never advances self.key, mjx_planner.py:388)
@@ -102,9 +103,12 @@ def test_compute_cem_end_to_end_against_oracle_pipeline(oracle64):
     assert tuple(thetadot.shape) == (1, B, 6 * T) and tuple(theta.shape) == (1, B, 6 * T)
     # oracle pipeline with the planner's own z (jax.random cannot be reproduced; samples are injected)
     pr = PlannerRef(6, B, T, 0.05, 0.05, 20.0, 3.0, 80.0, 10)
-    z = pl._normal(pl.key + 2).cpu().numpy().astype(np.float64)
+    from manipulator_mujoco_b200 import jax_prng
+    k1 = jax_prng.split(pl.key)[0]                                     # compute_cem (:388)
+    k2 = jax_prng.split(k1)[0]                                         # compute_xi_samples (:314)
+    z = pl._normal(k2).cpu().numpy().astype(np.float64)
     xi_ref = pr.compute_xi_samples(z, np.zeros(66), 10 * np.eye(66))
-    xi_gpu, _ = pl.compute_xi_samples(pl.key + 1, np.zeros(66), 10 * np.eye(66))      # the draws compute_cem used
+    xi_gpu, _ = pl.compute_xi_samples(k1, np.zeros(66), 10 * np.eye(66))              # the draws compute_cem used
     xi = xi_gpu.cpu().numpy().astype(np.float64)
     np.testing.assert_allclose(xi, xi_ref, atol=5e-5)
     xif = pr.compute_projection_filter(xi, pr.state_term(Q0, np.zeros(6), np.zeros(6), B))

@@ -35,7 +35,7 @@ def main():
         tp = torch.tensor([-0.3, 0.3, 0.4], device=dev)
         tr = torch.tensor([0.0, 0.7071, -0.7071, 0.0], device=dev)
         state_term = torch.cat([q0, z6, z6, z6, z6]).unsqueeze(0).expand(B, 30).contiguous()
-        xi, _ = pl.compute_xi_samples(pl.key + 1, torch.zeros(pl.nvar, device=dev), 10 * torch.eye(pl.nvar, device=dev))
+        xi, _ = pl.compute_xi_samples(pl.key, torch.zeros(pl.nvar, device=dev), 10 * torch.eye(pl.nvar, device=dev))
         _, thetadot = pl._project(xi, state_term, True)
         ref = None
         for w in [int(x) for x in args.cta.split(",")]:
