@@ -100,9 +100,9 @@ int cemk_mean_cov(cemk_handle* h, int k, const float* cost_elite, const float* x
                   void* stream);
 
 /* Options.  "force_rerun" (0/1): recompute every sample with the big-capacity (48 contacts) rollout kernel,
- * used by the tests to check that it agrees bit for bit with the fast kernel.  "cta_warps" (0..16): fixed
- * number of samples per CTA of the rollout kernel for A/B timing (0 = the library's balanced-wave choice);
- * never changes a result. */
+ * used by the tests to check that it agrees bit for bit with the fast kernel.  "cta_samples" (0..28): fixed
+ * number of samples per CTA of the rollout kernel for A/B timing (0 = the library's own choice); never
+ * changes a result. */
 int cemk_set_option(cemk_handle* h, const char* name, int value);
 
 /* Calibration: measured FP32 FMA throughput (TFLOP/s, register operands) of the handle's device; synchronous.

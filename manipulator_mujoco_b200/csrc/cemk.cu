@@ -19,7 +19,8 @@
 #define NVAR 66
 #define NCOEF 11
 #ifndef ROLLOUT_WARPS
-#define ROLLOUT_WARPS 16      // samples (warps) per CTA; they step in lockstep (STEP_ALIGN) to share the instruction cache
+#define ROLLOUT_WARPS 14      // warps per CTA (28 samples with two samples per warp: all the shared memory of an SM); they
+                              // step in lockstep (STEP_ALIGN) to share the instruction cache
 #endif
 #ifndef ROLLOUT_MINB
 #define ROLLOUT_MINB 1
@@ -41,8 +42,9 @@ struct cemk_handle {
   float* d_K;      // Kpp[121] Kpe[55] bounds[3]
   long long launches;
   int* d_flags; int flags_cap; int num_sms;
+  float* d_prevd; int prevd_cap;   // previous-step slot distances of every sample (rollout scratch, stays in L2)
   int force_rerun;               // debug option: recompute every sample with the big-capacity kernel
-  int cta_warps;                 // debug option: fixed number of samples per CTA (0 = balanced waves, see cemk_rollout_cost)
+  int cta_warps;                 // debug option "cta_samples": fixed number of samples per CTA (0 = see cemk_rollout_cost)
 };
 
 // ---------------------------------------------------------------------------------------------- rollout
@@ -54,27 +56,32 @@ struct RolloutBatch {
   const float* thetadot; const float* q0; const float* v0; const float* target_pos; const float* target_rot;
   float w_pos, w_rot, w_col;
   float* theta; float* cost4; float* eef_pos; float* eef_rot; float* collision; float* qacc; int* flags;
+  float* prevd;                  // [B][2 * KM_NPASS][KW] previous-step slot distances (library scratch)
   // CTA -> samples: the first n_hi CTAs run w_hi samples each, the others w_lo (both <= the launch width);
   // warps beyond a CTA's share exit at once
   int n_hi, w_hi, w_lo;
 };
 
-// NC = capacity of the per-sample active-contact list, WARPS = samples per CTA.  The fast
-// instantiation (NC = 16) covers every sample; samples that ever needed more contacts set flag bit 0
-// and are recomputed from scratch by the big instantiation (NC = 48, one warp per CTA, ONLY_FLAGGED).
+// NC = capacity of the per-sample active-contact list, WARPS = warps per CTA; a warp carries 32 / KW samples
+// (one per lane group, warp_dsl.h).  The fast instantiation covers every sample; samples that ever needed
+// more contacts set flag bit 0 and are recomputed from scratch by the big instantiation (NC = 48, one warp
+// per CTA, ONLY_FLAGGED).
+#define GPW (32 / KW)                                     // lane groups (samples) per warp
 template <int NC, int WARPS, bool ONLY_FLAGGED>
 __global__ void __launch_bounds__(WARPS * 32, ROLLOUT_MINB) k_rollout(const KModel* __restrict__ gm, RolloutBatch a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   KModel* sm = reinterpret_cast<KModel*>(smem_raw);
   WarpSmemT<NC>* ws = reinterpret_cast<WarpSmemT<NC>*>(smem_raw + ((sizeof(KModel) + 15) & ~size_t(15)));
-  const int warp = threadIdx.x >> 5;
+  const int group = threadIdx.x / KW;                     // sample slot within the CTA
   const int cta = blockIdx.x;
   const int share = cta < a.n_hi ? a.w_hi : a.w_lo;
   const int base = cta < a.n_hi ? cta * a.w_hi : a.n_hi * a.w_hi + (cta - a.n_hi) * a.w_lo;
   const int nlive = min(share, a.B - base);               // samples this CTA rolls out (<= 0: nothing left)
-  const int s = base + warp;
+  const int s = base + group;
+  bool mine = group < nlive;
   if (ONLY_FLAGGED) {
-    if (s >= a.B || !(a.flags[s] & 1)) return;            // WARPS == 1: the whole CTA leaves together
+    mine = mine && (a.flags[s] & 1);
+    if (!__any_sync(0xffffffffu, mine)) return;           // WARPS == 1: the whole CTA leaves together
   }
   if (nlive <= 0) return;
   {
@@ -83,11 +90,14 @@ __global__ void __launch_bounds__(WARPS * 32, ROLLOUT_MINB) k_rollout(const KMod
     for (int i = threadIdx.x; i < (int)(sizeof(KModel) / 4); i += blockDim.x) dst[i] = src[i];
   }
   __syncthreads();
-  if (warp >= nlive) return;                              // the live warps align on a named barrier of nlive * 32 threads
-  const bool live = true;
+  const unsigned wlive = __ballot_sync(0xffffffffu, mine); // lanes of this warp that own a sample
+  if (!mine) return;                                       // the live warps align on a named barrier (CTA_ALIGN)
   Warp W;
-  W.lane = threadIdx.x & 31;
-  W.nthr = nlive * 32;
+  W.lane = threadIdx.x & (KW - 1);
+  W.shift = (threadIdx.x & 31) & ~(KW - 1);
+  W.mask = KW_FULL << W.shift;
+  W.wmask = wlive;
+  W.nthr = ONLY_FLAGGED ? 32 : ((nlive + GPW - 1) / GPW) * 32;
 #ifdef CEMK_PHASE_TIMING
   W.phase = 14; W.t0 = clock64();
   for (int i = 0; i < 24; ++i) W.ph[i] = 0;
@@ -95,7 +105,7 @@ __global__ void __launch_bounds__(WARPS * 32, ROLLOUT_MINB) k_rollout(const KMod
   RolloutArgs A;
   const size_t row = (size_t)s * KM_NL * a.T;
   A.T = a.T;
-  A.live = live;
+  A.live = true;
   A.thetadot = a.thetadot + row;
   A.q0 = a.q0; A.v0 = a.v0; A.target_pos = a.target_pos; A.target_rot = a.target_rot;
   A.w_pos = a.w_pos; A.w_rot = a.w_rot; A.w_col = a.w_col;
@@ -106,14 +116,17 @@ __global__ void __launch_bounds__(WARPS * 32, ROLLOUT_MINB) k_rollout(const KMod
   A.collision = a.collision ? a.collision + (size_t)s * a.T * sm->nslot_robot : nullptr;
   A.qacc_dbg = a.qacc ? a.qacc + (size_t)s * a.T * KM_NV : nullptr;
   A.flags = a.flags + s;
-  rollout_sample<NC>(W, *sm, ws[warp], A);
+  A.prevd = a.prevd + (size_t)s * (2 * KM_NPASS * KW);
+  rollout_sample<NC>(W, *sm, ws[group], A);
 #ifdef CEMK_PHASE_TIMING
   PHASE(W, 15);
   if (W.lane == 0 && !ONLY_FLAGGED) for (int i = 0; i < 24; ++i) atomicAdd(&g_phase[i], (unsigned long long)W.ph[i]);
 #endif
 }
 template <int NC, int WARPS>
-static size_t rollout_smem() { return ((sizeof(KModel) + 15) & ~size_t(15)) + WARPS * sizeof(WarpSmemT<NC>); }
+static size_t rollout_smem() { return ((sizeof(KModel) + 15) & ~size_t(15)) + WARPS * GPW * sizeof(WarpSmemT<NC>); }
+static_assert(((sizeof(KModel) + 15) & ~size_t(15)) + ROLLOUT_WARPS * GPW * sizeof(WarpSmemT<KM_NC_FAST>) <= 227 * 1024,
+              "rollout scratch exceeds the 227 KB of shared memory a CTA can have");
 
 // ---------------------------------------------------------------------------------------------- sampling
 // L = chol(cov + 0.003 I), lower, row-major [66][66]; one CTA.
@@ -455,7 +468,7 @@ int cemk_create(const void* kmodel, int kmodel_bytes, int device, cemk_handle** 
     return set_err(CEMK_ERR_MODEL, "cemk_create: unsupported topology");
   CK(cudaSetDevice(device));
   cemk_handle* h = new cemk_handle();
-  h->device = device; h->T = 0; h->d_G = nullptr; h->d_K = nullptr; h->launches = 0; h->d_flags = nullptr; h->flags_cap = 0; h->force_rerun = 0; h->cta_warps = 0;
+  h->device = device; h->T = 0; h->d_G = nullptr; h->d_K = nullptr; h->launches = 0; h->d_flags = nullptr; h->flags_cap = 0; h->force_rerun = 0; h->cta_warps = 0; h->d_prevd = nullptr; h->prevd_cap = 0;
   { cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device)); h->num_sms = prop.multiProcessorCount; }
   CK(cudaMalloc(&h->d_model, sizeof(KModel)));
   CK(cudaMemcpy(h->d_model, kmodel, sizeof(KModel), cudaMemcpyHostToDevice));
@@ -472,7 +485,7 @@ int cemk_create(const void* kmodel, int kmodel_bytes, int device, cemk_handle** 
 int cemk_destroy(cemk_handle* h) {
   if (!h) return CEMK_OK;
   cudaSetDevice(h->device);
-  cudaFree(h->d_model); cudaFree(h->d_G); cudaFree(h->d_K); cudaFree(h->d_flags);
+  cudaFree(h->d_model); cudaFree(h->d_G); cudaFree(h->d_K); cudaFree(h->d_flags); cudaFree(h->d_prevd);
   delete h;
   return CEMK_OK;
 }
@@ -547,42 +560,48 @@ int cemk_rollout_cost(cemk_handle* h, int B, int T, const float* thetadot, const
   a.B = B; a.T = T; a.thetadot = thetadot; a.q0 = q0; a.v0 = v0; a.target_pos = target_pos; a.target_rot = target_rot;
   a.w_pos = w_pos; a.w_rot = w_rot; a.w_col = w_col;
   a.theta = theta; a.cost4 = cost4; a.eef_pos = eef_pos; a.eef_rot = eef_rot; a.collision = collision; a.qacc = qacc; a.flags = flags;
-  // Samples per CTA.  One CTA is resident per SM and its warps step in lockstep, so the time of a wave
-  // grows with the warps per SM sub-partition (4 schedulers): shares are multiples of 4 where possible.
-  //  * B <= 4 SMs-worth: 4-warp CTAs of the 4-warp instantiation (more registers, latency-bound regime);
+  if (h->prevd_cap < B) {
+    CK(cudaSetDevice(h->device));
+    if (h->d_prevd) CK(cudaFree(h->d_prevd));
+    CK(cudaMalloc(&h->d_prevd, sizeof(float) * (size_t)B * 2 * KM_NPASS * KW));
+    h->prevd_cap = B;
+  }
+  a.prevd = h->d_prevd;
+  // Samples per CTA (a warp carries GPW = 32 / KW of them).  One CTA is resident per SM and its warps step
+  // in lockstep, so the time of a wave grows with the warps per SM sub-partition (4 schedulers):
+  //  * up to 4 / 8 warps-worth of samples per SM: the 4- / 8-warp instantiations (more registers per
+  //    thread, latency-bound regime, e.g. the closed-loop config B = 1000);
   //  * one wave: every SM gets ceil(B / SMs) samples;
   //  * several waves: the ceil(B / SMs) samples an SM has to run are split into `waves` shares counted in
-  //    quads, e.g. 4096 samples on 148 SMs = 28 per SM = one wave of 16 and one of 12 (a uniform 14 + 14
-  //    would load two of the four schedulers with 4 warps in both waves).
+  //    units of 4 warps where that fits the CTA capacity, otherwise evenly.
   const int nsm = h->num_sms > 0 ? h->num_sms : 148;
+  const int cap = ROLLOUT_WARPS * GPW, unit = 4 * GPW;
   int grid;
 #define CEMK_LAUNCH_ROLLOUT(W_) k_rollout<KM_NC_FAST, W_, false><<<grid, (W_) * 32, rollout_smem<KM_NC_FAST, W_>(), st>>>(h->d_model, a)
+  const int need = (B + nsm - 1) / nsm;                            // samples per SM
   if (h->cta_warps > 0) {
-    const int w = h->cta_warps < ROLLOUT_WARPS ? h->cta_warps : ROLLOUT_WARPS;
+    const int w = h->cta_warps < cap ? h->cta_warps : cap;
     a.n_hi = 0; a.w_hi = a.w_lo = w; grid = (B + w - 1) / w;
     CEMK_LAUNCH_ROLLOUT(ROLLOUT_WARPS);
-  } else if (B <= nsm * 4) {
-    a.n_hi = 0; a.w_hi = a.w_lo = 4; grid = (B + 3) / 4;
-    CEMK_LAUNCH_ROLLOUT(4);
+  } else if (need <= cap) {
+    a.n_hi = 0; a.w_hi = a.w_lo = need; grid = (B + need - 1) / need;
+    if (need <= 4 * GPW) CEMK_LAUNCH_ROLLOUT(4);
+    else if (need <= 8 * GPW) CEMK_LAUNCH_ROLLOUT(8);
+    else CEMK_LAUNCH_ROLLOUT(ROLLOUT_WARPS);
   } else {
-    const int need = (B + nsm - 1) / nsm;                          // samples per SM
-    const int waves = (need + ROLLOUT_WARPS - 1) / ROLLOUT_WARPS;
-    if (waves == 1) {
-      a.n_hi = 0; a.w_hi = a.w_lo = need; grid = (B + need - 1) / need;
-      if (need <= 8) CEMK_LAUNCH_ROLLOUT(8); else CEMK_LAUNCH_ROLLOUT(ROLLOUT_WARPS);
-    } else {
-      const int quads = (need + 3) / 4, q_lo = quads / waves, r = quads % waves;
-      a.w_lo = 4 * q_lo; a.w_hi = 4 * (q_lo + (r ? 1 : 0)); a.n_hi = r * nsm;
-      const int rest = B - a.n_hi * a.w_hi;
-      grid = a.n_hi + (rest > 0 ? (rest + a.w_lo - 1) / a.w_lo : 0);
-      CEMK_LAUNCH_ROLLOUT(ROLLOUT_WARPS);
-    }
+    const int waves = (need + cap - 1) / cap;
+    const int units = (need + unit - 1) / unit, u_lo = units / waves, r = units % waves;
+    a.w_lo = unit * u_lo; a.w_hi = unit * (u_lo + (r ? 1 : 0)); a.n_hi = r * nsm;
+    if (a.w_hi > cap || a.w_lo == 0) { a.n_hi = 0; a.w_hi = a.w_lo = (need + waves - 1) / waves; }
+    const int rest = B - a.n_hi * a.w_hi;
+    grid = a.n_hi + (rest > 0 ? (rest + a.w_lo - 1) / a.w_lo : 0);
+    CEMK_LAUNCH_ROLLOUT(ROLLOUT_WARPS);
   }
 #undef CEMK_LAUNCH_ROLLOUT
   // samples whose active-contact list overflowed the fast capacity are recomputed with the big one
   if (h->force_rerun) CK(cudaMemsetAsync(flags, 1, sizeof(int) * B, st));      // 0x01010101: bit 0 set
-  a.n_hi = 0; a.w_hi = a.w_lo = 1;
-  k_rollout<KM_NC_BIG, 1, true><<<B, 32, rollout_smem<KM_NC_BIG, 1>(), st>>>(h->d_model, a);
+  a.n_hi = 0; a.w_hi = a.w_lo = GPW;
+  k_rollout<KM_NC_BIG, 1, true><<<(B + GPW - 1) / GPW, 32, rollout_smem<KM_NC_BIG, 1>(), st>>>(h->d_model, a);
   h->launches += 2;
   CK(cudaPeekAtLastError());
   return CEMK_OK;
@@ -662,7 +681,7 @@ long long cemk_launch_count(cemk_handle* h) { return h ? h->launches : 0; }
 int cemk_set_option(cemk_handle* h, const char* name, int value) {
   if (!h || !name) return set_err(CEMK_ERR_ARG, "cemk_set_option: null argument");
   if (!strcmp(name, "force_rerun")) { h->force_rerun = value != 0; return CEMK_OK; }
-  if (!strcmp(name, "cta_warps")) { h->cta_warps = value > 0 ? value : 0; return CEMK_OK; }
+  if (!strcmp(name, "cta_samples")) { h->cta_warps = value > 0 ? value : 0; return CEMK_OK; }
   return set_err(CEMK_ERR_ARG, "cemk_set_option: unknown option");
 }
 

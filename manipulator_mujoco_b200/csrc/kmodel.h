@@ -16,8 +16,7 @@
 #define KM_NQ 13
 #define KM_MAXCAP 12
 #define KM_MAXSBOX 8
-#define KM_MAXRPAIR 128  // robot-involving pairs (4 passes of 32 lanes)
-#define KM_NPASS 4
+#define KM_MAXRPAIR 128  // robot-involving pairs (KM_MAXRPAIR / KW collider passes of KW lanes, see warp_dsl.h)
 #define KM_MAXBPAIR 8    // free-box vs static pairs
 
 // robot pair types
@@ -52,7 +51,7 @@ struct KModel {
   float sb_pos[KM_MAXSBOX][4], sb_mat[KM_MAXSBOX][12], sb_size[KM_MAXSBOX][4];
   float fb_size[4], fb_inertia[4];      // free box half sizes; principal inertia (body frame)
   float fb_mass, fb_damping, fb_invw, pad4;
-  // robot pairs, pass-major: entry p*32 + lane
+  // robot pairs, pass-major: entry p*KW + lane
   int rp_type[KM_MAXRPAIR], rp_a[KM_MAXRPAIR], rp_b[KM_MAXRPAIR], rp_slot[KM_MAXRPAIR];
   int bp_type[KM_MAXBPAIR], bp_a[KM_MAXBPAIR];
   float qpos0[16], warm0[12], qvel0[12];   // snapshot every rollout starts from (mjx_planner.py:267)

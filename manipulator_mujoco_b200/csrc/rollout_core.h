@@ -1,4 +1,5 @@
-// rollout_core.h -- one warp rolls one CEM sample through the whole horizon.
+// rollout_core.h -- one lane group (KW = 16 lanes: two samples per warp) rolls one CEM sample through the
+// whole horizon.
 //
 // Replaces, for the planner scene, the reference's `vmap(scan(mjx.step))` + `vmap(compute_cost_single)`
 // (reference sampling_based_planner/mjx_planner.py:251-303): forward kinematics, joint-space
@@ -26,7 +27,8 @@
 #ifndef CEMK_SYNC_EVERY
 #define CEMK_SYNC_EVERY 1                   // env-steps between two CTA-wide re-alignments (STEP_ALIGN)
 #endif
-#define KM_NC_FAST 24                     // active-contact capacity of the fast kernel
+#define KM_NC_FAST (KW == 16 ? 20 : 24)   // active-contact capacity of the fast kernel (shared-memory budget per sample)
+#define KM_NPASS (KM_MAXRPAIR / KW)         // collider passes over the robot pair table
 #define KM_NC_BIG 48                      // capacity of the re-run kernel for samples that overflowed
 #define MJ_MINVAL 1e-15f
 #define MJ_MINIMP 0.0001f
@@ -36,32 +38,34 @@ struct LaneRegs {
   float cost_c;               // this lane's share of cost_c
   int nact, off;              // active contacts this lane will emit, and where
   int actmask;                // bit (2*pass + slot)
-  int tri;                    // (i, j) of the 6x6 lower-triangle entry this lane owns, 4 bits each (lanes 0-20)
+  int tri;                    // (i, j), 4 bits each, of the 6x6 lower-triangle entries lane and lane + KW (8 bits per entry; 0xff = none)
   float td;                   // next step's commanded joint velocity (lanes < 6), prefetched one step ahead
   float acc[9];               // line-search partial sums (compile-time indices only)
   float h[KM_NV];             // row `lane` of the Newton Hessian / its Cholesky factor
   float f0, f1, f2;
 };
 
-// Per-warp scratch in shared memory.  Two unions reuse space between phases that never overlap:
-// the spatial-dynamics arrays (P2-P5) vs the constraint rows (C1-S5), and the free-box contact
-// staging (N1-N2) vs the contact Jacobians (C2-S5).
+// Per-sample scratch in shared memory.  Unions reuse space between phases that never overlap: the
+// spatial-dynamics arrays (P2-P5) vs the constraint rows (C1-S5), the capsule end points (P2-N2) vs the
+// Newton Hessian (S3-S4), and the free-box contact staging (N1-N2) vs the contact Jacobians (C2-S5).
+// With KW = 16 a CTA of 14 warps holds 28 of these next to the model table (227 KB per SM).
 template <int NC>
 struct WarpSmemT {
   static constexpr int NROW = KM_NL + 4 * NC;
   float qpos[16], qvel[12], warm[12];
   float lpos[KM_NL][4], lquat[KM_NL][4], lmat[KM_NL][12];
   float cdof[KM_NL][8];
-  float capA[KM_MAXCAP][4], capB[KM_MAXCAP][4];
   float bmat[12];
   float Mr[KM_NL][KM_NL];             // robot block of the joint-space inertia (box block is constant, diagonal)
-  float H[KM_NV][KM_NV];
-  float fs[12], as[12], qacc[12], Ma[12], grad[12], search[12], mv[12];
+  union {
+    struct { float capA[KM_MAXCAP][4], capB[KM_MAXCAP][4]; };
+    float H[KM_NV][KM_NV];
+  };
+  float fs[12], as[12], qacc[12], Ma[12], grad[12], search[12];
   int ncon, nrow, nlim, flags;
-  float prevd[KM_NPASS * 2][32];      // previous-step distance of every lane's robot slots
   union {
     struct { float cinert[KM_NL][12], crb[KM_NL][12], cvel[KM_NL][8], cdofdot[KM_NL][8], cfrc[KM_NL][8]; };
-    struct { float rD[NROW], rAref[NROW], rJaref[NROW], rJv[NROW], rJs[NROW]; };
+    struct { float rD[NROW], rAref[NROW], rJaref[NROW], rJv[NROW]; };   // rJv doubles as the smooth-start J.a - aref in S1
   };
   float cgeo[NC][16];                 // pos3 n3 t1 3 t2 3 dist invw link1 link2
   union {
@@ -71,7 +75,7 @@ struct WarpSmemT {
       float bbR[12], bbc[4], bbsz[2][4], bbrf[4][4], bben[4][4], bbpoly[2][8][4], bbpref[8][4];
     };
   };
-  float cd[2][NC][4];                 // per contact: Jn.v, mu*Jt1.v, mu*Jt2.v for up to two vectors v
+  float cd[2][NC][3];                 // per contact: Jn.v, mu*Jt1.v, mu*Jt2.v for up to two vectors v
   int limdof[KM_NL];
   float limsign[KM_NL];
 };
@@ -719,7 +723,7 @@ template <int NC>
 KFN void contact_dots(Warp& W, WarpSmemT<NC>& S, int ncon, const float* v0, const float* v1) {
   LANES(W, R)
 #pragma unroll 1
-    for (int e = lane; e < 3 * ncon; e += 32) {
+    for (int e = lane; e < 3 * ncon; e += KW) {
       const int c = e / 3, k = e - 3 * c;
       const float* J = S.cJ[c] + 12 * k;
       float s0 = 0.f, s1 = 0.f;
@@ -828,7 +832,7 @@ KNOINLINE void emit_robot_contacts(const KModel& m, WarpSmemT<NC>& S, int lane, 
   for (int p = 0; p < KM_NPASS; ++p) {
     const int bits = (actmask >> (2 * p)) & 3;
     if (!bits) continue;
-    const int e = p * 32 + lane, ty = m.rp_type[e], a = m.rp_a[e], b = m.rp_b[e];
+    const int e = p * KW + lane, ty = m.rp_type[e], a = m.rp_a[e], b = m.rp_b[e];
     Contact2 c;
     float invw; int l1, l2;
     float pt1[3]; bool own_t1 = false;
@@ -871,6 +875,7 @@ KNOINLINE void emit_robot_contacts(const KModel& m, WarpSmemT<NC>& S, int lane, 
 struct StepIO {
   bool first;                 // t == 0: no previous distance yet
   float* collision_row;       // optional dump of this step's robot-slot distances [nslot_robot]
+  float* prevd;               // this sample's previous-step distances, [2 * KM_NPASS][KW] (global scratch, L2-resident)
 };
 
 // ------------------------------------------------------------------------------------------ one forward()
@@ -887,6 +892,11 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
       k_sincos(0.5f * S.qpos[lane], &sn, &cs);
       qj[0] = cs; qj[1] = sn * m.l_axis[lane][0]; qj[2] = sn * m.l_axis[lane][1]; qj[3] = sn * m.l_axis[lane][2];
       quat_mul(S.lquat[lane], m.l_quat[lane], qj);
+    } else if (lane == 8 && m.has_box) {
+      float* q = S.qpos + KM_NL + 3;
+      float inv = 1.f / sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+      q[0] *= inv; q[1] *= inv; q[2] *= inv; q[3] *= inv;
+      quat_to_mat(S.bmat, q);
     }
   END_LANES
   {
@@ -913,8 +923,10 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
   PHASE(W, 2);
   // ---- P2: per-link spatial quantities, capsule end points, box frame ----
   LANES(W, R)
-    if (lane < KM_NL) {
-      const int i = lane;
+#pragma unroll 1
+   for (int it = lane; it < KM_NL + m.ncap; it += KW) {
+    if (it < KM_NL) {
+      const int i = it;
       float a[3], off[3], com[3], d[3], t[3];
       mat_vec(a, S.lmat[i], m.l_axis[i]);
       sub3(off, m.refpt, S.lpos[i]);
@@ -944,33 +956,27 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
       ci[4] = T02 - ms * d[0] * d[2];
       ci[5] = T12 - ms * d[1] * d[2];
       ci[6] = ms * d[0]; ci[7] = ms * d[1]; ci[8] = ms * d[2]; ci[9] = ms;
-    } else if (lane >= 8 && lane < 8 + m.ncap) {
-      const int j = lane - 8, L = m.cap_link[j];
+    } else {
+      const int j = it - KM_NL, L = m.cap_link[j];
       float cpos[3], ax[3], t[3];
       mat_vec(t, S.lmat[L], m.cap_pos[j]); add3(cpos, S.lpos[L], t);
       mat_vec(ax, S.lmat[L], m.cap_axis[j]);
       madd3(S.capA[j], cpos, ax, -m.cap_hl[j]);
       madd3(S.capB[j], cpos, ax, m.cap_hl[j]);
-    } else if (lane == 24 && m.has_box) {
-      float* q = S.qpos + KM_NL + 3;
-      float inv = 1.f / sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-      q[0] *= inv; q[1] *= inv; q[2] *= inv; q[3] *= inv;
-      quat_to_mat(S.bmat, q);
     }
+   }
   END_LANES
   // ---- P3: composite inertias and link velocities, one (link, component) item per lane (BD.3, BD.4) ----
   LANES(W, R)
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int e = lane + 32 * q;
+#pragma unroll 1
+    for (int e = lane; e < KM_NL * 16; e += KW) {
       if (e < KM_NL * 10) {
         const int i = e / 10, k = e - 10 * i;
         float s = 0.f;
         for (int b = i; b < KM_NL; ++b) s += S.cinert[b][k];
         S.crb[i][k] = s;
-      }
-      if (e < KM_NL * 6) {
-        const int i = e / 6, k = e - 6 * i;
+      } else {
+        const int e2 = e - KM_NL * 10, i = e2 / 6, k = e2 - 6 * i;
         float v = 0.f;
         for (int b = 0; b <= i; ++b) v += S.cdof[b][k] * S.qvel[b];
         S.cvel[i][k] = v;
@@ -979,15 +985,19 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
   END_LANES
   // ---- P4: robot inertia matrix entries (lanes 0-20), cdof_dot (lanes 24-29) ----
   LANES(W, R)
-    if (lane < 21) {
-      const int i = R.tri & 15, j = (R.tri >> 4) & 15;
-      float buf[6];
-      mul_inert(buf, S.crb[i], S.cdof[i]);
-      float v = dot6(S.cdof[j], buf);
-      if (i == j) v += m.l_armature[i];
-      S.Mr[i][j] = v; S.Mr[j][i] = v;
-    } else if (lane >= 24 && lane < 24 + KM_NL) {
-      const int i = lane - 24;
+#pragma unroll
+    for (int q = 0; q < 32 / KW; ++q) {
+      const int i = (R.tri >> (8 * q)) & 15, j = (R.tri >> (8 * q + 4)) & 15;
+      if (i < KM_NL) {
+        float buf[6];
+        mul_inert(buf, S.crb[i], S.cdof[i]);
+        float v = dot6(S.cdof[j], buf);
+        if (i == j) v += m.l_armature[i];
+        S.Mr[i][j] = v; S.Mr[j][i] = v;
+      }
+    }
+    if (lane >= KW - KM_NL) {                  // the last six lanes (idle in the second pass above)
+      const int i = lane - (KW - KM_NL);
       if (i == 0) { for (int k = 0; k < 6; ++k) S.cdofdot[0][k] = 0.f; }
       else cross_motion(S.cdofdot[i], S.cvel[i - 1], S.cdof[i]);
     }
@@ -1037,10 +1047,16 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
   LANES(W, R)
     int nact = 0, actmask = 0;
     float cc = 0.f;
+    // previous distances of this lane's two slots, fetched one pass ahead so the L2 latency hides behind the collider
+    float* pd = io.prevd + lane;
+    float pv0 = 0.f, pv1 = 0.f;
+    if (!io.first) { pv0 = pd[0]; pv1 = pd[KW]; }
 #pragma unroll 1
     for (int p = 0; p < KM_NPASS; ++p) {
-      const int e = p * 32 + lane;
+      const int e = p * KW + lane;
       const int ty = m.rp_type[e];
+      const float prev0 = pv0, prev1 = pv1;
+      if (!io.first && p + 1 < KM_NPASS) { pv0 = pd[(2 * p + 2) * KW]; pv1 = pd[(2 * p + 3) * KW]; }
       if (ty == KP_NONE) continue;
       const int a = m.rp_a[e], b = m.rp_b[e];
       float d0, d1 = 1.f;
@@ -1061,12 +1077,12 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
       const int ns = ty == KP_CAP_CAP ? 1 : 2;
       // cost_c (mjx_planner.py:287-296): sum max(0, (1-y) c_t - c_{t+1}) + #(c < 0), y = 0.005
       if (d0 < 0.f) { ++nact; actmask |= 1 << (2 * p); cc += 1.f; }
-      if (!io.first) cc += fmaxf((1.f - 0.005f) * S.prevd[2 * p][lane] - d0, 0.f);
-      S.prevd[2 * p][lane] = d0;
+      if (!io.first) cc += fmaxf((1.f - 0.005f) * prev0 - d0, 0.f);
+      pd[(2 * p) * KW] = d0;
       if (ns == 2) {
         if (d1 < 0.f) { ++nact; actmask |= 1 << (2 * p + 1); cc += 1.f; }
-        if (!io.first) cc += fmaxf((1.f - 0.005f) * S.prevd[2 * p + 1][lane] - d1, 0.f);
-        S.prevd[2 * p + 1][lane] = d1;
+        if (!io.first) cc += fmaxf((1.f - 0.005f) * prev1 - d1, 0.f);
+        pd[(2 * p + 1) * KW] = d1;
       }
       if (io.collision_row) {
         io.collision_row[m.rp_slot[e]] = d0;
@@ -1084,7 +1100,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
   if (m.has_box) {
     const float* bp = S.qpos + KM_NL;
     LANES(W, R)
-      if (lane < 4 * m.nbpair) S.bstage[lane >> 2][lane & 3][3] = 1.f;
+      for (int sl = lane; sl < 4 * m.nbpair; sl += KW) S.bstage[sl >> 2][sl & 3][3] = 1.f;
     END_LANES
     const unsigned cand = warp_ballot(W, [&](int q, LaneRegs&) {
       if (q >= m.nbpair) return false;
@@ -1121,19 +1137,20 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
   END_LANES
   // list positions: robot contacts first (lane-major), then the staged free-box contacts (pair-major)
   const int nrob = warp_excl_scan(W, [](int, LaneRegs& R) { return R.nact; }, [](int, LaneRegs& R, int o) { R.off = o; });
-  const unsigned bmask = m.has_box ? warp_ballot(W, [&](int l, LaneRegs&) { return l < 4 * m.nbpair && S.bstage[l >> 2][l & 3][3] < 0.f; }) : 0u;
+  const unsigned bmask = m.has_box ? warp_ballot32(W, [&](int l) { return l < 4 * m.nbpair && S.bstage[l >> 2][l & 3][3] < 0.f; }) : 0u;
   const int ncon_all = nrob + KPOPC(bmask);
   const int ncon = ncon_all < NC ? ncon_all : NC;
   PHASE(W, 6);
   // ---- N2: full contact records for the active slots (divergent, rare for robot slots) ----
   LANES(W, R)
     if (R.nact > 0) emit_robot_contacts<NC>(m, S, lane, R.actmask, R.off);
-    if (bmask & (1u << lane)) {
-      const int o = nrob + KPOPC(bmask & ((1u << lane) - 1u)), q = lane >> 2;
+    for (int sl = lane; sl < 32; sl += KW) {
+      if (!(bmask & (1u << sl))) continue;
+      const int o = nrob + KPOPC(bmask & ((1u << sl) - 1u)), q = sl >> 2;
       if (o < NC) {
         const bool sw = m.bp_type[q] == KB_BOX_BOX_SWAP;
         float* g = S.cgeo[o];
-        const float* st = S.bstage[q][lane & 3];
+        const float* st = S.bstage[q][sl & 3];
         copy3(g, st); copy3(g + 3, S.bnrm[q]);
         make_tangents(S.bnrm[q], g + 6, g + 9);
         g[12] = st[3]; g[13] = m.fb_invw; g[14] = sw ? (float)KM_NL : -1.f; g[15] = sw ? -1.f : (float)KM_NL;
@@ -1177,7 +1194,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
     const int d = lane & 15;
     if (d < KM_NV) {
 #pragma unroll 1
-      for (int c = lane >> 4; c < ncon; c += 2) {
+      for (int c = lane >> 4; c < ncon; c += KW / 16) {
         const float* g = S.cgeo[c];
         float c1[3], c2[3], df[3];
         jac_col(m, S, g, (int)g[14], d, c1);
@@ -1194,7 +1211,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
   contact_dots<NC>(W, S, ncon, S.qvel, nullptr);
   LANES(W, R)
 #pragma unroll 1
-    for (int r = nlim + lane; r < nrow; r += 32) {
+    for (int r = nlim + lane; r < nrow; r += KW) {
       const float* g = S.cgeo[(r - nlim) >> 2];
       float w = g[13];
       w = w + m.mu * m.mu * w;
@@ -1205,7 +1222,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
     }
     // does any active contact join a robot link and the free box?  (then H is a full 12x12)
     R.f2 = 0.f;
-    for (int c = lane; c < ncon; c += 32) {
+    for (int c = lane; c < ncon; c += KW) {
       const int l1 = (int)S.cgeo[c][14], l2 = (int)S.cgeo[c][15];
       if ((l1 == KM_NL && l2 >= 0 && l2 < KM_NL) || (l2 == KM_NL && l1 >= 0 && l1 < KM_NL)) R.f2 = 1.f;
     }
@@ -1217,9 +1234,9 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
   LANES(W, R)
     float cw = 0.f, cs = 0.f;
 #pragma unroll 1
-    for (int r = lane; r < nrow; r += 32) {
+    for (int r = lane; r < nrow; r += KW) {
       float jw = row_val<NC>(S, 0, r, S.warm) - S.rAref[r], js = row_val<NC>(S, 1, r, S.as) - S.rAref[r];
-      S.rJaref[r] = jw; S.rJs[r] = js;
+      S.rJaref[r] = jw; S.rJv[r] = js;
       if (jw < 0.f) cw += 0.5f * S.rD[r] * jw * jw;
       if (js < 0.f) cs += 0.5f * S.rD[r] * js * js;
     }
@@ -1240,7 +1257,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
   const float gauss = use_warm ? gauss_w : 0.f;
   LANES(W, R)
     if (!use_warm) {
-      for (int r = lane; r < nrow; r += 32) S.rJaref[r] = S.rJs[r];
+      for (int r = lane; r < nrow; r += KW) S.rJaref[r] = S.rJv[r];
       if (lane < KM_NV) {
         S.Ma[lane] = mul_M<NC>(m, S, lane, S.as);
       }
@@ -1253,7 +1270,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
   // Jn, mu*Jt1, mu*Jt2; the contact position / frame slots of cgeo are dead after C2 and are reused.
   LANES(W, R)
 #pragma unroll 1
-    for (int c = lane; c < ncon; c += 32) {
+    for (int c = lane; c < ncon; c += KW) {
       const int r0 = nlim + 4 * c;
       float w[4], f[4];
 #pragma unroll
@@ -1267,8 +1284,8 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
   END_LANES
   // which contacts touch the robot block / the box block (ncon <= 32: one bit per contact); the loops
   // below then visit only the contacts that can contribute (typically: 4 box contacts, no robot contact)
-  const unsigned mrob = warp_ballot(W, [&](int l, LaneRegs&) { return l < ncon && (__float_as_int(S.cgeo[l][7]) & 1); });
-  const unsigned mbox = warp_ballot(W, [&](int l, LaneRegs&) { return l < ncon && (__float_as_int(S.cgeo[l][7]) & 2); });
+  const unsigned mrob = warp_ballot32(W, [&](int l) { return l < ncon && (__float_as_int(S.cgeo[l][7]) & 1); });
+  const unsigned mbox = warp_ballot32(W, [&](int l) { return l < ncon && (__float_as_int(S.cgeo[l][7]) & 2); });
   LANES(W, R)
     if (lane < KM_NV) {
       float fc = 0.f;
@@ -1293,8 +1310,10 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
   // block and for the box block; the 36 robot/box cross entries exist only when a contact couples the two
   // (otherwise the blocks are solved separately and the cross entries are never read).
   LANES(W, R)
-    if (lane < 21) {
-      const int i = R.tri & 15, j = (R.tri >> 4) & 15;
+#pragma unroll
+   for (int q = 0; q < 32 / KW; ++q) {
+    const int i = (R.tri >> (8 * q)) & 15, j = (R.tri >> (8 * q + 4)) & 15;
+    if (i < KM_NL) {
       float hr = S.Mr[i][j];
       for (int r = 0; r < nlim; ++r) if (S.rJaref[r] < 0.f && S.limdof[r] == i && i == j) hr += S.rD[r];
       hr += hess_contacts<NC>(S, mrob, ncon, i, j);
@@ -1303,9 +1322,10 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
       hb += hess_contacts<NC>(S, mbox, ncon, KM_NL + i, KM_NL + j);
       S.H[KM_NL + i][KM_NL + j] = hb;
     }
+   }
     if (coupled) {
 #pragma unroll 1
-      for (int e = lane; e < KM_NL * KM_NL; e += 32) {
+      for (int e = lane; e < KM_NL * KM_NL; e += KW) {
         const int i = KM_NL + e / KM_NL, j = e % KM_NL;
         S.H[i][j] = hess_contacts<NC>(S, mrob & mbox, ncon, i, j);
       }
@@ -1345,7 +1365,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
       e0 = s * s; e1 = s * S.Ma[lane] - s * S.fs[lane]; e2 = 0.5f * s * mv;
     }
 #pragma unroll 1
-    for (int r = lane; r < nrow; r += 32) {
+    for (int r = lane; r < nrow; r += KW) {
       const float jv = row_val<NC>(S, 0, r, S.search), ja = S.rJaref[r], D = S.rD[r];
       S.rJv[r] = jv;
       if (ja < 0.f) { a0 += 0.5f * D * ja * ja; a1 += D * jv * ja; a2 += 0.5f * D * jv * jv; }
@@ -1381,7 +1401,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
     LANES(W, R)
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
 #pragma unroll 1
-      for (int r = lane; r < nrow; r += 32) {
+      for (int r = lane; r < nrow; r += KW) {
         const float ja = S.rJaref[r], jv = S.rJv[r], D = S.rD[r];
         const float q0 = 0.5f * D * ja * ja, q1 = D * jv * ja, q2 = 0.5f * D * jv * jv;
         if (ja + al0 * jv < 0.f) { a0 += q0; a1 += q1; a2 += q2; }
@@ -1469,6 +1489,7 @@ struct RolloutArgs {
   float* eef_pos; float* eef_rot; float* collision;     // optional per-step dumps [T][3], [T][4], [T][nslot]
   float* qacc_dbg;            // optional [T][12]
   int* flags;
+  float* prevd;               // scratch [2 * KM_NPASS][KW] of this sample (StepIO::prevd)
 };
 
 template <int NC>
@@ -1477,10 +1498,14 @@ KFN void rollout_sample(Warp& W, const KModel& m, WarpSmemT<NC>& S, const Rollou
     if (lane < KM_NQ) S.qpos[lane] = lane < KM_NL ? A.q0[lane] : m.qpos0[lane];
     if (lane < KM_NV) { S.qvel[lane] = lane < KM_NL ? A.v0[lane] : m.qvel0[lane]; S.warm[lane] = m.warm0[lane]; }
     {
-      // the entry (i, j), j <= i, of a 6x6 lower triangle this lane owns (lanes 0-20)
-      int i = 0, j = lane;
-      if (lane < KM_NL * (KM_NL + 1) / 2) { while (j > i) { j -= i + 1; ++i; } } else { i = 15; j = 15; }
-      R.tri = i | (j << 4);
+      // the entries (i, j), j <= i, of a 6x6 lower triangle this lane owns: e = lane (and lane + 16 when KW = 16)
+      int tri = 0;
+      for (int q = 0; q < 32 / KW; ++q) {
+        int e = lane + KW * q, i = 0, j = e;
+        if (e < KM_NL * (KM_NL + 1) / 2) { while (j > i) { j -= i + 1; ++i; } } else { i = 15; j = 15; }
+        tri |= (i | (j << 4)) << (8 * q);
+      }
+      R.tri = tri;
     }
     if (lane == 0) S.flags = 0;
     R.cost_c = 0.f;
@@ -1506,6 +1531,7 @@ KFN void rollout_sample(Warp& W, const KModel& m, WarpSmemT<NC>& S, const Rollou
     StepIO io;
     io.first = t == 0;
     io.collision_row = (A.collision && A.live) ? A.collision + (size_t)t * m.nslot_robot : nullptr;
+    io.prevd = A.prevd;
     step_forward<NC>(W, m, S, io);
     PHASE(W, 12);
     // pre-step observations (mjx_planner.py:259-261) and running cost (:277-285)

@@ -1,20 +1,34 @@
-// warp_dsl.h -- a tiny "one warp = one sample" programming layer.
+// warp_dsl.h -- a tiny "one lane group = one sample" programming layer.
 //
-// The rollout core (rollout_core.h) is written once against these macros and compiled twice:
-//   * by nvcc for sm_100a, where a LANES block is the body executed by each of the 32 lanes of the
-//     warp that owns the sample, per-lane state lives in registers, collectives are warp shuffles
-//     and every block is fenced by __syncwarp();
+// A sample is owned by a group of KW lanes: KW = 16 (default, two samples per warp) or 32 (one sample
+// per warp, -DCEMK_KW=32).  The rollout core (rollout_core.h) is written once against these macros and
+// compiled twice:
+//   * by nvcc for sm_100a, where a LANES block is the body executed by each of the KW lanes of the
+//     group, per-lane state lives in registers, collectives are shuffles / ballots restricted to the
+//     group (member mask = the group's lanes, width = KW) and every block is fenced by
+//     __syncwarp(group mask).  With KW = 16 the two halves of a warp run the same instruction stream on
+//     two samples: "uniform" scalar code (small dense solves, the serial joint chain, line-search control)
+//     is issued once for both, and phases that only have 6..16 work items fill the warp twice as well.
+//     Control flow that depends on the sample (line-search trip counts, contact cases) may diverge
+//     between the halves; nothing in the core synchronises across groups except CTA_ALIGN;
 //   * by g++ with -DCEMK_EMU (tests/emu, no-GPU unit tests only), where a LANES block is a plain
-//     `for (lane = 0..31)` loop over an array of per-lane register structs.  This is a debugging
+//     `for (lane = 0..KW-1)` loop over an array of per-lane register structs.  This is a debugging
 //     aid for kernel logic in a container without a GPU; it is never used by the product path.
 //
 // Rules the core follows so both builds mean the same thing:
 //   1. inside one LANES block a lane reads only shared scratch written in *earlier* blocks (or by
 //      itself) and writes only locations no other lane touches in that block;
-//   2. code outside LANES blocks is warp-uniform (every lane computes the same scalars); shared
-//      scratch is written there only through UNIFORM_WRITE, which is fenced on both sides.
+//   2. code outside LANES blocks is group-uniform (every lane of the group computes the same scalars);
+//      shared scratch is written there only through UNIFORM_WRITE, which is fenced on both sides.
 #pragma once
 #include <math.h>
+
+#ifndef CEMK_KW
+#define CEMK_KW 16
+#endif
+#define KW CEMK_KW
+static_assert(KW == 16 || KW == 32, "CEMK_KW must be 16 or 32");
+#define KW_FULL (KW == 32 ? 0xffffffffu : 0xffffu)
 
 #ifdef CEMK_EMU
 #include <cstring>
@@ -22,7 +36,7 @@
 #define KNOINLINE static
 #define STEP_ALIGN()
 #define PHASE_ALIGN(bit)
-#define LANES(W, R) for (int lane = 0; lane < 32; ++lane) { auto& R = (W).regs[lane]; (void)R;
+#define LANES(W, R) for (int lane = 0; lane < KW; ++lane) { auto& R = (W).regs[lane]; (void)R;
 #define END_LANES }
 #define RLANES(W, R) LANES(W, R)
 #define END_RLANES }
@@ -37,29 +51,30 @@ static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); retur
 #else
 #define KFN __device__ __forceinline__
 #define KNOINLINE __device__ __noinline__
+// Keep the live warps of a CTA on the same code (instruction-cache locality): named barrier 1 with the
+// live thread count of this CTA (a CTA may run fewer samples than its launch width, see
+// cemk_rollout_cost).  The two groups of a warp re-converge first (bar.sync is a per-warp instruction).
+#define CTA_ALIGN(W) do { __syncwarp((W).wmask); asm volatile("bar.sync 1, %0;" :: "r"((W).nthr) : "memory"); } while (0)
 #ifdef CEMK_STEP_SYNC
-// keep the live warps of a CTA on the same code (instruction-cache locality).  Named barrier 1 with the
-// live thread count of this CTA (a CTA may run fewer samples than its launch width, see cemk_rollout_cost).
-#define CTA_ALIGN(W) asm volatile("bar.sync 1, %0;" :: "r"((W).nthr) : "memory")
 #define STEP_ALIGN() CTA_ALIGN(W)
 #else
 #define STEP_ALIGN()
 #endif
 // optional extra CTA-wide re-alignments inside a step, selected by the bits of CEMK_PHASE_SYNC
-// (only at points every warp reaches)
+// (only at points every group reaches)
 #if defined(CEMK_STEP_SYNC) && defined(CEMK_PHASE_SYNC)
 #define PHASE_ALIGN(bit) do { if ((CEMK_PHASE_SYNC) & (bit)) CTA_ALIGN(W); } while (0)
 #else
 #define PHASE_ALIGN(bit)
 #endif
-#define LANES(W, R) { __syncwarp(); const int lane = (W).lane; auto& R = (W).regs; (void)R;
-#define END_LANES } __syncwarp();
+#define LANES(W, R) { __syncwarp((W).mask); const int lane = (W).lane; auto& R = (W).regs; (void)R;
+#define END_LANES } __syncwarp((W).mask);
 // register-only lane block: touches no shared scratch, so no fences
 #define RLANES(W, R) { const int lane = (W).lane; auto& R = (W).regs; (void)R; (void)lane;
 #define END_RLANES }
-#define UNIFORM_WRITE(W) __syncwarp(); if ((W).lane == 0)
-#define END_UNIFORM_WRITE __syncwarp();
-#define USYNC() __syncwarp()
+#define UNIFORM_WRITE(W) __syncwarp((W).mask); if ((W).lane == 0)
+#define END_UNIFORM_WRITE __syncwarp((W).mask);
+#define USYNC() __syncwarp((W).mask)
 #define KRSQRT(x) rsqrtf(x)
 #define KPOPC(x) __popc(x)
 #define KFFS(x) __ffs((int)(x))
@@ -68,10 +83,13 @@ static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); retur
 template <class LR>
 struct WarpCtx {
 #ifdef CEMK_EMU
-  LR regs[32];
+  LR regs[KW];
 #else
   LR regs;
-  int lane;
+  int lane;          // lane within the group, 0..KW-1
+  int shift;         // first lane of the group within the warp (0 or 16)
+  unsigned mask;     // member mask of the group
+  unsigned wmask;    // lanes of this warp that own a sample (both groups, or this one if the other is idle)
   int nthr;          // live threads of this CTA (barrier width)
 #ifdef CEMK_PHASE_TIMING
   long long t0; int phase; long long ph[24];
@@ -79,7 +97,7 @@ struct WarpCtx {
 #endif
 };
 
-// Debug build only (-DCEMK_PHASE_TIMING): per-phase SM-clock accounting of one warp's step, summed
+// Debug build only (-DCEMK_PHASE_TIMING): per-phase SM-clock accounting of one group's step, summed
 // into a global table by the kernel wrapper (tools/phase_timing.py).  No-op otherwise.
 #if !defined(CEMK_EMU) && defined(CEMK_PHASE_TIMING)
 #define PHASE(W, id) do { long long now_ = clock64(); (W).ph[(W).phase] += now_ - (W).t0; (W).t0 = now_; (W).phase = (id); } while (0)
@@ -87,62 +105,62 @@ struct WarpCtx {
 #define PHASE(W, id) do { } while (0)
 #endif
 
-// sum over lanes of f(lane, regs); result is warp-uniform
+// sum over the group's lanes of f(lane, regs); result is group-uniform
 template <class W, class F>
 KFN float warp_sum(W& w, F f) {
 #ifdef CEMK_EMU
   float s = 0.f;
-  for (int l = 0; l < 32; ++l) s += f(l, w.regs[l]);
+  for (int l = 0; l < KW; ++l) s += f(l, w.regs[l]);
   return s;
 #else
   float v = f(w.lane, w.regs);
 #pragma unroll
-  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  for (int o = KW / 2; o; o >>= 1) v += __shfl_xor_sync(w.mask, v, o, KW);
   return v;
 #endif
 }
 
 // exclusive prefix sum of small non-negative ints; set(lane, regs, offset) receives each lane's
-// offset; returns the warp total
+// offset; returns the group total
 template <class W, class G, class S>
 KFN int warp_excl_scan(W& w, G get, S set) {
 #ifdef CEMK_EMU
   int run = 0;
-  for (int l = 0; l < 32; ++l) { int v = get(l, w.regs[l]); set(l, w.regs[l], run); run += v; }
+  for (int l = 0; l < KW; ++l) { int v = get(l, w.regs[l]); set(l, w.regs[l], run); run += v; }
   return run;
 #else
   int v = get(w.lane, w.regs), inc = v;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (w.lane >= o) inc += t; }
+  for (int o = 1; o < KW; o <<= 1) { int t = __shfl_up_sync(w.mask, inc, o, KW); if (w.lane >= o) inc += t; }
   set(w.lane, w.regs, inc - v);
-  return __shfl_sync(0xffffffffu, inc, 31);
+  return __shfl_sync(w.mask, inc, KW - 1, KW);
 #endif
 }
 
-// value of f(src, regs[src]) broadcast to every lane
+// value of f(src, regs[src]) broadcast to every lane of the group
 template <class W, class F>
 KFN float warp_bcast(W& w, int src, F f) {
 #ifdef CEMK_EMU
   return f(src, w.regs[src]);
 #else
-  return __shfl_sync(0xffffffffu, f(w.lane, w.regs), src);
+  return __shfl_sync(w.mask, f(w.lane, w.regs), src, KW);
 #endif
 }
 
-// lane index of the maximum of f(lane, regs) over all lanes; ties -> lowest lane ("first max");
+// lane index of the maximum of f(lane, regs) over the group; ties -> lowest lane ("first max");
 // lanes whose value is NaN never win against a number
 template <class W, class F>
 KFN int warp_argmax_first(W& w, F f) {
 #ifdef CEMK_EMU
   int best = 0; float bv = f(0, w.regs[0]);
-  for (int l = 1; l < 32; ++l) { float v = f(l, w.regs[l]); if (v > bv || (bv != bv && v == v)) { bv = v; best = l; } }
+  for (int l = 1; l < KW; ++l) { float v = f(l, w.regs[l]); if (v > bv || (bv != bv && v == v)) { bv = v; best = l; } }
   return best;
 #else
   float v = f(w.lane, w.regs); int idx = w.lane;
 #pragma unroll
-  for (int o = 16; o; o >>= 1) {
-    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+  for (int o = KW / 2; o; o >>= 1) {
+    const float ov = __shfl_xor_sync(w.mask, v, o, KW);
+    const int oi = __shfl_xor_sync(w.mask, idx, o, KW);
     if (ov > v || (ov == v && oi < idx) || (v != v && ov == ov)) { v = ov; idx = oi; }
   }
   return idx;
@@ -153,24 +171,41 @@ KFN int warp_argmax_first(W& w, F f) {
 template <class W, class G, class SRC, class SET>
 KFN void warp_shfl_each(W& w, G get, SRC src, SET set) {
 #ifdef CEMK_EMU
-  float vals[32];
-  for (int l = 0; l < 32; ++l) vals[l] = get(l, w.regs[l]);
-  for (int l = 0; l < 32; ++l) set(l, w.regs[l], vals[src(l) & 31]);
+  float vals[KW];
+  for (int l = 0; l < KW; ++l) vals[l] = get(l, w.regs[l]);
+  for (int l = 0; l < KW; ++l) set(l, w.regs[l], vals[src(l) & (KW - 1)]);
 #else
-  const float v = __shfl_sync(0xffffffffu, get(w.lane, w.regs), src(w.lane));
+  const float v = __shfl_sync(w.mask, get(w.lane, w.regs), src(w.lane), KW);
   set(w.lane, w.regs, v);
 #endif
 }
 
-// bit l of the result is set iff pred(l, regs[l]) holds
+// bit l of the result is set iff pred(l, regs[l]) holds, l = 0..KW-1
 template <class W, class F>
 KFN unsigned warp_ballot(W& w, F pred) {
 #ifdef CEMK_EMU
   unsigned m = 0;
-  for (int l = 0; l < 32; ++l) if (pred(l, w.regs[l])) m |= 1u << l;
+  for (int l = 0; l < KW; ++l) if (pred(l, w.regs[l])) m |= 1u << l;
   return m;
 #else
-  return __ballot_sync(0xffffffffu, pred(w.lane, w.regs));
+  return (__ballot_sync(w.mask, pred(w.lane, w.regs)) >> w.shift) & KW_FULL;
+#endif
+}
+// ballot over 32 items: bit i of the result is pred(i), evaluated by lane i % KW
+template <class W, class F>
+KFN unsigned warp_ballot32(W& w, F pred) {
+#ifdef CEMK_EMU
+  unsigned m = 0;
+  for (int i = 0; i < 32; ++i) if (pred(i)) m |= 1u << i;
+  return m;
+#else
+  unsigned m = 0;
+#pragma unroll
+  for (int q = 0; q < 32 / KW; ++q) {
+    const int i = q * KW + w.lane;
+    m |= ((__ballot_sync(w.mask, pred(i)) >> w.shift) & KW_FULL) << (q * KW);
+  }
+  return m;
 #endif
 }
 // warp_argmax_first restricted to lanes 0..7 (three exchange rounds); other lanes' values are ignored
@@ -184,53 +219,54 @@ KFN int warp_argmax_first8(W& w, F f) {
   float v = f(w.lane, w.regs); int idx = w.lane;
 #pragma unroll
   for (int o = 4; o; o >>= 1) {
-    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    const float ov = __shfl_xor_sync(w.mask, v, o, KW);
+    const int oi = __shfl_xor_sync(w.mask, idx, o, KW);
     if (ov > v || (ov == v && oi < idx) || (v != v && ov == ov)) { v = ov; idx = oi; }
   }
-  return __shfl_sync(0xffffffffu, idx, 0);
+  return __shfl_sync(w.mask, idx, 0, KW);
 #endif
 }
 
-// Sums of nine per-lane values (regs.acc[0..8]) over the warp, all nine results to every lane.
+#ifndef CEMK_EMU
+// one round of the transposed butterfly: a lane carrying N values keeps ceil(N/2) of them (the low ones
+// if its `bit` is clear, the high ones otherwise) and adds the partner's copy of the same values
+template <int N, class W>
+KFN void fold_round(W& w, const float* in, float* out, bool hi, int xor_lanes) {
+  constexpr int H = (N + 1) / 2;
+#pragma unroll
+  for (int k = 0; k < H; ++k) {
+    const float upper = H + k < N ? in[H + k] : 0.f;
+    const float mine = hi ? upper : in[k];
+    const float send = hi ? in[k] : upper;
+    out[k] = mine + __shfl_xor_sync(w.mask, send, xor_lanes, KW);
+  }
+}
+#endif
+
+// Sums of nine per-lane values (regs.acc[0..8]) over the group, all nine results to every lane.
 // GPU: transposed butterfly -- each exchange round halves the number of values a lane still carries
-// (5+3+2+1+1 shuffles), then nine broadcasts: 21 shuffles instead of 45.
+// (9 -> 5 -> 3 -> 2 -> 1), then nine broadcasts: 20 shuffles for 16 lanes (36 if summed one by one).
 template <class W>
 KFN void warp_sum9(W& w, float* out) {
 #ifdef CEMK_EMU
-  for (int k = 0; k < 9; ++k) { float s = 0.f; for (int l = 0; l < 32; ++l) s += w.regs[l].acc[k]; out[k] = s; }
+  for (int k = 0; k < 9; ++k) { float s = 0.f; for (int l = 0; l < KW; ++l) s += w.regs[l].acc[k]; out[k] = s; }
 #else
   const int lane = w.lane;
-  const bool hi = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
-  float v[10];
+  float v[9], u[5], t[3], s2[2], r[1];
 #pragma unroll
   for (int k = 0; k < 9; ++k) v[k] = w.regs.acc[k];
-  v[9] = 0.f;
-  float u[5];
+  if (KW == 32) {
+    // lanes 16..31 carry no extra values: plain add first, then the same four folding rounds
 #pragma unroll
-  for (int k = 0; k < 5; ++k) {
-    const float recv = __shfl_xor_sync(0xffffffffu, hi ? v[k] : v[5 + k], 16);
-    u[k] = (hi ? v[5 + k] : v[k]) + recv;
+    for (int k = 0; k < 9; ++k) v[k] += __shfl_xor_sync(w.mask, v[k], 16, KW);
   }
-  float t[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const float mine = h8 ? (k < 2 ? u[3 + k] : 0.f) : u[k];
-    const float send = h8 ? u[k] : (k < 2 ? u[3 + k] : 0.f);
-    t[k] = mine + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-  float s2[2];
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const float mine = h4 ? (k < 1 ? t[2] : 0.f) : t[k];
-    const float send = h4 ? t[k] : (k < 1 ? t[2] : 0.f);
-    s2[k] = mine + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-  float r = (h2 ? s2[1] : s2[0]) + __shfl_xor_sync(0xffffffffu, h2 ? s2[0] : s2[1], 2);
-  r += __shfl_xor_sync(0xffffffffu, r, 1);
-  // lane that ends up holding the total of original index k
-  out[0] = __shfl_sync(0xffffffffu, r, 0);  out[1] = __shfl_sync(0xffffffffu, r, 2);  out[2] = __shfl_sync(0xffffffffu, r, 4);
-  out[3] = __shfl_sync(0xffffffffu, r, 8);  out[4] = __shfl_sync(0xffffffffu, r, 10); out[5] = __shfl_sync(0xffffffffu, r, 16);
-  out[6] = __shfl_sync(0xffffffffu, r, 18); out[7] = __shfl_sync(0xffffffffu, r, 20); out[8] = __shfl_sync(0xffffffffu, r, 24);
+  fold_round<9>(w, v, u, lane & 8, 8);
+  fold_round<5>(w, u, t, lane & 4, 4);
+  fold_round<3>(w, t, s2, lane & 2, 2);
+  fold_round<2>(w, s2, r, lane & 1, 1);
+  // lane holding the total of value k: bit 3 adds 5, bit 2 adds 3, bit 1 adds 2, bit 0 adds 1 to the index
+  out[0] = __shfl_sync(w.mask, r[0], 0, KW); out[1] = __shfl_sync(w.mask, r[0], 1, KW);  out[2] = __shfl_sync(w.mask, r[0], 2, KW);
+  out[3] = __shfl_sync(w.mask, r[0], 4, KW); out[4] = __shfl_sync(w.mask, r[0], 5, KW);  out[5] = __shfl_sync(w.mask, r[0], 8, KW);
+  out[6] = __shfl_sync(w.mask, r[0], 9, KW); out[7] = __shfl_sync(w.mask, r[0], 10, KW); out[8] = __shfl_sync(w.mask, r[0], 12, KW);
 #endif
 }

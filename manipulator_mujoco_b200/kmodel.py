@@ -15,7 +15,8 @@ import numpy as np
 from .mjcf import (GEOM_BOX, GEOM_CAPSULE, GEOM_PLANE, JNT_FREE, JNT_HINGE, ModelConsts, quat_mul,
                    quat_normalize, quat_to_mat)
 
-NL, NV, NQ, MAXCAP, MAXSBOX, MAXRPAIR, NPASS, MAXBPAIR = 6, 12, 13, 12, 8, 128, 4, 8
+NL, NV, NQ, MAXCAP, MAXSBOX, MAXRPAIR, MAXBPAIR = 6, 12, 13, 12, 8, 128, 8
+LANE_GROUP = 16          # lanes per sample in the rollout kernel (csrc/warp_dsl.h KW); one collider pass = 16 pair entries
 KP_NONE, KP_PLANE_CAP, KP_CAP_CAP, KP_CAP_BOX = -1, 0, 1, 2
 KB_PLANE_BOX, KB_BOX_BOX, KB_BOX_BOX_SWAP = 0, 1, 2
 _f, _i = C.c_float, C.c_int
@@ -259,12 +260,11 @@ def build_kmodel(mc: ModelConsts, timestep: float, robot_geom_names=None, tcp_si
     if len(rpairs) > MAXRPAIR or len(bpairs) > MAXBPAIR:
         raise NotImplementedError("too many pairs")
     m.nrpair, m.nbpair, m.nslot_robot = len(rpairs), len(bpairs), slot
-    # lanes of one pass should run the same collider: order by type (cap-box first)
-    # lanes of one 32-wide pass should run the same collider (a divergent pass pays for every collider
+    # lanes of one 16-wide pass should run the same collider (a divergent pass pays for every collider
     # present in it): capsule-box first, plane-capsule right behind, capsule-capsule on its own pass(es)
     by = lambda ty: [i for i in range(len(rpairs)) if rpairs[i][0] == ty]
     order = by(KP_CAP_BOX) + by(KP_PLANE_CAP)
-    pad = (-len(order)) % 32
+    pad = (-len(order)) % LANE_GROUP
     if len(order) + pad + len(by(KP_CAP_CAP)) > MAXRPAIR:
         pad = 0
     order = order + [None] * pad + by(KP_CAP_CAP)

@@ -1,7 +1,7 @@
 // tests/emu/emu.cpp -- CPU single-stepping harness for the rollout core (NO-GPU UNIT TESTS ONLY).
 //
 // Compiles manipulator_mujoco_b200/csrc/rollout_core.h with -DCEMK_EMU, where each LANES block
-// becomes a loop over 32 per-lane register structs (see warp_dsl.h).  It exists so the kernel's
+// becomes a loop over KW per-lane register structs (see warp_dsl.h).  It exists so the kernel's
 // indexing / physics logic can be checked against the oracle in a container without a GPU.
 // Nothing in the package imports it; the product path is the CUDA build in csrc/cemk.cu.
 #define CEMK_EMU 1
@@ -20,6 +20,7 @@ extern "C" int emu_rollout(const KModel* m, int B, int T, const float* thetadot,
     Warp* W = new Warp();
     WarpSmemT<KM_NC_FAST>* S = new WarpSmemT<KM_NC_FAST>();
     WarpSmemT<KM_NC_BIG>* Sb = new WarpSmemT<KM_NC_BIG>();
+    float* prevd = new float[2 * KM_NPASS * KW];
 #pragma omp for schedule(dynamic, 4)
     for (int s = 0; s < B; ++s) {
       memset((void*)W, 0, sizeof(Warp));
@@ -38,9 +39,10 @@ extern "C" int emu_rollout(const KModel* m, int B, int T, const float* thetadot,
       A.collision = collision ? collision + (size_t)s * T * m->nslot_robot : nullptr;
       A.qacc_dbg = qacc_dbg ? qacc_dbg + (size_t)s * T * KM_NV : nullptr;
       A.flags = flags ? flags + s : nullptr;
+      A.prevd = prevd;
       if (nc <= KM_NC_FAST) rollout_sample<KM_NC_FAST>(*W, *m, *S, A); else rollout_sample<KM_NC_BIG>(*W, *m, *Sb, A);
     }
-    delete W; delete S; delete Sb;
+    delete W; delete S; delete Sb; delete[] prevd;
   }
   return 0;
 }
