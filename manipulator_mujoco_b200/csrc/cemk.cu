@@ -90,13 +90,11 @@ __global__ void __launch_bounds__(WARPS * 32, ROLLOUT_MINB) k_rollout(const KMod
     for (int i = threadIdx.x; i < (int)(sizeof(KModel) / 4); i += blockDim.x) dst[i] = src[i];
   }
   __syncthreads();
-  const unsigned wlive = __ballot_sync(0xffffffffu, mine); // lanes of this warp that own a sample
-  if (!mine) return;                                       // the live warps align on a named barrier (CTA_ALIGN)
+  if (!mine) return;                                       // idle group of a partly filled warp: exits (full-mask fences skip exited lanes)
   Warp W;
   W.lane = threadIdx.x & (KW - 1);
   W.shift = (threadIdx.x & 31) & ~(KW - 1);
   W.mask = KW_FULL << W.shift;
-  W.wmask = wlive;
   W.nthr = ONLY_FLAGGED ? 32 : ((nlive + GPW - 1) / GPW) * 32;
 #ifdef CEMK_PHASE_TIMING
   W.phase = 14; W.t0 = clock64();

@@ -420,13 +420,13 @@ KNOINLINE int plane_box(const float* ppos, const float* pn, const float* bpos, c
 template <int NC>
 KFN int box_box_warp(Warp& W, WarpSmemT<NC>& S, int slot, const float* p1, const float* m1, const float* s1,
                      const float* p2, const float* m2, const float* s2) {
-  LANES(W, R)
+  DLANES(W, R)
     if (lane < 9) { const int i = lane / 3, j = lane % 3; S.bbR[lane] = m2[i] * m1[j] + m2[3 + i] * m1[3 + j] + m2[6 + i] * m1[6 + j]; }
     else if (lane < 12) { const int i = lane - 9; S.bbc[i] = m2[i] * (p1[0] - p2[0]) + m2[3 + i] * (p1[1] - p2[1]) + m2[6 + i] * (p1[2] - p2[2]); }
     else if (lane < 16) { float* o = S.bstage[slot][lane - 12]; o[0] = o[1] = o[2] = 0.f; o[3] = 1.f; }
-  END_LANES
+  END_DLANES
   // ---- separating axes, one per lane ----
-  LANES(W, R)
+  DLANES(W, R)
     float cmp = -INFINITY, a0 = 0.f, a1 = 0.f, a2 = 1.f, sgn = 1.f;
     if (lane < 15) {
       const float* Rm = S.bbR; const float* c = S.bbc;
@@ -450,17 +450,17 @@ KFN int box_box_warp(Warp& W, WarpSmemT<NC>& S, int slot, const float* p1, const
       sgn = dc > 0.f ? -1.f : 1.f;          // contact normal points from box 1 (at c) to box 2 (origin)
     }
     R.f0 = cmp; R.f1 = a0 * sgn; R.f2 = a1 * sgn; R.acc[0] = a2 * sgn;
-  END_LANES
-  const int bl = warp_argmax_first(W, [](int, LaneRegs& R) { return R.f0; });
-  const float bestsep = warp_bcast(W, bl, [](int, LaneRegs& R) { return R.f0; });
+  END_DLANES
+  const int bl = warp_argmax_first<true>(W, [](int, LaneRegs& R) { return R.f0; });
+  const float bestsep = warp_bcast<true>(W, bl, [](int, LaneRegs& R) { return R.f0; });
   if (bestsep > 0.f) return 0;               // separated: no slot can be active
-  const float bn[3] = {warp_bcast(W, bl, [](int, LaneRegs& R) { return R.f1; }), warp_bcast(W, bl, [](int, LaneRegs& R) { return R.f2; }),
-                       warp_bcast(W, bl, [](int, LaneRegs& R) { return R.acc[0]; })};
+  const float bn[3] = {warp_bcast<true>(W, bl, [](int, LaneRegs& R) { return R.f1; }), warp_bcast<true>(W, bl, [](int, LaneRegs& R) { return R.f2; }),
+                       warp_bcast<true>(W, bl, [](int, LaneRegs& R) { return R.acc[0]; })};
   {
     float nw[3];
     mat_vec(nw, m2, bn);
     normalize3(nw);
-    UNIFORM_WRITE(W) { copy3(S.bnrm[slot], nw); } END_UNIFORM_WRITE
+    DUNIFORM_WRITE(W) { copy3(S.bnrm[slot], nw); } END_DUNIFORM_WRITE
   }
   float Rm[9], c[3];
 #pragma unroll
@@ -486,7 +486,7 @@ KFN int box_box_warp(Warp& W, WarpSmemT<NC>& S, int slot, const float* p1, const
     mat_vec(w, m2, mid); add3(w, w, p2);
     sub3(df, sp.b, sp.a);
     const float d = dot3(df, bn);
-    UNIFORM_WRITE(W) { copy3(S.bstage[slot][0], w); S.bstage[slot][0][3] = d; } END_UNIFORM_WRITE
+    DUNIFORM_WRITE(W) { copy3(S.bstage[slot][0], w); S.bstage[slot][0][3] = d; } END_DUNIFORM_WRITE
     return d < 0.f ? 1 : 0;
   }
   // ---- face-face: reference face on the box owning the axis, incident face on the other ----
@@ -522,7 +522,7 @@ KFN int box_box_warp(Warp& W, WarpSmemT<NC>& S, int slot, const float* p1, const
   }
   // box face f = 2*axis + (0:+, 1:-), vertices counter-clockwise seen from outside:
   // in-plane signs (u, w) = (-,-),(+,-),(+,+),(-,+) for +k, reversed for -k  (u = k+1, w = k+2 cyclic)
-  LANES(W, R)
+  DLANES(W, R)
     if (lane < 8) {
       const bool ref = lane < 4;
       const int i = lane & 3;
@@ -539,21 +539,21 @@ KFN int box_box_warp(Warp& W, WarpSmemT<NC>& S, int slot, const float* p1, const
       if (ref) copy3(S.bbrf[i], v);
       else { float t[3]; mat_vec(t, Rr, v); add3(S.bbpoly[0][i], t, rc); }
     }
-  END_LANES
-  LANES(W, R)
+  END_DLANES
+  DLANES(W, R)
     if (lane < 4) {                            // outward side-plane normals of the reference face
       float e[3], en[3];
       sub3(e, S.bbrf[lane], S.bbrf[(lane + 3) & 3]);
       cross3(en, e, rn); normalize3(en);
       copy3(S.bben[lane], en);
     }
-  END_LANES
+  END_DLANES
   // ---- Sutherland-Hodgman against the four side planes, polygon edges on lanes; output slots by
   //      ballot (each edge emits its start vertex if inside, then the crossing point) ----
   int np = 4, cur = 0;
   // common case (a box resting on a larger one): every incident vertex is inside every side plane,
   // so clipping would return the polygon unchanged -- 16 tests on 16 lanes and one ballot
-  const unsigned outside = warp_ballot(W, [&](int l, LaneRegs&) {
+  const unsigned outside = warp_ballot<true>(W, [&](int l, LaneRegs&) {
     if (l >= 16) return false;
     float t[3];
     sub3(t, S.bbpoly[0][l & 3], S.bbrf[l >> 2]);
@@ -561,7 +561,7 @@ KFN int box_box_warp(Warp& W, WarpSmemT<NC>& S, int slot, const float* p1, const
   });
 #pragma unroll 1
   for (int i = 0; i < 4 && np > 0 && outside != 0u; ++i) {
-    LANES(W, R)
+    DLANES(W, R)
       R.actmask = 0; R.f0 = 0.f;
       if (lane < np) {
         const float* a = S.bbpoly[cur][lane]; const float* b = S.bbpoly[cur][lane + 1 == np ? 0 : lane + 1];
@@ -572,10 +572,10 @@ KFN int box_box_warp(Warp& W, WarpSmemT<NC>& S, int slot, const float* p1, const
         R.actmask = (keep ? 1 : 0) | (cross ? 2 : 0);
         R.f0 = cross ? da / (da - db) : 0.f;
       }
-    END_LANES
-    const unsigned mk = warp_ballot(W, [](int, LaneRegs& R) { return (R.actmask & 1) != 0; });
-    const unsigned mx = warp_ballot(W, [](int, LaneRegs& R) { return (R.actmask & 2) != 0; });
-    LANES(W, R)
+    END_DLANES
+    const unsigned mk = warp_ballot<true>(W, [](int, LaneRegs& R) { return (R.actmask & 1) != 0; });
+    const unsigned mx = warp_ballot<true>(W, [](int, LaneRegs& R) { return (R.actmask & 2) != 0; });
+    DLANES(W, R)
       if (lane < np && R.actmask) {
         const float* a = S.bbpoly[cur][lane]; const float* b = S.bbpoly[cur][lane + 1 == np ? 0 : lane + 1];
         const unsigned below = (1u << lane) - 1u;
@@ -583,12 +583,12 @@ KFN int box_box_warp(Warp& W, WarpSmemT<NC>& S, int slot, const float* p1, const
         if (R.actmask & 1) { copy3(S.bbpoly[cur ^ 1][o], a); ++o; }
         if (R.actmask & 2) { float ab[3]; sub3(ab, b, a); madd3(S.bbpoly[cur ^ 1][o], a, ab, R.f0); }
       }
-    END_LANES
+    END_DLANES
     np = KPOPC(mk) + KPOPC(mx); cur ^= 1;
   }
   if (np == 0) return 0;
   // ---- penetrating vertices projected on the reference face; 4-point manifold ----
-  LANES(W, R)
+  DLANES(W, R)
     R.f0 = -1e6f; R.actmask = 0;
     if (lane < np) {
       float tt[3];
@@ -599,12 +599,12 @@ KFN int box_box_warp(Warp& W, WarpSmemT<NC>& S, int slot, const float* p1, const
       R.actmask = h < 0.f;
       R.f0 = h < 0.f ? 0.f : -1e6f;            // dm
     }
-  END_LANES
+  END_DLANES
   if (np <= 4) {
     // With at most four vertices MJX's 4-point rule returns exactly the penetrating ones (every
     // later pick prefers a not-yet-chosen vertex); emit them in polygon order.
-    const unsigned pen = warp_ballot(W, [&](int l, LaneRegs& R) { return l < np && R.actmask != 0; });
-    LANES(W, R)
+    const unsigned pen = warp_ballot<true>(W, [&](int l, LaneRegs& R) { return l < np && R.actmask != 0; });
+    DLANES(W, R)
       if (pen & (1u << lane)) {
         const int q = KPOPC(pen & ((1u << lane) - 1u));
         float w[3];
@@ -613,34 +613,34 @@ KFN int box_box_warp(Warp& W, WarpSmemT<NC>& S, int slot, const float* p1, const
         add3(w, w, p2);
         copy3(S.bstage[slot][q], w); S.bstage[slot][q][3] = S.bbpref[lane][3];
       }
-    END_LANES
+    END_DLANES
     return KPOPC(pen);
   }
   // lanes >= np must never win: give them -inf in every argmax
-  const int ia = warp_argmax_first8(W, [&](int l, LaneRegs& R) { return l < np ? R.f0 : -INFINITY; });
-  LANES(W, R)
+  const int ia = warp_argmax_first8<true>(W, [&](int l, LaneRegs& R) { return l < np ? R.f0 : -INFINITY; });
+  DLANES(W, R)
     R.f1 = -INFINITY;
     if (lane < np) { float t[3]; sub3(t, S.bbpref[ia], S.bbpref[lane]); R.f1 = dot3(t, t) + R.f0; }
-  END_LANES
-  const int ib = warp_argmax_first8(W, [](int, LaneRegs& R) { return R.f1; });
+  END_DLANES
+  const int ib = warp_argmax_first8<true>(W, [](int, LaneRegs& R) { return R.f1; });
   float ab[3];
   { float t[3]; sub3(t, S.bbpref[ia], S.bbpref[ib]); cross3(ab, rn, t); }
-  LANES(W, R)
+  DLANES(W, R)
     R.f1 = -INFINITY;
     if (lane < np) { float ap[3]; sub3(ap, S.bbpref[ia], S.bbpref[lane]); R.f1 = fabsf(dot3(ap, ab)) + R.f0; }
-  END_LANES
-  const int ic = warp_argmax_first8(W, [](int, LaneRegs& R) { return R.f1; });
+  END_DLANES
+  const int ic = warp_argmax_first8<true>(W, [](int, LaneRegs& R) { return R.f1; });
   float ac[3], bc[3];
   { float t[3]; sub3(t, S.bbpref[ia], S.bbpref[ic]); cross3(ac, rn, t); sub3(t, S.bbpref[ib], S.bbpref[ic]); cross3(bc, rn, t); }
-  LANES(W, R)
+  DLANES(W, R)
     R.f1 = -INFINITY;
     if (lane < np) {
       float bp[3], ap[3];
       sub3(bp, S.bbpref[ib], S.bbpref[lane]); sub3(ap, S.bbpref[ia], S.bbpref[lane]);
       R.f1 = fmaxf(fabsf(dot3(bp, bc)), fabsf(dot3(ap, ac))) + R.f0 - ((lane == ia || lane == ib || lane == ic) ? 2e6f : 0.f);
     }
-  END_LANES
-  const int id = warp_argmax_first8(W, [](int, LaneRegs& R) { return R.f1; });
+  END_DLANES
+  const int id = warp_argmax_first8<true>(W, [](int, LaneRegs& R) { return R.f1; });
   const int idx[4] = {ia, ib, ic, id};
   int nact = 0;
 #pragma unroll
@@ -654,7 +654,7 @@ KFN int box_box_warp(Warp& W, WarpSmemT<NC>& S, int slot, const float* p1, const
     if (swap) { float u[3]; mat_vec(u, Rm, S.bbpref[idx[q]]); add3(u, u, c); mat_vec(w, m2, u); }
     else mat_vec(w, m2, S.bbpref[idx[q]]);
     add3(w, w, p2);
-    UNIFORM_WRITE(W) { copy3(S.bstage[slot][q], w); S.bstage[slot][q][3] = h; } END_UNIFORM_WRITE
+    DUNIFORM_WRITE(W) { copy3(S.bstage[slot][q], w); S.bstage[slot][q][3] = h; } END_DUNIFORM_WRITE
     ++nact;
   }
   return nact;
@@ -775,24 +775,24 @@ KFN void chol_solve_rows(Warp& W) {
   auto loc = [&](int l) { return l - base(l); };
 #pragma unroll
   for (int j = 0; j < N; ++j) {
-    warp_shfl_each(W, [&](int, LaneRegs& R) { return R.h[j]; }, [&](int l) { return base(l) + j; },
+    warp_shfl_each<true>(W, [&](int, LaneRegs& R) { return R.h[j]; }, [&](int l) { return base(l) + j; },
                    [&](int l, LaneRegs& R, float d) { const float dj = sqrtf(d); R.h[j] = (loc(l) == j) ? dj : R.h[j] / dj; });
 #pragma unroll
     for (int k = j + 1; k < N; ++k)
-      warp_shfl_each(W, [&](int, LaneRegs& R) { return R.h[j]; }, [&](int l) { return base(l) + k; },
+      warp_shfl_each<true>(W, [&](int, LaneRegs& R) { return R.h[j]; }, [&](int l) { return base(l) + k; },
                      [&](int l, LaneRegs& R, float lkj) { if (loc(l) >= k) R.h[k] -= R.h[j] * lkj; });
   }
 #pragma unroll
   for (int k = 0; k < N; ++k)                  // forward substitution L y = rhs
-    warp_shfl_each(W, [&](int, LaneRegs& R) { return R.f0 / R.h[k]; }, [&](int l) { return base(l) + k; },
+    warp_shfl_each<true>(W, [&](int, LaneRegs& R) { return R.f0 / R.h[k]; }, [&](int l) { return base(l) + k; },
                    [&](int l, LaneRegs& R, float yk) { if (loc(l) == k) R.f0 = yk; else if (loc(l) > k) R.f0 -= R.h[k] * yk; });
 #pragma unroll
   for (int k = N - 1; k >= 0; --k) {           // back substitution L^T x = y, column k of L^T lives in lane base+k
-    warp_shfl_each(W, [&](int, LaneRegs& R) { return R.f0 / R.h[k]; }, [&](int l) { return base(l) + k; },
+    warp_shfl_each<true>(W, [&](int, LaneRegs& R) { return R.f0 / R.h[k]; }, [&](int l) { return base(l) + k; },
                    [&](int l, LaneRegs& R, float xk) { R.f1 = xk; if (loc(l) == k) R.f0 = xk; });
 #pragma unroll
     for (int i = 0; i < k; ++i)
-      warp_shfl_each(W, [&](int, LaneRegs& R) { return R.h[i] * R.f1; }, [&](int l) { return base(l) + k; },
+      warp_shfl_each<true>(W, [&](int, LaneRegs& R) { return R.h[i] * R.f1; }, [&](int l) { return base(l) + k; },
                      [&](int l, LaneRegs& R, float p) { if (loc(l) == i) R.f0 -= p; });
   }
 }
@@ -1124,12 +1124,13 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
       const int q = KFFS(rem) - 1;
       const int ty = m.bp_type[q], a = m.bp_a[q];
       if (ty == KB_PLANE_BOX) {
-        LANES(W, R)
+        DLANES(W, R)
           if (lane == q) { plane_box(m.plane_pos, m.plane_n, bp, S.bmat, m.fb_size, S.bstage[q]); copy3(S.bnrm[q], m.plane_n); }
-        END_LANES
+        END_DLANES
       } else if (ty == KB_BOX_BOX) box_box_warp<NC>(W, S, q, m.sb_pos[a], m.sb_mat[a], m.sb_size[a], bp, S.bmat, m.fb_size);
       else box_box_warp<NC>(W, S, q, bp, S.bmat, m.fb_size, m.sb_pos[a], m.sb_mat[a], m.sb_size[a]);
     }
+    REGROUP();                                  // the two samples of a warp may have tested different pairs
   }
   LANES(W, R)
     R.actmask = __float_as_int(R.h[0]);
@@ -1173,7 +1174,10 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
   const int nlim = warp_excl_scan(W, [](int, LaneRegs& R) { return R.nact; }, [](int, LaneRegs& R, int o) { R.off = o; });
   UNIFORM_WRITE(W) { S.ncon = ncon; S.nlim = nlim; S.nrow = nlim + 4 * ncon; if (ncon_all > NC) S.flags |= 1; } END_UNIFORM_WRITE
   const int nrow = nlim + 4 * ncon;
-  if (nrow == 0) {
+  // No active row: qacc = qacc_smooth.  The solver below is skipped only when that holds for both samples
+  // of the warp (keeps the fenced code warp-uniform); otherwise a row-less sample runs through it with
+  // empty loops and takes qacc_smooth at the end.
+  if (warp_all_groups(W, nrow == 0)) {
     LANES(W, R)
       if (lane < KM_NV) { S.qacc[lane] = S.as[lane]; S.warm[lane] = S.as[lane]; }
     END_LANES
@@ -1335,17 +1339,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
   // ---- S4: search = -H^-1 grad, Cholesky with one row per lane in registers.  Robot and box
   //      blocks only couple through a robot/box contact; otherwise the two 6x6 blocks are factorised
   //      side by side (6 column steps instead of 12) ----
-  if (coupled) {
-    LANES(W, R)
-#pragma unroll
-      for (int k = 0; k < KM_NV; ++k) R.h[k] = (lane < KM_NV && k <= lane) ? S.H[lane][k] : 0.f;
-      R.f0 = lane < KM_NV ? S.grad[lane] : 0.f;
-    END_LANES
-    chol_solve_rows<12>(W);
-    LANES(W, R)
-      if (lane < KM_NV) S.search[lane] = -R.f0;
-    END_LANES
-  } else {
+  {
     USYNC();
     const Vec6 xr = chol_solve6(&S.H[0][0], KM_NV, S.grad);
     const Vec6 xb = chol_solve6(&S.H[KM_NL][KM_NL], KM_NV, S.grad + KM_NL);
@@ -1353,6 +1347,18 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
       for (int i = 0; i < KM_NL; ++i) { S.search[i] = -xr.v[i]; S.search[KM_NL + i] = -xb.v[i]; }
     } END_UNIFORM_WRITE
   }
+  if (coupled) {                                // rare: full 12x12 system (replaces the block solution above)
+    DLANES(W, R)
+#pragma unroll
+      for (int k = 0; k < KM_NV; ++k) R.h[k] = (lane < KM_NV && k <= lane) ? S.H[lane][k] : 0.f;
+      R.f0 = lane < KM_NV ? S.grad[lane] : 0.f;
+    END_DLANES
+    chol_solve_rows<12>(W);
+    DLANES(W, R)
+      if (lane < KM_NV) S.search[lane] = -R.f0;
+    END_DLANES
+  }
+  REGROUP();
   PHASE(W, 11);
   // ---- S5: line search (BD.10) ----
   // J.search per row, the Gauss-term sums and the constraint sums of the starting point alpha = 0
@@ -1386,16 +1392,18 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
   PHASE(W, 19);
   // One rolled loop evaluates the piecewise quadratic at three step sizes per trip:
   //   trip -1: lo = point(-p0.d0/p0.d1); trips 0..ls_iterations-1: MJX bracket update.
-  bool swapped = true;
+  // The loop is warp-uniform: it runs until every sample of the warp is done; a sample that finished
+  // earlier idles through the remaining trips with its bracket frozen.
+  bool swapped = true, done = nrow == 0;
 #pragma unroll 1
   for (int it = -1; it < m.ls_iterations; ++it) {
     float al0, al1, al2;
     if (it == -1) { al0 = al1 = al2 = p0.alpha - p0.d0 / p0.d1; }
     else {
-      bool done = !swapped;
+      done = done || !swapped;
       done = done || ((lo.d0 < 0.f) && (lo.d0 > -gtol));
       done = done || ((hi.d0 > 0.f) && (hi.d0 < gtol));
-      if (done) break;
+      if (warp_all_groups(W, done)) break;
       al0 = lo.alpha - lo.d0 / lo.d1; al1 = hi.alpha - hi.d0 / hi.d1; al2 = 0.5f * (lo.alpha + hi.alpha);
     }
     LANES(W, R)
@@ -1427,6 +1435,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
       if (pt[0].d0 < p0.d0) { lo = pt[0]; hi = p0; } else { hi = pt[0]; lo = p0; }
       continue;
     }
+    if (done) continue;
     const LSPoint lo_next = pt[0], hi_next = pt[1], mid = pt[2];
     bool s1 = in_bracket(lo, lo_next); if (s1) lo = lo_next;
     bool s2 = in_bracket(lo, mid);     if (s2) lo = mid;
@@ -1447,6 +1456,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
   LANES(W, R)
     if (lane < KM_NV) {
       float a = S.qacc[lane] + alpha * S.search[lane];
+      if (nrow == 0) a = S.as[lane];
       S.qacc[lane] = a; S.warm[lane] = a;
     }
   END_LANES

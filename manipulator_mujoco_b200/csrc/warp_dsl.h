@@ -9,8 +9,14 @@
 //     __syncwarp(group mask).  With KW = 16 the two halves of a warp run the same instruction stream on
 //     two samples: "uniform" scalar code (small dense solves, the serial joint chain, line-search control)
 //     is issued once for both, and phases that only have 6..16 work items fill the warp twice as well.
-//     Control flow that depends on the sample (line-search trip counts, contact cases) may diverge
-//     between the halves; nothing in the core synchronises across groups except CTA_ALIGN;
+//     Two flavours of every fence / collective exist.  The plain ones (LANES, UNIFORM_WRITE, warp_sum ...)
+//     use the constant full-warp member mask and may only appear where both groups of the warp are on
+//     the same path ("converged" code: the core keeps its sample-dependent control flow warp-uniform
+//     there, e.g. the line search runs until both samples are done).  The D-flavours (DLANES,
+//     DUNIFORM_WRITE, warp_sum<true> ...) use the group's own mask and are for the few regions where the
+//     two samples may take different paths (free-box narrow phase, coupled 12x12 solve); a variable
+//     member mask costs a MATCH/vote sequence per fence, which is why it is not used everywhere.
+//     A divergent region ends with REGROUP(), a full-warp fence;
 //   * by g++ with -DCEMK_EMU (tests/emu, no-GPU unit tests only), where a LANES block is a plain
 //     `for (lane = 0..KW-1)` loop over an array of per-lane register structs.  This is a debugging
 //     aid for kernel logic in a container without a GPU; it is never used by the product path.
@@ -38,11 +44,16 @@ static_assert(KW == 16 || KW == 32, "CEMK_KW must be 16 or 32");
 #define PHASE_ALIGN(bit)
 #define LANES(W, R) for (int lane = 0; lane < KW; ++lane) { auto& R = (W).regs[lane]; (void)R;
 #define END_LANES }
+#define DLANES(W, R) LANES(W, R)
+#define END_DLANES }
 #define RLANES(W, R) LANES(W, R)
 #define END_RLANES }
 #define UNIFORM_WRITE(W) if (true)
 #define END_UNIFORM_WRITE
+#define DUNIFORM_WRITE(W) if (true)
+#define END_DUNIFORM_WRITE
 #define USYNC()
+#define REGROUP()
 #define KRSQRT(x) (1.0f / sqrtf(x))
 #define KPOPC(x) __builtin_popcount(x)
 #define KFFS(x) __builtin_ffs((int)(x))
@@ -54,7 +65,7 @@ static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); retur
 // Keep the live warps of a CTA on the same code (instruction-cache locality): named barrier 1 with the
 // live thread count of this CTA (a CTA may run fewer samples than its launch width, see
 // cemk_rollout_cost).  The two groups of a warp re-converge first (bar.sync is a per-warp instruction).
-#define CTA_ALIGN(W) do { __syncwarp((W).wmask); asm volatile("bar.sync 1, %0;" :: "r"((W).nthr) : "memory"); } while (0)
+#define CTA_ALIGN(W) do { __syncwarp(); asm volatile("bar.sync 1, %0;" :: "r"((W).nthr) : "memory"); } while (0)
 #ifdef CEMK_STEP_SYNC
 #define STEP_ALIGN() CTA_ALIGN(W)
 #else
@@ -67,18 +78,26 @@ static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); retur
 #else
 #define PHASE_ALIGN(bit)
 #endif
-#define LANES(W, R) { __syncwarp((W).mask); const int lane = (W).lane; auto& R = (W).regs; (void)R;
-#define END_LANES } __syncwarp((W).mask);
+#define LANES(W, R) { __syncwarp(); const int lane = (W).lane; auto& R = (W).regs; (void)R;
+#define END_LANES } __syncwarp();
+#define DLANES(W, R) { __syncwarp((W).mask); const int lane = (W).lane; auto& R = (W).regs; (void)R;
+#define END_DLANES } __syncwarp((W).mask);
 // register-only lane block: touches no shared scratch, so no fences
 #define RLANES(W, R) { const int lane = (W).lane; auto& R = (W).regs; (void)R; (void)lane;
 #define END_RLANES }
-#define UNIFORM_WRITE(W) __syncwarp((W).mask); if ((W).lane == 0)
-#define END_UNIFORM_WRITE __syncwarp((W).mask);
-#define USYNC() __syncwarp((W).mask)
+#define UNIFORM_WRITE(W) __syncwarp(); if ((W).lane == 0)
+#define END_UNIFORM_WRITE __syncwarp();
+#define DUNIFORM_WRITE(W) __syncwarp((W).mask); if ((W).lane == 0)
+#define END_DUNIFORM_WRITE __syncwarp((W).mask);
+#define USYNC() __syncwarp()
+#define REGROUP() __syncwarp()
 #define KRSQRT(x) rsqrtf(x)
 #define KPOPC(x) __popc(x)
 #define KFFS(x) __ffs((int)(x))
 #endif
+
+// member mask of a collective: the group's own lanes in divergent regions, the whole warp otherwise
+#define KMASK(w) (DIV ? (w).mask : 0xffffffffu)
 
 template <class LR>
 struct WarpCtx {
@@ -89,7 +108,6 @@ struct WarpCtx {
   int lane;          // lane within the group, 0..KW-1
   int shift;         // first lane of the group within the warp (0 or 16)
   unsigned mask;     // member mask of the group
-  unsigned wmask;    // lanes of this warp that own a sample (both groups, or this one if the other is idle)
   int nthr;          // live threads of this CTA (barrier width)
 #ifdef CEMK_PHASE_TIMING
   long long t0; int phase; long long ph[24];
@@ -106,7 +124,7 @@ struct WarpCtx {
 #endif
 
 // sum over the group's lanes of f(lane, regs); result is group-uniform
-template <class W, class F>
+template <bool DIV = false, class W, class F>
 KFN float warp_sum(W& w, F f) {
 #ifdef CEMK_EMU
   float s = 0.f;
@@ -115,14 +133,14 @@ KFN float warp_sum(W& w, F f) {
 #else
   float v = f(w.lane, w.regs);
 #pragma unroll
-  for (int o = KW / 2; o; o >>= 1) v += __shfl_xor_sync(w.mask, v, o, KW);
+  for (int o = KW / 2; o; o >>= 1) v += __shfl_xor_sync(KMASK(w), v, o, KW);
   return v;
 #endif
 }
 
 // exclusive prefix sum of small non-negative ints; set(lane, regs, offset) receives each lane's
 // offset; returns the group total
-template <class W, class G, class S>
+template <bool DIV = false, class W, class G, class S>
 KFN int warp_excl_scan(W& w, G get, S set) {
 #ifdef CEMK_EMU
   int run = 0;
@@ -131,25 +149,25 @@ KFN int warp_excl_scan(W& w, G get, S set) {
 #else
   int v = get(w.lane, w.regs), inc = v;
 #pragma unroll
-  for (int o = 1; o < KW; o <<= 1) { int t = __shfl_up_sync(w.mask, inc, o, KW); if (w.lane >= o) inc += t; }
+  for (int o = 1; o < KW; o <<= 1) { int t = __shfl_up_sync(KMASK(w), inc, o, KW); if (w.lane >= o) inc += t; }
   set(w.lane, w.regs, inc - v);
-  return __shfl_sync(w.mask, inc, KW - 1, KW);
+  return __shfl_sync(KMASK(w), inc, KW - 1, KW);
 #endif
 }
 
 // value of f(src, regs[src]) broadcast to every lane of the group
-template <class W, class F>
+template <bool DIV = false, class W, class F>
 KFN float warp_bcast(W& w, int src, F f) {
 #ifdef CEMK_EMU
   return f(src, w.regs[src]);
 #else
-  return __shfl_sync(w.mask, f(w.lane, w.regs), src, KW);
+  return __shfl_sync(KMASK(w), f(w.lane, w.regs), src, KW);
 #endif
 }
 
 // lane index of the maximum of f(lane, regs) over the group; ties -> lowest lane ("first max");
 // lanes whose value is NaN never win against a number
-template <class W, class F>
+template <bool DIV = false, class W, class F>
 KFN int warp_argmax_first(W& w, F f) {
 #ifdef CEMK_EMU
   int best = 0; float bv = f(0, w.regs[0]);
@@ -159,8 +177,8 @@ KFN int warp_argmax_first(W& w, F f) {
   float v = f(w.lane, w.regs); int idx = w.lane;
 #pragma unroll
   for (int o = KW / 2; o; o >>= 1) {
-    const float ov = __shfl_xor_sync(w.mask, v, o, KW);
-    const int oi = __shfl_xor_sync(w.mask, idx, o, KW);
+    const float ov = __shfl_xor_sync(KMASK(w), v, o, KW);
+    const int oi = __shfl_xor_sync(KMASK(w), idx, o, KW);
     if (ov > v || (ov == v && oi < idx) || (v != v && ov == ov)) { v = ov; idx = oi; }
   }
   return idx;
@@ -168,31 +186,31 @@ KFN int warp_argmax_first(W& w, F f) {
 }
 
 // per-lane-source shuffle: lane l receives get(src(l), regs[src(l)]) through set(l, regs[l], value)
-template <class W, class G, class SRC, class SET>
+template <bool DIV = false, class W, class G, class SRC, class SET>
 KFN void warp_shfl_each(W& w, G get, SRC src, SET set) {
 #ifdef CEMK_EMU
   float vals[KW];
   for (int l = 0; l < KW; ++l) vals[l] = get(l, w.regs[l]);
   for (int l = 0; l < KW; ++l) set(l, w.regs[l], vals[src(l) & (KW - 1)]);
 #else
-  const float v = __shfl_sync(w.mask, get(w.lane, w.regs), src(w.lane), KW);
+  const float v = __shfl_sync(KMASK(w), get(w.lane, w.regs), src(w.lane), KW);
   set(w.lane, w.regs, v);
 #endif
 }
 
 // bit l of the result is set iff pred(l, regs[l]) holds, l = 0..KW-1
-template <class W, class F>
+template <bool DIV = false, class W, class F>
 KFN unsigned warp_ballot(W& w, F pred) {
 #ifdef CEMK_EMU
   unsigned m = 0;
   for (int l = 0; l < KW; ++l) if (pred(l, w.regs[l])) m |= 1u << l;
   return m;
 #else
-  return (__ballot_sync(w.mask, pred(w.lane, w.regs)) >> w.shift) & KW_FULL;
+  return (__ballot_sync(KMASK(w), pred(w.lane, w.regs)) >> w.shift) & KW_FULL;
 #endif
 }
 // ballot over 32 items: bit i of the result is pred(i), evaluated by lane i % KW
-template <class W, class F>
+template <bool DIV = false, class W, class F>
 KFN unsigned warp_ballot32(W& w, F pred) {
 #ifdef CEMK_EMU
   unsigned m = 0;
@@ -203,13 +221,13 @@ KFN unsigned warp_ballot32(W& w, F pred) {
 #pragma unroll
   for (int q = 0; q < 32 / KW; ++q) {
     const int i = q * KW + w.lane;
-    m |= ((__ballot_sync(w.mask, pred(i)) >> w.shift) & KW_FULL) << (q * KW);
+    m |= ((__ballot_sync(KMASK(w), pred(i)) >> w.shift) & KW_FULL) << (q * KW);
   }
   return m;
 #endif
 }
 // warp_argmax_first restricted to lanes 0..7 (three exchange rounds); other lanes' values are ignored
-template <class W, class F>
+template <bool DIV = false, class W, class F>
 KFN int warp_argmax_first8(W& w, F f) {
 #ifdef CEMK_EMU
   int best = 0; float bv = f(0, w.regs[0]);
@@ -219,18 +237,18 @@ KFN int warp_argmax_first8(W& w, F f) {
   float v = f(w.lane, w.regs); int idx = w.lane;
 #pragma unroll
   for (int o = 4; o; o >>= 1) {
-    const float ov = __shfl_xor_sync(w.mask, v, o, KW);
-    const int oi = __shfl_xor_sync(w.mask, idx, o, KW);
+    const float ov = __shfl_xor_sync(KMASK(w), v, o, KW);
+    const int oi = __shfl_xor_sync(KMASK(w), idx, o, KW);
     if (ov > v || (ov == v && oi < idx) || (v != v && ov == ov)) { v = ov; idx = oi; }
   }
-  return __shfl_sync(w.mask, idx, 0, KW);
+  return __shfl_sync(KMASK(w), idx, 0, KW);
 #endif
 }
 
 #ifndef CEMK_EMU
 // one round of the transposed butterfly: a lane carrying N values keeps ceil(N/2) of them (the low ones
 // if its `bit` is clear, the high ones otherwise) and adds the partner's copy of the same values
-template <int N, class W>
+template <int N, bool DIV, class W>
 KFN void fold_round(W& w, const float* in, float* out, bool hi, int xor_lanes) {
   constexpr int H = (N + 1) / 2;
 #pragma unroll
@@ -238,7 +256,7 @@ KFN void fold_round(W& w, const float* in, float* out, bool hi, int xor_lanes) {
     const float upper = H + k < N ? in[H + k] : 0.f;
     const float mine = hi ? upper : in[k];
     const float send = hi ? in[k] : upper;
-    out[k] = mine + __shfl_xor_sync(w.mask, send, xor_lanes, KW);
+    out[k] = mine + __shfl_xor_sync(KMASK(w), send, xor_lanes, KW);
   }
 }
 #endif
@@ -246,7 +264,7 @@ KFN void fold_round(W& w, const float* in, float* out, bool hi, int xor_lanes) {
 // Sums of nine per-lane values (regs.acc[0..8]) over the group, all nine results to every lane.
 // GPU: transposed butterfly -- each exchange round halves the number of values a lane still carries
 // (9 -> 5 -> 3 -> 2 -> 1), then nine broadcasts: 20 shuffles for 16 lanes (36 if summed one by one).
-template <class W>
+template <bool DIV = false, class W>
 KFN void warp_sum9(W& w, float* out) {
 #ifdef CEMK_EMU
   for (int k = 0; k < 9; ++k) { float s = 0.f; for (int l = 0; l < KW; ++l) s += w.regs[l].acc[k]; out[k] = s; }
@@ -258,15 +276,27 @@ KFN void warp_sum9(W& w, float* out) {
   if (KW == 32) {
     // lanes 16..31 carry no extra values: plain add first, then the same four folding rounds
 #pragma unroll
-    for (int k = 0; k < 9; ++k) v[k] += __shfl_xor_sync(w.mask, v[k], 16, KW);
+    for (int k = 0; k < 9; ++k) v[k] += __shfl_xor_sync(KMASK(w), v[k], 16, KW);
   }
-  fold_round<9>(w, v, u, lane & 8, 8);
-  fold_round<5>(w, u, t, lane & 4, 4);
-  fold_round<3>(w, t, s2, lane & 2, 2);
-  fold_round<2>(w, s2, r, lane & 1, 1);
+  fold_round<9, DIV>(w, v, u, lane & 8, 8);
+  fold_round<5, DIV>(w, u, t, lane & 4, 4);
+  fold_round<3, DIV>(w, t, s2, lane & 2, 2);
+  fold_round<2, DIV>(w, s2, r, lane & 1, 1);
   // lane holding the total of value k: bit 3 adds 5, bit 2 adds 3, bit 1 adds 2, bit 0 adds 1 to the index
-  out[0] = __shfl_sync(w.mask, r[0], 0, KW); out[1] = __shfl_sync(w.mask, r[0], 1, KW);  out[2] = __shfl_sync(w.mask, r[0], 2, KW);
-  out[3] = __shfl_sync(w.mask, r[0], 4, KW); out[4] = __shfl_sync(w.mask, r[0], 5, KW);  out[5] = __shfl_sync(w.mask, r[0], 8, KW);
-  out[6] = __shfl_sync(w.mask, r[0], 9, KW); out[7] = __shfl_sync(w.mask, r[0], 10, KW); out[8] = __shfl_sync(w.mask, r[0], 12, KW);
+  out[0] = __shfl_sync(KMASK(w), r[0], 0, KW); out[1] = __shfl_sync(KMASK(w), r[0], 1, KW);  out[2] = __shfl_sync(KMASK(w), r[0], 2, KW);
+  out[3] = __shfl_sync(KMASK(w), r[0], 4, KW); out[4] = __shfl_sync(KMASK(w), r[0], 5, KW);  out[5] = __shfl_sync(KMASK(w), r[0], 8, KW);
+  out[6] = __shfl_sync(KMASK(w), r[0], 9, KW); out[7] = __shfl_sync(KMASK(w), r[0], 10, KW); out[8] = __shfl_sync(KMASK(w), r[0], 12, KW);
+#endif
+}
+
+// true iff pred holds for every sample of the warp (both lane groups); converged code only
+template <class W>
+KFN bool warp_all_groups(W& w, bool pred) {
+#ifdef CEMK_EMU
+  (void)w;
+  return pred;
+#else
+  (void)w;
+  return __all_sync(0xffffffffu, pred);
 #endif
 }
