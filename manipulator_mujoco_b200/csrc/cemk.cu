@@ -22,6 +22,9 @@
 #define ROLLOUT_WARPS 14      // warps per CTA (28 samples with two samples per warp: all the shared memory of an SM); they
                               // step in lockstep (STEP_ALIGN) to share the instruction cache
 #endif
+#ifndef ROLLOUT_SETS
+#define ROLLOUT_SETS 1        // independent lockstep sets per CTA (named barriers 1 .. ROLLOUT_SETS)
+#endif
 #ifndef ROLLOUT_MINB
 #define ROLLOUT_MINB 1
 #endif
@@ -95,7 +98,13 @@ __global__ void __launch_bounds__(WARPS * 32, ROLLOUT_MINB) k_rollout(const KMod
   W.lane = threadIdx.x & (KW - 1);
   W.shift = (threadIdx.x & 31) & ~(KW - 1);
   W.mask = KW_FULL << W.shift;
-  W.nthr = ONLY_FLAGGED ? 32 : ((nlive + GPW - 1) / GPW) * 32;
+  {
+    // alignment sets: the live warps of the CTA step in lockstep within ROLLOUT_SETS sets (warp w -> set w % SETS)
+    const int nw = ONLY_FLAGGED ? 1 : (nlive + GPW - 1) / GPW, w = threadIdx.x >> 5;
+    const int sets = nw < ROLLOUT_SETS ? 1 : ROLLOUT_SETS, set = w % sets;
+    W.bar = 1 + set;
+    W.nthr = ((nw - set + sets - 1) / sets) * 32;
+  }
 #ifdef CEMK_PHASE_TIMING
   W.phase = 14; W.t0 = clock64();
   for (int i = 0; i < 24; ++i) W.ph[i] = 0;

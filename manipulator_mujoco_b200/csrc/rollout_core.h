@@ -966,21 +966,18 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
     }
    }
   END_LANES
-  // ---- P3: composite inertias and link velocities, one (link, component) item per lane (BD.3, BD.4) ----
+  // ---- P3: composite inertias (suffix sums over the chain, one inertia component per lane 0-9) and link
+  //      velocities (prefix sums, one spatial component per lane 10-15) (BD.3, BD.4) ----
   LANES(W, R)
-#pragma unroll 1
-    for (int e = lane; e < KM_NL * 16; e += KW) {
-      if (e < KM_NL * 10) {
-        const int i = e / 10, k = e - 10 * i;
-        float s = 0.f;
-        for (int b = i; b < KM_NL; ++b) s += S.cinert[b][k];
-        S.crb[i][k] = s;
-      } else {
-        const int e2 = e - KM_NL * 10, i = e2 / 6, k = e2 - 6 * i;
-        float v = 0.f;
-        for (int b = 0; b <= i; ++b) v += S.cdof[b][k] * S.qvel[b];
-        S.cvel[i][k] = v;
-      }
+    if (lane < 10) {
+      float s = 0.f;
+#pragma unroll
+      for (int b = KM_NL - 1; b >= 0; --b) { s += S.cinert[b][lane]; S.crb[b][lane] = s; }
+    } else if (lane < 16) {
+      const int k = lane - 10;
+      float v = 0.f;
+#pragma unroll
+      for (int b = 0; b < KM_NL; ++b) { v += S.cdof[b][k] * S.qvel[b]; S.cvel[b][k] = v; }
     }
   END_LANES
   // ---- P4: robot inertia matrix entries (lanes 0-20), cdof_dot (lanes 24-29) ----
@@ -1174,15 +1171,9 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
   const int nlim = warp_excl_scan(W, [](int, LaneRegs& R) { return R.nact; }, [](int, LaneRegs& R, int o) { R.off = o; });
   UNIFORM_WRITE(W) { S.ncon = ncon; S.nlim = nlim; S.nrow = nlim + 4 * ncon; if (ncon_all > NC) S.flags |= 1; } END_UNIFORM_WRITE
   const int nrow = nlim + 4 * ncon;
-  // No active row: qacc = qacc_smooth.  The solver below is skipped only when that holds for both samples
-  // of the warp (keeps the fenced code warp-uniform); otherwise a row-less sample runs through it with
-  // empty loops and takes qacc_smooth at the end.
-  if (warp_all_groups(W, nrow == 0)) {
-    LANES(W, R)
-      if (lane < KM_NV) { S.qacc[lane] = S.as[lane]; S.warm[lane] = S.as[lane]; }
-    END_LANES
-    return;
-  }
+  // No active row (the box in free fall, first steps of a rollout): qacc = qacc_smooth.  Such a sample
+  // still runs through the solver below with empty loops and takes qacc_smooth at the end, which keeps
+  // the fenced code and the CTA alignment points the same for every warp.
   LANES(W, R)
     if (R.nact) {
       const int r = R.off;
@@ -1232,6 +1223,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
     }
   END_LANES
   const bool coupled = warp_sum(W, [](int, LaneRegs& R) { return R.f2; }) > 0.f;
+  PHASE_ALIGN(8);
   PHASE(W, 8);
   // ---- S1: warm start vs smooth start (B.6) ----
   contact_dots<NC>(W, S, ncon, S.warm, S.as);
@@ -1359,6 +1351,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
     END_DLANES
   }
   REGROUP();
+  PHASE_ALIGN(16);
   PHASE(W, 11);
   // ---- S5: line search (BD.10) ----
   // J.search per row, the Gauss-term sums and the constraint sums of the starting point alpha = 0

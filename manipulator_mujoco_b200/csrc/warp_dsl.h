@@ -65,7 +65,7 @@ static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); retur
 // Keep the live warps of a CTA on the same code (instruction-cache locality): named barrier 1 with the
 // live thread count of this CTA (a CTA may run fewer samples than its launch width, see
 // cemk_rollout_cost).  The two groups of a warp re-converge first (bar.sync is a per-warp instruction).
-#define CTA_ALIGN(W) do { __syncwarp(); asm volatile("bar.sync 1, %0;" :: "r"((W).nthr) : "memory"); } while (0)
+#define CTA_ALIGN(W) do { __syncwarp(); asm volatile("bar.sync %0, %1;" :: "r"((W).bar), "r"((W).nthr) : "memory"); } while (0)
 #ifdef CEMK_STEP_SYNC
 #define STEP_ALIGN() CTA_ALIGN(W)
 #else
@@ -108,7 +108,8 @@ struct WarpCtx {
   int lane;          // lane within the group, 0..KW-1
   int shift;         // first lane of the group within the warp (0 or 16)
   unsigned mask;     // member mask of the group
-  int nthr;          // live threads of this CTA (barrier width)
+  int nthr;          // threads of this warp's alignment set (barrier width)
+  int bar;           // named barrier of the alignment set (1 ..)
 #ifdef CEMK_PHASE_TIMING
   long long t0; int phase; long long ph[24];
 #endif
