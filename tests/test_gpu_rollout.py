@@ -65,7 +65,7 @@ def test_fused_cost_equals_standalone_cost(planner16):
 
 def test_results_do_not_depend_on_batch_size_or_cta_variant():
     """Samples are independent: the same sample must give bit-identical results whether it runs in a
-    batch of 100 (4-warp CTAs), 1000 (8-warp CTAs) or 2300 (14/16-warp CTAs, padded last CTA)."""
+    batch of 100, 1000 or 2300 (different kernel instantiations, CTA shares and a partly filled last CTA)."""
     from manipulator_mujoco_b200 import cem_planner
     T = 24
     pr, z, xi, st, xif, td = planner_inputs(T, 2300, seed=9)
@@ -81,6 +81,35 @@ def test_results_do_not_depend_on_batch_size_or_cta_variant():
     np.testing.assert_array_equal(outs[1000][1], outs[2300][1][:1000])
 
 
+def test_results_do_not_depend_on_the_partner_sample_or_odd_batch_sizes():
+    """Two samples share a warp (16-lane groups).  A sample's result must not depend on which sample it is
+    paired with, on which half of the warp it runs, or on partly filled warps / CTAs (odd batch sizes)."""
+    from manipulator_mujoco_b200 import cem_planner
+    T, B = 40, 301
+    pr, z, xi, st, xif, td = planner_inputs(T, B, seed=21)
+    td = np.ascontiguousarray(td, dtype=np.float32)
+
+    def run(rows):
+        pl = cem_planner(num_dof=6, num_batch=len(rows), num_steps=T, timestep=0.05, maxiter_cem=1, num_elite=0.05,
+                         w_pos=20.0, w_rot=3.0, w_col=80.0, maxiter_projection=10)
+        theta, cost4, ep, er, col = pl._rollout(td[rows], Q0, np.zeros(6), TARGET_POS, TARGET_ROT, True)
+        return theta.cpu().numpy(), cost4.cpu().numpy(), col.cpu().numpy()
+
+    base = run(np.arange(B))
+    rev = run(np.arange(B)[::-1].copy())                       # other partner, other half of the warp
+    for a, b in zip(base, rev):
+        np.testing.assert_array_equal(a, b[::-1])
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(B)
+    shuf = run(perm)
+    for a, b in zip(base, shuf):
+        np.testing.assert_array_equal(a[perm], b)
+    for n in (1, 2, 3, 29, 57):                                # single group, odd counts, one full CTA + 1
+        sub = run(np.arange(n))
+        for a, b in zip(base, sub):
+            np.testing.assert_array_equal(a[:n], b)
+
+
 def test_big_capacity_kernel_agrees_with_fast_kernel():
     """`force_rerun` recomputes every sample with the 48-contact instantiation (the overflow path)."""
     from manipulator_mujoco_b200 import _lib, cem_planner
@@ -89,7 +118,7 @@ def test_big_capacity_kernel_agrees_with_fast_kernel():
                      w_pos=20.0, w_rot=3.0, w_col=80.0, maxiter_projection=10)
     pr, z, xi, st, xif, td = planner_inputs(T, B, seed=11)
     a = pl._rollout(td, Q0, np.zeros(6), TARGET_POS, TARGET_ROT, True)
-    assert int(pl._buf("flags", (B,), __import__("torch").int32).max()) == 0      # nothing overflowed 24 contacts
+    assert int(pl._buf("flags", (B,), __import__("torch").int32).max()) == 0      # nothing overflowed the fast kernel's contact capacity
     _lib.check(pl._lib.cemk_set_option(pl._h, b"force_rerun", 1), pl._lib)
     b = pl._rollout(td, Q0, np.zeros(6), TARGET_POS, TARGET_ROT, True)
     _lib.check(pl._lib.cemk_set_option(pl._h, b"force_rerun", 0), pl._lib)
