@@ -136,30 +136,28 @@ static_assert(((sizeof(KModel) + 15) & ~size_t(15)) + ROLLOUT_WARPS * GPW * size
               "rollout scratch exceeds the 227 KB of shared memory a CTA can have");
 
 // ---------------------------------------------------------------------------------------------- sampling
-// L = chol(cov + 0.003 I), lower, row-major [66][66]; one CTA.
+// L = chol(cov + 0.003 I), lower, row-major [66][66]; one CTA of 16 x 16 threads.  Right-looking on the
+// unscaled columns (A[i][k] -= A[i][j] A[k][j] / A[j][j], one barrier per column; column j is final after
+// step j), scaled by 1 / sqrt(A[j][j]) in a last pass.
 __global__ void __launch_bounds__(256) k_chol66(const float* __restrict__ cov, float* __restrict__ L) {
   __shared__ float A[NVAR][NVAR + 1];
-  for (int e = threadIdx.x; e < NVAR * NVAR; e += blockDim.x) {
-    int i = e / NVAR, j = e % NVAR;
-    A[i][j] = cov[e] + (i == j ? 0.003f : 0.f);
-  }
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  for (int i = ty; i < NVAR; i += 16)
+    for (int j = tx; j < NVAR; j += 16) A[i][j] = cov[i * NVAR + j] + (i == j ? 0.003f : 0.f);
   __syncthreads();
-  for (int j = 0; j < NVAR; ++j) {
-    const float d = sqrtf(A[j][j]);
-    __syncthreads();
-    for (int i = j + threadIdx.x; i < NVAR; i += blockDim.x) A[i][j] = (i == j) ? d : A[i][j] / d;
-    __syncthreads();
-    const int n = NVAR - j - 1;
-    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-      int i = j + 1 + e / n, k = j + 1 + e % n;
-      if (k <= i) A[i][k] -= A[i][j] * A[k][j];
+  for (int j = 0; j < NVAR - 1; ++j) {
+    const float p = 1.f / A[j][j];
+    for (int i = j + 1 + ty; i < NVAR; i += 16) {
+      const float aij = A[i][j] * p;
+      for (int k = j + 1 + tx; k <= i; k += 16) A[i][k] -= aij * A[k][j];
     }
     __syncthreads();
   }
-  for (int e = threadIdx.x; e < NVAR * NVAR; e += blockDim.x) {
-    int i = e / NVAR, j = e % NVAR;
-    L[e] = j <= i ? A[i][j] : 0.f;
-  }
+  for (int i = ty; i < NVAR; i += 16)
+    for (int j = tx; j < NVAR; j += 16) {
+      const float d = sqrtf(A[j][j]);
+      L[i * NVAR + j] = j > i ? 0.f : (i == j ? d : A[i][j] / d);
+    }
 }
 // xi[b][i] = mean[i] + sum_{j<=i} L[i][j] z[b][j]
 __global__ void __launch_bounds__(256) k_sample(int B, const float* __restrict__ z, const float* __restrict__ mean,
@@ -244,8 +242,9 @@ __global__ void __launch_bounds__(256) k_jax_normal(uint32_t k0, uint32_t k1, in
 }
 
 // ---------------------------------------------------------------------------------------------- projection
-// One thread per (sample, dof).  Q_inv of the reference is block diagonal per DOF, and with
-// A_c = [G_c; -G_c] the slack / residual / multiplier updates of mjx_planner.py:196-223 collapse to
+// One lane per (sample, dof) problem, four warps per group of 32 problems.  Q_inv of the reference is block
+// diagonal per DOF, and with A_c = [G_c; -G_c] the slack / residual / multiplier updates of
+// mjx_planner.py:196-223 collapse to
 //   u_c   = G_c x                                  c in {velocity, acceleration, position}
 //   e_c   = u_c - clip(u_c, -b_c, b_c)             (= res+ - res-; exactly 0 inside the bounds)
 //   h_c   = u_c + clip(u_c, -b_c, b_c)             (= (b - s+) - (b - s-))
@@ -254,19 +253,39 @@ __global__ void __launch_bounds__(256) k_jax_normal(uint32_t k0, uint32_t k1, in
 // i.e. the reference iteration with s and res eliminated.  e_c is formed per time step *before* the
 // transpose product -- forming G^T G x - G^T clip(.) instead cancels catastrophically in float32
 // (|G^T G| ~ 1e6 at T = 16).
-__global__ void __launch_bounds__(128) k_project(int B, int T, int iters, const float* __restrict__ G, const float* __restrict__ Kc,
-                                                 const float* __restrict__ xi, const float* __restrict__ state_term,
-                                                 float* __restrict__ xi_f, float* __restrict__ thetadot) {
-  extern __shared__ float sm[];
-  float* sG = sm;                        // [3][T][11]
-  float* sK = sm + 3 * T * NCOEF;        // Kpp[121] Kpe[55] bounds[3]
-  for (int e = threadIdx.x; e < 3 * T * NCOEF; e += blockDim.x) sG[e] = G[e];
-  for (int e = threadIdx.x; e < 179; e += blockDim.x) sK[e] = Kc[e];
+// Mapping: the 32 lanes of a warp hold 32 different problems and walk the same basis rows, so a row
+// (11 coefficients padded to 12 floats) costs three broadcast 128-bit shared-memory loads for 33 FMAs per
+// lane.  The time steps are dealt round-robin to the PROJ_SLICES warps of the CTA, which own the same 32
+// problems; their partial G^T e / G^T h are exchanged through shared memory and summed in a fixed order
+// (so all warps carry identical iterates).  One thread per problem alone gives a B200 only ~5 warps per
+// SM on a 1e5-long dependent FMA chain; splitting a problem over lanes instead makes every lane fetch its
+// own rows and runs into the shared-memory bandwidth.
+#ifndef PROJ_SLICES
+#define PROJ_SLICES 4
+#endif
+__global__ void __launch_bounds__(32 * PROJ_SLICES) k_project(int B, int T, int iters, const float* __restrict__ G,
+                                                              const float* __restrict__ Kc, const float* __restrict__ xi,
+                                                              const float* __restrict__ state_term, float* __restrict__ xi_f,
+                                                              float* __restrict__ thetadot) {
+  extern __shared__ __align__(16) float sm[];
+  float* sG = sm;                        // [3][T][12]
+  float* sKpp = sm + 3 * T * 12;         // [11][12]
+  float* sK = sKpp + NCOEF * 12;         // Kpe[55] bounds[3], padded to 60
+  float* sX = sK + 60;                   // [PROJ_SLICES][22][32] partial sums
+  for (int e = threadIdx.x; e < 3 * T * 12; e += blockDim.x) { const int r = e / 12, k = e % 12; sG[e] = k < NCOEF ? G[r * NCOEF + k] : 0.f; }
+  for (int e = threadIdx.x; e < NCOEF * 12; e += blockDim.x) { const int r = e / 12, k = e % 12; sKpp[e] = k < NCOEF ? Kc[r * NCOEF + k] : 0.f; }
+  for (int e = threadIdx.x; e < 58; e += blockDim.x) sK[e] = Kc[121 + e];
   __syncthreads();
-  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= B * 6) return;
-  const int b = gid / 6, d = gid % 6;
-  const float* Kpp = sK; const float* Kpe = sK + 121; const float* bnd = sK + 176;
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  int prob = blockIdx.x * 32 + lane;
+  const bool act = prob < B * 6;         // idle lanes of the last CTA still take part in the barriers
+  if (!act) prob = B * 6 - 1;
+  const int b = prob / 6, d = prob % 6;
+  const float* Kpe = sK; const float* bnd = sK + 55;
+  auto row12 = [](const float* p, float* g) {
+    const float4 a = reinterpret_cast<const float4*>(p)[0], b4 = reinterpret_cast<const float4*>(p)[1], c4 = reinterpret_cast<const float4*>(p)[2];
+    g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w; g[4] = b4.x; g[5] = b4.y; g[6] = b4.z; g[7] = b4.w; g[8] = c4.x; g[9] = c4.y; g[10] = c4.z;
+  };
   float x[NCOEF], lam[NCOEF], xs[NCOEF], beq[5], cst[NCOEF], rh[NCOEF], re[NCOEF];
 #pragma unroll
   for (int k = 0; k < NCOEF; ++k) { xs[k] = xi[(size_t)b * NVAR + d * NCOEF + k]; lam[k] = 0.f; x[k] = 0.f; rh[k] = 0.f; }
@@ -279,12 +298,13 @@ __global__ void __launch_bounds__(128) k_project(int B, int T, int iters, const 
 #pragma unroll
     for (int k = 0; k < NCOEF; ++k) { rhs[k] = lam[k] + xs[k] + rh[k]; rh[k] = 0.f; re[k] = 0.f; }
 #pragma unroll
-    for (int i = 0; i < NCOEF; ++i) { float s = cst[i]; for (int k = 0; k < NCOEF; ++k) s += Kpp[i * NCOEF + k] * rhs[k]; x[i] = s; }
+    for (int i = 0; i < NCOEF; ++i) { float kr[NCOEF]; row12(sKpp + i * 12, kr); float s = cst[i]; for (int k = 0; k < NCOEF; ++k) s += kr[k] * rhs[k]; x[i] = s; }
     for (int c = 0; c < 3; ++c) {
       const float bc = bnd[c];
-      const float* Gc = sG + c * T * NCOEF;
-      for (int t = 0; t < T; ++t) {
-        const float* g = Gc + t * NCOEF;
+      const float* Gc = sG + c * T * 12;
+      for (int t = slice; t < T; t += PROJ_SLICES) {
+        float g[NCOEF];
+        row12(Gc + t * 12, g);
         float u = 0.f;
 #pragma unroll
         for (int k = 0; k < NCOEF; ++k) u += g[k] * x[k];
@@ -294,18 +314,35 @@ __global__ void __launch_bounds__(128) k_project(int B, int T, int iters, const 
         for (int k = 0; k < NCOEF; ++k) { re[k] += g[k] * e; rh[k] += g[k] * h; }
       }
     }
+    // exchange the partial sums of the slices
+    float* mine = sX + slice * 22 * 32 + lane;
 #pragma unroll
-    for (int k = 0; k < NCOEF; ++k) lam[k] -= re[k];
+    for (int k = 0; k < NCOEF; ++k) { mine[k * 32] = re[k]; mine[(NCOEF + k) * 32] = rh[k]; }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NCOEF; ++k) {
+      float se = 0.f, sh = 0.f;
+#pragma unroll
+      for (int q = 0; q < PROJ_SLICES; ++q) { se += sX[(q * 22 + k) * 32 + lane]; sh += sX[(q * 22 + NCOEF + k) * 32 + lane]; }
+      re[k] = se; rh[k] = sh;
+      lam[k] -= se;
+    }
+    __syncthreads();
   }
+  if (!act) return;
+  if (slice == 0) {
 #pragma unroll
-  for (int k = 0; k < NCOEF; ++k) xi_f[(size_t)b * NVAR + d * NCOEF + k] = x[k];
+    for (int k = 0; k < NCOEF; ++k) xi_f[(size_t)b * NVAR + d * NCOEF + k] = x[k];
+  }
   if (thetadot) {
     const float* Gv = sG;    // Pdot
     float* out = thetadot + (size_t)b * 6 * T + (size_t)d * T;
-    for (int t = 0; t < T; ++t) {
+    for (int t = slice; t < T; t += PROJ_SLICES) {
+      float g[NCOEF];
+      row12(Gv + t * 12, g);
       float u = 0.f;
 #pragma unroll
-      for (int k = 0; k < NCOEF; ++k) u += Gv[t * NCOEF + k] * x[k];
+      for (int k = 0; k < NCOEF; ++k) u += g[k] * x[k];
       out[t] = u;
     }
   }
@@ -514,7 +551,7 @@ int cemk_set_horizon(cemk_handle* h, int T, const float* G, const float* Kpp, co
   memcpy(kc, Kpp, 121 * 4); memcpy(kc + 121, Kpe, 55 * 4); memcpy(kc + 176, bounds3, 12);
   CK(cudaMemcpy(h->d_K, kc, sizeof kc, cudaMemcpyHostToDevice));
   h->T = T;
-  const int smem = (3 * T * NCOEF + 179) * (int)sizeof(float);
+  const int smem = (3 * T * 12 + NCOEF * 12 + 60 + PROJ_SLICES * 22 * 32) * (int)sizeof(float);
   CK(cudaFuncSetAttribute(k_project, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   return CEMK_OK;
 }
@@ -541,8 +578,8 @@ int cemk_jax_normal(cemk_handle* h, unsigned key0, unsigned key1, int original, 
 int cemk_project(cemk_handle* h, int B, int iters, const float* xi, const float* state_term, float* xi_f, float* thetadot, void* stream) {
   if (!h || !xi || !state_term || !xi_f || B <= 0 || iters < 1) return set_err(CEMK_ERR_ARG, "cemk_project: bad argument");
   if (!h->d_G) return set_err(CEMK_ERR_ARG, "cemk_project: cemk_set_horizon has not been called");
-  const int T = h->T, smem = (3 * T * NCOEF + 179) * (int)sizeof(float);
-  k_project<<<(B * 6 + 127) / 128, 128, smem, (cudaStream_t)stream>>>(B, T, iters, h->d_G, h->d_K, xi, state_term, xi_f, thetadot);
+  const int T = h->T, smem = (3 * T * 12 + NCOEF * 12 + 60 + PROJ_SLICES * 22 * 32) * (int)sizeof(float);
+  k_project<<<(B * 6 + 31) / 32, 32 * PROJ_SLICES, smem, (cudaStream_t)stream>>>(B, T, iters, h->d_G, h->d_K, xi, state_term, xi_f, thetadot);
   h->launches += 1;
   CK(cudaPeekAtLastError());
   return CEMK_OK;
