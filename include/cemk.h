@@ -68,8 +68,8 @@ int cemk_project(cemk_handle* h, int B, int maxiter_projection, const float* xi,
  *   theta[B][6T] (post-step joint angles, dof-major), cost4[B][4] = (cost, cost_g, cost_r, cost_c).
  *   Optional per-step dumps (pass NULL to skip): eef_pos[B][T][3], eef_rot[B][T][4],
  *   collision[B][T][nslot_robot] (pre-step, mjx_planner.py:259-261), qacc[B][T][12],
- *   flags[B] (bit 0: more than 48 simultaneously active contacts even in the re-run kernel, extra ones
- *   dropped; samples exceeding the fast kernel's capacity of 24 are transparently recomputed). */
+ *   flags[B] (bit 0: more than 48 simultaneously active contacts, extra ones dropped; up to 20 contacts of
+ *   a sample live in shared memory, contacts 21..48 in a library-owned global spill area). */
 int cemk_rollout_cost(cemk_handle* h, int B, int T, const float* thetadot, const float* q0, const float* v0,
                       const float* target_pos, const float* target_rot, float w_pos, float w_rot, float w_col,
                       float* theta, float* cost4, float* eef_pos, float* eef_rot, float* collision, float* qacc,
@@ -99,8 +99,9 @@ int cemk_mean_cov(cemk_handle* h, int k, const float* cost_elite, const float* x
                   const float* cov_prev, float lamda, float alpha_mean, float alpha_cov, float* mean_out, float* cov_out,
                   void* stream);
 
-/* Options.  "force_rerun" (0/1): recompute every sample with the big-capacity (48 contacts) rollout kernel,
- * used by the tests to check that it agrees bit for bit with the fast kernel.  "cta_samples" (0..28): fixed
+/* Options.  "force_rerun" (0/1): recompute every sample with the rollout instantiation that keeps all 48
+ * contacts in shared memory, used by the tests to check that it agrees bit for bit with the fast kernel
+ * and its spill area.  "cta_samples" (0..28): fixed
  * number of samples per CTA of the rollout kernel for A/B timing (0 = the library's own choice); never
  * changes a result. */
 int cemk_set_option(cemk_handle* h, const char* name, int value);

@@ -46,6 +46,7 @@ struct cemk_handle {
   long long launches;
   int* d_flags; int flags_cap; int num_sms;
   float* d_prevd; int prevd_cap;   // previous-step slot distances of every sample (rollout scratch, stays in L2)
+  float* d_ovf;                    // contact spill area of every sample (same capacity as d_prevd)
   int force_rerun;               // debug option: recompute every sample with the big-capacity kernel
   int cta_warps;                 // debug option "cta_samples": fixed number of samples per CTA (0 = see cemk_rollout_cost)
 };
@@ -60,6 +61,7 @@ struct RolloutBatch {
   float w_pos, w_rot, w_col;
   float* theta; float* cost4; float* eef_pos; float* eef_rot; float* collision; float* qacc; int* flags;
   float* prevd;                  // [B][2 * KM_NPASS][KW] previous-step slot distances (library scratch)
+  float* ovf;                    // [B][KM_NC_TOT - KM_NC_FAST][KM_OVF_STRIDE] contact spill area (library scratch)
   // CTA -> samples: the first n_hi CTAs run w_hi samples each, the others w_lo (both <= the launch width);
   // warps beyond a CTA's share exit at once
   int n_hi, w_hi, w_lo;
@@ -124,6 +126,7 @@ __global__ void __launch_bounds__(WARPS * 32, ROLLOUT_MINB) k_rollout(const KMod
   A.qacc_dbg = a.qacc ? a.qacc + (size_t)s * a.T * KM_NV : nullptr;
   A.flags = a.flags + s;
   A.prevd = a.prevd + (size_t)s * (2 * KM_NPASS * KW);
+  A.ovf = a.ovf + (size_t)s * ((KM_NC_TOT - KM_NC_FAST) * KM_OVF_STRIDE);
   rollout_sample<NC>(W, *sm, ws[group], A);
 #ifdef CEMK_PHASE_TIMING
   PHASE(W, 15);
@@ -512,7 +515,7 @@ int cemk_create(const void* kmodel, int kmodel_bytes, int device, cemk_handle** 
     return set_err(CEMK_ERR_MODEL, "cemk_create: unsupported topology");
   CK(cudaSetDevice(device));
   cemk_handle* h = new cemk_handle();
-  h->device = device; h->T = 0; h->d_G = nullptr; h->d_K = nullptr; h->launches = 0; h->d_flags = nullptr; h->flags_cap = 0; h->force_rerun = 0; h->cta_warps = 0; h->d_prevd = nullptr; h->prevd_cap = 0;
+  h->device = device; h->T = 0; h->d_G = nullptr; h->d_K = nullptr; h->launches = 0; h->d_flags = nullptr; h->flags_cap = 0; h->force_rerun = 0; h->cta_warps = 0; h->d_prevd = nullptr; h->prevd_cap = 0; h->d_ovf = nullptr;
   { cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device)); h->num_sms = prop.multiProcessorCount; }
   CK(cudaMalloc(&h->d_model, sizeof(KModel)));
   CK(cudaMemcpy(h->d_model, kmodel, sizeof(KModel), cudaMemcpyHostToDevice));
@@ -529,7 +532,7 @@ int cemk_create(const void* kmodel, int kmodel_bytes, int device, cemk_handle** 
 int cemk_destroy(cemk_handle* h) {
   if (!h) return CEMK_OK;
   cudaSetDevice(h->device);
-  cudaFree(h->d_model); cudaFree(h->d_G); cudaFree(h->d_K); cudaFree(h->d_flags); cudaFree(h->d_prevd);
+  cudaFree(h->d_model); cudaFree(h->d_G); cudaFree(h->d_K); cudaFree(h->d_flags); cudaFree(h->d_prevd); cudaFree(h->d_ovf);
   delete h;
   return CEMK_OK;
 }
@@ -608,9 +611,12 @@ int cemk_rollout_cost(cemk_handle* h, int B, int T, const float* thetadot, const
     CK(cudaSetDevice(h->device));
     if (h->d_prevd) CK(cudaFree(h->d_prevd));
     CK(cudaMalloc(&h->d_prevd, sizeof(float) * (size_t)B * 2 * KM_NPASS * KW));
+    if (h->d_ovf) CK(cudaFree(h->d_ovf));
+    CK(cudaMalloc(&h->d_ovf, sizeof(float) * (size_t)B * (KM_NC_TOT - KM_NC_FAST) * KM_OVF_STRIDE));
     h->prevd_cap = B;
   }
   a.prevd = h->d_prevd;
+  a.ovf = h->d_ovf;
   // Samples per CTA (a warp carries GPW = 32 / KW of them).  One CTA is resident per SM and its warps step
   // in lockstep, so the time of a wave grows with the warps per SM sub-partition (4 schedulers):
   //  * up to 4 / 8 warps-worth of samples per SM: the 4- / 8-warp instantiations (more registers per
@@ -642,11 +648,14 @@ int cemk_rollout_cost(cemk_handle* h, int B, int T, const float* thetadot, const
     CEMK_LAUNCH_ROLLOUT(ROLLOUT_WARPS);
   }
 #undef CEMK_LAUNCH_ROLLOUT
-  // samples whose active-contact list overflowed the fast capacity are recomputed with the big one
-  if (h->force_rerun) CK(cudaMemsetAsync(flags, 1, sizeof(int) * B, st));      // 0x01010101: bit 0 set
-  a.n_hi = 0; a.w_hi = a.w_lo = GPW;
-  k_rollout<KM_NC_BIG, 1, true><<<(B + GPW - 1) / GPW, 32, rollout_smem<KM_NC_BIG, 1>(), st>>>(h->d_model, a);
-  h->launches += 2;
+  h->launches += 1;
+  // debug option: recompute every sample with the all-in-shared-memory instantiation (no spill area)
+  if (h->force_rerun) {
+    CK(cudaMemsetAsync(flags, 1, sizeof(int) * B, st));                        // 0x01010101: bit 0 set
+    a.n_hi = 0; a.w_hi = a.w_lo = GPW;
+    k_rollout<KM_NC_BIG, 1, true><<<(B + GPW - 1) / GPW, 32, rollout_smem<KM_NC_BIG, 1>(), st>>>(h->d_model, a);
+    h->launches += 1;
+  }
   CK(cudaPeekAtLastError());
   return CEMK_OK;
 }

@@ -29,6 +29,9 @@
 #endif
 #define KM_NC_FAST (KW == 16 ? 20 : 24)   // active-contact capacity of the fast kernel (shared-memory budget per sample)
 #define KM_NPASS (KM_MAXRPAIR / KW)         // collider passes over the robot pair table
+#define KM_NC_TOT 48                      // contacts a sample can have in total: the ones beyond the shared-memory capacity
+                                          // spill to a per-sample global (L2) area
+#define KM_OVF_STRIDE 80                  // floats per spilled contact: geo 16, J 36, dots 2x3, rows 4x4
 #define KM_NC_BIG 48                      // capacity of the re-run kernel for samples that overflowed
 #define MJ_MINVAL 1e-15f
 #define MJ_MINIMP 0.0001f
@@ -78,6 +81,27 @@ struct WarpSmemT {
   float cd[2][NC][3];                 // per contact: Jn.v, mu*Jt1.v, mu*Jt2.v for up to two vectors v
   int limdof[KM_NL];
   float limsign[KM_NL];
+  float* ovf;                         // spill area of this sample for contacts NC .. KM_NC_TOT-1: [KM_NC_TOT - NC][KM_OVF_STRIDE]
+  float* ovf_pad;                     // (keeps the record a multiple of 16 bytes)
+
+  // Per-contact / per-row storage: shared memory for the first NC contacts, the spill area beyond.  Samples
+  // with more than NC simultaneous contacts are rare (deep-collision trajectories); they run in the same
+  // kernel at the price of L2 accesses for the extra contacts instead of a serial re-run afterwards.
+  // SP = false: the caller knows nothing is spilled -- plain shared-memory addressing (an address that may
+  // point to either space would turn every access into a generic load).
+  template <bool SP> KMEM float* geo(int c) const { return (!SP || c < NC) ? const_cast<float*>(cgeo[c]) : ovf + (c - NC) * KM_OVF_STRIDE; }
+  template <bool SP> KMEM float* jac(int c) const { return (!SP || c < NC) ? const_cast<float*>(cJ[c]) : ovf + (c - NC) * KM_OVF_STRIDE + 16; }
+  template <bool SP> KMEM float* dots(int set, int c) const {
+    return (!SP || c < NC) ? const_cast<float*>(cd[set][c]) : ovf + (c - NC) * KM_OVF_STRIDE + 52 + 3 * set;
+  }
+  template <bool SP> KMEM float& row(const float* arr, int off, int r, int nl) const {
+    const int rc = r - nl;              // rows nl + 4 c + q belong to contact c; limit rows (rc < 0) are always in shared memory
+    return (!SP || rc < 4 * NC) ? const_cast<float*>(arr)[r] : ovf[((rc >> 2) - NC) * KM_OVF_STRIDE + off + (rc & 3)];
+  }
+  template <bool SP> KMEM float& D(int r, int nl) const { return row<SP>(rD, 58, r, nl); }
+  template <bool SP> KMEM float& Aref(int r, int nl) const { return row<SP>(rAref, 62, r, nl); }
+  template <bool SP> KMEM float& Jaref(int r, int nl) const { return row<SP>(rJaref, 66, r, nl); }
+  template <bool SP> KMEM float& Jv(int r, int nl) const { return row<SP>(rJv, 70, r, nl); }
 };
 
 typedef WarpCtx<LaneRegs> Warp;
@@ -706,39 +730,32 @@ KFN void jac_col(const KModel& m, const WarpSmemT<NC>& S, const float* p, int li
     cross3(col, r, off);
   }
 }
-template <int NC>
-KFN float row_J(const WarpSmemT<NC>& S, int r, int d) {
-  if (r < S.nlim) return S.limdof[r] == d ? S.limsign[r] : 0.f;
-  int c = (r - S.nlim) >> 2, q = (r - S.nlim) & 3;
-  float jn = S.cJ[c][d], jt = S.cJ[c][(q < 2 ? 12 : 24) + d];
-  return (q & 1) ? jn - jt : jn + jt;
-}
 
 // Dense 6x6 SPD solve in registers, executed redundantly by every lane (uniform): for matrices this
 // small a straight-line Cholesky beats a lane-distributed one, whose ~50 dependent shuffles cost more
 // than the arithmetic (measured: profiles/README.md).  A: lower triangle read with row stride `ld`.
 // The 4 pyramid rows of a contact are Jn +- mu*Jt1, Jn +- mu*Jt2: three dot products per contact (one
 // (contact, component) item per lane) give all four J_r . v.
-template <int NC>
+template <int NC, bool SP>
 KFN void contact_dots(Warp& W, WarpSmemT<NC>& S, int ncon, const float* v0, const float* v1) {
   LANES(W, R)
 #pragma unroll 1
     for (int e = lane; e < 3 * ncon; e += KW) {
       const int c = e / 3, k = e - 3 * c;
-      const float* J = S.cJ[c] + 12 * k;
+      const float* J = S.template jac<SP>(c) + 12 * k;
       float s0 = 0.f, s1 = 0.f;
 #pragma unroll
       for (int d = 0; d < KM_NV; ++d) { s0 += J[d] * v0[d]; if (v1) s1 += J[d] * v1[d]; }
-      S.cd[0][c][k] = s0;
-      if (v1) S.cd[1][c][k] = s1;
+      S.template dots<SP>(0, c)[k] = s0;
+      if (v1) S.template dots<SP>(1, c)[k] = s1;
     }
   END_LANES
 }
-template <int NC>
+template <int NC, bool SP>
 KFN float row_val(const WarpSmemT<NC>& S, int set, int r, const float* v) {
   if (r < S.nlim) return S.limsign[r] * v[S.limdof[r]];
   const int c = (r - S.nlim) >> 2, q = (r - S.nlim) & 3;
-  const float dn = S.cd[set][c][0], dt = S.cd[set][c][q < 2 ? 1 : 2];
+  const float dn = S.template dots<SP>(set, c)[0], dt = S.template dots<SP>(set, c)[q < 2 ? 1 : 2];
   return (q & 1) ? dn - dt : dn + dt;
 }
 
@@ -799,20 +816,20 @@ KFN void chol_solve_rows(Warp& W) {
 
 // sum over the contacts in `sel` (bit c = contact c; contacts >= 32 exist only in the 48-contact re-run
 // kernel and are all visited) of the Hessian contribution of the four pyramid rows to entry (i, j)
-template <int NC>
+template <int NC, bool SP>
 KFN float hess_contacts(const WarpSmemT<NC>& S, unsigned sel, int ncon, int i, int j) {
   float h = 0.f;
 #pragma unroll 1
   for (unsigned rem = sel; rem != 0u; rem &= rem - 1u) {
     const int c = KFFS(rem) - 1;
-    const float* g = S.cgeo[c]; const float* J = S.cJ[c];
+    const float* g = S.template geo<SP>(c); const float* J = S.template jac<SP>(c);
     const float ni = J[i], nj = J[j], ai = J[12 + i], aj = J[12 + j], bi = J[24 + i], bj = J[24 + j];
     h += g[3] * (ni + ai) * (nj + aj) + g[4] * (ni - ai) * (nj - aj) + g[5] * (ni + bi) * (nj + bj) + g[6] * (ni - bi) * (nj - bj);
   }
-  if (NC > 32) {
+  if (KM_NC_TOT > 32) {
 #pragma unroll 1
     for (int c = 32; c < ncon; ++c) {
-      const float* g = S.cgeo[c]; const float* J = S.cJ[c];
+      const float* g = S.template geo<SP>(c); const float* J = S.template jac<SP>(c);
       const float ni = J[i], nj = J[j], ai = J[12 + i], aj = J[12 + j], bi = J[24 + i], bj = J[24 + j];
       h += g[3] * (ni + ai) * (nj + aj) + g[4] * (ni - ai) * (nj - aj) + g[5] * (ni + bi) * (nj + bj) + g[6] * (ni - bi) * (nj - bj);
     }
@@ -860,8 +877,8 @@ KNOINLINE void emit_robot_contacts(const KModel& m, WarpSmemT<NC>& S, int lane, 
 #pragma unroll 1
     for (int k = 0; k < 2; ++k) {
       if (!((bits >> k) & 1)) continue;
-      if (o < NC) {
-        float* g = S.cgeo[o];
+      if (o < KM_NC_TOT) {
+        float* g = S.template geo<true>(o);       // rare path: a pointer into either space is fine here
         copy3(g, c.pos[k]); copy3(g + 3, c.nrm[k]);
         if (own_t1) { copy3(g + 6, pt1); cross3(g + 9, c.nrm[k], pt1); }
         else make_tangents(c.nrm[k], g + 6, g + 9);
@@ -877,6 +894,284 @@ struct StepIO {
   float* collision_row;       // optional dump of this step's robot-slot distances [nslot_robot]
   float* prevd;               // this sample's previous-step distances, [2 * KM_NPASS][KW] (global scratch, L2-resident)
 };
+
+// ------------------------------------------------------------------------------------------ constraint solve
+// C2 .. S5 of one forward(): rows of the active constraints, Newton direction, line search.  SP = true is
+// the instantiation for a sample whose contact list does not fit shared memory (spill area, see WarpSmemT).
+template <int NC, bool SP>
+KFN void solve_rows(Warp& W, const KModel& m, WarpSmemT<NC>& S, const int ncon, const int nlim, const int nrow) {
+  PHASE(W, 16);
+  // ---- C2: contact Jacobians in the contact frame: Jn, mu*Jt1, mu*Jt2 ----
+  LANES(W, R)
+    const int d = lane & 15;
+    if (d < KM_NV) {
+#pragma unroll 1
+      for (int c = lane >> 4; c < ncon; c += KW / 16) {
+        const float* g = S.template geo<SP>(c);
+        float c1[3], c2[3], df[3];
+        jac_col(m, S, g, (int)g[14], d, c1);
+        jac_col(m, S, g, (int)g[15], d, c2);
+        sub3(df, c2, c1);
+        S.template jac<SP>(c)[d] = dot3(g + 3, df);
+        S.template jac<SP>(c)[12 + d] = m.mu * dot3(g + 6, df);
+        S.template jac<SP>(c)[24 + d] = m.mu * dot3(g + 9, df);
+      }
+    }
+  END_LANES
+  PHASE(W, 17);
+  // ---- C3: contact row parameters (the 4 pyramid edges share pos and D) ----
+  contact_dots<NC, SP>(W, S, ncon, S.qvel, nullptr);
+  LANES(W, R)
+#pragma unroll 1
+    for (int r = nlim + lane; r < nrow; r += KW) {
+      const float* g = S.template geo<SP>((r - nlim) >> 2);
+      float w = g[13];
+      w = w + m.mu * m.mu * w;
+      w = w * 2.f * m.mu * m.mu / m.impratio;
+      float vel = row_val<NC, SP>(S, 0, r, S.qvel), D, aref;
+      row_params(m, g[12], w, vel, D, aref);
+      S.template D<SP>(r, nlim) = D; S.template Aref<SP>(r, nlim) = aref;
+    }
+    // does any active contact join a robot link and the free box?  (then H is a full 12x12)
+    R.f2 = 0.f;
+    for (int c = lane; c < ncon; c += KW) {
+      const int l1 = (int)S.template geo<SP>(c)[14], l2 = (int)S.template geo<SP>(c)[15];
+      if ((l1 == KM_NL && l2 >= 0 && l2 < KM_NL) || (l2 == KM_NL && l1 >= 0 && l1 < KM_NL)) R.f2 = 1.f;
+    }
+  END_LANES
+  const bool coupled = warp_sum(W, [](int, LaneRegs& R) { return R.f2; }) > 0.f;
+  PHASE_ALIGN(8);
+  PHASE(W, 8);
+  // ---- S1: warm start vs smooth start (B.6) ----
+  contact_dots<NC, SP>(W, S, ncon, S.warm, S.as);
+  LANES(W, R)
+    float cw = 0.f, cs = 0.f;
+#pragma unroll 1
+    for (int r = lane; r < nrow; r += KW) {
+      const float ar = S.template Aref<SP>(r, nlim), Dr = S.template D<SP>(r, nlim);
+      float jw = row_val<NC, SP>(S, 0, r, S.warm) - ar, js = row_val<NC, SP>(S, 1, r, S.as) - ar;
+      S.template Jaref<SP>(r, nlim) = jw; S.template Jv<SP>(r, nlim) = js;
+      if (jw < 0.f) cw += 0.5f * Dr * jw * jw;
+      if (js < 0.f) cs += 0.5f * Dr * js * js;
+    }
+    R.f0 = cw; R.f1 = cs; R.f2 = 0.f;
+    if (lane < KM_NV) {
+      float ma = mul_M<NC>(m, S, lane, S.warm);
+      S.Ma[lane] = ma;
+      R.f2 = 0.5f * (ma - S.fs[lane]) * (S.warm[lane] - S.as[lane]);
+    }
+  END_LANES
+  const float gauss_w = warp_sum(W, [](int, LaneRegs& R) { return R.f2; });
+  const float cost_w = warp_sum(W, [](int, LaneRegs& R) { return R.f0; }) + gauss_w;
+  const float cost_s = warp_sum(W, [](int, LaneRegs& R) { return R.f1; });
+  const bool use_warm = cost_w < cost_s;
+#ifdef CEMK_EMU_DEBUG
+  printf("[emu] nrow %d nlim %d ncon %d cost_w %.9g cost_s %.9g use_warm %d\n", nrow, nlim, ncon, cost_w, cost_s, (int)use_warm);
+#endif
+  const float gauss = use_warm ? gauss_w : 0.f;
+  LANES(W, R)
+    if (!use_warm) {
+      for (int r = lane; r < nrow; r += KW) S.template Jaref<SP>(r, nlim) = S.template Jv<SP>(r, nlim);
+      if (lane < KM_NV) {
+        S.Ma[lane] = mul_M<NC>(m, S, lane, S.as);
+      }
+    }
+    if (lane < KM_NV) S.qacc[lane] = use_warm ? S.warm[lane] : S.as[lane];
+  END_LANES
+  PHASE(W, 9);
+  // ---- S3: gradient and Hessian over the active rows (BD.9) ----
+  // per contact: the pyramid-edge weights w_q = D [Jaref_q < 0] and the force sums that multiply
+  // Jn, mu*Jt1, mu*Jt2; the contact position / frame slots of cgeo are dead after C2 and are reused.
+  LANES(W, R)
+#pragma unroll 1
+    for (int c = lane; c < ncon; c += KW) {
+      const int r0 = nlim + 4 * c;
+      float w[4], f[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const float ja = S.template Jaref<SP>(r0 + q, nlim); w[q] = ja < 0.f ? S.template D<SP>(r0 + q, nlim) : 0.f; f[q] = -w[q] * ja; }
+      float* g = S.template geo<SP>(c);
+      const int l1 = (int)g[14], l2 = (int)g[15];
+      g[0] = f[0] + f[1] + f[2] + f[3]; g[1] = f[0] - f[1]; g[2] = f[2] - f[3];
+      g[3] = w[0]; g[4] = w[1]; g[5] = w[2]; g[6] = w[3];
+      g[7] = __int_as_float((((l1 >= 0 && l1 < KM_NL) || (l2 >= 0 && l2 < KM_NL)) ? 1 : 0) | ((l1 == KM_NL || l2 == KM_NL) ? 2 : 0));
+    }
+  END_LANES
+  // which contacts touch the robot block / the box block (ncon <= 32: one bit per contact); the loops
+  // below then visit only the contacts that can contribute (typically: 4 box contacts, no robot contact)
+  const unsigned mrob = warp_ballot32(W, [&](int l) { return l < ncon && (__float_as_int(S.template geo<SP>(l)[7]) & 1); });
+  const unsigned mbox = warp_ballot32(W, [&](int l) { return l < ncon && (__float_as_int(S.template geo<SP>(l)[7]) & 2); });
+  LANES(W, R)
+    if (lane < KM_NV) {
+      float fc = 0.f;
+      for (int r = 0; r < nlim; ++r) { const float ja = S.rJaref[r]; if (ja < 0.f && S.limdof[r] == lane) fc += S.limsign[r] * (-S.rD[r] * ja); }
+#pragma unroll 1
+      for (unsigned rem = lane < KM_NL ? mrob : mbox; rem != 0u; rem &= rem - 1u) {
+        const int c = KFFS(rem) - 1;
+        const float* g = S.template geo<SP>(c); const float* J = S.template jac<SP>(c);
+        fc += J[lane] * g[0] + J[12 + lane] * g[1] + J[24 + lane] * g[2];
+      }
+      if (KM_NC_TOT > 32) {
+#pragma unroll 1
+        for (int c = 32; c < ncon; ++c) {        // only the 48-contact re-run kernel can get here
+          const float* g = S.template geo<SP>(c); const float* J = S.template jac<SP>(c);
+          fc += J[lane] * g[0] + J[12 + lane] * g[1] + J[24 + lane] * g[2];
+        }
+      }
+      S.grad[lane] = S.Ma[lane] - S.fs[lane] - fc;
+    }
+  END_LANES
+  // Hessian by blocks: lanes 0-20 own entry (i, j) of the 6x6 lower triangle and build it for the robot
+  // block and for the box block; the 36 robot/box cross entries exist only when a contact couples the two
+  // (otherwise the blocks are solved separately and the cross entries are never read).
+  LANES(W, R)
+#pragma unroll
+   for (int q = 0; q < 32 / KW; ++q) {
+    const int i = (R.tri >> (8 * q)) & 15, j = (R.tri >> (8 * q + 4)) & 15;
+    if (i < KM_NL) {
+      float hr = S.Mr[i][j];
+      for (int r = 0; r < nlim; ++r) if (S.rJaref[r] < 0.f && S.limdof[r] == i && i == j) hr += S.rD[r];
+      hr += hess_contacts<NC, SP>(S, mrob, ncon, i, j);
+      S.H[i][j] = hr;
+      float hb = i != j ? 0.f : (i < 3 ? m.fb_mass : (i == 3 ? m.fb_inertia[0] : (i == 4 ? m.fb_inertia[1] : m.fb_inertia[2])));
+      hb += hess_contacts<NC, SP>(S, mbox, ncon, KM_NL + i, KM_NL + j);
+      S.H[KM_NL + i][KM_NL + j] = hb;
+    }
+   }
+    if (coupled) {
+#pragma unroll 1
+      for (int e = lane; e < KM_NL * KM_NL; e += KW) {
+        const int i = KM_NL + e / KM_NL, j = e % KM_NL;
+        S.H[i][j] = hess_contacts<NC, SP>(S, mrob & mbox, ncon, i, j);
+      }
+    }
+  END_LANES
+  PHASE(W, 10);
+  // ---- S4: search = -H^-1 grad, Cholesky with one row per lane in registers.  Robot and box
+  //      blocks only couple through a robot/box contact; otherwise the two 6x6 blocks are factorised
+  //      side by side (6 column steps instead of 12) ----
+  {
+    USYNC();
+    const Vec6 xr = chol_solve6(&S.H[0][0], KM_NV, S.grad);
+    const Vec6 xb = chol_solve6(&S.H[KM_NL][KM_NL], KM_NV, S.grad + KM_NL);
+    UNIFORM_WRITE(W) {
+      for (int i = 0; i < KM_NL; ++i) { S.search[i] = -xr.v[i]; S.search[KM_NL + i] = -xb.v[i]; }
+    } END_UNIFORM_WRITE
+  }
+  if (coupled) {                                // rare: full 12x12 system (replaces the block solution above)
+    DLANES(W, R)
+#pragma unroll
+      for (int k = 0; k < KM_NV; ++k) R.h[k] = (lane < KM_NV && k <= lane) ? S.H[lane][k] : 0.f;
+      R.f0 = lane < KM_NV ? S.grad[lane] : 0.f;
+    END_DLANES
+    chol_solve_rows<12>(W);
+    DLANES(W, R)
+      if (lane < KM_NV) S.search[lane] = -R.f0;
+    END_DLANES
+  }
+  REGROUP();
+  PHASE_ALIGN(16);
+  PHASE(W, 11);
+  // ---- S5: line search (BD.10) ----
+  // J.search per row, the Gauss-term sums and the constraint sums of the starting point alpha = 0
+  // (MJX's p0) in one pass and one fused warp reduction
+  contact_dots<NC, SP>(W, S, ncon, S.search, nullptr);
+  LANES(W, R)
+    float e0 = 0.f, e1 = 0.f, e2 = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    if (lane < KM_NV) {
+      const float mv = mul_M<NC>(m, S, lane, S.search), s = S.search[lane];
+      e0 = s * s; e1 = s * S.Ma[lane] - s * S.fs[lane]; e2 = 0.5f * s * mv;
+    }
+#pragma unroll 1
+    for (int r = lane; r < nrow; r += KW) {
+      const float jv = row_val<NC, SP>(S, 0, r, S.search), ja = S.template Jaref<SP>(r, nlim), D = S.template D<SP>(r, nlim);
+      S.template Jv<SP>(r, nlim) = jv;
+      if (ja < 0.f) { a0 += 0.5f * D * ja * ja; a1 += D * jv * ja; a2 += 0.5f * D * jv * jv; }
+    }
+    R.acc[0] = e0; R.acc[1] = e1; R.acc[2] = e2; R.acc[3] = a0; R.acc[4] = a1; R.acc[5] = a2; R.acc[6] = R.acc[7] = R.acc[8] = 0.f;
+  END_LANES
+  float qg[3], gtol;
+  LSPoint p0, lo, hi;
+  {
+    float sums[9];
+    warp_sum9(W, sums);
+    qg[0] = gauss; qg[1] = sums[1]; qg[2] = sums[2];
+    gtol = m.tolerance * m.ls_tolerance * sqrtf(sums[0]) * m.meaninertia * (float)KM_NV;
+    const float q2 = qg[2] + sums[5];
+    p0.alpha = 0.f; p0.cost = qg[0] + sums[3]; p0.d0 = qg[1] + sums[4]; p0.d1 = 2.f * q2 + (q2 == 0.f ? MJ_MINVAL : 0.f);
+    lo = p0; hi = p0;
+  }
+  PHASE(W, 19);
+  // One rolled loop evaluates the piecewise quadratic at three step sizes per trip:
+  //   trip -1: lo = point(-p0.d0/p0.d1); trips 0..ls_iterations-1: MJX bracket update.
+  // The loop is warp-uniform: it runs until every sample of the warp is done; a sample that finished
+  // earlier idles through the remaining trips with its bracket frozen.
+  bool swapped = true, done = nrow == 0;
+#pragma unroll 1
+  for (int it = -1; it < m.ls_iterations; ++it) {
+    float al0, al1, al2;
+    if (it == -1) { al0 = al1 = al2 = p0.alpha - p0.d0 / p0.d1; }
+    else {
+      done = done || !swapped;
+      done = done || ((lo.d0 < 0.f) && (lo.d0 > -gtol));
+      done = done || ((hi.d0 > 0.f) && (hi.d0 < gtol));
+      if (warp_all_groups(W, done)) break;
+      al0 = lo.alpha - lo.d0 / lo.d1; al1 = hi.alpha - hi.d0 / hi.d1; al2 = 0.5f * (lo.alpha + hi.alpha);
+    }
+    LANES(W, R)
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+#pragma unroll 1
+      for (int r = lane; r < nrow; r += KW) {
+        const float ja = S.template Jaref<SP>(r, nlim), jv = S.template Jv<SP>(r, nlim), D = S.template D<SP>(r, nlim);
+        const float q0 = 0.5f * D * ja * ja, q1 = D * jv * ja, q2 = 0.5f * D * jv * jv;
+        if (ja + al0 * jv < 0.f) { a0 += q0; a1 += q1; a2 += q2; }
+        if (ja + al1 * jv < 0.f) { b0 += q0; b1 += q1; b2 += q2; }
+        if (ja + al2 * jv < 0.f) { c0 += q0; c1 += q1; c2 += q2; }
+      }
+      R.acc[0] = a0; R.acc[1] = a1; R.acc[2] = a2; R.acc[3] = b0; R.acc[4] = b1; R.acc[5] = b2; R.acc[6] = c0; R.acc[7] = c1; R.acc[8] = c2;
+    END_LANES
+    float sums[9];
+    warp_sum9(W, sums);
+    LSPoint pt[3];
+    const float als[3] = {al0, al1, al2};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float q0 = qg[0] + sums[3 * k], q1 = qg[1] + sums[3 * k + 1], q2 = qg[2] + sums[3 * k + 2];
+      const float a = als[k];
+      pt[k].alpha = a;
+      pt[k].cost = a * a * q2 + a * q1 + q0;
+      pt[k].d0 = 2.f * a * q2 + q1;
+      pt[k].d1 = 2.f * q2 + (q2 == 0.f ? MJ_MINVAL : 0.f);
+    }
+    if (it == -1) {
+      if (pt[0].d0 < p0.d0) { lo = pt[0]; hi = p0; } else { hi = pt[0]; lo = p0; }
+      continue;
+    }
+    if (done) continue;
+    const LSPoint lo_next = pt[0], hi_next = pt[1], mid = pt[2];
+    bool s1 = in_bracket(lo, lo_next); if (s1) lo = lo_next;
+    bool s2 = in_bracket(lo, mid);     if (s2) lo = mid;
+    bool s3 = in_bracket(lo, hi_next); if (s3) lo = hi_next;
+    bool s4 = in_bracket(hi, hi_next); if (s4) hi = hi_next;
+    bool s5 = in_bracket(hi, mid);     if (s5) hi = mid;
+    bool s6 = in_bracket(hi, lo_next); if (s6) hi = lo_next;
+    swapped = s1 || s2 || s3 || s4 || s5 || s6;
+#ifdef CEMK_EMU_DEBUG
+    printf("[emu]  it %d cand %.7g %.7g %.7g -> lo a %.7g d0 %.5g  hi a %.7g d0 %.5g swaps %d%d%d%d%d%d\n", it, al0, al1, al2, lo.alpha, lo.d0, hi.alpha, hi.d0, s1, s2, s3, s4, s5, s6);
+#endif
+  }
+  const bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
+#ifdef CEMK_EMU_DEBUG
+  printf("[emu] p0 cost %.9g d0 %.6g d1 %.6g | lo a %.7g cost %.9g d0 %.6g | hi a %.7g cost %.9g d0 %.6g | gtol %.3g\n", p0.cost, p0.d0, p0.d1, lo.alpha, lo.cost, lo.d0, hi.alpha, hi.cost, hi.d0, gtol);
+#endif
+  const float alpha = improved ? (lo.cost < hi.cost ? lo.alpha : hi.alpha) : 0.f;
+  LANES(W, R)
+    if (lane < KM_NV) {
+      float a = S.qacc[lane] + alpha * S.search[lane];
+      if (nrow == 0) a = S.as[lane];
+      S.qacc[lane] = a; S.warm[lane] = a;
+    }
+  END_LANES
+}
 
 // ------------------------------------------------------------------------------------------ one forward()
 // Inputs: S.qpos, S.qvel, S.warm.  Outputs: S.qacc (= new warm start), link frames, and the
@@ -1137,7 +1432,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
   const int nrob = warp_excl_scan(W, [](int, LaneRegs& R) { return R.nact; }, [](int, LaneRegs& R, int o) { R.off = o; });
   const unsigned bmask = m.has_box ? warp_ballot32(W, [&](int l) { return l < 4 * m.nbpair && S.bstage[l >> 2][l & 3][3] < 0.f; }) : 0u;
   const int ncon_all = nrob + KPOPC(bmask);
-  const int ncon = ncon_all < NC ? ncon_all : NC;
+  const int ncon = ncon_all < KM_NC_TOT ? ncon_all : KM_NC_TOT;
   PHASE(W, 6);
   // ---- N2: full contact records for the active slots (divergent, rare for robot slots) ----
   LANES(W, R)
@@ -1145,13 +1440,15 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
     for (int sl = lane; sl < 32; sl += KW) {
       if (!(bmask & (1u << sl))) continue;
       const int o = nrob + KPOPC(bmask & ((1u << sl) - 1u)), q = sl >> 2;
-      if (o < NC) {
+      if (o < KM_NC_TOT) {
         const bool sw = m.bp_type[q] == KB_BOX_BOX_SWAP;
-        float* g = S.cgeo[o];
         const float* st = S.bstage[q][sl & 3];
-        copy3(g, st); copy3(g + 3, S.bnrm[q]);
-        make_tangents(S.bnrm[q], g + 6, g + 9);
-        g[12] = st[3]; g[13] = m.fb_invw; g[14] = sw ? (float)KM_NL : -1.f; g[15] = sw ? -1.f : (float)KM_NL;
+        auto put = [&](float* g) {
+          copy3(g, st); copy3(g + 3, S.bnrm[q]);
+          make_tangents(S.bnrm[q], g + 6, g + 9);
+          g[12] = st[3]; g[13] = m.fb_invw; g[14] = sw ? (float)KM_NL : -1.f; g[15] = sw ? -1.f : (float)KM_NL;
+        };
+        if (o < NC) put(S.cgeo[o]); else put(S.template geo<true>(o));      // every step: keep the common case in shared-memory addressing
       }
     }
   END_LANES
@@ -1169,7 +1466,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
     }
   END_LANES
   const int nlim = warp_excl_scan(W, [](int, LaneRegs& R) { return R.nact; }, [](int, LaneRegs& R, int o) { R.off = o; });
-  UNIFORM_WRITE(W) { S.ncon = ncon; S.nlim = nlim; S.nrow = nlim + 4 * ncon; if (ncon_all > NC) S.flags |= 1; } END_UNIFORM_WRITE
+  UNIFORM_WRITE(W) { S.ncon = ncon; S.nlim = nlim; S.nrow = nlim + 4 * ncon; if (ncon_all > KM_NC_TOT) S.flags |= 1; } END_UNIFORM_WRITE
   const int nrow = nlim + 4 * ncon;
   // No active row (the box in free fall, first steps of a rollout): qacc = qacc_smooth.  Such a sample
   // still runs through the solver below with empty loops and takes qacc_smooth at the end, which keeps
@@ -1183,276 +1480,10 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
       S.rD[r] = D; S.rAref[r] = aref;
     }
   END_LANES
-  PHASE(W, 16);
-  // ---- C2: contact Jacobians in the contact frame: Jn, mu*Jt1, mu*Jt2 ----
-  LANES(W, R)
-    const int d = lane & 15;
-    if (d < KM_NV) {
-#pragma unroll 1
-      for (int c = lane >> 4; c < ncon; c += KW / 16) {
-        const float* g = S.cgeo[c];
-        float c1[3], c2[3], df[3];
-        jac_col(m, S, g, (int)g[14], d, c1);
-        jac_col(m, S, g, (int)g[15], d, c2);
-        sub3(df, c2, c1);
-        S.cJ[c][d] = dot3(g + 3, df);
-        S.cJ[c][12 + d] = m.mu * dot3(g + 6, df);
-        S.cJ[c][24 + d] = m.mu * dot3(g + 9, df);
-      }
-    }
-  END_LANES
-  PHASE(W, 17);
-  // ---- C3: contact row parameters (the 4 pyramid edges share pos and D) ----
-  contact_dots<NC>(W, S, ncon, S.qvel, nullptr);
-  LANES(W, R)
-#pragma unroll 1
-    for (int r = nlim + lane; r < nrow; r += KW) {
-      const float* g = S.cgeo[(r - nlim) >> 2];
-      float w = g[13];
-      w = w + m.mu * m.mu * w;
-      w = w * 2.f * m.mu * m.mu / m.impratio;
-      float vel = row_val<NC>(S, 0, r, S.qvel), D, aref;
-      row_params(m, g[12], w, vel, D, aref);
-      S.rD[r] = D; S.rAref[r] = aref;
-    }
-    // does any active contact join a robot link and the free box?  (then H is a full 12x12)
-    R.f2 = 0.f;
-    for (int c = lane; c < ncon; c += KW) {
-      const int l1 = (int)S.cgeo[c][14], l2 = (int)S.cgeo[c][15];
-      if ((l1 == KM_NL && l2 >= 0 && l2 < KM_NL) || (l2 == KM_NL && l1 >= 0 && l1 < KM_NL)) R.f2 = 1.f;
-    }
-  END_LANES
-  const bool coupled = warp_sum(W, [](int, LaneRegs& R) { return R.f2; }) > 0.f;
-  PHASE_ALIGN(8);
-  PHASE(W, 8);
-  // ---- S1: warm start vs smooth start (B.6) ----
-  contact_dots<NC>(W, S, ncon, S.warm, S.as);
-  LANES(W, R)
-    float cw = 0.f, cs = 0.f;
-#pragma unroll 1
-    for (int r = lane; r < nrow; r += KW) {
-      float jw = row_val<NC>(S, 0, r, S.warm) - S.rAref[r], js = row_val<NC>(S, 1, r, S.as) - S.rAref[r];
-      S.rJaref[r] = jw; S.rJv[r] = js;
-      if (jw < 0.f) cw += 0.5f * S.rD[r] * jw * jw;
-      if (js < 0.f) cs += 0.5f * S.rD[r] * js * js;
-    }
-    R.f0 = cw; R.f1 = cs; R.f2 = 0.f;
-    if (lane < KM_NV) {
-      float ma = mul_M<NC>(m, S, lane, S.warm);
-      S.Ma[lane] = ma;
-      R.f2 = 0.5f * (ma - S.fs[lane]) * (S.warm[lane] - S.as[lane]);
-    }
-  END_LANES
-  const float gauss_w = warp_sum(W, [](int, LaneRegs& R) { return R.f2; });
-  const float cost_w = warp_sum(W, [](int, LaneRegs& R) { return R.f0; }) + gauss_w;
-  const float cost_s = warp_sum(W, [](int, LaneRegs& R) { return R.f1; });
-  const bool use_warm = cost_w < cost_s;
-#ifdef CEMK_EMU_DEBUG
-  printf("[emu] nrow %d nlim %d ncon %d cost_w %.9g cost_s %.9g use_warm %d\n", nrow, nlim, ncon, cost_w, cost_s, (int)use_warm);
-#endif
-  const float gauss = use_warm ? gauss_w : 0.f;
-  LANES(W, R)
-    if (!use_warm) {
-      for (int r = lane; r < nrow; r += KW) S.rJaref[r] = S.rJv[r];
-      if (lane < KM_NV) {
-        S.Ma[lane] = mul_M<NC>(m, S, lane, S.as);
-      }
-    }
-    if (lane < KM_NV) S.qacc[lane] = use_warm ? S.warm[lane] : S.as[lane];
-  END_LANES
-  PHASE(W, 9);
-  // ---- S3: gradient and Hessian over the active rows (BD.9) ----
-  // per contact: the pyramid-edge weights w_q = D [Jaref_q < 0] and the force sums that multiply
-  // Jn, mu*Jt1, mu*Jt2; the contact position / frame slots of cgeo are dead after C2 and are reused.
-  LANES(W, R)
-#pragma unroll 1
-    for (int c = lane; c < ncon; c += KW) {
-      const int r0 = nlim + 4 * c;
-      float w[4], f[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) { const float ja = S.rJaref[r0 + q]; w[q] = ja < 0.f ? S.rD[r0 + q] : 0.f; f[q] = -w[q] * ja; }
-      float* g = S.cgeo[c];
-      const int l1 = (int)g[14], l2 = (int)g[15];
-      g[0] = f[0] + f[1] + f[2] + f[3]; g[1] = f[0] - f[1]; g[2] = f[2] - f[3];
-      g[3] = w[0]; g[4] = w[1]; g[5] = w[2]; g[6] = w[3];
-      g[7] = __int_as_float((((l1 >= 0 && l1 < KM_NL) || (l2 >= 0 && l2 < KM_NL)) ? 1 : 0) | ((l1 == KM_NL || l2 == KM_NL) ? 2 : 0));
-    }
-  END_LANES
-  // which contacts touch the robot block / the box block (ncon <= 32: one bit per contact); the loops
-  // below then visit only the contacts that can contribute (typically: 4 box contacts, no robot contact)
-  const unsigned mrob = warp_ballot32(W, [&](int l) { return l < ncon && (__float_as_int(S.cgeo[l][7]) & 1); });
-  const unsigned mbox = warp_ballot32(W, [&](int l) { return l < ncon && (__float_as_int(S.cgeo[l][7]) & 2); });
-  LANES(W, R)
-    if (lane < KM_NV) {
-      float fc = 0.f;
-      for (int r = 0; r < nlim; ++r) { const float ja = S.rJaref[r]; if (ja < 0.f && S.limdof[r] == lane) fc += S.limsign[r] * (-S.rD[r] * ja); }
-#pragma unroll 1
-      for (unsigned rem = lane < KM_NL ? mrob : mbox; rem != 0u; rem &= rem - 1u) {
-        const int c = KFFS(rem) - 1;
-        const float* g = S.cgeo[c]; const float* J = S.cJ[c];
-        fc += J[lane] * g[0] + J[12 + lane] * g[1] + J[24 + lane] * g[2];
-      }
-      if (NC > 32) {
-#pragma unroll 1
-        for (int c = 32; c < ncon; ++c) {        // only the 48-contact re-run kernel can get here
-          const float* g = S.cgeo[c]; const float* J = S.cJ[c];
-          fc += J[lane] * g[0] + J[12 + lane] * g[1] + J[24 + lane] * g[2];
-        }
-      }
-      S.grad[lane] = S.Ma[lane] - S.fs[lane] - fc;
-    }
-  END_LANES
-  // Hessian by blocks: lanes 0-20 own entry (i, j) of the 6x6 lower triangle and build it for the robot
-  // block and for the box block; the 36 robot/box cross entries exist only when a contact couples the two
-  // (otherwise the blocks are solved separately and the cross entries are never read).
-  LANES(W, R)
-#pragma unroll
-   for (int q = 0; q < 32 / KW; ++q) {
-    const int i = (R.tri >> (8 * q)) & 15, j = (R.tri >> (8 * q + 4)) & 15;
-    if (i < KM_NL) {
-      float hr = S.Mr[i][j];
-      for (int r = 0; r < nlim; ++r) if (S.rJaref[r] < 0.f && S.limdof[r] == i && i == j) hr += S.rD[r];
-      hr += hess_contacts<NC>(S, mrob, ncon, i, j);
-      S.H[i][j] = hr;
-      float hb = i != j ? 0.f : (i < 3 ? m.fb_mass : (i == 3 ? m.fb_inertia[0] : (i == 4 ? m.fb_inertia[1] : m.fb_inertia[2])));
-      hb += hess_contacts<NC>(S, mbox, ncon, KM_NL + i, KM_NL + j);
-      S.H[KM_NL + i][KM_NL + j] = hb;
-    }
-   }
-    if (coupled) {
-#pragma unroll 1
-      for (int e = lane; e < KM_NL * KM_NL; e += KW) {
-        const int i = KM_NL + e / KM_NL, j = e % KM_NL;
-        S.H[i][j] = hess_contacts<NC>(S, mrob & mbox, ncon, i, j);
-      }
-    }
-  END_LANES
-  PHASE(W, 10);
-  // ---- S4: search = -H^-1 grad, Cholesky with one row per lane in registers.  Robot and box
-  //      blocks only couple through a robot/box contact; otherwise the two 6x6 blocks are factorised
-  //      side by side (6 column steps instead of 12) ----
-  {
-    USYNC();
-    const Vec6 xr = chol_solve6(&S.H[0][0], KM_NV, S.grad);
-    const Vec6 xb = chol_solve6(&S.H[KM_NL][KM_NL], KM_NV, S.grad + KM_NL);
-    UNIFORM_WRITE(W) {
-      for (int i = 0; i < KM_NL; ++i) { S.search[i] = -xr.v[i]; S.search[KM_NL + i] = -xb.v[i]; }
-    } END_UNIFORM_WRITE
-  }
-  if (coupled) {                                // rare: full 12x12 system (replaces the block solution above)
-    DLANES(W, R)
-#pragma unroll
-      for (int k = 0; k < KM_NV; ++k) R.h[k] = (lane < KM_NV && k <= lane) ? S.H[lane][k] : 0.f;
-      R.f0 = lane < KM_NV ? S.grad[lane] : 0.f;
-    END_DLANES
-    chol_solve_rows<12>(W);
-    DLANES(W, R)
-      if (lane < KM_NV) S.search[lane] = -R.f0;
-    END_DLANES
-  }
-  REGROUP();
-  PHASE_ALIGN(16);
-  PHASE(W, 11);
-  // ---- S5: line search (BD.10) ----
-  // J.search per row, the Gauss-term sums and the constraint sums of the starting point alpha = 0
-  // (MJX's p0) in one pass and one fused warp reduction
-  contact_dots<NC>(W, S, ncon, S.search, nullptr);
-  LANES(W, R)
-    float e0 = 0.f, e1 = 0.f, e2 = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f;
-    if (lane < KM_NV) {
-      const float mv = mul_M<NC>(m, S, lane, S.search), s = S.search[lane];
-      e0 = s * s; e1 = s * S.Ma[lane] - s * S.fs[lane]; e2 = 0.5f * s * mv;
-    }
-#pragma unroll 1
-    for (int r = lane; r < nrow; r += KW) {
-      const float jv = row_val<NC>(S, 0, r, S.search), ja = S.rJaref[r], D = S.rD[r];
-      S.rJv[r] = jv;
-      if (ja < 0.f) { a0 += 0.5f * D * ja * ja; a1 += D * jv * ja; a2 += 0.5f * D * jv * jv; }
-    }
-    R.acc[0] = e0; R.acc[1] = e1; R.acc[2] = e2; R.acc[3] = a0; R.acc[4] = a1; R.acc[5] = a2; R.acc[6] = R.acc[7] = R.acc[8] = 0.f;
-  END_LANES
-  float qg[3], gtol;
-  LSPoint p0, lo, hi;
-  {
-    float sums[9];
-    warp_sum9(W, sums);
-    qg[0] = gauss; qg[1] = sums[1]; qg[2] = sums[2];
-    gtol = m.tolerance * m.ls_tolerance * sqrtf(sums[0]) * m.meaninertia * (float)KM_NV;
-    const float q2 = qg[2] + sums[5];
-    p0.alpha = 0.f; p0.cost = qg[0] + sums[3]; p0.d0 = qg[1] + sums[4]; p0.d1 = 2.f * q2 + (q2 == 0.f ? MJ_MINVAL : 0.f);
-    lo = p0; hi = p0;
-  }
-  PHASE(W, 19);
-  // One rolled loop evaluates the piecewise quadratic at three step sizes per trip:
-  //   trip -1: lo = point(-p0.d0/p0.d1); trips 0..ls_iterations-1: MJX bracket update.
-  // The loop is warp-uniform: it runs until every sample of the warp is done; a sample that finished
-  // earlier idles through the remaining trips with its bracket frozen.
-  bool swapped = true, done = nrow == 0;
-#pragma unroll 1
-  for (int it = -1; it < m.ls_iterations; ++it) {
-    float al0, al1, al2;
-    if (it == -1) { al0 = al1 = al2 = p0.alpha - p0.d0 / p0.d1; }
-    else {
-      done = done || !swapped;
-      done = done || ((lo.d0 < 0.f) && (lo.d0 > -gtol));
-      done = done || ((hi.d0 > 0.f) && (hi.d0 < gtol));
-      if (warp_all_groups(W, done)) break;
-      al0 = lo.alpha - lo.d0 / lo.d1; al1 = hi.alpha - hi.d0 / hi.d1; al2 = 0.5f * (lo.alpha + hi.alpha);
-    }
-    LANES(W, R)
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
-#pragma unroll 1
-      for (int r = lane; r < nrow; r += KW) {
-        const float ja = S.rJaref[r], jv = S.rJv[r], D = S.rD[r];
-        const float q0 = 0.5f * D * ja * ja, q1 = D * jv * ja, q2 = 0.5f * D * jv * jv;
-        if (ja + al0 * jv < 0.f) { a0 += q0; a1 += q1; a2 += q2; }
-        if (ja + al1 * jv < 0.f) { b0 += q0; b1 += q1; b2 += q2; }
-        if (ja + al2 * jv < 0.f) { c0 += q0; c1 += q1; c2 += q2; }
-      }
-      R.acc[0] = a0; R.acc[1] = a1; R.acc[2] = a2; R.acc[3] = b0; R.acc[4] = b1; R.acc[5] = b2; R.acc[6] = c0; R.acc[7] = c1; R.acc[8] = c2;
-    END_LANES
-    float sums[9];
-    warp_sum9(W, sums);
-    LSPoint pt[3];
-    const float als[3] = {al0, al1, al2};
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const float q0 = qg[0] + sums[3 * k], q1 = qg[1] + sums[3 * k + 1], q2 = qg[2] + sums[3 * k + 2];
-      const float a = als[k];
-      pt[k].alpha = a;
-      pt[k].cost = a * a * q2 + a * q1 + q0;
-      pt[k].d0 = 2.f * a * q2 + q1;
-      pt[k].d1 = 2.f * q2 + (q2 == 0.f ? MJ_MINVAL : 0.f);
-    }
-    if (it == -1) {
-      if (pt[0].d0 < p0.d0) { lo = pt[0]; hi = p0; } else { hi = pt[0]; lo = p0; }
-      continue;
-    }
-    if (done) continue;
-    const LSPoint lo_next = pt[0], hi_next = pt[1], mid = pt[2];
-    bool s1 = in_bracket(lo, lo_next); if (s1) lo = lo_next;
-    bool s2 = in_bracket(lo, mid);     if (s2) lo = mid;
-    bool s3 = in_bracket(lo, hi_next); if (s3) lo = hi_next;
-    bool s4 = in_bracket(hi, hi_next); if (s4) hi = hi_next;
-    bool s5 = in_bracket(hi, mid);     if (s5) hi = mid;
-    bool s6 = in_bracket(hi, lo_next); if (s6) hi = lo_next;
-    swapped = s1 || s2 || s3 || s4 || s5 || s6;
-#ifdef CEMK_EMU_DEBUG
-    printf("[emu]  it %d cand %.7g %.7g %.7g -> lo a %.7g d0 %.5g  hi a %.7g d0 %.5g swaps %d%d%d%d%d%d\n", it, al0, al1, al2, lo.alpha, lo.d0, hi.alpha, hi.d0, s1, s2, s3, s4, s5, s6);
-#endif
-  }
-  const bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
-#ifdef CEMK_EMU_DEBUG
-  printf("[emu] p0 cost %.9g d0 %.6g d1 %.6g | lo a %.7g cost %.9g d0 %.6g | hi a %.7g cost %.9g d0 %.6g | gtol %.3g\n", p0.cost, p0.d0, p0.d1, lo.alpha, lo.cost, lo.d0, hi.alpha, hi.cost, hi.d0, gtol);
-#endif
-  const float alpha = improved ? (lo.cost < hi.cost ? lo.alpha : hi.alpha) : 0.f;
-  LANES(W, R)
-    if (lane < KM_NV) {
-      float a = S.qacc[lane] + alpha * S.search[lane];
-      if (nrow == 0) a = S.as[lane];
-      S.qacc[lane] = a; S.warm[lane] = a;
-    }
-  END_LANES
+  // contacts beyond the shared-memory capacity: both samples of the warp take the spill-capable instantiation
+  // (same arithmetic, other addressing), so fences stay warp-uniform
+  if (NC < KM_NC_TOT && !warp_all_groups(W, ncon <= NC)) solve_rows<NC, true>(W, m, S, ncon, nlim, nrow);
+  else solve_rows<NC, false>(W, m, S, ncon, nlim, nrow);
 }
 
 // B.8: semi-implicit Euler with eulerdamp disabled
@@ -1493,6 +1524,7 @@ struct RolloutArgs {
   float* qacc_dbg;            // optional [T][12]
   int* flags;
   float* prevd;               // scratch [2 * KM_NPASS][KW] of this sample (StepIO::prevd)
+  float* ovf;                 // spill area [KM_NC_TOT - NC][KM_OVF_STRIDE] of this sample (WarpSmemT::ovf)
 };
 
 template <int NC>
@@ -1510,7 +1542,7 @@ KFN void rollout_sample(Warp& W, const KModel& m, WarpSmemT<NC>& S, const Rollou
       }
       R.tri = tri;
     }
-    if (lane == 0) S.flags = 0;
+    if (lane == 0) { S.flags = 0; S.ovf = A.ovf; }
     R.cost_c = 0.f;
     R.td = lane < KM_NL ? A.thetadot[lane * A.T] : 0.f;
   END_LANES

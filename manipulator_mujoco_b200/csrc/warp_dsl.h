@@ -39,6 +39,7 @@ static_assert(KW == 16 || KW == 32, "CEMK_KW must be 16 or 32");
 #ifdef CEMK_EMU
 #include <cstring>
 #define KFN static inline
+#define KMEM inline
 #define KNOINLINE static
 #define STEP_ALIGN()
 #define PHASE_ALIGN(bit)
@@ -61,6 +62,7 @@ static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); ret
 static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
 #else
 #define KFN __device__ __forceinline__
+#define KMEM __device__ __forceinline__
 #define KNOINLINE __device__ __noinline__
 // Keep the live warps of a CTA on the same code (instruction-cache locality): named barrier 1 with the
 // live thread count of this CTA (a CTA may run fewer samples than its launch width, see

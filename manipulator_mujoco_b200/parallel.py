@@ -26,21 +26,39 @@ def local_topk_size(k: int, batch_local: int) -> int:
     return min(k, batch_local)
 
 
-def pack_elites(xi_e: torch.Tensor, cost_e: torch.Tensor, gidx: torch.Tensor) -> torch.Tensor:
-    """[k', nvar] , [k'], [k'] int -> [k', nvar + 2] float32 (global indices < 2^24 are exact in float32)."""
-    if int(gidx.max()) >= 1 << 24:
-        raise ValueError("global sample index does not fit a float32 mantissa")
-    return torch.cat([xi_e, cost_e[:, None], gidx.to(torch.float32)[:, None]], dim=1).contiguous()
+def check_index_range(num_batch: int):
+    if num_batch > 1 << 24:
+        raise ValueError("global sample index does not fit a float32 mantissa (num_batch > 2^24)")
 
 
-def gather_elites(pack: torch.Tensor, world: int, group=None) -> torch.Tensor:
+def pack_elites(xi_e: torch.Tensor, cost_e: torch.Tensor, gidx: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """[k', nvar] , [k'], [k'] int -> [k', nvar + 2] float32.  Global indices must be < 2^24 to be exact in
+    float32; the planner checks its batch size once at construction (`check_index_range`) -- reading the
+    index tensor here would put a device synchronisation into every CEM iteration."""
+    if out is None:
+        return torch.cat([xi_e, cost_e[:, None], gidx.to(torch.float32)[:, None]], dim=1).contiguous()
+    nvar = xi_e.shape[1]
+    out[:, :nvar].copy_(xi_e)
+    out[:, nvar].copy_(cost_e)
+    out[:, nvar + 1].copy_(gidx)            # int32 -> float32
+    return out
+
+
+def gather_elites(pack: torch.Tensor, world: int, group=None, out: torch.Tensor | None = None) -> torch.Tensor:
     import torch.distributed as dist
-    out = torch.empty(world * pack.shape[0], pack.shape[1], dtype=pack.dtype, device=pack.device)
+    if out is None:
+        out = torch.empty(world * pack.shape[0], pack.shape[1], dtype=pack.dtype, device=pack.device)
     dist.all_gather_into_tensor(out, pack, group=group)
     return out
 
 
-def split_gathered(gathered: torch.Tensor):
+def split_gathered(gathered: torch.Tensor, out=None):
     nvar = gathered.shape[1] - 2
+    if out is not None:
+        g_cost, g_idx, g_xi = out
+        g_cost.copy_(gathered[:, nvar])
+        g_idx.copy_(gathered[:, nvar + 1])      # float32 -> int32 (exact below 2^24)
+        g_xi.copy_(gathered[:, :nvar])
+        return g_cost, g_idx, g_xi
     return (gathered[:, nvar].contiguous(), gathered[:, nvar + 1].to(torch.int32).contiguous(),
             gathered[:, :nvar].contiguous())

@@ -186,6 +186,8 @@ class cem_planner:
         self.mjx_data = self._initial_forward()
 
         self._z_cache = {}
+        self._split_cache = {}
+        parallel.check_index_range(self.num_batch)
         self._ws = {}
         self._graph, self._graph_out, self._eager_ticks = None, None, 0
         self.use_cuda_graph = os.environ.get("CEMK_CUDA_GRAPH", "1") != "0"
@@ -299,6 +301,16 @@ class cem_planner:
             self._ws[key] = b
         return b
 
+    def _split0(self, key):
+        """``jax.random.split(key)[0]``; memoised, the reference walks the same key chain every tick (:80, :388)."""
+        k = jax_prng.as_key(key)
+        ck = (int(k[0]), int(k[1]))
+        out = self._split_cache.get(ck)
+        if out is None:
+            out = jax_prng.split(k, 2, self._partitionable)[0]
+            self._split_cache[ck] = out
+        return out
+
     def _normal(self, key):
         """jax.random.normal(key, (num_batch, nvar)) rows [rank*Bl, (rank+1)*Bl): the draws behind
         jax.random.multivariate_normal (:315), generated on the device by cemk_jax_normal.  A function of
@@ -326,7 +338,7 @@ class cem_planner:
     def compute_xi_samples(self, key, xi_mean, xi_cov):
         """mjx_planner.py:313-316.  ``key``: raw threefry key data (2 x uint32, what jax.random.key_data
         gives) or an integer seed; returns (xi_samples, new key)."""
-        key = jax_prng.split(key, 2, self._partitionable)[0]   # key, subkey = split(key); sample with key
+        key = self._split0(key)                                # key, subkey = split(key); sample with key
         z = self._normal(key)
         B = z.shape[0]
         xi = torch.empty(B, self.nvar, device=self.device)
@@ -437,9 +449,16 @@ class cem_planner:
         xi_e, idx, cost_e = self._argsort_topk(cost4, 4, Bl, kl, xi_samples, idx_base=base)
         if self.world == 1:
             return xi_e, cost_e, idx[:kl]
-        gathered = parallel.gather_elites(parallel.pack_elites(xi_e, cost_e, idx[:kl]), self.world, self.process_group)
+        # persistent buffers: tensors handed to the collective must not churn through the caching allocator
+        # (a block used on NCCL's stream is not reusable until that stream's event completes)
+        nv = self.nvar
+        pack = self._buf("elite_pack", (kl, nv + 2))
+        parallel.pack_elites(xi_e, cost_e, idx[:kl], out=pack)
+        gathered = self._buf("elite_gathered", (self.world * kl, nv + 2))
+        parallel.gather_elites(pack, self.world, self.process_group, out=gathered)
         n = self.world * kl
-        g_cost, g_idx, g_xi = parallel.split_gathered(gathered)
+        g_cost, g_idx, g_xi = parallel.split_gathered(gathered, out=(self._buf("elite_gcost", (n,)), self._buf("elite_gidx", (n,), torch.int32),
+                                                                    self._buf("elite_gxi", (n, nv))))
         np2 = 1 << max(0, (n - 1).bit_length())
         keys = self._buf("keys_merge", (np2,), torch.int64)
         xi_m = torch.empty(k, self.nvar, device=self.device)
@@ -478,7 +497,7 @@ class cem_planner:
         state_row = torch.cat([q0, v0, a0, z6, z6])
         state_term = state_row.unsqueeze(0).expand(Bl, 30).contiguous()                    # :374-384
         xi_cov = 10 * torch.eye(nv, device=dev)                                            # :386
-        key = jax_prng.split(self.key, 2, self._partitionable)[0]                          # :388
+        key = self._split0(self.key)                                                       # :388
         carry = (q0, v0, tp, tr, xi_mean_d, xi_cov, key, state_term)
         thetadot_all = torch.empty(self.maxiter_cem, Bl, nd * T, device=dev)
         theta_all = torch.empty(self.maxiter_cem, Bl, nd * T, device=dev)

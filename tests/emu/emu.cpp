@@ -21,6 +21,7 @@ extern "C" int emu_rollout(const KModel* m, int B, int T, const float* thetadot,
     WarpSmemT<KM_NC_FAST>* S = new WarpSmemT<KM_NC_FAST>();
     WarpSmemT<KM_NC_BIG>* Sb = new WarpSmemT<KM_NC_BIG>();
     float* prevd = new float[2 * KM_NPASS * KW];
+    float* ovf = new float[KM_NC_TOT * KM_OVF_STRIDE];
 #pragma omp for schedule(dynamic, 4)
     for (int s = 0; s < B; ++s) {
       memset((void*)W, 0, sizeof(Warp));
@@ -40,9 +41,10 @@ extern "C" int emu_rollout(const KModel* m, int B, int T, const float* thetadot,
       A.qacc_dbg = qacc_dbg ? qacc_dbg + (size_t)s * T * KM_NV : nullptr;
       A.flags = flags ? flags + s : nullptr;
       A.prevd = prevd;
+      A.ovf = ovf;
       if (nc <= KM_NC_FAST) rollout_sample<KM_NC_FAST>(*W, *m, *S, A); else rollout_sample<KM_NC_BIG>(*W, *m, *Sb, A);
     }
-    delete W; delete S; delete Sb; delete[] prevd;
+    delete W; delete S; delete Sb; delete[] prevd; delete[] ovf;
   }
   return 0;
 }

@@ -127,3 +127,31 @@ def test_robot_box_coupled_contact(emu, oracle64, oracle32, mc):
     dev = np.array(dev)
     assert (dev < 5e-2).all(), dev
     assert (dev < 1e-3).mean() >= 0.7, dev
+
+
+def test_contact_spill_area_is_bit_identical_to_all_shared_memory(emu, oracle64, mc):
+    """More simultaneous contacts than the fast kernel keeps in shared memory (20): the extra ones live in the
+    per-sample global spill area.  Same code, same arithmetic -- results must equal the 48-contact
+    all-in-shared-memory instantiation bit for bit, on single steps and over a horizon."""
+    rng = np.random.default_rng(3)
+    deep = []
+    for _ in range(4000):
+        q = rng.uniform(-3, 3, 6)
+        r = oracle64.forward(np.concatenate([q, mc.qpos0[6:]]), np.zeros(12))
+        n = int((r["con_dist"] < 0).sum())
+        if n > 20:
+            deep.append((n, q))
+        if len(deep) >= 3:
+            break
+    assert deep, "no state with more than 20 contacts found"
+    T = 6
+    for n, q in deep:
+        td = rng.normal(size=(1, 6 * T)) * 0.3
+        a = emu.rollout(td, q, np.zeros(6), TARGET_POS, TARGET_ROT, nc=20)
+        b = emu.rollout(td, q, np.zeros(6), TARGET_POS, TARGET_ROT, nc=48)
+        assert a["flags"][0] == 0 and b["flags"][0] == 0
+        for key in ("theta", "cost4", "qacc", "collision", "eef_pos"):
+            np.testing.assert_array_equal(a[key].view(np.int32), b[key].view(np.int32), err_msg=f"{key} ({n} contacts)")
+        # and the spilled contacts take part in the solve: the oracle agrees on the first step's distances
+        r64 = oracle64.forward(np.concatenate([q, mc.qpos0[6:]]), np.concatenate([td[0, ::T], np.zeros(6)]))
+        np.testing.assert_allclose(a["collision"][0, 0], r64["con_dist"][oracle64.mask], atol=2e-5)

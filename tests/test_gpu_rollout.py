@@ -111,7 +111,9 @@ def test_results_do_not_depend_on_the_partner_sample_or_odd_batch_sizes():
 
 
 def test_big_capacity_kernel_agrees_with_fast_kernel():
-    """`force_rerun` recomputes every sample with the 48-contact instantiation (the overflow path)."""
+    """`force_rerun` recomputes every sample with the 48-contact all-in-shared-memory instantiation; the fast
+    kernel (20 contacts in shared memory, the rest in the global spill area) must agree bit for bit -- also
+    from start configurations that lie deep inside the table (more than 20 simultaneous contacts)."""
     from manipulator_mujoco_b200 import _lib, cem_planner
     T, B = 60, 256
     pl = cem_planner(num_dof=6, num_batch=B, num_steps=T, timestep=0.05, maxiter_cem=1, num_elite=0.05,
@@ -124,3 +126,12 @@ def test_big_capacity_kernel_agrees_with_fast_kernel():
     _lib.check(pl._lib.cemk_set_option(pl._h, b"force_rerun", 0), pl._lib)
     for x, y in zip(a, b):
         np.testing.assert_array_equal(x.cpu().numpy(), y.cpu().numpy())
+    for q_deep in ([1.181, 0.789, -0.949, -0.051, 2.391, -0.535], [1.168, 0.758, -0.921, -0.796, 0.168, 2.145]):
+        a = pl._rollout(td * 0.2, np.array(q_deep), np.zeros(6), TARGET_POS, TARGET_ROT, True)
+        ncol = int((a[4][:, 0].cpu().numpy() < 0).sum(axis=1).max())
+        assert ncol > 16                                           # robot slots alone; the box adds 4 after it lands
+        _lib.check(pl._lib.cemk_set_option(pl._h, b"force_rerun", 1), pl._lib)
+        b = pl._rollout(td * 0.2, np.array(q_deep), np.zeros(6), TARGET_POS, TARGET_ROT, True)
+        _lib.check(pl._lib.cemk_set_option(pl._h, b"force_rerun", 0), pl._lib)
+        for x, y in zip(a, b):
+            np.testing.assert_array_equal(x.cpu().numpy().view(np.int32), y.cpu().numpy().view(np.int32))
