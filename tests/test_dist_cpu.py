@@ -45,6 +45,16 @@ def _worker(rank, world, port, B, k, seed, ret):
     pack = parallel.pack_elites(torch.from_numpy(xi[lo:hi][loc]), torch.from_numpy(cost[lo:hi][loc]),
                                 torch.from_numpy((loc + lo).astype(np.int32)))
     g_cost, g_idx, g_xi = parallel.split_gathered(parallel.gather_elites(pack, world))
+    # the planner's allocation-free variants (persistent buffers) must give the same tensors
+    nv = xi.shape[1]
+    pack2 = parallel.pack_elites(torch.from_numpy(xi[lo:hi][loc]), torch.from_numpy(cost[lo:hi][loc]),
+                                 torch.from_numpy((loc + lo).astype(np.int32)), out=torch.empty(kl, nv + 2))
+    bits = lambda t: t.contiguous().view(torch.int32)                 # NaN-safe bitwise comparison
+    assert torch.equal(bits(pack), bits(pack2))
+    gath2 = parallel.gather_elites(pack2, world, out=torch.empty(world * kl, nv + 2))
+    c2, i2, x2 = parallel.split_gathered(gath2, out=(torch.empty(world * kl), torch.empty(world * kl, dtype=torch.int32),
+                                                     torch.empty(world * kl, nv)))
+    assert torch.equal(bits(c2), bits(g_cost)) and torch.equal(i2, g_idx) and torch.equal(bits(x2), bits(g_xi))
     sel = _order(g_cost.numpy())[:k]                                  # what cemk_merge_elites does (cost, row)
     ret[rank] = (g_idx.numpy()[sel].copy(), g_xi.numpy()[sel].copy(), g_cost.numpy()[sel].copy())
     dist.destroy_process_group()
@@ -63,6 +73,12 @@ def test_sharded_merge_equals_global_stable_topk(world, B, k):
         np.testing.assert_array_equal(gidx, ref)                      # bit-identical elite index lists on every rank
         np.testing.assert_array_equal(gxi, xi[ref])
         np.testing.assert_array_equal(gcost, cost[ref])
+
+
+def test_index_range_check():
+    parallel.check_index_range(1 << 24)
+    with pytest.raises(ValueError):
+        parallel.check_index_range((1 << 24) + 1)
 
 
 def test_shard_bounds():
