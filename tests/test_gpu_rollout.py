@@ -110,6 +110,29 @@ def test_results_do_not_depend_on_the_partner_sample_or_odd_batch_sizes():
             np.testing.assert_array_equal(a[:n], b)
 
 
+def test_multi_wave_cta_shares_cover_every_sample_once():
+    """More samples than one wave of CTAs holds (148 SMs x 28): the per-SM share is split over waves with two
+    different CTA shares (cemk_rollout_cost).  Every sample must be rolled out exactly once, with the same
+    result as in a small batch."""
+    from manipulator_mujoco_b200 import cem_planner
+    T, B = 10, 9000
+    pr, z, xi, st, xif, td = planner_inputs(T, 600, seed=33)
+    td = np.ascontiguousarray(np.tile(td, (B // 600, 1)), dtype=np.float32)        # 15 copies of 600 distinct samples
+    pl = cem_planner(num_dof=6, num_batch=B, num_steps=T, timestep=0.05, maxiter_cem=1, num_elite=0.05,
+                     w_pos=20.0, w_rot=3.0, w_col=80.0, maxiter_projection=10)
+    theta, cost4, _, _, _ = pl._rollout(td, Q0, np.zeros(6), TARGET_POS, TARGET_ROT, False)
+    theta, cost4 = theta.cpu().numpy(), cost4.cpu().numpy()
+    assert np.isfinite(cost4).all()
+    for rep in range(1, B // 600):                                                 # all copies agree bit for bit
+        np.testing.assert_array_equal(theta[:600], theta[rep * 600:(rep + 1) * 600])
+        np.testing.assert_array_equal(cost4[:600], cost4[rep * 600:(rep + 1) * 600])
+    small = cem_planner(num_dof=6, num_batch=600, num_steps=T, timestep=0.05, maxiter_cem=1, num_elite=0.05,
+                        w_pos=20.0, w_rot=3.0, w_col=80.0, maxiter_projection=10)
+    th2, c2, _, _, _ = small._rollout(td[:600], Q0, np.zeros(6), TARGET_POS, TARGET_ROT, False)
+    np.testing.assert_array_equal(theta[:600], th2.cpu().numpy())
+    np.testing.assert_array_equal(cost4[:600], c2.cpu().numpy())
+
+
 def test_big_capacity_kernel_agrees_with_fast_kernel():
     """`force_rerun` recomputes every sample with the 48-contact all-in-shared-memory instantiation; the fast
     kernel (20 contacts in shared memory, the rest in the global spill area) must agree bit for bit -- also
