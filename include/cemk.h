@@ -94,6 +94,15 @@ int cemk_argsort_topk(cemk_handle* h, int n, const float* cost, int cost_stride,
 int cemk_merge_elites(cemk_handle* h, int n, const float* cost, const int* gidx, const float* xi, unsigned long long* keys_ws,
                       int k, float* xi_elite, float* cost_elite, int* gidx_elite, void* stream);
 
+/* The two halves of the multi-GPU form of compute_ellite_samples without intermediate tensors.
+ * cemk_topk_pack: this rank's k best samples as exchange records pack[k][68] = xi[66], cost, global index
+ * (idx_base + local row, stored as float: exact below 2^24) -- the send buffer of the NCCL all-gather.
+ * cemk_merge_packed: n gathered records (rank-major) -> the k best by (cost, row) = (cost, global index). */
+int cemk_topk_pack(cemk_handle* h, int n, const float* cost, int cost_stride, int idx_base, unsigned long long* keys_ws, int k,
+                   const float* xi, float* pack, void* stream);
+int cemk_merge_packed(cemk_handle* h, int n, const float* packed, unsigned long long* keys_ws, int k, float* xi_elite,
+                      float* cost_elite, int* gidx_elite, void* stream);
+
 /* compute_mean_cov (mjx_planner.py:326-335): k elites -> mean_out[66], cov_out[66][66]. */
 int cemk_mean_cov(cemk_handle* h, int k, const float* cost_elite, const float* xi_elite, const float* mean_prev,
                   const float* cov_prev, float lamda, float alpha_mean, float alpha_cov, float* mean_out, float* cov_out,

@@ -442,6 +442,29 @@ __global__ void k_finish_sort(int n, const unsigned long long* __restrict__ keys
   }
 }
 
+// Elite exchange records [..][NVAR + 2] = xi[66], cost, global index (as float, exact below 2^24):
+// what one rank contributes to the NCCL all-gather, written / read without intermediate tensors.
+#define PACKW (NVAR + 2)
+__global__ void k_pack_sorted(const unsigned long long* __restrict__ keys, int idx_base, int k, const float* __restrict__ cost, int stride,
+                              const float* __restrict__ xi, float* __restrict__ pack) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= k * PACKW) return;
+  const int e = i / PACKW, c = i % PACKW;
+  const int src = (int)(unsigned int)(keys[e] & 0xffffffffull);
+  pack[i] = c < NVAR ? xi[(size_t)src * NVAR + c] : (c == NVAR ? cost[(size_t)src * stride] : (float)(src + idx_base));
+}
+__global__ void k_unpack_sorted(const unsigned long long* __restrict__ keys, int k, const float* __restrict__ packed,
+                                float* __restrict__ xi_elite, float* __restrict__ cost_elite, int* __restrict__ gidx_elite) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= k * PACKW) return;
+  const int e = i / PACKW, c = i % PACKW;
+  const int src = (int)(unsigned int)(keys[e] & 0xffffffffull);
+  const float v = packed[(size_t)src * PACKW + c];
+  if (c < NVAR) xi_elite[e * NVAR + c] = v;
+  else if (c == NVAR) cost_elite[e] = v;
+  else gidx_elite[e] = (int)v;
+}
+
 // ---------------------------------------------------------------------------------------------- mean / covariance
 // grid = 66 CTAs (one covariance row each); fixed summation order => bit-identical on every rank.
 __global__ void __launch_bounds__(128) k_mean_cov(int k, const float* __restrict__ cost, const float* __restrict__ xi, const float* __restrict__ mean_prev,
@@ -714,6 +737,38 @@ int cemk_merge_elites(cemk_handle* h, int n, const float* cost, const int* gidx,
   h->launches += 1;
   sort_keys(h, np2, keys_ws, st);
   k_finish_sort<<<(k * NVAR + 255) / 256, 256, 0, st>>>(0, keys_ws, 0, nullptr, k, cost, 1, xi, xi_elite, cost_elite, gidx, gidx_elite);
+  h->launches += 1;
+  CK(cudaPeekAtLastError());
+  return CEMK_OK;
+}
+
+int cemk_topk_pack(cemk_handle* h, int n, const float* cost, int cost_stride, int idx_base, unsigned long long* keys_ws, int k,
+                   const float* xi, float* pack, void* stream) {
+  if (!h || !cost || !keys_ws || !xi || !pack || n <= 0 || k <= 0 || k > n || cost_stride < 1)
+    return set_err(CEMK_ERR_ARG, "cemk_topk_pack: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int np2 = next_pow2(n);
+  k_make_keys<<<(np2 + 255) / 256, 256, 0, st>>>(n, np2, cost, cost_stride, keys_ws);
+  h->launches += 1;
+  sort_keys(h, np2, keys_ws, st);
+  k_pack_sorted<<<(k * PACKW + 255) / 256, 256, 0, st>>>(keys_ws, idx_base, k, cost, cost_stride, xi, pack);
+  h->launches += 1;
+  CK(cudaPeekAtLastError());
+  return CEMK_OK;
+}
+
+int cemk_merge_packed(cemk_handle* h, int n, const float* packed, unsigned long long* keys_ws, int k, float* xi_elite,
+                      float* cost_elite, int* gidx_elite, void* stream) {
+  if (!h || !packed || !keys_ws || !xi_elite || !cost_elite || !gidx_elite || n <= 0 || k <= 0 || k > n)
+    return set_err(CEMK_ERR_ARG, "cemk_merge_packed: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int np2 = next_pow2(n);
+  // candidate rows arrive rank-major and (cost, index)-sorted within a rank, so the row number breaks
+  // cost ties exactly like the global sample index does
+  k_make_keys<<<(np2 + 255) / 256, 256, 0, st>>>(n, np2, packed + NVAR, PACKW, keys_ws);
+  h->launches += 1;
+  sort_keys(h, np2, keys_ws, st);
+  k_unpack_sorted<<<(k * PACKW + 255) / 256, 256, 0, st>>>(keys_ws, k, packed, xi_elite, cost_elite, gidx_elite);
   h->launches += 1;
   CK(cudaPeekAtLastError());
   return CEMK_OK;

@@ -446,26 +446,27 @@ class cem_planner:
         k = self.ellite_num
         kl = min(k, Bl)
         base = self.rank * Bl
-        xi_e, idx, cost_e = self._argsort_topk(cost4, 4, Bl, kl, xi_samples, idx_base=base)
         if self.world == 1:
+            xi_e, idx, cost_e = self._argsort_topk(cost4, 4, Bl, kl, xi_samples, idx_base=base)
             return xi_e, cost_e, idx[:kl]
-        # persistent buffers: tensors handed to the collective must not churn through the caching allocator
-        # (a block used on NCCL's stream is not reusable until that stream's event completes)
+        # Two library calls around one all-gather, persistent buffers only: tensors handed to the collective
+        # must not churn through the caching allocator, and nothing here reads device memory from the host.
         nv = self.nvar
+        np2l = 1 << max(0, (Bl - 1).bit_length())
         pack = self._buf("elite_pack", (kl, nv + 2))
-        parallel.pack_elites(xi_e, cost_e, idx[:kl], out=pack)
+        c4, xs = self._t(cost4), self._t(xi_samples)
+        _lib.check(self._lib.cemk_topk_pack(self._h, Bl, _ptr(c4), 4, base, _ptr(self._buf("keys", (np2l,), torch.int64)), kl,
+                                            _ptr(xs), _ptr(pack), self._stream()), self._lib)
         gathered = self._buf("elite_gathered", (self.world * kl, nv + 2))
         parallel.gather_elites(pack, self.world, self.process_group, out=gathered)
         n = self.world * kl
-        g_cost, g_idx, g_xi = parallel.split_gathered(gathered, out=(self._buf("elite_gcost", (n,)), self._buf("elite_gidx", (n,), torch.int32),
-                                                                    self._buf("elite_gxi", (n, nv))))
         np2 = 1 << max(0, (n - 1).bit_length())
-        keys = self._buf("keys_merge", (np2,), torch.int64)
-        xi_m = torch.empty(k, self.nvar, device=self.device)
+        xi_m = torch.empty(k, nv, device=self.device)
         cost_m = torch.empty(k, device=self.device)
         gidx_m = torch.empty(k, dtype=torch.int32, device=self.device)
-        _lib.check(self._lib.cemk_merge_elites(self._h, n, _ptr(g_cost), _ptr(g_idx), _ptr(g_xi), _ptr(keys), k, _ptr(xi_m),
-                                               _ptr(cost_m), _ptr(gidx_m), self._stream()), self._lib)
+        _lib.check(self._lib.cemk_merge_packed(self._h, n, _ptr(gathered), _ptr(self._buf("keys_merge", (np2,), torch.int64)), k,
+                                               _ptr(xi_m), _ptr(cost_m), _ptr(gidx_m), self._stream()), self._lib)
+        self._keep_e = (c4, xs)
         return xi_m, cost_m, gidx_m
 
     # ------------------------------------------------------------------ cem_iter / compute_cem (mjx_planner.py:337-406)

@@ -135,3 +135,36 @@ def test_compute_cem_end_to_end_against_oracle_pipeline(oracle64):
     m_ref, _ = pr.compute_mean_cov(ce_ref, np.zeros(66), 10 * np.eye(66), xe_ref)
     if got == set(order[:k].tolist()):
         np.testing.assert_allclose(xi_mean, m_ref, atol=5e-3)
+
+
+def test_packed_topk_and_merge_equal_global_stable_topk(planner):
+    """cemk_topk_pack on two shards + cemk_merge_packed (the multi-GPU elite exchange without NCCL in between)
+    must give the global stable top-k, ties and NaNs included."""
+    import ctypes as C
+    from manipulator_mujoco_b200 import _lib
+    lib, h = planner._lib, planner._h
+    rng = np.random.default_rng(4)
+    n, k, nv = 3000, 150, 66
+    cost = rng.uniform(0, 100, n).astype(np.float32)
+    cost[rng.integers(0, n, 600)] = 5.0                                # ties across both shards
+    cost[[7, 2000]] = np.nan
+    xi = rng.normal(size=(n, nv)).astype(np.float32)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    packs = []
+    for r in range(2):
+        lo, hi = r * n // 2, (r + 1) * n // 2
+        c = torch.tensor(cost[lo:hi], device="cuda"); x = torch.tensor(xi[lo:hi], device="cuda")
+        keys = torch.empty(2048, dtype=torch.int64, device="cuda")
+        pack = torch.empty(k, nv + 2, device="cuda")
+        _lib.check(lib.cemk_topk_pack(h, hi - lo, p(c), 1, lo, p(keys), k, p(x), p(pack), None), lib)
+        packs.append(pack)
+    gathered = torch.cat(packs).contiguous()
+    keys = torch.empty(512, dtype=torch.int64, device="cuda")
+    xe = torch.empty(k, nv, device="cuda"); ce = torch.empty(k, device="cuda"); ge = torch.empty(k, dtype=torch.int32, device="cuda")
+    _lib.check(lib.cemk_merge_packed(h, 2 * k, p(gathered), p(keys), k, p(xe), p(ce), p(ge), None), lib)
+    torch.cuda.synchronize()
+    key = np.where(np.isnan(cost), np.inf, cost)
+    ref = np.lexsort((np.arange(n), np.isnan(cost), key))[:k]
+    np.testing.assert_array_equal(ge.cpu().numpy(), ref)
+    np.testing.assert_array_equal(xe.cpu().numpy(), xi[ref])
+    np.testing.assert_array_equal(ce.cpu().numpy().view(np.int32), cost[ref].view(np.int32))
