@@ -47,7 +47,7 @@ struct cemk_handle {
   int* d_flags; int flags_cap; int num_sms;
   float* d_prevd; int prevd_cap;   // previous-step slot distances of every sample (rollout scratch, stays in L2)
   float* d_ovf;                    // contact spill area of every sample (same capacity as d_prevd)
-  int force_rerun;               // debug option: recompute every sample with the big-capacity kernel
+  int force_rerun;               // debug option: recompute every sample with the all-in-shared-memory instantiation
   int cta_warps;                 // debug option "cta_samples": fixed number of samples per CTA (0 = see cemk_rollout_cost)
 };
 
@@ -67,10 +67,10 @@ struct RolloutBatch {
   int n_hi, w_hi, w_lo;
 };
 
-// NC = capacity of the per-sample active-contact list, WARPS = warps per CTA; a warp carries 32 / KW samples
-// (one per lane group, warp_dsl.h).  The fast instantiation covers every sample; samples that ever needed
-// more contacts set flag bit 0 and are recomputed from scratch by the big instantiation (NC = 48, one warp
-// per CTA, ONLY_FLAGGED).
+// NC = contacts of a sample kept in shared memory (the rest, up to KM_NC_TOT, in the global spill area),
+// WARPS = warps per CTA; a warp carries 32 / KW samples (one per lane group, warp_dsl.h).  The fast
+// instantiation (NC = KM_NC_FAST) is the product path.  ONLY_FLAGGED is the debug instantiation behind
+// cemk_set_option("force_rerun"): NC = 48 (no spill area), one warp per CTA, samples whose flag bit 0 is set.
 #define GPW (32 / KW)                                     // lane groups (samples) per warp
 template <int NC, int WARPS, bool ONLY_FLAGGED>
 __global__ void __launch_bounds__(WARPS * 32, ROLLOUT_MINB) k_rollout(const KModel* __restrict__ gm, RolloutBatch a) {

@@ -32,7 +32,7 @@
 #define KM_NC_TOT 48                      // contacts a sample can have in total: the ones beyond the shared-memory capacity
                                           // spill to a per-sample global (L2) area
 #define KM_OVF_STRIDE 80                  // floats per spilled contact: geo 16, J 36, dots 2x3, rows 4x4
-#define KM_NC_BIG 48                      // capacity of the re-run kernel for samples that overflowed
+#define KM_NC_BIG 48                      // shared-memory capacity of the debug instantiation (everything in shared memory)
 #define MJ_MINVAL 1e-15f
 #define MJ_MINIMP 0.0001f
 #define MJ_MAXIMP 0.9999f
@@ -814,7 +814,7 @@ KFN void chol_solve_rows(Warp& W) {
   }
 }
 
-// sum over the contacts in `sel` (bit c = contact c; contacts >= 32 exist only in the 48-contact re-run
+// sum over the contacts in `sel` (bit c = contact c; contacts >= 32 exist only for samples deep in collision
 // kernel and are all visited) of the Hessian contribution of the four pyramid rows to entry (i, j)
 template <int NC, bool SP>
 KFN float hess_contacts(const WarpSmemT<NC>& S, unsigned sel, int ncon, int i, int j) {
@@ -1012,7 +1012,7 @@ KFN void solve_rows(Warp& W, const KModel& m, WarpSmemT<NC>& S, const int ncon, 
       }
       if (KM_NC_TOT > 32) {
 #pragma unroll 1
-        for (int c = 32; c < ncon; ++c) {        // only the 48-contact re-run kernel can get here
+        for (int c = 32; c < ncon; ++c) {        // more than 32 contacts: deep-collision samples only
           const float* g = S.template geo<SP>(c); const float* J = S.template jac<SP>(c);
           fc += J[lane] * g[0] + J[12 + lane] * g[1] + J[24 + lane] * g[2];
         }

@@ -74,10 +74,10 @@ def test_teacher_forced_steps_on_contact_states(emu, oracle64, oracle32):
 
 
 def test_contact_capacity_variants_agree(emu):
-    """NC = 24 (fast kernel) and NC = 48 (re-run kernel) are the same code: identical results
+    """NC = 20 (fast kernel) and NC = 48 (debug instantiation) are the same code: identical results
     whenever nothing overflows."""
     pr, z, xi, st, xif, td = planner_inputs(30, 32, seed=2)
-    a = emu.rollout(td, Q0, np.zeros(6), TARGET_POS, TARGET_ROT, nc=24)
+    a = emu.rollout(td, Q0, np.zeros(6), TARGET_POS, TARGET_ROT, nc=20)
     b = emu.rollout(td, Q0, np.zeros(6), TARGET_POS, TARGET_ROT, nc=48)
     assert a["flags"].max() == 0
     np.testing.assert_array_equal(a["theta"], b["theta"])

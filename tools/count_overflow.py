@@ -1,4 +1,5 @@
-"""How many samples of a planner-distributed batch overflow the fast kernel's contact capacity (GPU box only)."""
+"""How many samples of a planner-distributed batch exceed the 48-contact total capacity (flag bit 0; GPU box only).
+Samples between 21 and 48 contacts use the spill area and are not flagged."""
 import contextlib, io, os, sys
 import numpy as np
 import torch
@@ -22,4 +23,4 @@ for tp in ([-0.3, -0.3, 0.5], [0.3, 0.3, 0.44], [0.0, 0.0, 0.44]):
     pl.cem_iter = wrapped
     pl.compute_cem(np.zeros(66), q0, np.zeros(6), np.zeros(6), np.array(tp), np.array([0.0, 1.0, 0.0, 0.0]))
     pl.cem_iter = real_iter
-    print(f"target {tp}: samples flagged for the big-capacity re-run per CEM iteration: {counts}")
+    print(f"target {tp}: samples flagged (more than 48 contacts) per CEM iteration: {counts}")
