@@ -263,6 +263,10 @@ __global__ void __launch_bounds__(256) k_jax_normal(uint32_t k0, uint32_t k1, in
 // (so all warps carry identical iterates).  One thread per problem alone gives a B200 only ~5 warps per
 // SM on a 1e5-long dependent FMA chain; splitting a problem over lanes instead makes every lane fetch its
 // own rows and runs into the shared-memory bandwidth.
+#ifndef PROJ_UNROLL
+#define PROJ_UNROLL 2
+#endif
+constexpr int kProjUnroll = PROJ_UNROLL;
 #ifndef PROJ_SLICES
 #define PROJ_SLICES 4
 #endif
@@ -305,12 +309,15 @@ __global__ void __launch_bounds__(32 * PROJ_SLICES) k_project(int B, int T, int 
     for (int c = 0; c < 3; ++c) {
       const float bc = bnd[c];
       const float* Gc = sG + c * T * 12;
+#pragma unroll(kProjUnroll)
       for (int t = slice; t < T; t += PROJ_SLICES) {
         float g[NCOEF];
         row12(Gc + t * 12, g);
-        float u = 0.f;
+        float u0 = g[0] * x[0], u1 = g[1] * x[1], u2 = g[2] * x[2];   // three short chains instead of one of 11
 #pragma unroll
-        for (int k = 0; k < NCOEF; ++k) u += g[k] * x[k];
+        for (int k = 3; k < 9; k += 3) { u0 += g[k] * x[k]; u1 += g[k + 1] * x[k + 1]; u2 += g[k + 2] * x[k + 2]; }
+        u0 += g[9] * x[9]; u1 += g[10] * x[10];
+        const float u = (u0 + u1) + u2;
         const float cl = fminf(fmaxf(u, -bc), bc);
         const float e = u - cl, h = u + cl;
 #pragma unroll
