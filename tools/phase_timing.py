@@ -1,4 +1,6 @@
-"""Per-phase share of k_rollout's time (SM clocks of one lane per warp, summed over warps).
+"""Per-phase share of k_rollout's time (SM clocks of one lane per lane group, summed; a warp carries two groups).
+The clock read that closes a barrier phase issues before BAR.SYNC completes, so the waiting time of a barrier
+shows up in the phase that follows it (cross-checked with ncu: the stall samples sit on the instruction behind BAR.SYNC).
 Builds a debug library with -DCEMK_PHASE_TIMING next to the normal one, runs one 4096 x 100 rollout.
     python tools/phase_timing.py            (on a GPU box)"""
 import ctypes as C
@@ -33,8 +35,8 @@ pl._lib.cemk_debug_phase_clocks(buf)
 pl.compute_cem(np.zeros(66), q0, np.zeros(6), np.zeros(6), tp, tr)
 torch.cuda.synchronize()
 pl._lib.cemk_debug_phase_clocks(buf)
-names = ["align-exit", "P1 FK chain", "P2-P5 dynamics", "P6 qacc_smooth", "N1 robot narrow phase + cost", "N1 free-box pairs", "N2 emit contacts",
-         "phase-barrier wait + C1 limit rows", "S1 warm/smooth", "S3 grad + H", "S4 Cholesky + solve", "S5a line-search setup", "obs + euler", "step barrier wait",
+names = ["step barrier wait (sampled behind BAR.SYNC) + command load", "P1 FK chain", "P2-P5 dynamics", "P6 qacc_smooth", "N1 robot narrow phase + cost", "N1 free-box pairs", "N2 emit contacts",
+         "phase barrier wait (sampled behind BAR.SYNC) + C1 limit rows", "S1 warm/smooth", "S3 grad + H", "S4 Cholesky + solve", "S5a line-search setup", "obs + euler", "step barrier issue",
          "prologue", "epilogue", "C2 contact Jacobians", "C3 row parameters", "(issue of phase barrier)", "S5b line-search trips", "-", "-", "-", "-"]
 v = np.array(list(buf), dtype=np.float64)
 print(f"k_rollout phase shares, B={B} T={T} (clock64 per warp, summed)")
