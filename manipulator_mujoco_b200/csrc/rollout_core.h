@@ -439,18 +439,19 @@ KNOINLINE int plane_box(const float* ppos, const float* pn, const float* bpos, c
 // manifold reduced by the 4-point rule, or one edge-edge contact), with the 15 axes, the polygon edges
 // and the polygon vertices spread over lanes: the resting target_0 / table pair is evaluated every
 // step, and the scalar version on one lane was 30 % of all issued warp instructions (profiles/r1c).
-// Must be called by the whole warp.  Writes S.bstage[slot][k] = pos3, dist (dist = 1: unused) and
-// S.bnrm[slot]; returns the number of active contacts.
+// Called by the whole warp with warp-uniform control flow: both samples walk the same path (the union of
+// what they need) and `act` switches a sample's result writes off once it is done or if it does not test
+// this pair at all.  Writes S.bstage[slot][k] = pos3, dist (dist = 1: unused) and S.bnrm[slot].
 template <int NC>
-KFN int box_box_warp(Warp& W, WarpSmemT<NC>& S, int slot, const float* p1, const float* m1, const float* s1,
-                     const float* p2, const float* m2, const float* s2) {
-  DLANES(W, R)
+KFN void box_box_warp(Warp& W, WarpSmemT<NC>& S, bool act, int slot, const float* p1, const float* m1, const float* s1,
+                      const float* p2, const float* m2, const float* s2) {
+  LANES(W, R)
     if (lane < 9) { const int i = lane / 3, j = lane % 3; S.bbR[lane] = m2[i] * m1[j] + m2[3 + i] * m1[3 + j] + m2[6 + i] * m1[6 + j]; }
     else if (lane < 12) { const int i = lane - 9; S.bbc[i] = m2[i] * (p1[0] - p2[0]) + m2[3 + i] * (p1[1] - p2[1]) + m2[6 + i] * (p1[2] - p2[2]); }
-    else if (lane < 16) { float* o = S.bstage[slot][lane - 12]; o[0] = o[1] = o[2] = 0.f; o[3] = 1.f; }
-  END_DLANES
+    else if (lane < 16 && act) { float* o = S.bstage[slot][lane - 12]; o[0] = o[1] = o[2] = 0.f; o[3] = 1.f; }
+  END_LANES
   // ---- separating axes, one per lane ----
-  DLANES(W, R)
+  LANES(W, R)
     float cmp = -INFINITY, a0 = 0.f, a1 = 0.f, a2 = 1.f, sgn = 1.f;
     if (lane < 15) {
       const float* Rm = S.bbR; const float* c = S.bbc;
@@ -474,25 +475,27 @@ KFN int box_box_warp(Warp& W, WarpSmemT<NC>& S, int slot, const float* p1, const
       sgn = dc > 0.f ? -1.f : 1.f;          // contact normal points from box 1 (at c) to box 2 (origin)
     }
     R.f0 = cmp; R.f1 = a0 * sgn; R.f2 = a1 * sgn; R.acc[0] = a2 * sgn;
-  END_DLANES
-  const int bl = warp_argmax_first<true>(W, [](int, LaneRegs& R) { return R.f0; });
-  const float bestsep = warp_bcast<true>(W, bl, [](int, LaneRegs& R) { return R.f0; });
-  if (bestsep > 0.f) return 0;               // separated: no slot can be active
-  const float bn[3] = {warp_bcast<true>(W, bl, [](int, LaneRegs& R) { return R.f1; }), warp_bcast<true>(W, bl, [](int, LaneRegs& R) { return R.f2; }),
-                       warp_bcast<true>(W, bl, [](int, LaneRegs& R) { return R.acc[0]; })};
+  END_LANES
+  const int bl = warp_argmax_first(W, [](int, LaneRegs& R) { return R.f0; });
+  const float bestsep = warp_bcast(W, bl, [](int, LaneRegs& R) { return R.f0; });
+  act = act && !(bestsep > 0.f);             // separated: no slot can be active
+  if (!warp_any_groups(W, act)) return;
+  const float bn[3] = {warp_bcast(W, bl, [](int, LaneRegs& R) { return R.f1; }), warp_bcast(W, bl, [](int, LaneRegs& R) { return R.f2; }),
+                       warp_bcast(W, bl, [](int, LaneRegs& R) { return R.acc[0]; })};
   {
     float nw[3];
     mat_vec(nw, m2, bn);
     normalize3(nw);
-    DUNIFORM_WRITE(W) { copy3(S.bnrm[slot], nw); } END_DUNIFORM_WRITE
+    UNIFORM_WRITE(W) { if (act) copy3(S.bnrm[slot], nw); } END_UNIFORM_WRITE
   }
   float Rm[9], c[3];
 #pragma unroll
   for (int k = 0; k < 9; ++k) Rm[k] = S.bbR[k];
   c[0] = S.bbc[0]; c[1] = S.bbc[1]; c[2] = S.bbc[2];
-  if (bl >= 6) {
+  if (warp_any_groups(W, act && bl >= 6)) {
     // ---- edge-edge: closest points of the two support edges (uniform, rare) ----
-    const int bi = (bl - 6) / 3, bj = (bl - 6) % 3;
+    const int be = bl >= 6 ? bl - 6 : 0;       // (a face-face sample of the same warp computes a dummy pair)
+    const int bi = be / 3, bj = be % 3;
     float e1c[3] = {c[0], c[1], c[2]}, e2c[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -510,11 +513,12 @@ KFN int box_box_warp(Warp& W, WarpSmemT<NC>& S, int slot, const float* p1, const
     mat_vec(w, m2, mid); add3(w, w, p2);
     sub3(df, sp.b, sp.a);
     const float d = dot3(df, bn);
-    DUNIFORM_WRITE(W) { copy3(S.bstage[slot][0], w); S.bstage[slot][0][3] = d; } END_DUNIFORM_WRITE
-    return d < 0.f ? 1 : 0;
+    UNIFORM_WRITE(W) { if (act && bl >= 6) { copy3(S.bstage[slot][0], w); S.bstage[slot][0][3] = d; } } END_UNIFORM_WRITE
   }
+  act = act && bl < 6;
+  if (!warp_any_groups(W, act)) return;
   // ---- face-face: reference face on the box owning the axis, incident face on the other ----
-  const bool swap = bl >= 3;                   // reference = box 1
+  const bool swap = bl >= 3 && bl < 6;         // reference = box 1
   float rc[3], Rr[9], nref[3];
   if (!swap) {
     copy3(rc, c);
@@ -546,7 +550,7 @@ KFN int box_box_warp(Warp& W, WarpSmemT<NC>& S, int slot, const float* p1, const
   }
   // box face f = 2*axis + (0:+, 1:-), vertices counter-clockwise seen from outside:
   // in-plane signs (u, w) = (-,-),(+,-),(+,+),(-,+) for +k, reversed for -k  (u = k+1, w = k+2 cyclic)
-  DLANES(W, R)
+  LANES(W, R)
     if (lane < 8) {
       const bool ref = lane < 4;
       const int i = lane & 3;
@@ -563,31 +567,33 @@ KFN int box_box_warp(Warp& W, WarpSmemT<NC>& S, int slot, const float* p1, const
       if (ref) copy3(S.bbrf[i], v);
       else { float t[3]; mat_vec(t, Rr, v); add3(S.bbpoly[0][i], t, rc); }
     }
-  END_DLANES
-  DLANES(W, R)
+  END_LANES
+  LANES(W, R)
     if (lane < 4) {                            // outward side-plane normals of the reference face
       float e[3], en[3];
       sub3(e, S.bbrf[lane], S.bbrf[(lane + 3) & 3]);
       cross3(en, e, rn); normalize3(en);
       copy3(S.bben[lane], en);
     }
-  END_DLANES
+  END_LANES
   // ---- Sutherland-Hodgman against the four side planes, polygon edges on lanes; output slots by
   //      ballot (each edge emits its start vertex if inside, then the crossing point) ----
   int np = 4, cur = 0;
   // common case (a box resting on a larger one): every incident vertex is inside every side plane,
   // so clipping would return the polygon unchanged -- 16 tests on 16 lanes and one ballot
-  const unsigned outside = warp_ballot<true>(W, [&](int l, LaneRegs&) {
+  const unsigned outside = warp_ballot(W, [&](int l, LaneRegs&) {
     if (l >= 16) return false;
     float t[3];
     sub3(t, S.bbpoly[0][l & 3], S.bbrf[l >> 2]);
     return dot3(t, S.bben[l >> 2]) > 0.f;
   });
 #pragma unroll 1
-  for (int i = 0; i < 4 && np > 0 && outside != 0u; ++i) {
-    DLANES(W, R)
+  for (int i = 0; i < 4; ++i) {
+    const bool clip = act && np > 0 && outside != 0u;       // this sample still has something to clip
+    if (!warp_any_groups(W, clip)) break;
+    LANES(W, R)
       R.actmask = 0; R.f0 = 0.f;
-      if (lane < np) {
+      if (clip && lane < np) {
         const float* a = S.bbpoly[cur][lane]; const float* b = S.bbpoly[cur][lane + 1 == np ? 0 : lane + 1];
         float ta[3], tb[3];
         sub3(ta, a, S.bbrf[i]); sub3(tb, b, S.bbrf[i]);
@@ -596,23 +602,24 @@ KFN int box_box_warp(Warp& W, WarpSmemT<NC>& S, int slot, const float* p1, const
         R.actmask = (keep ? 1 : 0) | (cross ? 2 : 0);
         R.f0 = cross ? da / (da - db) : 0.f;
       }
-    END_DLANES
-    const unsigned mk = warp_ballot<true>(W, [](int, LaneRegs& R) { return (R.actmask & 1) != 0; });
-    const unsigned mx = warp_ballot<true>(W, [](int, LaneRegs& R) { return (R.actmask & 2) != 0; });
-    DLANES(W, R)
-      if (lane < np && R.actmask) {
+    END_LANES
+    const unsigned mk = warp_ballot(W, [](int, LaneRegs& R) { return (R.actmask & 1) != 0; });
+    const unsigned mx = warp_ballot(W, [](int, LaneRegs& R) { return (R.actmask & 2) != 0; });
+    LANES(W, R)
+      if (clip && lane < np && R.actmask) {
         const float* a = S.bbpoly[cur][lane]; const float* b = S.bbpoly[cur][lane + 1 == np ? 0 : lane + 1];
         const unsigned below = (1u << lane) - 1u;
         int o = KPOPC(mk & below) + KPOPC(mx & below);
         if (R.actmask & 1) { copy3(S.bbpoly[cur ^ 1][o], a); ++o; }
         if (R.actmask & 2) { float ab[3]; sub3(ab, b, a); madd3(S.bbpoly[cur ^ 1][o], a, ab, R.f0); }
       }
-    END_DLANES
-    np = KPOPC(mk) + KPOPC(mx); cur ^= 1;
+    END_LANES
+    if (clip) { np = KPOPC(mk) + KPOPC(mx); cur ^= 1; }
   }
-  if (np == 0) return 0;
+  act = act && np > 0;
+  if (!warp_any_groups(W, act)) return;
   // ---- penetrating vertices projected on the reference face; 4-point manifold ----
-  DLANES(W, R)
+  LANES(W, R)
     R.f0 = -1e6f; R.actmask = 0;
     if (lane < np) {
       float tt[3];
@@ -623,13 +630,13 @@ KFN int box_box_warp(Warp& W, WarpSmemT<NC>& S, int slot, const float* p1, const
       R.actmask = h < 0.f;
       R.f0 = h < 0.f ? 0.f : -1e6f;            // dm
     }
-  END_DLANES
-  if (np <= 4) {
+  END_LANES
+  if (warp_any_groups(W, act && np <= 4)) {
     // With at most four vertices MJX's 4-point rule returns exactly the penetrating ones (every
     // later pick prefers a not-yet-chosen vertex); emit them in polygon order.
-    const unsigned pen = warp_ballot<true>(W, [&](int l, LaneRegs& R) { return l < np && R.actmask != 0; });
-    DLANES(W, R)
-      if (pen & (1u << lane)) {
+    const unsigned pen = warp_ballot(W, [&](int l, LaneRegs& R) { return l < np && R.actmask != 0; });
+    LANES(W, R)
+      if (act && np <= 4 && (pen & (1u << lane))) {
         const int q = KPOPC(pen & ((1u << lane) - 1u));
         float w[3];
         if (swap) { float u[3]; mat_vec(u, Rm, S.bbpref[lane]); add3(u, u, c); mat_vec(w, m2, u); }
@@ -637,51 +644,49 @@ KFN int box_box_warp(Warp& W, WarpSmemT<NC>& S, int slot, const float* p1, const
         add3(w, w, p2);
         copy3(S.bstage[slot][q], w); S.bstage[slot][q][3] = S.bbpref[lane][3];
       }
-    END_DLANES
-    return KPOPC(pen);
+    END_LANES
   }
+  act = act && np > 4;
+  if (!warp_any_groups(W, act)) return;
   // lanes >= np must never win: give them -inf in every argmax
-  const int ia = warp_argmax_first8<true>(W, [&](int l, LaneRegs& R) { return l < np ? R.f0 : -INFINITY; });
-  DLANES(W, R)
+  const int ia = warp_argmax_first8(W, [&](int l, LaneRegs& R) { return l < np ? R.f0 : -INFINITY; });
+  LANES(W, R)
     R.f1 = -INFINITY;
     if (lane < np) { float t[3]; sub3(t, S.bbpref[ia], S.bbpref[lane]); R.f1 = dot3(t, t) + R.f0; }
-  END_DLANES
-  const int ib = warp_argmax_first8<true>(W, [](int, LaneRegs& R) { return R.f1; });
+  END_LANES
+  const int ib = warp_argmax_first8(W, [](int, LaneRegs& R) { return R.f1; });
   float ab[3];
   { float t[3]; sub3(t, S.bbpref[ia], S.bbpref[ib]); cross3(ab, rn, t); }
-  DLANES(W, R)
+  LANES(W, R)
     R.f1 = -INFINITY;
     if (lane < np) { float ap[3]; sub3(ap, S.bbpref[ia], S.bbpref[lane]); R.f1 = fabsf(dot3(ap, ab)) + R.f0; }
-  END_DLANES
-  const int ic = warp_argmax_first8<true>(W, [](int, LaneRegs& R) { return R.f1; });
+  END_LANES
+  const int ic = warp_argmax_first8(W, [](int, LaneRegs& R) { return R.f1; });
   float ac[3], bc[3];
   { float t[3]; sub3(t, S.bbpref[ia], S.bbpref[ic]); cross3(ac, rn, t); sub3(t, S.bbpref[ib], S.bbpref[ic]); cross3(bc, rn, t); }
-  DLANES(W, R)
+  LANES(W, R)
     R.f1 = -INFINITY;
     if (lane < np) {
       float bp[3], ap[3];
       sub3(bp, S.bbpref[ib], S.bbpref[lane]); sub3(ap, S.bbpref[ia], S.bbpref[lane]);
       R.f1 = fmaxf(fabsf(dot3(bp, bc)), fabsf(dot3(ap, ac))) + R.f0 - ((lane == ia || lane == ib || lane == ic) ? 2e6f : 0.f);
     }
-  END_DLANES
-  const int id = warp_argmax_first8<true>(W, [](int, LaneRegs& R) { return R.f1; });
+  END_LANES
+  const int id = warp_argmax_first8(W, [](int, LaneRegs& R) { return R.f1; });
   const int idx[4] = {ia, ib, ic, id};
-  int nact = 0;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     bool uniq = true;
 #pragma unroll
     for (int z = 0; z < q; ++z) if (idx[z] == idx[q]) uniq = false;
     const float h = S.bbpref[idx[q]][3];
-    if (!(h < 0.f) || !uniq) continue;
+    const bool put = act && h < 0.f && uniq;
     float w[3];
     if (swap) { float u[3]; mat_vec(u, Rm, S.bbpref[idx[q]]); add3(u, u, c); mat_vec(w, m2, u); }
     else mat_vec(w, m2, S.bbpref[idx[q]]);
     add3(w, w, p2);
-    DUNIFORM_WRITE(W) { copy3(S.bstage[slot][q], w); S.bstage[slot][q][3] = h; } END_DUNIFORM_WRITE
-    ++nact;
+    UNIFORM_WRITE(W) { if (put) { copy3(S.bstage[slot][q], w); S.bstage[slot][q][3] = h; } } END_UNIFORM_WRITE
   }
-  return nact;
 }
 
 // ------------------------------------------------------------------------------------------ constraints
@@ -1411,18 +1416,20 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
       }
       return overlap;
     });
+    // the loop runs over the pairs either sample of the warp has to test; a sample that does not need a
+    // pair walks through it with its writes switched off, so all fences stay full-warp
 #pragma unroll 1
-    for (unsigned rem = cand; rem != 0u; rem &= rem - 1u) {
+    for (unsigned rem = warp_or_groups(W, cand); rem != 0u; rem &= rem - 1u) {
       const int q = KFFS(rem) - 1;
+      const bool mine = (cand >> q) & 1u;
       const int ty = m.bp_type[q], a = m.bp_a[q];
       if (ty == KB_PLANE_BOX) {
-        DLANES(W, R)
-          if (lane == q) { plane_box(m.plane_pos, m.plane_n, bp, S.bmat, m.fb_size, S.bstage[q]); copy3(S.bnrm[q], m.plane_n); }
-        END_DLANES
-      } else if (ty == KB_BOX_BOX) box_box_warp<NC>(W, S, q, m.sb_pos[a], m.sb_mat[a], m.sb_size[a], bp, S.bmat, m.fb_size);
-      else box_box_warp<NC>(W, S, q, bp, S.bmat, m.fb_size, m.sb_pos[a], m.sb_mat[a], m.sb_size[a]);
+        LANES(W, R)
+          if (mine && lane == q) { plane_box(m.plane_pos, m.plane_n, bp, S.bmat, m.fb_size, S.bstage[q]); copy3(S.bnrm[q], m.plane_n); }
+        END_LANES
+      } else if (ty == KB_BOX_BOX) box_box_warp<NC>(W, S, mine, q, m.sb_pos[a], m.sb_mat[a], m.sb_size[a], bp, S.bmat, m.fb_size);
+      else box_box_warp<NC>(W, S, mine, q, bp, S.bmat, m.fb_size, m.sb_pos[a], m.sb_mat[a], m.sb_size[a]);
     }
-    REGROUP();                                  // the two samples of a warp may have tested different pairs
   }
   LANES(W, R)
     R.actmask = __float_as_int(R.h[0]);

@@ -303,3 +303,27 @@ KFN bool warp_all_groups(W& w, bool pred) {
   return __all_sync(0xffffffffu, pred);
 #endif
 }
+
+// true iff pred holds for some sample of the warp; converged code only
+template <class W>
+KFN bool warp_any_groups(W& w, bool pred) {
+#ifdef CEMK_EMU
+  (void)w;
+  return pred;
+#else
+  (void)w;
+  return __any_sync(0xffffffffu, pred);
+#endif
+}
+// bitwise OR of a group-uniform mask over the samples of the warp; converged code only
+template <class W>
+KFN unsigned warp_or_groups(W& w, unsigned m) {
+#ifdef CEMK_EMU
+  (void)w;
+  return m;
+#else
+  (void)w;
+  return __reduce_or_sync(0xffffffffu, m);
+#endif
+}
+
