@@ -1086,11 +1086,16 @@ KFN void solve_rows(Warp& W, const KModel& m, WarpSmemT<NC>& S, const int ncon, 
       const float mv = mul_M<NC>(m, S, lane, S.search), s = S.search[lane];
       e0 = s * s; e1 = s * S.Ma[lane] - s * S.fs[lane]; e2 = 0.5f * s * mv;
     }
+    // the lane's first row stays in registers for the line-search trips (R.h is free after the solve):
+    // ja, jv and the three quadratic coefficients; an idle lane gets a row that is never active
+    R.h[0] = 1.f; R.h[1] = 0.f; R.h[2] = 0.f; R.h[3] = 0.f; R.h[4] = 0.f;
 #pragma unroll 1
     for (int r = lane; r < nrow; r += KW) {
       const float jv = row_val<NC, SP>(S, 0, r, S.search), ja = S.template Jaref<SP>(r, nlim), D = S.template D<SP>(r, nlim);
       S.template Jv<SP>(r, nlim) = jv;
-      if (ja < 0.f) { a0 += 0.5f * D * ja * ja; a1 += D * jv * ja; a2 += 0.5f * D * jv * jv; }
+      const float q0 = 0.5f * D * ja * ja, q1 = D * jv * ja, q2 = 0.5f * D * jv * jv;
+      if (r == lane) { R.h[0] = ja; R.h[1] = jv; R.h[2] = q0; R.h[3] = q1; R.h[4] = q2; }
+      if (ja < 0.f) { a0 += q0; a1 += q1; a2 += q2; }
     }
     R.acc[0] = e0; R.acc[1] = e1; R.acc[2] = e2; R.acc[3] = a0; R.acc[4] = a1; R.acc[5] = a2; R.acc[6] = R.acc[7] = R.acc[8] = 0.f;
   END_LANES
@@ -1122,10 +1127,17 @@ KFN void solve_rows(Warp& W, const KModel& m, WarpSmemT<NC>& S, const int ncon, 
       if (warp_all_groups(W, done)) break;
       al0 = lo.alpha - lo.d0 / lo.d1; al1 = hi.alpha - hi.d0 / hi.d1; al2 = 0.5f * (lo.alpha + hi.alpha);
     }
-    LANES(W, R)
+    // rows are read-only here and the sums live in registers: no fences inside the loop
+    RLANES(W, R)
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+      {
+        const float ja = R.h[0], jv = R.h[1], q0 = R.h[2], q1 = R.h[3], q2 = R.h[4];
+        if (ja + al0 * jv < 0.f) { a0 = q0; a1 = q1; a2 = q2; }
+        if (ja + al1 * jv < 0.f) { b0 = q0; b1 = q1; b2 = q2; }
+        if (ja + al2 * jv < 0.f) { c0 = q0; c1 = q1; c2 = q2; }
+      }
 #pragma unroll 1
-      for (int r = lane; r < nrow; r += KW) {
+      for (int r = lane + KW; r < nrow; r += KW) {             // more than KW rows: the rest from shared memory
         const float ja = S.template Jaref<SP>(r, nlim), jv = S.template Jv<SP>(r, nlim), D = S.template D<SP>(r, nlim);
         const float q0 = 0.5f * D * ja * ja, q1 = D * jv * ja, q2 = 0.5f * D * jv * jv;
         if (ja + al0 * jv < 0.f) { a0 += q0; a1 += q1; a2 += q2; }
@@ -1133,7 +1145,7 @@ KFN void solve_rows(Warp& W, const KModel& m, WarpSmemT<NC>& S, const int ncon, 
         if (ja + al2 * jv < 0.f) { c0 += q0; c1 += q1; c2 += q2; }
       }
       R.acc[0] = a0; R.acc[1] = a1; R.acc[2] = a2; R.acc[3] = b0; R.acc[4] = b1; R.acc[5] = b2; R.acc[6] = c0; R.acc[7] = c1; R.acc[8] = c2;
-    END_LANES
+    END_RLANES
     float sums[9];
     warp_sum9(W, sums);
     LSPoint pt[3];
