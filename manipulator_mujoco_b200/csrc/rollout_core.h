@@ -824,12 +824,26 @@ KFN void chol_solve_rows(Warp& W) {
 template <int NC, bool SP>
 KFN float hess_contacts(const WarpSmemT<NC>& S, unsigned sel, int ncon, int i, int j) {
   float h = 0.f;
-#pragma unroll 1
-  for (unsigned rem = sel; rem != 0u; rem &= rem - 1u) {
-    const int c = KFFS(rem) - 1;
+  auto term = [&](int c) {
     const float* g = S.template geo<SP>(c); const float* J = S.template jac<SP>(c);
     const float ni = J[i], nj = J[j], ai = J[12 + i], aj = J[12 + j], bi = J[24 + i], bj = J[24 + j];
-    h += g[3] * (ni + ai) * (nj + aj) + g[4] * (ni - ai) * (nj - aj) + g[5] * (ni + bi) * (nj + bj) + g[6] * (ni - bi) * (nj - bj);
+    return g[3] * (ni + ai) * (nj + aj) + g[4] * (ni - ai) * (nj - aj) + g[5] * (ni + bi) * (nj + bj) + g[6] * (ni - bi) * (nj - bj);
+  };
+  if (sel != 0u && KPOPC(sel) <= 4) {
+    // up to four contacts (the resting box): the four terms are independent, only their sum is ordered
+    unsigned rem = sel;
+    const int c0 = KFFS(rem) - 1; rem &= rem - 1u;
+    const bool v1 = rem != 0u; const int c1 = v1 ? KFFS(rem) - 1 : c0; rem &= rem - 1u;
+    const bool v2 = rem != 0u; const int c2 = v2 ? KFFS(rem) - 1 : c0; rem &= rem - 1u;
+    const bool v3 = rem != 0u; const int c3 = v3 ? KFFS(rem) - 1 : c0;
+    const float t0 = term(c0), t1 = term(c1), t2 = term(c2), t3 = term(c3);
+    h = t0;
+    if (v1) h += t1;
+    if (v2) h += t2;
+    if (v3) h += t3;
+  } else {
+#pragma unroll 1
+    for (unsigned rem = sel; rem != 0u; rem &= rem - 1u) h += term(KFFS(rem) - 1);
   }
   if (KM_NC_TOT > 32) {
 #pragma unroll 1
@@ -908,19 +922,18 @@ KFN void solve_rows(Warp& W, const KModel& m, WarpSmemT<NC>& S, const int ncon, 
   PHASE(W, 16);
   // ---- C2: contact Jacobians in the contact frame: Jn, mu*Jt1, mu*Jt2 ----
   LANES(W, R)
-    const int d = lane & 15;
-    if (d < KM_NV) {
+    // one (contact, dof) item per lane
 #pragma unroll 1
-      for (int c = lane >> 4; c < ncon; c += KW / 16) {
-        const float* g = S.template geo<SP>(c);
-        float c1[3], c2[3], df[3];
-        jac_col(m, S, g, (int)g[14], d, c1);
-        jac_col(m, S, g, (int)g[15], d, c2);
-        sub3(df, c2, c1);
-        S.template jac<SP>(c)[d] = dot3(g + 3, df);
-        S.template jac<SP>(c)[12 + d] = m.mu * dot3(g + 6, df);
-        S.template jac<SP>(c)[24 + d] = m.mu * dot3(g + 9, df);
-      }
+    for (int e = lane; e < KM_NV * ncon; e += KW) {
+      const int c = e / KM_NV, d = e - KM_NV * c;
+      const float* g = S.template geo<SP>(c);
+      float c1[3], c2[3], df[3];
+      jac_col(m, S, g, (int)g[14], d, c1);
+      jac_col(m, S, g, (int)g[15], d, c2);
+      sub3(df, c2, c1);
+      S.template jac<SP>(c)[d] = dot3(g + 3, df);
+      S.template jac<SP>(c)[12 + d] = m.mu * dot3(g + 6, df);
+      S.template jac<SP>(c)[24 + d] = m.mu * dot3(g + 9, df);
     }
   END_LANES
   PHASE(W, 17);
@@ -1009,11 +1022,27 @@ KFN void solve_rows(Warp& W, const KModel& m, WarpSmemT<NC>& S, const int ncon, 
     if (lane < KM_NV) {
       float fc = 0.f;
       for (int r = 0; r < nlim; ++r) { const float ja = S.rJaref[r]; if (ja < 0.f && S.limdof[r] == lane) fc += S.limsign[r] * (-S.rD[r] * ja); }
+      {
+        const unsigned sel = lane < KM_NL ? mrob : mbox;
+        auto term = [&](int c) {
+          const float* g = S.template geo<SP>(c); const float* J = S.template jac<SP>(c);
+          return J[lane] * g[0] + J[12 + lane] * g[1] + J[24 + lane] * g[2];
+        };
+        if (sel != 0u && KPOPC(sel) <= 4) {
+          unsigned rem = sel;
+          const int c0 = KFFS(rem) - 1; rem &= rem - 1u;
+          const bool v1 = rem != 0u; const int c1 = v1 ? KFFS(rem) - 1 : c0; rem &= rem - 1u;
+          const bool v2 = rem != 0u; const int c2 = v2 ? KFFS(rem) - 1 : c0; rem &= rem - 1u;
+          const bool v3 = rem != 0u; const int c3 = v3 ? KFFS(rem) - 1 : c0;
+          const float t0 = term(c0), t1 = term(c1), t2 = term(c2), t3 = term(c3);
+          fc += t0;
+          if (v1) fc += t1;
+          if (v2) fc += t2;
+          if (v3) fc += t3;
+        } else {
 #pragma unroll 1
-      for (unsigned rem = lane < KM_NL ? mrob : mbox; rem != 0u; rem &= rem - 1u) {
-        const int c = KFFS(rem) - 1;
-        const float* g = S.template geo<SP>(c); const float* J = S.template jac<SP>(c);
-        fc += J[lane] * g[0] + J[12 + lane] * g[1] + J[24 + lane] * g[2];
+          for (unsigned rem = sel; rem != 0u; rem &= rem - 1u) fc += term(KFFS(rem) - 1);
+        }
       }
       if (KM_NC_TOT > 32) {
 #pragma unroll 1
