@@ -1225,14 +1225,23 @@ KFN void solve_rows(Warp& W, const KModel& m, WarpSmemT<NC>& S, const int ncon, 
 template <int NC>
 KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& io) {
   PHASE(W, 1);
-  // ---- P1: joint chain.  Local link rotations (body quat x joint rotation) on six lanes, then the
-  //      serial composition down the chain in uniform code ----
+  // ---- P1: joint chain as a parallel prefix of rigid transforms.  Lane 0 holds the static base frame, lane
+  //      i = 1..6 the local transform of link i-1 (body quat x joint rotation, body offset); composition
+  //      (qa, pa) o (qb, pb) = (qa qb, pa + R(qa) pb) is associative, so three shuffle rounds replace the six
+  //      dependent link-by-link products.  R.h[0..3] = quaternion, R.h[4..6] = position. ----
   LANES(W, R)
-    if (lane < KM_NL) {
-      float sn, cs, qj[4];
-      k_sincos(0.5f * S.qpos[lane], &sn, &cs);
-      qj[0] = cs; qj[1] = sn * m.l_axis[lane][0]; qj[2] = sn * m.l_axis[lane][1]; qj[3] = sn * m.l_axis[lane][2];
-      quat_mul(S.lquat[lane], m.l_quat[lane], qj);
+    R.h[0] = 1.f; R.h[1] = R.h[2] = R.h[3] = 0.f; R.h[4] = R.h[5] = R.h[6] = 0.f;
+    if (lane == 0) {
+      R.h[0] = m.base_quat[0]; R.h[1] = m.base_quat[1]; R.h[2] = m.base_quat[2]; R.h[3] = m.base_quat[3];
+      R.h[4] = m.base_pos[0]; R.h[5] = m.base_pos[1]; R.h[6] = m.base_pos[2];
+    } else if (lane <= KM_NL) {
+      const int i = lane - 1;
+      float sn, cs, qj[4], ql[4];
+      k_sincos(0.5f * S.qpos[i], &sn, &cs);
+      qj[0] = cs; qj[1] = sn * m.l_axis[i][0]; qj[2] = sn * m.l_axis[i][1]; qj[3] = sn * m.l_axis[i][2];
+      quat_mul(ql, m.l_quat[i], qj);
+      R.h[0] = ql[0]; R.h[1] = ql[1]; R.h[2] = ql[2]; R.h[3] = ql[3];
+      R.h[4] = m.l_pos[i][0]; R.h[5] = m.l_pos[i][1]; R.h[6] = m.l_pos[i][2];
     } else if (lane == 8 && m.has_box) {
       float* q = S.qpos + KM_NL + 3;
       float inv = 1.f / sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
@@ -1240,27 +1249,38 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
       quat_to_mat(S.bmat, q);
     }
   END_LANES
-  {
-    float pq[4] = {m.base_quat[0], m.base_quat[1], m.base_quat[2], m.base_quat[3]};
-    float pp[3] = {m.base_pos[0], m.base_pos[1], m.base_pos[2]}, pm[9];
-    quat_to_mat(pm, pq);
-#pragma unroll 1
-    for (int i = 0; i < KM_NL; ++i) {
-      float p[3], q[4], t[3], lq[4], mat[9];
-      lq[0] = S.lquat[i][0]; lq[1] = S.lquat[i][1]; lq[2] = S.lquat[i][2]; lq[3] = S.lquat[i][3];
-      mat_vec(t, pm, m.l_pos[i]); add3(p, pp, t);
-      quat_mul(q, pq, lq);
-      quat_to_mat(mat, q);
-      UNIFORM_WRITE(W) {
-        copy3(S.lpos[i], p);
-        for (int k = 0; k < 4; ++k) S.lquat[i][k] = q[k];
-        for (int k = 0; k < 9; ++k) S.lmat[i][k] = mat[k];
-      } END_UNIFORM_WRITE
-      copy3(pp, p);
-      for (int k = 0; k < 4; ++k) pq[k] = q[k];
-      for (int k = 0; k < 9; ++k) pm[k] = mat[k];
-    }
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {
+    // fetch the prefix that ends o lanes below (R.acc[0..6] as the receive buffer), then compose
+#pragma unroll
+    for (int k = 0; k < 7; ++k)
+      warp_shfl_each(W, [&](int, LaneRegs& R) { return R.h[k]; }, [&](int l) { return l >= o ? l - o : l; },
+                     [&](int, LaneRegs& R, float v) { R.acc[k] = v; });
+    RLANES(W, R)
+      if (lane >= o && lane <= KM_NL) {
+        const float qa[4] = {R.acc[0], R.acc[1], R.acc[2], R.acc[3]}, qb[4] = {R.h[0], R.h[1], R.h[2], R.h[3]};
+        const float pb[3] = {R.h[4], R.h[5], R.h[6]};
+        float q[4], t[3], u[3];
+        quat_mul(q, qa, qb);
+        // R(qa) pb = pb + 2 w (v x pb) + 2 v x (v x pb),  qa = (w, v)
+        cross3(t, qa + 1, pb);
+        cross3(u, qa + 1, t);
+        R.h[0] = q[0]; R.h[1] = q[1]; R.h[2] = q[2]; R.h[3] = q[3];
+        R.h[4] = R.acc[4] + pb[0] + 2.f * (qa[0] * t[0] + u[0]);
+        R.h[5] = R.acc[5] + pb[1] + 2.f * (qa[0] * t[1] + u[1]);
+        R.h[6] = R.acc[6] + pb[2] + 2.f * (qa[0] * t[2] + u[2]);
+      }
+    END_RLANES
   }
+  LANES(W, R)
+    if (lane >= 1 && lane <= KM_NL) {
+      const int i = lane - 1;
+      const float q[4] = {R.h[0], R.h[1], R.h[2], R.h[3]};
+      S.lpos[i][0] = R.h[4]; S.lpos[i][1] = R.h[5]; S.lpos[i][2] = R.h[6];
+      for (int k = 0; k < 4; ++k) S.lquat[i][k] = q[k];
+      quat_to_mat(S.lmat[i], q);
+    }
+  END_LANES
   PHASE(W, 2);
   // ---- P2: per-link spatial quantities, capsule end points, box frame ----
   LANES(W, R)
