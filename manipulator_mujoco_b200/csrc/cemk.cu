@@ -48,7 +48,7 @@ struct cemk_handle {
   float* d_prevd; int prevd_cap;   // previous-step slot distances of every sample (rollout scratch, stays in L2)
   float* d_ovf;                    // contact spill area of every sample (same capacity as d_prevd)
   int force_rerun;               // debug option: recompute every sample with the all-in-shared-memory instantiation
-  int cta_warps;                 // debug option "cta_samples": fixed number of samples per CTA (0 = see cemk_rollout_cost)
+  int cta_samples;                 // debug option "cta_samples": fixed number of samples per CTA (0 = see cemk_rollout_cost)
 };
 
 // ---------------------------------------------------------------------------------------------- rollout
@@ -545,7 +545,7 @@ int cemk_create(const void* kmodel, int kmodel_bytes, int device, cemk_handle** 
     return set_err(CEMK_ERR_MODEL, "cemk_create: unsupported topology");
   CK(cudaSetDevice(device));
   cemk_handle* h = new cemk_handle();
-  h->device = device; h->T = 0; h->d_G = nullptr; h->d_K = nullptr; h->launches = 0; h->d_flags = nullptr; h->flags_cap = 0; h->force_rerun = 0; h->cta_warps = 0; h->d_prevd = nullptr; h->prevd_cap = 0; h->d_ovf = nullptr;
+  h->device = device; h->T = 0; h->d_G = nullptr; h->d_K = nullptr; h->launches = 0; h->d_flags = nullptr; h->flags_cap = 0; h->force_rerun = 0; h->cta_samples = 0; h->d_prevd = nullptr; h->prevd_cap = 0; h->d_ovf = nullptr;
   { cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device)); h->num_sms = prop.multiProcessorCount; }
   CK(cudaMalloc(&h->d_model, sizeof(KModel)));
   CK(cudaMemcpy(h->d_model, kmodel, sizeof(KModel), cudaMemcpyHostToDevice));
@@ -659,8 +659,8 @@ int cemk_rollout_cost(cemk_handle* h, int B, int T, const float* thetadot, const
   int grid;
 #define CEMK_LAUNCH_ROLLOUT(W_) k_rollout<KM_NC_FAST, W_, false><<<grid, (W_) * 32, rollout_smem<KM_NC_FAST, W_>(), st>>>(h->d_model, a)
   const int need = (B + nsm - 1) / nsm;                            // samples per SM
-  if (h->cta_warps > 0) {
-    const int w = h->cta_warps < cap ? h->cta_warps : cap;
+  if (h->cta_samples > 0) {
+    const int w = h->cta_samples < cap ? h->cta_samples : cap;
     a.n_hi = 0; a.w_hi = a.w_lo = w; grid = (B + w - 1) / w;
     CEMK_LAUNCH_ROLLOUT(ROLLOUT_WARPS);
   } else if (need <= cap) {
@@ -796,7 +796,7 @@ long long cemk_launch_count(cemk_handle* h) { return h ? h->launches : 0; }
 int cemk_set_option(cemk_handle* h, const char* name, int value) {
   if (!h || !name) return set_err(CEMK_ERR_ARG, "cemk_set_option: null argument");
   if (!strcmp(name, "force_rerun")) { h->force_rerun = value != 0; return CEMK_OK; }
-  if (!strcmp(name, "cta_samples")) { h->cta_warps = value > 0 ? value : 0; return CEMK_OK; }
+  if (!strcmp(name, "cta_samples")) { h->cta_samples = value > 0 ? value : 0; return CEMK_OK; }
   return set_err(CEMK_ERR_ARG, "cemk_set_option: unknown option");
 }
 

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Compile k_rollout variants (samples per CTA x min CTAs/SM => register cap) on the GPU box and time them.
-# usage: tools/sweep_rollout.sh "4:1 4:4 4:5 4:6 8:2 8:3 8:4"
+# usage: tools/sweep_rollout.sh "14:1 12:1 8:1"      (warps per CTA : min CTAs per SM; at most 14 warps = 28 samples fit the shared memory)
 set -e
 cd "$(dirname "$0")/.."
 for v in $1; do
