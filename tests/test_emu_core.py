@@ -201,3 +201,33 @@ def test_free_box_contacts_in_odd_poses_match_oracle(emu, oracle64, oracle32, mc
     assert checked >= 40 and len(seen) >= 3, (checked, seen)          # 1 (edge-edge), 2-3 (clipped), 4 (face) contacts all occur
     assert (dev < 5e-2).all(), np.sort(dev)[-5:]
     assert (dev < 1e-3).mean() >= 0.85, np.sort(dev)[-10:]
+
+
+def test_spill_area_with_robot_box_coupling(emu, oracle64, mc):
+    """Deep in the table *and* touching the free box: the spill-capable instantiation of the solve together with
+    the coupled 12x12 system.  Bit-identical to the all-in-shared-memory instantiation over a short horizon."""
+    rng = np.random.default_rng(8)
+    hits = 0
+    for q in ([1.181, 0.789, -0.949, -0.051, 2.391, -0.535], [1.168, 0.758, -0.921, -0.796, 0.168, 2.145]):
+        q = np.array(q)
+        tcp = oracle64.forward(np.concatenate([q, mc.qpos0[6:]]), np.zeros(12))["site_tcp"]
+        for _ in range(6):
+            qbox = np.concatenate([tcp + rng.normal(size=3) * 0.015, [1.0, 0, 0, 0]])
+            r = oracle64.forward(np.concatenate([q, qbox]), np.zeros(12))
+            nact = int((r["con_dist"] < 0).sum())
+            if nact <= 20:
+                continue
+            km = copy.copy(emu.km)
+            for i in range(13):
+                km.qpos0[i] = np.concatenate([q, qbox])[i]
+            for i in range(12):
+                km.warm0[i], km.qvel0[i] = 0.0, 0.0
+            T = 5
+            td = rng.normal(size=(1, 6 * T)) * 0.2
+            a = emu.rollout(td, q, np.zeros(6), TARGET_POS, TARGET_ROT, nc=20, km=km)
+            b = emu.rollout(td, q, np.zeros(6), TARGET_POS, TARGET_ROT, nc=48, km=km)
+            for key in ("theta", "cost4", "qacc", "collision"):
+                np.testing.assert_array_equal(a[key].view(np.int32), b[key].view(np.int32), err_msg=f"{key} ({nact} contacts)")
+            np.testing.assert_allclose(a["collision"][0, 0], r["con_dist"][oracle64.mask], atol=2e-5)
+            hits += 1
+    assert hits >= 2
