@@ -82,3 +82,23 @@ def test_rollout_against_mjx(mj, mc, oracle64):
     np.testing.assert_allclose(np.abs(np.asarray(eef_rot)), np.abs(oer), atol=5e-4)
     # the far-field convention of capsule_convex shows up here first
     assert (np.abs(np.asarray(col) - ocol) > 1e-3).mean() < 1e-3
+
+
+def test_jax_random_stream_restatement():
+    """The sampler's key chain and draws against jax.random itself (mjx_planner.py:80,314-315,388): would pin
+    `jax_prng` / `oracle/jax_random_ref.py` for the counter layout of the installed jax (default config)."""
+    import jax.numpy as jnp
+    from manipulator_mujoco_b200 import jax_prng
+    from oracle import jax_random_ref as ref
+    part = bool(jax.config.jax_threefry_partitionable)
+    key = jax.random.PRNGKey(0)
+    np.testing.assert_array_equal(np.asarray(jax.random.key_data(key)), jax_prng.PRNGKey(0))
+    k1, _ = jax.random.split(key)
+    np.testing.assert_array_equal(np.asarray(jax.random.key_data(k1)), jax_prng.split(jax_prng.PRNGKey(0), 2, part)[0])
+    k2, _ = jax.random.split(k1)
+    mean = jnp.zeros(66)
+    cov = 10 * jnp.identity(66) + 0.003 * jnp.identity(66)
+    xi = np.asarray(jax.random.multivariate_normal(k2, mean, cov, (64,)))
+    mine = ref.multivariate_normal(jax_prng.split(jax_prng.split(jax_prng.PRNGKey(0), 2, part)[0], 2, part)[0],
+                                   np.zeros(66), np.asarray(cov, dtype=np.float64), 64, part)
+    np.testing.assert_allclose(xi, mine, rtol=0, atol=2e-5)
