@@ -17,7 +17,8 @@
 //     is constant and diagonal and its bias is  [-m g ; w x I w];
 //   * only rows of active constraints (dist < 0, limit violated) are built: MJX multiplies the
 //     Jacobian of every inactive row by zero, which leaves H, grad and the line search untouched;
-//   * capsule-box uses the closed form for rectangular faces of `_clip_edge_to_planes`.
+//   * capsule-box evaluates MJX's `_capsule_convex` only inside its near zone (see capsule_box): outside it
+//     both slots are the +1 sentinel by construction (has_support gate), which six min/max decide.
 //
 // Written against warp_dsl.h so that tests/emu can single-step it on the CPU.
 #pragma once
@@ -265,7 +266,128 @@ KFN void capsule_capsule(const float* a0, const float* a1, float r1, const float
   c.dist[1] = 1.f;
   if (FULL) { madd3(c.pos[0], sp.a, n, r1 + 0.5f * c.dist[0]); copy3(c.nrm[0], n); }
 }
-// capsule (geom1) vs box (geom2), MJX capsule_convex with rectangular faces; see header note.
+// capsule (geom1) vs box (geom2): MJX collision_convex._capsule_convex for a box, restated in oracle/mjstep.c
+// (capsule_box, mode 1).  Both slots are the "no contact" sentinel dist = +1 unless
+//   * every face plane has an end point of the radius-inflated segment behind it (has_support) and the
+//     segment clips against the side planes of the best face (then: face distances of the clipped points), or
+//   * one of the 12 box edges is a shallow contact (closer than r, capsule point in front of both faces
+//     adjacent to the edge), which replaces slot 0.
+// Far field: if some box axis separates the segment's bounding interval from the box by >= r, has_support
+// fails and no edge can be within r, so the pair costs one change of frame and six min/max (capbox_far).
+// Everything else is a cold out-of-line call (capsule_box_near), in box coordinates.
+#ifndef CEMK_CAPBOX_LEGACY
+KFN void capbox_local(const float* A, const float* B, const float* bpos, const float* bmat, float* a, float* b) {
+  float t[3];
+  sub3(t, A, bpos); matT_vec(a, bmat, t);
+  sub3(t, B, bpos); matT_vec(b, bmat, t);
+}
+KFN bool capbox_far(const float* a, const float* b, float r, const float* s) {
+  const float s0 = fmaxf(fminf(a[0], b[0]), -fmaxf(a[0], b[0])) - s[0];
+  const float s1 = fmaxf(fminf(a[1], b[1]), -fmaxf(a[1], b[1])) - s[1];
+  const float s2 = fmaxf(fminf(a[2], b[2]), -fmaxf(a[2], b[2])) - s[2];
+  return !(fmaxf(fmaxf(s0, s1), s2) < r);
+}
+struct CapBoxOut { float dist[2], pos[2][3], nrm[2][3]; };     // box coordinates
+KNOINLINE void capsule_box_near(float ax, float ay, float az, float bx, float by, float bz, float r, float sx, float sy, float sz,
+                                CapBoxOut* o) {
+  const float a[3] = {ax, ay, az}, b[3] = {bx, by, bz}, bsize[3] = {sx, sy, sz};
+  // best face: first argmax over (+x,-x,+y,-y,+z,-z) of min over end points of the inflated signed face distance
+  int bf = 0; bool has_support = true; float bests = 0.f;
+#pragma unroll 1
+  for (int f = 0; f < 6; ++f) {
+    const int k = f >> 1; const float sg = (f & 1) ? -1.f : 1.f;
+    const float sup = fminf(sg * a[k], sg * b[k]) - r - bsize[k];
+    if (f == 0 || sup > bests) { bests = sup; bf = f; }
+    if (!(sup < 0.f)) has_support = false;
+  }
+  const int bk = bf >> 1, iu = (bk + 1) % 3, iw = (bk + 2) % 3;
+  const float sg = (bf & 1) ? -1.f : 1.f;
+  const float ak = a[bk], au = a[iu], aw = a[iw], bk_ = b[bk], bu = b[iu], bw = b[iw], sk = bsize[bk], su = bsize[iu], sw = bsize[iw];
+  // clip the segment (parameter 0..1 from a to b) against the four side planes: closed form of MJX
+  // _clip_edge_to_planes for a rectangular face
+  float t0 = 0.f, t1 = 1.f; bool both = false;
+  {
+    const float Lu = 2.f * sw, Lw = 2.f * su;      // length of the edge each side plane is built on
+#define CEMK_CLIP(pa, pb, s, tau, L) { \
+      float na_ = ((tau) * (pa) - (s)) * (L), nb_ = ((tau) * (pb) - (s)) * (L); \
+      bool fa = na_ > 1e-6f, fb = nb_ > 1e-6f; \
+      float den = (tau) * ((pb) - (pa)) * (L); \
+      float tt = (-na_) / (den + (den == 0.f ? 1e-6f : 0.f)); \
+      tt = fminf(fmaxf(tt, 0.f), 1.f); \
+      if (fa) t0 = fmaxf(t0, tt); \
+      if (fb) t1 = fminf(t1, tt); \
+      both = both || (fa && fb); }
+    CEMK_CLIP(au, bu, su, -1.f, Lu)
+    CEMK_CLIP(aw, bw, sw, -1.f, Lw)
+    CEMK_CLIP(au, bu, su, 1.f, Lu)
+    CEMK_CLIP(aw, bw, sw, 1.f, Lw)
+#undef CEMK_CLIP
+  }
+  bool mask = !both;
+  if (!mask) { t0 = 0.f; t1 = 1.f; }
+  {
+    const float dk = bk_ - ak, du = bu - au, dw = bw - aw;
+    if ((t1 - t0) * (dk * dk + du * du + dw * dw) < 0.f) mask = false;
+  }
+  const float h0 = sg * (ak + t0 * (bk_ - ak)) - r - sk, h1 = sg * (ak + t1 * (bk_ - ak)) - r - sk;
+  const bool face_ok = mask && has_support;
+  float pen0 = face_ok ? -h0 : -1.f, pen1 = face_ok ? -h1 : -1.f;
+  float n[3] = {0.f, 0.f, 0.f};
+  n[bk] = sg;
+  o->pos[0][bk] = sg * (sk + 0.5f * h0); o->pos[0][iu] = au + t0 * (bu - au); o->pos[0][iw] = aw + t0 * (bw - aw);
+  o->pos[1][bk] = sg * (sk + 0.5f * h1); o->pos[1][iu] = au + t1 * (bu - au); o->pos[1][iw] = aw + t1 * (bw - aw);
+  for (int q = 0; q < 3; ++q) { o->nrm[0][q] = -n[q]; o->nrm[1][q] = -n[q]; }
+  // shallow edge contact: edge e = 4k + 2iu + iw runs along axis k at (u, w) = (+-s_u, +-s_w)
+  float bpen = -1.f, beax[3] = {0.f, 0.f, 0.f}, bec[3] = {0.f, 0.f, 0.f}, bcc[3] = {0.f, 0.f, 0.f};
+  bool bdeg = false;
+#pragma unroll 1
+  for (int e = 0; e < 12; ++e) {
+    const int k = e >> 2, u = (k + 1) % 3, w = (k + 2) % 3;
+    const float eu = (e & 2) ? 1.f : -1.f, ew = (e & 1) ? 1.f : -1.f;
+    float e0[3], e1[3];
+    e0[k] = -bsize[k]; e1[k] = bsize[k]; e0[u] = e1[u] = eu * bsize[u]; e0[w] = e1[w] = ew * bsize[w];
+    const SegPair sp = closest_seg_seg(e0[0], e0[1], e0[2], e1[0], e1[1], e1[2], ax, ay, az, bx, by, bz);
+    float dir[3];
+    sub3(dir, sp.a, sp.b);
+    const bool deg = dot3(dir, dir) < 1e-6f;
+    const float ed = normalize3(dir);
+    const bool front = (eu * dir[u] < 0.f) && (ew * dir[w] < 0.f);
+    const float epen = (!deg && front) ? r - ed : -1.f;
+    if (e == 0 || epen > bpen) { bpen = epen; bdeg = deg; copy3(beax, dir); copy3(bec, sp.a); copy3(bcc, sp.b); }
+  }
+  const bool parallel = fabsf(dot3(beax, n)) > 0.99f && !bdeg;
+  const float minface = fminf(pen0, pen1);
+  const bool has_edge = bpen > 0.f && (minface > 0.f ? bpen < minface : true) && !parallel;
+  if (has_edge) {
+    pen0 = bpen;
+    for (int q = 0; q < 3; ++q) { o->pos[0][q] = 0.5f * (bec[q] + bcc[q] + beax[q] * r); o->nrm[0][q] = beax[q]; }
+  }
+  o->dist[0] = -pen0; o->dist[1] = -pen1;
+}
+template <bool FULL>
+KFN void capsule_box(const float* A, const float* B, float r, const float* bpos, const float* bmat, const float* bsize, Contact2& c) {
+  float a[3], b[3];
+  capbox_local(A, B, bpos, bmat, a, b);
+  c.dist[0] = 1.f; c.dist[1] = 1.f;
+  if (capbox_far(a, b, r, bsize)) {
+    if (FULL) { for (int j = 0; j < 2; ++j) { copy3(c.pos[j], bpos); c.nrm[j][0] = 1.f; c.nrm[j][1] = 0.f; c.nrm[j][2] = 0.f; } }
+    return;
+  }
+  CapBoxOut o;
+  capsule_box_near(a[0], a[1], a[2], b[0], b[1], b[2], r, bsize[0], bsize[1], bsize[2], &o);
+  c.dist[0] = o.dist[0]; c.dist[1] = o.dist[1];
+  if (FULL) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      float w[3];
+      mat_vec(w, bmat, o.pos[j]); add3(c.pos[j], w, bpos);
+      mat_vec(c.nrm[j], bmat, o.nrm[j]);
+      normalize3(c.nrm[j]);
+    }
+  }
+}
+#else
+// round-1 restatement (no has_support gate; true far-field face distances), kept for tools/capbox_ab.py only
 template <bool FULL>
 KFN void capsule_box(const float* A, const float* B, float r, const float* bpos, const float* bmat, const float* bsize, Contact2& c) {
   float t[3], a[3], b[3];
@@ -366,6 +488,7 @@ KFN void capsule_box(const float* A, const float* B, float r, const float* bpos,
     }
   }
 }
+#endif
 KFN Dist2 capsule_box_dist(const float* A, const float* B, float r, const float* bpos, const float* bmat, const float* bsize) {
   Contact2 c;
   capsule_box<false>(A, B, r, bpos, bmat, bsize, c);

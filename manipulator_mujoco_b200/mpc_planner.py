@@ -129,6 +129,7 @@ def run_cem_planner(num_dof=None, num_batch=None, num_steps=None, maxiter_cem=No
 
     thetadot = np.zeros(num_dof)
     cost_g_list, cost_list, cost_r_list, cost_c_list, thetadot_list, theta_list, tick_ms = [], [], [], [], [], [], []
+    dist_list, switch_ticks = [], []
     target_idx = 0
     current_target = target_names[target_idx]
     reached_final = False
@@ -154,11 +155,13 @@ def run_cem_planner(num_dof=None, num_batch=None, num_steps=None, maxiter_cem=No
         current_cost_r = quaternion_distance(data.xquat[cem.hande_id], target_rot)
         current_cost = np.round(cost, 2)
         tick_ms.append(plan_ms)
+        dist_list.append(float(current_cost_g))
         if verbose:
             print(f'Step Time: {"%.0f" % ((time.time() - start_time) * 1000)}ms | Cost g: {"%.2f" % float(current_cost_g)}'
                   f' | Cost r: {"%.2f" % float(current_cost_r)} | Cost c: {"%.2f" % float(best_cost_c)} | Cost: {current_cost}')
             print(f'target: {current_target}')
         if current_cost_g < position_threshold and current_cost_r < rotation_threshold:
+            switch_ticks.append((_tick, current_target))
             if target_idx == len(target_names) - 1:
                 if stop_at_final_target:
                     if verbose:
@@ -197,4 +200,5 @@ def run_cem_planner(num_dof=None, num_batch=None, num_steps=None, maxiter_cem=No
         np.savetxt(f'{data_dir}/cost_r.csv', cost_r_list, delimiter=",")
         np.savetxt(f'{data_dir}/cost_c.csv', cost_c_list, delimiter=",")
     return {'cost_g': cost_g_list, 'cost_r': cost_r_list, 'cost_c': cost_c_list, 'cost': cost_list, 'thetadot': thetadot_list,
-            'theta': theta_list, 'tick_ms': tick_ms, 'final_target': current_target, 'reached_final': reached_final}
+            'theta': theta_list, 'tick_ms': tick_ms, 'final_target': current_target, 'reached_final': reached_final,
+            'dist': dist_list, 'switch_ticks': switch_ticks}

@@ -67,7 +67,7 @@ typedef struct {
   int nq, nv, nbody, njnt, ngeom, npair, ncon;
   int iterations, ls_iterations;
   int tcp_body, hande_body;
-  int pad0;
+  int capbox_mode;                  /* capsule_box restatement, see capsule_box(): 1 = has_support gate (default), 0 = round-1 */
   double timestep, tolerance, ls_tolerance, impratio, meaninertia;
   double gravity[3];
   double tcp_pos[3];
@@ -561,28 +561,47 @@ static int clip_edge_to_planes(const real *p0, const real *p1, int np, real pp[]
   if (dot3(e10, dn) < 0) mask = 0;
   return mask;
 }
-/* MJX collision_convex.capsule_convex specialised to a box:
- *  - best face = argmax over the 6 faces of min over the two segment end points of the signed
- *    distance to the face plane (axis of least penetration),
- *  - the segment is clipped against the 4 side planes of that face; the two clipped points, pushed
- *    by the radius along -normal, are measured against the face plane (slots 0,1); a failed clip
- *    gives penetration -1, i.e. dist = +1,
- *  - if one of the 4 face edges is closer than the radius to the segment, slot 0 becomes that
- *    edge contact. */
+/* MJX collision_convex._capsule_convex specialised to a box.  Two restatements
+ * selected by omodel.capbox_mode:
+ *
+ * mode 1 (default) -- mujoco-mjx 3.x as recalled by the round-1 review (VERDICT.md "What's weak" #1) and
+ * pinned, weakly, by the reference's own recording (tests/test_oracle_pins.py::test_recorded_run_pins_
+ * capsule_box_far_field: replaying data/theta.csv must not produce the +1 -> 0.2 sentinel flips that
+ * data/cost_c.csv, max 0.021, never shows):
+ *  - support_f = min over the two end points of dot(pt - r n_f - face_f[0], n_f) for each of the 6 faces;
+ *    has_support = all(support_f < 0); best face = first argmax of support_f;
+ *  - the segment is clipped against the 4 side planes of the best face (_clip_edge_to_planes); the two
+ *    clipped points, pushed by the radius along -n, are measured against the face plane;
+ *    face_penetration = where(mask & has_support, ., -1)  => both face slots are the dist = +1 sentinel
+ *    whenever any face plane separates the radius-inflated capsule from the box: no far-field distance;
+ *  - shallow edge contact over all 12 box edges: closest points edge <-> segment, edge_axis = normalised
+ *    (edge_pt - cap_pt); an edge qualifies when it is not degenerate (|.|^2 >= 1e-6) and the capsule point
+ *    lies in front of both faces adjacent to the edge (edge_voronoi_front); edge_penetration = r - dist for
+ *    qualifying edges, -1 otherwise; the edge with the largest penetration (first) is the candidate;
+ *    has_edge_contact = pen > 0 & (min face pen > 0 ? pen < min face pen : true) & !(|edge_axis . n| > 0.99);
+ *    it replaces slot 0 (position, normal = edge_axis, penetration).
+ *
+ * mode 0 -- the round-1 restatement (brax-era collider): best face by the same argmax, face slots report
+ * the true face distance whenever the clip succeeds (no has_support gate), edge contact = closest of the
+ * best face's 4 edges with r - dist > 0.  Kept only so that the pin test can show it contradicts the
+ * reference's recording. */
 static void capsule_box(const real *cpos, const real *cmat, const real *csize, const real *bpos, const real *bmat, const real *bsize,
-                        real *dist, real pos[][3], real frame[][9]) {
+                        real *dist, real pos[][3], real frame[][9], int mode) {
   real t[3], cp[3], ax[3], axw[3] = {cmat[2], cmat[5], cmat[8]}, seg[3], pts[2][3];
+  const real r = csize[0];
   sub3(t, cpos, bpos); matT_vec(cp, bmat, t);
   matT_vec(ax, bmat, axw);
   scl3(seg, ax, csize[1]);
   sub3(pts[0], cp, seg); add3(pts[1], cp, seg);
-  int best = 0; real bests = 0;
+  int best = 0, has_support = 1; real bests = 0;
   for (int f = 0; f < 6; f++) {
     int k = f >> 1; real sg = (f & 1) ? -1 : 1;
-    real s0 = sg * pts[0][k] - bsize[k], s1 = sg * pts[1][k] - bsize[k];
+    real s0 = sg * pts[0][k] - r - bsize[k], s1 = sg * pts[1][k] - r - bsize[k];
     real sup = s0 < s1 ? s0 : s1;
     if (f == 0 || sup > bests) { bests = sup; best = f; }
+    if (!(sup < 0)) has_support = 0;
   }
+  if (mode == 0) has_support = 1;
   real face[4][3], n[3], ep0[4][3], en[4][3];
   box_face(bsize, best, face, n);
   for (int i = 0; i < 4; i++) {
@@ -595,31 +614,60 @@ static void capsule_box(const real *cpos, const real *cmat, const real *csize, c
   real nrm[2][3], pen[2], lp[2][3];
   for (int k = 0; k < 2; k++) {
     real c[3], fp[3], tt[3];
-    addscl3(c, cl[k], n, -csize[0]);
+    addscl3(c, cl[k], n, -r);
     sub3(tt, c, face[0]);
     addscl3(fp, c, n, -dot3(tt, n));
     for (int q = 0; q < 3; q++) lp[k][q] = (c[q] + fp[q]) * (real)0.5;
     sub3(tt, fp, c);
-    pen[k] = mask ? dot3(tt, n) : -1;
+    pen[k] = (mask && has_support) ? dot3(tt, n) : -1;
     scl3(nrm[k], n, -1);
   }
-  /* edge contact */
-  real bd = 0; int be = -1; real bec[3], bcc[3];
-  for (int i = 0; i < 4; i++) {
-    real ec[3], cc[3], df[3];
-    closest_seg_seg(ec, cc, ep0[i], face[i], pts[0], pts[1]);
-    sub3(df, ec, cc);
-    real dd = dot3(df, df);
-    if (be < 0 || dd < bd) { bd = dd; be = i; copy3(bec, ec); copy3(bcc, cc); }
-  }
-  real eax[3];
-  sub3(eax, bcc, bec);
-  real ed = normalize3(eax);
-  real epen = csize[0] - ed;
-  if (epen > 0) {
-    for (int q = 0; q < 3; q++) lp[0][q] = (bec[q] + (bcc[q] - eax[q] * csize[0])) * (real)0.5;
-    scl3(nrm[0], eax, -1);
-    pen[0] = epen;
+  if (mode == 0) {
+    /* edge contact, round-1 restatement */
+    real bd = 0; int be = -1; real bec[3], bcc[3];
+    for (int i = 0; i < 4; i++) {
+      real ec[3], cc[3], df[3];
+      closest_seg_seg(ec, cc, ep0[i], face[i], pts[0], pts[1]);
+      sub3(df, ec, cc);
+      real dd = dot3(df, df);
+      if (be < 0 || dd < bd) { bd = dd; be = i; copy3(bec, ec); copy3(bcc, cc); }
+    }
+    real eax[3];
+    sub3(eax, bcc, bec);
+    real ed = normalize3(eax);
+    real epen = r - ed;
+    if (epen > 0) {
+      for (int q = 0; q < 3; q++) lp[0][q] = (bec[q] + (bcc[q] - eax[q] * r)) * (real)0.5;
+      scl3(nrm[0], eax, -1);
+      pen[0] = epen;
+    }
+  } else {
+    /* shallow edge contact over the 12 edges: edge e = 4*k + 2*iu + iw runs along axis k at
+     * (u, w) = (su * s_u, sw * s_w), su = iu ? +1 : -1, sw = iw ? +1 : -1; adjacent faces: su*e_u, sw*e_w */
+    real bpen = -1; int be = -1; real beax[3] = {0, 0, 0}, bec[3] = {0, 0, 0}, bcc[3] = {0, 0, 0};
+    for (int e = 0; e < 12; e++) {
+      int k = e >> 2, u = (k + 1) % 3, w = (k + 2) % 3;
+      real su = (e & 2) ? 1 : -1, sw = (e & 1) ? 1 : -1;
+      real e0[3], e1[3], ec[3], cc[3], dir[3];
+      e0[k] = -bsize[k]; e1[k] = bsize[k]; e0[u] = e1[u] = su * bsize[u]; e0[w] = e1[w] = sw * bsize[w];
+      closest_seg_seg(ec, cc, e0, e1, pts[0], pts[1]);
+      sub3(dir, ec, cc);
+      int degenerate = dot3(dir, dir) < (real)1e-6;
+      real ed = normalize3(dir);
+      int front = (su * dir[u] < 0) && (sw * dir[w] < 0);
+      real epen = (!degenerate && front) ? r - ed : -1;
+      if (be < 0 || epen > bpen) { bpen = epen; be = e; copy3(beax, dir); copy3(bec, ec); copy3(bcc, cc); }
+    }
+    int degenerate = 0;
+    { real d[3]; sub3(d, bec, bcc); degenerate = dot3(d, d) < (real)1e-6; }
+    int parallel = (RFABS(dot3(beax, n)) > (real)0.99) && !degenerate;
+    real minface = pen[0] < pen[1] ? pen[0] : pen[1];
+    int has_edge = (bpen > 0) && (minface > 0 ? bpen < minface : 1) && !parallel;
+    if (has_edge) {
+      for (int q = 0; q < 3; q++) lp[0][q] = (bec[q] + (bcc[q] + beax[q] * r)) * (real)0.5;
+      copy3(nrm[0], beax);
+      pen[0] = bpen;
+    }
   }
   for (int k = 0; k < 2; k++) {
     real w[3], nw[3];
@@ -820,7 +868,7 @@ static void collision(const omodel *m, odata *d) {
     if (t1 == G_PLANE && t2 == G_CAPSULE) plane_capsule(d->gpos[g1], d->gmat[g1], d->gpos[g2], d->gmat[g2], s2, d->con_dist + a, d->con_pos + a, d->con_frame + a);
     else if (t1 == G_PLANE && t2 == G_BOX) plane_box(d->gpos[g1], d->gmat[g1], d->gpos[g2], d->gmat[g2], s2, d->con_dist + a, d->con_pos + a, d->con_frame + a);
     else if (t1 == G_CAPSULE && t2 == G_CAPSULE) capsule_capsule(d->gpos[g1], d->gmat[g1], s1, d->gpos[g2], d->gmat[g2], s2, d->con_dist + a, d->con_pos + a, d->con_frame + a);
-    else if (t1 == G_CAPSULE && t2 == G_BOX) capsule_box(d->gpos[g1], d->gmat[g1], s1, d->gpos[g2], d->gmat[g2], s2, d->con_dist + a, d->con_pos + a, d->con_frame + a);
+    else if (t1 == G_CAPSULE && t2 == G_BOX) capsule_box(d->gpos[g1], d->gmat[g1], s1, d->gpos[g2], d->gmat[g2], s2, d->con_dist + a, d->con_pos + a, d->con_frame + a, m->capbox_mode);
     else if (t1 == G_BOX && t2 == G_BOX) box_box(d->gpos[g1], d->gmat[g1], s1, d->gpos[g2], d->gmat[g2], s2, d->con_dist + a, d->con_pos + a, d->con_frame + a);
     for (int k = 0; k < m->pair_nslot[p]; k++) {
       d->con_b1[a+k] = m->geom_body[g1]; d->con_b2[a+k] = m->geom_body[g2];
@@ -1160,7 +1208,8 @@ int oracle_collide(int type, const double *p1, const double *m1, const double *s
   int n = 0;
   if (type == 0) { plane_capsule(P1, M1, P2, M2, S2, d, ps, fr); n = 2; }
   else if (type == 1) { capsule_capsule(P1, M1, S1, P2, M2, S2, d, ps, fr); n = 1; }
-  else if (type == 2) { capsule_box(P1, M1, S1, P2, M2, S2, d, ps, fr); n = 2; }
+  else if (type == 2) { capsule_box(P1, M1, S1, P2, M2, S2, d, ps, fr, 1); n = 2; }
+  else if (type == 5) { capsule_box(P1, M1, S1, P2, M2, S2, d, ps, fr, 0); n = 2; }   /* round-1 restatement */
   else if (type == 3) { plane_box(P1, M1, P2, M2, S2, d, ps, fr); n = 4; }
   else if (type == 4) { box_box(P1, M1, S1, P2, M2, S2, d, ps, fr); n = 4; }
   for (int i = 0; i < n; i++) {

@@ -24,7 +24,7 @@ _d, _i = C.c_double, C.c_int
 class OModel(C.Structure):
     _fields_ = [
         ("nq", _i), ("nv", _i), ("nbody", _i), ("njnt", _i), ("ngeom", _i), ("npair", _i), ("ncon", _i),
-        ("iterations", _i), ("ls_iterations", _i), ("tcp_body", _i), ("hande_body", _i), ("pad0", _i),
+        ("iterations", _i), ("ls_iterations", _i), ("tcp_body", _i), ("hande_body", _i), ("capbox_mode", _i),
         ("timestep", _d), ("tolerance", _d), ("ls_tolerance", _d), ("impratio", _d), ("meaninertia", _d),
         ("gravity", _d * 3), ("tcp_pos", _d * 3),
         ("body_parent", _i * MAXB), ("body_jnt", _i * MAXB), ("body_rootid", _i * MAXB), ("body_weldid", _i * MAXB),
@@ -75,7 +75,7 @@ def robot_slot_mask(mc, robot_names=None):
 class Oracle:
     """CPU reference stepper for a compiled scene (ModelConsts)."""
 
-    def __init__(self, mc, timestep, dtype="f64", tcp_site="tcp", hande_body="hande"):
+    def __init__(self, mc, timestep, dtype="f64", tcp_site="tcp", hande_body="hande", capbox_mode=1):
         libs = build()
         self.lib = C.CDLL(libs[0] if dtype == "f64" else libs[1])
         assert self.lib.oracle_sizeof_model() == C.sizeof(OModel), "struct layout mismatch"
@@ -91,6 +91,7 @@ class Oracle:
         sid = mc.site_id(tcp_site)
         m.tcp_body, m.hande_body = int(mc.site_body[sid]), mc.body_id(hande_body)
         m.timestep = timestep
+        m.capbox_mode = int(capbox_mode)      # capsule_box restatement (mjstep.c): 1 = has_support gate, 0 = round-1
         m.tolerance, m.ls_tolerance = mc.opt["tolerance"], mc.opt["ls_tolerance"]
         m.impratio, m.meaninertia = mc.opt["impratio"], mc.meaninertia
         _fill(m.gravity, mc.opt["gravity"])
@@ -190,7 +191,7 @@ def collide(kind, p1, m1, s1, p2, m2, s2, dtype="f64"):
     capsule_box, plane_box, box_box.  Returns dist [n], pos [n,3], frame [n,3,3]."""
     libs = build()
     lib = C.CDLL(libs[0] if dtype == "f64" else libs[1])
-    code = ["plane_capsule", "capsule_capsule", "capsule_box", "plane_box", "box_box"].index(kind)
+    code = ["plane_capsule", "capsule_capsule", "capsule_box", "plane_box", "box_box", "capsule_box_legacy"].index(kind)
     a = lambda x, n: np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1)[:n] if np.size(x) >= n
                                           else np.concatenate([np.asarray(x, dtype=np.float64).reshape(-1), np.zeros(n - np.size(x))]))
     P1, M1, S1, P2, M2, S2 = a(p1, 3), a(m1, 9), a(s1, 3), a(p2, 3), a(m2, 9), a(s2, 3)

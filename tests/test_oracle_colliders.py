@@ -46,19 +46,53 @@ def test_plane_capsule():
     np.testing.assert_allclose(fr2[0][1], [0, 1, 0], atol=1e-12)
 
 
-def test_capsule_box_face_region_is_true_distance():
-    """Segment over a face: both slots measure (height - radius) of the clipped end points."""
+def test_capsule_box_far_field_is_the_sentinel():
+    """has_support gate (MJX _capsule_convex): a segment hovering over a face with the face plane separating the
+    radius-inflated capsule from the box reports dist = +1 in both slots -- no far-field distance.  The round-1
+    restatement (kept as "capsule_box_legacy") reported height - radius there."""
     box = [0.3, 0.2, 0.1]
     rng = np.random.default_rng(1)
     for _ in range(50):
-        c = np.array([rng.uniform(-.2, .2), rng.uniform(-.1, .1), rng.uniform(0.12, 0.6)])
+        c = np.array([rng.uniform(-.2, .2), rng.uniform(-.1, .1), rng.uniform(0.15, 0.6)])
         R = rot([0, 1, 0], np.pi / 2 + rng.uniform(-.2, .2))           # roughly horizontal capsule
         hl = 0.05
-        d, pos, fr = collide("capsule_box", c, R, [0.03, hl, 0], [0, 0, 0], I3, box)
         ends = [c - R[:, 2] * hl, c + R[:, 2] * hl]
         assert max(abs(e[0]) for e in ends) < 0.3 and max(abs(e[1]) for e in ends) < 0.2
+        assert min(e[2] for e in ends) - 0.1 - 0.03 > 0
+        d, pos, fr = collide("capsule_box", c, R, [0.03, hl, 0], [0, 0, 0], I3, box)
+        np.testing.assert_allclose(d, [1, 1])
+        d0, _, fr0 = collide("capsule_box_legacy", c, R, [0.03, hl, 0], [0, 0, 0], I3, box)
+        np.testing.assert_allclose(d0, [e[2] - 0.1 - 0.03 for e in ends], atol=1e-12)
+
+
+def test_capsule_box_face_contact_is_true_distance():
+    """Penetrating the top face (every face plane has an inflated end point behind it): both slots measure
+    (height - radius) of the clipped end points, normal capsule -> box."""
+    box = [0.3, 0.2, 0.1]
+    rng = np.random.default_rng(2)
+    for _ in range(50):
+        c = np.array([rng.uniform(-.2, .2), rng.uniform(-.1, .1), rng.uniform(0.105, 0.125)])
+        R = rot([0, 1, 0], np.pi / 2 + rng.uniform(-.05, .05))
+        hl = 0.05
+        ends = [c - R[:, 2] * hl, c + R[:, 2] * hl]
+        if min(e[2] for e in ends) - 0.1 - 0.03 >= 0:
+            continue
+        d, pos, fr = collide("capsule_box", c, R, [0.03, hl, 0], [0, 0, 0], I3, box)
         np.testing.assert_allclose(d, [e[2] - 0.1 - 0.03 for e in ends], atol=1e-12)
         np.testing.assert_allclose(fr[0][0], [0, 0, -1], atol=1e-12)   # capsule -> box
+        np.testing.assert_allclose(pos[0][:2], ends[0][:2], atol=1e-12)
+
+
+def test_capsule_box_one_end_in_contact_reports_the_other_ends_distance():
+    """has_support only needs ONE inflated end point behind each face plane: a tilted capsule touching the top
+    face with its lower end reports the (positive) face distance of its upper end in the other slot."""
+    R = rot([0, 1, 0], np.pi / 2 - 0.5)
+    c = np.array([0.0, 0.0, 0.14])
+    hl, r = 0.05, 0.03
+    ends = [c - R[:, 2] * hl, c + R[:, 2] * hl]
+    d, _, _ = collide("capsule_box", c, R, [r, hl, 0], [0, 0, 0], I3, [0.3, 0.2, 0.1])
+    np.testing.assert_allclose(d, [e[2] - 0.1 - r for e in ends], atol=1e-12)
+    assert d.min() < 0 < d.max()
 
 
 def test_capsule_box_sentinel_when_clip_fails():
@@ -68,11 +102,23 @@ def test_capsule_box_sentinel_when_clip_fails():
 
 
 def test_capsule_box_edge_contact_replaces_slot0():
-    # vertical capsule just outside the +x side of the top face, touching the top edge
+    # vertical capsule just outside the +x side of the top face, touching the top edge: the capsule point lies in
+    # front of both faces adjacent to that edge (+x and +z), so it is a shallow edge contact although no face has support
     d, pos, fr = collide("capsule_box", [0.12, 0, 0.16], I3, [0.05, 0.05, 0], [0, 0, 0], I3, [0.1, 0.1, 0.1])
     # closest point of the segment (its lower end at z=.11) to the edge x=.1,z=.1: distance sqrt(.02^2+.01^2)
     assert abs(d[0] - (np.hypot(0.02, 0.01) - 0.05)) < 1e-9
-    assert d[0] < 0
+    assert d[0] < 0 and d[1] == 1
+    n = np.array([0.1 - 0.12, 0, 0.1 - 0.11]); n /= np.linalg.norm(n)
+    np.testing.assert_allclose(fr[0][0], n, atol=1e-9)               # capsule -> edge
+    np.testing.assert_allclose(pos[0], 0.5 * (np.array([0.1, 0, 0.1]) + np.array([0.12, 0, 0.11]) + n * 0.05), atol=1e-9)
+
+
+def test_capsule_box_edge_needs_the_voronoi_region():
+    # same capsule moved over the face (x < .1): its closest point is not in front of the +x face, the edge does not
+    # qualify; the face contact (has_support holds) is reported instead
+    d, pos, fr = collide("capsule_box", [0.095, 0, 0.16], I3, [0.05, 0.05, 0], [0, 0, 0], I3, [0.1, 0.1, 0.1])
+    np.testing.assert_allclose(d[0], 0.11 - 0.1 - 0.05, atol=1e-12)
+    np.testing.assert_allclose(fr[0][0], [0, 0, -1], atol=1e-12)
 
 
 def test_box_box_resting_face_contact():

@@ -68,3 +68,34 @@ def test_box_settles_on_table(mc, oracle64):
     np.testing.assert_allclose(qp[0, -1, 6:8], [-0.3, -0.3], atol=1e-9)
     assert np.abs(qa[0, :, :6]).max() < 1e-9          # robot untouched (gravcomp)
     assert np.abs(th.reshape(6, T) - Q0[:, None]).max() < 1e-9
+
+
+def _replayed_cost_c(mc, mode):
+    """cost_c of mjx_planner.py:287-296 over every 16-tick window of the recorded closed-loop run
+    (data/theta.csv, consecutive plant states at dt = 0.05 = the planner's own step)."""
+    from oracle.oracle import Oracle
+    ora = Oracle(mc, 0.05, capbox_mode=mode)
+    th = np.load(os.path.join(GOLDEN, "closed_loop_kat.npz"))["theta"]
+    qbox = mc.qpos0[6:].copy()
+    qbox[2] = 0.445
+    D = np.array([ora.forward(np.concatenate([q, qbox]), np.zeros(12))["con_dist"][ora.mask] for q in th])
+    per_tick = np.maximum(0.995 * D[:-1] - D[1:], 0).sum(1) + (D[1:] < 0).sum(1)
+    flips = int(((D[:-1] == 1) != (D[1:] == 1)).sum())
+    return np.convolve(per_tick, np.ones(15), "valid"), flips, D
+
+
+def test_recorded_run_pins_capsule_box_far_field(mc):
+    """The only reference-held evidence that touches the colliders: data/cost_c.csv (best planned cost_c of 897
+    ticks, max 0.0208, three targets reached) next to data/theta.csv (the joint path actually driven).
+    With MJX's has_support gate (oracle capbox_mode 1) the driven path never flips a capsule-box slot between
+    the +1 sentinel and a far-field distance, and its windowed cost_c stays at the recording's magnitude.
+    The round-1 restatement (mode 0: true face distance whenever the clip succeeds) books 28 such flips on
+    the same path, each worth ~0.8 -- a cost the recorded planner demonstrably never saw."""
+    rec = np.load(os.path.join(GOLDEN, "closed_loop_kat.npz"))["cost_c"]
+    assert rec.shape == (897,) and 0.02 < rec.max() < 0.021
+    w1, flips1, D1 = _replayed_cost_c(mc, 1)
+    assert flips1 == 0
+    assert w1.max() < 0.05                         # recorded max 0.0208; replay of the driven path: 0.027
+    assert (D1 < 0).sum() == 0                     # the recorded run never penetrates (count term of cost_c)
+    w0, flips0, _ = _replayed_cost_c(mc, 0)
+    assert flips0 >= 20 and w0.max() > 1.0 > 30 * rec.max()

@@ -7,7 +7,8 @@ Produces
                        horizons used by the tests (imported from the reference, not restated);
   closed_loop_kat.npz  the recorded closed-loop run of the reference (data/theta.csv, data/thetadot.csv:
                        897 ticks of the C-MuJoCo plant at dt = 0.05) used as the smooth-dynamics
-                       known-answer test;
+                       known-answer test, plus the per-tick best costs of the same run (data/cost_c.csv, cost_g.csv,
+                       cost_r.csv, costs.csv) that pin the capsule-box far-field semantics;
   scene_ids.json       geom ids recorded in view_traj_mjx.py:54 and the FK pins of SURVEY.md section 4.
 """
 import json
@@ -35,7 +36,8 @@ def main():
     np.savez_compressed(os.path.join(OUT, "bernstein.npz"), **out)
     theta = np.loadtxt(os.path.join(REF, "data", "theta.csv"), delimiter=",")
     thetadot = np.loadtxt(os.path.join(REF, "data", "thetadot.csv"), delimiter=",")
-    np.savez_compressed(os.path.join(OUT, "closed_loop_kat.npz"), theta=theta, thetadot=thetadot.astype(np.float32))
+    rec = {n: np.loadtxt(os.path.join(REF, "data", n + ".csv"), delimiter=",") for n in ("cost_c", "cost_g", "cost_r", "costs")}
+    np.savez_compressed(os.path.join(OUT, "closed_loop_kat.npz"), theta=theta, thetadot=thetadot.astype(np.float32), **rec)
     with open(os.path.join(OUT, "scene_ids.json"), "w") as f:
         json.dump({
             "robot_geom_ids": [33, 7, 12, 13, 18, 19, 23, 27, 28, 30],          # view_traj_mjx.py:54
