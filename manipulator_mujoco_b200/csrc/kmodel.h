@@ -16,14 +16,19 @@
 #define KM_NQ 13
 #define KM_MAXCAP 12
 #define KM_MAXSBOX 8
-#define KM_MAXRPAIR 128  // robot-involving pairs (KM_MAXRPAIR / KW collider passes of KW lanes, see warp_dsl.h)
+#define KM_MAXRPAIR 160  // robot pair table entries = KM_MAXRPAIR / KW collider passes of KW lanes (see warp_dsl.h)
+#define KM_MAXNEAR 96    // capsule-box pairs a model may have (capacity of the per-step near list)
 #define KM_MAXBPAIR 8    // free-box vs static pairs
 
-// robot pair types
+// robot pair types; a table entry packs (type + 1) | a << 4 | b << 8 | first cost slot << 16  (0 = no pair)
 #define KP_NONE (-1)
 #define KP_PLANE_CAP 0
 #define KP_CAP_CAP 1
 #define KP_CAP_BOX 2
+#define KP_TYPE(x) (((x) & 15) - 1)
+#define KP_A(x) (((x) >> 4) & 15)
+#define KP_B(x) (((x) >> 8) & 15)
+#define KP_SLOT(x) ((x) >> 16)
 // free-box pair types
 #define KB_PLANE_BOX 0
 #define KB_BOX_BOX 1        // static box is geom1, free box geom2
@@ -42,7 +47,7 @@ struct KModel {
   float l_inertia[KM_NL][8];            // xx yy zz xy xz yz (link frame, about com), mass, 0
   float l_armature[KM_NL], l_damping[KM_NL], l_lo[KM_NL], l_hi[KM_NL], l_invw[KM_NL], l_margin[KM_NL];
   int l_limited[KM_NL];
-  int pad3[2];
+  int ncbpass, pad3;                    // leading passes of the pair table that hold the capsule-box pairs (see rp)
   float tcp_pos[4], hande_quat[4];      // relative to the last link frame
   int cap_link[KM_MAXCAP];
   float cap_pos[KM_MAXCAP][4], cap_axis[KM_MAXCAP][4];
@@ -51,8 +56,11 @@ struct KModel {
   float sb_pos[KM_MAXSBOX][4], sb_mat[KM_MAXSBOX][12], sb_size[KM_MAXSBOX][4];
   float fb_size[4], fb_inertia[4];      // free box half sizes; principal inertia (body frame)
   float fb_mass, fb_damping, fb_invw, pad4;
-  // robot pairs, pass-major: entry p*KW + lane
-  int rp_type[KM_MAXRPAIR], rp_a[KM_MAXRPAIR], rp_b[KM_MAXRPAIR], rp_slot[KM_MAXRPAIR];
+  // robot pairs, pass-major: entry p*KW + lane.  Passes 0 .. ncbpass-1 hold the capsule-box pairs with a fixed shape:
+  // pass p = box p (static boxes 0 .. nsbox-1, then the free box), lane l = capsule l, so a lane keeps its capsule in
+  // registers and a pass reads one box; missing (excluded) pairs are empty entries.  Plane-capsule and
+  // capsule-capsule pairs follow, grouped by type.
+  int rp[KM_MAXRPAIR];
   int bp_type[KM_MAXBPAIR], bp_a[KM_MAXBPAIR];
   float qpos0[16], warm0[12], qvel0[12];   // snapshot every rollout starts from (mjx_planner.py:267)
 };

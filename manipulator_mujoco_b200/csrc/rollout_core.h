@@ -42,6 +42,7 @@ struct LaneRegs {
   float cost_c;               // this lane's share of cost_c
   int nact, off;              // active contacts this lane will emit, and where
   int actmask;                // bit (2*pass + slot)
+  int farprev;                // bit p: the previous step's distances of this lane's capsule-box pair of pass p were the (+1, +1) sentinel
   int tri;                    // (i, j), 4 bits each, of the 6x6 lower-triangle entries lane and lane + KW (8 bits per entry; 0xff = none)
   float td;                   // next step's commanded joint velocity (lanes < 6), prefetched one step ahead
   float acc[9];               // line-search partial sums (compile-time indices only)
@@ -70,6 +71,7 @@ struct WarpSmemT {
   union {
     struct { float cinert[KM_NL][12], crb[KM_NL][12], cvel[KM_NL][8], cdofdot[KM_NL][8], cfrc[KM_NL][8]; };
     struct { float rD[NROW], rAref[NROW], rJaref[NROW], rJv[NROW]; };   // rJv doubles as the smooth-start J.a - aref in S1
+    struct { float nres[KM_MAXNEAR][2]; unsigned char nlist[KM_MAXNEAR]; };   // N1 only: the near capsule-box pairs of this step and their distances
   };
   float cgeo[NC][16];                 // pos3 n3 t1 3 t2 3 dist invw link1 link2
   union {
@@ -274,8 +276,8 @@ KFN void capsule_capsule(const float* a0, const float* a1, float r1, const float
 //     adjacent to the edge), which replaces slot 0.
 // Far field: if some box axis separates the segment's bounding interval from the box by >= r, has_support
 // fails and no edge can be within r, so the pair costs one change of frame and six min/max (capbox_far).
-// Everything else is a cold out-of-line call (capsule_box_near), in box coordinates.
-#ifndef CEMK_CAPBOX_LEGACY
+// Otherwise (near path, = has_support): face part in registers; the edge stage is an out-of-line call taken only
+// when the segment sticks out of the box on two axes.
 KFN void capbox_local(const float* A, const float* B, const float* bpos, const float* bmat, float* a, float* b) {
   float t[3];
   sub3(t, A, bpos); matT_vec(a, bmat, t);
@@ -288,21 +290,62 @@ KFN bool capbox_far(const float* a, const float* b, float r, const float* s) {
   return !(fmaxf(fmaxf(s0, s1), s2) < r);
 }
 struct CapBoxOut { float dist[2], pos[2][3], nrm[2][3]; };     // box coordinates
-KNOINLINE void capsule_box_near(float ax, float ay, float az, float bx, float by, float bz, float r, float sx, float sy, float sz,
-                                CapBoxOut* o) {
-  const float a[3] = {ax, ay, az}, b[3] = {bx, by, bz}, bsize[3] = {sx, sy, sz};
-  // best face: first argmax over (+x,-x,+y,-y,+z,-z) of min over end points of the inflated signed face distance
-  int bf = 0; bool has_support = true; float bests = 0.f;
+// Shallow edge contact of the near path (rare: only when the segment's bounding box sticks out of the box on two
+// axes).  Edge e = 4k + 2iu + iw runs along axis k at (u, w) = (+-s_u, +-s_w).  An edge can only win with a
+// positive penetration, which needs a point of the segment in front of both faces adjacent to the edge and closer
+// than r to it; the interval tests are necessary for that, so edges failing them skip the segment-segment routine
+// without changing the result.  On a hit: slot 0 of *o becomes the edge contact.  n = outward normal of the best face.
+KNOINLINE void capbox_edges(float ax, float ay, float az, float bx, float by, float bz, float r, float sx, float sy, float sz,
+                            float nx, float ny, float nz, CapBoxOut* o) {
+  const float bsize[3] = {sx, sy, sz}, n[3] = {nx, ny, nz};
+  float bpen = -1.f, beax[3] = {0.f, 0.f, 0.f}, bec[3] = {0.f, 0.f, 0.f}, bcc[3] = {0.f, 0.f, 0.f};
+  bool bdeg = false;
+  const float lo[3] = {fminf(ax, bx), fminf(ay, by), fminf(az, bz)}, hi[3] = {fmaxf(ax, bx), fmaxf(ay, by), fmaxf(az, bz)};
 #pragma unroll 1
-  for (int f = 0; f < 6; ++f) {
-    const int k = f >> 1; const float sg = (f & 1) ? -1.f : 1.f;
-    const float sup = fminf(sg * a[k], sg * b[k]) - r - bsize[k];
-    if (f == 0 || sup > bests) { bests = sup; bf = f; }
-    if (!(sup < 0.f)) has_support = false;
+  for (int e = 0; e < 12; ++e) {
+    const int k = e >> 2, u = (k + 1) % 3, w = (k + 2) % 3;
+    const float eu = (e & 2) ? 1.f : -1.f, ew = (e & 1) ? 1.f : -1.f;
+    const float cu = eu * bsize[u], cw = ew * bsize[w];
+    // furthest the segment reaches in front of the two faces, measured from the edge (must be > 0), and its
+    // nearest approach (must be < r)
+    const float fu = eu > 0.f ? hi[u] - cu : cu - lo[u], fw = ew > 0.f ? hi[w] - cw : cw - lo[w];
+    const float gu = eu > 0.f ? lo[u] - cu : cu - hi[u], gw = ew > 0.f ? lo[w] - cw : cw - hi[w];
+    if (!(fu > 0.f && fw > 0.f && gu < r && gw < r && lo[k] < bsize[k] + r && hi[k] > -bsize[k] - r)) continue;
+    float e0[3], e1[3];
+    e0[k] = -bsize[k]; e1[k] = bsize[k]; e0[u] = e1[u] = cu; e0[w] = e1[w] = cw;
+    const SegPair sp = closest_seg_seg(e0[0], e0[1], e0[2], e1[0], e1[1], e1[2], ax, ay, az, bx, by, bz);
+    float dir[3];
+    sub3(dir, sp.a, sp.b);
+    const bool deg = dot3(dir, dir) < 1e-6f;
+    const float ed = normalize3(dir);
+    const bool front = (eu * dir[u] < 0.f) && (ew * dir[w] < 0.f);
+    const float epen = (!deg && front) ? r - ed : -1.f;
+    if (epen > bpen) { bpen = epen; bdeg = deg; copy3(beax, dir); copy3(bec, sp.a); copy3(bcc, sp.b); }
   }
-  const int bk = bf >> 1, iu = (bk + 1) % 3, iw = (bk + 2) % 3;
-  const float sg = (bf & 1) ? -1.f : 1.f;
-  const float ak = a[bk], au = a[iu], aw = a[iw], bk_ = b[bk], bu = b[iu], bw = b[iw], sk = bsize[bk], su = bsize[iu], sw = bsize[iw];
+  const bool parallel = fabsf(dot3(beax, n)) > 0.99f && !bdeg;
+  const float minface = fminf(-o->dist[0], -o->dist[1]);
+  const bool has_edge = bpen > 0.f && (minface > 0.f ? bpen < minface : true) && !parallel;
+  if (has_edge) {
+    o->dist[0] = -bpen;
+    for (int q = 0; q < 3; ++q) { o->pos[0][q] = 0.5f * (bec[q] + bcc[q] + beax[q] * r); o->nrm[0][q] = beax[q]; }
+  }
+}
+// Near path, in box coordinates; the caller has established has_support (= !capbox_far).  Face part in registers
+// (no dynamic indexing); FULL also produces contact positions / normals.
+template <bool FULL>
+KFN void capsule_box_near(const float* a, const float* b, float r, const float* bsize, CapBoxOut& o) {
+  // best face: first argmax over (+x,-x,+y,-y,+z,-z) of min over end points of the signed face distance
+  float bests = fminf(a[0], b[0]) - bsize[0]; int bk = 0; float sg = 1.f;
+  { float s = -fmaxf(a[0], b[0]) - bsize[0]; if (s > bests) { bests = s; sg = -1.f; } }
+  { float s = fminf(a[1], b[1]) - bsize[1]; if (s > bests) { bests = s; bk = 1; sg = 1.f; } }
+  { float s = -fmaxf(a[1], b[1]) - bsize[1]; if (s > bests) { bests = s; bk = 1; sg = -1.f; } }
+  { float s = fminf(a[2], b[2]) - bsize[2]; if (s > bests) { bests = s; bk = 2; sg = 1.f; } }
+  { float s = -fmaxf(a[2], b[2]) - bsize[2]; if (s > bests) { bests = s; bk = 2; sg = -1.f; } }
+  // cyclic permutation into (k, u, w) coordinates without dynamic indexing
+  float ak, au, aw, bk_, bu, bw, sk, su, sw;
+  if (bk == 0)      { ak = a[0]; au = a[1]; aw = a[2]; bk_ = b[0]; bu = b[1]; bw = b[2]; sk = bsize[0]; su = bsize[1]; sw = bsize[2]; }
+  else if (bk == 1) { ak = a[1]; au = a[2]; aw = a[0]; bk_ = b[1]; bu = b[2]; bw = b[0]; sk = bsize[1]; su = bsize[2]; sw = bsize[0]; }
+  else              { ak = a[2]; au = a[0]; aw = a[1]; bk_ = b[2]; bu = b[0]; bw = b[1]; sk = bsize[2]; su = bsize[0]; sw = bsize[1]; }
   // clip the segment (parameter 0..1 from a to b) against the four side planes: closed form of MJX
   // _clip_edge_to_planes for a rectangular face
   float t0 = 0.f, t1 = 1.f; bool both = false;
@@ -330,39 +373,23 @@ KNOINLINE void capsule_box_near(float ax, float ay, float az, float bx, float by
     if ((t1 - t0) * (dk * dk + du * du + dw * dw) < 0.f) mask = false;
   }
   const float h0 = sg * (ak + t0 * (bk_ - ak)) - r - sk, h1 = sg * (ak + t1 * (bk_ - ak)) - r - sk;
-  const bool face_ok = mask && has_support;
-  float pen0 = face_ok ? -h0 : -1.f, pen1 = face_ok ? -h1 : -1.f;
-  float n[3] = {0.f, 0.f, 0.f};
-  n[bk] = sg;
-  o->pos[0][bk] = sg * (sk + 0.5f * h0); o->pos[0][iu] = au + t0 * (bu - au); o->pos[0][iw] = aw + t0 * (bw - aw);
-  o->pos[1][bk] = sg * (sk + 0.5f * h1); o->pos[1][iu] = au + t1 * (bu - au); o->pos[1][iw] = aw + t1 * (bw - aw);
-  for (int q = 0; q < 3; ++q) { o->nrm[0][q] = -n[q]; o->nrm[1][q] = -n[q]; }
-  // shallow edge contact: edge e = 4k + 2iu + iw runs along axis k at (u, w) = (+-s_u, +-s_w)
-  float bpen = -1.f, beax[3] = {0.f, 0.f, 0.f}, bec[3] = {0.f, 0.f, 0.f}, bcc[3] = {0.f, 0.f, 0.f};
-  bool bdeg = false;
-#pragma unroll 1
-  for (int e = 0; e < 12; ++e) {
-    const int k = e >> 2, u = (k + 1) % 3, w = (k + 2) % 3;
-    const float eu = (e & 2) ? 1.f : -1.f, ew = (e & 1) ? 1.f : -1.f;
-    float e0[3], e1[3];
-    e0[k] = -bsize[k]; e1[k] = bsize[k]; e0[u] = e1[u] = eu * bsize[u]; e0[w] = e1[w] = ew * bsize[w];
-    const SegPair sp = closest_seg_seg(e0[0], e0[1], e0[2], e1[0], e1[1], e1[2], ax, ay, az, bx, by, bz);
-    float dir[3];
-    sub3(dir, sp.a, sp.b);
-    const bool deg = dot3(dir, dir) < 1e-6f;
-    const float ed = normalize3(dir);
-    const bool front = (eu * dir[u] < 0.f) && (ew * dir[w] < 0.f);
-    const float epen = (!deg && front) ? r - ed : -1.f;
-    if (e == 0 || epen > bpen) { bpen = epen; bdeg = deg; copy3(beax, dir); copy3(bec, sp.a); copy3(bcc, sp.b); }
+  o.dist[0] = mask ? h0 : 1.f;
+  o.dist[1] = mask ? h1 : 1.f;
+  const float nx = bk == 0 ? sg : 0.f, ny = bk == 1 ? sg : 0.f, nz = bk == 2 ? sg : 0.f;
+  // an edge needs the segment in front of two faces of different axes
+  const int nout = ((fmaxf(a[0], b[0]) > bsize[0] || fminf(a[0], b[0]) < -bsize[0]) ? 1 : 0) +
+                   ((fmaxf(a[1], b[1]) > bsize[1] || fminf(a[1], b[1]) < -bsize[1]) ? 1 : 0) +
+                   ((fmaxf(a[2], b[2]) > bsize[2] || fminf(a[2], b[2]) < -bsize[2]) ? 1 : 0);
+  if (FULL || nout >= 2) {
+    // contact points / normals in (k,u,w) coordinates, rotated back to box axes
+    const float l0[3] = {sg * (sk + 0.5f * h0), au + t0 * (bu - au), aw + t0 * (bw - aw)};
+    const float l1[3] = {sg * (sk + 0.5f * h1), au + t1 * (bu - au), aw + t1 * (bw - aw)};
+    if (bk == 0)      { o.pos[0][0] = l0[0]; o.pos[0][1] = l0[1]; o.pos[0][2] = l0[2]; o.pos[1][0] = l1[0]; o.pos[1][1] = l1[1]; o.pos[1][2] = l1[2]; }
+    else if (bk == 1) { o.pos[0][1] = l0[0]; o.pos[0][2] = l0[1]; o.pos[0][0] = l0[2]; o.pos[1][1] = l1[0]; o.pos[1][2] = l1[1]; o.pos[1][0] = l1[2]; }
+    else              { o.pos[0][2] = l0[0]; o.pos[0][0] = l0[1]; o.pos[0][1] = l0[2]; o.pos[1][2] = l1[0]; o.pos[1][0] = l1[1]; o.pos[1][1] = l1[2]; }
+    o.nrm[0][0] = o.nrm[1][0] = -nx; o.nrm[0][1] = o.nrm[1][1] = -ny; o.nrm[0][2] = o.nrm[1][2] = -nz;
+    if (nout >= 2) capbox_edges(a[0], a[1], a[2], b[0], b[1], b[2], r, bsize[0], bsize[1], bsize[2], nx, ny, nz, &o);
   }
-  const bool parallel = fabsf(dot3(beax, n)) > 0.99f && !bdeg;
-  const float minface = fminf(pen0, pen1);
-  const bool has_edge = bpen > 0.f && (minface > 0.f ? bpen < minface : true) && !parallel;
-  if (has_edge) {
-    pen0 = bpen;
-    for (int q = 0; q < 3; ++q) { o->pos[0][q] = 0.5f * (bec[q] + bcc[q] + beax[q] * r); o->nrm[0][q] = beax[q]; }
-  }
-  o->dist[0] = -pen0; o->dist[1] = -pen1;
 }
 template <bool FULL>
 KFN void capsule_box(const float* A, const float* B, float r, const float* bpos, const float* bmat, const float* bsize, Contact2& c) {
@@ -374,7 +401,7 @@ KFN void capsule_box(const float* A, const float* B, float r, const float* bpos,
     return;
   }
   CapBoxOut o;
-  capsule_box_near(a[0], a[1], a[2], b[0], b[1], b[2], r, bsize[0], bsize[1], bsize[2], &o);
+  capsule_box_near<FULL>(a, b, r, bsize, o);
   c.dist[0] = o.dist[0]; c.dist[1] = o.dist[1];
   if (FULL) {
 #pragma unroll
@@ -385,115 +412,6 @@ KFN void capsule_box(const float* A, const float* B, float r, const float* bpos,
       normalize3(c.nrm[j]);
     }
   }
-}
-#else
-// round-1 restatement (no has_support gate; true far-field face distances), kept for tools/capbox_ab.py only
-template <bool FULL>
-KFN void capsule_box(const float* A, const float* B, float r, const float* bpos, const float* bmat, const float* bsize, Contact2& c) {
-  float t[3], a[3], b[3];
-  sub3(t, A, bpos); matT_vec(a, bmat, t);
-  sub3(t, B, bpos); matT_vec(b, bmat, t);
-  // best face: argmax over (+x,-x,+y,-y,+z,-z) of min over end points of the signed face distance
-  float bests = fminf(a[0], b[0]) - bsize[0]; int bk = 0; float sg = 1.f;
-  { float s = -fmaxf(a[0], b[0]) - bsize[0]; if (s > bests) { bests = s; sg = -1.f; } }
-  { float s = fminf(a[1], b[1]) - bsize[1]; if (s > bests) { bests = s; bk = 1; sg = 1.f; } }
-  { float s = -fmaxf(a[1], b[1]) - bsize[1]; if (s > bests) { bests = s; bk = 1; sg = -1.f; } }
-  { float s = fminf(a[2], b[2]) - bsize[2]; if (s > bests) { bests = s; bk = 2; sg = 1.f; } }
-  { float s = -fmaxf(a[2], b[2]) - bsize[2]; if (s > bests) { bests = s; bk = 2; sg = -1.f; } }
-  // cyclic permutation into (k, u, w) coordinates without dynamic indexing
-  float ak, au, aw, bk_, bu, bw, sk, su, sw;
-  if (bk == 0)      { ak = a[0]; au = a[1]; aw = a[2]; bk_ = b[0]; bu = b[1]; bw = b[2]; sk = bsize[0]; su = bsize[1]; sw = bsize[2]; }
-  else if (bk == 1) { ak = a[1]; au = a[2]; aw = a[0]; bk_ = b[1]; bu = b[2]; bw = b[0]; sk = bsize[1]; su = bsize[2]; sw = bsize[0]; }
-  else              { ak = a[2]; au = a[0]; aw = a[1]; bk_ = b[2]; bu = b[0]; bw = b[1]; sk = bsize[2]; su = bsize[0]; sw = bsize[1]; }
-  // clip the segment (parameter 0..1 from a to b) against the four side planes
-  float t0 = 0.f, t1 = 1.f; bool both = false;
-  {
-    const float Lu = 2.f * sw, Lw = 2.f * su;      // length of the edge each side plane is built on
-#define CEMK_CLIP(pa, pb, s, tau, L) { \
-      float na_ = ((tau) * (pa) - (s)) * (L), nb_ = ((tau) * (pb) - (s)) * (L); \
-      bool fa = na_ > 1e-6f, fb = nb_ > 1e-6f; \
-      float den = (tau) * ((pb) - (pa)) * (L); \
-      float tt = (-na_) / (den + (den == 0.f ? 1e-6f : 0.f)); \
-      tt = fminf(fmaxf(tt, 0.f), 1.f); \
-      if (fa) t0 = fmaxf(t0, tt); \
-      if (fb) t1 = fminf(t1, tt); \
-      both = both || (fa && fb); }
-    CEMK_CLIP(au, bu, su, -1.f, Lu)
-    CEMK_CLIP(aw, bw, sw, -1.f, Lw)
-    CEMK_CLIP(au, bu, su, 1.f, Lu)
-    CEMK_CLIP(aw, bw, sw, 1.f, Lw)
-#undef CEMK_CLIP
-  }
-  bool mask = !both;
-  if (!mask) { t0 = 0.f; t1 = 1.f; }
-  {
-    float dk = bk_ - ak, du = bu - au, dw = bw - aw;
-    if ((t1 - t0) * (dk * dk + du * du + dw * dw) < 0.f) mask = false;
-  }
-  float h0 = sg * (ak + t0 * (bk_ - ak)) - r - sk, h1 = sg * (ak + t1 * (bk_ - ak)) - r - sk;
-  c.dist[0] = mask ? h0 : 1.f;
-  c.dist[1] = mask ? h1 : 1.f;
-  float lp[2][3], ln[2][3];     // contact point / normal in (k,u,w) box coordinates
-  if (FULL) {
-    lp[0][0] = sg * (sk + 0.5f * h0); lp[0][1] = au + t0 * (bu - au); lp[0][2] = aw + t0 * (bw - aw);
-    lp[1][0] = sg * (sk + 0.5f * h1); lp[1][1] = au + t1 * (bu - au); lp[1][2] = aw + t1 * (bw - aw);
-    ln[0][0] = -sg; ln[0][1] = 0.f; ln[0][2] = 0.f;
-    ln[1][0] = -sg; ln[1][1] = 0.f; ln[1][2] = 0.f;
-  }
-  // shallow edge contact: an edge of the face closer than r to the segment replaces slot 0.
-  // Every edge lies in the face plane, so nothing to do when the segment stays >= r away from it.
-  // ... nor when both end points lie inside the face rectangle shrunk by r (the shrunk rectangle is
-  // convex, so every point of the segment is then >= r from every edge).
-  float ha = sg * ak - sk, hb = sg * bk_ - sk;
-  float hmin = (ha * hb <= 0.f) ? 0.f : fminf(fabsf(ha), fabsf(hb));
-  const bool interior = fmaxf(fabsf(au), fabsf(bu)) < su - r && fmaxf(fabsf(aw), fabsf(bw)) < sw - r;
-  if (hmin < r && !interior) {
-    float bd = 0.f, bec[3] = {0.f, 0.f, 0.f}, bcc[3] = {0.f, 0.f, 0.f};
-#pragma unroll 1
-    for (int i = 0; i < 4; ++i) {
-      // face polygon counter-clockwise seen from outside (reversed for the negative face);
-      // edge i runs from V[i-1] to V[i]
-      const int ip = (i + 3) & 3;
-      const int vi = sg < 0.f ? 3 - i : i, vp = sg < 0.f ? 3 - ip : ip;
-      const float u1 = (vi == 1 || vi == 2) ? su : -su, w1 = vi >= 2 ? sw : -sw;
-      const float u0 = (vp == 1 || vp == 2) ? su : -su, w0 = vp >= 2 ? sw : -sw;
-      SegPair sp = closest_seg_seg(sg * sk, u0, w0, sg * sk, u1, w1, ak, au, aw, bk_, bu, bw);
-      float df[3];
-      sub3(df, sp.a, sp.b);
-      float d2 = dot3(df, df);
-      if (i == 0 || d2 < bd) { bd = d2; copy3(bec, sp.a); copy3(bcc, sp.b); }
-    }
-    float eax[3];
-    sub3(eax, bcc, bec);
-    float ed = normalize3(eax);
-    float epen = r - ed;
-    if (epen > 0.f) {
-      c.dist[0] = -epen;
-      if (FULL) {
-        for (int q = 0; q < 3; ++q) { lp[0][q] = 0.5f * (bec[q] + bcc[q] - eax[q] * r); ln[0][q] = -eax[q]; }
-      }
-    }
-  }
-  if (FULL) {
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      float p[3], n[3];
-      if (bk == 0)      { p[0] = lp[j][0]; p[1] = lp[j][1]; p[2] = lp[j][2]; n[0] = ln[j][0]; n[1] = ln[j][1]; n[2] = ln[j][2]; }
-      else if (bk == 1) { p[1] = lp[j][0]; p[2] = lp[j][1]; p[0] = lp[j][2]; n[1] = ln[j][0]; n[2] = ln[j][1]; n[0] = ln[j][2]; }
-      else              { p[2] = lp[j][0]; p[0] = lp[j][1]; p[1] = lp[j][2]; n[2] = ln[j][0]; n[0] = ln[j][1]; n[1] = ln[j][2]; }
-      float w[3];
-      mat_vec(w, bmat, p); add3(c.pos[j], w, bpos);
-      mat_vec(c.nrm[j], bmat, n);
-      normalize3(c.nrm[j]);
-    }
-  }
-}
-#endif
-KFN Dist2 capsule_box_dist(const float* A, const float* B, float r, const float* bpos, const float* bmat, const float* bsize) {
-  Contact2 c;
-  capsule_box<false>(A, B, r, bpos, bmat, bsize, c);
-  Dist2 d; d.d0 = c.dist[0]; d.d1 = c.dist[1];
-  return d;
 }
 
 // ---- free-box colliders (lane-serial, rarely past the bounding-sphere test) -------------------
@@ -984,23 +902,29 @@ KFN bool in_bracket(const LSPoint& x, const LSPoint& y) {
   return ((x.d0 < y.d0) && (y.d0 < 0.f)) || ((x.d0 > y.d0) && (y.d0 > 0.f));
 }
 
-// emit the full contact records (position, frame) of one lane's active robot slots; rare path
+// write one contact record (position, frame, distance, weights, the two links); t1 = own first tangent or nullptr
+template <int NC>
+KFN void put_contact(WarpSmemT<NC>& S, int o, const float* pos, const float* nrm, const float* t1, float dist, float invw, int l1, int l2) {
+  if (o >= KM_NC_TOT) return;
+  float* g = S.template geo<true>(o);             // rare path: a pointer into either space is fine here
+  copy3(g, pos); copy3(g + 3, nrm);
+  if (t1) { copy3(g + 6, t1); cross3(g + 9, nrm, t1); }
+  else make_tangents(nrm, g + 6, g + 9);
+  g[12] = dist; g[13] = invw; g[14] = (float)l1; g[15] = (float)l2;
+}
+// emit the full contact records of one lane's active plane-capsule / capsule-capsule slots; rare path
+// (capsule-box contacts are written by the near pass of the narrow phase itself)
 template <int NC>
 KNOINLINE void emit_robot_contacts(const KModel& m, WarpSmemT<NC>& S, int lane, int actmask, int o) {
 #pragma unroll 1
-  for (int p = 0; p < KM_NPASS; ++p) {
+  for (int p = m.ncbpass; p < KM_NPASS; ++p) {
     const int bits = (actmask >> (2 * p)) & 3;
     if (!bits) continue;
-    const int e = p * KW + lane, ty = m.rp_type[e], a = m.rp_a[e], b = m.rp_b[e];
+    const int x = m.rp[p * KW + lane], ty = KP_TYPE(x), a = KP_A(x), b = KP_B(x);
     Contact2 c;
     float invw; int l1, l2;
     float pt1[3]; bool own_t1 = false;
-    if (ty == KP_CAP_BOX) {
-      const bool st = b < m.nsbox;
-      capsule_box<true>(S.capA[a], S.capB[a], m.cap_r[a], st ? m.sb_pos[b] : S.qpos + KM_NL, st ? m.sb_mat[b] : S.bmat,
-                        st ? m.sb_size[b] : m.fb_size, c);
-      invw = m.cap_invw[a] + (st ? 0.f : m.fb_invw); l1 = m.cap_link[a]; l2 = st ? -1 : KM_NL;
-    } else if (ty == KP_CAP_CAP) {
+    if (ty == KP_CAP_CAP) {
       capsule_capsule<true>(S.capA[a], S.capB[a], m.cap_r[a], S.capA[b], S.capB[b], m.cap_r[b], c);
       invw = m.cap_invw[a] + m.cap_invw[b]; l1 = m.cap_link[a]; l2 = m.cap_link[b];
     } else {
@@ -1019,13 +943,7 @@ KNOINLINE void emit_robot_contacts(const KModel& m, WarpSmemT<NC>& S, int lane, 
 #pragma unroll 1
     for (int k = 0; k < 2; ++k) {
       if (!((bits >> k) & 1)) continue;
-      if (o < KM_NC_TOT) {
-        float* g = S.template geo<true>(o);       // rare path: a pointer into either space is fine here
-        copy3(g, c.pos[k]); copy3(g + 3, c.nrm[k]);
-        if (own_t1) { copy3(g + 6, pt1); cross3(g + 9, c.nrm[k], pt1); }
-        else make_tangents(c.nrm[k], g + 6, g + 9);
-        g[12] = c.dist[k]; g[13] = invw; g[14] = (float)l1; g[15] = (float)l2;
-      }
+      put_contact<NC>(S, o, c.pos[k], c.nrm[k], own_t1 ? pt1 : nullptr, c.dist[k], invw, l1, l2);
       ++o;
     }
   }
@@ -1524,39 +1442,70 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
   }
   PHASE_ALIGN(1);
   PHASE(W, 4);
-  // ---- N1: narrow phase (distances only) + collision cost of this step ----
+  // ---- N1: narrow phase + collision cost of this step (mjx_planner.py:287-296:
+  //      cost_c = sum max(0, (1-y) c_t - c_{t+1}) + #(c < 0), y = 0.005) ----
+  // Capsule-box (70 of the 107 pairs): lane l keeps capsule l in registers and walks the boxes; a pair is decided by
+  // its far-field test (both slots = +1, see capsule_box) and then costs nothing -- not even its previous
+  // distances are touched while it stays far (R.farprev).  The few pairs that are not far are *compacted* into a
+  // per-sample list and evaluated densely by the first lanes, full contact records included, so a sample's narrow
+  // phase costs one extra collider pass however its near pairs are spread over the table (the warps of a CTA
+  // step in lockstep: the slowest one sets the pace).
   LANES(W, R)
-    int nact = 0, actmask = 0;
+    int nact = 0, actmask = 0, nearbits = 0, farbits = 0;
     float cc = 0.f;
-    // previous distances of this lane's two slots, fetched one pass ahead so the L2 latency hides behind the collider
     float* pd = io.prevd + lane;
-    float pv0 = 0.f, pv1 = 0.f;
-    if (!io.first) { pv0 = pd[0]; pv1 = pd[KW]; }
+    if (lane < m.ncap) {
+      const float A[3] = {S.capA[lane][0], S.capA[lane][1], S.capA[lane][2]}, B[3] = {S.capB[lane][0], S.capB[lane][1], S.capB[lane][2]};
+      const float r = m.cap_r[lane];
+#pragma unroll 2
+      for (int p = 0; p < m.ncbpass; ++p) {
+        const bool st = p < m.nsbox;
+        float la[3], lb[3];
+        capbox_local(A, B, st ? m.sb_pos[p] : S.qpos + KM_NL, st ? m.sb_mat[p] : S.bmat, la, lb);
+        const bool far = capbox_far(la, lb, r, st ? m.sb_size[p] : m.fb_size);
+        const bool valid = KP_TYPE(m.rp[p * KW + lane]) == KP_CAP_BOX;
+        if (valid) { if (far) farbits |= 1 << p; else nearbits |= 1 << p; }
+      }
+    }
+    // a far pair whose previous distances were real: (1-y) c_t - 1 can only be positive for c_t > 1 / (1-y)
+    if (!io.first) {
 #pragma unroll 1
-    for (int p = 0; p < KM_NPASS; ++p) {
+      for (int rem = farbits & ~R.farprev; rem; rem &= rem - 1) {
+        const int p = KFFS(rem) - 1;
+        cc += fmaxf((1.f - 0.005f) * pd[(2 * p) * KW] - 1.f, 0.f) + fmaxf((1.f - 0.005f) * pd[(2 * p + 1) * KW] - 1.f, 0.f);
+      }
+    }
+    if (io.collision_row) {
+#pragma unroll 1
+      for (int rem = farbits; rem; rem &= rem - 1) {
+        const int sl = KP_SLOT(m.rp[(KFFS(rem) - 1) * KW + lane]);
+        io.collision_row[sl] = 1.f; io.collision_row[sl + 1] = 1.f;
+      }
+    }
+    R.off = nearbits | ((nearbits & R.farprev) << 16);     // near pairs, and which of them were far one step ago
+    R.farprev = farbits;
+    // plane-capsule and capsule-capsule passes: previous distances of this lane's two slots, fetched one pass ahead
+    // so the L2 latency hides behind the collider
+    float pv0 = 0.f, pv1 = 0.f;
+    if (!io.first) { pv0 = pd[(2 * m.ncbpass) * KW]; pv1 = pd[(2 * m.ncbpass + 1) * KW]; }
+#pragma unroll 1
+    for (int p = m.ncbpass; p < KM_NPASS; ++p) {
       const int e = p * KW + lane;
-      const int ty = m.rp_type[e];
+      const int x = m.rp[e], ty = KP_TYPE(x);
       const float prev0 = pv0, prev1 = pv1;
       if (!io.first && p + 1 < KM_NPASS) { pv0 = pd[(2 * p + 2) * KW]; pv1 = pd[(2 * p + 3) * KW]; }
       if (ty == KP_NONE) continue;
-      const int a = m.rp_a[e], b = m.rp_b[e];
+      const int a = KP_A(x), b = KP_B(x);
       float d0, d1 = 1.f;
-      if (ty == KP_CAP_BOX) {
-        const bool st = b < m.nsbox;
-        Dist2 d = capsule_box_dist(S.capA[a], S.capB[a], m.cap_r[a], st ? m.sb_pos[b] : S.qpos + KM_NL, st ? m.sb_mat[b] : S.bmat,
-                                   st ? m.sb_size[b] : m.fb_size);
-        d0 = d.d0; d1 = d.d1;
-      } else if (ty == KP_CAP_CAP) {
-        Contact2 c;
+      Contact2 c;
+      if (ty == KP_CAP_CAP) {
         capsule_capsule<false>(S.capA[a], S.capB[a], m.cap_r[a], S.capA[b], S.capB[b], m.cap_r[b], c);
         d0 = c.dist[0];
       } else {
-        Contact2 c;
         plane_capsule<false>(m.plane_pos, m.plane_n, S.capA[b], S.capB[b], m.cap_r[b], c);
         d0 = c.dist[0]; d1 = c.dist[1];
       }
       const int ns = ty == KP_CAP_CAP ? 1 : 2;
-      // cost_c (mjx_planner.py:287-296): sum max(0, (1-y) c_t - c_{t+1}) + #(c < 0), y = 0.005
       if (d0 < 0.f) { ++nact; actmask |= 1 << (2 * p); cc += 1.f; }
       if (!io.first) cc += fmaxf((1.f - 0.005f) * prev0 - d0, 0.f);
       pd[(2 * p) * KW] = d0;
@@ -1566,14 +1515,104 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
         pd[(2 * p + 1) * KW] = d1;
       }
       if (io.collision_row) {
-        io.collision_row[m.rp_slot[e]] = d0;
-        if (ns == 2) io.collision_row[m.rp_slot[e] + 1] = d1;
+        io.collision_row[KP_SLOT(x)] = d0;
+        if (ns == 2) io.collision_row[KP_SLOT(x) + 1] = d1;
       }
     }
     R.cost_c += cc;
-    R.h[0] = __int_as_float(actmask);          // parked: the cooperative box colliders below reuse the scratch fields
-    R.h[1] = __int_as_float(nact);
+    R.acc[7] = __int_as_float(actmask);        // parked: the near pass and the cooperative box colliders below reuse the scratch fields
+    R.acc[8] = __int_as_float(nact);
   END_LANES
+  PHASE(W, 20);
+  int ncbcon = 0;                                  // capsule-box contacts: they open the contact list
+  {
+    // list position of a near pair: pass-major, lane-minor
+    unsigned nm[KM_MAXSBOX + 1];
+    int ntot = 0;
+#pragma unroll
+    for (int p = 0; p < KM_MAXSBOX + 1; ++p) {
+      nm[p] = 0u;
+      if (p < m.ncbpass) {
+        nm[p] = warp_ballot(W, [&](int, LaneRegs& R) { return ((R.off >> p) & 1) != 0; });
+        ntot += KPOPC(nm[p]);
+      }
+    }
+    if (warp_any_groups(W, ntot > 0)) {
+      LANES(W, R)
+        int base = 0;
+#pragma unroll
+        for (int p = 0; p < KM_MAXSBOX + 1; ++p) {
+          if ((R.off >> p) & 1) S.nlist[base + KPOPC(nm[p] & ((1u << lane) - 1u))] = (unsigned char)(p * KW + lane);
+          base += KPOPC(nm[p]);
+        }
+      END_LANES
+      PHASE(W, 21);
+#pragma unroll 1
+      for (int i0 = 0; warp_any_groups(W, i0 < ntot); i0 += KW) {
+        // one near pair per lane: both distances, and the full record of every penetrating slot (parked in R.h)
+        LANES(W, R)
+          const int i = i0 + lane;
+          R.nact = 0;
+          if (i < ntot) {
+            const int x = m.rp[S.nlist[i]], a = KP_A(x), b = KP_B(x);
+            const bool st = b < m.nsbox;
+            Contact2 c;
+            capsule_box<true>(S.capA[a], S.capB[a], m.cap_r[a], st ? m.sb_pos[b] : S.qpos + KM_NL, st ? m.sb_mat[b] : S.bmat,
+                              st ? m.sb_size[b] : m.fb_size, c);
+            S.nres[i][0] = c.dist[0]; S.nres[i][1] = c.dist[1];
+            R.nact = (c.dist[0] < 0.f ? 1 : 0) + (c.dist[1] < 0.f ? 2 : 0);
+            if (R.nact) {
+#pragma unroll
+              for (int k = 0; k < 3; ++k) { R.h[k] = c.pos[0][k]; R.h[3 + k] = c.nrm[0][k]; R.h[6 + k] = c.pos[1][k]; R.h[9 + k] = c.nrm[1][k]; }
+              R.f0 = c.dist[0]; R.f1 = c.dist[1];
+            }
+          }
+        END_LANES
+        const int nnew = warp_excl_scan(W, [](int, LaneRegs& R) { return (R.nact & 1) + (R.nact >> 1); }, [](int, LaneRegs& R, int o) { R.actmask = o; });
+        if (warp_any_groups(W, nnew > 0)) {
+          LANES(W, R)
+            if (R.nact) {
+              const int x = m.rp[S.nlist[i0 + lane]], a = KP_A(x), b = KP_B(x);
+              const bool st = b < m.nsbox;
+              const float invw = m.cap_invw[a] + (st ? 0.f : m.fb_invw);
+              int o = ncbcon + R.actmask;
+              if (R.nact & 1) { put_contact<NC>(S, o, R.h, R.h + 3, nullptr, R.f0, invw, m.cap_link[a], st ? -1 : KM_NL); ++o; }
+              if (R.nact & 2) put_contact<NC>(S, o, R.h + 6, R.h + 9, nullptr, R.f1, invw, m.cap_link[a], st ? -1 : KM_NL);
+            }
+          END_LANES
+        }
+        ncbcon += nnew;
+      }
+      PHASE(W, 22);
+      // the owners of the near pairs account for them: cost, previous distances
+      LANES(W, R)
+        if (R.off) {
+          int base = 0;
+          float cc = 0.f;
+          float* pd = io.prevd + lane;
+#pragma unroll
+          for (int p = 0; p < KM_MAXSBOX + 1; ++p) {
+            if ((R.off >> p) & 1) {
+              const int i = base + KPOPC(nm[p] & ((1u << lane) - 1u));
+              const float d0 = S.nres[i][0], d1 = S.nres[i][1];
+              if (d0 < 0.f) cc += 1.f;
+              if (d1 < 0.f) cc += 1.f;
+              if (!io.first) {
+                const bool wasfar = (R.off >> (16 + p)) & 1;
+                const float prev0 = wasfar ? 1.f : pd[(2 * p) * KW], prev1 = wasfar ? 1.f : pd[(2 * p + 1) * KW];
+                cc += fmaxf((1.f - 0.005f) * prev0 - d0, 0.f) + fmaxf((1.f - 0.005f) * prev1 - d1, 0.f);
+              }
+              pd[(2 * p) * KW] = d0; pd[(2 * p + 1) * KW] = d1;
+              if (io.collision_row) { const int sl = KP_SLOT(m.rp[p * KW + lane]); io.collision_row[sl] = d0; io.collision_row[sl + 1] = d1; }
+            }
+            base += KPOPC(nm[p]);
+          }
+          R.cost_c += cc;
+        }
+      END_LANES
+    }
+  }
+  PHASE(W, 23);
   PHASE_ALIGN(4);
   PHASE(W, 5);
   // free-box pairs: broad phase for all pairs at once (one lane per pair), then the cooperative
@@ -1616,11 +1655,12 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
     }
   }
   LANES(W, R)
-    R.actmask = __float_as_int(R.h[0]);
-    R.nact = __float_as_int(R.h[1]);
+    R.actmask = __float_as_int(R.acc[7]);
+    R.nact = __float_as_int(R.acc[8]);
   END_LANES
-  // list positions: robot contacts first (lane-major), then the staged free-box contacts (pair-major)
-  const int nrob = warp_excl_scan(W, [](int, LaneRegs& R) { return R.nact; }, [](int, LaneRegs& R, int o) { R.off = o; });
+  // list positions: capsule-box contacts (written above, near-list order), then the other robot contacts
+  // (lane-major), then the staged free-box contacts (pair-major)
+  const int nrob = ncbcon + warp_excl_scan(W, [](int, LaneRegs& R) { return R.nact; }, [&](int, LaneRegs& R, int o) { R.off = ncbcon + o; });
   const unsigned bmask = m.has_box ? warp_ballot32(W, [&](int l) { return l < 4 * m.nbpair && S.bstage[l >> 2][l & 3][3] < 0.f; }) : 0u;
   const int ncon_all = nrob + KPOPC(bmask);
   const int ncon = ncon_all < KM_NC_TOT ? ncon_all : KM_NC_TOT;
@@ -1735,6 +1775,7 @@ KFN void rollout_sample(Warp& W, const KModel& m, WarpSmemT<NC>& S, const Rollou
     }
     if (lane == 0) { S.flags = 0; S.ovf = A.ovf; }
     R.cost_c = 0.f;
+    R.farprev = 0;
     R.td = lane < KM_NL ? A.thetadot[lane * A.T] : 0.f;
   END_LANES
   float tq[4] = {A.target_rot[0], A.target_rot[1], A.target_rot[2], A.target_rot[3]};

@@ -15,7 +15,7 @@ import numpy as np
 from .mjcf import (GEOM_BOX, GEOM_CAPSULE, GEOM_PLANE, JNT_FREE, JNT_HINGE, ModelConsts, quat_mul,
                    quat_normalize, quat_to_mat)
 
-NL, NV, NQ, MAXCAP, MAXSBOX, MAXRPAIR, MAXBPAIR = 6, 12, 13, 12, 8, 128, 8
+NL, NV, NQ, MAXCAP, MAXSBOX, MAXRPAIR, MAXBPAIR, MAXNEAR = 6, 12, 13, 12, 8, 160, 8, 96
 LANE_GROUP = 16          # lanes per sample in the rollout kernel (csrc/warp_dsl.h KW); one collider pass = 16 pair entries
 KP_NONE, KP_PLANE_CAP, KP_CAP_CAP, KP_CAP_BOX = -1, 0, 1, 2
 KB_PLANE_BOX, KB_BOX_BOX, KB_BOX_BOX_SWAP = 0, 1, 2
@@ -37,7 +37,7 @@ class KModel(C.Structure):
         ("l_armature", _f * NL), ("l_damping", _f * NL), ("l_lo", _f * NL), ("l_hi", _f * NL),
         ("l_invw", _f * NL), ("l_margin", _f * NL),
         ("l_limited", _i * NL),
-        ("pad3", _i * 2),
+        ("ncbpass", _i), ("pad3", _i),
         ("tcp_pos", _f * 4), ("hande_quat", _f * 4),
         ("cap_link", _i * MAXCAP),
         ("cap_pos", _f * 4 * MAXCAP), ("cap_axis", _f * 4 * MAXCAP),
@@ -46,7 +46,7 @@ class KModel(C.Structure):
         ("sb_pos", _f * 4 * MAXSBOX), ("sb_mat", _f * 12 * MAXSBOX), ("sb_size", _f * 4 * MAXSBOX),
         ("fb_size", _f * 4), ("fb_inertia", _f * 4),
         ("fb_mass", _f), ("fb_damping", _f), ("fb_invw", _f), ("pad4", _f),
-        ("rp_type", _i * MAXRPAIR), ("rp_a", _i * MAXRPAIR), ("rp_b", _i * MAXRPAIR), ("rp_slot", _i * MAXRPAIR),
+        ("rp", _i * MAXRPAIR),
         ("bp_type", _i * MAXBPAIR), ("bp_a", _i * MAXBPAIR),
         ("qpos0", _f * 16), ("warm0", _f * 12), ("qvel0", _f * 12),
     ]
@@ -260,19 +260,30 @@ def build_kmodel(mc: ModelConsts, timestep: float, robot_geom_names=None, tcp_si
     if len(rpairs) > MAXRPAIR or len(bpairs) > MAXBPAIR:
         raise NotImplementedError("too many pairs")
     m.nrpair, m.nbpair, m.nslot_robot = len(rpairs), len(bpairs), slot
-    # lanes of one 16-wide pass should run the same collider (a divergent pass pays for every collider
-    # present in it): capsule-box first, plane-capsule right behind, capsule-capsule on its own pass(es)
+    # Table layout (csrc/kmodel.h): passes 0 .. ncbpass-1 = capsule-box, pass p = box p, lane l = capsule l; then
+    # plane-capsule and capsule-capsule, each type starting on a pass boundary (lanes of a pass run one collider).
     by = lambda ty: [i for i in range(len(rpairs)) if rpairs[i][0] == ty]
-    order = by(KP_CAP_BOX) + by(KP_PLANE_CAP)
-    pad = (-len(order)) % LANE_GROUP
-    if len(order) + pad + len(by(KP_CAP_CAP)) > MAXRPAIR:
-        pad = 0
-    order = order + [None] * pad + by(KP_CAP_CAP)
+    table = {}
+    cb = by(KP_CAP_BOX)
+    if len(cb) > MAXNEAR or m.ncap > LANE_GROUP:
+        raise NotImplementedError("too many capsule-box pairs")
+    m.ncbpass = (max(rpairs[i][2] for i in cb) + 1) if cb else 0
+    for i in cb:
+        _, cap, box, _ = rpairs[i]
+        table[box * LANE_GROUP + cap] = i
+    e = m.ncbpass * LANE_GROUP
+    for ty in (KP_PLANE_CAP, KP_CAP_CAP):
+        for i in by(ty):
+            table[e] = i
+            e += 1
+        e += (-e) % LANE_GROUP
+    if e > MAXRPAIR:
+        raise NotImplementedError("pair table too small")
     for e in range(MAXRPAIR):
-        m.rp_type[e] = KP_NONE
-    for e, i in enumerate(order):
-        if i is not None:
-            m.rp_type[e], m.rp_a[e], m.rp_b[e], m.rp_slot[e] = rpairs[i]
+        m.rp[e] = 0
+    for e, i in table.items():
+        ty, a, b, sl = rpairs[i]
+        m.rp[e] = (ty + 1) | (a << 4) | (b << 8) | (sl << 16)
     for e, (ty, a) in enumerate(bpairs):
         m.bp_type[e], m.bp_a[e] = ty, a
     _set(m.qpos0, mc.qpos0)

@@ -201,4 +201,6 @@ def run_cem_planner(num_dof=None, num_batch=None, num_steps=None, maxiter_cem=No
         np.savetxt(f'{data_dir}/cost_c.csv', cost_c_list, delimiter=",")
     return {'cost_g': cost_g_list, 'cost_r': cost_r_list, 'cost_c': cost_c_list, 'cost': cost_list, 'thetadot': thetadot_list,
             'theta': theta_list, 'tick_ms': tick_ms, 'final_target': current_target, 'reached_final': reached_final,
-            'dist': dist_list, 'switch_ticks': switch_ticks}
+            'dist': dist_list, 'switch_ticks': switch_ticks, 'cem': cem,
+            'last': dict(xi_mean=xi_mean, qpos=data.qpos.copy(), qvel=data.qvel.copy(), qacc=data.qacc.copy(),
+                         target_pos=np.array(target_pos), target_rot=np.array(target_rot))}

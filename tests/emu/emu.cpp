@@ -48,3 +48,14 @@ extern "C" int emu_rollout(const KModel* m, int B, int T, const float* thetadot,
   }
   return 0;
 }
+
+// the kernel's capsule-box collider in isolation (full contact record), for fuzzing against the oracle's
+extern "C" void emu_capsule_box(const float* A, const float* B, float r, const float* bpos, const float* bmat, const float* bsize,
+                                float* dist2, float* pos6, float* nrm6) {
+  Contact2 c;
+  capsule_box<true>(A, B, r, bpos, bmat, bsize, c);
+  for (int j = 0; j < 2; ++j) {
+    dist2[j] = c.dist[j];
+    for (int k = 0; k < 3; ++k) { pos6[3 * j + k] = c.pos[j][k]; nrm6[3 * j + k] = c.nrm[j][k]; }
+  }
+}

@@ -42,3 +42,16 @@ class Emu:
                              p(out["theta"]), p(out["cost4"]), p(out["eef_pos"]), p(out["eef_rot"]), p(out["collision"]), p(out["qacc"]),
                              p(out["flags"]), int(nc))
         return out
+
+
+def capsule_box(cpos, cmat, csize, bpos, bmat, bsize):
+    """The kernel's capsule_box<true> (csrc/rollout_core.h) on one pair -> dist [2], pos [2,3], normal [2,3]."""
+    lib = C.CDLL(build())
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    cpos, cmat = np.asarray(cpos, float), np.asarray(cmat, float).reshape(3, 3)
+    A, B = f(cpos - cmat[:, 2] * csize[1]), f(cpos + cmat[:, 2] * csize[1])
+    bp, bm, bs = f(bpos), f(np.asarray(bmat, float).reshape(-1)), f(bsize)
+    d, p, n = np.zeros(2, np.float32), np.zeros(6, np.float32), np.zeros(6, np.float32)
+    q = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib.emu_capsule_box(q(A), q(B), C.c_float(csize[0]), q(bp), q(bm), q(bs), q(d), q(p), q(n))
+    return d, p.reshape(2, 3), n.reshape(2, 3)

@@ -45,6 +45,7 @@ def test_teacher_forced_steps_on_contact_states(emu, oracle64, oracle32):
     warm0 = oracle64.initial_warmstart()
     n = stable = 0
     worst_col = 0.0
+    dev = []
     for s in has[:24]:
         qvbox = np.zeros(6)
         for t in range(T):
@@ -68,9 +69,12 @@ def test_teacher_forced_steps_on_contact_states(emu, oracle64, oracle32):
             n += 1
             if np.abs(r32["qacc"] - r64["qacc"]).max() < 1e-3 * scale:
                 stable += 1
-                assert np.abs(out["qacc"][0, 0] - r64["qacc"]).max() < 2e-2 * scale, (s, t)
+                dev.append(np.abs(out["qacc"][0, 0] - r64["qacc"]).max() / scale)
     assert n > 50 and stable > 0.3 * n
     assert worst_col < 1e-5
+    dev = np.array(dev)
+    assert (dev < 5e-2).all(), np.sort(dev)[-5:]                  # inside the line-search bracket-flip jump
+    assert (dev < 1e-3).mean() >= 0.85, np.sort(dev)[-10:]
 
 
 def test_contact_capacity_variants_agree(emu):
@@ -231,3 +235,56 @@ def test_spill_area_with_robot_box_coupling(emu, oracle64, mc):
             np.testing.assert_allclose(a["collision"][0, 0], r["con_dist"][oracle64.mask], atol=2e-5)
             hits += 1
     assert hits >= 2
+
+
+def test_kernel_capsule_box_matches_oracle_fuzz():
+    """The kernel's capsule-box collider (far-field early-out, closed-form clip, filtered edge loop) against the
+    oracle's literal restatement of MJX _capsule_convex on random poses concentrated around contact: distances of
+    both slots (incl. the +1 sentinel), and position / normal of every penetrating slot."""
+    from emu_util import capsule_box
+    from oracle.oracle import collide
+    from test_oracle_colliders import rot
+    rng = np.random.default_rng(7)
+    n_near = n_act = n_edge = n_flip = 0
+    dev_p, dev_n = [], []
+    for trial in range(6000):
+        bs = rng.uniform(0.02, 0.3, 3)
+        r, hl = rng.uniform(0.02, 0.06), rng.uniform(0.02, 0.2)
+        Rb = rot(rng.normal(size=3), rng.uniform(0, 3)) if trial % 2 else np.eye(3)
+        Rc = rot(rng.normal(size=3), rng.uniform(0, 3))
+        # capsule centre near the box surface: pick a point on a random face / edge / corner shell
+        p = rng.uniform(-1, 1, 3) * bs
+        k = rng.integers(3)
+        p[k] = np.sign(p[k] or 1.0) * bs[k]
+        if trial % 3 == 0:
+            k2 = (k + 1) % 3
+            p[k2] = np.sign(p[k2] or 1.0) * bs[k2]
+        off = rng.normal(size=3)
+        c_local = p + off / np.linalg.norm(off) * rng.uniform(0, 1.5) * (r + hl * rng.uniform(0, 1))
+        bpos = rng.uniform(-0.5, 0.5, 3)
+        cpos = bpos + Rb @ c_local
+        d_o, p_o, f_o = collide("capsule_box", cpos, Rc, [r, hl, 0], bpos, Rb, bs)
+        # position / normal of an edge contact come out of MJX's regularised closest-segment routine, which is
+        # float32-sensitive (~1e-3 on the normal for near-parallel segments): compare those in the same precision
+        _, p_o, f_o = collide("capsule_box", cpos, Rc, [r, hl, 0], bpos, Rb, bs, dtype="f32")
+        d_k, p_k, n_k = capsule_box(cpos, Rc, [r, hl, 0], bpos, Rb, bs)
+        sent_o, sent_k = d_o == 1, d_k == 1
+        if (sent_o != sent_k).any():
+            # the +1 / real-distance switch is a genuine discontinuity of MJX's collider (support == 0 or
+            # edge penetration == 0): float32 may sit on the other side only within rounding of it
+            real = np.where(sent_o, d_k, d_o)[sent_o != sent_k]
+            assert np.abs(real).max() < 1e-5, (trial, d_o, d_k)
+            n_flip += 1
+            continue
+        n_near += (~sent_o).any()
+        np.testing.assert_allclose(d_k, d_o, atol=2e-6, err_msg=str(trial))
+        for j in range(2):
+            if d_o[j] < -1e-4:
+                n_act += 1
+                n_edge += abs(abs(f_o[j][0] @ Rb[:, 0]) - 1) > 1e-6 and abs(abs(f_o[j][0] @ Rb[:, 1]) - 1) > 1e-6 and abs(abs(f_o[j][0] @ Rb[:, 2]) - 1) > 1e-6
+                dev_p.append(np.abs(p_k[j] - p_o[j]).max())
+                dev_n.append(np.abs(n_k[j] - f_o[j][0]).max())
+    dev_p, dev_n = np.array(dev_p), np.array(dev_n)
+    assert dev_p.max() < 2e-4 and np.percentile(dev_p, 99) < 2e-5, (dev_p.max(), np.percentile(dev_p, 99))
+    assert dev_n.max() < 5e-3 and np.percentile(dev_n, 99) < 2e-4, (dev_n.max(), np.percentile(dev_n, 99))
+    assert n_near > 1500 and n_act > 1000 and n_edge > 100 and n_flip < 10, (n_near, n_act, n_edge, n_flip)

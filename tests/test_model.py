@@ -72,12 +72,19 @@ def test_kmodel_flattening(mc):
     assert abs(sum(masses) - mc.body_mass[3:12].sum()) < 1e-5
     # the pass-major pair table covers every robot slot exactly once
     seen = np.zeros(187, dtype=int)
-    for e in range(128):
-        if km.rp_type[e] == KM.KP_NONE:
+    for e in range(KM.MAXRPAIR):
+        x = km.rp[e]
+        ty, a, b, sl = (x & 15) - 1, (x >> 4) & 15, (x >> 8) & 15, x >> 16
+        if ty == KM.KP_NONE:
             continue
-        n = 1 if km.rp_type[e] == KM.KP_CAP_CAP else 2
-        seen[km.rp_slot[e]:km.rp_slot[e] + n] += 1
+        n = 1 if ty == KM.KP_CAP_CAP else 2
+        seen[sl:sl + n] += 1
+        if ty == KM.KP_CAP_BOX:                       # pass = box, lane = capsule
+            assert e // KM.LANE_GROUP == b and e % KM.LANE_GROUP == a and e // KM.LANE_GROUP < km.ncbpass
+        else:
+            assert e // KM.LANE_GROUP >= km.ncbpass
     assert (seen == 1).all()
+    assert km.ncbpass == 7
     assert C.sizeof(km) % 4 == 0
 
 

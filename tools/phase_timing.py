@@ -15,7 +15,7 @@ sys.path.insert(0, ROOT)
 from manipulator_mujoco_b200 import _lib  # noqa: E402
 
 dbg = os.path.join(ROOT, "manipulator_mujoco_b200", "libcemk_phase.so")
-cmd = ["nvcc"] + [f for f in _lib.NVCC_FLAGS] + ["-DCEMK_PHASE_TIMING", "-o", dbg, _lib.SRC[0]]
+cmd = ["nvcc"] + [f for f in _lib.NVCC_FLAGS] + os.environ.get("EXTRA", "").split() + ["-DCEMK_PHASE_TIMING", "-o", dbg, _lib.SRC[0]]
 subprocess.run(cmd, check=True)
 _lib.LIB_PATH = dbg
 import torch  # noqa: E402
@@ -37,7 +37,7 @@ torch.cuda.synchronize()
 pl._lib.cemk_debug_phase_clocks(buf)
 names = ["step barrier wait (sampled behind BAR.SYNC) + command load", "P1 FK chain", "P2-P5 dynamics", "P6 qacc_smooth", "N1 robot narrow phase + cost", "N1 free-box pairs", "N2 emit contacts",
          "phase barrier wait (sampled behind BAR.SYNC) + C1 limit rows", "S1 warm/smooth", "S3 grad + H", "S4 Cholesky + solve", "S5a line-search setup", "obs + euler", "step barrier issue",
-         "prologue", "epilogue", "C2 contact Jacobians", "C3 row parameters", "(issue of phase barrier)", "S5b line-search trips", "-", "-", "-", "-"]
+         "prologue", "epilogue", "C2 contact Jacobians", "C3 row parameters", "(issue of phase barrier)", "S5b line-search trips", "N1b ballots + near list", "N1c near capsule-box pass", "N1d deferred accounting", "N1e park"]
 v = np.array(list(buf), dtype=np.float64)
 print(f"k_rollout phase shares, B={B} T={T} (clock64 per warp, summed)")
 for n, x in sorted(zip(names, v), key=lambda t: -t[1]):
