@@ -46,7 +46,10 @@ struct LaneRegs {
   int tri;                    // (i, j), 4 bits each, of the 6x6 lower-triangle entries lane and lane + KW (8 bits per entry; 0xff = none)
   float td;                   // next step's commanded joint velocity (lanes < 6), prefetched one step ahead
   float acc[9];               // line-search partial sums (compile-time indices only)
-  float h[KM_NV];             // row `lane` of the Newton Hessian / its Cholesky factor
+  float h[KM_NV];             // row `lane` of the Newton Hessian / its Cholesky factor (compile-time indices only)
+#ifdef CEMK_EMU
+  float hrow[KM_NV];          // emulation build: chol_solve_rows' working copy (a plain local array on the GPU)
+#endif
   float f0, f1, f2;
 };
 
@@ -294,17 +297,22 @@ struct CapBoxOut { float dist[2], pos[2][3], nrm[2][3]; };     // box coordinate
 // axes).  Edge e = 4k + 2iu + iw runs along axis k at (u, w) = (+-s_u, +-s_w).  An edge can only win with a
 // positive penetration, which needs a point of the segment in front of both faces adjacent to the edge and closer
 // than r to it; the interval tests are necessary for that, so edges failing them skip the segment-segment routine
-// without changing the result.  On a hit: slot 0 of *o becomes the edge contact.  n = outward normal of the best face.
-KNOINLINE void capbox_edges(float ax, float ay, float az, float bx, float by, float bz, float r, float sx, float sy, float sz,
-                            float nx, float ny, float nz, CapBoxOut* o) {
+// without changing the result.  On a hit (pen > 0) the caller replaces slot 0 by the edge contact.  n = outward normal of the
+// best face, minface = min(-dist[0], -dist[1]) of the face part.
+struct CapBoxEdge { float pen, pos[3], nrm[3]; };            // pen <= 0: no edge contact
+KNOINLINE CapBoxEdge capbox_edges(float ax, float ay, float az, float bx, float by, float bz, float r, float sx, float sy, float sz,
+                                  float nx, float ny, float nz, float minface) {
   const float bsize[3] = {sx, sy, sz}, n[3] = {nx, ny, nz};
   float bpen = -1.f, beax[3] = {0.f, 0.f, 0.f}, bec[3] = {0.f, 0.f, 0.f}, bcc[3] = {0.f, 0.f, 0.f};
   bool bdeg = false;
   const float lo[3] = {fminf(ax, bx), fminf(ay, by), fminf(az, bz)}, hi[3] = {fmaxf(ax, bx), fmaxf(ay, by), fmaxf(az, bz)};
+  // axis k unrolled (compile-time component indices keep every array in registers), the four edges of an axis rolled
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
 #pragma unroll 1
-  for (int e = 0; e < 12; ++e) {
-    const int k = e >> 2, u = (k + 1) % 3, w = (k + 2) % 3;
-    const float eu = (e & 2) ? 1.f : -1.f, ew = (e & 1) ? 1.f : -1.f;
+  for (int e4 = 0; e4 < 4; ++e4) {
+    const int u = (k + 1) % 3, w = (k + 2) % 3;
+    const float eu = (e4 & 2) ? 1.f : -1.f, ew = (e4 & 1) ? 1.f : -1.f;
     const float cu = eu * bsize[u], cw = ew * bsize[w];
     // furthest the segment reaches in front of the two faces, measured from the edge (must be > 0), and its
     // nearest approach (must be < r)
@@ -323,12 +331,12 @@ KNOINLINE void capbox_edges(float ax, float ay, float az, float bx, float by, fl
     if (epen > bpen) { bpen = epen; bdeg = deg; copy3(beax, dir); copy3(bec, sp.a); copy3(bcc, sp.b); }
   }
   const bool parallel = fabsf(dot3(beax, n)) > 0.99f && !bdeg;
-  const float minface = fminf(-o->dist[0], -o->dist[1]);
   const bool has_edge = bpen > 0.f && (minface > 0.f ? bpen < minface : true) && !parallel;
-  if (has_edge) {
-    o->dist[0] = -bpen;
-    for (int q = 0; q < 3; ++q) { o->pos[0][q] = 0.5f * (bec[q] + bcc[q] + beax[q] * r); o->nrm[0][q] = beax[q]; }
-  }
+  CapBoxEdge out;
+  out.pen = has_edge ? bpen : 0.f;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) { out.pos[q] = 0.5f * (bec[q] + bcc[q] + beax[q] * r); out.nrm[q] = beax[q]; }
+  return out;
 }
 // Near path, in box coordinates; the caller has established has_support (= !capbox_far).  Face part in registers
 // (no dynamic indexing); FULL also produces contact positions / normals.
@@ -388,7 +396,10 @@ KFN void capsule_box_near(const float* a, const float* b, float r, const float* 
     else if (bk == 1) { o.pos[0][1] = l0[0]; o.pos[0][2] = l0[1]; o.pos[0][0] = l0[2]; o.pos[1][1] = l1[0]; o.pos[1][2] = l1[1]; o.pos[1][0] = l1[2]; }
     else              { o.pos[0][2] = l0[0]; o.pos[0][0] = l0[1]; o.pos[0][1] = l0[2]; o.pos[1][2] = l1[0]; o.pos[1][0] = l1[1]; o.pos[1][1] = l1[2]; }
     o.nrm[0][0] = o.nrm[1][0] = -nx; o.nrm[0][1] = o.nrm[1][1] = -ny; o.nrm[0][2] = o.nrm[1][2] = -nz;
-    if (nout >= 2) capbox_edges(a[0], a[1], a[2], b[0], b[1], b[2], r, bsize[0], bsize[1], bsize[2], nx, ny, nz, &o);
+    if (nout >= 2) {
+      const CapBoxEdge e = capbox_edges(a[0], a[1], a[2], b[0], b[1], b[2], r, bsize[0], bsize[1], bsize[2], nx, ny, nz, fminf(-o.dist[0], -o.dist[1]));
+      if (e.pen > 0.f) { o.dist[0] = -e.pen; copy3(o.pos[0], e.pos); copy3(o.nrm[0], e.nrm); }
+    }
   }
 }
 template <bool FULL>
@@ -769,7 +780,7 @@ KFN void jac_col(const KModel& m, const WarpSmemT<NC>& S, const float* p, int li
   } else {
     if (link != KM_NL) return;
     int k = d - KM_NL;
-    if (k < 3) { col[k] = 1.f; return; }
+    if (k < 3) { col[0] = k == 0 ? 1.f : 0.f; col[1] = k == 1 ? 1.f : 0.f; col[2] = k == 2 ? 1.f : 0.f; return; }   // (no dynamic index: keeps col in registers)
     k -= 3;
     float r[3] = {S.bmat[k], S.bmat[3 + k], S.bmat[6 + k]}, off[3];
     sub3(off, p, S.qpos + KM_NL);
@@ -830,34 +841,43 @@ KNOINLINE Vec6 chol_solve6(const float* A, int ld, const float* rhs) {
 // Cholesky solve with one matrix row per lane, all in registers.  N = 12: lanes 0..11 hold the
 // rows of one 12x12 SPD matrix (R.h[k] = A[lane][k], k <= lane).  N = 6: two independent 6x6 systems
 // at once, rows of the first on lanes 0..5 and of the second on lanes 6..11 (R.h[k] = A[lane][base+k]).
-// In: R.h, R.f0 = right-hand side.  Out: R.f0 = A^-1 rhs (R.h = Cholesky factor, lower).
+// In: R.h, R.f0 = right-hand side.  Out: R.f0 = A^-1 rhs.
 template <int N>
 KFN void chol_solve_rows(Warp& W) {
   static_assert(N == 6 || N == 12, "N");
   auto base = [](int l) { return (N == 6 && l >= 6 && l < 12) ? 6 : 0; };
   auto loc = [&](int l) { return l - base(l); };
+  // The column loops below are too long for nvcc to unroll completely, so the row is indexed dynamically: work on
+  // a copy (R.hrow) that only this rare path touches -- a dynamic index into LaneRegs::h itself would force the
+  // whole per-lane state of the kernel out of registers into local memory.
+#ifdef CEMK_EMU
+#define CEMK_ROW(R) (R).hrow
+#else
+  float hrow_[N];
+#define CEMK_ROW(R) hrow_
+#endif
+  RLANES(W, R)
 #pragma unroll
+    for (int k = 0; k < N; ++k) CEMK_ROW(R)[k] = R.h[k];
+  END_RLANES
   for (int j = 0; j < N; ++j) {
-    warp_shfl_each<true>(W, [&](int, LaneRegs& R) { return R.h[j]; }, [&](int l) { return base(l) + j; },
-                   [&](int l, LaneRegs& R, float d) { const float dj = sqrtf(d); R.h[j] = (loc(l) == j) ? dj : R.h[j] / dj; });
-#pragma unroll
+    warp_shfl_each<true>(W, [&](int, LaneRegs& R) { return CEMK_ROW(R)[j]; }, [&](int l) { return base(l) + j; },
+                   [&](int l, LaneRegs& R, float d) { const float dj = sqrtf(d); CEMK_ROW(R)[j] = (loc(l) == j) ? dj : CEMK_ROW(R)[j] / dj; });
     for (int k = j + 1; k < N; ++k)
-      warp_shfl_each<true>(W, [&](int, LaneRegs& R) { return R.h[j]; }, [&](int l) { return base(l) + k; },
-                     [&](int l, LaneRegs& R, float lkj) { if (loc(l) >= k) R.h[k] -= R.h[j] * lkj; });
+      warp_shfl_each<true>(W, [&](int, LaneRegs& R) { return CEMK_ROW(R)[j]; }, [&](int l) { return base(l) + k; },
+                     [&](int l, LaneRegs& R, float lkj) { if (loc(l) >= k) CEMK_ROW(R)[k] -= CEMK_ROW(R)[j] * lkj; });
   }
-#pragma unroll
   for (int k = 0; k < N; ++k)                  // forward substitution L y = rhs
-    warp_shfl_each<true>(W, [&](int, LaneRegs& R) { return R.f0 / R.h[k]; }, [&](int l) { return base(l) + k; },
-                   [&](int l, LaneRegs& R, float yk) { if (loc(l) == k) R.f0 = yk; else if (loc(l) > k) R.f0 -= R.h[k] * yk; });
-#pragma unroll
+    warp_shfl_each<true>(W, [&](int, LaneRegs& R) { return R.f0 / CEMK_ROW(R)[k]; }, [&](int l) { return base(l) + k; },
+                   [&](int l, LaneRegs& R, float yk) { if (loc(l) == k) R.f0 = yk; else if (loc(l) > k) R.f0 -= CEMK_ROW(R)[k] * yk; });
   for (int k = N - 1; k >= 0; --k) {           // back substitution L^T x = y, column k of L^T lives in lane base+k
-    warp_shfl_each<true>(W, [&](int, LaneRegs& R) { return R.f0 / R.h[k]; }, [&](int l) { return base(l) + k; },
+    warp_shfl_each<true>(W, [&](int, LaneRegs& R) { return R.f0 / CEMK_ROW(R)[k]; }, [&](int l) { return base(l) + k; },
                    [&](int l, LaneRegs& R, float xk) { R.f1 = xk; if (loc(l) == k) R.f0 = xk; });
-#pragma unroll
     for (int i = 0; i < k; ++i)
-      warp_shfl_each<true>(W, [&](int, LaneRegs& R) { return R.h[i] * R.f1; }, [&](int l) { return base(l) + k; },
+      warp_shfl_each<true>(W, [&](int, LaneRegs& R) { return CEMK_ROW(R)[i] * R.f1; }, [&](int l) { return base(l) + k; },
                      [&](int l, LaneRegs& R, float p) { if (loc(l) == i) R.f0 -= p; });
   }
+#undef CEMK_ROW
 }
 
 // sum over the contacts in `sel` (bit c = contact c; contacts >= 32 exist only for samples deep in collision

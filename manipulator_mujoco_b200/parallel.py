@@ -9,6 +9,9 @@ blocks arrive in rank order, the row number orders equal costs exactly like the 
 does -- i.e. like the reference's stable ``jnp.argsort`` over the whole batch (mjx_planner.py:307).
 Every rank therefore holds the identical elite list and computes the identical mean / covariance;
 no broadcast is needed.
+
+Exchange record (what ``cemk_topk_pack`` writes and ``cemk_merge_packed`` reads): ``[k'][nvar + 2]`` float32 =
+xi[nvar], cost, global sample index (exact in float32 below 2^24, checked once at construction).
 """
 from __future__ import annotations
 
@@ -31,19 +34,6 @@ def check_index_range(num_batch: int):
         raise ValueError("global sample index does not fit a float32 mantissa (num_batch > 2^24)")
 
 
-def pack_elites(xi_e: torch.Tensor, cost_e: torch.Tensor, gidx: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
-    """[k', nvar] , [k'], [k'] int -> [k', nvar + 2] float32.  Global indices must be < 2^24 to be exact in
-    float32; the planner checks its batch size once at construction (`check_index_range`) -- reading the
-    index tensor here would put a device synchronisation into every CEM iteration."""
-    if out is None:
-        return torch.cat([xi_e, cost_e[:, None], gidx.to(torch.float32)[:, None]], dim=1).contiguous()
-    nvar = xi_e.shape[1]
-    out[:, :nvar].copy_(xi_e)
-    out[:, nvar].copy_(cost_e)
-    out[:, nvar + 1].copy_(gidx)            # int32 -> float32
-    return out
-
-
 def gather_elites(pack: torch.Tensor, world: int, group=None, out: torch.Tensor | None = None) -> torch.Tensor:
     import torch.distributed as dist
     if out is None:
@@ -52,13 +42,11 @@ def gather_elites(pack: torch.Tensor, world: int, group=None, out: torch.Tensor 
     return out
 
 
-def split_gathered(gathered: torch.Tensor, out=None):
-    nvar = gathered.shape[1] - 2
-    if out is not None:
-        g_cost, g_idx, g_xi = out
-        g_cost.copy_(gathered[:, nvar])
-        g_idx.copy_(gathered[:, nvar + 1])      # float32 -> int32 (exact below 2^24)
-        g_xi.copy_(gathered[:, :nvar])
-        return g_cost, g_idx, g_xi
-    return (gathered[:, nvar].contiguous(), gathered[:, nvar + 1].to(torch.int32).contiguous(),
-            gathered[:, :nvar].contiguous())
+def exchange_owned_row(row: torch.Tensor, own: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum-all-reduce in which exactly one rank (``own`` true) contributes ``row`` and every other rank contributes
+    exact zeros.  ``torch.where`` rather than a 0/1 multiplication: a non-owning rank's ``row`` is an arbitrary local
+    sample and may hold NaN / Inf (diverged rollout), and NaN * 0 = NaN would poison the sum on every rank."""
+    import torch.distributed as dist
+    out = torch.where(own.reshape(-1)[0], row, torch.zeros_like(row))
+    dist.all_reduce(out, group=group)
+    return out

@@ -26,6 +26,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import warnings
 
 import numpy as np
 import torch
@@ -189,7 +190,8 @@ class cem_planner:
         self._split_cache = {}
         parallel.check_index_range(self.num_batch)
         self._ws = {}
-        self._graph, self._graph_out, self._eager_ticks = None, None, 0
+        self._graph, self._graph_out, self._graph_key, self._eager_ticks = None, None, None, 0
+        self.overflow_samples, self._warned_overflow = 0, False
         self.use_cuda_graph = os.environ.get("CEMK_CUDA_GRAPH", "1") != "0"
         self.print_info()
 
@@ -504,8 +506,10 @@ class cem_planner:
         theta_all = torch.empty(self.maxiter_cem, Bl, nd * T, device=dev)
         cost_min = torch.empty(self.maxiter_cem, device=dev)
         last = None
+        ovf = torch.zeros((), dtype=torch.int32, device=dev)
         for i in range(self.maxiter_cem):                                                  # :390-392
             carry, out = self.cem_iter(carry, None)
+            ovf = ovf + (self._buf("flags", (Bl,), torch.int32) & 1).sum(dtype=torch.int32)   # contact-capacity overflows
             thetadot_all[i].copy_(out[4])
             theta_all[i].copy_(out[5])
             cost_min[i:i + 1].copy_(self._last_elite[0][0:1])                              # min over the (global) batch
@@ -517,11 +521,13 @@ class cem_planner:
             li = gbest
             best = torch.cat([last[4][li].reshape(-1), last[5][li].reshape(-1), last[1][li], last[2][li], last[3][li]])
         else:
+            # only the owning rank contributes its row; the others send exact zeros (their clamped row may hold
+            # NaN / Inf of a diverged sample, which a 0/1 multiplication would leak into the sum)
             li = (gbest - lo).clamp(0, Bl - 1)
-            own = ((gbest >= lo) & (gbest < lo + Bl)).to(torch.float32)
-            best = torch.cat([last[4][li].reshape(-1), last[5][li].reshape(-1), last[1][li], last[2][li], last[3][li]]) * own
-            self._dist.all_reduce(best, group=self.process_group)
-        out_d = torch.cat([cost_min, best, carry[4]])
+            own = (gbest >= lo) & (gbest < lo + Bl)
+            row = torch.cat([last[4][li].reshape(-1), last[5][li].reshape(-1), last[1][li], last[2][li], last[3][li]])
+            best = parallel.exchange_owned_row(row, own, self.process_group)
+        out_d = torch.cat([cost_min, best, carry[4], ovf.to(torch.float32).reshape(1)])
         pout.copy_(out_d, non_blocking=True)
         return thetadot_all, theta_all
 
@@ -540,23 +546,32 @@ class cem_planner:
             self._ws["pin_in"] = pin
         pin.copy_(torch.from_numpy(host))
         m = self.maxiter_cem
-        nout = m + 2 * nd * T + 3 + self.nvar
-        pout = self._ws.get("pin_out")
-        if pout is None or pout.numel() != nout:
-            pout = torch.empty(nout, dtype=torch.float32).pin_memory()
-            self._ws["pin_out"] = pout
+        nout = m + 2 * nd * T + 3 + self.nvar + 1
         # The device side of a tick is a fixed sequence of launches on fixed buffers: after two eager
         # ticks (allocations, caches) it is captured once into a CUDA graph and replayed, which removes
-        # the per-launch CPU cost that dominates small batches (closed-loop config: 3 x 9 launches).
+        # the per-launch CPU cost that dominates small batches (closed-loop config: 3 x 9 launches).  With
+        # several GPUs the NCCL all-gather / all-reduce are captured with it (every rank captures at the same
+        # tick).  The graph bakes in everything that reaches a kernel as a scalar or a host pointer, so it is
+        # keyed on those and dropped when one of them changes.
+        w = self.cost_weights
+        gkey = (m, int(self.maxiter_projection), float(w['w_pos']), float(w['w_rot']), float(w['w_col']),
+                tuple(int(x) for x in jax_prng.as_key(self.key)), self._partitionable, T, Bl, int(self.ellite_num))
+        if self._graph is not None and gkey != self._graph_key:
+            torch.cuda.current_stream(dev).synchronize()
+            self._graph, self._graph_out, self._eager_ticks = None, None, 0
+        pout = self._ws.get("pin_out")
+        if pout is None or pout.numel() != nout:          # (no graph is alive here: nout is a function of the key)
+            pout = torch.empty(nout, dtype=torch.float32).pin_memory()
+            self._ws["pin_out"] = pout
         if self._graph is not None:
             self._graph.replay()
             thetadot_all, theta_all = self._graph_out
-        elif self.use_cuda_graph and self.world == 1 and self._eager_ticks >= 2:
+        elif self.use_cuda_graph and self._eager_ticks >= 2:
             torch.cuda.current_stream(dev).synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 out = self._cem_device(pin, pout)
-            self._graph, self._graph_out = g, out
+            self._graph, self._graph_out, self._graph_key = g, out, gkey
             g.replay()
             thetadot_all, theta_all = out
         else:
@@ -570,6 +585,13 @@ class cem_planner:
         o = m + 2 * nd * T
         best_cost_g, best_cost_r, best_cost_c = res[o], res[o + 1], res[o + 2]
         xi_mean_out = res[o + 3:o + 3 + nv].copy()
+        # Samples whose simultaneous contacts exceeded the kernel's capacity (KM_NC_TOT = 48) were rolled out with
+        # the extra contacts dropped -- MJX never truncates.  Count of such (sample, iteration) pairs on this rank:
+        self.overflow_samples = int(res[o + 3 + nv])
+        if self.overflow_samples and not self._warned_overflow:
+            self._warned_overflow = True
+            warnings.warn(f"cem_planner: {self.overflow_samples} rollout(s) of this tick exceeded the contact capacity of the "
+                          "rollout kernel (48 simultaneous contacts); their extra contacts were dropped", RuntimeWarning)
         self.h2d_bytes = host.size * 4
         self.d2h_bytes = nout * 4
         if self._graph is not None:          # graph outputs are static buffers: hand out copies

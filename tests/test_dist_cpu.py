@@ -1,6 +1,8 @@
-"""world_size-2 (and 4) gloo test of the sample-sharded elite merge (manipulator_mujoco_b200/parallel.py):
-local top-k' + all-gather + (cost, row) merge == the reference's global stable argsort top-k,
-including cost ties across ranks and NaN costs."""
+"""world_size-2 (and 4) gloo tests of the sample-sharded CEM plumbing (manipulator_mujoco_b200/parallel.py), on the exchange
+record layout the kernels use (cemk_topk_pack -> all-gather -> cemk_merge_packed; tests/pack_ref.py restates the two
+kernels in numpy and tests/test_gpu_kernels.py checks the kernels against that restatement bit for bit):
+local top-k' + all-gather + (cost, row) merge == the reference's global stable argsort top-k, including cost ties across
+ranks and NaN costs; the best-sample exchange survives NaN rows on non-owning ranks."""
 import os
 import socket
 
@@ -11,6 +13,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from manipulator_mujoco_b200 import parallel
+from pack_ref import merge_packed_ref, stable_order, topk_pack_ref
 
 NVAR = 66
 
@@ -30,33 +33,28 @@ def _make(B, seed):
     return cost, xi
 
 
-def _order(cost):
-    key = np.where(np.isnan(cost), np.inf, cost)
-    return np.lexsort((np.arange(len(cost)), np.isnan(cost), key))
-
-
 def _worker(rank, world, port, B, k, seed, ret):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     cost, xi = _make(B, seed)
     lo, hi = parallel.shard_bounds(B, world, rank)
     kl = parallel.local_topk_size(k, hi - lo)
-    loc = _order(cost[lo:hi])[:kl]                                    # what cemk_argsort_topk does per GPU
-    pack = parallel.pack_elites(torch.from_numpy(xi[lo:hi][loc]), torch.from_numpy(cost[lo:hi][loc]),
-                                torch.from_numpy((loc + lo).astype(np.int32)))
-    g_cost, g_idx, g_xi = parallel.split_gathered(parallel.gather_elites(pack, world))
-    # the planner's allocation-free variants (persistent buffers) must give the same tensors
-    nv = xi.shape[1]
-    pack2 = parallel.pack_elites(torch.from_numpy(xi[lo:hi][loc]), torch.from_numpy(cost[lo:hi][loc]),
-                                 torch.from_numpy((loc + lo).astype(np.int32)), out=torch.empty(kl, nv + 2))
-    bits = lambda t: t.contiguous().view(torch.int32)                 # NaN-safe bitwise comparison
-    assert torch.equal(bits(pack), bits(pack2))
-    gath2 = parallel.gather_elites(pack2, world, out=torch.empty(world * kl, nv + 2))
-    c2, i2, x2 = parallel.split_gathered(gath2, out=(torch.empty(world * kl), torch.empty(world * kl, dtype=torch.int32),
-                                                     torch.empty(world * kl, nv)))
-    assert torch.equal(bits(c2), bits(g_cost)) and torch.equal(i2, g_idx) and torch.equal(bits(x2), bits(g_xi))
-    sel = _order(g_cost.numpy())[:k]                                  # what cemk_merge_elites does (cost, row)
-    ret[rank] = (g_idx.numpy()[sel].copy(), g_xi.numpy()[sel].copy(), g_cost.numpy()[sel].copy())
+    cost4 = np.zeros((hi - lo, 4), np.float32)
+    cost4[:, 0] = cost[lo:hi]                                                        # the rollout kernel's [B][4] cost record
+    pack = torch.from_numpy(topk_pack_ref(cost4[:, 0], lo, kl, xi[lo:hi]))           # cemk_topk_pack
+    gathered = parallel.gather_elites(pack, world, out=torch.empty(world * kl, NVAR + 2))     # the planner's call (persistent buffer)
+    assert torch.equal(gathered[rank * kl:(rank + 1) * kl].view(torch.int32), pack.view(torch.int32))
+    xi_e, cost_e, gidx_e = merge_packed_ref(gathered.numpy(), k)                     # cemk_merge_packed
+    # best-sample exchange (planner._cem_device): the owner of the global best contributes its row, every other
+    # rank's candidate row is an arbitrary local sample -- here NaN / Inf on purpose
+    gbest = int(gidx_e[0])
+    own = torch.tensor([lo <= gbest < hi])
+    row = torch.full((9,), float("nan"))
+    row[3] = float("inf")
+    if bool(own):
+        row = torch.from_numpy(np.concatenate([xi[gbest, :8], cost[gbest:gbest + 1]]))
+    best = parallel.exchange_owned_row(row, own)
+    ret[rank] = (gidx_e.copy(), xi_e.copy(), cost_e.copy(), best.numpy().copy())
     dist.destroy_process_group()
 
 
@@ -67,12 +65,14 @@ def test_sharded_merge_equals_global_stable_topk(world, B, k):
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, B, k, 7, ret), nprocs=world, join=True)
     cost, xi = _make(B, 7)
-    ref = _order(cost)[:k]
+    ref = stable_order(cost)[:k]
     for r in range(world):
-        gidx, gxi, gcost = ret[r]
+        gidx, gxi, gcost, best = ret[r]
         np.testing.assert_array_equal(gidx, ref)                      # bit-identical elite index lists on every rank
         np.testing.assert_array_equal(gxi, xi[ref])
         np.testing.assert_array_equal(gcost, cost[ref])
+        # NaN rows of the non-owning ranks did not leak into the exchanged best sample
+        np.testing.assert_array_equal(best, np.concatenate([xi[ref[0], :8], cost[ref[0]:ref[0] + 1]]))
 
 
 def test_index_range_check():

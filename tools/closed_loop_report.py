@@ -41,8 +41,8 @@ def main(max_ticks=1200, out=None):
         rep["final_state_near"] = {names[i]: float(c0[i]) for i in np.where((c0 >= 0) & (c0 < 0.03))[0]}
         # where does the best plan's cost_c at the final state come from?  (slot, step, term)
         L = res['last']
-        out = cem.compute_cem(L['xi_mean'], L['qpos'][:6], L['qvel'][:6], L['qacc'][:6], L['target_pos'], L['target_rot'])
-        td = torch.as_tensor(out[4].T.reshape(1, -1).copy(), dtype=torch.float32, device=cem.device)
+        plan = cem.compute_cem(L['xi_mean'], L['qpos'][:6], L['qvel'][:6], L['qacc'][:6], L['target_pos'], L['target_rot'])
+        td = torch.as_tensor(plan[4].T.reshape(1, -1).copy(), dtype=torch.float32, device=cem.device)
         _, _, _, col = cem.compute_rollout_batch(td, L['qpos'][:6], L['qvel'][:6])
         cc = col[0].cpu().numpy()
         terms = []
@@ -52,7 +52,7 @@ def main(max_ticks=1200, out=None):
                     terms.append((t, names[i], "count", float(cc[t, i])))
                 if t > 0 and 0.995 * cc[t - 1, i] - cc[t, i] > 0.05:
                     terms.append((t, names[i], "approach", float(cc[t - 1, i]), float(cc[t, i])))
-        rep["final_best_plan_cost_c"] = float(out[3])
+        rep["final_best_plan_cost_c"] = float(plan[3])
         rep["final_best_plan_terms"] = terms[:40]
     c_ts = np.array(res['cost_c'])
     rep["cost_c_first_100_ticks_p50_max"] = [float(np.median(c_ts[:100])), float(c_ts[:100].max())]
