@@ -27,7 +27,9 @@
 #include <omp.h>
 #endif
 
-#ifdef ORACLE_FLOAT
+#ifdef ORACLE_COUNT
+#include "count_real.h"      /* C++ build: `real` tallies its arithmetic per stage (profiles/r2_flop_count.json) */
+#elif defined(ORACLE_FLOAT)
 typedef float real;
 #define RSQRT sqrtf
 #define RFABS fabsf
@@ -41,6 +43,10 @@ typedef double real;
 #define RSIN sin
 #define RCOS cos
 #define RPOW pow
+#endif
+
+#ifndef ORACLE_COUNT
+#define OSTAGE(k)
 #endif
 
 #define MAXB 24      /* bodies */
@@ -462,7 +468,7 @@ static real closest_segment_point(real *res, const real *a, const real *b, const
   real ab[3], ap[3], t, d[3];
   sub3(ab, b, a); sub3(ap, pt, a);
   t = dot3(ap, ab) / (dot3(ab, ab) + (real)1e-6);
-  t = t < 0 ? 0 : (t > 1 ? 1 : t);
+  t = t < 0 ? (real)0 : (t > 1 ? (real)1 : t);
   addscl3(res, a, ab, t);
   sub3(d, pt, res);
   return dot3(d, d);
@@ -521,8 +527,8 @@ static void seg_point_plane(real *res, const real *a, const real *b, const real 
   real ab[3];
   sub3(ab, b, a);
   real dd = dot3(p0, n), denom = dot3(n, ab);
-  real t = (dd - dot3(n, a)) / (denom + (denom == 0 ? (real)1e-6 : 0));
-  t = t < 0 ? 0 : (t > 1 ? 1 : t);
+  real t = (dd - dot3(n, a)) / (denom + (denom == 0 ? (real)1e-6 : (real)0));
+  t = t < 0 ? (real)0 : (t > 1 ? (real)1 : t);
   addscl3(res, a, ab, t);
 }
 /* MJX collision_convex._clip_edge_to_planes; returns mask */
@@ -619,7 +625,7 @@ static void capsule_box(const real *cpos, const real *cmat, const real *csize, c
     addscl3(fp, c, n, -dot3(tt, n));
     for (int q = 0; q < 3; q++) lp[k][q] = (c[q] + fp[q]) * (real)0.5;
     sub3(tt, fp, c);
-    pen[k] = (mask && has_support) ? dot3(tt, n) : -1;
+    pen[k] = (mask && has_support) ? dot3(tt, n) : (real)-1;
     scl3(nrm[k], n, -1);
   }
   if (mode == 0) {
@@ -655,7 +661,7 @@ static void capsule_box(const real *cpos, const real *cmat, const real *csize, c
       int degenerate = dot3(dir, dir) < (real)1e-6;
       real ed = normalize3(dir);
       int front = (su * dir[u] < 0) && (sw * dir[w] < 0);
-      real epen = (!degenerate && front) ? r - ed : -1;
+      real epen = (!degenerate && front) ? r - ed : (real)-1;
       if (be < 0 || epen > bpen) { bpen = epen; be = e; copy3(beax, dir); copy3(bec, ec); copy3(bcc, cc); }
     }
     int degenerate = 0;
@@ -681,7 +687,7 @@ static void capsule_box(const real *cpos, const real *cmat, const real *csize, c
 /* MJX collision_convex._manifold_points: 4 points of (approximately) maximal area */
 static void manifold_points(int n, real poly[][3], const int *mask, const real *nrm, int idx[4]) {
   real dm[16];
-  for (int i = 0; i < n; i++) dm[i] = mask[i] ? 0 : (real)-1e6;
+  for (int i = 0; i < n; i++) dm[i] = mask[i] ? (real)0 : (real)-1e6;
   int a = 0;
   for (int i = 1; i < n; i++) if (dm[i] > dm[a]) a = i;
   int b = 0; real bv = 0;
@@ -701,7 +707,7 @@ static void manifold_points(int n, real poly[][3], const int *mask, const real *
     real bp[3], ap[3];
     sub3(bp, poly[b], poly[i]); sub3(ap, poly[a], poly[i]);
     real v1 = RFABS(dot3(bp, bc)), v2 = RFABS(dot3(ap, ac));
-    real v = (v1 > v2 ? v1 : v2) + dm[i] - ((i == a || i == b || i == c) ? (real)2e6 : 0);
+    real v = (v1 > v2 ? v1 : v2) + dm[i] - ((i == a || i == b || i == c) ? (real)2e6 : (real)0);
     if (i == 0 || v > dv) { dv = v; dsel = i; }
   }
   idx[0]=a; idx[1]=b; idx[2]=c; idx[3]=dsel;
@@ -727,7 +733,7 @@ static void plane_box(const real *ppos, const real *pmat, const real *bpos, cons
     for (int q = 0; q < k; q++) if (idx[q] == idx[k]) uniq = 0;
     real w[3];
     mat_vec(w, bmat, v[idx[k]]); add3(w, w, bpos);
-    dist[k] = uniq ? -sup[idx[k]] : 1;
+    dist[k] = uniq ? -sup[idx[k]] : (real)1;
     addscl3(pos[k], w, nw, -(real)0.5 * dist[k]);
     memcpy(frame[k], fr, sizeof fr);
   }
@@ -772,7 +778,7 @@ static void box_box(const real *p1, const real *m1, const real *s1, const real *
     real dc = dot3(c, ax);
     real sep = RFABS(dc) - r1 - r2;
     /* prefer face axes over edge axes on near ties (standard bias) */
-    real cmp = sep - (type == 2 ? (real)1e-6 : 0);
+    real cmp = sep - (type == 2 ? (real)1e-6 : (real)0);
     if (cmp > bestsep) {
       bestsep = cmp; besttype = type; bi = i; bj = j;
       real sg = dc > 0 ? -1 : 1;           /* from box1 (at c) towards box2 (at origin) */
@@ -1004,7 +1010,7 @@ static lspoint ls_point(const odata *d, const sctx *c, real alpha, const real *j
   p.alpha = alpha;
   p.cost = alpha * alpha * q2 + alpha * q1 + q0;
   p.d0 = 2 * alpha * q2 + q1;
-  p.d1 = 2 * q2 + (q2 == 0 ? (real)MJ_MINVAL : 0);
+  p.d1 = 2 * q2 + (q2 == 0 ? (real)MJ_MINVAL : (real)0);
   return p;
 }
 static int in_bracket(lspoint x, lspoint y) {
@@ -1097,18 +1103,25 @@ static void solve(const omodel *m, odata *d) {
 
 /* ------------------------------------------------------------------ B.1 forward, B.8 euler */
 static void forward(const omodel *m, odata *d) {
+  OSTAGE(0);                   /* stages of the op counter (count_real.h); no-ops in the normal builds */
   kinematics(m, d);
+  OSTAGE(1);
   com_pos(m, d);
   crb(m, d);
   chol(m->nv, d->M, d->L);
+  OSTAGE(3);
   collision(m, d);
+  OSTAGE(2);
   com_vel(m, d);
   passive(m, d);
   rne(m, d);
   for (int i = 0; i < m->nv; i++) d->qfrc_smooth[i] = d->qfrc_passive[i] - d->qfrc_bias[i];
   chol_solve(m->nv, d->L, d->qacc_smooth, d->qfrc_smooth);
+  OSTAGE(4);
   make_constraint(m, d);       /* row values do not depend on the velocity stage order */
+  OSTAGE(5);
   solve(m, d);
+  OSTAGE(7);
 }
 static void euler(const omodel *m, odata *d) {
   real dt = (real)m->timestep;
@@ -1135,7 +1148,7 @@ int oracle_forward(const omodel *m, const double *qpos, const double *qvel, cons
                    double *xpos, double *xquat, double *site_tcp, double *con_pos, double *con_frame, int *nefc) {
   odata *d = calloc(1, sizeof(odata));
   for (int i = 0; i < m->nq; i++) d->qpos[i] = (real)qpos[i];
-  for (int i = 0; i < m->nv; i++) { d->qvel[i] = (real)qvel[i]; d->qacc_warmstart[i] = warm ? (real)warm[i] : 0; }
+  for (int i = 0; i < m->nv; i++) { d->qvel[i] = (real)qvel[i]; d->qacc_warmstart[i] = warm ? (real)warm[i] : (real)0; }
   forward(m, d);
   if (qacc) for (int i = 0; i < m->nv; i++) qacc[i] = d->qacc[i];
   if (M_out) for (int i = 0; i < m->nv; i++) for (int j = 0; j < m->nv; j++) M_out[i * m->nv + j] = d->M[i][j];
@@ -1183,7 +1196,9 @@ int oracle_rollout(const omodel *m, int B, int T, int ndof, const double *thetad
         for (int k = 0; k < 4; k++) eef_rot[((size_t)s * T + t) * 4 + k] = d->xquat[m->hande_body][k];
         if (collision) { int o = 0; for (int c = 0; c < m->ncon; c++) if (m->slot_robot[c]) collision[((size_t)s * T + t) * nrobot + o++] = d->con_dist[c]; }
         if (qacc_out) for (int i = 0; i < m->nv; i++) qacc_out[((size_t)s * T + t) * m->nv + i] = d->qacc[i];
+        OSTAGE(6);
         euler(m, d);
+        OSTAGE(7);
         for (int i = 0; i < ndof; i++) theta[(size_t)s * ndof * T + i * T + t] = d->qpos[i];
         if (qpos_out) for (int i = 0; i < m->nq; i++) qpos_out[((size_t)s * T + t) * m->nq + i] = d->qpos[i];
       }

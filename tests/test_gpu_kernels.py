@@ -142,6 +142,7 @@ def test_packed_topk_and_merge_equal_global_stable_topk(planner):
     must give the global stable top-k, ties and NaNs included."""
     import ctypes as C
     from manipulator_mujoco_b200 import _lib
+    from pack_ref import merge_packed_ref, topk_pack_ref
     lib, h = planner._lib, planner._h
     rng = np.random.default_rng(4)
     n, k, nv = 3000, 150, 66
@@ -158,6 +159,8 @@ def test_packed_topk_and_merge_equal_global_stable_topk(planner):
         pack = torch.empty(k, nv + 2, device="cuda")
         _lib.check(lib.cemk_topk_pack(h, hi - lo, p(c), 1, lo, p(keys), k, p(x), p(pack), None), lib)
         packs.append(pack)
+        # the numpy restatement the gloo tests run on (tests/pack_ref.py) is the kernel's record, bit for bit
+        np.testing.assert_array_equal(pack.cpu().numpy().view(np.int32), topk_pack_ref(cost[lo:hi], lo, k, xi[lo:hi]).view(np.int32))
     gathered = torch.cat(packs).contiguous()
     keys = torch.empty(512, dtype=torch.int64, device="cuda")
     xe = torch.empty(k, nv, device="cuda"); ce = torch.empty(k, device="cuda"); ge = torch.empty(k, dtype=torch.int32, device="cuda")
@@ -168,3 +171,7 @@ def test_packed_topk_and_merge_equal_global_stable_topk(planner):
     np.testing.assert_array_equal(ge.cpu().numpy(), ref)
     np.testing.assert_array_equal(xe.cpu().numpy(), xi[ref])
     np.testing.assert_array_equal(ce.cpu().numpy().view(np.int32), cost[ref].view(np.int32))
+    rx, rc, rg = merge_packed_ref(gathered.cpu().numpy(), k)
+    np.testing.assert_array_equal(ge.cpu().numpy(), rg)
+    np.testing.assert_array_equal(xe.cpu().numpy(), rx)
+    np.testing.assert_array_equal(ce.cpu().numpy().view(np.int32), rc.view(np.int32))

@@ -66,3 +66,27 @@ def test_mean_cov_and_elites_reference_properties():
     mean, cov = pr.compute_mean_cov(ce, np.zeros(66), 10 * np.eye(66), xe)
     np.testing.assert_allclose(cov, cov.T, atol=1e-12)
     assert np.linalg.eigvalsh(cov).min() > 0
+
+
+def test_vectorised_cost_and_float32_variant_match_the_literal_restatement():
+    """bench.py's CPU arm times compute_cost_batch_vec and the float32 copy of the constants; both must be the same
+    arithmetic as the line-by-line float64 restatement."""
+    rng = np.random.default_rng(3)
+    B, T, ns = 12, 16, 187
+    pr = PlannerRef(6, B, T, 0.05, 0.25, 20, 3, 80, 10)
+    ep, er = rng.normal(size=(B, T, 3)), rng.normal(size=(B, T, 4))
+    col = rng.uniform(-0.05, 1.0, size=(B, T, ns))
+    col[rng.uniform(size=col.shape) < 0.5] = 1.0                     # sentinel slots
+    tp, tr = np.array([-0.3, -0.3, 0.5]), np.array([0.0, 1.0, 0.0, 0.0])
+    a = pr.compute_cost_batch(ep, er, col, tp, tr)
+    b = pr.compute_cost_batch_vec(ep, er, col, tp, tr)
+    for x, y in zip(a, b):
+        np.testing.assert_allclose(x, y, rtol=1e-12, atol=1e-12)
+    pr32 = pr.astype(np.float32)
+    assert pr32.Q_inv.dtype == np.float32 and pr.Q_inv.dtype == np.float64
+    xi = rng.normal(size=(B, 66)) * 3
+    st = pr.state_term(Q0, np.zeros(6), np.zeros(6), B)
+    x64 = pr.compute_projection_filter(xi, st)
+    x32 = pr32.compute_projection_filter(xi.astype(np.float32), st.astype(np.float32))
+    assert x32.dtype == np.float32
+    np.testing.assert_allclose(x32, x64, atol=5e-5)

@@ -27,25 +27,31 @@ def main():
     q0, tp, tr = np.array([1.5, -1.8, 1.75, -1.25, -1.6, 0]), np.array([-0.3, -0.3, 0.5]), np.array([0.0, 1, 0, 0])
     with contextlib.redirect_stdout(io.StringIO()):
         pl = cem_planner(**kw, process_group=dist.group.WORLD)
-    out = pl.compute_cem(np.zeros(66), q0, np.zeros(6), np.zeros(6), tp, tr)
-    elite = pl._last_elite[1].cpu().numpy()
+        ref = cem_planner(**kw) if rank == 0 else None
     ok = True
-    if rank == 0:
-        with contextlib.redirect_stdout(io.StringIO()):
-            ref = cem_planner(**kw)
-        o1 = ref.compute_cem(np.zeros(66), q0, np.zeros(6), np.zeros(6), tp, tr)
-        e1 = ref._last_elite[1].cpu().numpy()
-        names = ["cost", "best_cost_g", "best_cost_r", "best_cost_c", "best_vels", "best_traj", "xi_mean"]
-        for n, a, b in zip(names, out[:7], o1[:7]):
-            same = np.array_equal(np.asarray(a), np.asarray(b))
+    names = ["cost", "best_cost_g", "best_cost_r", "best_cost_c", "best_vels", "best_traj", "xi_mean"]
+    xi_mean = np.zeros(66)
+    # four ticks: two eager, the third is captured into a CUDA graph (NCCL collectives included), the fourth replays it
+    for tick in range(4):
+        out = pl.compute_cem(xi_mean, q0, np.zeros(6), np.zeros(6), tp, tr)
+        elite = pl._last_elite[1].cpu().numpy()
+        if rank == 0:
+            o1 = ref.compute_cem(xi_mean, q0, np.zeros(6), np.zeros(6), tp, tr)
+            e1 = ref._last_elite[1].cpu().numpy()
+            for n, a, b in zip(names, out[:7], o1[:7]):
+                same = np.array_equal(np.asarray(a), np.asarray(b))
+                ok &= same
+                print(f"tick {tick} {n:12s} identical: {same}")
+            same = np.array_equal(elite, e1)
             ok &= same
-            print(f"{n:12s} identical: {same}")
-        same = np.array_equal(elite, e1)
-        ok &= same
-        print(f"elite index list identical ({len(e1)} of {B}): {same}")
-        lo = 0
-        ok &= bool(torch.equal(out[8][:, :B // world], o1[8][:, lo:lo + B // world]))
-        print("rank-0 theta shard identical:", bool(torch.equal(out[8][:, :B // world], o1[8][:, :B // world])))
+            print(f"tick {tick} elite index list identical ({len(e1)} of {B}): {same}")
+            same = bool(torch.equal(out[8][:, :B // world], o1[8][:, :B // world]))
+            ok &= same
+            print(f"tick {tick} rank-0 theta shard identical: {same}")
+        xi_mean = out[6]
+    if rank == 0:
+        print("graph captured:", pl._graph is not None, "| overflow samples:", pl.overflow_samples)
+        ok &= pl._graph is not None
     flag = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
