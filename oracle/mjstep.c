@@ -29,6 +29,8 @@
 
 #ifdef ORACLE_COUNT
 #include "count_real.h"      /* C++ build: `real` tallies its arithmetic per stage (profiles/r2_flop_count.json) */
+thread_local long long g_cnt[ORACLE_NSTAGE];
+thread_local int g_stage = 7;
 #elif defined(ORACLE_FLOAT)
 typedef float real;
 #define RSQRT sqrtf
@@ -47,6 +49,13 @@ typedef double real;
 
 #ifndef ORACLE_COUNT
 #define OSTAGE(k)
+#define OINACTIVE_BEGIN(active)
+#define OINACTIVE_END()
+#else
+/* Work MJX does for a contact slot that turns out inactive (position, frame) feeds nothing: the op counter books it
+ * under stage 7 ("dense, unobservable") instead of the collider stage. */
+#define OINACTIVE_BEGIN(active) int ostage_keep_ = g_stage; if (!(active)) g_stage = 7
+#define OINACTIVE_END() g_stage = ostage_keep_
 #endif
 
 #define MAXB 24      /* bodies */
@@ -448,19 +457,23 @@ static void make_frame(real *frame, const real *nin) {
 static void plane_capsule(const real *ppos, const real *pmat, const real *cpos, const real *cmat, const real *csize,
                           real *dist, real pos[][3], real frame[][9]) {
   real n[3] = {pmat[2], pmat[5], pmat[8]}, axis[3] = {cmat[2], cmat[5], cmat[8]};
-  real b[3], fr[9];
+  real b[3], fr[9], e[2][3];
+  for (int k = 0; k < 2; k++) {
+    real t[3], sgn = k == 0 ? 1 : -1;
+    addscl3(e[k], cpos, axis, sgn * csize[1]);
+    sub3(t, e[k], ppos);
+    dist[k] = dot3(t, n) - csize[0];
+  }
+  OINACTIVE_BEGIN(dist[0] < 0 || dist[1] < 0);
   addscl3(b, axis, n, -dot3(n, axis));
   real bn = normalize3(b);
   if (bn < (real)0.5) { b[0]=0; if (n[1] > (real)-0.5 && n[1] < (real)0.5) { b[1]=1; b[2]=0; } else { b[1]=0; b[2]=1; } }
   copy3(fr, n); copy3(fr + 3, b); cross3(fr + 6, n, b);
   for (int k = 0; k < 2; k++) {
-    real e[3], t[3], sgn = k == 0 ? 1 : -1;
-    addscl3(e, cpos, axis, sgn * csize[1]);
-    sub3(t, e, ppos);
-    dist[k] = dot3(t, n) - csize[0];
-    addscl3(pos[k], e, n, -(csize[0] + (real)0.5 * dist[k]));
+    addscl3(pos[k], e[k], n, -(csize[0] + (real)0.5 * dist[k]));
     memcpy(frame[k], fr, sizeof fr);
   }
+  OINACTIVE_END();
 }
 
 /* MJX math.closest_segment_point_and_dist */
@@ -505,8 +518,10 @@ static void capsule_capsule(const real *p1, const real *m1, const real *s1, cons
   real dn = normalize3(n);
   if (dn == 0) { n[0]=1; n[1]=0; n[2]=0; }
   dist[0] = dn - (s1[0] + s2[0]);
+  OINACTIVE_BEGIN(dist[0] < 0);
   addscl3(pos[0], pa, n, s1[0] + dist[0] * (real)0.5);
   make_frame(frame[0], n);
+  OINACTIVE_END();
 }
 
 /* box faces in the box frame: index f = 2*axis + (0: +, 1: -).  Vertices counter-clockwise seen
@@ -865,12 +880,45 @@ static void box_box(const real *p1, const real *m1, const real *s1, const real *
   }
 }
 
+#ifdef ORACLE_COUNT
+/* Exact shortcuts taken only by the op-counting build, so that it tallies the work the results depend on rather than
+ * MJX's dense evaluation (tests/test_flop_count.py: outputs identical to the dense build, bit for bit):
+ *  - capsule vs box: if some box axis separates the segment's bounding interval from the box by >= r, has_support
+ *    fails and no edge can be within r, so both slots are the +1 sentinel (rollout_core.h capbox_far);
+ *  - box vs box: disjoint world AABBs cannot have an active slot (these slots never enter the planner's cost). */
+static int count_capbox_far(const real *cpos, const real *cmat, const real *csize, const real *bpos, const real *bmat, const real *bsize) {
+  real t[3], cp[3], ax[3], axw[3] = {cmat[2], cmat[5], cmat[8]};
+  sub3(t, cpos, bpos); matT_vec(cp, bmat, t);
+  matT_vec(ax, bmat, axw);
+  for (int k = 0; k < 3; k++) {
+    real h = RFABS(ax[k] * csize[1]);
+    real lo = cp[k] - h, hi = cp[k] + h;
+    real sep = (lo > -hi ? lo : -hi) - bsize[k];
+    if (!(sep < csize[0])) return 1;
+  }
+  return 0;
+}
+static int count_aabb_disjoint(const real *p1, const real *m1, const real *s1, const real *p2, const real *m2, const real *s2) {
+  for (int i = 0; i < 3; i++) {
+    real e1 = RFABS(m1[3*i]) * s1[0] + RFABS(m1[3*i+1]) * s1[1] + RFABS(m1[3*i+2]) * s1[2];
+    real e2 = RFABS(m2[3*i]) * s2[0] + RFABS(m2[3*i+1]) * s2[1] + RFABS(m2[3*i+2]) * s2[2];
+    if (RFABS(p1[i] - p2[i]) > e1 + e2) return 1;
+  }
+  return 0;
+}
+#endif
 static void collision(const omodel *m, odata *d) {
   for (int p = 0; p < m->npair; p++) {
     int g1 = m->pair_g1[p], g2 = m->pair_g2[p], a = m->pair_slotadr[p];
     int t1 = m->geom_type[g1], t2 = m->geom_type[g2];
     real s1[3], s2[3];
     for (int k = 0; k < 3; k++) { s1[k] = (real)m->geom_size[g1][k]; s2[k] = (real)m->geom_size[g2][k]; }
+#ifdef ORACLE_COUNT
+    if ((t1 == G_CAPSULE && t2 == G_BOX && count_capbox_far(d->gpos[g1], d->gmat[g1], s1, d->gpos[g2], d->gmat[g2], s2)) ||
+        (t1 == G_BOX && t2 == G_BOX && count_aabb_disjoint(d->gpos[g1], d->gmat[g1], s1, d->gpos[g2], d->gmat[g2], s2))) {
+      for (int k = 0; k < m->pair_nslot[p]; k++) d->con_dist[a+k] = 1;
+    } else
+#endif
     if (t1 == G_PLANE && t2 == G_CAPSULE) plane_capsule(d->gpos[g1], d->gmat[g1], d->gpos[g2], d->gmat[g2], s2, d->con_dist + a, d->con_pos + a, d->con_frame + a);
     else if (t1 == G_PLANE && t2 == G_BOX) plane_box(d->gpos[g1], d->gmat[g1], d->gpos[g2], d->gmat[g2], s2, d->con_dist + a, d->con_pos + a, d->con_frame + a);
     else if (t1 == G_CAPSULE && t2 == G_CAPSULE) capsule_capsule(d->gpos[g1], d->gmat[g1], s1, d->gpos[g2], d->gmat[g2], s2, d->con_dist + a, d->con_pos + a, d->con_frame + a);
@@ -994,10 +1042,17 @@ static void update_gradient(const omodel *m, odata *d, sctx *c) {
     real fc = 0;
     for (int r = 0; r < d->nefc; r++) if (c->active[r]) fc += d->efc_J[r][i] * (-d->efc_D[r] * c->Jaref[r]);
     c->grad[i] = c->Ma[i] - d->qfrc_smooth[i] - fc;
+#ifdef ORACLE_COUNT
+    for (int j = 0; j <= i; j++) {               /* H is symmetric: the op count books one triangle */
+#else
     for (int j = 0; j < nv; j++) {
+#endif
       real s = d->M[i][j];
       for (int r = 0; r < d->nefc; r++) if (c->active[r]) s += d->efc_J[r][i] * d->efc_D[r] * d->efc_J[r][j];
       H[i][j] = s;
+#ifdef ORACLE_COUNT
+      H[j][i] = s;
+#endif
     }
   }
   chol(nv, H, HL);
@@ -1140,6 +1195,24 @@ static void euler(const omodel *m, odata *d) {
 }
 
 /* ================================================================== exported entry points */
+#ifdef __cplusplus
+extern "C" {
+#endif
+#ifdef ORACLE_COUNT
+static long long g_total[ORACLE_NSTAGE];
+static void count_flush(void) {
+  #pragma omp critical
+  for (int k = 0; k < ORACLE_NSTAGE; k++) { g_total[k] += g_cnt[k]; g_cnt[k] = 0; }
+}
+/* stage totals since the last call: 0 kinematics, 1 com_pos + CRBA + factor, 2 velocity / passive / RNE / qacc_smooth,
+ * 3 narrow phase, 4 constraint rows, 5 Newton + line search, 6 Euler, 7 not counted (I/O conversion, dense unobservable work) */
+int oracle_count_read(long long *out) {
+  for (int k = 0; k < ORACLE_NSTAGE; k++) { out[k] = g_total[k]; g_total[k] = 0; }
+  return ORACLE_NSTAGE;
+}
+#else
+static void count_flush(void) {}
+#endif
 
 /* One `mjx.forward` at (qpos, qvel) with the given warm start; returns qacc and a few intermediates
  * for unit tests (any output pointer may be NULL). */
@@ -1162,6 +1235,7 @@ int oracle_forward(const omodel *m, const double *qpos, const double *qvel, cons
   if (site_tcp) for (int k = 0; k < 3; k++) site_tcp[k] = d->site_tcp[k];
   if (nefc) *nefc = d->nefc;
   free(d);
+  count_flush();
   return 0;
 }
 
@@ -1204,6 +1278,7 @@ int oracle_rollout(const omodel *m, int B, int T, int ndof, const double *thetad
       }
     }
     free(d);
+    count_flush();
   }
   return 0;
 }
@@ -1234,3 +1309,6 @@ int oracle_collide(int type, const double *p1, const double *m1, const double *s
   }
   return n;
 }
+#ifdef __cplusplus
+}
+#endif

@@ -47,8 +47,9 @@ def build(force=False):
     """Compile oracle/mjstep.c (gcc) into oracle/_build/; a no-op when the .so files are fresh."""
     out = os.path.join(_HERE, "_build")
     src = os.path.join(_HERE, "mjstep.c")
-    libs = [os.path.join(out, n) for n in ("liboracle_f64.so", "liboracle_f32.so")]
-    fresh = all(os.path.exists(p) and os.path.getmtime(p) >= os.path.getmtime(src) for p in libs)
+    libs = [os.path.join(out, n) for n in ("liboracle_f64.so", "liboracle_f32.so", "liboracle_count.so")]
+    hdr = os.path.join(_HERE, "count_real.h")
+    fresh = all(os.path.exists(p) and os.path.getmtime(p) >= max(os.path.getmtime(src), os.path.getmtime(hdr)) for p in libs)
     if force or not fresh:
         subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
     return libs
@@ -77,7 +78,8 @@ class Oracle:
 
     def __init__(self, mc, timestep, dtype="f64", tcp_site="tcp", hande_body="hande", capbox_mode=1):
         libs = build()
-        self.lib = C.CDLL(libs[0] if dtype == "f64" else libs[1])
+        # "count": the op-counting build (float64 arithmetic + exact shortcuts, see count_real.h / tools/count_flops.py)
+        self.lib = C.CDLL(libs[{"f64": 0, "f32": 1, "count": 2}[dtype]])
         assert self.lib.oracle_sizeof_model() == C.sizeof(OModel), "struct layout mismatch"
         self.mc = mc
         m = OModel()
@@ -155,6 +157,15 @@ class Oracle:
                                 C.byref(nefc))
         out["nefc"] = nefc.value
         return out
+
+    STAGES = ("kinematics", "com_pos + CRBA + factor", "velocity + passive + RNE + qacc_smooth", "narrow phase",
+              "constraint rows", "Newton + line search", "Euler", "not counted (I/O, dense unobservable work)")
+
+    def read_counts(self):
+        """Op counts per stage since the last call (dtype="count" build only)."""
+        out = (C.c_longlong * 8)()
+        self.lib.oracle_count_read(out)
+        return dict(zip(self.STAGES, [int(v) for v in out]))
 
     def initial_warmstart(self):
         """qacc of the constructor's ``mjx.forward`` at qpos0 (mjx_planner.py:107) = first warm start."""
