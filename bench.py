@@ -363,9 +363,20 @@ def main():
     F_A, F_A_source = flop_per_env_step()
     achieved = steps_per_s_kernel * F_A / 1e12
 
-    if rank != 0:
+    def shutdown():
+        """Drop the captured graphs (they hold NCCL kernels) before the communicator goes; never let teardown hang the run."""
+        sys.stdout.flush()
         if world > 1:
+            threading.Timer(30.0, lambda: os._exit(0)).start()
+            main_res["pl"].close()
+            if c5 is not None:
+                c5["pl"].close()
+            torch.cuda.synchronize(dev)
             dist.destroy_process_group()
+            os._exit(0)
+
+    if rank != 0:
+        shutdown()
         return
     traffic = None
     try:
@@ -407,8 +418,7 @@ def main():
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_record()
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown()
 
 
 if __name__ == "__main__":

@@ -54,6 +54,8 @@ struct cemk_handle {
 // ---------------------------------------------------------------------------------------------- rollout
 #ifdef CEMK_PHASE_TIMING
 __device__ unsigned long long g_phase[24];
+__device__ unsigned long long g_event[16];
+__device__ unsigned long long g_phase_cond[25];
 #endif
 struct RolloutBatch {
   int B, T;
@@ -109,7 +111,9 @@ __global__ void __launch_bounds__(WARPS * 32, ROLLOUT_MINB) k_rollout(const KMod
   }
 #ifdef CEMK_PHASE_TIMING
   W.phase = 14; W.t0 = clock64();
-  for (int i = 0; i < 24; ++i) W.ph[i] = 0;
+  for (int i = 0; i < 24; ++i) { W.ph[i] = 0; W.phs[i] = 0; W.phc[i] = 0; }
+  W.stepflag = 0; W.nflag = 0;
+  for (int i = 0; i < 16; ++i) W.ev[i] = 0;
 #endif
   RolloutArgs A;
   const size_t row = (size_t)s * KM_NL * a.T;
@@ -131,6 +135,8 @@ __global__ void __launch_bounds__(WARPS * 32, ROLLOUT_MINB) k_rollout(const KMod
 #ifdef CEMK_PHASE_TIMING
   PHASE(W, 15);
   if (W.lane == 0 && !ONLY_FLAGGED) for (int i = 0; i < 24; ++i) atomicAdd(&g_phase[i], (unsigned long long)W.ph[i]);
+  if (W.lane == 0 && !ONLY_FLAGGED) for (int i = 0; i < 16; ++i) atomicAdd(&g_event[i], (unsigned long long)W.ev[i]);
+  if (W.lane == 0 && !ONLY_FLAGGED) { for (int i = 0; i < 24; ++i) atomicAdd(&g_phase_cond[i], (unsigned long long)W.phc[i]); atomicAdd(&g_phase_cond[24], (unsigned long long)W.nflag); }
 #endif
 }
 template <int NC, int WARPS>
@@ -831,6 +837,18 @@ int cemk_debug_phase_clocks(unsigned long long* out24) {
   unsigned long long z[24] = {0};
   if (cudaMemcpyFromSymbol(out24, g_phase, sizeof z) != cudaSuccess) return CEMK_ERR_CUDA;
   if (cudaMemcpyToSymbol(g_phase, z, sizeof z) != cudaSuccess) return CEMK_ERR_CUDA;
+  return CEMK_OK;
+}
+int cemk_debug_phase_cond(unsigned long long* out25) {
+  unsigned long long z[25] = {0};
+  if (cudaMemcpyFromSymbol(out25, g_phase_cond, sizeof z) != cudaSuccess) return CEMK_ERR_CUDA;
+  if (cudaMemcpyToSymbol(g_phase_cond, z, sizeof z) != cudaSuccess) return CEMK_ERR_CUDA;
+  return CEMK_OK;
+}
+int cemk_debug_events(unsigned long long* out16) {
+  unsigned long long z[16] = {0};
+  if (cudaMemcpyFromSymbol(out16, g_event, sizeof z) != cudaSuccess) return CEMK_ERR_CUDA;
+  if (cudaMemcpyToSymbol(g_event, z, sizeof z) != cudaSuccess) return CEMK_ERR_CUDA;
   return CEMK_OK;
 }
 #endif

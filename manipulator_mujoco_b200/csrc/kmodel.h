@@ -53,7 +53,7 @@ struct KModel {
   float cap_pos[KM_MAXCAP][4], cap_axis[KM_MAXCAP][4];
   float cap_r[KM_MAXCAP], cap_hl[KM_MAXCAP], cap_invw[KM_MAXCAP];
   float plane_pos[4], plane_n[4];
-  float sb_pos[KM_MAXSBOX][4], sb_mat[KM_MAXSBOX][12], sb_size[KM_MAXSBOX][4];
+  float sb_pos[KM_MAXSBOX][4], sb_mat[KM_MAXSBOX][12], sb_size[KM_MAXSBOX][4];   // sb_size[.][3] = 1: axis-aligned box, sb_mat[.][9..11] = its half sizes along the world axes
   float fb_size[4], fb_inertia[4];      // free box half sizes; principal inertia (body frame)
   float fb_mass, fb_damping, fb_invw, pad4;
   // robot pairs, pass-major: entry p*KW + lane.  Passes 0 .. ncbpass-1 hold the capsule-box pairs with a fixed shape:

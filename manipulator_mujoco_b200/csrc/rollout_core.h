@@ -34,6 +34,10 @@
                                           // spill to a per-sample global (L2) area
 #define KM_OVF_STRIDE 80                  // floats per spilled contact: geo 16, J 36, dots 2x3, rows 4x4
 #define KM_NC_BIG 48                      // shared-memory capacity of the debug instantiation (everything in shared memory)
+#ifndef CEMK_ROW_UNROLL
+#define CEMK_ROW_UNROLL 1            // unroll factor of the per-row / per-item loops of the constraint solve
+#endif
+constexpr int kRowUnroll = CEMK_ROW_UNROLL;
 #define MJ_MINVAL 1e-15f
 #define MJ_MINIMP 0.0001f
 #define MJ_MAXIMP 0.9999f
@@ -74,7 +78,7 @@ struct WarpSmemT {
   union {
     struct { float cinert[KM_NL][12], crb[KM_NL][12], cvel[KM_NL][8], cdofdot[KM_NL][8], cfrc[KM_NL][8]; };
     struct { float rD[NROW], rAref[NROW], rJaref[NROW], rJv[NROW]; };   // rJv doubles as the smooth-start J.a - aref in S1
-    struct { float nres[KM_MAXNEAR][2]; unsigned char nlist[KM_MAXNEAR]; };   // N1 only: the near capsule-box pairs of this step and their distances
+    struct { unsigned short nlist[KM_MAXNEAR]; };   // N1 only: the near capsule-box pairs of this step (pair table entry | was-far bit << 15)
   };
   float cgeo[NC][16];                 // pos3 n3 t1 3 t2 3 dist invw link1 link2
   union {
@@ -111,6 +115,40 @@ struct WarpSmemT {
 };
 
 typedef WarpCtx<LaneRegs> Warp;
+
+// the entries (i, j), j <= i, of a 6x6 lower triangle a lane owns: e = lane (and lane + 16 when KW = 16); 8 bits per entry
+KFN int tri_entries(int lane) {
+  int tri = 0;
+  for (int q = 0; q < 32 / KW; ++q) {
+    int e = lane + KW * q, i = 0, j = e;
+    if (e < KM_NL * (KM_NL + 1) / 2) { while (j > i) { j -= i + 1; ++i; } } else { i = 15; j = 15; }
+    tri |= (i | (j << 4)) << (8 * q);
+  }
+  return tri;
+}
+// A lane-group context of its own for an out-of-line (cold) routine.  Rare paths are real functions so that they do not
+// sit inside the step loop, whose address span decides how well the instruction fetch of the lockstep warps works; a
+// routine taking the caller's Warp by reference would force that struct (the per-lane state of the whole kernel) out of
+// registers, so cold routines rebuild the few fields they need and exchange everything else through the sample's record.
+KFN void cold_warp(Warp& W, int bar, int nthr) {
+#ifdef CEMK_EMU
+  std::memset((void*)&W, 0, sizeof(Warp));
+  W.race = g_emu_race;
+  for (int l = 0; l < KW; ++l) W.regs[l].tri = tri_entries(l);
+  (void)bar; (void)nthr;
+#else
+  W.lane = threadIdx.x & (KW - 1);
+  W.shift = (threadIdx.x & 31) & ~(KW - 1);
+  W.mask = KW_FULL << W.shift;
+  W.bar = bar; W.nthr = nthr;
+  W.regs.tri = tri_entries(W.lane);
+#ifdef CEMK_PHASE_TIMING
+  W.phase = 0; W.t0 = clock64(); W.stepflag = 0; W.nflag = 0;
+  for (int i = 0; i < 24; ++i) { W.ph[i] = 0; W.phs[i] = 0; W.phc[i] = 0; }
+  for (int i = 0; i < 16; ++i) W.ev[i] = 0;
+#endif
+#endif
+}
 
 // ------------------------------------------------------------------------------------------ vec3
 KFN float dot3(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
@@ -744,7 +782,7 @@ KFN void box_box_warp(Warp& W, WarpSmemT<NC>& S, bool act, int slot, const float
 // ------------------------------------------------------------------------------------------ constraints
 KFN float pow_pos(float x, float p) { return p == 2.f ? x * x : (p == 1.f ? x : powf(x, p)); }
 // MJX constraint._kbi + row regulariser (BD.8)
-KFN void row_params(const KModel& m, float pos, float invw, float vel, float& D, float& aref) {
+KNOINLINE void row_params(const KModel& m, float pos, float invw, float vel, float& D, float& aref) {
   float tc = fmaxf(m.solref[0], 2.f * m.dt), dr = m.solref[1];
   float dmin = fminf(fmaxf(m.solimp[0], MJ_MINIMP), MJ_MAXIMP), dmax = fminf(fmaxf(m.solimp[1], MJ_MINIMP), MJ_MAXIMP);
   float width = fmaxf(m.solimp[2], MJ_MINVAL), mid = fminf(fmaxf(m.solimp[3], MJ_MINIMP), MJ_MAXIMP), power = fmaxf(m.solimp[4], 1.f);
@@ -793,16 +831,29 @@ KFN void jac_col(const KModel& m, const WarpSmemT<NC>& S, const float* p, int li
 // than the arithmetic (measured: profiles/README.md).  A: lower triangle read with row stride `ld`.
 // The 4 pyramid rows of a contact are Jn +- mu*Jt1, Jn +- mu*Jt2: three dot products per contact (one
 // (contact, component) item per lane) give all four J_r . v.
+// which dof blocks a contact touches: bit 0 = robot (a link 0..5 on either side), bit 1 = free box.  Its Jacobian is
+// identically zero in a block it does not touch; those entries are neither written (C2) nor read.
+KFN int contact_blocks(const float* g) {
+  const int l1 = (int)g[14], l2 = (int)g[15];
+  return (((unsigned)l1 < (unsigned)KM_NL || (unsigned)l2 < (unsigned)KM_NL) ? 1 : 0) | ((l1 == KM_NL || l2 == KM_NL) ? 2 : 0);
+}
 template <int NC, bool SP>
 KFN void contact_dots(Warp& W, WarpSmemT<NC>& S, int ncon, const float* v0, const float* v1) {
   LANES(W, R)
-#pragma unroll 1
+#pragma unroll(kRowUnroll)
     for (int e = lane; e < 3 * ncon; e += KW) {
       const int c = e / 3, k = e - 3 * c;
+      const int blk = contact_blocks(S.template geo<SP>(c));
       const float* J = S.template jac<SP>(c) + 12 * k;
       float s0 = 0.f, s1 = 0.f;
+      if (blk != 3) {                               // one block (the usual case): six terms
+        const int o = (blk & 1) ? 0 : KM_NL;
 #pragma unroll
-      for (int d = 0; d < KM_NV; ++d) { s0 += J[d] * v0[d]; if (v1) s1 += J[d] * v1[d]; }
+        for (int d = 0; d < KM_NL; ++d) { s0 += J[o + d] * v0[o + d]; if (v1) s1 += J[o + d] * v1[o + d]; }
+      } else {
+#pragma unroll
+        for (int d = 0; d < KM_NV; ++d) { s0 += J[d] * v0[d]; if (v1) s1 += J[d] * v1[d]; }
+      }
       S.template dots<SP>(0, c)[k] = s0;
       if (v1) S.template dots<SP>(1, c)[k] = s1;
     }
@@ -880,10 +931,13 @@ KFN void chol_solve_rows(Warp& W) {
 #undef CEMK_ROW
 }
 
-// sum over the contacts in `sel` (bit c = contact c; contacts >= 32 exist only for samples deep in collision
-// kernel and are all visited) of the Hessian contribution of the four pyramid rows to entry (i, j)
+// (Out of line like every routine with more than one call site: the address span of the step loop decides how well the
+// instruction fetch of the lockstep warps works -- one inlined copy less of the box-box routine was worth 4 %.)
+// sum over the contacts in `sel` (bit c = contact c; contacts >= 32 exist only for samples deep in collision and are
+// tested one by one: `need` = the dof blocks of entry (i, j), 1 robot, 2 box, 3 cross) of the Hessian contribution of
+// the four pyramid rows to entry (i, j)
 template <int NC, bool SP>
-KFN float hess_contacts(const WarpSmemT<NC>& S, unsigned sel, int ncon, int i, int j) {
+KNOINLINE float hess_contacts(const WarpSmemT<NC>& S, unsigned sel, int need, int ncon, int i, int j) {
   float h = 0.f;
   auto term = [&](int c) {
     const float* g = S.template geo<SP>(c); const float* J = S.template jac<SP>(c);
@@ -910,6 +964,7 @@ KFN float hess_contacts(const WarpSmemT<NC>& S, unsigned sel, int ncon, int i, i
 #pragma unroll 1
     for (int c = 32; c < ncon; ++c) {
       const float* g = S.template geo<SP>(c); const float* J = S.template jac<SP>(c);
+      if ((__float_as_int(g[7]) & need) != need) continue;       // the Jacobian only exists in the blocks the contact touches
       const float ni = J[i], nj = J[j], ai = J[12 + i], aj = J[12 + j], bi = J[24 + i], bj = J[24 + j];
       h += g[3] * (ni + ai) * (nj + aj) + g[4] * (ni - ai) * (nj - aj) + g[5] * (ni + bi) * (nj + bj) + g[6] * (ni - bi) * (nj - bj);
     }
@@ -975,6 +1030,23 @@ struct StepIO {
   float* prevd;               // this sample's previous-step distances, [2 * KM_NPASS][KW] (global scratch, L2-resident)
 };
 
+// search = -H^-1 grad for the full 12x12 system (a contact couples a robot link and the free box).  Cold: a real
+// function with its own lane-group context; may be entered by one of the two samples of a warp (D-flavoured fences).
+template <int NC>
+KNOINLINE void coupled_solve(WarpSmemT<NC>& S) {
+  Warp W;
+  cold_warp(W, 0, 0);
+  DLANES(W, R)
+#pragma unroll
+    for (int k = 0; k < KM_NV; ++k) R.h[k] = (lane < KM_NV && k <= lane) ? S.H[lane][k] : 0.f;
+    R.f0 = lane < KM_NV ? S.grad[lane] : 0.f;
+  END_DLANES
+  chol_solve_rows<12>(W);
+  DLANES(W, R)
+    if (lane < KM_NV) S.search[lane] = -R.f0;
+  END_DLANES
+}
+
 // ------------------------------------------------------------------------------------------ constraint solve
 // C2 .. S5 of one forward(): rows of the active constraints, Newton direction, line search.  SP = true is
 // the instantiation for a sample whose contact list does not fit shared memory (spill area, see WarpSmemT).
@@ -983,25 +1055,32 @@ KFN void solve_rows(Warp& W, const KModel& m, WarpSmemT<NC>& S, const int ncon, 
   PHASE(W, 16);
   // ---- C2: contact Jacobians in the contact frame: Jn, mu*Jt1, mu*Jt2 ----
   LANES(W, R)
-    // one (contact, dof) item per lane
-#pragma unroll 1
-    for (int e = lane; e < KM_NV * ncon; e += KW) {
-      const int c = e / KM_NV, d = e - KM_NV * c;
+    // one (contact, dof of a block the contact touches) item per lane: six items per contact, twelve for a contact
+    // between a robot link and the free box
+#pragma unroll(kRowUnroll)
+    for (int e = lane; e < KM_NL * ncon; e += KW) {
+      const int c = e / KM_NL, k = e - KM_NL * c;
       const float* g = S.template geo<SP>(c);
-      float c1[3], c2[3], df[3];
-      jac_col(m, S, g, (int)g[14], d, c1);
-      jac_col(m, S, g, (int)g[15], d, c2);
-      sub3(df, c2, c1);
-      S.template jac<SP>(c)[d] = dot3(g + 3, df);
-      S.template jac<SP>(c)[12 + d] = m.mu * dot3(g + 6, df);
-      S.template jac<SP>(c)[24 + d] = m.mu * dot3(g + 9, df);
+      const int blk = contact_blocks(g);
+      float* J = S.template jac<SP>(c);
+#pragma unroll 1
+      for (int d = (blk & 1) ? k : KM_NL + k; d < KM_NV; d += KM_NL) {       // (the second trip only for blk == 3)
+        float c1[3], c2[3], df[3];
+        jac_col(m, S, g, (int)g[14], d, c1);
+        jac_col(m, S, g, (int)g[15], d, c2);
+        sub3(df, c2, c1);
+        J[d] = dot3(g + 3, df);
+        J[12 + d] = m.mu * dot3(g + 6, df);
+        J[24 + d] = m.mu * dot3(g + 9, df);
+        if (blk != 3) break;
+      }
     }
   END_LANES
   PHASE(W, 17);
   // ---- C3: contact row parameters (the 4 pyramid edges share pos and D) ----
   contact_dots<NC, SP>(W, S, ncon, S.qvel, nullptr);
   LANES(W, R)
-#pragma unroll 1
+#pragma unroll(kRowUnroll)
     for (int r = nlim + lane; r < nrow; r += KW) {
       const float* g = S.template geo<SP>((r - nlim) >> 2);
       float w = g[13];
@@ -1025,7 +1104,7 @@ KFN void solve_rows(Warp& W, const KModel& m, WarpSmemT<NC>& S, const int ncon, 
   contact_dots<NC, SP>(W, S, ncon, S.warm, S.as);
   LANES(W, R)
     float cw = 0.f, cs = 0.f;
-#pragma unroll 1
+#pragma unroll(kRowUnroll)
     for (int r = lane; r < nrow; r += KW) {
       const float ar = S.template Aref<SP>(r, nlim), Dr = S.template D<SP>(r, nlim);
       float jw = row_val<NC, SP>(S, 0, r, S.warm) - ar, js = row_val<NC, SP>(S, 1, r, S.as) - ar;
@@ -1062,7 +1141,7 @@ KFN void solve_rows(Warp& W, const KModel& m, WarpSmemT<NC>& S, const int ncon, 
   // per contact: the pyramid-edge weights w_q = D [Jaref_q < 0] and the force sums that multiply
   // Jn, mu*Jt1, mu*Jt2; the contact position / frame slots of cgeo are dead after C2 and are reused.
   LANES(W, R)
-#pragma unroll 1
+#pragma unroll(kRowUnroll)
     for (int c = lane; c < ncon; c += KW) {
       const int r0 = nlim + 4 * c;
       float w[4], f[4];
@@ -1109,6 +1188,7 @@ KFN void solve_rows(Warp& W, const KModel& m, WarpSmemT<NC>& S, const int ncon, 
 #pragma unroll 1
         for (int c = 32; c < ncon; ++c) {        // more than 32 contacts: deep-collision samples only
           const float* g = S.template geo<SP>(c); const float* J = S.template jac<SP>(c);
+          if (!(__float_as_int(g[7]) & (lane < KM_NL ? 1 : 2))) continue;
           fc += J[lane] * g[0] + J[12 + lane] * g[1] + J[24 + lane] * g[2];
         }
       }
@@ -1125,10 +1205,10 @@ KFN void solve_rows(Warp& W, const KModel& m, WarpSmemT<NC>& S, const int ncon, 
     if (i < KM_NL) {
       float hr = S.Mr[i][j];
       for (int r = 0; r < nlim; ++r) if (S.rJaref[r] < 0.f && S.limdof[r] == i && i == j) hr += S.rD[r];
-      hr += hess_contacts<NC, SP>(S, mrob, ncon, i, j);
+      hr += hess_contacts<NC, SP>(S, mrob, 1, ncon, i, j);
       S.H[i][j] = hr;
       float hb = i != j ? 0.f : (i < 3 ? m.fb_mass : (i == 3 ? m.fb_inertia[0] : (i == 4 ? m.fb_inertia[1] : m.fb_inertia[2])));
-      hb += hess_contacts<NC, SP>(S, mbox, ncon, KM_NL + i, KM_NL + j);
+      hb += hess_contacts<NC, SP>(S, mbox, 2, ncon, KM_NL + i, KM_NL + j);
       S.H[KM_NL + i][KM_NL + j] = hb;
     }
    }
@@ -1136,7 +1216,7 @@ KFN void solve_rows(Warp& W, const KModel& m, WarpSmemT<NC>& S, const int ncon, 
 #pragma unroll 1
       for (int e = lane; e < KM_NL * KM_NL; e += KW) {
         const int i = KM_NL + e / KM_NL, j = e % KM_NL;
-        S.H[i][j] = hess_contacts<NC, SP>(S, mrob & mbox, ncon, i, j);
+        S.H[i][j] = hess_contacts<NC, SP>(S, mrob & mbox, 3, ncon, i, j);
       }
     }
   END_LANES
@@ -1152,17 +1232,8 @@ KFN void solve_rows(Warp& W, const KModel& m, WarpSmemT<NC>& S, const int ncon, 
       for (int i = 0; i < KM_NL; ++i) { S.search[i] = -xr.v[i]; S.search[KM_NL + i] = -xb.v[i]; }
     } END_UNIFORM_WRITE
   }
-  if (coupled) {                                // rare: full 12x12 system (replaces the block solution above)
-    DLANES(W, R)
-#pragma unroll
-      for (int k = 0; k < KM_NV; ++k) R.h[k] = (lane < KM_NV && k <= lane) ? S.H[lane][k] : 0.f;
-      R.f0 = lane < KM_NV ? S.grad[lane] : 0.f;
-    END_DLANES
-    chol_solve_rows<12>(W);
-    DLANES(W, R)
-      if (lane < KM_NV) S.search[lane] = -R.f0;
-    END_DLANES
-  }
+  EVENT(W, 7, coupled);
+  if (coupled) coupled_solve<NC>(S);            // rare: full 12x12 system (replaces the block solution above); out of line
   REGROUP();
   PHASE_ALIGN(16);
   PHASE(W, 11);
@@ -1179,7 +1250,7 @@ KFN void solve_rows(Warp& W, const KModel& m, WarpSmemT<NC>& S, const int ncon, 
     // the lane's first row stays in registers for the line-search trips (R.h is free after the solve):
     // ja, jv and the three quadratic coefficients; an idle lane gets a row that is never active
     R.h[0] = 1.f; R.h[1] = 0.f; R.h[2] = 0.f; R.h[3] = 0.f; R.h[4] = 0.f;
-#pragma unroll 1
+#pragma unroll(kRowUnroll)
     for (int r = lane; r < nrow; r += KW) {
       const float jv = row_val<NC, SP>(S, 0, r, S.search), ja = S.template Jaref<SP>(r, nlim), D = S.template D<SP>(r, nlim);
       S.template Jv<SP>(r, nlim) = jv;
@@ -1214,7 +1285,10 @@ KFN void solve_rows(Warp& W, const KModel& m, WarpSmemT<NC>& S, const int ncon, 
       done = done || !swapped;
       done = done || ((lo.d0 < 0.f) && (lo.d0 > -gtol));
       done = done || ((hi.d0 > 0.f) && (hi.d0 < gtol));
+#ifndef CEMK_X_ALLTRIPS
       if (warp_all_groups(W, done)) break;
+#endif
+      EVENT(W, 6, 1); EVENT(W, 5, !done);
       al0 = lo.alpha - lo.d0 / lo.d1; al1 = hi.alpha - hi.d0 / hi.d1; al2 = 0.5f * (lo.alpha + hi.alpha);
     }
     // rows are read-only here and the sums live in registers: no fences inside the loop
@@ -1226,7 +1300,7 @@ KFN void solve_rows(Warp& W, const KModel& m, WarpSmemT<NC>& S, const int ncon, 
         if (ja + al1 * jv < 0.f) { b0 = q0; b1 = q1; b2 = q2; }
         if (ja + al2 * jv < 0.f) { c0 = q0; c1 = q1; c2 = q2; }
       }
-#pragma unroll 1
+#pragma unroll(kRowUnroll)
       for (int r = lane + KW; r < nrow; r += KW) {             // more than KW rows: the rest from shared memory
         const float ja = S.template Jaref<SP>(r, nlim), jv = S.template Jv<SP>(r, nlim), D = S.template D<SP>(r, nlim);
         const float q0 = 0.5f * D * ja * ja, q1 = D * jv * ja, q2 = 0.5f * D * jv * jv;
@@ -1278,6 +1352,15 @@ KFN void solve_rows(Warp& W, const KModel& m, WarpSmemT<NC>& S, const int ncon, 
       S.qacc[lane] = a; S.warm[lane] = a;
     }
   END_LANES
+}
+
+// the spill-capable instantiation (a sample of the warp has more contacts than fit its shared-memory record): cold, out
+// of line, with its own lane-group context (solve_rows leaves its results in the sample's record, nothing in registers)
+template <int NC>
+KNOINLINE void solve_rows_spilled(const KModel& m, WarpSmemT<NC>& S, int ncon, int nlim, int nrow, int bar, int nthr) {
+  Warp W;
+  cold_warp(W, bar, nthr);
+  solve_rows<NC, true>(W, m, S, ncon, nlim, nrow);
 }
 
 // ------------------------------------------------------------------------------------------ one forward()
@@ -1481,8 +1564,17 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
       for (int p = 0; p < m.ncbpass; ++p) {
         const bool st = p < m.nsbox;
         float la[3], lb[3];
-        capbox_local(A, B, st ? m.sb_pos[p] : S.qpos + KM_NL, st ? m.sb_mat[p] : S.bmat, la, lb);
-        const bool far = capbox_far(la, lb, r, st ? m.sb_size[p] : m.fb_size);
+        bool far;
+        if (st && m.sb_size[p][3] != 0.f) {
+          // axis-aligned static box: its frame is a signed permutation of the world axes, so the box coordinates are
+          // the world offsets up to order and sign and the test is the same arithmetic on (A - c, B - c) with the
+          // permuted half sizes -- bit-identical decision without the change of frame
+          sub3(la, A, m.sb_pos[p]); sub3(lb, B, m.sb_pos[p]);
+          far = capbox_far(la, lb, r, m.sb_mat[p] + 9);
+        } else {
+          capbox_local(A, B, st ? m.sb_pos[p] : S.qpos + KM_NL, st ? m.sb_mat[p] : S.bmat, la, lb);
+          far = capbox_far(la, lb, r, st ? m.sb_size[p] : m.fb_size);
+        }
         const bool valid = KP_TYPE(m.rp[p * KW + lane]) == KP_CAP_BOX;
         if (valid) { if (far) farbits |= 1 << p; else nearbits |= 1 << p; }
       }
@@ -1546,90 +1638,98 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
   PHASE(W, 20);
   int ncbcon = 0;                                  // capsule-box contacts: they open the contact list
   {
-    // list position of a near pair: pass-major, lane-minor
-    unsigned nm[KM_MAXSBOX + 1];
-    int ntot = 0;
-#pragma unroll
-    for (int p = 0; p < KM_MAXSBOX + 1; ++p) {
-      nm[p] = 0u;
-      if (p < m.ncbpass) {
-        nm[p] = warp_ballot(W, [&](int, LaneRegs& R) { return ((R.off >> p) & 1) != 0; });
-        ntot += KPOPC(nm[p]);
-      }
-    }
-    if (warp_any_groups(W, ntot > 0)) {
+    // List position of a near pair: lane-major (capsule), pass-minor (box).
+    int ntot = warp_excl_scan(W, [](int, LaneRegs& R) { return KPOPC(R.off & 0xffff); }, [](int, LaneRegs& R, int o) { R.actmask = o; });
+    EVENT(W, 0, 1); EVENT(W, 1, ntot > 0); EVENT(W, 2, ntot); EVENT(W, 11, warp_any_groups(W, ntot > 0));
+#ifdef CEMK_X_NONEAR
+    ntot = 0;      // timing experiment only (wrong results): what the near pass costs, lockstep wait included
+#endif
+    // CEMK_UNIFORM_NEAR: every warp walks the near pass every step.  Most steps some warp of the CTA has near pairs
+    // (and three in four near pairs penetrate), and the warps of a CTA wait for each other at the next alignment point
+    // anyway; a warp running this code alone runs it at instruction-fetch speed (nothing else shares its cache lines),
+    // several times slower than the same code executed by all warps in lockstep.  So a sample without near pairs sends
+    // lane 0 through the pass with a dummy pair (table entry 0) whose results go to an unused spill record.
+#ifdef CEMK_UNIFORM_NEAR
+    const bool uniform_pass = true;
+#else
+    const bool uniform_pass = false;
+    if (warp_any_groups(W, ntot > 0))
+#endif
+    {
       LANES(W, R)
-        int base = 0;
-#pragma unroll
-        for (int p = 0; p < KM_MAXSBOX + 1; ++p) {
-          if ((R.off >> p) & 1) S.nlist[base + KPOPC(nm[p] & ((1u << lane) - 1u))] = (unsigned char)(p * KW + lane);
-          base += KPOPC(nm[p]);
+        int o = R.actmask;
+#pragma unroll 1
+        for (int rem = R.off & 0xffff; rem; rem &= rem - 1, ++o) {
+          const int p = KFFS(rem) - 1;
+          S.nlist[o] = (unsigned short)((p * KW + lane) | (((R.off >> (16 + p)) & 1) << 15));     // bit 15: the pair was far one step ago
         }
       END_LANES
       PHASE(W, 21);
 #pragma unroll 1
-      for (int i0 = 0; warp_any_groups(W, i0 < ntot); i0 += KW) {
-        // one near pair per lane: both distances, and the full record of every penetrating slot (parked in R.h)
+      for (int i0 = 0; warp_any_groups(W, i0 < ntot) || (uniform_pass && i0 == 0); i0 += KW) {
+        // one near pair per lane: both distances, their share of the collision cost, the previous-distance record and
+        // the contact geometry of the penetrating slots (parked in R.h)
         LANES(W, R)
           const int i = i0 + lane;
+          const bool dummy = uniform_pass && i0 == 0 && lane == 0 && ntot == 0;
           R.nact = 0;
-          if (i < ntot) {
-            const int x = m.rp[S.nlist[i]], a = KP_A(x), b = KP_B(x);
-            const bool st = b < m.nsbox;
-            Contact2 c;
-            capsule_box<true>(S.capA[a], S.capB[a], m.cap_r[a], st ? m.sb_pos[b] : S.qpos + KM_NL, st ? m.sb_mat[b] : S.bmat,
-                              st ? m.sb_size[b] : m.fb_size, c);
-            S.nres[i][0] = c.dist[0]; S.nres[i][1] = c.dist[1];
-            R.nact = (c.dist[0] < 0.f ? 1 : 0) + (c.dist[1] < 0.f ? 2 : 0);
+          if (i < ntot || dummy) {
+            const int e = dummy ? 0 : S.nlist[i] & 0x7fff, x = m.rp[e], a = KP_A(x), b = KP_B(x);
+            const bool wasfar = dummy || (S.nlist[i] >> 15) != 0, st = b < m.nsbox;
+            const float* bpos = st ? m.sb_pos[b] : S.qpos + KM_NL;
+            const float* bmat = st ? m.sb_mat[b] : S.bmat;
+            // (the list holds exactly the pairs that failed the far test: straight to the near path)
+            float la[3], lb[3];
+            CapBoxOut c;
+            capbox_local(S.capA[a], S.capB[a], bpos, bmat, la, lb);
+            capsule_box_near<true>(la, lb, m.cap_r[a], st ? m.sb_size[b] : m.fb_size, c);
+            const float d0 = c.dist[0], d1 = c.dist[1];
+            float cc = (d0 < 0.f ? 1.f : 0.f) + (d1 < 0.f ? 1.f : 0.f);
+            float* pd = io.prevd + (2 * (e / KW)) * KW + (e & (KW - 1));       // the owner's slots: pass e / KW, capsule lane e % KW
+            if (!io.first) {
+              const float prev0 = wasfar ? 1.f : pd[0], prev1 = wasfar ? 1.f : pd[KW];
+              cc += fmaxf((1.f - 0.005f) * prev0 - d0, 0.f) + fmaxf((1.f - 0.005f) * prev1 - d1, 0.f);
+            }
+            if (!dummy) {
+              pd[0] = d0; pd[KW] = d1;
+              if (io.collision_row) { io.collision_row[KP_SLOT(x)] = d0; io.collision_row[KP_SLOT(x) + 1] = d1; }
+              R.cost_c += cc;                      // (cost_c is summed over the lanes at the end of the rollout: any lane may book a pair)
+            }
+            R.nact = dummy ? 4 : (d0 < 0.f ? 1 : 0) + (d1 < 0.f ? 2 : 0);       // bit 2: dummy record
+#ifdef CEMK_X_NEARNOCON
+            R.nact = 0;   // timing experiment only (wrong results): near pass without the contacts it finds
+#endif
             if (R.nact) {
+              // world position and normal of both slots: box frame -> world
 #pragma unroll
-              for (int k = 0; k < 3; ++k) { R.h[k] = c.pos[0][k]; R.h[3 + k] = c.nrm[0][k]; R.h[6 + k] = c.pos[1][k]; R.h[9 + k] = c.nrm[1][k]; }
-              R.f0 = c.dist[0]; R.f1 = c.dist[1];
+              for (int j = 0; j < 2; ++j) {
+                float w[3], nw[3];
+                mat_vec(w, bmat, c.pos[j]); add3(w, w, bpos);
+                mat_vec(nw, bmat, c.nrm[j]);
+                normalize3(nw);
+                R.h[6 * j] = w[0]; R.h[6 * j + 1] = w[1]; R.h[6 * j + 2] = w[2];
+                R.h[6 * j + 3] = nw[0]; R.h[6 * j + 4] = nw[1]; R.h[6 * j + 5] = nw[2];
+              }
+              R.f0 = d0; R.f1 = d1;
+              R.f2 = m.cap_invw[a] + (st ? 0.f : m.fb_invw);
+              R.tri = (R.tri & 0xffff) | (m.cap_link[a] << 16) | ((st ? 15 : KM_NL) << 20);     // links of the pair, parked above the triangle entries
             }
           }
         END_LANES
-        const int nnew = warp_excl_scan(W, [](int, LaneRegs& R) { return (R.nact & 1) + (R.nact >> 1); }, [](int, LaneRegs& R, int o) { R.actmask = o; });
-        if (warp_any_groups(W, nnew > 0)) {
+        const int nnew = warp_excl_scan(W, [](int, LaneRegs& R) { return (R.nact & 1) + ((R.nact >> 1) & 1); }, [](int, LaneRegs& R, int o) { R.actmask = o; });
+        if (uniform_pass || warp_any_groups(W, nnew > 0)) {
           LANES(W, R)
             if (R.nact) {
-              const int x = m.rp[S.nlist[i0 + lane]], a = KP_A(x), b = KP_B(x);
-              const bool st = b < m.nsbox;
-              const float invw = m.cap_invw[a] + (st ? 0.f : m.fb_invw);
-              int o = ncbcon + R.actmask;
-              if (R.nact & 1) { put_contact<NC>(S, o, R.h, R.h + 3, nullptr, R.f0, invw, m.cap_link[a], st ? -1 : KM_NL); ++o; }
-              if (R.nact & 2) put_contact<NC>(S, o, R.h + 6, R.h + 9, nullptr, R.f1, invw, m.cap_link[a], st ? -1 : KM_NL);
+              const int l1 = (R.tri >> 16) & 15, l2raw = (R.tri >> 20) & 15, l2 = l2raw == 15 ? -1 : l2raw;
+              int o = (R.nact & 4) ? KM_NC_TOT - 1 : ncbcon + R.actmask;         // dummy: the last spill record (only a 48th contact would use it)
+              if (R.nact & 5) { put_contact<NC>(S, o, R.h, R.h + 3, nullptr, R.f0, R.f2, l1, l2); ++o; }
+              if (R.nact & 2) put_contact<NC>(S, o, R.h + 6, R.h + 9, nullptr, R.f1, R.f2, l1, l2);
             }
           END_LANES
         }
         ncbcon += nnew;
       }
       PHASE(W, 22);
-      // the owners of the near pairs account for them: cost, previous distances
-      LANES(W, R)
-        if (R.off) {
-          int base = 0;
-          float cc = 0.f;
-          float* pd = io.prevd + lane;
-#pragma unroll
-          for (int p = 0; p < KM_MAXSBOX + 1; ++p) {
-            if ((R.off >> p) & 1) {
-              const int i = base + KPOPC(nm[p] & ((1u << lane) - 1u));
-              const float d0 = S.nres[i][0], d1 = S.nres[i][1];
-              if (d0 < 0.f) cc += 1.f;
-              if (d1 < 0.f) cc += 1.f;
-              if (!io.first) {
-                const bool wasfar = (R.off >> (16 + p)) & 1;
-                const float prev0 = wasfar ? 1.f : pd[(2 * p) * KW], prev1 = wasfar ? 1.f : pd[(2 * p + 1) * KW];
-                cc += fmaxf((1.f - 0.005f) * prev0 - d0, 0.f) + fmaxf((1.f - 0.005f) * prev1 - d1, 0.f);
-              }
-              pd[(2 * p) * KW] = d0; pd[(2 * p + 1) * KW] = d1;
-              if (io.collision_row) { const int sl = KP_SLOT(m.rp[p * KW + lane]); io.collision_row[sl] = d0; io.collision_row[sl + 1] = d1; }
-            }
-            base += KPOPC(nm[p]);
-          }
-          R.cost_c += cc;
-        }
-      END_LANES
     }
   }
   PHASE(W, 23);
@@ -1663,6 +1763,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
     // pair walks through it with its writes switched off, so all fences stay full-warp
 #pragma unroll 1
     for (unsigned rem = warp_or_groups(W, cand); rem != 0u; rem &= rem - 1u) {
+      EVENT(W, 10, 1);
       const int q = KFFS(rem) - 1;
       const bool mine = (cand >> q) & 1u;
       const int ty = m.bp_type[q], a = m.bp_a[q];
@@ -1670,8 +1771,12 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
         LANES(W, R)
           if (mine && lane == q) { plane_box(m.plane_pos, m.plane_n, bp, S.bmat, m.fb_size, S.bstage[q]); copy3(S.bnrm[q], m.plane_n); }
         END_LANES
-      } else if (ty == KB_BOX_BOX) box_box_warp<NC>(W, S, mine, q, m.sb_pos[a], m.sb_mat[a], m.sb_size[a], bp, S.bmat, m.fb_size);
-      else box_box_warp<NC>(W, S, mine, q, bp, S.bmat, m.fb_size, m.sb_pos[a], m.sb_mat[a], m.sb_size[a]);
+      } else {
+        // one call site (the routine is large and inlined): geom1 is the static box, or the free box when it has the lower geom id
+        const bool sw = ty == KB_BOX_BOX_SWAP;
+        box_box_warp<NC>(W, S, mine, q, sw ? bp : m.sb_pos[a], sw ? S.bmat : m.sb_mat[a], sw ? m.fb_size : m.sb_size[a],
+                         sw ? m.sb_pos[a] : bp, sw ? m.sb_mat[a] : S.bmat, sw ? m.sb_size[a] : m.fb_size);
+      }
     }
   }
   LANES(W, R)
@@ -1684,10 +1789,14 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
   const unsigned bmask = m.has_box ? warp_ballot32(W, [&](int l) { return l < 4 * m.nbpair && S.bstage[l >> 2][l & 3][3] < 0.f; }) : 0u;
   const int ncon_all = nrob + KPOPC(bmask);
   const int ncon = ncon_all < KM_NC_TOT ? ncon_all : KM_NC_TOT;
+  EVENT(W, 3, ncon); EVENT(W, 4, nrob > 0); EVENT(W, 12, warp_any_groups(W, nrob > 0));
+  FLAGSTEP(W, warp_any_groups(W, nrob > 0));
   PHASE(W, 6);
   // ---- N2: full contact records for the active slots (divergent, rare for robot slots) ----
   LANES(W, R)
+#ifndef CEMK_X_NOEMIT
     if (R.nact > 0) emit_robot_contacts<NC>(m, S, lane, R.actmask, R.off);
+#endif
     for (int sl = lane; sl < 32; sl += KW) {
       if (!(bmask & (1u << sl))) continue;
       const int o = nrob + KPOPC(bmask & ((1u << sl) - 1u)), q = sl >> 2;
@@ -1733,7 +1842,8 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
   END_LANES
   // contacts beyond the shared-memory capacity: both samples of the warp take the spill-capable instantiation
   // (same arithmetic, other addressing), so fences stay warp-uniform
-  if (NC < KM_NC_TOT && !warp_all_groups(W, ncon <= NC)) solve_rows<NC, true>(W, m, S, ncon, nlim, nrow);
+  EVENT(W, 8, nrow == 0); EVENT(W, 9, !warp_all_groups(W, ncon <= NC)); EVENT(W, 13, nlim > 0);
+  if (NC < KM_NC_TOT && !warp_all_groups(W, ncon <= NC)) solve_rows_spilled<NC>(m, S, ncon, nlim, nrow, WARP_BAR(W), WARP_NTHR(W));
   else solve_rows<NC, false>(W, m, S, ncon, nlim, nrow);
 }
 
@@ -1783,21 +1893,13 @@ KFN void rollout_sample(Warp& W, const KModel& m, WarpSmemT<NC>& S, const Rollou
   LANES(W, R)
     if (lane < KM_NQ) S.qpos[lane] = lane < KM_NL ? A.q0[lane] : m.qpos0[lane];
     if (lane < KM_NV) { S.qvel[lane] = lane < KM_NL ? A.v0[lane] : m.qvel0[lane]; S.warm[lane] = m.warm0[lane]; }
-    {
-      // the entries (i, j), j <= i, of a 6x6 lower triangle this lane owns: e = lane (and lane + 16 when KW = 16)
-      int tri = 0;
-      for (int q = 0; q < 32 / KW; ++q) {
-        int e = lane + KW * q, i = 0, j = e;
-        if (e < KM_NL * (KM_NL + 1) / 2) { while (j > i) { j -= i + 1; ++i; } } else { i = 15; j = 15; }
-        tri |= (i | (j << 4)) << (8 * q);
-      }
-      R.tri = tri;
-    }
+    R.tri = tri_entries(lane);
     if (lane == 0) { S.flags = 0; S.ovf = A.ovf; }
     R.cost_c = 0.f;
     R.farprev = 0;
     R.td = lane < KM_NL ? A.thetadot[lane * A.T] : 0.f;
   END_LANES
+  const float tp[3] = {A.target_pos[0], A.target_pos[1], A.target_pos[2]};       // read once: the step loop only touches registers for the goal terms
   float tq[4] = {A.target_rot[0], A.target_rot[1], A.target_rot[2], A.target_rot[3]};
   {
     float inv = 1.f / sqrtf(tq[0] * tq[0] + tq[1] * tq[1] + tq[2] * tq[2] + tq[3] * tq[3]);
@@ -1827,7 +1929,7 @@ KFN void rollout_sample(Warp& W, const KModel& m, WarpSmemT<NC>& S, const Rollou
       USYNC();
       mat_vec(tv, S.lmat[KM_NL - 1], m.tcp_pos); add3(tcp, S.lpos[KM_NL - 1], tv);
       quat_mul(eq, S.lquat[KM_NL - 1], m.hande_quat);
-      float d[3]; sub3(d, tcp, A.target_pos);
+      float d[3]; sub3(d, tcp, tp);
       cost_g += sqrtf(dot3(d, d));
       float inv = 1.f / sqrtf(eq[0] * eq[0] + eq[1] * eq[1] + eq[2] * eq[2] + eq[3] * eq[3]);
       float dp = fabsf((eq[0] * tq[0] + eq[1] * tq[1] + eq[2] * tq[2] + eq[3] * tq[3]) * inv);
@@ -1845,6 +1947,8 @@ KFN void rollout_sample(Warp& W, const KModel& m, WarpSmemT<NC>& S, const Rollou
     LANES(W, R)
       if (A.live && lane < KM_NL) A.theta[lane * A.T + t] = S.qpos[lane];
     END_LANES
+    PHASE(W, 12);
+    STEPEND(W);
   }
   const float cost_c = warp_sum(W, [](int, LaneRegs& R) { return R.cost_c; });
   LANES(W, R)

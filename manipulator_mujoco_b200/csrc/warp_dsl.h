@@ -43,11 +43,64 @@ static_assert(KW == 16 || KW == 32, "CEMK_KW must be 16 or 32");
 #define KNOINLINE static
 #define STEP_ALIGN()
 #define PHASE_ALIGN(bit)
+#ifdef CEMK_EMU_RACE
+// Race-checking emulation (tests/test_emu_race.py): every lane of a LANES block runs against the scratch as it was when
+// the block started (plus its own writes); the lanes' writes are merged when the block ends.  That is exactly what rule 1
+// below promises the GPU build, so a kernel that obeys the rule computes bit-identical results in this mode and in the
+// plain lane-after-lane emulation, while a block in which a lane consumes another lane's write of the same block (a
+// missing fence) gives that lane the stale value here and the results differ.  Two lanes writing different values to
+// the same scratch byte in one block are counted directly (RaceState::waw).
+struct RaceState {
+  struct Region { unsigned char* p; size_t n; } reg[4];
+  int nreg = 0, open = -1, line = 0;
+  long long waw = 0, blocks = 0;
+  int first_line = 0, first_word = 0, first_lanes = 0;      // where the first write-write conflict was seen (source line of the block)
+  size_t total = 0;
+  unsigned char* snap = nullptr; unsigned char* pend = nullptr; signed char* owner = nullptr;
+  void add(void* p, size_t n) { reg[nreg].p = (unsigned char*)p; reg[nreg].n = n & ~size_t(3); total += reg[nreg].n; ++nreg; }
+  void gather(unsigned char* dst) { size_t o = 0; for (int i = 0; i < nreg; ++i) { std::memcpy(dst + o, reg[i].p, reg[i].n); o += reg[i].n; } }
+  void scatter(const unsigned char* src) { size_t o = 0; for (int i = 0; i < nreg; ++i) { std::memcpy(reg[i].p, src + o, reg[i].n); o += reg[i].n; } }
+  void begin_block() {
+    if (!snap) { snap = new unsigned char[total]; pend = new unsigned char[total]; owner = new signed char[total]; }
+    gather(snap); std::memcpy(pend, snap, total); std::memset(owner, -1, total); open = -1; ++blocks;
+  }
+  void close_lane() {                          // byte granularity: lanes may own different bytes of one word (S.nlist)
+    if (open < 0) return;
+    size_t o = 0;
+    for (int i = 0; i < nreg; ++i) {
+      for (size_t w = 0; w < reg[i].n; ++w, ++o) {
+        const unsigned char v = reg[i].p[w];
+        if (v == snap[o]) continue;            // not written (or rewritten with the old value)
+        if (owner[o] >= 0 && owner[o] != open && v != pend[o]) {
+          if (!waw) { first_line = line; first_word = (int)(o / 4); first_lanes = owner[o] * 100 + open; }
+          ++waw;
+        }
+        owner[o] = (signed char)open;
+        pend[o] = v;
+      }
+    }
+    open = -1;
+  }
+  void begin_lane(int lane) { close_lane(); scatter(snap); open = lane; }
+  void end_block() { close_lane(); scatter(pend); }
+};
+struct RaceBlock {
+  RaceState* rs;
+  RaceBlock(void* p, int line) : rs((RaceState*)p) { if (rs) { rs->line = line; rs->begin_block(); } }
+  void lane(int l) { if (rs) rs->begin_lane(l); }
+  ~RaceBlock() { if (rs) rs->end_block(); }
+};
+#define LANES(W, R) { RaceBlock race_blk_((W).race, __LINE__); for (int lane = 0; lane < KW; ++lane) { race_blk_.lane(lane); auto& R = (W).regs[lane]; (void)R;
+#define END_LANES } }
+#define DLANES(W, R) LANES(W, R)
+#define END_DLANES } }
+#else
 #define LANES(W, R) for (int lane = 0; lane < KW; ++lane) { auto& R = (W).regs[lane]; (void)R;
 #define END_LANES }
 #define DLANES(W, R) LANES(W, R)
 #define END_DLANES }
-#define RLANES(W, R) LANES(W, R)
+#endif
+#define RLANES(W, R) for (int lane = 0; lane < KW; ++lane) { auto& R = (W).regs[lane]; (void)R;
 #define END_RLANES }
 #define UNIFORM_WRITE(W) if (true)
 #define END_UNIFORM_WRITE
@@ -56,6 +109,8 @@ static_assert(KW == 16 || KW == 32, "CEMK_KW must be 16 or 32");
 #define USYNC()
 #define REGROUP()
 #define KRSQRT(x) (1.0f / sqrtf(x))
+#define WARP_BAR(W) 0
+#define WARP_NTHR(W) 0
 #define KPOPC(x) __builtin_popcount(x)
 #define KFFS(x) __builtin_ffs((int)(x))
 static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
@@ -94,6 +149,8 @@ static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); retur
 #define USYNC() __syncwarp()
 #define REGROUP() __syncwarp()
 #define KRSQRT(x) rsqrtf(x)
+#define WARP_BAR(W) ((W).bar)
+#define WARP_NTHR(W) ((W).nthr)
 #define KPOPC(x) __popc(x)
 #define KFFS(x) __ffs((int)(x))
 #endif
@@ -101,10 +158,15 @@ static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); retur
 // member mask of a collective: the group's own lanes in divergent regions, the whole warp otherwise
 #define KMASK(w) (DIV ? (w).mask : 0xffffffffu)
 
+#ifdef CEMK_EMU
+inline thread_local void* g_emu_race = nullptr;      // RaceState of the sample being emulated (race-checking build), for cold_warp()
+#endif
+
 template <class LR>
 struct WarpCtx {
 #ifdef CEMK_EMU
   LR regs[KW];
+  void* race;        // RaceState* of the race-checking emulation (null otherwise)
 #else
   LR regs;
   int lane;          // lane within the group, 0..KW-1
@@ -114,6 +176,8 @@ struct WarpCtx {
   int bar;           // named barrier of the alignment set (1 ..)
 #ifdef CEMK_PHASE_TIMING
   long long t0; int phase; long long ph[24];
+  long long phs[24], phc[24]; int stepflag, nflag;   // this step's clocks; clocks of the steps with stepflag set (conditional profile)
+  int ev[16];        // event counters (tools/phase_timing.py)
 #endif
 #endif
 };
@@ -121,9 +185,16 @@ struct WarpCtx {
 // Debug build only (-DCEMK_PHASE_TIMING): per-phase SM-clock accounting of one group's step, summed
 // into a global table by the kernel wrapper (tools/phase_timing.py).  No-op otherwise.
 #if !defined(CEMK_EMU) && defined(CEMK_PHASE_TIMING)
-#define PHASE(W, id) do { long long now_ = clock64(); (W).ph[(W).phase] += now_ - (W).t0; (W).t0 = now_; (W).phase = (id); } while (0)
+#define PHASE(W, id) do { long long now_ = clock64(); (W).ph[(W).phase] += now_ - (W).t0; (W).phs[(W).phase] += now_ - (W).t0; (W).t0 = now_; (W).phase = (id); } while (0)
+// conditional profile: FLAGSTEP marks the current step, STEPEND books the step's clocks under the flag
+#define FLAGSTEP(W, cond) do { if (cond) (W).stepflag = 1; } while (0)
+#define STEPEND(W) do { for (int i_ = 0; i_ < 24; ++i_) { if ((W).stepflag) (W).phc[i_] += (W).phs[i_]; (W).phs[i_] = 0; } (W).nflag += (W).stepflag; (W).stepflag = 0; } while (0)
+#define EVENT(W, id, n) do { (W).ev[(id)] += (n); } while (0)
 #else
 #define PHASE(W, id) do { } while (0)
+#define EVENT(W, id, n) do { } while (0)
+#define FLAGSTEP(W, cond) do { } while (0)
+#define STEPEND(W) do { } while (0)
 #endif
 
 // sum over the group's lanes of f(lane, regs); result is group-uniform

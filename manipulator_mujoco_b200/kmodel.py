@@ -212,6 +212,12 @@ def build_kmodel(mc: ModelConsts, timestep: float, robot_geom_names=None, tcp_si
                 m.sb_pos[k][:3] = list(gp)
                 m.sb_mat[k][:9] = list(gm.reshape(-1))
                 m.sb_size[k][:3] = list(mc.geom_size[g])
+                # axis-aligned box (frame = signed permutation of the world axes, in float32): its far-field test
+                # runs on world coordinates with the permuted half sizes, no change of frame (rollout_core.h N1)
+                gm32 = gm.astype(np.float32)
+                if np.all((gm32 == 0) | (np.abs(gm32) == 1)):
+                    m.sb_mat[k][9:12] = list(np.abs(gm32.astype(np.float64)) @ np.asarray(mc.geom_size[g], dtype=np.float64))
+                    m.sb_size[k][3] = 1.0
             else:
                 raise NotImplementedError("static geoms must be planes or boxes")
     m.ncap, m.nsbox = len(caps), len(sboxes)

@@ -193,6 +193,8 @@ class cem_planner:
         self._graph, self._graph_out, self._graph_key, self._eager_ticks = None, None, None, 0
         self.overflow_samples, self._warned_overflow = 0, False
         self.use_cuda_graph = os.environ.get("CEMK_CUDA_GRAPH", "1") != "0"
+        if self.world > 1 and os.environ.get("CEMK_CUDA_GRAPH_MULTI", "1") == "0":
+            self.use_cuda_graph = False
         self.print_info()
 
     # ------------------------------------------------------------------ constants (mjx_planner.py:142-172)
@@ -278,11 +280,20 @@ class cem_planner:
                 f'\n Time per trajectory: {self.t_fin}',
             )
 
+    def close(self):
+        """Release the captured CUDA graph and the library handle.  With several GPUs call this before
+        ``torch.distributed.destroy_process_group()``: a live graph holds captured NCCL kernels, and tearing the
+        communicator down under it blocks."""
+        if getattr(self, "_graph", None) is not None:
+            torch.cuda.current_stream(self.device).synchronize()
+            self._graph, self._graph_out, self._graph_key = None, None, None
+        if getattr(self, "_h", None):
+            self._lib.cemk_destroy(self._h)
+            self._h = None
+
     def __del__(self):
         try:
-            if getattr(self, "_h", None):
-                self._lib.cemk_destroy(self._h)
-                self._h = None
+            self.close()
         except Exception:
             pass
 
@@ -569,7 +580,8 @@ class cem_planner:
         elif self.use_cuda_graph and self._eager_ticks >= 2:
             torch.cuda.current_stream(dev).synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            # thread_local: NCCL's watchdog thread polls events while this thread captures
+            with torch.cuda.graph(g, capture_error_mode="thread_local" if self.world > 1 else "global"):
                 out = self._cem_device(pin, pout)
             self._graph, self._graph_out, self._graph_key = g, out, gkey
             g.replay()

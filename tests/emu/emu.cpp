@@ -11,6 +11,64 @@
 
 extern "C" int emu_sizeof_kmodel() { return (int)sizeof(KModel); }
 
+// Race-checking build (-DCEMK_EMU_RACE, see warp_dsl.h): counters over all rollouts since the last read.
+static long long g_race_waw = 0, g_race_blocks = 0;
+static int g_race_first[3] = {0, 0, 0};
+extern "C" int emu_race_enabled() {
+#ifdef CEMK_EMU_RACE
+  return 1;
+#else
+  return 0;
+#endif
+}
+extern "C" void emu_race_stats(long long* out5) {
+  out5[0] = g_race_waw; out5[1] = g_race_blocks; out5[2] = g_race_first[0]; out5[3] = g_race_first[1]; out5[4] = g_race_first[2];
+  g_race_waw = g_race_blocks = 0; g_race_first[0] = 0;
+}
+
+// Deliberately broken lane blocks, to show that the checker sees what it is meant to see (tests/test_emu_race.py).
+//   which = 1: a lane reads what its neighbour wrote in the same block (missing fence, rule 1);
+//   which = 2: two lanes write different values to the same scratch word in one block;
+//   which = 0: the correctly fenced version of 1 (write block, then read block).
+// out[0..KW-1] = what each lane read, out[KW] = write-write conflicts counted.
+extern "C" void emu_race_selftest(int which, float* out) {
+  Warp* W = new Warp();
+  WarpSmemT<KM_NC_FAST>* S = new WarpSmemT<KM_NC_FAST>();
+  memset((void*)W, 0, sizeof(Warp));
+  memset((void*)S, 0, sizeof(*S));
+  long long waw = 0;
+#ifdef CEMK_EMU_RACE
+  RaceState rs;
+  rs.add(S, sizeof(*S));
+  W->race = &rs;
+#endif
+  Warp& Wr = *W;
+  if (which == 1) {
+    LANES(Wr, R)
+      if (lane < KM_NV) S->qacc[lane] = (float)(lane + 1);
+      R.f0 = (lane > 0 && lane <= KM_NV) ? S->qacc[lane - 1] : 0.f;      // BUG on purpose: same-block read of another lane's write
+    END_LANES
+  } else if (which == 2) {
+    LANES(Wr, R)
+      if (lane < 2) S->qacc[0] = (float)(lane + 1);                       // BUG on purpose: two writers, different values
+      R.f0 = 0.f;
+    END_LANES
+  } else {
+    LANES(Wr, R)
+      if (lane < KM_NV) S->qacc[lane] = (float)(lane + 1);
+    END_LANES
+    LANES(Wr, R)
+      R.f0 = (lane > 0 && lane <= KM_NV) ? S->qacc[lane - 1] : 0.f;
+    END_LANES
+  }
+#ifdef CEMK_EMU_RACE
+  waw = rs.waw;
+#endif
+  for (int l = 0; l < KW; ++l) out[l] = W->regs[l].f0;
+  out[KW] = (float)waw;
+  delete W; delete S;
+}
+
 extern "C" int emu_rollout(const KModel* m, int B, int T, const float* thetadot, const float* q0, const float* v0,
                            const float* tpos, const float* trot, float w_pos, float w_rot, float w_col,
                            float* theta, float* cost4, float* eef_pos, float* eef_rot, float* collision,
@@ -42,7 +100,21 @@ extern "C" int emu_rollout(const KModel* m, int B, int T, const float* thetadot,
       A.flags = flags ? flags + s : nullptr;
       A.prevd = prevd;
       A.ovf = ovf;
+#ifdef CEMK_EMU_RACE
+      RaceState rs;                                   // shared scratch of this sample: the record, the previous distances, the spill area
+      if (nc <= KM_NC_FAST) rs.add(S, sizeof(*S)); else rs.add(Sb, sizeof(*Sb));
+      rs.add(prevd, sizeof(float) * 2 * KM_NPASS * KW);
+      rs.add(ovf, sizeof(float) * KM_NC_TOT * KM_OVF_STRIDE);
+      W->race = &rs;
+      g_emu_race = &rs;
+#endif
       if (nc <= KM_NC_FAST) rollout_sample<KM_NC_FAST>(*W, *m, *S, A); else rollout_sample<KM_NC_BIG>(*W, *m, *Sb, A);
+#ifdef CEMK_EMU_RACE
+#pragma omp critical
+      { g_race_waw += rs.waw; g_race_blocks += rs.blocks;
+        if (rs.waw && !g_race_first[0]) { g_race_first[0] = rs.first_line; g_race_first[1] = rs.first_word; g_race_first[2] = rs.first_lanes; } }
+      delete[] rs.snap; delete[] rs.pend; delete[] rs.owner;
+#endif
     }
     delete W; delete S; delete Sb; delete[] prevd; delete[] ovf;
   }

@@ -11,20 +11,23 @@ SRCS = [os.path.join(ROOT, "tests", "emu", "emu.cpp")] + [os.path.join(ROOT, "ma
                                                           for n in ("rollout_core.h", "warp_dsl.h", "kmodel.h")]
 
 
-def build():
-    if os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(s) for s in SRCS):
-        return OUT
-    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+def build(race=False):
+    """race=True: the race-checking emulation (-DCEMK_EMU_RACE, csrc/warp_dsl.h) as a second library."""
+    out = OUT.replace(".so", "_race.so") if race else OUT
+    if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in SRCS):
+        return out
+    os.makedirs(os.path.dirname(out), exist_ok=True)
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    subprocess.run([cxx, "-O2", "-fPIC", "-shared", "-fopenmp", "-std=c++17", "-Wno-unknown-pragmas", "-o", OUT, SRCS[0]],
-                   check=True, capture_output=True)
-    return OUT
+    subprocess.run([cxx, "-O2", "-fPIC", "-shared", "-fopenmp", "-std=c++17", "-Wno-unknown-pragmas"] + (["-DCEMK_EMU_RACE"] if race else [])
+                   + ["-o", out, SRCS[0]], check=True, capture_output=True)
+    return out
 
 
 class Emu:
-    def __init__(self, km):
+    def __init__(self, km, race=False):
         from manipulator_mujoco_b200.kmodel import KModel
-        self.lib = C.CDLL(build())
+        self.lib = C.CDLL(build(race))
+        assert self.lib.emu_race_enabled() == int(race)
         assert self.lib.emu_sizeof_kmodel() == C.sizeof(KModel)
         self.km = km
 
@@ -55,3 +58,18 @@ def capsule_box(cpos, cmat, csize, bpos, bmat, bsize):
     q = lambda a: a.ctypes.data_as(C.c_void_p)
     lib.emu_capsule_box(q(A), q(B), C.c_float(csize[0]), q(bp), q(bm), q(bs), q(d), q(p), q(n))
     return d, p.reshape(2, 3), n.reshape(2, 3)
+
+
+def race_stats(emu):
+    """(write-write conflicts, lane blocks checked) since the last call; race build only."""
+    out = (C.c_longlong * 5)()
+    emu.lib.emu_race_stats(out)
+    emu.first_conflict = dict(line=int(out[2]), word=int(out[3]), lanes=(int(out[4]) // 100, int(out[4]) % 100)) if out[0] else None
+    return int(out[0]), int(out[1])
+
+
+def race_selftest(which, race):
+    lib = C.CDLL(build(race))
+    out = np.zeros(33, np.float32)
+    lib.emu_race_selftest(int(which), out.ctypes.data_as(C.c_void_p))
+    return out[:16].copy(), int(out[16])

@@ -56,6 +56,11 @@ def main():
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print("MULTI_GPU_CHECK", "PASS" if int(flag.item()) else "FAIL", f"(world={world})")
+    sys.stdout.flush()
+    pl.close()                      # the captured graph holds NCCL kernels: release it before the communicator
+    if ref is not None:
+        ref.close()
+    torch.cuda.synchronize()
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) else 1)
 

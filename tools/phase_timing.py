@@ -32,6 +32,8 @@ for _ in range(2):
     pl.compute_cem(np.zeros(66), q0, np.zeros(6), np.zeros(6), tp, tr)
 torch.cuda.synchronize()
 pl._lib.cemk_debug_phase_clocks(buf)
+pl._lib.cemk_debug_phase_cond((C.c_ulonglong * 25)())        # (reading clears the tables)
+pl._lib.cemk_debug_events((C.c_ulonglong * 16)())
 pl.compute_cem(np.zeros(66), q0, np.zeros(6), np.zeros(6), tp, tr)
 torch.cuda.synchronize()
 pl._lib.cemk_debug_phase_clocks(buf)
@@ -43,4 +45,25 @@ print(f"k_rollout phase shares, B={B} T={T} (clock64 per warp, summed)")
 for n, x in sorted(zip(names, v), key=lambda t: -t[1]):
     print(f"  {100 * x / v.sum():6.2f}%  {x / (B * T):9.0f} clk/env-step  {n}")
 print(f"  total {v.sum() / (B * T):.0f} clk per env-step per warp")
+pc = (C.c_ulonglong * 25)()
+pl._lib.cemk_debug_phase_cond(pc)
+c = np.array(list(pc)[:24], dtype=np.float64)
+nflag = max(float(pc[24]), 1.0)
+nall = B * T                       # one lane per lane group counts: group-steps
+rest_n = max(nall - nflag, 1.0)
+print(f"conditional profile: clk per step of a warp whose step has robot contacts ({int(nflag)} group-steps) vs the other steps")
+for n, xc, xa in sorted(zip(names, c, v), key=lambda t: -t[1]):
+    print(f"  {xc / nflag:9.0f} vs {(xa - xc) / rest_n:9.0f}   {n}")
+print(f"  {c.sum() / nflag:9.0f} vs {(v.sum() - c.sum()) / rest_n:9.0f}   total")
+ev = (C.c_ulonglong * 16)()
+pl._lib.cemk_debug_events(ev)
+e = [float(x) for x in ev]
+n = max(e[0], 1.0)
+print("events per sample-step (lane group), B x T =", B * T, "counted", int(e[0]))
+for label, val in [("has near capsule-box pairs", e[1] / n), ("near pairs (mean)", e[2] / n), ("warp runs the near pass (either sample)", e[11] / n),
+                   ("active contacts (mean)", e[3] / n), ("has robot contacts", e[4] / n), ("warp emits robot contacts (either sample)", e[12] / n),
+                   ("no active row", e[8] / n), ("has active limit rows", e[13] / n), ("coupled 12x12 solve", e[7] / n), ("spill instantiation", e[9] / n),
+                   ("line-search trips executed by the warp (mean)", e[6] / n), ("line-search trips the sample needed (mean)", e[5] / n),
+                   ("free-box pairs walked by the warp (mean)", e[10] / n)]:
+    print(f"  {val:8.3f}  {label}")
 os.remove(dbg)
