@@ -524,6 +524,135 @@ KNOINLINE int plane_box(const float* ppos, const float* pn, const float* bpos, c
   }
   return nact;
 }
+// ---- rare parts of box_box_warp, out of line (they would otherwise sit, never executed, inside the step loop; each
+//      builds a lane-group context of its own, see cold_warp).  `act`, `outside`, the polygon size and the results are
+//      per sample (per lane group); everything else is read from the scratch the inlined part has filled. ----
+// edge-edge contact: closest points of the two support edges
+template <int NC>
+KNOINLINE void bb_edge_edge(WarpSmemT<NC>& S, bool act, int slot, int bl, float bn0, float bn1, float bn2, const float* s1, const float* s2,
+                            const float* m2, const float* p2) {
+  Warp W;
+  cold_warp(W, 0, 0);
+  const float bn[3] = {bn0, bn1, bn2};
+  float Rm[9], c[3];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) Rm[k] = S.bbR[k];
+  c[0] = S.bbc[0]; c[1] = S.bbc[1]; c[2] = S.bbc[2];
+  const int be = bl >= 6 ? bl - 6 : 0;       // (a face-face sample of the same warp computes a dummy pair)
+  const int bi = be / 3, bj = be % 3;
+  float e1c[3] = {c[0], c[1], c[2]}, e2c[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float Ak[3] = {Rm[k], Rm[3 + k], Rm[6 + k]};
+    if (k != bi) { const float sg = dot3(Ak, bn) > 0.f ? 1.f : -1.f; madd3(e1c, e1c, Ak, sg * s1[k]); }
+    if (k != bj) e2c[k] = (bn[k] > 0.f ? -1.f : 1.f) * s2[k];
+  }
+  const float Ab[3] = {S.bbR[bi], S.bbR[3 + bi], S.bbR[6 + bi]}, e2[3] = {bj == 0 ? 1.f : 0.f, bj == 1 ? 1.f : 0.f, bj == 2 ? 1.f : 0.f};
+  float a0[3], a1[3], b0[3], b1[3];
+  madd3(a0, e1c, Ab, -s1[bi]); madd3(a1, e1c, Ab, s1[bi]);
+  madd3(b0, e2c, e2, -s2[bj]); madd3(b1, e2c, e2, s2[bj]);
+  SegPair sp = closest_seg_seg_v(a0, a1, b0, b1);
+  const float mid[3] = {0.5f * (sp.a[0] + sp.b[0]), 0.5f * (sp.a[1] + sp.b[1]), 0.5f * (sp.a[2] + sp.b[2])};
+  float w[3], df[3];
+  mat_vec(w, m2, mid); add3(w, w, p2);
+  sub3(df, sp.b, sp.a);
+  const float d = dot3(df, bn);
+  UNIFORM_WRITE(W) { if (act && bl >= 6) { copy3(S.bstage[slot][0], w); S.bstage[slot][0][3] = d; } } END_UNIFORM_WRITE
+}
+// Sutherland-Hodgman of the incident face (S.bbpoly[0], four vertices) against the four side planes of the reference
+// face, polygon edges on lanes; output slots by ballot (each edge emits its start vertex if inside, then the crossing
+// point).  Returns (polygon size) | (buffer holding it) << 8.
+template <int NC>
+KNOINLINE int bb_clip(WarpSmemT<NC>& S, bool act, unsigned outside) {
+  Warp W;
+  cold_warp(W, 0, 0);
+  int np = 4, cur = 0;
+#pragma unroll 1
+  for (int i = 0; i < 4; ++i) {
+    const bool clip = act && np > 0 && outside != 0u;       // this sample still has something to clip
+    if (!warp_any_groups(W, clip)) break;
+    LANES(W, R)
+      R.actmask = 0; R.f0 = 0.f;
+      if (clip && lane < np) {
+        const float* a = S.bbpoly[cur][lane]; const float* b = S.bbpoly[cur][lane + 1 == np ? 0 : lane + 1];
+        float ta[3], tb[3];
+        sub3(ta, a, S.bbrf[i]); sub3(tb, b, S.bbrf[i]);
+        const float da = dot3(ta, S.bben[i]), db = dot3(tb, S.bben[i]);
+        const bool keep = da <= 0.f, cross = (da < 0.f && db > 0.f) || (da > 0.f && db < 0.f);
+        R.actmask = (keep ? 1 : 0) | (cross ? 2 : 0);
+        R.f0 = cross ? da / (da - db) : 0.f;
+      }
+    END_LANES
+    const unsigned mk = warp_ballot(W, [](int, LaneRegs& R) { return (R.actmask & 1) != 0; });
+    const unsigned mx = warp_ballot(W, [](int, LaneRegs& R) { return (R.actmask & 2) != 0; });
+    LANES(W, R)
+      if (clip && lane < np && R.actmask) {
+        const float* a = S.bbpoly[cur][lane]; const float* b = S.bbpoly[cur][lane + 1 == np ? 0 : lane + 1];
+        const unsigned below = (1u << lane) - 1u;
+        int o = KPOPC(mk & below) + KPOPC(mx & below);
+        if (R.actmask & 1) { copy3(S.bbpoly[cur ^ 1][o], a); ++o; }
+        if (R.actmask & 2) { float ab[3]; sub3(ab, b, a); madd3(S.bbpoly[cur ^ 1][o], a, ab, R.f0); }
+      }
+    END_LANES
+    if (clip) { np = KPOPC(mk) + KPOPC(mx); cur ^= 1; }
+  }
+  return np | (cur << 8);
+}
+// MJX's 4-point manifold rule on a clipped polygon of more than four vertices (S.bbpref = the vertices projected on the
+// reference face, [3] = height; negative = penetrating)
+template <int NC>
+KNOINLINE void bb_manifold(WarpSmemT<NC>& S, bool act, int slot, int np, bool swap, float rn0, float rn1, float rn2, const float* m2, const float* p2) {
+  Warp W;
+  cold_warp(W, 0, 0);
+  const float rn[3] = {rn0, rn1, rn2};
+  float Rm[9], c[3];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) Rm[k] = S.bbR[k];
+  c[0] = S.bbc[0]; c[1] = S.bbc[1]; c[2] = S.bbc[2];
+  LANES(W, R)
+    R.f0 = (lane < np && S.bbpref[lane < 8 ? lane : 0][3] < 0.f) ? 0.f : -1e6f;            // dm: only penetrating vertices compete
+  END_LANES
+  // lanes >= np must never win: give them -inf in every argmax
+  const int ia = warp_argmax_first8(W, [&](int l, LaneRegs& R) { return l < np ? R.f0 : -INFINITY; });
+  LANES(W, R)
+    R.f1 = -INFINITY;
+    if (lane < np) { float t[3]; sub3(t, S.bbpref[ia], S.bbpref[lane]); R.f1 = dot3(t, t) + R.f0; }
+  END_LANES
+  const int ib = warp_argmax_first8(W, [](int, LaneRegs& R) { return R.f1; });
+  float ab[3];
+  { float t[3]; sub3(t, S.bbpref[ia], S.bbpref[ib]); cross3(ab, rn, t); }
+  LANES(W, R)
+    R.f1 = -INFINITY;
+    if (lane < np) { float ap[3]; sub3(ap, S.bbpref[ia], S.bbpref[lane]); R.f1 = fabsf(dot3(ap, ab)) + R.f0; }
+  END_LANES
+  const int ic = warp_argmax_first8(W, [](int, LaneRegs& R) { return R.f1; });
+  float ac[3], bc[3];
+  { float t[3]; sub3(t, S.bbpref[ia], S.bbpref[ic]); cross3(ac, rn, t); sub3(t, S.bbpref[ib], S.bbpref[ic]); cross3(bc, rn, t); }
+  LANES(W, R)
+    R.f1 = -INFINITY;
+    if (lane < np) {
+      float bp[3], ap[3];
+      sub3(bp, S.bbpref[ib], S.bbpref[lane]); sub3(ap, S.bbpref[ia], S.bbpref[lane]);
+      R.f1 = fmaxf(fabsf(dot3(bp, bc)), fabsf(dot3(ap, ac))) + R.f0 - ((lane == ia || lane == ib || lane == ic) ? 2e6f : 0.f);
+    }
+  END_LANES
+  const int id = warp_argmax_first8(W, [](int, LaneRegs& R) { return R.f1; });
+  const int idx[4] = {ia, ib, ic, id};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    bool uniq = true;
+#pragma unroll
+    for (int z = 0; z < q; ++z) if (idx[z] == idx[q]) uniq = false;
+    const float h = S.bbpref[idx[q]][3];
+    const bool put = act && h < 0.f && uniq;
+    float w[3];
+    if (swap) { float u[3]; mat_vec(u, Rm, S.bbpref[idx[q]]); add3(u, u, c); mat_vec(w, m2, u); }
+    else mat_vec(w, m2, S.bbpref[idx[q]]);
+    add3(w, w, p2);
+    UNIFORM_WRITE(W) { if (put) { copy3(S.bstage[slot][q], w); S.bstage[slot][q][3] = h; } } END_UNIFORM_WRITE
+  }
+}
+
 // Warp-cooperative box (geom1) vs box (geom2).  Same algorithm, axis order and tie rules as the
 // oracle's box_box (SAT over face2 x3, face1 x3, edge x edge 3x3; clipped face
 // manifold reduced by the 4-point rule, or one edge-edge contact), with the 15 axes, the polygon edges
@@ -582,29 +711,7 @@ KFN void box_box_warp(Warp& W, WarpSmemT<NC>& S, bool act, int slot, const float
 #pragma unroll
   for (int k = 0; k < 9; ++k) Rm[k] = S.bbR[k];
   c[0] = S.bbc[0]; c[1] = S.bbc[1]; c[2] = S.bbc[2];
-  if (warp_any_groups(W, act && bl >= 6)) {
-    // ---- edge-edge: closest points of the two support edges (uniform, rare) ----
-    const int be = bl >= 6 ? bl - 6 : 0;       // (a face-face sample of the same warp computes a dummy pair)
-    const int bi = be / 3, bj = be % 3;
-    float e1c[3] = {c[0], c[1], c[2]}, e2c[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const float Ak[3] = {Rm[k], Rm[3 + k], Rm[6 + k]};
-      if (k != bi) { const float sg = dot3(Ak, bn) > 0.f ? 1.f : -1.f; madd3(e1c, e1c, Ak, sg * s1[k]); }
-      if (k != bj) e2c[k] = (bn[k] > 0.f ? -1.f : 1.f) * s2[k];
-    }
-    const float Ab[3] = {S.bbR[bi], S.bbR[3 + bi], S.bbR[6 + bi]}, e2[3] = {bj == 0 ? 1.f : 0.f, bj == 1 ? 1.f : 0.f, bj == 2 ? 1.f : 0.f};
-    float a0[3], a1[3], b0[3], b1[3];
-    madd3(a0, e1c, Ab, -s1[bi]); madd3(a1, e1c, Ab, s1[bi]);
-    madd3(b0, e2c, e2, -s2[bj]); madd3(b1, e2c, e2, s2[bj]);
-    SegPair sp = closest_seg_seg_v(a0, a1, b0, b1);
-    const float mid[3] = {0.5f * (sp.a[0] + sp.b[0]), 0.5f * (sp.a[1] + sp.b[1]), 0.5f * (sp.a[2] + sp.b[2])};
-    float w[3], df[3];
-    mat_vec(w, m2, mid); add3(w, w, p2);
-    sub3(df, sp.b, sp.a);
-    const float d = dot3(df, bn);
-    UNIFORM_WRITE(W) { if (act && bl >= 6) { copy3(S.bstage[slot][0], w); S.bstage[slot][0][3] = d; } } END_UNIFORM_WRITE
-  }
+  if (warp_any_groups(W, act && bl >= 6)) bb_edge_edge<NC>(S, act, slot, bl, bn[0], bn[1], bn[2], s1, s2, m2, p2);      // rare, out of line
   act = act && bl < 6;
   if (!warp_any_groups(W, act)) return;
   // ---- face-face: reference face on the box owning the axis, incident face on the other ----
@@ -677,34 +784,9 @@ KFN void box_box_warp(Warp& W, WarpSmemT<NC>& S, bool act, int slot, const float
     sub3(t, S.bbpoly[0][l & 3], S.bbrf[l >> 2]);
     return dot3(t, S.bben[l >> 2]) > 0.f;
   });
-#pragma unroll 1
-  for (int i = 0; i < 4; ++i) {
-    const bool clip = act && np > 0 && outside != 0u;       // this sample still has something to clip
-    if (!warp_any_groups(W, clip)) break;
-    LANES(W, R)
-      R.actmask = 0; R.f0 = 0.f;
-      if (clip && lane < np) {
-        const float* a = S.bbpoly[cur][lane]; const float* b = S.bbpoly[cur][lane + 1 == np ? 0 : lane + 1];
-        float ta[3], tb[3];
-        sub3(ta, a, S.bbrf[i]); sub3(tb, b, S.bbrf[i]);
-        const float da = dot3(ta, S.bben[i]), db = dot3(tb, S.bben[i]);
-        const bool keep = da <= 0.f, cross = (da < 0.f && db > 0.f) || (da > 0.f && db < 0.f);
-        R.actmask = (keep ? 1 : 0) | (cross ? 2 : 0);
-        R.f0 = cross ? da / (da - db) : 0.f;
-      }
-    END_LANES
-    const unsigned mk = warp_ballot(W, [](int, LaneRegs& R) { return (R.actmask & 1) != 0; });
-    const unsigned mx = warp_ballot(W, [](int, LaneRegs& R) { return (R.actmask & 2) != 0; });
-    LANES(W, R)
-      if (clip && lane < np && R.actmask) {
-        const float* a = S.bbpoly[cur][lane]; const float* b = S.bbpoly[cur][lane + 1 == np ? 0 : lane + 1];
-        const unsigned below = (1u << lane) - 1u;
-        int o = KPOPC(mk & below) + KPOPC(mx & below);
-        if (R.actmask & 1) { copy3(S.bbpoly[cur ^ 1][o], a); ++o; }
-        if (R.actmask & 2) { float ab[3]; sub3(ab, b, a); madd3(S.bbpoly[cur ^ 1][o], a, ab, R.f0); }
-      }
-    END_LANES
-    if (clip) { np = KPOPC(mk) + KPOPC(mx); cur ^= 1; }
+  if (warp_any_groups(W, act && outside != 0u)) {                  // rare, out of line
+    const int r = bb_clip<NC>(S, act, outside);
+    if (act && outside != 0u) { np = r & 0xff; cur = r >> 8; }
   }
   act = act && np > 0;
   if (!warp_any_groups(W, act)) return;
@@ -738,45 +820,7 @@ KFN void box_box_warp(Warp& W, WarpSmemT<NC>& S, bool act, int slot, const float
   }
   act = act && np > 4;
   if (!warp_any_groups(W, act)) return;
-  // lanes >= np must never win: give them -inf in every argmax
-  const int ia = warp_argmax_first8(W, [&](int l, LaneRegs& R) { return l < np ? R.f0 : -INFINITY; });
-  LANES(W, R)
-    R.f1 = -INFINITY;
-    if (lane < np) { float t[3]; sub3(t, S.bbpref[ia], S.bbpref[lane]); R.f1 = dot3(t, t) + R.f0; }
-  END_LANES
-  const int ib = warp_argmax_first8(W, [](int, LaneRegs& R) { return R.f1; });
-  float ab[3];
-  { float t[3]; sub3(t, S.bbpref[ia], S.bbpref[ib]); cross3(ab, rn, t); }
-  LANES(W, R)
-    R.f1 = -INFINITY;
-    if (lane < np) { float ap[3]; sub3(ap, S.bbpref[ia], S.bbpref[lane]); R.f1 = fabsf(dot3(ap, ab)) + R.f0; }
-  END_LANES
-  const int ic = warp_argmax_first8(W, [](int, LaneRegs& R) { return R.f1; });
-  float ac[3], bc[3];
-  { float t[3]; sub3(t, S.bbpref[ia], S.bbpref[ic]); cross3(ac, rn, t); sub3(t, S.bbpref[ib], S.bbpref[ic]); cross3(bc, rn, t); }
-  LANES(W, R)
-    R.f1 = -INFINITY;
-    if (lane < np) {
-      float bp[3], ap[3];
-      sub3(bp, S.bbpref[ib], S.bbpref[lane]); sub3(ap, S.bbpref[ia], S.bbpref[lane]);
-      R.f1 = fmaxf(fabsf(dot3(bp, bc)), fabsf(dot3(ap, ac))) + R.f0 - ((lane == ia || lane == ib || lane == ic) ? 2e6f : 0.f);
-    }
-  END_LANES
-  const int id = warp_argmax_first8(W, [](int, LaneRegs& R) { return R.f1; });
-  const int idx[4] = {ia, ib, ic, id};
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    bool uniq = true;
-#pragma unroll
-    for (int z = 0; z < q; ++z) if (idx[z] == idx[q]) uniq = false;
-    const float h = S.bbpref[idx[q]][3];
-    const bool put = act && h < 0.f && uniq;
-    float w[3];
-    if (swap) { float u[3]; mat_vec(u, Rm, S.bbpref[idx[q]]); add3(u, u, c); mat_vec(w, m2, u); }
-    else mat_vec(w, m2, S.bbpref[idx[q]]);
-    add3(w, w, p2);
-    UNIFORM_WRITE(W) { if (put) { copy3(S.bstage[slot][q], w); S.bstage[slot][q][3] = h; } } END_UNIFORM_WRITE
-  }
+  bb_manifold<NC>(S, act, slot, np, swap, rn[0], rn[1], rn[2], m2, p2);             // more than four vertices: rare, out of line
 }
 
 // ------------------------------------------------------------------------------------------ constraints
@@ -1161,6 +1205,7 @@ KFN void solve_rows(Warp& W, const KModel& m, WarpSmemT<NC>& S, const int ncon, 
   LANES(W, R)
     if (lane < KM_NV) {
       float fc = 0.f;
+#pragma unroll 1
       for (int r = 0; r < nlim; ++r) { const float ja = S.rJaref[r]; if (ja < 0.f && S.limdof[r] == lane) fc += S.limsign[r] * (-S.rD[r] * ja); }
       {
         const unsigned sel = lane < KM_NL ? mrob : mbox;
@@ -1204,7 +1249,8 @@ KFN void solve_rows(Warp& W, const KModel& m, WarpSmemT<NC>& S, const int ncon, 
     const int i = (R.tri >> (8 * q)) & 15, j = (R.tri >> (8 * q + 4)) & 15;
     if (i < KM_NL) {
       float hr = S.Mr[i][j];
-      for (int r = 0; r < nlim; ++r) if (S.rJaref[r] < 0.f && S.limdof[r] == i && i == j) hr += S.rD[r];
+#pragma unroll 1
+      for (int r = 0; r < nlim; ++r) if (S.rJaref[r] < 0.f && S.limdof[r] == i && i == j) hr += S.rD[r];      // (rolled: limit rows are rare, their code must stay small)
       hr += hess_contacts<NC, SP>(S, mrob, 1, ncon, i, j);
       S.H[i][j] = hr;
       float hb = i != j ? 0.f : (i < 3 ? m.fb_mass : (i == 3 ? m.fb_inertia[0] : (i == 4 ? m.fb_inertia[1] : m.fb_inertia[2])));
