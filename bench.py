@@ -287,13 +287,14 @@ def main():
             carry = (q0, z6, tp, tr, mean0, cov0, key1, state_term)
             return pl.cem_iter(carry, None)
 
-        for _ in range(args.warmup):
+        # W warm-up steps; with several GPUs a few more, untimed: NCCL sets its channels up lazily over the first collectives
+        for _ in range(args.warmup + (8 if world > 1 else 0)):
             device_step()
         barrier()
         l0 = lib.cemk_launch_count(h)
         ms = timed(device_step, args.steps)
         barrier()
-        res = {"pl": pl, "Bl": Bl, "launches": lib.cemk_launch_count(h) - l0}
+        res = {"pl": pl, "Bl": Bl, "launches": lib.cemk_launch_count(h) - l0, "ms_all": [round(v, 4) for v in ms]}
         res["tot_ms"] = max_over_ranks(sum(ms))
         res["value"] = Bg * T * args.steps / (res["tot_ms"] * 1e-3)
         if with_e2e:
@@ -392,7 +393,7 @@ def main():
         "config": {"workload": f"UR5e+Hand-E scene A (ur5e_hande_mjx/scene.xml constants), {Bl} samples/GPU x {T} steps, dt={DT}, "
                                f"order-10 Bernstein, {PROJ_IT} projection iterations, elite {ELITE}, 1 CEM iteration per step",
                    "global_batch": Bg_main, "horizon": T, "parallelism": f"sample-sharded x{world}", "l2": "flushed (256 MB write) before every timed step"},
-        "cem_iter_latency_ms": main_res["tot_ms"] / args.steps,
+        "cem_iter_latency_ms": main_res["tot_ms"] / args.steps, "ms_per_step_rank0": main_res["ms_all"],
         "e2e": {"value": main_res["e2e_value"], "unit": "env-steps/s", "ms_per_step": main_res["e2e_tot_ms"] / args.steps,
                 "h2d_bytes_per_step": int(pl.h2d_bytes), "d2h_bytes_per_step": int(pl.d2h_bytes),
                 "cuda_graph": pl._graph is not None, "contact_overflow_samples": main_res["overflow_samples"]},

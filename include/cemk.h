@@ -40,9 +40,14 @@ int cemk_destroy(cemk_handle* h);
 /* Update the rollout snapshot (qpos0 / warm0 / qvel0 of the KModel) after construction. */
 int cemk_set_model(cemk_handle* h, const void* kmodel, int kmodel_bytes);
 
+/* Bernstein coefficients per DOF, nc = order + 1 (mjx_planner.py:40 calls bernstein_coeff_ordern_new(10, ...), i.e. nc = 11, the
+ * default; SURVEY.md 8 f.4: arbitrary order n).  4 <= nc <= 16; nvar = 6 nc is the width of every xi / mean / cov / elite array
+ * below ("66" in their descriptions is the default nvar).  Call before cemk_set_horizon (it discards the horizon tables). */
+int cemk_set_order(cemk_handle* h, int ncoef);
+
 /* Per-horizon constants, host pointers, float32:
- *   G [3][T][11] = Pdot, Pddot, P (bernstein_coeff_ordern_new, mjx_planner.py:40);
- *   Kpp [11][11], Kpe [11][5] = per-DOF blocks of Q_inv (mjx_planner.py:166-172, block diagonal per DOF);
+ *   G [3][T][nc] = Pdot, Pddot, P (bernstein_coeff_ordern_new, mjx_planner.py:40);
+ *   Kpp [nc][nc], Kpe [nc][5] = per-DOF blocks of Q_inv (mjx_planner.py:166-172, block diagonal per DOF);
  *   bounds = v_max, a_max, p_max (mjx_planner.py:84-86). */
 int cemk_set_horizon(cemk_handle* h, int T, const float* G, const float* Kpp, const float* Kpe, const float* bounds3);
 

@@ -16,8 +16,11 @@
 #include "../../include/cemk.h"
 #include "rollout_core.h"
 
-#define NVAR 66
-#define NCOEF 11
+// Bernstein order n (mjx_planner.py:40 hard-codes 10; SURVEY 8 f.4 asks for order n): ncoef = n + 1 coefficients per DOF,
+// nvar = 6 ncoef decision variables, chosen per handle by cemk_set_order (default 11 / 66).
+#define MINCOEF 4
+#define MAXCOEF 16
+#define MAXVAR (KM_NL * MAXCOEF)
 #ifndef ROLLOUT_WARPS
 #define ROLLOUT_WARPS 14      // warps per CTA (28 samples with two samples per warp: all the shared memory of an SM); they
                               // step in lockstep (STEP_ALIGN) to share the instruction cache
@@ -37,12 +40,23 @@ static int cuda_err(cudaError_t e, const char* where) {
 }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_err(e_, #call); } while (0)
 
+// Every entry point runs on its handle's device and leaves the caller's current device as it found it (a planner on
+// cuda:1 next to one on cuda:0, or torch code that never set a device, must not notice the library).
+struct DevGuard {
+  int prev = -1; bool switched = false;
+  explicit DevGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DevGuard() { if (switched) cudaSetDevice(prev); }
+};
+
 struct cemk_handle {
   int device;
   KModel* d_model;
+  int ncoef, nvar;                 // Bernstein coefficients per DOF, decision variables (6 ncoef)
   int T;
   float* d_G;      // [3][T][11]
-  float* d_K;      // Kpp[121] Kpe[55] bounds[3]
+  float* d_K;      // Kpp[ncoef^2] Kpe[ncoef*5] bounds[3]
   long long launches;
   int* d_flags; int flags_cap; int num_sms;
   float* d_prevd; int prevd_cap;   // previous-step slot distances of every sample (rollout scratch, stays in L2)
@@ -145,47 +159,48 @@ static_assert(((sizeof(KModel) + 15) & ~size_t(15)) + ROLLOUT_WARPS * GPW * size
               "rollout scratch exceeds the 227 KB of shared memory a CTA can have");
 
 // ---------------------------------------------------------------------------------------------- sampling
-// L = chol(cov + 0.003 I), lower, row-major [66][66]; one CTA of 16 x 16 threads.  Right-looking on the
+// L = chol(cov + 0.003 I), lower, row-major [n][n] (n = nvar <= MAXVAR); one CTA of 16 x 16 threads.  Right-looking on the
 // unscaled columns (A[i][k] -= A[i][j] A[k][j] / A[j][j], one barrier per column; column j is final after
 // step j), scaled by 1 / sqrt(A[j][j]) in a last pass.
-__global__ void __launch_bounds__(256) k_chol66(const float* __restrict__ cov, float* __restrict__ L) {
-  __shared__ float A[NVAR][NVAR + 1];
+__global__ void __launch_bounds__(256) k_chol66(int n, const float* __restrict__ cov, float* __restrict__ L) {
+  __shared__ float A[MAXVAR][MAXVAR + 1];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  for (int i = ty; i < NVAR; i += 16)
-    for (int j = tx; j < NVAR; j += 16) A[i][j] = cov[i * NVAR + j] + (i == j ? 0.003f : 0.f);
+  for (int i = ty; i < n; i += 16)
+    for (int j = tx; j < n; j += 16) A[i][j] = cov[i * n + j] + (i == j ? 0.003f : 0.f);
   __syncthreads();
-  for (int j = 0; j < NVAR - 1; ++j) {
-    const float p = 1.f / A[j][j];
-    for (int i = j + 1 + ty; i < NVAR; i += 16) {
+  for (int j = 0; j < n - 1; ++j) {
+    const float p = __frcp_rn(A[j][j]);                  // (the library is built with -use_fast_math for k_rollout; the small
+                                                         //  kernels spell out IEEE division / sqrt / exp so the flag does not touch them)
+    for (int i = j + 1 + ty; i < n; i += 16) {
       const float aij = A[i][j] * p;
       for (int k = j + 1 + tx; k <= i; k += 16) A[i][k] -= aij * A[k][j];
     }
     __syncthreads();
   }
-  for (int i = ty; i < NVAR; i += 16)
-    for (int j = tx; j < NVAR; j += 16) {
-      const float d = sqrtf(A[j][j]);
-      L[i * NVAR + j] = j > i ? 0.f : (i == j ? d : A[i][j] / d);
+  for (int i = ty; i < n; i += 16)
+    for (int j = tx; j < n; j += 16) {
+      const float d = __fsqrt_rn(A[j][j]);
+      L[i * n + j] = j > i ? 0.f : (i == j ? d : __fdiv_rn(A[i][j], d));
     }
 }
 // xi[b][i] = mean[i] + sum_{j<=i} L[i][j] z[b][j]
-__global__ void __launch_bounds__(256) k_sample(int B, const float* __restrict__ z, const float* __restrict__ mean,
+__global__ void __launch_bounds__(256) k_sample(int B, int n, const float* __restrict__ z, const float* __restrict__ mean,
                                                 const float* __restrict__ L, float* __restrict__ xi) {
-  __shared__ float sL[NVAR][NVAR + 1];
-  __shared__ float sz[4][NVAR];
-  for (int e = threadIdx.x; e < NVAR * NVAR; e += blockDim.x) sL[e / NVAR][e % NVAR] = L[e];
+  __shared__ float sL[MAXVAR][MAXVAR + 1];
+  __shared__ float sz[4][MAXVAR];
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) sL[e / n][e % n] = L[e];
   const int b0 = blockIdx.x * 4;
-  for (int e = threadIdx.x; e < 4 * NVAR; e += blockDim.x) {
-    int b = b0 + e / NVAR;
-    sz[e / NVAR][e % NVAR] = b < B ? z[(size_t)b * NVAR + e % NVAR] : 0.f;
+  for (int e = threadIdx.x; e < 4 * n; e += blockDim.x) {
+    int b = b0 + e / n;
+    sz[e / n][e % n] = b < B ? z[(size_t)b * n + e % n] : 0.f;
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < 4 * NVAR; e += blockDim.x) {
-    int bl = e / NVAR, i = e % NVAR, b = b0 + bl;
+  for (int e = threadIdx.x; e < 4 * n; e += blockDim.x) {
+    int bl = e / n, i = e % n, b = b0 + bl;
     if (b >= B) continue;
     float s = 0.f;
     for (int j = 0; j <= i; ++j) s += sL[i][j] * sz[bl][j];
-    xi[(size_t)b * NVAR + i] = mean[i] + s;
+    xi[(size_t)b * n + i] = mean[i] + s;
   }
 }
 
@@ -276,70 +291,79 @@ constexpr int kProjUnroll = PROJ_UNROLL;
 #ifndef PROJ_SLICES
 #define PROJ_SLICES 4
 #endif
+// NC = Bernstein coefficients per DOF (order + 1), a template parameter so that the iterates stay in registers; a basis
+// row is padded to PC = 4 ceil(NC / 4) floats and read with 128-bit broadcast loads.
+template <int NC>
 __global__ void __launch_bounds__(32 * PROJ_SLICES) k_project(int B, int T, int iters, const float* __restrict__ G,
                                                               const float* __restrict__ Kc, const float* __restrict__ xi,
                                                               const float* __restrict__ state_term, float* __restrict__ xi_f,
                                                               float* __restrict__ thetadot) {
+  constexpr int PC = (NC + 3) / 4 * 4, NV = KM_NL * NC, KPAD = (5 * NC + 3 + 3) / 4 * 4;
   extern __shared__ __align__(16) float sm[];
-  float* sG = sm;                        // [3][T][12]
-  float* sKpp = sm + 3 * T * 12;         // [11][12]
-  float* sK = sKpp + NCOEF * 12;         // Kpe[55] bounds[3], padded to 60
-  float* sX = sK + 60;                   // [PROJ_SLICES][22][32] partial sums
-  for (int e = threadIdx.x; e < 3 * T * 12; e += blockDim.x) { const int r = e / 12, k = e % 12; sG[e] = k < NCOEF ? G[r * NCOEF + k] : 0.f; }
-  for (int e = threadIdx.x; e < NCOEF * 12; e += blockDim.x) { const int r = e / 12, k = e % 12; sKpp[e] = k < NCOEF ? Kc[r * NCOEF + k] : 0.f; }
-  for (int e = threadIdx.x; e < 58; e += blockDim.x) sK[e] = Kc[121 + e];
+  float* sG = sm;                        // [3][T][PC]
+  float* sKpp = sm + 3 * T * PC;         // [NC][PC]
+  float* sK = sKpp + NC * PC;            // Kpe[5 NC] bounds[3], padded to KPAD
+  float* sX = sK + KPAD;                 // [PROJ_SLICES][2 NC][32] partial sums
+  for (int e = threadIdx.x; e < 3 * T * PC; e += blockDim.x) { const int r = e / PC, k = e % PC; sG[e] = k < NC ? G[r * NC + k] : 0.f; }
+  for (int e = threadIdx.x; e < NC * PC; e += blockDim.x) { const int r = e / PC, k = e % PC; sKpp[e] = k < NC ? Kc[r * NC + k] : 0.f; }
+  for (int e = threadIdx.x; e < 5 * NC + 3; e += blockDim.x) sK[e] = Kc[NC * NC + e];
   __syncthreads();
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
   int prob = blockIdx.x * 32 + lane;
   const bool act = prob < B * 6;         // idle lanes of the last CTA still take part in the barriers
   if (!act) prob = B * 6 - 1;
   const int b = prob / 6, d = prob % 6;
-  const float* Kpe = sK; const float* bnd = sK + 55;
-  auto row12 = [](const float* p, float* g) {
-    const float4 a = reinterpret_cast<const float4*>(p)[0], b4 = reinterpret_cast<const float4*>(p)[1], c4 = reinterpret_cast<const float4*>(p)[2];
-    g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w; g[4] = b4.x; g[5] = b4.y; g[6] = b4.z; g[7] = b4.w; g[8] = c4.x; g[9] = c4.y; g[10] = c4.z;
-  };
-  float x[NCOEF], lam[NCOEF], xs[NCOEF], beq[5], cst[NCOEF], rh[NCOEF], re[NCOEF];
+  const float* Kpe = sK; const float* bnd = sK + 5 * NC;
+  auto rowp = [](const float* p, float* g) {
 #pragma unroll
-  for (int k = 0; k < NCOEF; ++k) { xs[k] = xi[(size_t)b * NVAR + d * NCOEF + k]; lam[k] = 0.f; x[k] = 0.f; rh[k] = 0.f; }
+    for (int q = 0; q < PC / 4; ++q) {
+      const float4 a = reinterpret_cast<const float4*>(p)[q];
+      if (4 * q < NC) g[4 * q] = a.x;
+      if (4 * q + 1 < NC) g[4 * q + 1] = a.y;
+      if (4 * q + 2 < NC) g[4 * q + 2] = a.z;
+      if (4 * q + 3 < NC) g[4 * q + 3] = a.w;
+    }
+  };
+  float x[NC], lam[NC], xs[NC], beq[5], cst[NC], rh[NC], re[NC];
+#pragma unroll
+  for (int k = 0; k < NC; ++k) { xs[k] = xi[(size_t)b * NV + d * NC + k]; lam[k] = 0.f; x[k] = 0.f; rh[k] = 0.f; }
 #pragma unroll
   for (int k = 0; k < 5; ++k) beq[k] = state_term[(size_t)b * 30 + k * 6 + d];
 #pragma unroll
-  for (int i = 0; i < NCOEF; ++i) { float s = 0.f; for (int k = 0; k < 5; ++k) s += Kpe[i * 5 + k] * beq[k]; cst[i] = s; }
+  for (int i = 0; i < NC; ++i) { float s = 0.f; for (int k = 0; k < 5; ++k) s += Kpe[i * 5 + k] * beq[k]; cst[i] = s; }
   for (int it = 0; it < iters; ++it) {
-    float rhs[NCOEF];
+    float rhs[NC];
 #pragma unroll
-    for (int k = 0; k < NCOEF; ++k) { rhs[k] = lam[k] + xs[k] + rh[k]; rh[k] = 0.f; re[k] = 0.f; }
+    for (int k = 0; k < NC; ++k) { rhs[k] = lam[k] + xs[k] + rh[k]; rh[k] = 0.f; re[k] = 0.f; }
 #pragma unroll
-    for (int i = 0; i < NCOEF; ++i) { float kr[NCOEF]; row12(sKpp + i * 12, kr); float s = cst[i]; for (int k = 0; k < NCOEF; ++k) s += kr[k] * rhs[k]; x[i] = s; }
+    for (int i = 0; i < NC; ++i) { float kr[NC]; rowp(sKpp + i * PC, kr); float s = cst[i]; for (int k = 0; k < NC; ++k) s += kr[k] * rhs[k]; x[i] = s; }
     for (int c = 0; c < 3; ++c) {
       const float bc = bnd[c];
-      const float* Gc = sG + c * T * 12;
+      const float* Gc = sG + c * T * PC;
 #pragma unroll(kProjUnroll)
       for (int t = slice; t < T; t += PROJ_SLICES) {
-        float g[NCOEF];
-        row12(Gc + t * 12, g);
-        float u0 = g[0] * x[0], u1 = g[1] * x[1], u2 = g[2] * x[2];   // three short chains instead of one of 11
+        float g[NC];
+        rowp(Gc + t * PC, g);
+        float u0 = 0.f, u1 = 0.f, u2 = 0.f;                            // three short chains instead of one of NC
 #pragma unroll
-        for (int k = 3; k < 9; k += 3) { u0 += g[k] * x[k]; u1 += g[k + 1] * x[k + 1]; u2 += g[k + 2] * x[k + 2]; }
-        u0 += g[9] * x[9]; u1 += g[10] * x[10];
+        for (int k = 0; k < NC; ++k) { if (k % 3 == 0) u0 += g[k] * x[k]; else if (k % 3 == 1) u1 += g[k] * x[k]; else u2 += g[k] * x[k]; }
         const float u = (u0 + u1) + u2;
         const float cl = fminf(fmaxf(u, -bc), bc);
         const float e = u - cl, h = u + cl;
 #pragma unroll
-        for (int k = 0; k < NCOEF; ++k) { re[k] += g[k] * e; rh[k] += g[k] * h; }
+        for (int k = 0; k < NC; ++k) { re[k] += g[k] * e; rh[k] += g[k] * h; }
       }
     }
     // exchange the partial sums of the slices
-    float* mine = sX + slice * 22 * 32 + lane;
+    float* mine = sX + slice * 2 * NC * 32 + lane;
 #pragma unroll
-    for (int k = 0; k < NCOEF; ++k) { mine[k * 32] = re[k]; mine[(NCOEF + k) * 32] = rh[k]; }
+    for (int k = 0; k < NC; ++k) { mine[k * 32] = re[k]; mine[(NC + k) * 32] = rh[k]; }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < NCOEF; ++k) {
+    for (int k = 0; k < NC; ++k) {
       float se = 0.f, sh = 0.f;
 #pragma unroll
-      for (int q = 0; q < PROJ_SLICES; ++q) { se += sX[(q * 22 + k) * 32 + lane]; sh += sX[(q * 22 + NCOEF + k) * 32 + lane]; }
+      for (int q = 0; q < PROJ_SLICES; ++q) { se += sX[(q * 2 * NC + k) * 32 + lane]; sh += sX[(q * 2 * NC + NC + k) * 32 + lane]; }
       re[k] = se; rh[k] = sh;
       lam[k] -= se;
     }
@@ -348,21 +372,33 @@ __global__ void __launch_bounds__(32 * PROJ_SLICES) k_project(int B, int T, int 
   if (!act) return;
   if (slice == 0) {
 #pragma unroll
-    for (int k = 0; k < NCOEF; ++k) xi_f[(size_t)b * NVAR + d * NCOEF + k] = x[k];
+    for (int k = 0; k < NC; ++k) xi_f[(size_t)b * NV + d * NC + k] = x[k];
   }
   if (thetadot) {
     const float* Gv = sG;    // Pdot
     float* out = thetadot + (size_t)b * 6 * T + (size_t)d * T;
     for (int t = slice; t < T; t += PROJ_SLICES) {
-      float g[NCOEF];
-      row12(Gv + t * 12, g);
+      float g[NC];
+      rowp(Gv + t * PC, g);
       float u = 0.f;
 #pragma unroll
-      for (int k = 0; k < NCOEF; ++k) u += g[k] * x[k];
+      for (int k = 0; k < NC; ++k) u += g[k] * x[k];
       out[t] = u;
     }
   }
 }
+template <int NC>
+static int project_smem(int T) {
+  constexpr int PC = (NC + 3) / 4 * 4, KPAD = (5 * NC + 3 + 3) / 4 * 4;
+  return (3 * T * PC + NC * PC + KPAD + PROJ_SLICES * 2 * NC * 32) * (int)sizeof(float);
+}
+// run `body` with NC = ncoef as a compile-time constant
+#define CEMK_FOR_NCOEF(ncoef, body) switch (ncoef) { \
+  case 4: { constexpr int NC = 4; body; } break;   case 5: { constexpr int NC = 5; body; } break;   case 6: { constexpr int NC = 6; body; } break; \
+  case 7: { constexpr int NC = 7; body; } break;   case 8: { constexpr int NC = 8; body; } break;   case 9: { constexpr int NC = 9; body; } break; \
+  case 10: { constexpr int NC = 10; body; } break; case 11: { constexpr int NC = 11; body; } break; case 12: { constexpr int NC = 12; body; } break; \
+  case 13: { constexpr int NC = 13; body; } break; case 14: { constexpr int NC = 14; body; } break; case 15: { constexpr int NC = 15; body; } break; \
+  case 16: { constexpr int NC = 16; body; } break; default: break; }
 
 // ---------------------------------------------------------------------------------------------- standalone cost
 __global__ void __launch_bounds__(128) k_cost_batch(int B, int T, int nslot, const float* __restrict__ eef_pos, const float* __restrict__ eef_rot,
@@ -372,12 +408,12 @@ __global__ void __launch_bounds__(128) k_cost_batch(int B, int T, int nslot, con
   if (s >= B) return;
   float cg = 0.f, cr = 0.f, cc = 0.f;
   const float* tp = tpos + (size_t)s * 3; const float* tq = trot + (size_t)s * 4;
-  const float tn = rsqrtf(tq[0] * tq[0] + tq[1] * tq[1] + tq[2] * tq[2] + tq[3] * tq[3]);
+  const float tn = __frcp_rn(__fsqrt_rn(tq[0] * tq[0] + tq[1] * tq[1] + tq[2] * tq[2] + tq[3] * tq[3]));
   for (int t = lane; t < T; t += 32) {
     const float* p = eef_pos + ((size_t)s * T + t) * 3; const float* q = eef_rot + ((size_t)s * T + t) * 4;
     float dx = p[0] - tp[0], dy = p[1] - tp[1], dz = p[2] - tp[2];
-    cg += sqrtf(dx * dx + dy * dy + dz * dz);
-    float qn = rsqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    cg += __fsqrt_rn(dx * dx + dy * dy + dz * dz);
+    float qn = __frcp_rn(__fsqrt_rn(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]));
     float dp = fabsf((q[0] * tq[0] + q[1] * tq[1] + q[2] * tq[2] + q[3] * tq[3]) * qn * tn);
     cr += 2.f * acosf(fminf(fmaxf(dp, -1.f), 1.f));
   }
@@ -439,7 +475,7 @@ __global__ void k_bitonic_global(unsigned long long* __restrict__ keys, int npow
   unsigned long long a = keys[i], b = keys[p];
   if ((a > b) == up) { keys[i] = b; keys[p] = a; }
 }
-__global__ void k_finish_sort(int n, const unsigned long long* __restrict__ keys, int idx_base, int* __restrict__ idx_sorted, int k,
+__global__ void k_finish_sort(int NVAR, int n, const unsigned long long* __restrict__ keys, int idx_base, int* __restrict__ idx_sorted, int k,
                               const float* __restrict__ cost, int stride, const float* __restrict__ xi, float* __restrict__ xi_elite,
                               float* __restrict__ cost_elite, const int* __restrict__ aux_in, int* __restrict__ aux_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -455,20 +491,19 @@ __global__ void k_finish_sort(int n, const unsigned long long* __restrict__ keys
   }
 }
 
-// Elite exchange records [..][NVAR + 2] = xi[66], cost, global index (as float, exact below 2^24):
+// Elite exchange records [..][nvar + 2] = xi[nvar], cost, global index (as float, exact below 2^24):
 // what one rank contributes to the NCCL all-gather, written / read without intermediate tensors.
-#define PACKW (NVAR + 2)
-__global__ void k_pack_sorted(const unsigned long long* __restrict__ keys, int idx_base, int k, const float* __restrict__ cost, int stride,
+__global__ void k_pack_sorted(int NVAR, const unsigned long long* __restrict__ keys, int idx_base, int k, const float* __restrict__ cost, int stride,
                               const float* __restrict__ xi, float* __restrict__ pack) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, PACKW = NVAR + 2;
   if (i >= k * PACKW) return;
   const int e = i / PACKW, c = i % PACKW;
   const int src = (int)(unsigned int)(keys[e] & 0xffffffffull);
   pack[i] = c < NVAR ? xi[(size_t)src * NVAR + c] : (c == NVAR ? cost[(size_t)src * stride] : (float)(src + idx_base));
 }
-__global__ void k_unpack_sorted(const unsigned long long* __restrict__ keys, int k, const float* __restrict__ packed,
+__global__ void k_unpack_sorted(int NVAR, const unsigned long long* __restrict__ keys, int k, const float* __restrict__ packed,
                                 float* __restrict__ xi_elite, float* __restrict__ cost_elite, int* __restrict__ gidx_elite) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, PACKW = NVAR + 2;
   if (i >= k * PACKW) return;
   const int e = i / PACKW, c = i % PACKW;
   const int src = (int)(unsigned int)(keys[e] & 0xffffffffull);
@@ -479,12 +514,13 @@ __global__ void k_unpack_sorted(const unsigned long long* __restrict__ keys, int
 }
 
 // ---------------------------------------------------------------------------------------------- mean / covariance
-// grid = 66 CTAs (one covariance row each); fixed summation order => bit-identical on every rank.
-__global__ void __launch_bounds__(128) k_mean_cov(int k, const float* __restrict__ cost, const float* __restrict__ xi, const float* __restrict__ mean_prev,
+__device__ __forceinline__ float precise_expf(float x) { return (float)exp((double)x); }     // -use_fast_math would turn expf into ex2.approx
+// grid = nvar CTAs (one covariance row each); fixed summation order => bit-identical on every rank.
+__global__ void __launch_bounds__(128) k_mean_cov(int NVAR, int k, const float* __restrict__ cost, const float* __restrict__ xi, const float* __restrict__ mean_prev,
                                                   const float* __restrict__ cov_prev, float lamda, float am, float ac,
                                                   float* __restrict__ mean_out, float* __restrict__ cov_out) {
   __shared__ float red[128];
-  __shared__ float smean[NVAR];
+  __shared__ float smean[MAXVAR];
   __shared__ float s_cmin, s_sumw;
   const int tid = threadIdx.x, row = blockIdx.x;
   float v = INFINITY;
@@ -493,9 +529,9 @@ __global__ void __launch_bounds__(128) k_mean_cov(int k, const float* __restrict
   for (int o = 64; o; o >>= 1) { if (tid < o) red[tid] = fminf(red[tid], red[tid + o]); __syncthreads(); }
   if (tid == 0) s_cmin = red[0];
   __syncthreads();
-  const float cmin = s_cmin, il = 1.f / lamda;
+  const float cmin = s_cmin, il = __frcp_rn(lamda);
   float sw = 0.f;
-  for (int i = tid; i < k; i += 128) sw += expf(-il * (cost[i] - cmin));
+  for (int i = tid; i < k; i += 128) sw += precise_expf(-il * (cost[i] - cmin));
   red[tid] = sw; __syncthreads();
   for (int o = 64; o; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
   if (tid == 0) s_sumw = red[0];
@@ -503,8 +539,8 @@ __global__ void __launch_bounds__(128) k_mean_cov(int k, const float* __restrict
   const float sumw = s_sumw;
   if (tid < NVAR) {
     float s = 0.f;
-    for (int i = 0; i < k; ++i) s += expf(-il * (cost[i] - cmin)) * xi[(size_t)i * NVAR + tid];
-    float mnew = (1.f - am) * mean_prev[tid] + am * (s / sumw);
+    for (int i = 0; i < k; ++i) s += precise_expf(-il * (cost[i] - cmin)) * xi[(size_t)i * NVAR + tid];
+    float mnew = (1.f - am) * mean_prev[tid] + am * __fdiv_rn(s, sumw);
     smean[tid] = mnew;
     if (row == 0) mean_out[tid] = mnew;
   }
@@ -513,10 +549,10 @@ __global__ void __launch_bounds__(128) k_mean_cov(int k, const float* __restrict
     const float mr = smean[row], mj = smean[tid];
     float s = 0.f;
     for (int i = 0; i < k; ++i) {
-      float w = expf(-il * (cost[i] - cmin));
+      float w = precise_expf(-il * (cost[i] - cmin));
       s += w * (xi[(size_t)i * NVAR + row] - mr) * (xi[(size_t)i * NVAR + tid] - mj);
     }
-    cov_out[row * NVAR + tid] = (1.f - ac) * cov_prev[row * NVAR + tid] + ac * (s / sumw) + (row == tid ? 0.0001f : 0.f);
+    cov_out[row * NVAR + tid] = (1.f - ac) * cov_prev[row * NVAR + tid] + ac * __fdiv_rn(s, sumw) + (row == tid ? 0.0001f : 0.f);
   }
 }
 
@@ -549,13 +585,13 @@ int cemk_create(const void* kmodel, int kmodel_bytes, int device, cemk_handle** 
   const KModel* km = (const KModel*)kmodel;
   if (km->nl != KM_NL || km->ncap > KM_MAXCAP || km->nsbox > KM_MAXSBOX || km->nrpair > KM_MAXRPAIR || km->nbpair > KM_MAXBPAIR)
     return set_err(CEMK_ERR_MODEL, "cemk_create: unsupported topology");
-  CK(cudaSetDevice(device));
+  DevGuard guard(device);
   cemk_handle* h = new cemk_handle();
-  h->device = device; h->T = 0; h->d_G = nullptr; h->d_K = nullptr; h->launches = 0; h->d_flags = nullptr; h->flags_cap = 0; h->force_rerun = 0; h->cta_samples = 0; h->d_prevd = nullptr; h->prevd_cap = 0; h->d_ovf = nullptr;
+  h->device = device; h->ncoef = 11; h->nvar = KM_NL * 11; h->T = 0; h->d_G = nullptr; h->d_K = nullptr; h->launches = 0; h->d_flags = nullptr; h->flags_cap = 0; h->force_rerun = 0; h->cta_samples = 0; h->d_prevd = nullptr; h->prevd_cap = 0; h->d_ovf = nullptr;
   { cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device)); h->num_sms = prop.multiProcessorCount; }
   CK(cudaMalloc(&h->d_model, sizeof(KModel)));
   CK(cudaMemcpy(h->d_model, kmodel, sizeof(KModel), cudaMemcpyHostToDevice));
-  CK(cudaMalloc(&h->d_K, 179 * sizeof(float)));
+  CK(cudaMalloc(&h->d_K, (MAXCOEF * MAXCOEF + 5 * MAXCOEF + 3) * sizeof(float)));
   CK(cudaFuncSetAttribute(k_rollout<KM_NC_FAST, ROLLOUT_WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)rollout_smem<KM_NC_FAST, ROLLOUT_WARPS>()));
   CK(cudaFuncSetAttribute(k_rollout<KM_NC_FAST, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rollout_smem<KM_NC_FAST, 8>()));
@@ -567,7 +603,7 @@ int cemk_create(const void* kmodel, int kmodel_bytes, int device, cemk_handle** 
 }
 int cemk_destroy(cemk_handle* h) {
   if (!h) return CEMK_OK;
-  cudaSetDevice(h->device);
+  DevGuard guard(h->device);
   cudaFree(h->d_model); cudaFree(h->d_G); cudaFree(h->d_K); cudaFree(h->d_flags); cudaFree(h->d_prevd); cudaFree(h->d_ovf);
   delete h;
   return CEMK_OK;
@@ -575,31 +611,43 @@ int cemk_destroy(cemk_handle* h) {
 int cemk_set_model(cemk_handle* h, const void* kmodel, int kmodel_bytes) {
   if (!h || !kmodel) return set_err(CEMK_ERR_ARG, "cemk_set_model: null argument");
   if (kmodel_bytes != (int)sizeof(KModel)) return set_err(CEMK_ERR_MODEL, "cemk_set_model: KModel size mismatch");
-  CK(cudaSetDevice(h->device));
+  DevGuard guard(h->device);
   CK(cudaMemcpy(h->d_model, kmodel, sizeof(KModel), cudaMemcpyHostToDevice));
+  return CEMK_OK;
+}
+int cemk_set_order(cemk_handle* h, int ncoef) {
+  if (!h) return set_err(CEMK_ERR_ARG, "cemk_set_order: null handle");
+  if (ncoef < MINCOEF || ncoef > MAXCOEF) return set_err(CEMK_ERR_ARG, "cemk_set_order: coefficients per DOF out of range [4, 16]");
+  DevGuard guard(h->device);
+  if (h->d_G) { CK(cudaFree(h->d_G)); h->d_G = nullptr; }     // the horizon tables belong to the old order
+  h->T = 0;
+  h->ncoef = ncoef; h->nvar = KM_NL * ncoef;
   return CEMK_OK;
 }
 int cemk_set_horizon(cemk_handle* h, int T, const float* G, const float* Kpp, const float* Kpe, const float* bounds3) {
   if (!h || !G || !Kpp || !Kpe || !bounds3) return set_err(CEMK_ERR_ARG, "cemk_set_horizon: null argument");
   if (T < 2 || T > 1024) return set_err(CEMK_ERR_ARG, "cemk_set_horizon: T out of range [2, 1024]");
-  CK(cudaSetDevice(h->device));
+  DevGuard guard(h->device);
+  const int nc = h->ncoef;
   if (h->d_G) { CK(cudaFree(h->d_G)); h->d_G = nullptr; }
-  CK(cudaMalloc(&h->d_G, sizeof(float) * 3 * T * NCOEF));
-  CK(cudaMemcpy(h->d_G, G, sizeof(float) * 3 * T * NCOEF, cudaMemcpyHostToDevice));
-  float kc[179];
-  memcpy(kc, Kpp, 121 * 4); memcpy(kc + 121, Kpe, 55 * 4); memcpy(kc + 176, bounds3, 12);
-  CK(cudaMemcpy(h->d_K, kc, sizeof kc, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&h->d_G, sizeof(float) * 3 * T * nc));
+  CK(cudaMemcpy(h->d_G, G, sizeof(float) * 3 * T * nc, cudaMemcpyHostToDevice));
+  float kc[MAXCOEF * MAXCOEF + 5 * MAXCOEF + 3];
+  memcpy(kc, Kpp, nc * nc * 4); memcpy(kc + nc * nc, Kpe, nc * 5 * 4); memcpy(kc + nc * nc + nc * 5, bounds3, 12);
+  CK(cudaMemcpy(h->d_K, kc, (nc * nc + nc * 5 + 3) * sizeof(float), cudaMemcpyHostToDevice));
   h->T = T;
-  const int smem = (3 * T * 12 + NCOEF * 12 + 60 + PROJ_SLICES * 22 * 32) * (int)sizeof(float);
-  CK(cudaFuncSetAttribute(k_project, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  int smem = 0;
+  CEMK_FOR_NCOEF(nc, { smem = project_smem<NC>(T); CK(cudaFuncSetAttribute(k_project<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); });
+  if (smem > 227 * 1024) return set_err(CEMK_ERR_ARG, "cemk_set_horizon: horizon too long for the projection kernel's shared memory");
   return CEMK_OK;
 }
 
 int cemk_sample(cemk_handle* h, int B, const float* z, const float* mean, const float* cov, float* chol_ws, float* xi, void* stream) {
   if (!h || !z || !mean || !cov || !chol_ws || !xi || B <= 0) return set_err(CEMK_ERR_ARG, "cemk_sample: bad argument");
+  DevGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
-  k_chol66<<<1, 256, 0, st>>>(cov, chol_ws);
-  k_sample<<<(B + 3) / 4, 256, 0, st>>>(B, z, mean, chol_ws, xi);
+  k_chol66<<<1, 256, 0, st>>>(h->nvar, cov, chol_ws);
+  k_sample<<<(B + 3) / 4, 256, 0, st>>>(B, h->nvar, z, mean, chol_ws, xi);
   h->launches += 2;
   CK(cudaPeekAtLastError());
   return CEMK_OK;
@@ -608,6 +656,7 @@ int cemk_sample(cemk_handle* h, int B, const float* z, const float* mean, const 
 int cemk_jax_normal(cemk_handle* h, unsigned key0, unsigned key1, int original, unsigned total, unsigned offset, unsigned count,
                     float* out, void* stream) {
   if (!h || !out || count == 0 || offset > total || count > total - offset) return set_err(CEMK_ERR_ARG, "cemk_jax_normal: bad argument");
+  DevGuard guard(h->device);
   k_jax_normal<<<(count + 255) / 256, 256, 0, (cudaStream_t)stream>>>(key0, key1, original, total, offset, count, out);
   h->launches += 1;
   CK(cudaPeekAtLastError());
@@ -616,9 +665,11 @@ int cemk_jax_normal(cemk_handle* h, unsigned key0, unsigned key1, int original, 
 
 int cemk_project(cemk_handle* h, int B, int iters, const float* xi, const float* state_term, float* xi_f, float* thetadot, void* stream) {
   if (!h || !xi || !state_term || !xi_f || B <= 0 || iters < 1) return set_err(CEMK_ERR_ARG, "cemk_project: bad argument");
+  DevGuard guard(h->device);
   if (!h->d_G) return set_err(CEMK_ERR_ARG, "cemk_project: cemk_set_horizon has not been called");
-  const int T = h->T, smem = (3 * T * 12 + NCOEF * 12 + 60 + PROJ_SLICES * 22 * 32) * (int)sizeof(float);
-  k_project<<<(B * 6 + 31) / 32, 32 * PROJ_SLICES, smem, (cudaStream_t)stream>>>(B, T, iters, h->d_G, h->d_K, xi, state_term, xi_f, thetadot);
+  const int T = h->T;
+  CEMK_FOR_NCOEF(h->ncoef, (k_project<NC><<<(B * 6 + 31) / 32, 32 * PROJ_SLICES, project_smem<NC>(T), (cudaStream_t)stream>>>(
+                                B, T, iters, h->d_G, h->d_K, xi, state_term, xi_f, thetadot)));
   h->launches += 1;
   CK(cudaPeekAtLastError());
   return CEMK_OK;
@@ -629,10 +680,10 @@ int cemk_rollout_cost(cemk_handle* h, int B, int T, const float* thetadot, const
                       float* eef_rot, float* collision, float* qacc, int* flags, void* stream) {
   if (!h || !thetadot || !q0 || !v0 || !target_pos || !target_rot || !theta || !cost4 || B <= 0 || T <= 0)
     return set_err(CEMK_ERR_ARG, "cemk_rollout_cost: bad argument");
+  DevGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   if (!flags) {
     if (h->flags_cap < B) {
-      CK(cudaSetDevice(h->device));
       if (h->d_flags) CK(cudaFree(h->d_flags));
       CK(cudaMalloc(&h->d_flags, sizeof(int) * B));
       h->flags_cap = B;
@@ -644,7 +695,6 @@ int cemk_rollout_cost(cemk_handle* h, int B, int T, const float* thetadot, const
   a.w_pos = w_pos; a.w_rot = w_rot; a.w_col = w_col;
   a.theta = theta; a.cost4 = cost4; a.eef_pos = eef_pos; a.eef_rot = eef_rot; a.collision = collision; a.qacc = qacc; a.flags = flags;
   if (h->prevd_cap < B) {
-    CK(cudaSetDevice(h->device));
     if (h->d_prevd) CK(cudaFree(h->d_prevd));
     CK(cudaMalloc(&h->d_prevd, sizeof(float) * (size_t)B * 2 * KM_NPASS * KW));
     if (h->d_ovf) CK(cudaFree(h->d_ovf));
@@ -700,6 +750,7 @@ int cemk_cost_batch(cemk_handle* h, int B, int T, int nslot, const float* eef_po
                     const float* target_pos, const float* target_rot, float w_pos, float w_rot, float w_col, float* cost4, void* stream) {
   if (!h || !eef_pos || !eef_rot || !collision || !target_pos || !target_rot || !cost4 || B <= 0 || T <= 0 || nslot <= 0)
     return set_err(CEMK_ERR_ARG, "cemk_cost_batch: bad argument");
+  DevGuard guard(h->device);
   k_cost_batch<<<(B * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(B, T, nslot, eef_pos, eef_rot, collision, target_pos, target_rot, w_pos, w_rot, w_col, cost4);
   h->launches += 1;
   CK(cudaPeekAtLastError());
@@ -725,14 +776,15 @@ static int next_pow2(int n) { int p = 1; while (p < n) p <<= 1; return p; }
 int cemk_argsort_topk(cemk_handle* h, int n, const float* cost, int cost_stride, int idx_base, unsigned long long* keys_ws,
                       int* idx_sorted, int k, const float* xi, float* xi_elite, float* cost_elite, void* stream) {
   if (!h || !cost || !keys_ws || n <= 0 || k < 0 || k > n || cost_stride < 1) return set_err(CEMK_ERR_ARG, "cemk_argsort_topk: bad argument");
+  DevGuard guard(h->device);
   if (k > 0 && (!xi || !xi_elite || !cost_elite)) return set_err(CEMK_ERR_ARG, "cemk_argsort_topk: elite buffers missing");
   cudaStream_t st = (cudaStream_t)stream;
   const int np2 = next_pow2(n);
   k_make_keys<<<(np2 + 255) / 256, 256, 0, st>>>(n, np2, cost, cost_stride, keys_ws);
   h->launches += 1;
   sort_keys(h, np2, keys_ws, st);
-  const int work = n > k * NVAR ? n : k * NVAR;
-  k_finish_sort<<<(work + 255) / 256, 256, 0, st>>>(n, keys_ws, idx_base, idx_sorted, k, cost, cost_stride, xi, xi_elite, cost_elite, nullptr, nullptr);
+  const int NVAR = h->nvar, work = n > k * NVAR ? n : k * NVAR;
+  k_finish_sort<<<(work + 255) / 256, 256, 0, st>>>(NVAR, n, keys_ws, idx_base, idx_sorted, k, cost, cost_stride, xi, xi_elite, cost_elite, nullptr, nullptr);
   h->launches += 1;
   CK(cudaPeekAtLastError());
   return CEMK_OK;
@@ -742,6 +794,7 @@ int cemk_merge_elites(cemk_handle* h, int n, const float* cost, const int* gidx,
                       float* xi_elite, float* cost_elite, int* gidx_elite, void* stream) {
   if (!h || !cost || !gidx || !xi || !keys_ws || !xi_elite || !cost_elite || !gidx_elite || n <= 0 || k <= 0 || k > n)
     return set_err(CEMK_ERR_ARG, "cemk_merge_elites: bad argument");
+  DevGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   const int np2 = next_pow2(n);
   // candidate rows arrive rank-major and (cost, index)-sorted within a rank, so the row number breaks
@@ -749,7 +802,7 @@ int cemk_merge_elites(cemk_handle* h, int n, const float* cost, const int* gidx,
   k_make_keys<<<(np2 + 255) / 256, 256, 0, st>>>(n, np2, cost, 1, keys_ws);
   h->launches += 1;
   sort_keys(h, np2, keys_ws, st);
-  k_finish_sort<<<(k * NVAR + 255) / 256, 256, 0, st>>>(0, keys_ws, 0, nullptr, k, cost, 1, xi, xi_elite, cost_elite, gidx, gidx_elite);
+  k_finish_sort<<<(k * h->nvar + 255) / 256, 256, 0, st>>>(h->nvar, 0, keys_ws, 0, nullptr, k, cost, 1, xi, xi_elite, cost_elite, gidx, gidx_elite);
   h->launches += 1;
   CK(cudaPeekAtLastError());
   return CEMK_OK;
@@ -759,12 +812,13 @@ int cemk_topk_pack(cemk_handle* h, int n, const float* cost, int cost_stride, in
                    const float* xi, float* pack, void* stream) {
   if (!h || !cost || !keys_ws || !xi || !pack || n <= 0 || k <= 0 || k > n || cost_stride < 1)
     return set_err(CEMK_ERR_ARG, "cemk_topk_pack: bad argument");
+  DevGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   const int np2 = next_pow2(n);
   k_make_keys<<<(np2 + 255) / 256, 256, 0, st>>>(n, np2, cost, cost_stride, keys_ws);
   h->launches += 1;
   sort_keys(h, np2, keys_ws, st);
-  k_pack_sorted<<<(k * PACKW + 255) / 256, 256, 0, st>>>(keys_ws, idx_base, k, cost, cost_stride, xi, pack);
+  k_pack_sorted<<<(k * (h->nvar + 2) + 255) / 256, 256, 0, st>>>(h->nvar, keys_ws, idx_base, k, cost, cost_stride, xi, pack);
   h->launches += 1;
   CK(cudaPeekAtLastError());
   return CEMK_OK;
@@ -774,14 +828,15 @@ int cemk_merge_packed(cemk_handle* h, int n, const float* packed, unsigned long 
                       float* cost_elite, int* gidx_elite, void* stream) {
   if (!h || !packed || !keys_ws || !xi_elite || !cost_elite || !gidx_elite || n <= 0 || k <= 0 || k > n)
     return set_err(CEMK_ERR_ARG, "cemk_merge_packed: bad argument");
+  DevGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   const int np2 = next_pow2(n);
   // candidate rows arrive rank-major and (cost, index)-sorted within a rank, so the row number breaks
   // cost ties exactly like the global sample index does
-  k_make_keys<<<(np2 + 255) / 256, 256, 0, st>>>(n, np2, packed + NVAR, PACKW, keys_ws);
+  k_make_keys<<<(np2 + 255) / 256, 256, 0, st>>>(n, np2, packed + h->nvar, h->nvar + 2, keys_ws);
   h->launches += 1;
   sort_keys(h, np2, keys_ws, st);
-  k_unpack_sorted<<<(k * PACKW + 255) / 256, 256, 0, st>>>(keys_ws, k, packed, xi_elite, cost_elite, gidx_elite);
+  k_unpack_sorted<<<(k * (h->nvar + 2) + 255) / 256, 256, 0, st>>>(h->nvar, keys_ws, k, packed, xi_elite, cost_elite, gidx_elite);
   h->launches += 1;
   CK(cudaPeekAtLastError());
   return CEMK_OK;
@@ -791,7 +846,8 @@ int cemk_mean_cov(cemk_handle* h, int k, const float* cost_elite, const float* x
                   float lamda, float alpha_mean, float alpha_cov, float* mean_out, float* cov_out, void* stream) {
   if (!h || !cost_elite || !xi_elite || !mean_prev || !cov_prev || !mean_out || !cov_out || k <= 0)
     return set_err(CEMK_ERR_ARG, "cemk_mean_cov: bad argument");
-  k_mean_cov<<<NVAR, 128, 0, (cudaStream_t)stream>>>(k, cost_elite, xi_elite, mean_prev, cov_prev, lamda, alpha_mean, alpha_cov, mean_out, cov_out);
+  DevGuard guard(h->device);
+  k_mean_cov<<<h->nvar, 128, 0, (cudaStream_t)stream>>>(h->nvar, k, cost_elite, xi_elite, mean_prev, cov_prev, lamda, alpha_mean, alpha_cov, mean_out, cov_out);
   h->launches += 1;
   CK(cudaPeekAtLastError());
   return CEMK_OK;
@@ -808,7 +864,7 @@ int cemk_set_option(cemk_handle* h, const char* name, int value) {
 
 int cemk_fp32_fma_peak(cemk_handle* h, double* tflops) {
   if (!h || !tflops) return set_err(CEMK_ERR_ARG, "cemk_fp32_fma_peak: null argument");
-  CK(cudaSetDevice(h->device));
+  DevGuard guard(h->device);
   const int nsm = h->num_sms > 0 ? h->num_sms : 148, blocks = nsm * 8, threads = 256, iters = 4096;
   float* d = nullptr;
   CK(cudaMalloc(&d, sizeof(float) * blocks * threads));

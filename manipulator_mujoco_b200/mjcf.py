@@ -432,42 +432,19 @@ def compile_mjcf(xml_path) -> ModelConsts:
             body_mass[bi], body_ipos[bi], body_inertia[bi] = M, com, I
 
     # ---- collision geoms and the static candidate pair list ----
-    col = [gi for gi, g in enumerate(geoms) if (g["contype"] or g["conaffinity"])
-           and g["type"] in (GEOM_PLANE, GEOM_CAPSULE, GEOM_BOX)]
-    for gi, g in enumerate(geoms):
-        if (g["contype"] or g["conaffinity"]) and gi not in col:
-            raise NotImplementedError(f"collision geom type {g['typename']}")
-    pairs = []
-    for ia, ga in enumerate(col):
-        for gb in col[ia + 1:]:
-            A, Bg = geoms[ga], geoms[gb]
-            if not ((A["contype"] & Bg["conaffinity"]) or (Bg["contype"] & A["conaffinity"])):
-                continue
-            w1, w2 = body_weldid[A["body"]], body_weldid[Bg["body"]]
-            if w1 == w2:
-                continue
-            p1 = body_weldid[bodies[w1]["parent"]]
-            p2 = body_weldid[bodies[w2]["parent"]]
-            if w1 != 0 and w2 != 0 and (p1 == w2 or p2 == w1):
-                continue
-            g1, g2 = (ga, gb) if A["type"] <= Bg["type"] else (gb, ga)
-            key = (geoms[g1]["type"], geoms[g2]["type"])
-            if key not in PAIR_SLOTS:
-                raise NotImplementedError(f"collision pair types {key}")
-            pairs.append((key, g1, g2))
     # <contact><exclude body1=.. body2=../> (the planner scene ships them commented out, scene.xml:27-45)
     names = [b["name"] for b in bodies]
-    excl = set()
+    excl = []
     for c in root.findall("contact"):
         for e in c.findall("exclude"):
-            b1, b2 = names.index(e.get("body1")), names.index(e.get("body2"))
-            excl.add((min(b1, b2), max(b1, b2)))
-    pairs = [p for p in pairs if (min(geoms[p[1]]["body"], geoms[p[2]]["body"]), max(geoms[p[1]]["body"], geoms[p[2]]["body"])) not in excl]
-    pairs.sort(key=lambda p: (p[0], p[1], p[2]))
-    pair_geom = np.array([[p[1], p[2]] for p in pairs], dtype=np.int32).reshape(-1, 2)
-    pair_type = np.array([[p[0][0], p[0][1]] for p in pairs], dtype=np.int32).reshape(-1, 2)
-    pair_nslot = np.array([PAIR_SLOTS[p[0]] for p in pairs], dtype=np.int32)
-    pair_slotadr = np.concatenate([[0], np.cumsum(pair_nslot)[:-1]]).astype(np.int32)
+            excl.append((names.index(e.get("body1")), names.index(e.get("body2"))))
+    for g in geoms:
+        if (g["contype"] or g["conaffinity"]) and g["type"] not in (GEOM_PLANE, GEOM_CAPSULE, GEOM_BOX):
+            raise NotImplementedError(f"collision geom type {g['typename']}")
+    pair_geom, pair_type, pair_nslot, pair_slotadr, collides = _candidate_pairs(
+        [g["type"] for g in geoms], [g["body"] for g in geoms], [g["contype"] for g in geoms], [g["conaffinity"] for g in geoms],
+        body_weldid, [b["parent"] for b in bodies], excl)
+    col = [gi for gi in range(ngeom) if collides[gi]]
 
     d = dict(
         xml=os.path.basename(xml_path), nq=nq, nv=nv, nbody=nbody, njnt=njnt, ngeom=ngeom,
@@ -640,6 +617,104 @@ def exclude_body_pairs(mc: ModelConsts, body_pairs) -> ModelConsts:
     d["ncon"] = int(d["pair_nslot"].sum())
     return ModelConsts(d)
 
+
+def _candidate_pairs(geom_type, geom_body, contype, conaffinity, body_weldid, body_parent, excluded=()):
+    """MJX's static candidate pair list (collision_driver: same weld body / parent-child weld bodies / contype-conaffinity
+    filters; pairs grouped by geom-type pair, geom1 = the lower type): pair_geom, pair_type, pair_nslot, pair_slotadr, collides."""
+    col = [g for g in range(len(geom_type)) if (contype[g] or conaffinity[g]) and geom_type[g] in (GEOM_PLANE, GEOM_CAPSULE, GEOM_BOX)]
+    for g in range(len(geom_type)):
+        if (contype[g] or conaffinity[g]) and g not in col:
+            raise NotImplementedError(f"collision geom type {int(geom_type[g])}")
+    excl = {(min(a, b), max(a, b)) for a, b in excluded}
+    pairs = []
+    for ia, ga in enumerate(col):
+        for gb in col[ia + 1:]:
+            if not ((contype[ga] & conaffinity[gb]) or (contype[gb] & conaffinity[ga])):
+                continue
+            w1, w2 = body_weldid[geom_body[ga]], body_weldid[geom_body[gb]]
+            if w1 == w2:
+                continue
+            p1, p2 = body_weldid[body_parent[w1]], body_weldid[body_parent[w2]]
+            if w1 != 0 and w2 != 0 and (p1 == w2 or p2 == w1):
+                continue
+            if (min(geom_body[ga], geom_body[gb]), max(geom_body[ga], geom_body[gb])) in excl:
+                continue
+            g1, g2 = (ga, gb) if geom_type[ga] <= geom_type[gb] else (gb, ga)
+            key = (int(geom_type[g1]), int(geom_type[g2]))
+            if key not in PAIR_SLOTS:
+                raise NotImplementedError(f"collision pair types {key}")
+            pairs.append((key, g1, g2))
+    pairs.sort(key=lambda p: (p[0], p[1], p[2]))
+    pair_geom = np.array([[p[1], p[2]] for p in pairs], dtype=np.int32).reshape(-1, 2)
+    pair_type = np.array([[p[0][0], p[0][1]] for p in pairs], dtype=np.int32).reshape(-1, 2)
+    pair_nslot = np.array([PAIR_SLOTS[p[0]] for p in pairs], dtype=np.int32)
+    pair_slotadr = np.concatenate([[0], np.cumsum(pair_nslot)[:-1]]).astype(np.int32)
+    collides = np.array([g in col for g in range(len(geom_type))], dtype=np.int32)
+    return pair_geom, pair_type, pair_nslot, pair_slotadr, collides
+
+
+def from_mjmodel(m) -> ModelConsts:
+    """Import a compiled ``mujoco.MjModel`` instead of compiling the MJCF here: the same
+    ModelConsts, taken from MuJoCo's own compiler output, including its mesh inertias, ``body_invweight0`` /
+    ``dof_invweight0`` and ``stat.meaninertia``.  Only attribute access on ``m`` is used (``mujoco`` itself is not
+    imported), so the day ``mujoco.mjx`` is installable this is what makes tests/test_against_mjx.py compare like with like.
+    The candidate pair list is rebuilt with MJX's rules (``_candidate_pairs``); excludes come from ``m.exclude_signature``."""
+    nbody, njnt, ngeom, nsite = int(m.nbody), int(m.njnt), int(m.ngeom), int(m.nsite)
+    A = lambda x, dt=np.float64: np.array(x, dtype=dt)
+    name = lambda kind, i: getattr(m, kind)(i).name
+    jnt_type = A(m.jnt_type, np.int32)
+    if not np.all(np.isin(jnt_type, (JNT_FREE, JNT_HINGE))):
+        raise NotImplementedError("only hinge and free joints are supported")
+    jnt_body = A(m.jnt_bodyid, np.int32)
+    jnt_dofadr = A(m.jnt_dofadr, np.int32)
+    body_jntadr = A(m.body_jntadr, np.int32)
+    if np.any(A(m.body_jntnum, np.int32) > 1):
+        raise NotImplementedError("more than one joint per body")
+    body_iquat = A(m.body_iquat)
+    body_inertia = np.zeros((nbody, 3, 3))
+    for b in range(nbody):                                   # MuJoCo stores the principal inertia and its frame
+        R = quat_to_mat(body_iquat[b])
+        body_inertia[b] = R @ np.diag(A(m.body_inertia)[b]) @ R.T
+    geom_type = A(m.geom_type, np.int32)
+    geom_body = A(m.geom_bodyid, np.int32)
+    body_weldid, body_parent = A(m.body_weldid, np.int32), A(m.body_parentid, np.int32)
+    excluded = [(int(s) >> 16, int(s) & 0xFFFF) for s in np.atleast_1d(getattr(m, "exclude_signature", []))]
+    pair_geom, pair_type, pair_nslot, pair_slotadr, collides = _candidate_pairs(
+        geom_type, geom_body, A(m.geom_contype, np.int32), A(m.geom_conaffinity, np.int32), body_weldid, body_parent, excluded)
+    flags = int(m.opt.disableflags)
+    opt = {"timestep": float(m.opt.timestep), "iterations": int(m.opt.iterations), "ls_iterations": int(m.opt.ls_iterations),
+           "tolerance": float(m.opt.tolerance), "ls_tolerance": float(m.opt.ls_tolerance), "impratio": float(m.opt.impratio),
+           "gravity": [float(g) for g in m.opt.gravity],
+           "eulerdamp": 0 if flags & (1 << 14) else 1,            # mjDSBL_EULERDAMP
+           "actuation": 0 if flags & (1 << 10) else 1,            # mjDSBL_ACTUATION
+           "integrator": {0: "Euler", 1: "RK4", 2: "implicit", 3: "implicitfast"}.get(int(m.opt.integrator), "?")}
+    if opt["integrator"] != "Euler":
+        raise NotImplementedError("only the Euler integrator is supported")
+    d = dict(
+        xml="<mujoco.MjModel>", nq=int(m.nq), nv=int(m.nv), nbody=nbody, njnt=njnt, ngeom=ngeom, opt=opt,
+        body_names=[name("body", i) for i in range(nbody)],
+        body_parent=body_parent, body_pos=A(m.body_pos), body_quat=A(m.body_quat),
+        body_mass=A(m.body_mass), body_ipos=A(m.body_ipos), body_inertia=body_inertia,
+        body_gravcomp=A(m.body_gravcomp), body_weldid=body_weldid, body_rootid=A(m.body_rootid, np.int32),
+        body_jntadr=body_jntadr, body_dofadr=A(m.body_dofadr, np.int32), body_dofnum=A(m.body_dofnum, np.int32),
+        jnt_names=[name("joint", i) for i in range(njnt)],
+        jnt_type=jnt_type, jnt_body=jnt_body, jnt_axis=A(m.jnt_axis).reshape(-1, 3), jnt_pos=A(m.jnt_pos).reshape(-1, 3),
+        jnt_range=A(m.jnt_range).reshape(-1, 2), jnt_limited=A(m.jnt_limited, np.int32),
+        jnt_armature=A(m.dof_armature)[jnt_dofadr], jnt_damping=A(m.dof_damping)[jnt_dofadr], jnt_margin=A(m.jnt_margin),
+        jnt_qposadr=A(m.jnt_qposadr, np.int32), jnt_dofadr=jnt_dofadr,
+        geom_names=[name("geom", i) for i in range(ngeom)],
+        geom_type=geom_type, geom_body=geom_body, geom_pos=A(m.geom_pos), geom_quat=A(m.geom_quat), geom_size=A(m.geom_size),
+        geom_friction=A(m.geom_friction), geom_solref=A(m.geom_solref), geom_solimp=A(m.geom_solimp), geom_margin=A(m.geom_margin),
+        geom_condim=A(m.geom_condim, np.int32), geom_collides=collides,
+        site_names=[name("site", i) for i in range(nsite)], site_body=A(m.site_bodyid, np.int32), site_pos=A(m.site_pos).reshape(-1, 3),
+        pair_geom=pair_geom, pair_type=pair_type, pair_nslot=pair_nslot, pair_slotadr=pair_slotadr, ncon=int(pair_nslot.sum()),
+        qpos0=A(m.qpos0), dof_invweight0=A(m.dof_invweight0), body_invweight0=A(m.body_invweight0).reshape(nbody, 2),
+        meaninertia=float(m.stat.meaninertia),
+    )
+    return ModelConsts(d)
+
+
+ModelConsts.from_mjmodel = staticmethod(from_mjmodel)
 
 DEFAULT_ASSET = os.path.join(os.path.dirname(__file__), "assets", "scene_a.json")
 

@@ -34,7 +34,7 @@ import torch
 from . import _lib, jax_prng, parallel
 from .bernstein import bernstein_coeff_ordern_new
 from .kmodel import KModel, build_kmodel
-from .mjcf import ModelConsts, exclude_body_pairs, host_kinematics, load_model
+from .mjcf import ModelConsts, exclude_body_pairs, host_kinematics, load_model, quat_mul, quat_normalize
 
 _VP = C.c_void_p
 
@@ -90,7 +90,7 @@ class cem_planner:
 
     def __init__(self, num_dof=None, num_batch=None, num_steps=None, timestep=None, maxiter_cem=None, num_elite=None,
                  w_pos=None, w_rot=None, w_col=None, maxiter_projection=None, *, model_path=None, device=None,
-                 process_group=None, seed=0, contact_exclude=None, threefry_partitionable=True):
+                 process_group=None, seed=0, contact_exclude=None, threefry_partitionable=True, bernstein_order=10):
         if not torch.cuda.is_available():
             raise RuntimeError("cem_planner needs a CUDA device (B200 / sm_100a); there is no CPU fallback")
         self._lib = _lib.load()
@@ -125,7 +125,11 @@ class cem_planner:
         tot_time = np.linspace(0, self.t_fin, self.num)
         self.tot_time = tot_time
         tc = tot_time.reshape(self.num, 1)
-        self.P, self.Pdot, self.Pddot = bernstein_coeff_ordern_new(10, tc[0], tc[-1], tc)
+        # the reference hard-codes order 10 (mjx_planner.py:40); `bernstein_order` is the order-n extension of SURVEY 8 f.4
+        if not 3 <= int(bernstein_order) <= 15:
+            raise ValueError("bernstein_order must be in [3, 15]")
+        self.bernstein_order = int(bernstein_order)
+        self.P, self.Pdot, self.Pddot = bernstein_coeff_ordern_new(self.bernstein_order, tc[0], tc[-1], tc)
         f32 = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32, device=dev)
         self.P_jax, self.Pdot_jax, self.Pddot_jax = f32(self.P), f32(self.Pdot), f32(self.Pddot)
         self.nvar_single = self.P.shape[1]
@@ -182,9 +186,14 @@ class cem_planner:
         h = _VP()
         _lib.check(self._lib.cemk_create(C.byref(km), C.sizeof(km), dev.index or 0, C.byref(h)), self._lib)
         self._h = h
+        _lib.check(self._lib.cemk_set_order(self._h, self.nvar_single), self._lib)
         self._set_horizon(Q_inv)
         # mjx.forward at qpos0 (:107): its qacc becomes the first warm start of every rollout
         self.mjx_data = self._initial_forward()
+
+        # attributes the notebooks touch (mjx_planner.py:98,108): the vmapped outer product and the jitted single step
+        self.vec_product = lambda diffs, d: self._t(d).reshape(-1, 1, 1) * torch.einsum("ki,kj->kij", self._t(diffs), self._t(diffs))
+        self.jit_step = self._single_step
 
         self._z_cache = {}
         self._split_cache = {}
@@ -267,6 +276,44 @@ class cem_planner:
             self.mjx_model.warm0[i] = float(warm[i])
         _lib.check(self._lib.cemk_set_model(self._h, C.byref(self.mjx_model), C.sizeof(self.mjx_model)), self._lib)
         return dict(qpos=self._mc.qpos0.copy(), qvel=np.zeros(12), qacc=warm.copy(), qacc_warmstart=warm.copy())
+
+    def _single_step(self, model, data):
+        """``jax.jit(mjx.step)(mjx_model, mjx_data)`` (mjx_planner.py:108,256) for one environment: ``data`` is a dict with
+        qpos[13], qvel[12], qacc_warmstart[12] (``self.mjx_data`` has that form); returns the stepped dict plus qacc.
+        Runs the rollout kernel with B = 1, T = 1 from that state (the free box included), like the closed-loop plant."""
+        km = type(self.mjx_model)()
+        C.memmove(C.byref(km), C.byref(self.mjx_model), C.sizeof(km))
+        qpos, qvel = np.asarray(data["qpos"], dtype=np.float64), np.asarray(data["qvel"], dtype=np.float64)
+        warm = np.asarray(data.get("qacc_warmstart", np.zeros(12)), dtype=np.float64)
+        for i in range(13):
+            km.qpos0[i] = qpos[i]
+        for i in range(12):
+            km.qvel0[i], km.warm0[i] = qvel[i], warm[i]
+        dev = self.device
+        h = _VP()
+        _lib.check(self._lib.cemk_create(C.byref(km), C.sizeof(km), dev.index or 0, C.byref(h)), self._lib)
+        try:
+            td = self._t(qvel[:6]).reshape(1, 6)
+            q0, v0 = self._t(qpos[:6]), self._t(qvel[:6])
+            tp, tr = torch.zeros(3, device=dev), torch.tensor([1.0, 0, 0, 0], device=dev)
+            theta, cost4, qacc = torch.empty(1, 6, device=dev), torch.empty(1, 4, device=dev), torch.empty(1, 1, 12, device=dev)
+            _lib.check(self._lib.cemk_rollout_cost(h, 1, 1, _ptr(td), _ptr(q0), _ptr(v0), _ptr(tp), _ptr(tr), 0.0, 0.0, 0.0, _ptr(theta),
+                                                   _ptr(cost4), None, None, None, _ptr(qacc), None, self._stream()), self._lib)
+            a = qacc[0, 0].cpu().numpy().astype(np.float64)
+        finally:
+            self._lib.cemk_destroy(h)
+        dt = float(self.t)
+        v = qvel + dt * a
+        q = qpos.copy()
+        q[:9] += dt * v[:9]
+        w = v[9:12]
+        n = np.linalg.norm(w)
+        if n > 0:
+            ang = dt * n
+            b = np.concatenate([[np.cos(ang / 2)], np.sin(ang / 2) * w / n])
+            p = q[9:13]
+            q[9:13] = quat_normalize(quat_mul(p, b))
+        return dict(qpos=q, qvel=v, qacc=a, qacc_warmstart=a.copy())
 
     def print_info(self):
         if self.rank == 0:
@@ -566,7 +613,7 @@ class cem_planner:
         # keyed on those and dropped when one of them changes.
         w = self.cost_weights
         gkey = (m, int(self.maxiter_projection), float(w['w_pos']), float(w['w_rot']), float(w['w_col']),
-                tuple(int(x) for x in jax_prng.as_key(self.key)), self._partitionable, T, Bl, int(self.ellite_num))
+                tuple(int(x) for x in jax_prng.as_key(self.key)), self._partitionable, T, Bl, int(self.ellite_num), nv)
         if self._graph is not None and gkey != self._graph_key:
             torch.cuda.current_stream(dev).synchronize()
             self._graph, self._graph_out, self._eager_ticks = None, None, 0

@@ -37,3 +37,16 @@ def test_known_answers():
     np.testing.assert_allclose(Pdd[0, :3], [140.625, -281.25, 140.625], atol=1e-10)
     # the grid spacing is num*t/(num-1), not t (mjx_planner.py:36)
     assert abs((tt[1] - tt[0])[0] - 16 * 0.05 / 15) < 1e-15
+
+
+@pytest.mark.parametrize("n", [5, 8, 12, 15])
+def test_other_orders_match_reference_golden(n):
+    """bernstein_coeff_ordern_new(n, ...) of the reference for the orders of the order-n extension (cem_planner(bernstein_order=n))."""
+    T, dt = 16, 0.05
+    tt = np.linspace(0, T * dt, T).reshape(T, 1)
+    for fn in (bernstein_coeff_ordern_new, bernstein_coeff_ordern):
+        P, Pd, Pdd = fn(n, tt[0], tt[-1], tt)
+        for name, a in (("P", P), ("Pdot", Pd), ("Pddot", Pdd)):
+            ref = G[f"{name}_n{n}"]
+            assert a.shape == ref.shape == (T, n + 1)
+            np.testing.assert_allclose(a, ref, rtol=0, atol=1e-12 * max(1.0, np.abs(ref).max()))

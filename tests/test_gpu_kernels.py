@@ -175,3 +175,67 @@ def test_packed_topk_and_merge_equal_global_stable_topk(planner):
     np.testing.assert_array_equal(ge.cpu().numpy(), rg)
     np.testing.assert_array_equal(xe.cpu().numpy(), rx)
     np.testing.assert_array_equal(ce.cpu().numpy().view(np.int32), rc.view(np.int32))
+
+
+def test_notebook_attributes_jit_step_and_vec_product(planner, oracle64):
+    """mjx_planner.py:98,108: `vec_product` (vmapped outer product) and `jit_step` (one mjx.step of one environment),
+    touched by mpc_planning.ipynb."""
+    rng = np.random.default_rng(2)
+    diffs, d = rng.normal(size=(5, 66)).astype(np.float32), rng.uniform(size=5).astype(np.float32)
+    vp = planner.vec_product(diffs, d).cpu().numpy()
+    np.testing.assert_allclose(vp, d[:, None, None] * diffs[:, :, None] * diffs[:, None, :], rtol=1e-6)
+    data = dict(planner.mjx_data)
+    data["qpos"] = data["qpos"].copy()
+    data["qpos"][:6] = Q0
+    data["qvel"] = np.zeros(12)
+    data["qvel"][:6] = [0.2, -0.1, 0.3, 0.0, 0.1, -0.2]
+    out = planner.jit_step(planner.mjx_model, data)
+    ref = oracle64.forward(data["qpos"], data["qvel"], data["qacc_warmstart"])
+    np.testing.assert_allclose(out["qacc"], ref["qacc"], atol=2e-3 * max(1.0, np.abs(ref["qacc"]).max()))
+    np.testing.assert_allclose(out["qvel"], data["qvel"] + 0.05 * out["qacc"], atol=1e-12)
+    np.testing.assert_allclose(out["qpos"][:9], data["qpos"][:9] + 0.05 * out["qvel"][:9], atol=1e-12)
+
+
+@pytest.mark.parametrize("order", [5, 8, 12, 15])
+def test_order_n_bernstein_pipeline(order):
+    """SURVEY 8 f.4 (order-n half): cem_planner(bernstein_order=n) -- sampling, projection filter + Bernstein evaluation,
+    elite selection and mean / covariance at nvar = 6 (n + 1), against the dense float64 restatement built with the same
+    order (oracle/planner_ref.py, whose basis is pinned to the reference's bernstein_coeff_ordern_new(n, ...) golden)."""
+    from manipulator_mujoco_b200 import cem_planner
+    from oracle.planner_ref import PlannerRef
+    B, T = 96, 16
+    nv = 6 * (order + 1)
+    pl = cem_planner(num_dof=6, num_batch=B, num_steps=T, timestep=0.05, maxiter_cem=2, num_elite=0.1, w_pos=20.0, w_rot=3.0,
+                     w_col=80.0, maxiter_projection=10, bernstein_order=order)
+    pr = PlannerRef(6, B, T, 0.05, 0.1, 20.0, 3.0, 80.0, 10, order=order)
+    assert pl.nvar == nv == pr.nvar and tuple(pl.A_thetadot.shape) == (6 * T, nv)
+    rng = np.random.default_rng(order)
+    A = rng.normal(size=(nv, nv))
+    cov = (A @ A.T / nv + np.eye(nv)).astype(np.float32)
+    mean = rng.normal(size=nv).astype(np.float32)
+    xi, key = pl.compute_xi_samples(3, mean, cov)
+    z = pl._normal(key).cpu().numpy().astype(np.float64)
+    ref_xi = pr.compute_xi_samples(z, mean.astype(np.float64), cov.astype(np.float64))
+    np.testing.assert_allclose(xi.cpu().numpy(), ref_xi, rtol=0, atol=3e-5)
+    st = pr.state_term(Q0, np.zeros(6), np.zeros(6), B)
+    xs = (rng.normal(size=(B, nv)) * 3).astype(np.float32)
+    xf, td = pl._project(xs, st, True)
+    ref_xf = pr.compute_projection_filter(xs.astype(np.float64), st)
+    np.testing.assert_allclose(xf.cpu().numpy(), ref_xf, rtol=0, atol=1e-4)
+    np.testing.assert_allclose(td.cpu().numpy(), ref_xf @ pr.A_thetadot.T, rtol=0, atol=1e-4)
+    k = pl.ellite_num
+    ce = np.sort(rng.uniform(200, 260, k)).astype(np.float32)
+    xe = rng.normal(size=(k, nv)).astype(np.float32)
+    m2, c2 = pl.compute_mean_cov(ce, mean, cov, xe)
+    rm, rc = pr.compute_mean_cov(ce.astype(np.float64), mean.astype(np.float64), cov.astype(np.float64), xe.astype(np.float64))
+    np.testing.assert_allclose(m2.cpu().numpy(), rm, rtol=0, atol=3e-5)
+    np.testing.assert_allclose(c2.cpu().numpy(), rc, rtol=0, atol=1e-4)
+    cost = rng.uniform(0, 10, B).astype(np.float32)
+    xi_e, idx, cost_e = pl.compute_ellite_samples(cost, xs)
+    order_ref = np.argsort(cost, kind="stable")
+    np.testing.assert_array_equal(idx.cpu().numpy(), order_ref)
+    np.testing.assert_array_equal(xi_e.cpu().numpy(), xs[order_ref[:k]])
+    # and the whole tick runs (two CEM iterations, graph capture on the third call)
+    for _ in range(3):
+        out = pl.compute_cem(np.zeros(nv), Q0, np.zeros(6), np.zeros(6), np.array([-0.3, -0.3, 0.5]), np.array([0.0, 1.0, 0.0, 0.0]))
+    assert out[6].shape == (nv,) and np.isfinite(out[0]).all() and out[4].shape == (T, 6)

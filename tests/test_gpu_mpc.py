@@ -5,19 +5,30 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def test_closed_loop_reaches_first_target(tmp_path):
+def test_closed_loop_reaches_targets_and_switches_like_the_recorded_run(tmp_path):
+    """The reference's canonical run (run_mpc_planner.py:7-44) against its own recording (data/cost_c.csv, cost_g.csv of
+    897 ticks, tests/golden/closed_loop_kat.npz): with MJX's has_support gate in capsule_box the loop reaches target_0
+    inside the position / rotation thresholds, switches to target_1 and reaches that too, and the best plan's collision
+    cost stays at the recording's magnitude while it approaches (recorded maximum over the whole run: 0.0208).  The
+    round-1 restatement without the gate stalled 12.5 cm short of target_0 for good (profiles/r2_closed_loop_legacy.json);
+    tests/test_oracle_pins.py::test_recorded_run_pins_capsule_box_far_field shows the same contradiction on the CPU."""
+    import os
+    from conftest import GOLDEN
     from manipulator_mujoco_b200.mpc_planner import run_cem_planner
     res = run_cem_planner(num_dof=6, num_batch=1000, num_steps=16, num_elite=0.05, timestep=0.05, maxiter_cem=3,
                           maxiter_projection=10, w_pos=20.0, w_rot=3.0, w_col=80.0, show_viewer=False, show_contact_points=False,
                           initial_qpos=[1.5, -1.8, 1.75, -1.25, -1.6, 0], target_names=["target_0", "target_1", "target_2", "home"],
                           cam_distance=4, position_threshold=0.05, rotation_threshold=0.1, save_data=True, data_dir=str(tmp_path),
-                          stop_at_final_target=True, max_ticks=120, verbose=False)
+                          stop_at_final_target=True, max_ticks=700, verbose=False)
     theta = np.array(res["theta"])
     assert theta.shape[1] == 6 and np.isfinite(theta).all()
-    g = np.array(res["cost_g"])
-    assert np.isfinite(g).all()
-    # the planner drives the tool towards target_0: the per-tick goal cost of the best sample falls
-    assert g[:100].min() < 0.75 * g[0]
+    assert np.isfinite(np.array(res["cost_g"])).all()
+    reached = dict((name, tick) for tick, name in res["switch_ticks"])
+    assert "target_0" in reached and reached["target_0"] < 200, res["switch_ticks"]           # measured: tick 123
+    assert "target_1" in reached and reached["target_1"] < 700, res["switch_ticks"]           # measured: tick 379 .. 477
+    rec = np.load(os.path.join(GOLDEN, "closed_loop_kat.npz"))["cost_c"]
+    c = np.array(res["cost_c"])[:reached["target_0"]]
+    assert np.median(c) < 2 * np.median(rec) + 0.01 and c.max() < 0.05                       # recorded: median 0.0037, max 0.0208
     # joint velocities applied to the plant respect the projection filter's velocity bound (v_max = 0.8)
     assert np.abs(np.array(res["thetadot"])).max() < 0.8 + 0.15
     # real-time budget of the reference loop: one tick <= timestep = 50 ms (mpc_planner.py:231-233)

@@ -94,3 +94,89 @@ def test_unsupported_models_are_refused(mc):
     bad.d["opt"] = dict(mc.opt, iterations=4)
     with pytest.raises(NotImplementedError):
         KM.build_kmodel(bad, 0.05)
+
+
+class _MockMjModel:
+    """An object with mujoco.MjModel's attribute names (the subset ModelConsts.from_mjmodel reads), filled from a compiled
+    ModelConsts: stands in for MuJoCo, which cannot be installed here."""
+
+    def __init__(self, mc):
+        import types
+        n = types.SimpleNamespace
+        self.nq, self.nv, self.nbody, self.njnt, self.ngeom, self.nsite = mc.nq, mc.nv, mc.nbody, mc.njnt, mc.ngeom, len(mc.site_names)
+        self.body_parentid, self.body_pos, self.body_quat, self.body_mass, self.body_ipos = mc.body_parent, mc.body_pos, mc.body_quat, mc.body_mass, mc.body_ipos
+        # MuJoCo stores principal inertias + their frame: diagonalise our full tensors
+        iq, diag = [], []
+        for I in mc.body_inertia:
+            w, V = np.linalg.eigh(I)
+            if np.linalg.det(V) < 0:
+                V[:, 0] = -V[:, 0]
+            tr = np.trace(V)                                      # rotation matrix -> quaternion (w, x, y, z)
+            qw = np.sqrt(max(0.0, 1 + tr)) / 2
+            if qw > 1e-6:
+                q = np.array([qw, (V[2, 1] - V[1, 2]) / (4 * qw), (V[0, 2] - V[2, 0]) / (4 * qw), (V[1, 0] - V[0, 1]) / (4 * qw)])
+            else:                                                 # 180 degree turns: fall back to the axis with the largest diagonal
+                i = int(np.argmax(np.diag(V))); j, k = (i + 1) % 3, (i + 2) % 3
+                s = np.sqrt(max(0.0, 1 + V[i, i] - V[j, j] - V[k, k])) * 2
+                q = np.zeros(4); q[1 + i] = s / 4; q[1 + j] = (V[j, i] + V[i, j]) / s; q[1 + k] = (V[k, i] + V[i, k]) / s; q[0] = (V[k, j] - V[j, k]) / s
+            iq.append(q / np.linalg.norm(q)); diag.append(w)
+        self.body_iquat, self.body_inertia = np.array(iq), np.array(diag)
+        self.body_gravcomp, self.body_weldid, self.body_rootid = mc.body_gravcomp, mc.body_weldid, mc.body_rootid
+        self.body_jntadr, self.body_dofadr, self.body_dofnum = mc.body_jntadr, mc.body_dofadr, mc.body_dofnum
+        self.body_jntnum = (mc.body_jntadr >= 0).astype(np.int32)
+        self.body_invweight0 = mc.body_invweight0
+        self.jnt_type, self.jnt_bodyid, self.jnt_axis, self.jnt_pos, self.jnt_range = mc.jnt_type, mc.jnt_body, mc.jnt_axis, mc.jnt_pos, mc.jnt_range
+        self.jnt_limited, self.jnt_margin, self.jnt_qposadr, self.jnt_dofadr = mc.jnt_limited, mc.jnt_margin, mc.jnt_qposadr, mc.jnt_dofadr
+        arm, damp = np.zeros(mc.nv), np.zeros(mc.nv)
+        for j in range(mc.njnt):
+            w = 6 if mc.jnt_type[j] == 0 else 1
+            arm[mc.jnt_dofadr[j]:mc.jnt_dofadr[j] + w] = mc.jnt_armature[j]
+            damp[mc.jnt_dofadr[j]:mc.jnt_dofadr[j] + w] = mc.jnt_damping[j]
+        self.dof_armature, self.dof_damping, self.dof_invweight0 = arm, damp, mc.dof_invweight0
+        self.geom_type, self.geom_bodyid, self.geom_pos, self.geom_quat, self.geom_size = mc.geom_type, mc.geom_body, mc.geom_pos, mc.geom_quat, mc.geom_size
+        self.geom_friction, self.geom_solref, self.geom_solimp, self.geom_margin, self.geom_condim = mc.geom_friction, mc.geom_solref, mc.geom_solimp, mc.geom_margin, mc.geom_condim
+        self.geom_contype = mc.geom_collides.copy()
+        self.geom_conaffinity = mc.geom_collides.copy()
+        self.site_bodyid, self.site_pos = mc.site_body, mc.site_pos
+        self.qpos0 = mc.qpos0
+        self.exclude_signature = np.zeros(0, dtype=np.int64)
+        o = mc.opt
+        self.opt = n(timestep=o["timestep"], iterations=o["iterations"], ls_iterations=o["ls_iterations"], tolerance=o["tolerance"],
+                     ls_tolerance=o["ls_tolerance"], impratio=o["impratio"], gravity=np.array(o["gravity"]), integrator=0,
+                     disableflags=((1 << 14) if not o.get("eulerdamp", 1) else 0) | ((1 << 10) if not o.get("actuation", 1) else 0))
+        self.stat = n(meaninertia=mc.meaninertia)
+        self._names = dict(body=mc.body_names, joint=mc.jnt_names, geom=mc.geom_names, site=mc.site_names)
+
+    def body(self, i):
+        import types
+        return types.SimpleNamespace(name=self._names["body"][i])
+
+    def joint(self, i):
+        import types
+        return types.SimpleNamespace(name=self._names["joint"][i])
+
+    def geom(self, i):
+        import types
+        return types.SimpleNamespace(name=self._names["geom"][i])
+
+    def site(self, i):
+        import types
+        return types.SimpleNamespace(name=self._names["site"][i])
+
+
+def test_from_mjmodel_reproduces_the_compiled_model(mc):
+    """ModelConsts.from_mjmodel on an MjModel-shaped object carrying scene A gives back the same model: the same kernel
+    table (KModel bytes) and the same oracle behaviour, pair list and slot order included."""
+    import ctypes as C
+    from manipulator_mujoco_b200.kmodel import build_kmodel
+    from manipulator_mujoco_b200.mjcf import ModelConsts
+    mc2 = ModelConsts.from_mjmodel(_MockMjModel(mc))
+    assert mc2.nq == 13 and mc2.nv == 12 and mc2.ncon == mc.ncon == 215
+    np.testing.assert_array_equal(mc2.pair_geom, mc.pair_geom)
+    np.testing.assert_array_equal(mc2.pair_slotadr, mc.pair_slotadr)
+    np.testing.assert_allclose(mc2.body_inertia, mc.body_inertia, atol=1e-12)
+    k1, _ = build_kmodel(mc, 0.05)
+    k2, _ = build_kmodel(mc2, 0.05)
+    a = np.frombuffer(bytes(k1), dtype=np.float32)
+    b = np.frombuffer(bytes(k2), dtype=np.float32)
+    np.testing.assert_allclose(a, b, rtol=0, atol=1e-6)

@@ -33,6 +33,12 @@ def main():
         out[f"P_{T}_{dt}"], out[f"Pdot_{T}_{dt}"], out[f"Pddot_{T}_{dt}"] = P, Pd, Pdd
         P10, Pd10, Pdd10 = ref_b10.bernstein_coeff_order10_new(10, tt[0], tt[-1], tt)
         out[f"P10_{T}_{dt}"], out[f"Pdot10_{T}_{dt}"], out[f"Pddot10_{T}_{dt}"] = P10, Pd10, Pdd10
+    # other orders (order-n sweep) from the same reference function
+    for n in (5, 8, 12, 15):
+        T, dt = 16, 0.05
+        tt = np.linspace(0, T * dt, T).reshape(T, 1)
+        P, Pd, Pdd = ref_b.bernstein_coeff_ordern_new(n, tt[0], tt[-1], tt)
+        out[f"P_n{n}"], out[f"Pdot_n{n}"], out[f"Pddot_n{n}"] = P, Pd, Pdd
     np.savez_compressed(os.path.join(OUT, "bernstein.npz"), **out)
     theta = np.loadtxt(os.path.join(REF, "data", "theta.csv"), delimiter=",")
     thetadot = np.loadtxt(os.path.join(REF, "data", "thetadot.csv"), delimiter=",")
