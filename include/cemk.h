@@ -107,6 +107,11 @@ int cemk_topk_pack(cemk_handle* h, int n, const float* cost, int cost_stride, in
                    const float* xi, float* pack, void* stream);
 int cemk_merge_packed(cemk_handle* h, int n, const float* packed, unsigned long long* keys_ws, int k, float* xi_elite,
                       float* cost_elite, int* gidx_elite, void* stream);
+/* The same merge for what the all-gather actually delivers: `nlist` blocks of `kl` records, each block already sorted by
+ * cemk_topk_pack on its rank.  No sort: every record finds its global (cost, row) position by binary searches in the other
+ * blocks (one launch). */
+int cemk_merge_sorted_lists(cemk_handle* h, int nlist, int kl, const float* packed, int k, float* xi_elite, float* cost_elite,
+                            int* gidx_elite, void* stream);
 
 /* compute_mean_cov (mjx_planner.py:326-335): k elites -> mean_out[66], cov_out[66][66]. */
 int cemk_mean_cov(cemk_handle* h, int k, const float* cost_elite, const float* xi_elite, const float* mean_prev,

@@ -519,13 +519,11 @@ class cem_planner:
                                             _ptr(xs), _ptr(pack), self._stream()), self._lib)
         gathered = self._buf("elite_gathered", (self.world * kl, nv + 2))
         parallel.gather_elites(pack, self.world, self.process_group, out=gathered)
-        n = self.world * kl
-        np2 = 1 << max(0, (n - 1).bit_length())
         xi_m = torch.empty(k, nv, device=self.device)
         cost_m = torch.empty(k, device=self.device)
         gidx_m = torch.empty(k, dtype=torch.int32, device=self.device)
-        _lib.check(self._lib.cemk_merge_packed(self._h, n, _ptr(gathered), _ptr(self._buf("keys_merge", (np2,), torch.int64)), k,
-                                               _ptr(xi_m), _ptr(cost_m), _ptr(gidx_m), self._stream()), self._lib)
+        _lib.check(self._lib.cemk_merge_sorted_lists(self._h, self.world, kl, _ptr(gathered), k, _ptr(xi_m), _ptr(cost_m), _ptr(gidx_m),
+                                                     self._stream()), self._lib)
         self._keep_e = (c4, xs)
         return xi_m, cost_m, gidx_m
 

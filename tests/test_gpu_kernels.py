@@ -171,6 +171,11 @@ def test_packed_topk_and_merge_equal_global_stable_topk(planner):
     np.testing.assert_array_equal(ge.cpu().numpy(), ref)
     np.testing.assert_array_equal(xe.cpu().numpy(), xi[ref])
     np.testing.assert_array_equal(ce.cpu().numpy().view(np.int32), cost[ref].view(np.int32))
+    # the sort-free merge of per-rank sorted blocks (what the planner calls after the all-gather) gives the same answer
+    xe2 = torch.empty(k, nv, device="cuda"); ce2 = torch.empty(k, device="cuda"); ge2 = torch.empty(k, dtype=torch.int32, device="cuda")
+    _lib.check(lib.cemk_merge_sorted_lists(h, 2, k, p(gathered), k, p(xe2), p(ce2), p(ge2), None), lib)
+    torch.cuda.synchronize()
+    assert torch.equal(ge2, ge) and torch.equal(xe2, xe) and torch.equal(ce2.view(torch.int32), ce.view(torch.int32))
     rx, rc, rg = merge_packed_ref(gathered.cpu().numpy(), k)
     np.testing.assert_array_equal(ge.cpu().numpy(), rg)
     np.testing.assert_array_equal(xe.cpu().numpy(), rx)

@@ -57,7 +57,7 @@ def iteration(rec):
         gathered = pl._buf("elite_gathered", (n, nv + 2))
         parallel.gather_elites(pack, world, pg, out=gathered); ev[5].record()
         xi_e, cost_e, gi = torch.empty(k, nv, device=dev), torch.empty(k, device=dev), torch.empty(k, dtype=torch.int32, device=dev)
-        _lib.check(lib.cemk_merge_packed(h, n, _ptr(gathered), _ptr(pl._buf("keys_merge", (np2,), torch.int64)), k, _ptr(xi_e), _ptr(cost_e), _ptr(gi), pl._stream()), lib)
+        _lib.check(lib.cemk_merge_sorted_lists(h, world, kl, _ptr(gathered), k, _ptr(xi_e), _ptr(cost_e), _ptr(gi), pl._stream()), lib)
         ev[6].record()
     pl.compute_mean_cov(cost_e, mean0, cov0, xi_e); ev[7].record()
     rec.append(ev)
