@@ -48,7 +48,6 @@ struct LaneRegs {
   int actmask;                // bit (2*pass + slot)
   int farprev;                // bit p: the previous step's distances of this lane's capsule-box pair of pass p were the (+1, +1) sentinel
   int tri;                    // (i, j), 4 bits each, of the 6x6 lower-triangle entries lane and lane + KW (8 bits per entry; 0xff = none)
-  float td;                   // next step's commanded joint velocity (lanes < 6), prefetched one step ahead
   float acc[9];               // line-search partial sums (compile-time indices only)
   float h[KM_NV];             // row `lane` of the Newton Hessian / its Cholesky factor (compile-time indices only)
 #ifdef CEMK_EMU
@@ -74,17 +73,22 @@ struct WarpSmemT {
     float H[KM_NV][KM_NV];
   };
   float fs[12], as[12], qacc[12], Ma[12], grad[12], search[12];
+  float tdn[2][8];                    // commanded joint velocities of this / the next step (double buffer of the asynchronous copy)
   int ncon, nrow, nlim, flags;
   union {
     struct { float cinert[KM_NL][12], crb[KM_NL][12], cvel[KM_NL][8], cdofdot[KM_NL][8], cfrc[KM_NL][8]; };
     struct { float rD[NROW], rAref[NROW], rJaref[NROW], rJv[NROW]; };   // rJv doubles as the smooth-start J.a - aref in S1
-    struct { unsigned short nlist[KM_MAXNEAR]; };   // N1 only: the near capsule-box pairs of this step (pair table entry | was-far bit << 15)
+    struct {                            // N1 only: the near capsule-box pairs of this step (pair table entry | prefetched << 14 | was-far << 15)
+      unsigned short nlist[KM_MAXNEAR]; //          and, per pair table entry, their previous distances fetched ahead by the owner lane
+      float nprev[(KM_MAXSBOX + 1) * KW][2];
+    };
   };
   float cgeo[NC][16];                 // pos3 n3 t1 3 t2 3 dist invw link1 link2
   union {
     float cJ[NC][36];                 // Jn[12] Jt1[12] Jt2[12] (tangents pre-multiplied by mu)
     struct {                          // free-box pair candidates (pos3, dist) + scratch of the cooperative box-box
       float bstage[KM_MAXBPAIR][4][4], bnrm[KM_MAXBPAIR][4];
+      float pstage[2 * (KM_NPASS - 1)][KW];   // previous distances of the plane-capsule / capsule-capsule passes, copied in at the start of the step
       float bbR[12], bbc[4], bbsz[2][4], bbrf[4][4], bben[4][4], bbpoly[2][8][4], bbpref[8][4];
     };
   };
@@ -1599,6 +1603,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
   // per-sample list and evaluated densely by the first lanes, full contact records included, so a sample's narrow
   // phase costs one extra collider pass however its near pairs are spread over the table (the warps of a CTA
   // step in lockstep: the slowest one sets the pace).
+  ASYNC_COPY_WAIT();                               // S.pstage
   LANES(W, R)
     int nact = 0, actmask = 0, nearbits = 0, farbits = 0;
     float cc = 0.f;
@@ -1625,6 +1630,15 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
         if (valid) { if (far) farbits |= 1 << p; else nearbits |= 1 << p; }
       }
     }
+    // previous distances of the pairs that stay near (an L2 round trip): fetched here by the owner lane, handed to the
+    // near pass through the sample's record at the end of this block, so the latency hides behind the other passes
+    int pf = 0, pf0 = 0, pf1 = 0;
+    float q00 = 0.f, q01 = 0.f, q10 = 0.f, q11 = 0.f;
+    if (!io.first) {
+      int rem = nearbits & ~R.farprev;
+      if (rem) { pf0 = KFFS(rem) - 1; rem &= rem - 1; pf = 1; q00 = pd[(2 * pf0) * KW]; q01 = pd[(2 * pf0 + 1) * KW]; }
+      if (rem) { pf1 = KFFS(rem) - 1; pf = 2; q10 = pd[(2 * pf1) * KW]; q11 = pd[(2 * pf1 + 1) * KW]; }
+    }
     // a far pair whose previous distances were real: (1-y) c_t - 1 can only be positive for c_t > 1 / (1-y)
     if (!io.first) {
 #pragma unroll 1
@@ -1642,16 +1656,13 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
     }
     R.off = nearbits | ((nearbits & R.farprev) << 16);     // near pairs, and which of them were far one step ago
     R.farprev = farbits;
-    // plane-capsule and capsule-capsule passes: previous distances of this lane's two slots, fetched one pass ahead
-    // so the L2 latency hides behind the collider
-    float pv0 = 0.f, pv1 = 0.f;
-    if (!io.first) { pv0 = pd[(2 * m.ncbpass) * KW]; pv1 = pd[(2 * m.ncbpass + 1) * KW]; }
+    // plane-capsule and capsule-capsule passes (the previous distances of this lane's slots were copied into S.pstage
+    // at the start of the step: the L2 latency hides behind FK and the dynamics)
 #pragma unroll 1
     for (int p = m.ncbpass; p < KM_NPASS; ++p) {
       const int e = p * KW + lane;
       const int x = m.rp[e], ty = KP_TYPE(x);
-      const float prev0 = pv0, prev1 = pv1;
-      if (!io.first && p + 1 < KM_NPASS) { pv0 = pd[(2 * p + 2) * KW]; pv1 = pd[(2 * p + 3) * KW]; }
+      const float prev0 = S.pstage[2 * (p - m.ncbpass)][lane], prev1 = S.pstage[2 * (p - m.ncbpass) + 1][lane];
       if (ty == KP_NONE) continue;
       const int a = KP_A(x), b = KP_B(x);
       float d0, d1 = 1.f;
@@ -1678,6 +1689,9 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
       }
     }
     R.cost_c += cc;
+    if (pf >= 1) { S.nprev[pf0 * KW + lane][0] = q00; S.nprev[pf0 * KW + lane][1] = q01; }
+    if (pf >= 2) { S.nprev[pf1 * KW + lane][0] = q10; S.nprev[pf1 * KW + lane][1] = q11; }
+    R.acc[6] = __int_as_float((pf >= 1 ? 1 << pf0 : 0) | (pf >= 2 ? 1 << pf1 : 0));     // which near pairs have their previous distances in S.nprev
     R.acc[7] = __int_as_float(actmask);        // parked: the near pass and the cooperative box colliders below reuse the scratch fields
     R.acc[8] = __int_as_float(nact);
   END_LANES
@@ -1707,7 +1721,8 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
 #pragma unroll 1
         for (int rem = R.off & 0xffff; rem; rem &= rem - 1, ++o) {
           const int p = KFFS(rem) - 1;
-          S.nlist[o] = (unsigned short)((p * KW + lane) | (((R.off >> (16 + p)) & 1) << 15));     // bit 15: the pair was far one step ago
+          S.nlist[o] = (unsigned short)((p * KW + lane) | (((__float_as_int(R.acc[6]) >> p) & 1) << 14) | (((R.off >> (16 + p)) & 1) << 15));
+                                                                   // bit 14: previous distances prefetched, bit 15: the pair was far one step ago
         }
       END_LANES
       PHASE(W, 21);
@@ -1715,13 +1730,14 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
       for (int i0 = 0; warp_any_groups(W, i0 < ntot) || (uniform_pass && i0 == 0); i0 += KW) {
         // one near pair per lane: both distances, their share of the collision cost, the previous-distance record and
         // the contact geometry of the penetrating slots (parked in R.h)
+        const long long tk0 = TICK(); (void)tk0;
         LANES(W, R)
           const int i = i0 + lane;
           const bool dummy = uniform_pass && i0 == 0 && lane == 0 && ntot == 0;
           R.nact = 0;
           if (i < ntot || dummy) {
-            const int e = dummy ? 0 : S.nlist[i] & 0x7fff, x = m.rp[e], a = KP_A(x), b = KP_B(x);
-            const bool wasfar = dummy || (S.nlist[i] >> 15) != 0, st = b < m.nsbox;
+            const int e = dummy ? 0 : S.nlist[i] & 0x3fff, x = m.rp[e], a = KP_A(x), b = KP_B(x);
+            const bool wasfar = dummy || (S.nlist[i] >> 15) != 0, pref = !dummy && ((S.nlist[i] >> 14) & 1) != 0, st = b < m.nsbox;
             const float* bpos = st ? m.sb_pos[b] : S.qpos + KM_NL;
             const float* bmat = st ? m.sb_mat[b] : S.bmat;
             // (the list holds exactly the pairs that failed the far test: straight to the near path)
@@ -1733,7 +1749,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
             float cc = (d0 < 0.f ? 1.f : 0.f) + (d1 < 0.f ? 1.f : 0.f);
             float* pd = io.prevd + (2 * (e / KW)) * KW + (e & (KW - 1));       // the owner's slots: pass e / KW, capsule lane e % KW
             if (!io.first) {
-              const float prev0 = wasfar ? 1.f : pd[0], prev1 = wasfar ? 1.f : pd[KW];
+              const float prev0 = wasfar ? 1.f : (pref ? S.nprev[e][0] : pd[0]), prev1 = wasfar ? 1.f : (pref ? S.nprev[e][1] : pd[KW]);
               cc += fmaxf((1.f - 0.005f) * prev0 - d0, 0.f) + fmaxf((1.f - 0.005f) * prev1 - d1, 0.f);
             }
             if (!dummy) {
@@ -1762,6 +1778,8 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
             }
           }
         END_LANES
+        const long long tk1 = TICK(); (void)tk1;
+        EVENT(W, 14, (int)(tk1 - tk0));
         const int nnew = warp_excl_scan(W, [](int, LaneRegs& R) { return (R.nact & 1) + ((R.nact >> 1) & 1); }, [](int, LaneRegs& R, int o) { R.actmask = o; });
         if (uniform_pass || warp_any_groups(W, nnew > 0)) {
           LANES(W, R)
@@ -1774,6 +1792,7 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
           END_LANES
         }
         ncbcon += nnew;
+        EVENT(W, 15, (int)(TICK() - tk1));
       }
       PHASE(W, 22);
     }
@@ -1943,7 +1962,7 @@ KFN void rollout_sample(Warp& W, const KModel& m, WarpSmemT<NC>& S, const Rollou
     if (lane == 0) { S.flags = 0; S.ovf = A.ovf; }
     R.cost_c = 0.f;
     R.farprev = 0;
-    R.td = lane < KM_NL ? A.thetadot[lane * A.T] : 0.f;
+    if (lane < KM_NL) ASYNC_COPY_F32(&S.tdn[0][lane], &A.thetadot[lane * A.T]);
   END_LANES
   const float tp[3] = {A.target_pos[0], A.target_pos[1], A.target_pos[2]};       // read once: the step loop only touches registers for the goal terms
   float tq[4] = {A.target_rot[0], A.target_rot[1], A.target_rot[2], A.target_rot[3]};
@@ -1957,10 +1976,17 @@ KFN void rollout_sample(Warp& W, const KModel& m, WarpSmemT<NC>& S, const Rollou
     PHASE(W, 13);
     if ((t % CEMK_SYNC_EVERY) == 0) { STEP_ALIGN(); }
     PHASE(W, 0);
+    ASYNC_COPY_WAIT();                                                  // this step's command (issued one step ago)
     LANES(W, R)
       if (lane < KM_NL) {
-        S.qvel[lane] = R.td;                                             // mjx_planner.py:254
-        if (t + 1 < A.T) R.td = A.thetadot[lane * A.T + t + 1];          // consumed next step: latency hidden
+        S.qvel[lane] = S.tdn[t & 1][lane];                                // mjx_planner.py:254
+        if (t + 1 < A.T) ASYNC_COPY_F32(&S.tdn[(t + 1) & 1][lane], &A.thetadot[lane * A.T + t + 1]);     // consumed next step
+      }
+      // previous distances of this lane's plane-capsule / capsule-capsule slots: in flight during FK and dynamics
+      if (t > 0) {
+        const int p0 = m.ncbpass;
+#pragma unroll 1
+        for (int q = 0; q < 2 * (KM_NPASS - p0); ++q) ASYNC_COPY_F32(&S.pstage[q][lane], A.prevd + (2 * p0 + q) * KW + lane);
       }
     END_LANES
     StepIO io;

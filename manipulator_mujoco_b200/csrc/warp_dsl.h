@@ -109,6 +109,9 @@ struct RaceBlock {
 #define USYNC()
 #define REGROUP()
 #define KRSQRT(x) (1.0f / sqrtf(x))
+// asynchronous 4-byte global -> shared copies (cp.async on the GPU): issued early, awaited before the first use
+#define ASYNC_COPY_F32(dst, src) (*(dst) = *(src))
+#define ASYNC_COPY_WAIT()
 #define WARP_BAR(W) 0
 #define WARP_NTHR(W) 0
 #define KPOPC(x) __builtin_popcount(x)
@@ -149,6 +152,10 @@ static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); retur
 #define USYNC() __syncwarp()
 #define REGROUP() __syncwarp()
 #define KRSQRT(x) rsqrtf(x)
+// asynchronous 4-byte global -> shared copies: no register is tied up while the data is in flight (a plain prefetch into a
+// register gets spilled to local memory by the 128-register cap and the reload is as slow as the original load)
+#define ASYNC_COPY_F32(dst, src) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory")
+#define ASYNC_COPY_WAIT() asm volatile("cp.async.wait_all;" ::: "memory")
 #define WARP_BAR(W) ((W).bar)
 #define WARP_NTHR(W) ((W).nthr)
 #define KPOPC(x) __popc(x)
@@ -190,9 +197,11 @@ struct WarpCtx {
 #define FLAGSTEP(W, cond) do { if (cond) (W).stepflag = 1; } while (0)
 #define STEPEND(W) do { for (int i_ = 0; i_ < 24; ++i_) { if ((W).stepflag) (W).phc[i_] += (W).phs[i_]; (W).phs[i_] = 0; } (W).nflag += (W).stepflag; (W).stepflag = 0; } while (0)
 #define EVENT(W, id, n) do { (W).ev[(id)] += (n); } while (0)
+#define TICK() clock64()
 #else
 #define PHASE(W, id) do { } while (0)
 #define EVENT(W, id, n) do { } while (0)
+#define TICK() 0LL
 #define FLAGSTEP(W, cond) do { } while (0)
 #define STEPEND(W) do { } while (0)
 #endif

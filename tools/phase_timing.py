@@ -64,6 +64,7 @@ for label, val in [("has near capsule-box pairs", e[1] / n), ("near pairs (mean)
                    ("active contacts (mean)", e[3] / n), ("has robot contacts", e[4] / n), ("warp emits robot contacts (either sample)", e[12] / n),
                    ("no active row", e[8] / n), ("has active limit rows", e[13] / n), ("coupled 12x12 solve", e[7] / n), ("spill instantiation", e[9] / n),
                    ("line-search trips executed by the warp (mean)", e[6] / n), ("line-search trips the sample needed (mean)", e[5] / n),
-                   ("free-box pairs walked by the warp (mean)", e[10] / n)]:
+                   ("free-box pairs walked by the warp (mean)", e[10] / n),
+                   ("clk per near-pass trip: pair evaluation block", e[14] / max(e[11], 1.0)), ("clk per near-pass trip: scan + contact records", e[15] / max(e[11], 1.0))]:
     print(f"  {val:8.3f}  {label}")
 os.remove(dbg)
