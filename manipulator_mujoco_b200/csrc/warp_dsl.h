@@ -109,9 +109,6 @@ struct RaceBlock {
 #define USYNC()
 #define REGROUP()
 #define KRSQRT(x) (1.0f / sqrtf(x))
-// asynchronous 4-byte global -> shared copies (cp.async on the GPU): issued early, awaited before the first use
-#define ASYNC_COPY_F32(dst, src) (*(dst) = *(src))
-#define ASYNC_COPY_WAIT()
 #define WARP_BAR(W) 0
 #define WARP_NTHR(W) 0
 #define KPOPC(x) __builtin_popcount(x)
@@ -152,10 +149,6 @@ static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); retur
 #define USYNC() __syncwarp()
 #define REGROUP() __syncwarp()
 #define KRSQRT(x) rsqrtf(x)
-// asynchronous 4-byte global -> shared copies: no register is tied up while the data is in flight (a plain prefetch into a
-// register gets spilled to local memory by the 128-register cap and the reload is as slow as the original load)
-#define ASYNC_COPY_F32(dst, src) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory")
-#define ASYNC_COPY_WAIT() asm volatile("cp.async.wait_all;" ::: "memory")
 #define WARP_BAR(W) ((W).bar)
 #define WARP_NTHR(W) ((W).nthr)
 #define KPOPC(x) __popc(x)
@@ -184,7 +177,7 @@ struct WarpCtx {
 #ifdef CEMK_PHASE_TIMING
   long long t0; int phase; long long ph[24];
   long long phs[24], phc[24]; int stepflag, nflag;   // this step's clocks; clocks of the steps with stepflag set (conditional profile)
-  int ev[16];        // event counters (tools/phase_timing.py)
+  int ev[24];        // event counters (tools/phase_timing.py)
 #endif
 #endif
 };

@@ -33,7 +33,7 @@ for _ in range(2):
 torch.cuda.synchronize()
 pl._lib.cemk_debug_phase_clocks(buf)
 pl._lib.cemk_debug_phase_cond((C.c_ulonglong * 25)())        # (reading clears the tables)
-pl._lib.cemk_debug_events((C.c_ulonglong * 16)())
+pl._lib.cemk_debug_events((C.c_ulonglong * 24)())
 pl.compute_cem(np.zeros(66), q0, np.zeros(6), np.zeros(6), tp, tr)
 torch.cuda.synchronize()
 pl._lib.cemk_debug_phase_clocks(buf)
@@ -55,7 +55,7 @@ print(f"conditional profile: clk per step of a warp whose step has robot contact
 for n, xc, xa in sorted(zip(names, c, v), key=lambda t: -t[1]):
     print(f"  {xc / nflag:9.0f} vs {(xa - xc) / rest_n:9.0f}   {n}")
 print(f"  {c.sum() / nflag:9.0f} vs {(v.sum() - c.sum()) / rest_n:9.0f}   total")
-ev = (C.c_ulonglong * 16)()
+ev = (C.c_ulonglong * 24)()
 pl._lib.cemk_debug_events(ev)
 e = [float(x) for x in ev]
 n = max(e[0], 1.0)
@@ -65,6 +65,7 @@ for label, val in [("has near capsule-box pairs", e[1] / n), ("near pairs (mean)
                    ("no active row", e[8] / n), ("has active limit rows", e[13] / n), ("coupled 12x12 solve", e[7] / n), ("spill instantiation", e[9] / n),
                    ("line-search trips executed by the warp (mean)", e[6] / n), ("line-search trips the sample needed (mean)", e[5] / n),
                    ("free-box pairs walked by the warp (mean)", e[10] / n),
-                   ("clk per near-pass trip: pair evaluation block", e[14] / max(e[11], 1.0)), ("clk per near-pass trip: scan + contact records", e[15] / max(e[11], 1.0))]:
+                   ("clk per near-pass trip: pair evaluation block", e[14] / max(e[11], 1.0)), ("clk per near-pass trip: scan + contact records", e[15] / max(e[11], 1.0)),
+                   ("clk of capbox_local + capsule_box_near (edges included) inside the evaluation block, lane 0", e[16] / max(e[17], 1.0))]:
     print(f"  {val:8.3f}  {label}")
 os.remove(dbg)
