@@ -381,7 +381,7 @@ def main():
         return
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r2_k_rollout_metrics.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_final_k_rollout_metrics.json")) as f:
             traffic = float(json.load(f)["dram_traffic_bytes_per_launch"]) if Bl == B_PER_GPU else None
     except Exception:
         pass
