@@ -630,8 +630,15 @@ __global__ void __launch_bounds__(MC_THREADS) k_mean_cov(int NVAR, int k, const 
   const float sumw = red[0];
   auto weight = [&](int i) { return i < MC_WCACHE ? sw[i] : precise_expf(-il * (cost[i] - cmin)); };
   // new mean (every CTA needs all of it)
+  // (cached weights in a loop of their own: with the recomputing branch inside, the loop is not unrolled and runs at one
+  //  L2 round trip per elite -- 127 us at k = 1638)
+  const int kc = k < MC_WCACHE ? k : MC_WCACHE;
   float s = 0.f;
-  if (on) for (int i = g; i < k; i += G) s += weight(i) * xi[(size_t)i * NVAR + j];
+  if (on) {
+#pragma unroll 8
+    for (int i = g; i < kc; i += G) s += sw[i] * xi[(size_t)i * NVAR + j];
+    for (int i = g + ((kc - g + G - 1) / G) * G; i < k; i += G) s += weight(i) * xi[(size_t)i * NVAR + j];
+  }
   part[tid] = s; __syncthreads();
   if (tid < NVAR) {
     float t = 0.f;
@@ -645,7 +652,9 @@ __global__ void __launch_bounds__(MC_THREADS) k_mean_cov(int NVAR, int k, const 
   s = 0.f;
   if (on) {
     const float mr = smean[row], mj = smean[j];
-    for (int i = g; i < k; i += G) s += weight(i) * (xi[(size_t)i * NVAR + row] - mr) * (xi[(size_t)i * NVAR + j] - mj);
+#pragma unroll 8
+    for (int i = g; i < kc; i += G) s += sw[i] * (xi[(size_t)i * NVAR + row] - mr) * (xi[(size_t)i * NVAR + j] - mj);
+    for (int i = g + ((kc - g + G - 1) / G) * G; i < k; i += G) s += weight(i) * (xi[(size_t)i * NVAR + row] - mr) * (xi[(size_t)i * NVAR + j] - mj);
   }
   part[tid] = s; __syncthreads();
   if (tid < NVAR) {
