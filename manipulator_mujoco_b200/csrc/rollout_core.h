@@ -88,7 +88,10 @@ struct WarpSmemT {
     float cJ[NC][36];                 // Jn[12] Jt1[12] Jt2[12] (tangents pre-multiplied by mu)
     struct {                          // free-box pair candidates (pos3, dist) + scratch of the cooperative box-box
       float bstage[KM_MAXBPAIR][4][4], bnrm[KM_MAXBPAIR][4];
-      float bbR[12], bbc[4], bbsz[2][4], bbrf[4][4], bben[4][4], bbpoly[2][8][4], bbpref[8][4];
+      union {
+        struct { float bbR[12], bbc[4], bbsz[2][4], bbrf[4][4], bben[4][4], bbpoly[2][8][4], bbpref[8][4]; };
+        struct { float estage[KW][16], eres[KW][8]; };      // near pass: box-frame geometry of the pairs in their edge stage, and its result
+      };
     };
   };
   float cd[2][NC][3];                 // per contact: Jn.v, mu*Jt1.v, mu*Jt2.v for up to two vectors v
@@ -413,8 +416,11 @@ KNOINLINE CapBoxEdge capbox_edges(float ax, float ay, float az, float bx, float 
 }
 // Near path, in box coordinates; the caller has established has_support (= !capbox_far).  Face part in registers
 // (no dynamic indexing); FULL also produces contact positions / normals.
-template <bool FULL>
-KFN void capsule_box_near(const float* a, const float* b, float r, const float* bsize, CapBoxOut& o) {
+// Returns the number of box axes on which the segment's bounding interval sticks out of the box (the edge stage can only
+// matter when that is >= 2).  EDGES = false leaves the edge stage to the caller (the near pass spreads the 12 edges of a pair
+// over lanes, see capbox_edge_lane) and also returns the outward normal of the best face in `nface`.
+template <bool FULL, bool EDGES = true>
+KFN int capsule_box_near(const float* a, const float* b, float r, const float* bsize, CapBoxOut& o, float* nface = nullptr) {
   // best face: first argmax over (+x,-x,+y,-y,+z,-z) of min over end points of the signed face distance
   float bests = fminf(a[0], b[0]) - bsize[0]; int bk = 0; float sg = 1.f;
   { float s = -fmaxf(a[0], b[0]) - bsize[0]; if (s > bests) { bests = s; sg = -1.f; } }
@@ -469,11 +475,72 @@ KFN void capsule_box_near(const float* a, const float* b, float r, const float* 
     else if (bk == 1) { o.pos[0][1] = l0[0]; o.pos[0][2] = l0[1]; o.pos[0][0] = l0[2]; o.pos[1][1] = l1[0]; o.pos[1][2] = l1[1]; o.pos[1][0] = l1[2]; }
     else              { o.pos[0][2] = l0[0]; o.pos[0][0] = l0[1]; o.pos[0][1] = l0[2]; o.pos[1][2] = l1[0]; o.pos[1][0] = l1[1]; o.pos[1][1] = l1[2]; }
     o.nrm[0][0] = o.nrm[1][0] = -nx; o.nrm[0][1] = o.nrm[1][1] = -ny; o.nrm[0][2] = o.nrm[1][2] = -nz;
-    if (nout >= 2) {
+    if (EDGES && nout >= 2) {
       const CapBoxEdge e = capbox_edges(a[0], a[1], a[2], b[0], b[1], b[2], r, bsize[0], bsize[1], bsize[2], nx, ny, nz, fminf(-o.dist[0], -o.dist[1]));
       if (e.pen > 0.f) { o.dist[0] = -e.pen; copy3(o.pos[0], e.pos); copy3(o.nrm[0], e.nrm); }
     }
   }
+  if (nface) { nface[0] = nx; nface[1] = ny; nface[2] = nz; }
+  return nout;
+}
+// One of the 12 box edges against the capsule segment: the body of capbox_edges' loop for edge e = 4 k + 2 iu + iw, written in
+// the edge's own (k, u, w) coordinates with component selects instead of indices (e is a lane number here, and a dynamic index
+// would put the vectors in local memory).  epen = r - distance if the edge qualifies, -1 otherwise; pa / pb = closest points
+// on the edge / on the segment, dir = normalised pa - pb, all in box coordinates.
+struct EdgeEval { float epen, deg, dir[3], pa[3], pb[3]; };
+KFN float pick3(const float* v, int k) { return k == 0 ? v[0] : (k == 1 ? v[1] : v[2]); }
+KFN void unpick3(float* out, int k, int u, float vk, float vu, float vw) {
+  out[0] = k == 0 ? vk : (u == 0 ? vu : vw); out[1] = k == 1 ? vk : (u == 1 ? vu : vw); out[2] = k == 2 ? vk : (u == 2 ? vu : vw);
+}
+KFN EdgeEval capbox_edge_lane(int e, const float* a, const float* b, float r, const float* bsize) {
+  EdgeEval out;
+  out.epen = -1.f; out.deg = 0.f;
+  out.dir[0] = out.dir[1] = out.dir[2] = 0.f; out.pa[0] = out.pa[1] = out.pa[2] = 0.f; out.pb[0] = out.pb[1] = out.pb[2] = 0.f;
+  const int k = e >> 2, u = k == 2 ? 0 : k + 1, w = k == 0 ? 2 : k - 1;
+  const float eu = (e & 2) ? 1.f : -1.f, ew = (e & 1) ? 1.f : -1.f;
+  const float ak = pick3(a, k), au = pick3(a, u), aw = pick3(a, w), bk = pick3(b, k), bu = pick3(b, u), bw = pick3(b, w);
+  const float sk = pick3(bsize, k), su = pick3(bsize, u), sw = pick3(bsize, w);
+  const float lou = fminf(au, bu), hiu = fmaxf(au, bu), low = fminf(aw, bw), hiw = fmaxf(aw, bw), lok = fminf(ak, bk), hik = fmaxf(ak, bk);
+  const float cu = eu * su, cw = ew * sw;
+  const float fu = eu > 0.f ? hiu - cu : cu - lou, fw = ew > 0.f ? hiw - cw : cw - low;
+  const float gu = eu > 0.f ? lou - cu : cu - hiu, gw = ew > 0.f ? low - cw : cw - hiw;
+  if (!(fu > 0.f && fw > 0.f && gu < r && gw < r && lok < sk + r && hik > -sk - r)) return out;
+  // closest points of the edge and the segment (same formulas as capbox_edges), vectors as (k, u, w) triples
+  const float abk = bk - ak, abu = bu - au, abw = bw - aw;
+  const float den = abk * abk + abu * abu + abw * abw + 1e-6f;
+  float dv[3] = {abk, abu, abw};
+  const float hb = 0.5f * normalize3(dv);
+  const float mk = ak + dv[0] * hb, mu = au + dv[1] * hb, mw = aw + dv[2] * hb;
+  const float trk = -mk, tru = cu - mu, trw = cw - mw;
+  const float dd = dv[0], dat = trk, dbt = dv[0] * trk + dv[1] * tru + dv[2] * trw;
+  float ta = (-dat + dd * dbt) / (1.f - dd * dd + 1e-6f);
+  float tb = dbt + ta * dd;
+  ta = fminf(fmaxf(ta, -sk), sk);
+  tb = fminf(fmaxf(tb, -hb), hb);
+  float pa[3] = {ta, cu, cw}, pb[3] = {mk + dv[0] * tb, mu + dv[1] * tb, mw + dv[2] * tb};
+  float t1 = ((pb[0] + sk) * (2.f * sk)) / (4.f * sk * sk + 1e-6f);
+  t1 = fminf(fmaxf(t1, 0.f), 1.f);
+  const float na[3] = {-sk + 2.f * sk * t1, cu, cw};
+  float d[3];
+  sub3(d, pb, na);
+  const float d1 = dot3(d, d);
+  float t2 = ((pa[0] - ak) * abk + (pa[1] - au) * abu + (pa[2] - aw) * abw) / den;
+  t2 = fminf(fmaxf(t2, 0.f), 1.f);
+  const float nb[3] = {ak + abk * t2, au + abu * t2, aw + abw * t2};
+  sub3(d, pa, nb);
+  const float d2 = dot3(d, d);
+  if (d1 < d2) copy3(pa, na); else copy3(pb, nb);
+  float dir[3];
+  sub3(dir, pa, pb);
+  const bool deg = dot3(dir, dir) < 1e-6f;
+  const float ed = normalize3(dir);
+  const bool front = (eu * dir[1] < 0.f) && (ew * dir[2] < 0.f);
+  out.epen = (!deg && front) ? r - ed : -1.f;
+  out.deg = deg ? 1.f : 0.f;
+  unpick3(out.dir, k, u, dir[0], dir[1], dir[2]);
+  unpick3(out.pa, k, u, pa[0], pa[1], pa[2]);
+  unpick3(out.pb, k, u, pb[0], pb[1], pb[2]);
+  return out;
 }
 template <bool FULL>
 KFN void capsule_box(const float* A, const float* B, float r, const float* bpos, const float* bmat, const float* bsize, Contact2& c) {
@@ -1738,18 +1805,9 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
 #ifdef CEMK_X_NONEAR
     ntot = 0;      // timing experiment only (wrong results): what the near pass costs, lockstep wait included
 #endif
-    // CEMK_UNIFORM_NEAR: every warp walks the near pass every step.  Most steps some warp of the CTA has near pairs
-    // (and three in four near pairs penetrate), and the warps of a CTA wait for each other at the next alignment point
-    // anyway; a warp running this code alone runs it at instruction-fetch speed (nothing else shares its cache lines),
-    // several times slower than the same code executed by all warps in lockstep.  So a sample without near pairs sends
-    // lane 0 through the pass with a dummy pair (table entry 0) whose results go to an unused spill record.
-#ifdef CEMK_UNIFORM_NEAR
-    const bool uniform_pass = true;
-#else
-    const bool uniform_pass = false;
-    if (warp_any_groups(W, ntot > 0))
-#endif
-    {
+    // (Letting every warp walk this pass with a dummy pair, so that it runs in lockstep like the rest of the step, was
+    //  measured: +1.4 %.)
+    if (warp_any_groups(W, ntot > 0)) {
       LANES(W, R)
         int o = R.actmask;
 #pragma unroll 1
@@ -1761,39 +1819,96 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
       END_LANES
       PHASE(W, 21);
 #pragma unroll 1
-      for (int i0 = 0; warp_any_groups(W, i0 < ntot) || (uniform_pass && i0 == 0); i0 += KW) {
-        // one near pair per lane: both distances, their share of the collision cost, the previous-distance record and
-        // the contact geometry of the penetrating slots (parked in R.h)
+      for (int i0 = 0; warp_any_groups(W, i0 < ntot); i0 += KW) {
         const long long tk0 = TICK(); (void)tk0;
+        // (1) one near pair per lane: the face part of the collider (both slots, in box coordinates; parked in R.h); the
+        //     pairs that need the edge stage leave their box-frame geometry in S.estage
         LANES(W, R)
           const int i = i0 + lane;
-          const bool dummy = uniform_pass && i0 == 0 && lane == 0 && ntot == 0;
           R.nact = 0;
-          if (i < ntot || dummy) {
-            const int e = dummy ? 0 : S.nlist[i] & 0x3fff, x = m.rp[e], a = KP_A(x), b = KP_B(x);
-            const bool wasfar = dummy || (S.nlist[i] >> 15) != 0, pref = !dummy && ((S.nlist[i] >> 14) & 1) != 0, st = b < m.nsbox;
+          if (i < ntot) {
+            const int e = S.nlist[i] & 0x3fff, x = m.rp[e], a = KP_A(x), b = KP_B(x);
+            const bool st = b < m.nsbox;
+            const float* bsz = st ? m.sb_size[b] : m.fb_size;
+            // (the list holds exactly the pairs that failed the far test: straight to the near path)
+            float la[3], lb[3], nf[3];
+            CapBoxOut c;
+            capbox_local(S.capA[a], S.capB[a], st ? m.sb_pos[b] : S.qpos + KM_NL, st ? m.sb_mat[b] : S.bmat, la, lb);
+            const int nout = capsule_box_near<true, false>(la, lb, m.cap_r[a], bsz, c, nf);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { R.h[k] = c.pos[0][k]; R.h[3 + k] = c.nrm[0][k]; R.h[6 + k] = c.pos[1][k]; R.h[9 + k] = c.nrm[1][k]; }
+            R.f0 = c.dist[0]; R.f1 = c.dist[1];
+            if (nout >= 2) {
+              R.nact = 1;
+              float* g = S.estage[lane];
+              g[0] = la[0]; g[1] = la[1]; g[2] = la[2]; g[3] = lb[0]; g[4] = lb[1]; g[5] = lb[2];
+              g[6] = bsz[0]; g[7] = bsz[1]; g[8] = bsz[2]; g[9] = m.cap_r[a]; g[10] = nf[0]; g[11] = nf[1]; g[12] = nf[2];
+            }
+          }
+        END_LANES
+        // (2) the shallow edge contact of those pairs (MJX: closest box edge in front of two faces, see capbox_edges):
+        //     the 12 edges of a pair on 12 lanes, first maximum of the penetration by a lane reduction
+        const unsigned emine = warp_ballot(W, [](int, LaneRegs& R) { return R.nact != 0; });
+#pragma unroll 1
+        for (unsigned rem = warp_or_groups(W, emine); rem != 0u; rem &= rem - 1u) {
+          const int q = KFFS(rem) - 1;
+          const bool mine = (emine >> q) & 1u;
+          LANES(W, R)
+            R.f2 = -INFINITY;
+            if (mine && lane < 12) {
+              const float* g = S.estage[q];
+              const EdgeEval e1 = capbox_edge_lane(lane, g, g + 3, g[9], g + 6);
+              R.f2 = e1.epen;
+              if (e1.epen > 0.f) {                 // (only a positive penetration can become the contact: park the candidate)
+                R.acc[0] = e1.dir[0]; R.acc[1] = e1.dir[1]; R.acc[2] = e1.dir[2];
+                R.acc[3] = 0.5f * (e1.pa[0] + e1.pb[0] + e1.dir[0] * g[9]); R.acc[4] = 0.5f * (e1.pa[1] + e1.pb[1] + e1.dir[1] * g[9]);
+                R.acc[5] = 0.5f * (e1.pa[2] + e1.pb[2] + e1.dir[2] * g[9]);
+              }
+            }
+          END_LANES
+          const int bl = warp_argmax_first(W, [](int, LaneRegs& R) { return R.f2; });
+          LANES(W, R)
+            if (mine && lane == bl) {
+              float* g = S.eres[q];
+              g[0] = R.f2;
+              if (R.f2 > 0.f) { g[1] = R.acc[0]; g[2] = R.acc[1]; g[3] = R.acc[2]; g[4] = R.acc[3]; g[5] = R.acc[4]; g[6] = R.acc[5]; }
+            }
+          END_LANES
+        }
+        // (3) back on the pair's lane: edge contact or not, the pair's share of the collision cost, its previous-distance
+        //     record, world position and normal of the penetrating slots
+        LANES(W, R)
+          const int i = i0 + lane;
+          const bool edges = R.nact != 0;
+          R.nact = 0;
+          if (i < ntot) {
+            const int e = S.nlist[i] & 0x3fff, x = m.rp[e], a = KP_A(x), b = KP_B(x);
+            const bool wasfar = (S.nlist[i] >> 15) != 0, pref = ((S.nlist[i] >> 14) & 1) != 0, st = b < m.nsbox;
             const float* bpos = st ? m.sb_pos[b] : S.qpos + KM_NL;
             const float* bmat = st ? m.sb_mat[b] : S.bmat;
-            // (the list holds exactly the pairs that failed the far test: straight to the near path)
-            float la[3], lb[3];
-            CapBoxOut c;
-            const long long tn0 = TICK(); (void)tn0;
-            capbox_local(S.capA[a], S.capB[a], bpos, bmat, la, lb);
-            capsule_box_near<true>(la, lb, m.cap_r[a], st ? m.sb_size[b] : m.fb_size, c);
-            const float d0 = c.dist[0], d1 = c.dist[1];
-            if (lane == 0) { EVENT(W, 16, (int)(TICK() - tn0)); EVENT(W, 17, 1); }
+            if (edges) {
+              const float* g = S.eres[lane];
+              const float* nf = S.estage[lane] + 10;
+              const float bpen = g[0], minface = fminf(-R.f0, -R.f1);
+              if (bpen > 0.f) {
+                const bool parallel = fabsf(g[1] * nf[0] + g[2] * nf[1] + g[3] * nf[2]) > 0.99f;
+                if ((minface > 0.f ? bpen < minface : true) && !parallel) {
+                  R.f0 = -bpen;
+                  R.h[0] = g[4]; R.h[1] = g[5]; R.h[2] = g[6]; R.h[3] = g[1]; R.h[4] = g[2]; R.h[5] = g[3];
+                }
+              }
+            }
+            const float d0 = R.f0, d1 = R.f1;
             float cc = (d0 < 0.f ? 1.f : 0.f) + (d1 < 0.f ? 1.f : 0.f);
             float* pd = io.prevd + (2 * (e / KW)) * KW + (e & (KW - 1));       // the owner's slots: pass e / KW, capsule lane e % KW
             if (!io.first) {
               const float prev0 = wasfar ? 1.f : (pref ? S.nprev[e][0] : pd[0]), prev1 = wasfar ? 1.f : (pref ? S.nprev[e][1] : pd[KW]);
               cc += fmaxf((1.f - 0.005f) * prev0 - d0, 0.f) + fmaxf((1.f - 0.005f) * prev1 - d1, 0.f);
             }
-            if (!dummy) {
-              pd[0] = d0; pd[KW] = d1;
-              if (io.collision_row) { io.collision_row[KP_SLOT(x)] = d0; io.collision_row[KP_SLOT(x) + 1] = d1; }
-              R.cost_c += cc;                      // (cost_c is summed over the lanes at the end of the rollout: any lane may book a pair)
-            }
-            R.nact = dummy ? 4 : (d0 < 0.f ? 1 : 0) + (d1 < 0.f ? 2 : 0);       // bit 2: dummy record
+            pd[0] = d0; pd[KW] = d1;
+            if (io.collision_row) { io.collision_row[KP_SLOT(x)] = d0; io.collision_row[KP_SLOT(x) + 1] = d1; }
+            R.cost_c += cc;                        // (cost_c is summed over the lanes at the end of the rollout: any lane may book a pair)
+            R.nact = (d0 < 0.f ? 1 : 0) + (d1 < 0.f ? 2 : 0);
 #ifdef CEMK_X_NEARNOCON
             R.nact = 0;   // timing experiment only (wrong results): near pass without the contacts it finds
 #endif
@@ -1801,14 +1916,14 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
               // world position and normal of both slots: box frame -> world
 #pragma unroll
               for (int j = 0; j < 2; ++j) {
+                const float pj[3] = {R.h[6 * j], R.h[6 * j + 1], R.h[6 * j + 2]}, nj[3] = {R.h[6 * j + 3], R.h[6 * j + 4], R.h[6 * j + 5]};
                 float w[3], nw[3];
-                mat_vec(w, bmat, c.pos[j]); add3(w, w, bpos);
-                mat_vec(nw, bmat, c.nrm[j]);
+                mat_vec(w, bmat, pj); add3(w, w, bpos);
+                mat_vec(nw, bmat, nj);
                 normalize3(nw);
                 R.h[6 * j] = w[0]; R.h[6 * j + 1] = w[1]; R.h[6 * j + 2] = w[2];
                 R.h[6 * j + 3] = nw[0]; R.h[6 * j + 4] = nw[1]; R.h[6 * j + 5] = nw[2];
               }
-              R.f0 = d0; R.f1 = d1;
               R.f2 = m.cap_invw[a] + (st ? 0.f : m.fb_invw);
               R.tri = (R.tri & 0xffff) | (m.cap_link[a] << 16) | ((st ? 15 : KM_NL) << 20);     // links of the pair, parked above the triangle entries
             }
@@ -1816,13 +1931,13 @@ KFN void step_forward(Warp& W, const KModel& m, WarpSmemT<NC>& S, const StepIO& 
         END_LANES
         const long long tk1 = TICK(); (void)tk1;
         EVENT(W, 14, (int)(tk1 - tk0));
-        const int nnew = warp_excl_scan(W, [](int, LaneRegs& R) { return (R.nact & 1) + ((R.nact >> 1) & 1); }, [](int, LaneRegs& R, int o) { R.actmask = o; });
-        if (uniform_pass || warp_any_groups(W, nnew > 0)) {
+        const int nnew = warp_excl_scan(W, [](int, LaneRegs& R) { return (R.nact & 1) + (R.nact >> 1); }, [](int, LaneRegs& R, int o) { R.actmask = o; });
+        if (warp_any_groups(W, nnew > 0)) {
           LANES(W, R)
             if (R.nact) {
               const int l1 = (R.tri >> 16) & 15, l2raw = (R.tri >> 20) & 15, l2 = l2raw == 15 ? -1 : l2raw;
-              int o = (R.nact & 4) ? KM_NC_TOT - 1 : ncbcon + R.actmask;         // dummy: the last spill record (only a 48th contact would use it)
-              if (R.nact & 5) { put_contact<NC>(S, o, R.h, R.h + 3, nullptr, R.f0, R.f2, l1, l2); ++o; }
+              int o = ncbcon + R.actmask;
+              if (R.nact & 1) { put_contact<NC>(S, o, R.h, R.h + 3, nullptr, R.f0, R.f2, l1, l2); ++o; }
               if (R.nact & 2) put_contact<NC>(S, o, R.h + 6, R.h + 9, nullptr, R.f1, R.f2, l1, l2);
             }
           END_LANES

@@ -131,3 +131,29 @@ extern "C" void emu_capsule_box(const float* A, const float* B, float r, const f
     for (int k = 0; k < 3; ++k) { pos6[3 * j + k] = c.pos[j][k]; nrm6[3 * j + k] = c.nrm[j][k]; }
   }
 }
+
+// The near pass spreads the edge stage of a pair over 12 lanes (capbox_edge_lane + first-maximum reduction); this is the same
+// computation done serially, for fuzzing against capsule_box<true> (which runs capbox_edges): dist2 / pos6 / nrm6 in box coordinates.
+extern "C" void emu_capsule_box_lanes(const float* a, const float* b, float r, const float* bsize, float* dist2, float* pos6, float* nrm6,
+                                      float* dist2_serial, float* pos6_serial, float* nrm6_serial) {
+  CapBoxOut c, cs;
+  float nf[3];
+  const int nout = capsule_box_near<true, false>(a, b, r, bsize, c, nf);
+  capsule_box_near<true, true>(a, b, r, bsize, cs);
+  if (nout >= 2) {
+    float best = -INFINITY; EdgeEval be; be.epen = -1.f;
+    for (int e = 0; e < 12; ++e) { const EdgeEval ev = capbox_edge_lane(e, a, b, r, bsize); if (ev.epen > best) { best = ev.epen; be = ev; } }
+    const float minface = fminf(-c.dist[0], -c.dist[1]);
+    if (best > 0.f) {
+      const bool parallel = fabsf(be.dir[0] * nf[0] + be.dir[1] * nf[1] + be.dir[2] * nf[2]) > 0.99f;
+      if ((minface > 0.f ? best < minface : true) && !parallel) {
+        c.dist[0] = -best;
+        for (int k = 0; k < 3; ++k) { c.pos[0][k] = 0.5f * (be.pa[k] + be.pb[k] + be.dir[k] * r); c.nrm[0][k] = be.dir[k]; }
+      }
+    }
+  }
+  for (int j = 0; j < 2; ++j) {
+    dist2[j] = c.dist[j]; dist2_serial[j] = cs.dist[j];
+    for (int k = 0; k < 3; ++k) { pos6[3 * j + k] = c.pos[j][k]; nrm6[3 * j + k] = c.nrm[j][k]; pos6_serial[3 * j + k] = cs.pos[j][k]; nrm6_serial[3 * j + k] = cs.nrm[j][k]; }
+  }
+}

@@ -288,3 +288,33 @@ def test_kernel_capsule_box_matches_oracle_fuzz():
     assert dev_p.max() < 2e-4 and np.percentile(dev_p, 99) < 2e-5, (dev_p.max(), np.percentile(dev_p, 99))
     assert dev_n.max() < 5e-3 and np.percentile(dev_n, 99) < 2e-4, (dev_n.max(), np.percentile(dev_n, 99))
     assert n_near > 1500 and n_act > 1000 and n_edge > 100 and n_flip < 10, (n_near, n_act, n_edge, n_flip)
+
+
+def test_lane_parallel_edge_stage_equals_the_serial_one():
+    """The near pass evaluates the 12 box edges of a pair on 12 lanes (capbox_edge_lane, written in the edge's own coordinates
+    with component selects) and reduces to the first maximum; capsule_box<true> -- the version fuzzed against the oracle in
+    tests/test_oracle_colliders.py -- walks them serially (capbox_edges).  Same contact on random near poses, edge hits included."""
+    import ctypes as C
+    from emu_util import build
+    lib = C.CDLL(build())
+    rng = np.random.default_rng(8)
+    n_edge = 0
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    for _ in range(4000):
+        size = f(rng.uniform(0.02, 0.3, 3))
+        r = float(rng.uniform(0.02, 0.06))
+        # segments hovering around a box edge / corner region, so the edge stage runs and often wins
+        c = rng.uniform(-1, 1, 3) * (size + 1.2 * r)
+        d = rng.normal(size=3); d /= np.linalg.norm(d)
+        hl = rng.uniform(0.02, 0.2)
+        a, b = f(c - d * hl), f(c + d * hl)
+        outs = [np.zeros(2, np.float32), np.zeros(6, np.float32), np.zeros(6, np.float32), np.zeros(2, np.float32), np.zeros(6, np.float32), np.zeros(6, np.float32)]
+        lib.emu_capsule_box_lanes(p(a), p(b), C.c_float(r), p(size), *[p(o) for o in outs])
+        d2, p6, n6, d2s, p6s, n6s = outs
+        np.testing.assert_allclose(d2, d2s, atol=2e-6)
+        if d2s[0] < 0 or d2s[1] < 0:
+            np.testing.assert_allclose(p6, p6s, atol=1e-4)      # (the foot point on a near-parallel edge moves with the summation order)
+            np.testing.assert_allclose(n6, n6s, atol=2e-3)
+        n_edge += int(abs(n6s[:3]).max() < 0.999)              # slot 0 carries an edge contact (normal not a face normal)
+    assert n_edge > 100
