@@ -1,5 +1,7 @@
-"""Smallest end-to-end case for compute-sanitizer (one tool per gpurun call):
-    compute-sanitizer --tool racecheck python tools/sanitize_small.py"""
+"""Smallest end-to-end case with robot contacts, for `compute-sanitizer --tool memcheck python tools/sanitize_small.py`
+(one tool per gpurun call).  Shared-memory hazards between the lanes of a sample are NOT checked this way -- racecheck does
+not follow named barriers over 16-lane groups; that check is the race-detecting emulation build of the same source,
+tests/test_emu_race.py (csrc/warp_dsl.h, CEMK_EMU_RACE)."""
 import os
 import sys
 

@@ -5,7 +5,7 @@ set -e
 cd "$(dirname "$0")/.."
 for v in $1; do
   W=${v%%:*}; M=${v##*:}
-  (cd manipulator_mujoco_b200/csrc && nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 ${SYNCFLAGS--DCEMK_STEP_SYNC -DCEMK_PHASE_SYNC=2} \
+  (cd manipulator_mujoco_b200/csrc && nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 ${SYNCFLAGS--DCEMK_STEP_SYNC -DCEMK_PHASE_SYNC=18} \
      -use_fast_math -DROLLOUT_WARPS=$W -DROLLOUT_MINB=$M $EXTRA -Xptxas -v -shared -Xcompiler -fPIC -o ../libcemk.so cemk.cu 2>&1 \
      | grep -A2 "k_rolloutILi20" | grep -E "registers|spill" | tr '\n' ' ')
   python bench.py --steps 3 --warmup 2 --no-cpu-baseline 2>&1 | tail -1 | python -c "
