@@ -277,6 +277,7 @@ def main():
         with contextlib.redirect_stdout(io.StringIO()):
             pl = cem_planner(num_dof=6, num_batch=Bg, num_steps=T, timestep=DT, maxiter_cem=1, num_elite=ELITE, w_pos=W_POS, w_rot=W_ROT,
                              w_col=W_COL, maxiter_projection=PROJ_IT, device=dev, process_group=pg)
+        pl.cache_normal_draws = False      # the timed step draws its normals like the reference's cem_iter does (mjx_planner.py:315)
         lib, h = pl._lib, pl._h
         state_term = torch.cat([q0, z6, z6, z6, z6]).unsqueeze(0).expand(Bl, 30).contiguous()
         mean0 = torch.zeros(pl.nvar, device=dev)

@@ -159,22 +159,74 @@ static_assert(((sizeof(KModel) + 15) & ~size_t(15)) + ROLLOUT_WARPS * GPW * size
               "rollout scratch exceeds the 227 KB of shared memory a CTA can have");
 
 // ---------------------------------------------------------------------------------------------- sampling
-// L = chol(cov + 0.003 I), lower, row-major [n][n] (n = nvar <= MAXVAR); one CTA of 16 x 16 threads.  Right-looking on the
-// unscaled columns (A[i][k] -= A[i][j] A[k][j] / A[j][j], one barrier per column; column j is final after
-// step j), scaled by 1 / sqrt(A[j][j]) in a last pass.  (A left-looking variant with four lanes per row dot product and
-// one barrier per column was measured slower: 43 vs 33 us.)
+// L = chol(cov + 0.003 I), lower, row-major [n][n] (n = nvar <= MAXVAR); one CTA of 256 threads.  Right-looking on the
+// unscaled columns: A[i][k] -= (A[i][j] / A[j][j]) A[k][j] for j = 0 .. k-1 in this order for every element, column j is
+// final after step j, scaled by 1 / sqrt(A[j][j]) in a last pass.  The updates are applied in panels of CHOL_NB columns:
+// inside a panel every column step touches only the panel's columns (at most 2 elements per thread, one barrier), then
+// one pass applies the panel's CHOL_NB updates to every trailing element -- the same operations on the same operands in
+// the same order per element as the column-at-a-time loop (bit-identical, 33 us), with the long per-column trailing
+// sweep off the barrier chain.  (A left-looking variant with four lanes per row dot product was slower: 43 us.)
+#define CHOL_NB 8
+#define CHOL_KU ((MAXVAR + 15) / 16)
+static_assert(CHOL_NB == 8, "k_chol66 deals the panel columns with threadIdx.x & 7");
 __global__ void __launch_bounds__(256) k_chol66(int n, const float* __restrict__ cov, float* __restrict__ L) {
   __shared__ float A[MAXVAR][MAXVAR + 1];
+  __shared__ float P[MAXVAR];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   for (int i = ty; i < n; i += 16)
     for (int j = tx; j < n; j += 16) A[i][j] = cov[i * n + j] + (i == j ? 0.003f : 0.f);
   __syncthreads();
-  for (int j = 0; j < n - 1; ++j) {
-    const float p = __frcp_rn(A[j][j]);                  // (the library is built with -use_fast_math for k_rollout; the small
+  const int pc = threadIdx.x & (CHOL_NB - 1), pr = threadIdx.x >> 3;      // panel steps: thread = (row offset, panel column)
+  for (int j0 = 0; j0 < n - 1; j0 += CHOL_NB) {
+    const int je = j0 + CHOL_NB < n ? j0 + CHOL_NB : n;
+    for (int j = j0; j < je && j < n - 1; ++j) {
+      // every load of the step is issued before the first dependent instruction (rows i0, i0 + 32, i0 + 64)
+      const int k = j + 1 + pc, i0 = j + 1 + pr;
+      const bool kon = k < je;
+      const float ajj = A[j][j], akj = kon ? A[k][j] : 0.f;
+      float aij[3], aik[3]; bool on[3];
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+        const int i = i0 + 32 * m;
+        on[m] = kon && i < n && k <= i;
+        aij[m] = on[m] ? A[i][j] : 0.f; aik[m] = on[m] ? A[i][k] : 0.f;
+      }
+      const float p = __frcp_rn(ajj);                    // (the library is built with -use_fast_math for k_rollout; the small
                                                          //  kernels spell out IEEE division / sqrt / exp so the flag does not touch them)
-    for (int i = j + 1 + ty; i < n; i += 16) {
-      const float aij = A[i][j] * p;
-      for (int k = j + 1 + tx; k <= i; k += 16) A[i][k] -= aij * A[k][j];
+      if (threadIdx.x == 0) P[j] = p;
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+        const float s = aij[m] * p;
+        aik[m] -= s * akj;
+        if (on[m]) A[i0 + 32 * m][k] = aik[m];
+      }
+      __syncthreads();
+    }
+    if (je < n) {
+      float pp[CHOL_NB];
+#pragma unroll
+      for (int q = 0; q < CHOL_NB; ++q) pp[q] = P[j0 + q];
+      for (int i = je + ty; i < n; i += 16) {
+        float ai[CHOL_NB];
+#pragma unroll
+        for (int q = 0; q < CHOL_NB; ++q) ai[q] = A[i][j0 + q] * pp[q];
+        // up to CHOL_KU elements of row i per thread, their CHOL_NB-long chains interleaved
+        float a[CHOL_KU], ak[CHOL_KU][CHOL_NB]; bool on[CHOL_KU];
+#pragma unroll
+        for (int u = 0; u < CHOL_KU; ++u) {
+          const int k = je + tx + 16 * u;
+          on[u] = k <= i;
+          a[u] = on[u] ? A[i][k] : 0.f;
+#pragma unroll
+          for (int q = 0; q < CHOL_NB; ++q) ak[u][q] = on[u] ? A[k][j0 + q] : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < CHOL_NB; ++q)
+#pragma unroll
+          for (int u = 0; u < CHOL_KU; ++u) a[u] -= ai[q] * ak[u][q];
+#pragma unroll
+        for (int u = 0; u < CHOL_KU; ++u) if (on[u]) A[i][je + tx + 16 * u] = a[u];
+      }
     }
     __syncthreads();
   }
@@ -184,26 +236,39 @@ __global__ void __launch_bounds__(256) k_chol66(int n, const float* __restrict__
       L[i * n + j] = j > i ? 0.f : (i == j ? d : __fdiv_rn(A[i][j], d));
     }
 }
-// xi[b][i] = mean[i] + sum_{j<=i} L[i][j] z[b][j]
-__global__ void __launch_bounds__(256) k_sample(int B, int n, const float* __restrict__ z, const float* __restrict__ mean,
-                                                const float* __restrict__ L, float* __restrict__ xi) {
-  __shared__ float sL[MAXVAR][MAXVAR + 1];
-  __shared__ float sz[4][MAXVAR];
-  for (int e = threadIdx.x; e < n * n; e += blockDim.x) sL[e / n][e % n] = L[e];
-  const int b0 = blockIdx.x * 4;
-  for (int e = threadIdx.x; e < 4 * n; e += blockDim.x) {
-    int b = b0 + e / n;
-    sz[e / n][e % n] = b < B ? z[(size_t)b * n + e % n] : 0.f;
+// xi[b][i] = mean[i] + sum_{j<=i} L[i][j] z[b][j] (the sum runs j = 0 .. i in this order).  One CTA per SAMPLE_TILE
+// consecutive samples: L and the tile's draws in shared memory, a warp works on one row i for different samples (L[i][j]
+// is a broadcast, the triangular trip count is uniform in the warp), results leave through a shared tile so that the
+// global reads and writes are contiguous.
+#define SAMPLE_TILE 28
+#define SAMPLE_THREADS 1024      // the kernel is a few dependent memory round trips long: many threads = few loads per thread
+__global__ void __launch_bounds__(SAMPLE_THREADS) k_sample(int B, int n, const float* __restrict__ z, const float* __restrict__ mean,
+                                                           const float* __restrict__ L, float* __restrict__ xi) {
+  extern __shared__ float ssm[];
+  const int ld = n + 1, zs = n | 1;                // odd strides: rows i / samples bl fall on different banks
+  float* sL = ssm;                                 // [n][ld]
+  float* sz = sL + n * ld;                         // [SAMPLE_TILE][zs]
+  float* sx = sz + SAMPLE_TILE * zs;               // [SAMPLE_TILE][n]
+  float* smu = sx + SAMPLE_TILE * n;               // [n]
+  const int b0 = blockIdx.x * SAMPLE_TILE, nb = B - b0 < SAMPLE_TILE ? B - b0 : SAMPLE_TILE;
+#pragma unroll 5
+  for (int e = threadIdx.x; e < n * n; e += SAMPLE_THREADS) { const int i = e / n; sL[i * ld + (e - i * n)] = L[e]; }
+#pragma unroll 2
+  for (int e = threadIdx.x; e < nb * n; e += SAMPLE_THREADS) { const int bl = e / n; sz[bl * zs + (e - bl * n)] = z[(size_t)b0 * n + e]; }
+  if (threadIdx.x < n) smu[threadIdx.x] = mean[threadIdx.x];
+  __syncthreads();
+  for (int e = threadIdx.x; e < SAMPLE_TILE * n; e += SAMPLE_THREADS) {
+    const int i = e / SAMPLE_TILE, bl = e - i * SAMPLE_TILE;
+    if (bl >= nb) continue;
+    const float* Li = sL + i * ld; const float* zb = sz + bl * zs;
+    float s = 0.f;
+    for (int j = 0; j <= i; ++j) s += Li[j] * zb[j];
+    sx[bl * n + i] = smu[i] + s;
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < 4 * n; e += blockDim.x) {
-    int bl = e / n, i = e % n, b = b0 + bl;
-    if (b >= B) continue;
-    float s = 0.f;
-    for (int j = 0; j <= i; ++j) s += sL[i][j] * sz[bl][j];
-    xi[(size_t)b * n + i] = mean[i] + s;
-  }
+  for (int e = threadIdx.x; e < nb * n; e += SAMPLE_THREADS) xi[(size_t)b0 * n + e] = sx[e];
 }
+static size_t sample_smem(int n) { return sizeof(float) * ((size_t)n * (n + 1) + SAMPLE_TILE * (size_t)(n | 1) + SAMPLE_TILE * (size_t)n + n); }
 
 // ---------------------------------------------------------------------------------------------- jax.random stream
 // Threefry-2x32 (20 rounds) as used by jax.random (jax/_src/prng.py, pinned jax==0.5.3 in the reference's
@@ -267,7 +332,7 @@ __global__ void __launch_bounds__(256) k_jax_normal(uint32_t k0, uint32_t k1, in
 }
 
 // ---------------------------------------------------------------------------------------------- projection
-// One lane per (sample, dof) problem, four warps per group of 32 problems.  Q_inv of the reference is block
+// Four lanes per (sample, dof) problem.  Q_inv of the reference is block
 // diagonal per DOF, and with A_c = [G_c; -G_c] the slack / residual / multiplier updates of
 // mjx_planner.py:196-223 collapse to
 //   u_c   = G_c x                                  c in {velocity, acceleration, position}
@@ -278,24 +343,35 @@ __global__ void __launch_bounds__(256) k_jax_normal(uint32_t k0, uint32_t k1, in
 // i.e. the reference iteration with s and res eliminated.  e_c is formed per time step *before* the
 // transpose product -- forming G^T G x - G^T clip(.) instead cancels catastrophically in float32
 // (|G^T G| ~ 1e6 at T = 16).
-// Mapping: the 32 lanes of a warp hold 32 different problems and walk the same basis rows, so a row
-// (11 coefficients padded to 12 floats) costs three broadcast 128-bit shared-memory loads for 33 FMAs per
-// lane.  The time steps are dealt round-robin to the PROJ_SLICES warps of the CTA, which own the same 32
-// problems; their partial G^T e / G^T h are exchanged through shared memory and summed in a fixed order
-// (so all warps carry identical iterates).  One thread per problem alone gives a B200 only ~5 warps per
-// SM on a 1e5-long dependent FMA chain; splitting a problem over lanes instead makes every lane fetch its
-// own rows and runs into the shared-memory bandwidth.
+// Mapping: a warp holds 8 problems x 4 time slices (lane = 8 slice + problem); slice s walks the basis rows t = s, s + 4, ...
+// A row (NC coefficients padded to PC floats) is read with PC / 4 128-bit shared-memory loads (four distinct rows per warp
+// instruction, one per quarter warp) for 3 NC FMAs per lane.  The partial G^T e / G^T h of the four slices are exchanged with
+// shuffles inside the quad and summed in slice order by every lane (so the four lanes of a problem carry identical iterates):
+// no block barrier after the prologue, a CTA is just PROJ_WARPS independent warps sharing the basis in shared memory.
+// One thread per problem alone gives a B200 only ~5 warps per SM on a 1e5-long dependent FMA chain; splitting a problem
+// over more lanes runs into the shared-memory bandwidth.
+// Occupancy decides this kernel: 6 B / 8 warps have to be resident at once or the tail wave runs the SMs nearly empty
+// (4096 samples: 3072 warps; at 118 registers 16 warps fit an SM = 1.3 waves, 175 us).  Registers are
+// allocated per SM quadrant, 16384 each: 3072 warps = 20.8 per SM means six warps in some quadrant = at most 80 registers,
+// and a CTA size of 7 (or 3 or 1) warps so that 21 per SM is reachable.  The per-problem vectors that are touched once per
+// iteration (xs, cst, the multiplier sum) sit in per-thread shared-memory columns, which brings the kernel to 80 registers:
+// 3 CTAs of 7 warps per SM = 3108 warp slots, one wave.
 #ifndef PROJ_UNROLL
 #define PROJ_UNROLL 2
 #endif
 constexpr int kProjUnroll = PROJ_UNROLL;
-#ifndef PROJ_SLICES
 #define PROJ_SLICES 4
+#define PROJ_PPW (32 / PROJ_SLICES)      // problems per warp
+#ifndef PROJ_WARPS
+#define PROJ_WARPS 7
+#endif
+#ifndef PROJ_MINB
+#define PROJ_MINB 3
 #endif
 // NC = Bernstein coefficients per DOF (order + 1), a template parameter so that the iterates stay in registers; a basis
-// row is padded to PC = 4 ceil(NC / 4) floats and read with 128-bit broadcast loads.
+// row is padded to PC = 4 ceil(NC / 4) floats.
 template <int NC>
-__global__ void __launch_bounds__(32 * PROJ_SLICES) k_project(int B, int T, int iters, const float* __restrict__ G,
+__global__ void __launch_bounds__(32 * PROJ_WARPS, NC <= 11 ? PROJ_MINB : 1) k_project(int B, int T, int iters, const float* __restrict__ G,
                                                               const float* __restrict__ Kc, const float* __restrict__ xi,
                                                               const float* __restrict__ state_term, float* __restrict__ xi_f,
                                                               float* __restrict__ thetadot) {
@@ -304,17 +380,31 @@ __global__ void __launch_bounds__(32 * PROJ_SLICES) k_project(int B, int T, int 
   float* sG = sm;                        // [3][T][PC]
   float* sKpp = sm + 3 * T * PC;         // [NC][PC]
   float* sK = sKpp + NC * PC;            // Kpe[5 NC] bounds[3], padded to KPAD
-  float* sX = sK + KPAD;                 // [PROJ_SLICES][2 NC][32] partial sums
+  float* sP = sK + KPAD;                 // [3 NC][blockDim.x] per-thread columns: xs, cst, lam
   for (int e = threadIdx.x; e < 3 * T * PC; e += blockDim.x) { const int r = e / PC, k = e % PC; sG[e] = k < NC ? G[r * NC + k] : 0.f; }
   for (int e = threadIdx.x; e < NC * PC; e += blockDim.x) { const int r = e / PC, k = e % PC; sKpp[e] = k < NC ? Kc[r * NC + k] : 0.f; }
   for (int e = threadIdx.x; e < 5 * NC + 3; e += blockDim.x) sK[e] = Kc[NC * NC + e];
   __syncthreads();
-  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
-  int prob = blockIdx.x * 32 + lane;
-  const bool act = prob < B * 6;         // idle lanes of the last CTA still take part in the barriers
+#ifndef PROJ_LANEMAP
+#define PROJ_LANEMAP 1
+#endif
+#if PROJ_LANEMAP
+  // lane = 8 slice + problem: the eight lanes of a quarter warp (one phase of a 128-bit shared-memory load) read the same row
+  const int lane = threadIdx.x & 31, slice = lane >> 3, pl = lane & (PROJ_PPW - 1);
+#define PROJ_SRC(q) ((q) * PROJ_PPW + pl)
+#else
+  const int lane = threadIdx.x & 31, slice = lane & (PROJ_SLICES - 1), pl = lane >> 2;
+#define PROJ_SRC(q) ((lane & ~(PROJ_SLICES - 1)) | (q))
+#endif
+  int prob = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * PROJ_PPW + pl;
+  const bool act = prob < B * 6;         // idle lanes still take part in the shuffles
   if (!act) prob = B * 6 - 1;
   const int b = prob / 6, d = prob % 6;
   const float* Kpe = sK; const float* bnd = sK + 5 * NC;
+  float* myxs = sP + threadIdx.x;
+  float* mycst = sP + NC * blockDim.x + threadIdx.x;
+  float* mylam = sP + 2 * NC * blockDim.x + threadIdx.x;
+  const int cs = blockDim.x;
   auto rowp = [](const float* p, float* g) {
 #pragma unroll
     for (int q = 0; q < PC / 4; ++q) {
@@ -325,19 +415,24 @@ __global__ void __launch_bounds__(32 * PROJ_SLICES) k_project(int B, int T, int 
       if (4 * q + 3 < NC) g[4 * q + 3] = a.w;
     }
   };
-  float x[NC], lam[NC], xs[NC], beq[5], cst[NC], rh[NC], re[NC];
+  float x[NC], rh[NC], re[NC];
+  {
+    float beq[5];
 #pragma unroll
-  for (int k = 0; k < NC; ++k) { xs[k] = xi[(size_t)b * NV + d * NC + k]; lam[k] = 0.f; x[k] = 0.f; rh[k] = 0.f; }
+    for (int k = 0; k < NC; ++k) { myxs[k * cs] = xi[(size_t)b * NV + d * NC + k]; mylam[k * cs] = 0.f; x[k] = 0.f; rh[k] = 0.f; }
 #pragma unroll
-  for (int k = 0; k < 5; ++k) beq[k] = state_term[(size_t)b * 30 + k * 6 + d];
+    for (int k = 0; k < 5; ++k) beq[k] = state_term[(size_t)b * 30 + k * 6 + d];
 #pragma unroll
-  for (int i = 0; i < NC; ++i) { float s = 0.f; for (int k = 0; k < 5; ++k) s += Kpe[i * 5 + k] * beq[k]; cst[i] = s; }
+    for (int i = 0; i < NC; ++i) { float s = 0.f; for (int k = 0; k < 5; ++k) s += Kpe[i * 5 + k] * beq[k]; mycst[i * cs] = s; }
+  }
   for (int it = 0; it < iters; ++it) {
-    float rhs[NC];
+    {
+      float rhs[NC];
 #pragma unroll
-    for (int k = 0; k < NC; ++k) { rhs[k] = lam[k] + xs[k] + rh[k]; rh[k] = 0.f; re[k] = 0.f; }
+      for (int k = 0; k < NC; ++k) { rhs[k] = mylam[k * cs] + myxs[k * cs] + rh[k]; rh[k] = 0.f; re[k] = 0.f; }
 #pragma unroll
-    for (int i = 0; i < NC; ++i) { float kr[NC]; rowp(sKpp + i * PC, kr); float s = cst[i]; for (int k = 0; k < NC; ++k) s += kr[k] * rhs[k]; x[i] = s; }
+      for (int i = 0; i < NC; ++i) { float kr[NC]; rowp(sKpp + i * PC, kr); float s = mycst[i * cs]; for (int k = 0; k < NC; ++k) s += kr[k] * rhs[k]; x[i] = s; }
+    }
     for (int c = 0; c < 3; ++c) {
       const float bc = bnd[c];
       const float* Gc = sG + c * T * PC;
@@ -355,20 +450,15 @@ __global__ void __launch_bounds__(32 * PROJ_SLICES) k_project(int B, int T, int 
         for (int k = 0; k < NC; ++k) { re[k] += g[k] * e; rh[k] += g[k] * h; }
       }
     }
-    // exchange the partial sums of the slices
-    float* mine = sX + slice * 2 * NC * 32 + lane;
-#pragma unroll
-    for (int k = 0; k < NC; ++k) { mine[k * 32] = re[k]; mine[(NC + k) * 32] = rh[k]; }
-    __syncthreads();
+    // exchange the partial sums of the four slices of a problem; every lane adds them in slice order
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
       float se = 0.f, sh = 0.f;
 #pragma unroll
-      for (int q = 0; q < PROJ_SLICES; ++q) { se += sX[(q * 2 * NC + k) * 32 + lane]; sh += sX[(q * 2 * NC + NC + k) * 32 + lane]; }
-      re[k] = se; rh[k] = sh;
-      lam[k] -= se;
+      for (int q = 0; q < PROJ_SLICES; ++q) { se += __shfl_sync(0xffffffffu, re[k], PROJ_SRC(q)); sh += __shfl_sync(0xffffffffu, rh[k], PROJ_SRC(q)); }
+      rh[k] = sh;
+      mylam[k * cs] -= se;
     }
-    __syncthreads();
   }
   if (!act) return;
   if (slice == 0) {
@@ -389,9 +479,15 @@ __global__ void __launch_bounds__(32 * PROJ_SLICES) k_project(int B, int T, int 
   }
 }
 template <int NC>
-static int project_smem(int T) {
+static int project_smem(int T, int threads) {
   constexpr int PC = (NC + 3) / 4 * 4, KPAD = (5 * NC + 3 + 3) / 4 * 4;
-  return (3 * T * PC + NC * PC + KPAD + PROJ_SLICES * 2 * NC * 32) * (int)sizeof(float);
+  return (3 * T * PC + NC * PC + KPAD + 3 * NC * threads) * (int)sizeof(float);
+}
+// warps per CTA: PROJ_WARPS when the problems fill the GPU, fewer (more CTAs) for small batches
+static int project_warps(int B) {
+  const int warps = (B * 6 + PROJ_PPW - 1) / PROJ_PPW;
+  const int w = (warps + 148 * PROJ_MINB - 1) / (148 * PROJ_MINB);
+  return w < 1 ? 1 : (w > PROJ_WARPS ? PROJ_WARPS : w);
 }
 // run `body` with NC = ncoef as a compile-time constant
 #define CEMK_FOR_NCOEF(ncoef, body) switch (ncoef) { \
@@ -529,6 +625,58 @@ __global__ void k_bitonic_global(unsigned long long* __restrict__ keys, int npow
   unsigned long long a = keys[i], b = keys[p];
   if ((a > b) == up) { keys[i] = b; keys[p] = a; }
 }
+// Small inputs (n <= RANK_MAXN, every per-GPU shard of the weak-scaling configurations): the sorted position of a key is the
+// number of keys below it (keys are unique), so one launch does what key generation + 78 compare-exchange stages + the
+// gather did: every CTA builds all n keys in shared memory, takes RANK_CAND candidates (one per lane), its warps count
+// over disjoint parts of the key array (broadcast 64-bit loads), and the candidates whose position is below k copy their
+// row straight to its place.  n^2 / 2 comparisons spread over the whole GPU (4096 keys: 1.7e7, a few microseconds)
+// instead of a latency chain of barriers in one CTA (37 us).
+#define RANK_CAND 32
+#define RANK_MAXN 8192
+#define RANK_THREADS 512
+__global__ void __launch_bounds__(RANK_THREADS) k_rank_select(int NVAR, int n, const float* __restrict__ cost, int stride, int idx_base,
+                                                              unsigned long long* __restrict__ keys_sorted, int* __restrict__ idx_sorted, int k,
+                                                              const float* __restrict__ xi, float* __restrict__ xi_elite,
+                                                              float* __restrict__ cost_elite, float* __restrict__ pack) {
+  extern __shared__ unsigned long long rk_keys[];
+  __shared__ int cnt[RANK_CAND];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = RANK_THREADS / 32;
+  for (int e = tid; e < n; e += RANK_THREADS) rk_keys[e] = ((unsigned long long)float_order(cost[(size_t)e * stride]) << 32) | (unsigned int)e;
+  if (tid < RANK_CAND) cnt[tid] = 0;
+  __syncthreads();
+  const int base = blockIdx.x * RANK_CAND, i = base + lane;
+  const unsigned long long ki = i < n ? rk_keys[i] : 0ull;
+  const int chunk = (n + nw - 1) / nw, j0 = warp * chunk, j1 = j0 + chunk < n ? j0 + chunk : n;
+  int c = 0;
+#pragma unroll 8
+  for (int j = j0; j < j1; ++j) c += rk_keys[j] < ki ? 1 : 0;
+  atomicAdd(&cnt[lane], c);
+  __syncthreads();
+  if (tid < RANK_CAND && i < n) {
+    const int r = cnt[tid];
+    if (idx_sorted) idx_sorted[r] = i + idx_base;
+    if (keys_sorted) keys_sorted[r] = ki;
+  }
+  if (k <= 0) return;
+  const int W = pack ? NVAR + 2 : NVAR;
+  for (int e = tid; e < RANK_CAND * W; e += RANK_THREADS) {
+    const int cnd = e / W, col = e - cnd * W, src = base + cnd;
+    if (src >= n) break;
+    const int r = cnt[cnd];
+    if (r >= k) continue;
+    if (pack) pack[(size_t)r * W + col] = col < NVAR ? xi[(size_t)src * NVAR + col] : (col == NVAR ? cost[(size_t)src * stride] : (float)(src + idx_base));
+    else {
+      xi_elite[(size_t)r * NVAR + col] = xi[(size_t)src * NVAR + col];
+      if (col == 0) cost_elite[r] = cost[(size_t)src * stride];
+    }
+  }
+}
+static void rank_select(cemk_handle* h, int n, const float* cost, int stride, int idx_base, unsigned long long* keys, int* idx_sorted, int k,
+                        const float* xi, float* xi_elite, float* cost_elite, float* pack, cudaStream_t st) {
+  k_rank_select<<<(n + RANK_CAND - 1) / RANK_CAND, RANK_THREADS, sizeof(unsigned long long) * n, st>>>(h->nvar, n, cost, stride, idx_base, keys, idx_sorted,
+                                                                                                     k, xi, xi_elite, cost_elite, pack);
+  h->launches += 1;
+}
 __global__ void k_finish_sort(int NVAR, int n, const unsigned long long* __restrict__ keys, int idx_base, int* __restrict__ idx_sorted, int k,
                               const float* __restrict__ cost, int stride, const float* __restrict__ xi, float* __restrict__ xi_elite,
                               float* __restrict__ cost_elite, const int* __restrict__ aux_in, int* __restrict__ aux_out) {
@@ -572,29 +720,52 @@ __global__ void k_unpack_sorted(int NVAR, const unsigned long long* __restrict__
 // (cost, row) order = its position in its own block + for every other block the count of records with a smaller key (blocks
 // before it also count equal keys: rows there are lower).  One thread per record, a binary search per block; records whose
 // position is below k are written straight to their place.  Replaces key generation + a bitonic sort of nlist * kl keys.
-__global__ void __launch_bounds__(256) k_merge_lists(int NVAR, int nlist, int kl, int k, const float* __restrict__ packed,
-                                                     float* __restrict__ xi_elite, float* __restrict__ cost_elite, int* __restrict__ gidx_elite) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x, PACKW = NVAR + 2;
-  if (r >= nlist * kl) return;
-  const int a = r / kl, p = r - a * kl;
-  const unsigned key = float_order(packed[(size_t)r * PACKW + NVAR]);
-  int pos = p;
-  for (int b = 0; b < nlist; ++b) {
-    if (b == a) continue;
-    const float* blk = packed + (size_t)b * kl * PACKW + NVAR;
-    int lo = 0, hi = kl;                              // first record of block b that does not precede this one
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      const unsigned km = float_order(blk[(size_t)mid * PACKW]);
-      if (km < key || (km == key && b < a)) lo = mid + 1; else hi = mid;
-    }
-    pos += lo;
+// STAGED: the (order-mapped) cost keys of all records are first copied to shared memory (nlist * kl <= MERGE_MAXKEYS), so
+// the nlist - 1 binary searches of a record run at shared-memory instead of L2 latency.  The winners of a CTA are then
+// compacted and their rows copied element-wise by all threads with several independent loads in flight per thread (a thread
+// copying its own 68-float row alone was a chain of 68 L2 round trips: most of the 39 us at 8 lists of 1638).
+#define MERGE_MAXKEYS (48 * 1024)
+#define MERGE_THREADS 1024
+template <bool STAGED>
+__global__ void __launch_bounds__(MERGE_THREADS) k_merge_lists(int NVAR, int nlist, int kl, int k, const float* __restrict__ packed,
+                                                               float* __restrict__ xi_elite, float* __restrict__ cost_elite, int* __restrict__ gidx_elite) {
+  extern __shared__ unsigned mk[];
+  __shared__ int wsrc[MERGE_THREADS], wpos[MERGE_THREADS], nwin;
+  const int tid = threadIdx.x, n = nlist * kl, PACKW = NVAR + 2;
+  if (tid == 0) nwin = 0;
+  if (STAGED) {
+#pragma unroll 8
+    for (int e = tid; e < n; e += MERGE_THREADS) mk[e] = float_order(packed[(size_t)e * PACKW + NVAR]);
   }
-  if (pos >= k) return;
-  const float* rec = packed + (size_t)r * PACKW;
-  for (int c = 0; c < NVAR; ++c) xi_elite[(size_t)pos * NVAR + c] = rec[c];
-  cost_elite[pos] = rec[NVAR];
-  gidx_elite[pos] = (int)rec[NVAR + 1];
+  __syncthreads();
+  const int r = blockIdx.x * MERGE_THREADS + tid;
+  if (r < n) {
+    const int a = r / kl, p = r - a * kl;
+    const unsigned key = STAGED ? mk[r] : float_order(packed[(size_t)r * PACKW + NVAR]);
+    int pos = p;
+    for (int b = 0; b < nlist && pos < k; ++b) {
+      if (b == a) continue;
+      const float* blk = packed + (size_t)b * kl * PACKW + NVAR;
+      int lo = 0, hi = kl;                              // first record of block b that does not precede this one
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const unsigned km = STAGED ? mk[b * kl + mid] : float_order(blk[(size_t)mid * PACKW]);
+        if (km < key || (km == key && b < a)) lo = mid + 1; else hi = mid;
+      }
+      pos += lo;
+    }
+    if (pos < k) { const int w = atomicAdd(&nwin, 1); wsrc[w] = r; wpos[w] = pos; }
+  }
+  __syncthreads();
+  const int tot = nwin * PACKW;
+#pragma unroll 4
+  for (int e = tid; e < tot; e += MERGE_THREADS) {
+    const int w = e / PACKW, c = e - w * PACKW, ps = wpos[w];
+    const float v = packed[(size_t)wsrc[w] * PACKW + c];
+    if (c < NVAR) xi_elite[(size_t)ps * NVAR + c] = v;
+    else if (c == NVAR) cost_elite[ps] = v;
+    else gidx_elite[ps] = (int)v;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- mean / covariance
@@ -706,6 +877,9 @@ int cemk_create(const void* kmodel, int kmodel_bytes, int device, cemk_handle** 
   CK(cudaFuncSetAttribute(k_rollout<KM_NC_FAST, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rollout_smem<KM_NC_FAST, 4>()));
   CK(cudaFuncSetAttribute(k_rollout<KM_NC_BIG, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)rollout_smem<KM_NC_BIG, 1>()));
+  CK(cudaFuncSetAttribute(k_rank_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(unsigned long long) * RANK_MAXN)));
+  CK(cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sample_smem(MAXVAR)));
+  CK(cudaFuncSetAttribute(k_merge_lists<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(unsigned) * MERGE_MAXKEYS)));
   *out = h;
   return CEMK_OK;
 }
@@ -745,7 +919,8 @@ int cemk_set_horizon(cemk_handle* h, int T, const float* G, const float* Kpp, co
   CK(cudaMemcpy(h->d_K, kc, (nc * nc + nc * 5 + 3) * sizeof(float), cudaMemcpyHostToDevice));
   h->T = T;
   int smem = 0;
-  CEMK_FOR_NCOEF(nc, { smem = project_smem<NC>(T); CK(cudaFuncSetAttribute(k_project<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); });
+  CEMK_FOR_NCOEF(nc, { smem = project_smem<NC>(T, 32 * PROJ_WARPS); CK(cudaFuncSetAttribute(k_project<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                       CK(cudaFuncSetAttribute(k_project<NC>, cudaFuncAttributePreferredSharedMemoryCarveout, 100 * 3 * smem / (228 * 1024) + 8)); });
   if (smem > 227 * 1024) return set_err(CEMK_ERR_ARG, "cemk_set_horizon: horizon too long for the projection kernel's shared memory");
   return CEMK_OK;
 }
@@ -755,7 +930,7 @@ int cemk_sample(cemk_handle* h, int B, const float* z, const float* mean, const 
   DevGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   k_chol66<<<1, 256, 0, st>>>(h->nvar, cov, chol_ws);
-  k_sample<<<(B + 3) / 4, 256, 0, st>>>(B, h->nvar, z, mean, chol_ws, xi);
+  k_sample<<<(B + SAMPLE_TILE - 1) / SAMPLE_TILE, SAMPLE_THREADS, sample_smem(h->nvar), st>>>(B, h->nvar, z, mean, chol_ws, xi);
   h->launches += 2;
   CK(cudaPeekAtLastError());
   return CEMK_OK;
@@ -776,7 +951,8 @@ int cemk_project(cemk_handle* h, int B, int iters, const float* xi, const float*
   DevGuard guard(h->device);
   if (!h->d_G) return set_err(CEMK_ERR_ARG, "cemk_project: cemk_set_horizon has not been called");
   const int T = h->T;
-  CEMK_FOR_NCOEF(h->ncoef, (k_project<NC><<<(B * 6 + 31) / 32, 32 * PROJ_SLICES, project_smem<NC>(T), (cudaStream_t)stream>>>(
+  const int wpc = project_warps(B), warps = (B * 6 + PROJ_PPW - 1) / PROJ_PPW;
+  CEMK_FOR_NCOEF(h->ncoef, (k_project<NC><<<(warps + wpc - 1) / wpc, 32 * wpc, project_smem<NC>(T, 32 * wpc), (cudaStream_t)stream>>>(
                                 B, T, iters, h->d_G, h->d_K, xi, state_term, xi_f, thetadot)));
   h->launches += 1;
   CK(cudaPeekAtLastError());
@@ -889,6 +1065,11 @@ int cemk_argsort_topk(cemk_handle* h, int n, const float* cost, int cost_stride,
   DevGuard guard(h->device);
   if (k > 0 && (!xi || !xi_elite || !cost_elite)) return set_err(CEMK_ERR_ARG, "cemk_argsort_topk: elite buffers missing");
   cudaStream_t st = (cudaStream_t)stream;
+  if (n <= RANK_MAXN) {
+    rank_select(h, n, cost, cost_stride, idx_base, keys_ws, idx_sorted, k, xi, xi_elite, cost_elite, nullptr, st);
+    CK(cudaPeekAtLastError());
+    return CEMK_OK;
+  }
   const int np2 = next_pow2(n);
   k_make_keys<<<(np2 + 255) / 256, 256, 0, st>>>(n, np2, cost, cost_stride, keys_ws);
   h->launches += 1;
@@ -924,6 +1105,11 @@ int cemk_topk_pack(cemk_handle* h, int n, const float* cost, int cost_stride, in
     return set_err(CEMK_ERR_ARG, "cemk_topk_pack: bad argument");
   DevGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
+  if (n <= RANK_MAXN) {
+    rank_select(h, n, cost, cost_stride, idx_base, keys_ws, nullptr, k, xi, nullptr, nullptr, pack, st);
+    CK(cudaPeekAtLastError());
+    return CEMK_OK;
+  }
   const int np2 = next_pow2(n);
   k_make_keys<<<(np2 + 255) / 256, 256, 0, st>>>(n, np2, cost, cost_stride, keys_ws);
   h->launches += 1;
@@ -957,7 +1143,11 @@ int cemk_merge_sorted_lists(cemk_handle* h, int nlist, int kl, const float* pack
   if (!h || !packed || !xi_elite || !cost_elite || !gidx_elite || nlist <= 0 || kl <= 0 || k <= 0 || k > nlist * kl)
     return set_err(CEMK_ERR_ARG, "cemk_merge_sorted_lists: bad argument");
   DevGuard guard(h->device);
-  k_merge_lists<<<(nlist * kl + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->nvar, nlist, kl, k, packed, xi_elite, cost_elite, gidx_elite);
+  const int n = nlist * kl;
+  if (n <= MERGE_MAXKEYS)
+    k_merge_lists<true><<<(n + MERGE_THREADS - 1) / MERGE_THREADS, MERGE_THREADS, sizeof(unsigned) * n, (cudaStream_t)stream>>>(h->nvar, nlist, kl, k, packed, xi_elite, cost_elite, gidx_elite);
+  else
+    k_merge_lists<false><<<(n + MERGE_THREADS - 1) / MERGE_THREADS, MERGE_THREADS, 0, (cudaStream_t)stream>>>(h->nvar, nlist, kl, k, packed, xi_elite, cost_elite, gidx_elite);
   h->launches += 1;
   CK(cudaPeekAtLastError());
   return CEMK_OK;

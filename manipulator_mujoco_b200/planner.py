@@ -197,6 +197,10 @@ class cem_planner:
 
         self._z_cache = {}
         self._split_cache = {}
+        # compute_cem restarts from self.key on every call (mjx_planner.py:388 never stores the advanced key), so the closed
+        # loop asks for the same maxiter_cem blocks of normal draws every tick: keep them.  False = draw on every call
+        # (what bench.py times).
+        self.cache_normal_draws = True
         parallel.check_index_range(self.num_batch)
         self._ws = {}
         self._graph, self._graph_out, self._graph_key, self._eager_ticks = None, None, None, 0
@@ -377,13 +381,14 @@ class cem_planner:
         (key, global sample index) only, so results do not depend on the number of GPUs."""
         k = jax_prng.as_key(key)
         ck = (int(k[0]), int(k[1]))
-        z = self._z_cache.get(ck)
+        z = self._z_cache.get(ck) if self.cache_normal_draws else None
         if z is None:
             Bl, nv = self.num_batch_local, self.nvar
             z = torch.empty(Bl, nv, device=self.device, dtype=torch.float32)
             _lib.check(self._lib.cemk_jax_normal(self._h, ck[0], ck[1], 0 if self._partitionable else 1, self.num_batch * nv,
                                                  self.rank * Bl * nv, Bl * nv, _ptr(z), self._stream()), self._lib)
-            self._z_cache[ck] = z
+            if self.cache_normal_draws:
+                self._z_cache[ck] = z
         return z
 
     # ------------------------------------------------------------------ per-iteration methods

@@ -52,7 +52,7 @@ def test_projection_filter_and_bernstein(planner):
     np.testing.assert_allclose(thetadot.cpu().numpy().reshape(512, 6, 50)[:, 2, :], xf.cpu().numpy()[:, 22:33] @ pr.Pdot.T.astype(np.float32), atol=1e-4)
 
 
-@pytest.mark.parametrize("n", [1, 5, 100, 1000, 4096, 5000, 20000])
+@pytest.mark.parametrize("n", [1, 5, 100, 1000, 4096, 5000, 8192, 8193, 20000])   # <= 8192: counting-rank kernel, above: bitonic network
 def test_argsort_topk_is_stable_with_nan_last(planner, n):
     rng = np.random.default_rng(n)
     cost = rng.uniform(0, 1000, n).astype(np.float32)
@@ -180,6 +180,39 @@ def test_packed_topk_and_merge_equal_global_stable_topk(planner):
     np.testing.assert_array_equal(ge.cpu().numpy(), rg)
     np.testing.assert_array_equal(xe.cpu().numpy(), rx)
     np.testing.assert_array_equal(ce.cpu().numpy().view(np.int32), rc.view(np.int32))
+
+
+@pytest.mark.parametrize("nlist,kl", [(8, 500), (3, 1638), (8, 6200)])      # the last one exceeds the shared-memory key staging
+def test_merge_of_many_sorted_lists_with_ties_across_lists(planner, nlist, kl):
+    """cemk_merge_sorted_lists (what the planner runs after the all-gather): global stable top-k of `nlist` per-rank sorted
+    lists, bit-exact against a lexsort on (cost, global index), with cost ties inside and across lists and NaNs."""
+    import ctypes as C
+    from manipulator_mujoco_b200 import _lib
+    lib, h = planner._lib, planner._h
+    rng = np.random.default_rng(11 + nlist)
+    nv, Bl = 66, 4 * kl
+    k = kl
+    recs, allc, allg = [], [], []
+    for a in range(nlist):
+        c = np.round(rng.uniform(0, 30, kl), 1).astype(np.float32)          # one decimal: many ties
+        if a % 3 == 0:
+            c[rng.integers(0, kl, 3)] = np.nan
+        gi = a * Bl + np.sort(rng.choice(Bl, kl, replace=False))
+        o = np.lexsort((gi, np.isnan(c), np.where(np.isnan(c), np.inf, c)))
+        c, gi = c[o], gi[o]
+        x = rng.normal(size=(kl, nv)).astype(np.float32)
+        recs.append(np.concatenate([x, c[:, None], gi[:, None].astype(np.float32)], axis=1))
+        allc.append(c); allg.append(gi)
+    packed = torch.tensor(np.concatenate(recs), device="cuda").contiguous()
+    p = lambda t: C.c_void_p(t.data_ptr())
+    xe = torch.empty(k, nv, device="cuda"); ce = torch.empty(k, device="cuda"); ge = torch.empty(k, dtype=torch.int32, device="cuda")
+    _lib.check(lib.cemk_merge_sorted_lists(h, nlist, kl, p(packed), k, p(xe), p(ce), p(ge), None), lib)
+    torch.cuda.synchronize()
+    c, g = np.concatenate(allc), np.concatenate(allg)
+    ref = np.lexsort((g, np.isnan(c), np.where(np.isnan(c), np.inf, c)))[:k]
+    np.testing.assert_array_equal(ge.cpu().numpy(), g[ref])
+    np.testing.assert_array_equal(ce.cpu().numpy().view(np.int32), c[ref].view(np.int32))
+    np.testing.assert_array_equal(xe.cpu().numpy(), np.concatenate(recs)[ref, :nv])
 
 
 def test_notebook_attributes_jit_step_and_vec_product(planner, oracle64):

@@ -1,11 +1,22 @@
 """Where a multi-GPU CEM iteration spends its time: CUDA events between the stages of cem_iter, stream-ordered (no host
 synchronisation inside an iteration), averaged over 20 iterations, per rank.  Run under torchrun on N GPUs of one box:
     timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29544 tools/mg_profile.py
-The all-gather stage of a rank includes its wait for the slowest rank's rollout."""
+The all-gather stage of a rank includes its wait for the slowest rank's rollout.
+DUMP=<file.npz> (one GPU): also save every stage's outputs of one iteration, for bitwise A/B of library variants
+(CEMK_LIB_PATH=build_variants/<name>.so; compare with tools/mg_profile.py --compare a.npz b.npz)."""
 import contextlib
 import io
 import os
 import sys
+
+if len(sys.argv) == 4 and sys.argv[1] == "--compare":
+    import numpy as np
+    a, b = np.load(sys.argv[2]), np.load(sys.argv[3])
+    for name in a.files:
+        same = a[name].shape == b[name].shape and np.array_equal(a[name].view(np.int32) if a[name].dtype == np.float32 else a[name],
+                                                                 b[name].view(np.int32) if b[name].dtype == np.float32 else b[name])
+        print(f"{name:10s} {'bit-identical' if same else 'DIFFERENT  max |d| = %g' % float(np.nanmax(np.abs(a[name].astype(np.float64) - b[name].astype(np.float64))))}")
+    sys.exit(0)
 
 import torch
 import torch.distributed as dist
@@ -59,8 +70,10 @@ def iteration(rec):
         xi_e, cost_e, gi = torch.empty(k, nv, device=dev), torch.empty(k, device=dev), torch.empty(k, dtype=torch.int32, device=dev)
         _lib.check(lib.cemk_merge_sorted_lists(h, world, kl, _ptr(gathered), k, _ptr(xi_e), _ptr(cost_e), _ptr(gi), pl._stream()), lib)
         ev[6].record()
-    pl.compute_mean_cov(cost_e, mean0, cov0, xi_e); ev[7].record()
+    mc = pl.compute_mean_cov(cost_e, mean0, cov0, xi_e); ev[7].record()
     rec.append(ev)
+    return dict(xi=xi, xi_f=xf, thetadot=td, theta=theta, cost4=cost4, xi_elite=xi_e, cost_elite=cost_e, mean=mc[0], cov=mc[1],
+                chol=pl._buf("chol", (nv * nv,)), **({"idx": idx} if world == 1 else {"gidx": gi}))
 
 
 for _ in range(5):
@@ -86,3 +99,8 @@ if world > 1:
     dist.destroy_process_group()
 else:
     print(line)
+    if os.environ.get("DUMP"):
+        import numpy as np
+        out = iteration([])
+        torch.cuda.synchronize()
+        np.savez(os.environ["DUMP"], **{k_: v.detach().cpu().numpy() for k_, v in out.items()})
