@@ -118,6 +118,17 @@ int cemk_mean_cov(cemk_handle* h, int k, const float* cost_elite, const float* x
                   const float* cov_prev, float lamda, float alpha_mean, float alpha_cov, float* mean_out, float* cov_out,
                   void* stream);
 
+/* What compute_cem keeps of CEM iteration `iter` of `n_iter` (mjx_planner.py:390-404), written into the tick's packed result
+ *   out = [cost_min[n_iter] | best thetadot[6T] | best theta[6T] | cost_g, cost_r, cost_c | xi_mean[nvar] | overflow count]
+ * (floats; the planner copies it to the host once per tick): out[iter] = cost_elite[0], the overflow count grows by the number of
+ * rollouts of this iteration whose contacts exceeded the kernel's capacity (flags bit 0), and when `last` is set the new mean and
+ * the rows of the best sample -- local row gidx_elite[0] - idx_base of thetadot / theta [B][6T] and cost4 [B][4] -- are stored.
+ * best_row != NULL (several GPUs): the 12T + 3 best-sample floats go there instead, exact zeros when the row is not on this
+ * rank, for the caller's all-reduce. */
+int cemk_tick_record(cemk_handle* h, int iter, int n_iter, int last, int B, int T, const float* cost_elite, const int* gidx_elite,
+                     int idx_base, const int* flags, const float* thetadot, const float* theta, const float* cost4,
+                     const float* xi_mean, float* out, float* best_row, void* stream);
+
 /* Options.  "force_rerun" (0/1): recompute every sample with the rollout instantiation that keeps all 48
  * contacts in shared memory, used by the tests to check that it agrees bit for bit with the fast kernel
  * and its spill area.  "cta_samples" (0..28): fixed

@@ -55,6 +55,7 @@ _SIGS = {
     "cemk_mean_cov": ([_vp, _i, _vp, _vp, _vp, _vp, _f, _f, _f, _vp, _vp, _vp], _i),
     "cemk_set_option": ([_vp, C.c_char_p, _i], _i),
     "cemk_fp32_fma_peak": ([_vp, C.POINTER(C.c_double)], _i),
+    "cemk_tick_record": ([_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "cemk_launch_count": ([_vp], C.c_longlong),
 }
 EXPORTS = tuple(_SIGS)

@@ -1164,6 +1164,54 @@ int cemk_mean_cov(cemk_handle* h, int k, const float* cost_elite, const float* x
   return CEMK_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- tick record
+// What compute_cem (mjx_planner.py:390-404) keeps of an iteration, written straight into the tick's packed result
+//   out = [cost_min[n_iter] | best thetadot[6T] | best theta[6T] | cost_g, cost_r, cost_c | xi_mean[nvar] | overflow count]
+// (one D2H copy at the end of the tick): iteration `iter` stores the smallest (global) cost and adds the number of samples whose
+// contacts overflowed the rollout kernel's capacity (flags bit 0); the last iteration also stores the new mean and the best
+// sample's rows -- the head of the sorted elite list, local row gbest - idx_base.  With several GPUs only the owning rank
+// has that row: the segment then goes to `best_row` (6T + 6T + 3 floats), exact zeros on the other ranks, for the caller's
+// all-reduce.  Replaces a dozen framework kernels (index, cat, reduce, copies) per tick.
+__global__ void __launch_bounds__(256) k_tick_record(int NVAR, int iter, int n_iter, int last, int B, int T, const float* __restrict__ cost_elite,
+                                                     const int* __restrict__ gidx_elite, int idx_base, const int* __restrict__ flags,
+                                                     const float* __restrict__ thetadot, const float* __restrict__ theta,
+                                                     const float* __restrict__ cost4, const float* __restrict__ xi_mean,
+                                                     float* __restrict__ out, float* __restrict__ best_row) {
+  __shared__ int red[256];
+  const int tid = threadIdx.x, nd = KM_NL * T;
+  int c = 0;
+  for (int i = tid; i < B; i += 256) c += flags[i] & 1;
+  red[tid] = c; __syncthreads();
+  for (int o = 128; o; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
+  float* ovf = out + n_iter + 2 * nd + 3 + NVAR;
+  if (tid == 0) {
+    out[iter] = cost_elite[0];
+    *ovf = (iter == 0 ? 0.f : *ovf) + (float)red[0];
+  }
+  if (!last) return;
+  for (int e = tid; e < NVAR; e += 256) out[n_iter + 2 * nd + 3 + e] = xi_mean[e];
+  const int li = gidx_elite[0] - idx_base;
+  const bool own = li >= 0 && li < B;
+  float* dst = best_row ? best_row : out + n_iter;
+  for (int e = tid; e < 2 * nd + 3; e += 256) {
+    float v = 0.f;
+    if (own) v = e < nd ? thetadot[(size_t)li * nd + e] : (e < 2 * nd ? theta[(size_t)li * nd + (e - nd)] : cost4[(size_t)li * 4 + 1 + (e - 2 * nd)]);
+    dst[e] = v;
+  }
+}
+int cemk_tick_record(cemk_handle* h, int iter, int n_iter, int last, int B, int T, const float* cost_elite, const int* gidx_elite, int idx_base,
+                     const int* flags, const float* thetadot, const float* theta, const float* cost4, const float* xi_mean, float* out,
+                     float* best_row, void* stream) {
+  if (!h || !cost_elite || !gidx_elite || !flags || !thetadot || !theta || !cost4 || !xi_mean || !out || iter < 0 || iter >= n_iter || B <= 0 || T <= 0)
+    return set_err(CEMK_ERR_ARG, "cemk_tick_record: bad argument");
+  DevGuard guard(h->device);
+  k_tick_record<<<1, 256, 0, (cudaStream_t)stream>>>(h->nvar, iter, n_iter, last, B, T, cost_elite, gidx_elite, idx_base, flags, thetadot, theta, cost4,
+                                                    xi_mean, out, best_row);
+  h->launches += 1;
+  CK(cudaPeekAtLastError());
+  return CEMK_OK;
+}
+
 long long cemk_launch_count(cemk_handle* h) { return h ? h->launches : 0; }
 
 int cemk_set_option(cemk_handle* h, const char* name, int value) {

@@ -42,11 +42,13 @@ def gather_elites(pack: torch.Tensor, world: int, group=None, out: torch.Tensor 
     return out
 
 
-def exchange_owned_row(row: torch.Tensor, own: torch.Tensor, group=None) -> torch.Tensor:
+def exchange_owned_row(row: torch.Tensor, own, group=None) -> torch.Tensor:
     """Sum-all-reduce in which exactly one rank (``own`` true) contributes ``row`` and every other rank contributes
     exact zeros.  ``torch.where`` rather than a 0/1 multiplication: a non-owning rank's ``row`` is an arbitrary local
-    sample and may hold NaN / Inf (diverged rollout), and NaN * 0 = NaN would poison the sum on every rank."""
+    sample and may hold NaN / Inf (diverged rollout), and NaN * 0 = NaN would poison the sum on every rank.
+    ``own`` None: ``row`` is already the owner's values or exact zeros (``cemk_tick_record`` writes it that way) and is
+    reduced in place."""
     import torch.distributed as dist
-    out = torch.where(own.reshape(-1)[0], row, torch.zeros_like(row))
+    out = row if own is None else torch.where(own.reshape(-1)[0], row, torch.zeros_like(row))
     dist.all_reduce(out, group=group)
     return out

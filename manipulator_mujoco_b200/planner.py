@@ -203,6 +203,8 @@ class cem_planner:
         self.cache_normal_draws = True
         parallel.check_index_range(self.num_batch)
         self._ws = {}
+        self._iter_out = None
+        self._key_seen, self._key_tuple = None, None
         self._graph, self._graph_out, self._graph_key, self._eager_ticks = None, None, None, 0
         self.overflow_samples, self._warned_overflow = 0, False
         self.use_cuda_graph = os.environ.get("CEMK_CUDA_GRAPH", "1") != "0"
@@ -365,6 +367,15 @@ class cem_planner:
             self._ws[key] = b
         return b
 
+    def _const(self, name, make):
+        """A device constant built once (read-only afterwards; CUDA graphs keep pointing at it)."""
+        key = ("const", name)
+        b = self._ws.get(key)
+        if b is None:
+            b = make()
+            self._ws[key] = b
+        return b
+
     def _split0(self, key):
         """``jax.random.split(key)[0]``; memoised, the reference walks the same key chain every tick (:80, :388)."""
         k = jax_prng.as_key(key)
@@ -414,12 +425,14 @@ class cem_planner:
         self._keep_s = (mean, cov)
         return xi, key
 
-    def _project(self, xi_samples, state_term, want_thetadot):
+    def _project(self, xi_samples, state_term, want_thetadot, out_thetadot=None):
         xi = self._t(xi_samples)
         st = self._t(state_term)
         B = xi.shape[0]
         xi_f = torch.empty(B, self.nvar, device=self.device)
-        thetadot = torch.empty(B, self.num_dof * self.num, device=self.device) if want_thetadot else None
+        thetadot = None
+        if want_thetadot:
+            thetadot = out_thetadot if out_thetadot is not None else torch.empty(B, self.num_dof * self.num, device=self.device)
         _lib.check(self._lib.cemk_project(self._h, B, int(self.maxiter_projection), _ptr(xi), _ptr(st), _ptr(xi_f),
                                           _ptr(thetadot), self._stream()), self._lib)
         return xi_f, thetadot
@@ -428,11 +441,11 @@ class cem_planner:
         """mjx_planner.py:234-249 -> primal_sol [B, nvar]."""
         return self._project(xi_samples, state_term, False)[0]
 
-    def _rollout(self, thetadot, init_pos, init_vel, target_pos, target_rot, dumps):
+    def _rollout(self, thetadot, init_pos, init_vel, target_pos, target_rot, dumps, out_theta=None):
         td = self._t(thetadot)
         B, T = td.shape[0], self.num
         dev = self.device
-        theta = torch.empty(B, self.num_dof * T, device=dev)
+        theta = out_theta if out_theta is not None else torch.empty(B, self.num_dof * T, device=dev)
         cost4 = torch.empty(B, 4, device=dev)
         eef_pos = torch.empty(B, T, 3, device=dev) if dumps else None
         eef_rot = torch.empty(B, T, 4, device=dev) if dumps else None
@@ -537,58 +550,55 @@ class cem_planner:
         init_pos, init_vel, target_pos, target_rot, xi_mean, xi_cov, key, state_term = carry
         xi_mean_prev, xi_cov_prev = xi_mean, xi_cov
         xi_samples, key = self.compute_xi_samples(key, xi_mean, xi_cov)
-        xi_filtered, thetadot = self._project(xi_samples, state_term, True)
+        out_td, out_th = self._iter_out if self._iter_out is not None else (None, None)      # compute_cem: rows of its [maxiter, B, 6T] results
+        xi_filtered, thetadot = self._project(xi_samples, state_term, True, out_thetadot=out_td)
         tp = self._t(target_pos).reshape(-1, 3)[0]
         tr = self._t(target_rot).reshape(-1, 4)[0]
-        theta, cost4, _, _, _ = self._rollout(thetadot, init_pos, init_vel, tp, tr, False)
+        theta, cost4, _, _, _ = self._rollout(thetadot, init_pos, init_vel, tp, tr, False, out_theta=out_th)
         xi_ellite, cost_ellite, gidx = self._select_elites(cost4, xi_samples)
         xi_mean, xi_cov = self.compute_mean_cov(cost_ellite, xi_mean_prev, xi_cov_prev, xi_ellite)
         self._last_elite = (cost_ellite, gidx)
+        self._last_cost4 = cost4
         carry = (init_pos, init_vel, target_pos, target_rot, xi_mean, xi_cov, key, state_term)
         return carry, (cost4[:, 0], cost4[:, 1], cost4[:, 2], cost4[:, 3], thetadot, theta)
 
     def _cem_device(self, pin, pout):
         """Everything a planning tick does on the device: H2D of the packed inputs, maxiter_cem
-        iterations, best-sample extraction, D2H of the packed results (stream-ordered, no sync)."""
+        iterations, best-sample extraction, D2H of the packed results (stream-ordered, no sync).
+        pin = [xi_mean | q0 v0 a0 0 0 (the state row, :374-384) | target_pos | target_rot]."""
         dev = self.device
-        Bl, T, nd, nv = self.num_batch_local, self.num, self.num_dof, self.nvar
+        Bl, T, nd, nv, m = self.num_batch_local, self.num, self.num_dof, self.nvar, self.maxiter_cem
         d_in = self._buf("d_in", (pin.numel(),))
         d_in.copy_(pin, non_blocking=True)
         xi_mean_d = d_in[:nv]
-        q0, v0, a0 = d_in[nv:nv + 6], d_in[nv + 6:nv + 12], d_in[nv + 12:nv + 18]
-        tp, tr = d_in[nv + 18:nv + 21], d_in[nv + 21:nv + 25]
-        z6 = torch.zeros(6, device=dev)
-        state_row = torch.cat([q0, v0, a0, z6, z6])
-        state_term = state_row.unsqueeze(0).expand(Bl, 30).contiguous()                    # :374-384
-        xi_cov = 10 * torch.eye(nv, device=dev)                                            # :386
+        q0, v0 = d_in[nv:nv + 6], d_in[nv + 6:nv + 12]
+        tp, tr = d_in[nv + 30:nv + 33], d_in[nv + 33:nv + 37]
+        state_term = d_in[nv:nv + 30].unsqueeze(0).expand(Bl, 30).contiguous()             # :374-384
+        xi_cov = self._const("cov0", lambda: 10 * torch.eye(nv, device=dev))               # :386 (read-only)
         key = self._split0(self.key)                                                       # :388
         carry = (q0, v0, tp, tr, xi_mean_d, xi_cov, key, state_term)
-        thetadot_all = torch.empty(self.maxiter_cem, Bl, nd * T, device=dev)
-        theta_all = torch.empty(self.maxiter_cem, Bl, nd * T, device=dev)
-        cost_min = torch.empty(self.maxiter_cem, device=dev)
-        last = None
-        ovf = torch.zeros((), dtype=torch.int32, device=dev)
-        for i in range(self.maxiter_cem):                                                  # :390-392
-            carry, out = self.cem_iter(carry, None)
-            ovf = ovf + (self._buf("flags", (Bl,), torch.int32) & 1).sum(dtype=torch.int32)   # contact-capacity overflows
-            thetadot_all[i].copy_(out[4])
-            theta_all[i].copy_(out[5])
-            cost_min[i:i + 1].copy_(self._last_elite[0][0:1])                              # min over the (global) batch
-            last = out
-        # :395-402  best sample of the last iteration = head of the (merged) sorted list
-        gbest = self._last_elite[1][0:1].to(torch.int64)
-        lo = self.rank * Bl
-        if self.world == 1:
-            li = gbest
-            best = torch.cat([last[4][li].reshape(-1), last[5][li].reshape(-1), last[1][li], last[2][li], last[3][li]])
-        else:
-            # only the owning rank contributes its row; the others send exact zeros (their clamped row may hold
+        both = torch.empty(2, m, Bl, nd * T, device=dev)
+        thetadot_all, theta_all = both[0], both[1]
+        out_d = self._buf("tick_out", (pout.numel(),))
+        best_row = self._buf("best_row", (2 * nd * T + 3,)) if self.world > 1 else None
+        flags = self._buf("flags", (Bl,), torch.int32)
+        for i in range(m):                                                                 # :390-392
+            self._iter_out = (thetadot_all[i], theta_all[i])
+            try:
+                carry, out = self.cem_iter(carry, None)
+            finally:
+                self._iter_out = None
+            cost_e, gidx = self._last_elite
+            # min over the (global) batch, overflow count, and (last iteration, :395-402) the best sample = head of the
+            # (merged) sorted list and the new mean, straight into the packed result
+            _lib.check(self._lib.cemk_tick_record(self._h, i, m, int(i == m - 1), Bl, T, _ptr(cost_e), _ptr(gidx), self.rank * Bl, _ptr(flags),
+                                                  _ptr(out[4]), _ptr(out[5]), _ptr(self._last_cost4), _ptr(carry[4]), _ptr(out_d),
+                                                  _ptr(best_row), self._stream()), self._lib)
+            self._keep_t = (cost_e, gidx, carry[4])
+        if self.world > 1:
+            # only the owning rank wrote its row; the others contributed exact zeros (their clamped row may hold
             # NaN / Inf of a diverged sample, which a 0/1 multiplication would leak into the sum)
-            li = (gbest - lo).clamp(0, Bl - 1)
-            own = (gbest >= lo) & (gbest < lo + Bl)
-            row = torch.cat([last[4][li].reshape(-1), last[5][li].reshape(-1), last[1][li], last[2][li], last[3][li]])
-            best = parallel.exchange_owned_row(row, own, self.process_group)
-        out_d = torch.cat([cost_min, best, carry[4], ovf.to(torch.float32).reshape(1)])
+            out_d[m:m + 2 * nd * T + 3].copy_(parallel.exchange_owned_row(best_row, None, self.process_group))
         pout.copy_(out_d, non_blocking=True)
         return thetadot_all, theta_all
 
@@ -597,15 +607,15 @@ class cem_planner:
         dev = self.device
         Bl, T, nd, nv = self.num_batch_local, self.num, self.num_dof, self.nvar
         # one packed host->device copy for the per-tick inputs
-        host = np.concatenate([np.asarray(xi_mean.detach().cpu() if torch.is_tensor(xi_mean) else xi_mean, dtype=np.float32).reshape(-1),
-                               np.asarray(init_pos, dtype=np.float32).reshape(-1), np.asarray(init_vel, dtype=np.float32).reshape(-1),
-                               np.asarray(init_acc, dtype=np.float32).reshape(-1), np.asarray(target_pos, dtype=np.float32).reshape(-1),
-                               np.asarray(target_rot, dtype=np.float32).reshape(-1)])
         pin = self._ws.get("pin_in")
         if pin is None:
-            pin = torch.empty(host.size, dtype=torch.float32).pin_memory()
+            pin = torch.zeros(nv + 37, dtype=torch.float32).pin_memory()
             self._ws["pin_in"] = pin
-        pin.copy_(torch.from_numpy(host))
+            self._ws["pin_in_np"] = pin.numpy()                       # a view: written in place every tick
+        host = self._ws["pin_in_np"]
+        host[:nv] = np.asarray(xi_mean.detach().cpu() if torch.is_tensor(xi_mean) else xi_mean, dtype=np.float32).reshape(-1)
+        host[nv:nv + 6], host[nv + 6:nv + 12], host[nv + 12:nv + 18] = np.asarray(init_pos).reshape(-1), np.asarray(init_vel).reshape(-1), np.asarray(init_acc).reshape(-1)
+        host[nv + 30:nv + 33], host[nv + 33:nv + 37] = np.asarray(target_pos).reshape(-1), np.asarray(target_rot).reshape(-1)
         m = self.maxiter_cem
         nout = m + 2 * nd * T + 3 + self.nvar + 1
         # The device side of a tick is a fixed sequence of launches on fixed buffers: after two eager
@@ -615,8 +625,10 @@ class cem_planner:
         # tick).  The graph bakes in everything that reaches a kernel as a scalar or a host pointer, so it is
         # keyed on those and dropped when one of them changes.
         w = self.cost_weights
+        if self._key_seen is not self.key:                              # (the reference never reassigns its key)
+            self._key_seen, self._key_tuple = self.key, tuple(int(x) for x in jax_prng.as_key(self.key))
         gkey = (m, int(self.maxiter_projection), float(w['w_pos']), float(w['w_rot']), float(w['w_col']),
-                tuple(int(x) for x in jax_prng.as_key(self.key)), self._partitionable, T, Bl, int(self.ellite_num), nv)
+                self._key_tuple, self._partitionable, T, Bl, int(self.ellite_num), nv)
         if self._graph is not None and gkey != self._graph_key:
             torch.cuda.current_stream(dev).synchronize()
             self._graph, self._graph_out, self._eager_ticks = None, None, 0
@@ -656,6 +668,7 @@ class cem_planner:
                           "rollout kernel (48 simultaneous contacts); their extra contacts were dropped", RuntimeWarning)
         self.h2d_bytes = host.size * 4
         self.d2h_bytes = nout * 4
-        if self._graph is not None:          # graph outputs are static buffers: hand out copies
-            thetadot_all, theta_all = thetadot_all.clone(), theta_all.clone()
+        if self._graph is not None:          # graph outputs are static buffers: hand out copies (one launch for both)
+            both = thetadot_all._base.clone()
+            thetadot_all, theta_all = both[0], both[1]
         return cost, best_cost_g, best_cost_r, best_cost_c, best_vels, best_traj, xi_mean_out, thetadot_all, theta_all

@@ -54,6 +54,9 @@ def _worker(rank, world, port, B, k, seed, ret):
     if bool(own):
         row = torch.from_numpy(np.concatenate([xi[gbest, :8], cost[gbest:gbest + 1]]))
     best = parallel.exchange_owned_row(row, own)
+    # the pre-masked form the planner uses (cemk_tick_record writes the owner's row or exact zeros)
+    masked = row.clone() if bool(own) else torch.zeros_like(row)
+    assert torch.equal(parallel.exchange_owned_row(masked, None).view(torch.int32), best.view(torch.int32))
     ret[rank] = (gidx_e.copy(), xi_e.copy(), cost_e.copy(), best.numpy().copy())
     dist.destroy_process_group()
 

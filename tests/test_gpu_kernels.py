@@ -215,6 +215,52 @@ def test_merge_of_many_sorted_lists_with_ties_across_lists(planner, nlist, kl):
     np.testing.assert_array_equal(xe.cpu().numpy(), np.concatenate(recs)[ref, :nv])
 
 
+def test_tick_record_packs_what_compute_cem_returns(planner):
+    """cemk_tick_record: per-iteration minimum + overflow count, and at the last iteration the best sample's rows and the new
+    mean; with a best_row buffer (several GPUs) the rows go there, exact zeros when the sample lives on another rank even if
+    this rank's data is NaN."""
+    import ctypes as C
+    from manipulator_mujoco_b200 import _lib
+    lib, h = planner._lib, planner._h
+    rng = np.random.default_rng(8)
+    B, T, nv, m = 37, planner.num, planner.nvar, 3
+    nd = 6 * T
+    td, th = rng.normal(size=(B, nd)).astype(np.float32), rng.normal(size=(B, nd)).astype(np.float32)
+    c4 = rng.uniform(size=(B, 4)).astype(np.float32)
+    td[5, 3] = np.nan
+    mean = rng.normal(size=nv).astype(np.float32)
+    dv = lambda a: torch.tensor(a, device="cuda")
+    p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    d_td, d_th, d_c4, d_mean = dv(td), dv(th), dv(c4), dv(mean)
+    out = torch.full((m + 2 * nd + 3 + nv + 1,), -7.0, device="cuda")
+    flags_all, cmin = [], []
+    for i in range(m):
+        flags = rng.integers(0, 4, B).astype(np.int32)
+        ce = np.sort(rng.uniform(size=4).astype(np.float32)); gi = np.array([11, 2, 30, 4], np.int32)
+        d_f, d_ce, d_gi = dv(flags), dv(ce), dv(gi)
+        _lib.check(lib.cemk_tick_record(h, i, m, int(i == m - 1), B, T, p(d_ce), p(d_gi), 0, p(d_f), p(d_td), p(d_th), p(d_c4), p(d_mean), p(out), None, None), lib)
+        torch.cuda.synchronize()
+        flags_all.append(int((flags & 1).sum())); cmin.append(ce[0])
+    o = out.cpu().numpy()
+    np.testing.assert_array_equal(o[:m], np.array(cmin, np.float32))
+    np.testing.assert_array_equal(o[m:m + nd], td[11]); np.testing.assert_array_equal(o[m + nd:m + 2 * nd], th[11])
+    np.testing.assert_array_equal(o[m + 2 * nd:m + 2 * nd + 3], c4[11, 1:])
+    np.testing.assert_array_equal(o[m + 2 * nd + 3:m + 2 * nd + 3 + nv], mean)
+    assert o[-1] == sum(flags_all)
+    # several GPUs: this rank holds rows [100, 100 + B); the best sample 105 is local row 5 (which has a NaN), 11 is elsewhere
+    row = torch.full((2 * nd + 3,), 5.0, device="cuda")
+    for best, owned in ((105, True), (11, False), (100 + B, False)):
+        d_gi = dv(np.array([best, 0], np.int32))
+        _lib.check(lib.cemk_tick_record(h, 0, 1, 1, B, T, p(d_ce), p(d_gi), 100, p(d_f), p(d_td), p(d_th), p(d_c4), p(d_mean), p(out), p(row), None), lib)
+        torch.cuda.synchronize()
+        r = row.cpu().numpy()
+        if owned:
+            np.testing.assert_array_equal(r[:nd].view(np.int32), td[5].view(np.int32)); np.testing.assert_array_equal(r[nd:2 * nd], th[5])
+            np.testing.assert_array_equal(r[2 * nd:], c4[5, 1:])
+        else:
+            assert not r.any() and not np.signbit(r).any()
+
+
 def test_notebook_attributes_jit_step_and_vec_product(planner, oracle64):
     """mjx_planner.py:98,108: `vec_product` (vmapped outer product) and `jit_step` (one mjx.step of one environment),
     touched by mpc_planning.ipynb."""
