@@ -88,6 +88,28 @@ def build_kmodel(mc: ModelConsts, timestep: float, robot_geom_names=None, tcp_si
         robot_geom_names = [f"robot_{i}" for i in range(10)]
     hinge = [j for j in range(mc.njnt) if mc.jnt_type[j] == JNT_HINGE]
     free = [j for j in range(mc.njnt) if mc.jnt_type[j] == JNT_FREE]
+    # The loader (mjcf.compile_mjcf / from_mjmodel) accepts every scene the reference ships; the rollout kernel implements the
+    # topology of the scene the planner loads (mjx_planner.py:100).  Say exactly what a refused model asks for.
+    missing = []
+    nslide = int(np.sum(np.asarray(mc.jnt_type) == 2))
+    if nslide:
+        missing.append(f"{nslide} slide joint(s)")
+    if mc.d.get("neq", 0):
+        missing.append(f"{mc.d['neq']} equality constraint(s)")
+    if mc.d.get("ntendon", 0):
+        missing.append(f"{mc.d['ntendon']} tendon(s)")
+    if mc.d.get("nu", 0) and mc.opt.get("actuation", 1):
+        missing.append(f"{mc.d['nu']} actuator(s)")
+    if mc.opt.get("integrator", "Euler") != "Euler":
+        missing.append(f"the {mc.opt['integrator']} integrator")
+    if len(hinge) > NL:
+        missing.append(f"{len(hinge)} hinge joints (a second arm; the kernel has one chain of {NL})")
+    ncyl = int(np.sum((np.asarray(mc.geom_type) == 5) & (np.asarray(mc.geom_collides) != 0)))
+    if ncyl:
+        missing.append(f"{ncyl} cylinder collision geom(s)")
+    if missing:
+        raise NotImplementedError("the rollout kernel does not implement " + ", ".join(missing)
+                                  + " of this model (it loads: see mjcf.compile_mjcf; the kernel's scope is DESIGN.md section 8)")
     if len(hinge) != NL or len(free) > 1 or len(hinge) + len(free) != mc.njnt:
         raise NotImplementedError("kernel supports exactly 6 hinge joints and at most one free joint")
     if free and (mc.jnt_dofadr[free[0]] != NL or mc.jnt_qposadr[free[0]] != NL):

@@ -37,10 +37,10 @@ from dataclasses import dataclass, field
 import numpy as np
 
 # geom type codes: MuJoCo's mjtGeom ordering (pairs are sorted by it)
-GEOM_PLANE, GEOM_SPHERE, GEOM_CAPSULE, GEOM_BOX, GEOM_MESH = 0, 2, 3, 6, 7
-_GEOM_TYPES = {"plane": GEOM_PLANE, "sphere": GEOM_SPHERE, "capsule": GEOM_CAPSULE,
+GEOM_PLANE, GEOM_SPHERE, GEOM_CAPSULE, GEOM_CYLINDER, GEOM_BOX, GEOM_MESH = 0, 2, 3, 5, 6, 7
+_GEOM_TYPES = {"plane": GEOM_PLANE, "sphere": GEOM_SPHERE, "capsule": GEOM_CAPSULE, "cylinder": GEOM_CYLINDER,
                "box": GEOM_BOX, "mesh": GEOM_MESH}
-JNT_FREE, JNT_HINGE = 0, 3
+JNT_FREE, JNT_SLIDE, JNT_HINGE = 0, 2, 3
 
 # contact slots per pair function (MJX collision_driver ncon table)
 PAIR_SLOTS = {(GEOM_PLANE, GEOM_CAPSULE): 2, (GEOM_PLANE, GEOM_BOX): 4,
@@ -108,7 +108,7 @@ def _stl_mass_properties(path):
 
 
 def _primitive_mass_properties(gtype, size, density):
-    """(mass, inertia diag in geom frame) for box / capsule / sphere (MuJoCo mjCGeom::SetInertia)."""
+    """(mass, inertia diag in geom frame) for box / capsule / sphere / cylinder (MuJoCo mjCGeom::SetInertia)."""
     if gtype == GEOM_BOX:
         sx, sy, sz = size[:3]
         m = 8 * sx * sy * sz * density
@@ -125,6 +125,11 @@ def _primitive_mass_properties(gtype, size, density):
         r = size[0]
         m = density * 4.0 / 3.0 * np.pi * r ** 3
         return m, np.full(3, 0.4 * m * r * r)
+    if gtype == GEOM_CYLINDER:
+        r, h = size[0], 2 * size[1]
+        m = density * np.pi * r * r * h
+        ixx = m * (3 * r * r + h * h) / 12
+        return m, np.array([ixx, ixx, m * r * r / 2])
     return 0.0, np.zeros(3)
 
 
@@ -259,8 +264,8 @@ def compile_mjcf(xml_path) -> ModelConsts:
         for fl in o.findall("flag"):
             for k, v in fl.attrib.items():
                 opt[k] = 0 if v == "disable" else 1
-    if opt["integrator"] != "Euler":
-        raise NotImplementedError("only the Euler integrator is supported")
+    # (the integrator is recorded, not judged: the loader accepts every scene of the reference -- dual_arm_scene.xml asks for
+    #  implicitfast -- and kmodel.build_kmodel refuses what the rollout kernel does not implement)
 
     meshes = {}
     for a in root.findall("asset"):
@@ -294,14 +299,14 @@ def compile_mjcf(xml_path) -> ModelConsts:
             elif ch.tag in ("joint", "freejoint"):
                 a = _attrs(ch, classes, childclass)
                 jt = "free" if ch.tag == "freejoint" else a.get("type", "hinge")
-                if jt not in ("free", "hinge"):
+                if jt not in ("free", "hinge", "slide"):
                     raise NotImplementedError(f"joint type {jt}")
                 rng = _vec(a.get("range"), 2, [0, 0])
                 limited = a.get("limited", "auto")
                 lim = (limited == "true") or (limited == "auto" and autolimits and "range" in a)
                 if jt == "free":
                     lim = False
-                joints.append(dict(name=a.get("name"), type=JNT_FREE if jt == "free" else JNT_HINGE,
+                joints.append(dict(name=a.get("name"), type={"free": JNT_FREE, "slide": JNT_SLIDE, "hinge": JNT_HINGE}[jt],
                                    body=bid, axis=_vec(a.get("axis"), 3, [0, 0, 1]),
                                    pos=_vec(a.get("pos"), 3, [0, 0, 0]), range=rng, limited=lim,
                                    armature=float(a.get("armature", 0.0)),
@@ -419,7 +424,7 @@ def compile_mjcf(xml_path) -> ModelConsts:
                 vol, com, I = _stl_mass_properties(path)
                 m = g["density"] * vol
                 parts.append((m, g["pos"] + Rg @ com, Rg @ (g["density"] * I) @ Rg.T))
-            elif g["type"] in (GEOM_BOX, GEOM_CAPSULE, GEOM_SPHERE):
+            elif g["type"] in (GEOM_BOX, GEOM_CAPSULE, GEOM_SPHERE, GEOM_CYLINDER):
                 m, diag = _primitive_mass_properties(g["type"], g["size"], g["density"])
                 parts.append((m, g["pos"].copy(), Rg @ np.diag(diag) @ Rg.T))
         if parts:
@@ -439,11 +444,45 @@ def compile_mjcf(xml_path) -> ModelConsts:
         for e in c.findall("exclude"):
             excl.append((names.index(e.get("body1")), names.index(e.get("body2"))))
     for g in geoms:
-        if (g["contype"] or g["conaffinity"]) and g["type"] not in (GEOM_PLANE, GEOM_CAPSULE, GEOM_BOX):
+        if (g["contype"] or g["conaffinity"]) and g["type"] not in (GEOM_PLANE, GEOM_CAPSULE, GEOM_BOX, GEOM_CYLINDER):
             raise NotImplementedError(f"collision geom type {g['typename']}")
+    unknown_pairs = []
     pair_geom, pair_type, pair_nslot, pair_slotadr, collides = _candidate_pairs(
         [g["type"] for g in geoms], [g["body"] for g in geoms], [g["contype"] for g in geoms], [g["conaffinity"] for g in geoms],
-        body_weldid, [b["parent"] for b in bodies], excl)
+        body_weldid, [b["parent"] for b in bodies], excl, unknown=unknown_pairs)
+
+    # ---- equality constraints, tendons, actuators, keyframes: recorded for the loader's callers (scene_mjx.xml couples the
+    # two Hand-E fingers with a joint equality and a fixed tendon; the dual-arm scene has 12 position servos).  The rollout
+    # kernel implements none of them: kmodel.build_kmodel refuses a model that has any.
+    jname = {j["name"]: i for i, j in enumerate(joints)}
+    eqs, tendons, acts, keys = [], [], [], []
+    for e in root.findall("equality"):
+        for c in e:
+            a = _attrs(c, classes, None)
+            if c.tag != "joint":
+                raise NotImplementedError(f"equality type {c.tag}")
+            eqs.append(dict(type="joint", joint1=jname[a["joint1"]], joint2=jname[a["joint2"]] if "joint2" in a else -1,
+                            polycoef=np.concatenate([_vec(a.get("polycoef"), None, [0, 1, 0, 0, 0]), np.zeros(5)])[:5],
+                            solref=_vec(a.get("solref"), 2, [0.02, 1]), solimp=_vec(a.get("solimp"), None, [0.9, 0.95, 0.001, 0.5, 2]),
+                            active=a.get("active", "true") == "true"))
+    for t in root.findall("tendon"):
+        for c in t:
+            if c.tag != "fixed":
+                raise NotImplementedError(f"tendon type {c.tag}")
+            tendons.append(dict(name=c.get("name"), joints=[jname[w.get("joint")] for w in c.findall("joint")],
+                                coefs=[float(w.get("coef")) for w in c.findall("joint")]))
+    tname = {t["name"]: i for i, t in enumerate(tendons)}
+    for ac in root.findall("actuator"):
+        for c in ac:
+            a = _attrs(c, classes, None)
+            acts.append(dict(name=a.get("name"), kind=c.tag, joint=jname.get(a.get("joint"), -1), tendon=tname.get(a.get("tendon"), -1),
+                             gaintype=a.get("gaintype", "fixed"), biastype=a.get("biastype", "none"),
+                             gainprm=np.concatenate([_vec(a.get("gainprm"), None, [1.0]), np.zeros(3)])[:3],
+                             biasprm=np.concatenate([_vec(a.get("biasprm"), None, [0.0]), np.zeros(3)])[:3],
+                             ctrlrange=_vec(a.get("ctrlrange"), 2, [0, 0]), forcerange=_vec(a.get("forcerange"), 2, [0, 0])))
+    for kf in root.findall("keyframe"):
+        for c in kf.findall("key"):
+            keys.append(dict(name=c.get("name"), qpos=_vec(c.get("qpos"), None, []), ctrl=_vec(c.get("ctrl"), None, [])))
     col = [gi for gi in range(ngeom) if collides[gi]]
 
     d = dict(
@@ -485,8 +524,21 @@ def compile_mjcf(xml_path) -> ModelConsts:
         site_pos=np.array([s["pos"] for s in sites]).reshape(-1, 3),
         pair_geom=pair_geom, pair_type=pair_type, pair_nslot=pair_nslot, pair_slotadr=pair_slotadr,
         ncon=int(pair_nslot.sum()),
+        pair_unknown=np.array(unknown_pairs, dtype=np.int32).reshape(-1, 2),
+        nexclude=len(excl),
+        neq=len(eqs), eq_joint1=np.array([e["joint1"] for e in eqs], dtype=np.int32), eq_joint2=np.array([e["joint2"] for e in eqs], dtype=np.int32),
+        eq_polycoef=np.array([e["polycoef"] for e in eqs]).reshape(-1, 5), eq_active=np.array([e["active"] for e in eqs], dtype=np.int32),
+        eq_solref=np.array([e["solref"] for e in eqs]).reshape(-1, 2),
+        ntendon=len(tendons), tendon_names=[t["name"] for t in tendons], tendon_joints=[t["joints"] for t in tendons],
+        tendon_coefs=[t["coefs"] for t in tendons],
+        nu=len(acts), actuator_names=[a["name"] for a in acts], actuator_joint=np.array([a["joint"] for a in acts], dtype=np.int32),
+        actuator_tendon=np.array([a["tendon"] for a in acts], dtype=np.int32),
+        actuator_gainprm=np.array([a["gainprm"] for a in acts]).reshape(-1, 3), actuator_biasprm=np.array([a["biasprm"] for a in acts]).reshape(-1, 3),
+        actuator_ctrlrange=np.array([a["ctrlrange"] for a in acts]).reshape(-1, 2),
+        actuator_forcerange=np.array([a["forcerange"] for a in acts]).reshape(-1, 2),
+        key_names=[k["name"] for k in keys], key_qpos=[list(map(float, k["qpos"])) for k in keys],
     )
-    # qpos0: hinge 0, free joint = body pose
+    # qpos0: hinge / slide 0, free joint = body pose
     qpos0 = np.zeros(nq)
     for ji, j in enumerate(joints):
         if j["type"] == JNT_FREE:
@@ -526,6 +578,9 @@ def host_kinematics(mc: ModelConsts, qpos):
         if j >= 0:
             ang = qpos[mc.jnt_qposadr[j]]
             ax = mc.jnt_axis[j]
+            if mc.jnt_type[j] == JNT_SLIDE:
+                xpos[b] = xpos[b] + quat_to_mat(xquat[b]) @ ax * ang
+                continue
             # joint anchor offset jnt_pos is zero in the supported scenes
             if np.any(mc.jnt_pos[j] != 0):
                 raise NotImplementedError("non-zero joint pos")
@@ -569,6 +624,8 @@ def host_jac(mc: ModelConsts, xpos, xmat, body, point):
                 ax = xmat[b] @ mc.jnt_axis[j]
                 jr[:, da] = ax
                 jp[:, da] = np.cross(ax, point - xpos[b])
+            elif mc.jnt_type[j] == JNT_SLIDE:
+                jp[:, da] = xmat[b] @ mc.jnt_axis[j]
             else:
                 jp[:, da:da + 3] = np.eye(3)
                 for k in range(3):
@@ -618,10 +675,12 @@ def exclude_body_pairs(mc: ModelConsts, body_pairs) -> ModelConsts:
     return ModelConsts(d)
 
 
-def _candidate_pairs(geom_type, geom_body, contype, conaffinity, body_weldid, body_parent, excluded=()):
+def _candidate_pairs(geom_type, geom_body, contype, conaffinity, body_weldid, body_parent, excluded=(), unknown=None):
     """MJX's static candidate pair list (collision_driver: same weld body / parent-child weld bodies / contype-conaffinity
-    filters; pairs grouped by geom-type pair, geom1 = the lower type): pair_geom, pair_type, pair_nslot, pair_slotadr, collides."""
-    col = [g for g in range(len(geom_type)) if (contype[g] or conaffinity[g]) and geom_type[g] in (GEOM_PLANE, GEOM_CAPSULE, GEOM_BOX)]
+    filters; pairs grouped by geom-type pair, geom1 = the lower type): pair_geom, pair_type, pair_nslot, pair_slotadr, collides.
+    Pairs whose type combination has no slot count in PAIR_SLOTS (cylinders: the dual-arm scene) raise, or -- when the caller
+    passes a list as ``unknown`` -- are appended to it as (geom1, geom2) and left out of the slot table."""
+    col = [g for g in range(len(geom_type)) if (contype[g] or conaffinity[g]) and geom_type[g] in (GEOM_PLANE, GEOM_CAPSULE, GEOM_BOX, GEOM_CYLINDER)]
     for g in range(len(geom_type)):
         if (contype[g] or conaffinity[g]) and g not in col:
             raise NotImplementedError(f"collision geom type {int(geom_type[g])}")
@@ -642,7 +701,10 @@ def _candidate_pairs(geom_type, geom_body, contype, conaffinity, body_weldid, bo
             g1, g2 = (ga, gb) if geom_type[ga] <= geom_type[gb] else (gb, ga)
             key = (int(geom_type[g1]), int(geom_type[g2]))
             if key not in PAIR_SLOTS:
-                raise NotImplementedError(f"collision pair types {key}")
+                if unknown is None:
+                    raise NotImplementedError(f"collision pair types {key}")
+                unknown.append((g1, g2))
+                continue
             pairs.append((key, g1, g2))
     pairs.sort(key=lambda p: (p[0], p[1], p[2]))
     pair_geom = np.array([[p[1], p[2]] for p in pairs], dtype=np.int32).reshape(-1, 2)
@@ -663,8 +725,8 @@ def from_mjmodel(m) -> ModelConsts:
     A = lambda x, dt=np.float64: np.array(x, dtype=dt)
     name = lambda kind, i: getattr(m, kind)(i).name
     jnt_type = A(m.jnt_type, np.int32)
-    if not np.all(np.isin(jnt_type, (JNT_FREE, JNT_HINGE))):
-        raise NotImplementedError("only hinge and free joints are supported")
+    if not np.all(np.isin(jnt_type, (JNT_FREE, JNT_SLIDE, JNT_HINGE))):
+        raise NotImplementedError("only hinge, slide and free joints are supported")
     jnt_body = A(m.jnt_bodyid, np.int32)
     jnt_dofadr = A(m.jnt_dofadr, np.int32)
     body_jntadr = A(m.body_jntadr, np.int32)
@@ -688,8 +750,6 @@ def from_mjmodel(m) -> ModelConsts:
            "eulerdamp": 0 if flags & (1 << 14) else 1,            # mjDSBL_EULERDAMP
            "actuation": 0 if flags & (1 << 10) else 1,            # mjDSBL_ACTUATION
            "integrator": {0: "Euler", 1: "RK4", 2: "implicit", 3: "implicitfast"}.get(int(m.opt.integrator), "?")}
-    if opt["integrator"] != "Euler":
-        raise NotImplementedError("only the Euler integrator is supported")
     d = dict(
         xml="<mujoco.MjModel>", nq=int(m.nq), nv=int(m.nv), nbody=nbody, njnt=njnt, ngeom=ngeom, opt=opt,
         body_names=[name("body", i) for i in range(nbody)],
@@ -710,6 +770,7 @@ def from_mjmodel(m) -> ModelConsts:
         pair_geom=pair_geom, pair_type=pair_type, pair_nslot=pair_nslot, pair_slotadr=pair_slotadr, ncon=int(pair_nslot.sum()),
         qpos0=A(m.qpos0), dof_invweight0=A(m.dof_invweight0), body_invweight0=A(m.body_invweight0).reshape(nbody, 2),
         meaninertia=float(m.stat.meaninertia),
+        neq=int(getattr(m, "neq", 0)), ntendon=int(getattr(m, "ntendon", 0)), nu=int(getattr(m, "nu", 0)),
     )
     return ModelConsts(d)
 

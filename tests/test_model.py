@@ -39,7 +39,11 @@ def test_forward_kinematics_pins(mc):
 def test_packaged_constants_match_the_xml(mc):
     fresh = compile_mjcf(REF_XML)
     for k, v in fresh.d.items():
-        if isinstance(v, np.ndarray):
+        if k not in mc.d:
+            # fields of the loader extensions (equalities, tendons, actuators, keyframes, unknown pair types): scene A has
+            # none of them, and the packaged table predates them
+            assert (v == 0 if isinstance(v, int) else len(v) == 0), k
+        elif isinstance(v, np.ndarray):
             np.testing.assert_allclose(v, mc.d[k], rtol=0, atol=1e-12, err_msg=k)
         elif k != "xml":
             assert v == mc.d[k], k
@@ -180,3 +184,74 @@ def test_from_mjmodel_reproduces_the_compiled_model(mc):
     a = np.frombuffer(bytes(k1), dtype=np.float32)
     b = np.frombuffer(bytes(k2), dtype=np.float32)
     np.testing.assert_allclose(a, b, rtol=0, atol=1e-6)
+
+
+SCENE_B = "/root/reference/universal_robots_ur5e/scene_mjx.xml"
+DUAL_ARM = "/root/reference/universal_robots_ur5e/dual_arm_scene.xml"
+
+
+@pytest.mark.skipif(not os.path.exists(SCENE_B), reason="reference checkout not present (GPU box)")
+def test_scene_b_loads_with_the_counts_of_the_survey(tmp_path):
+    """universal_robots_ur5e/scene_mjx.xml (the file BASELINE.json names; the planner itself loads scene A): slide joints of the
+    two Hand-E fingers, their joint equality and fixed tendon, two contact excludes, one free box.  Counts: SURVEY.md A.3."""
+    from collections import Counter
+    from manipulator_mujoco_b200.mjcf import GEOM_BOX, GEOM_CAPSULE, GEOM_PLANE, JNT_SLIDE, ModelConsts
+    mb = compile_mjcf(SCENE_B)
+    assert (mb.nq, mb.nv, mb.njnt) == (15, 14, 9)
+    assert list(mb.jnt_type).count(JNT_SLIDE) == 2 and (mb.neq, mb.ntendon, mb.nexclude, mb.nu) == (1, 1, 2, 0)
+    assert mb.opt["iterations"] == 1 and mb.opt["ls_iterations"] == 5 and mb.opt["eulerdamp"] == 0 and mb.opt["integrator"] == "Euler"
+    assert not np.any(mb.body_gravcomp)                                              # no gravity compensation in this scene
+    pairs = Counter((int(a), int(b)) for a, b in mb.pair_type)
+    assert pairs == {(GEOM_PLANE, GEOM_CAPSULE): 10, (GEOM_CAPSULE, GEOM_BOX): 20, (GEOM_CAPSULE, GEOM_CAPSULE): 27,
+                     (GEOM_PLANE, GEOM_BOX): 1, (GEOM_BOX, GEOM_BOX): 1}
+    assert mb.ncon == 95
+    robot = [mb.geom_id(f"robot_{i}") for i in range(10)]
+    nrob = sum(int(n) for (g1, g2), n in zip(mb.pair_geom, mb.pair_nslot) if g1 in robot or g2 in robot)
+    assert nrob == 87                                                                # robot-involving contact slots
+    assert int(mb.jnt_limited.sum()) == 8 and mb.neq + int(mb.jnt_limited.sum()) + 4 * mb.ncon == 389     # nefc
+    e = 0
+    assert mb.jnt_names[mb.eq_joint1[e]] == "hande_left_finger_joint" and mb.jnt_names[mb.eq_joint2[e]] == "hande_right_finger_joint"
+    np.testing.assert_array_equal(mb.eq_polycoef[e], [0, 1, 0, 0, 0])
+    assert mb.tendon_coefs[0] == [0.5, 0.5]
+    np.testing.assert_allclose(mb.geom_size[mb.geom_id("robot_0")][:2], [0.03, 0.015])
+    # host kinematics / dynamics understand the slide joints: opening a finger moves its body along the joint axis, and its
+    # generalized inertia is the finger's mass
+    q = mb.qpos0.copy()
+    x0, _, xm = host_kinematics(mb, q)
+    jl = mb.jnt_names.index("hande_left_finger_joint")
+    q[mb.jnt_qposadr[jl]] = 0.02
+    x1, _, _ = host_kinematics(mb, q)
+    b = mb.jnt_body[jl]
+    np.testing.assert_allclose(x1[b] - x0[b], 0.02 * xm[b] @ mb.jnt_axis[jl], atol=1e-12)
+    M, _, _ = host_mass_matrix(mb, mb.qpos0)
+    assert M.shape == (14, 14) and np.linalg.eigvalsh(M).min() > 0
+    np.testing.assert_allclose(M[mb.jnt_dofadr[jl], mb.jnt_dofadr[jl]], mb.body_mass[b] + mb.jnt_armature[jl], rtol=1e-12)
+    # the table survives the JSON round trip the package ships scene A through
+    path = str(tmp_path / "scene_b.json")
+    mb.to_json(path)
+    back = ModelConsts.from_json(path)
+    assert back.neq == 1 and back.tendon_joints == mb.tendon_joints and np.array_equal(back.pair_geom, mb.pair_geom)
+    # ... and the rollout kernel says exactly what it lacks for it
+    with pytest.raises(NotImplementedError, match=r"2 slide joint\(s\), 1 equality constraint\(s\), 1 tendon\(s\)"):
+        KM.build_kmodel(mb, 0.05)
+
+
+@pytest.mark.skipif(not os.path.exists(DUAL_ARM), reason="reference checkout not present (GPU box)")
+def test_dual_arm_scene_loads_and_is_refused_by_the_kernel():
+    """universal_robots_ur5e/dual_arm_scene.xml (BASELINE config 4, an extension: the reference planner cannot load it either,
+    SURVEY.md finding 0.4 / A.4): 12 hinges, 12 position servos, implicitfast, cylinder end-effector geoms, keyframe `home`."""
+    from manipulator_mujoco_b200.mjcf import GEOM_CYLINDER
+    md = compile_mjcf(DUAL_ARM)
+    assert (md.nq, md.nv, md.njnt, md.nu) == (12, 12, 12, 12) and md.opt["integrator"] == "implicitfast"
+    cyl = [g for g in range(md.ngeom) if md.geom_type[g] == GEOM_CYLINDER and md.geom_collides[g]]
+    assert len(cyl) == 2
+    np.testing.assert_allclose(md.actuator_gainprm[0], [2000, 0, 0]); np.testing.assert_allclose(md.actuator_biasprm[0], [0, -2000, -400])
+    assert md.key_names == ["home"] and len(md.key_qpos[0]) == 12
+    t2 = md.body_id("table_2") if "table_2" in md.body_names else None
+    # pairs with a cylinder have no slot count in the MJX table this package restates: listed, not guessed
+    assert len(md.pair_unknown) > 0 and all(md.geom_type[g1] == GEOM_CYLINDER or md.geom_type[g2] == GEOM_CYLINDER for g1, g2 in md.pair_unknown)
+    M, _, _ = host_mass_matrix(md, np.array(md.key_qpos[0]))
+    assert M.shape == (12, 12) and np.linalg.eigvalsh(M).min() > 0
+    assert np.allclose(M[:6, 6:], 0)                                                 # two independent chains
+    with pytest.raises(NotImplementedError, match="12 hinge joints"):
+        KM.build_kmodel(md, 0.05)
