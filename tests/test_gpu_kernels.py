@@ -261,6 +261,24 @@ def test_tick_record_packs_what_compute_cem_returns(planner):
             assert not r.any() and not np.signbit(r).any()
 
 
+def test_normal_draw_cache_is_only_a_cache(planner):
+    """cem_planner keeps the normal draws of a key (the reference restarts from the same key every call); switching the cache off
+    (what bench.py times) must give the same samples."""
+    mean, cov = np.zeros(planner.nvar, np.float32), 10 * np.eye(planner.nvar, dtype=np.float32)
+    old = planner.cache_normal_draws
+    try:
+        planner.cache_normal_draws = True
+        a1, k1 = planner.compute_xi_samples(planner.key, mean, cov)
+        a2, _ = planner.compute_xi_samples(planner.key, mean, cov)
+        planner.cache_normal_draws = False
+        b1, k2 = planner.compute_xi_samples(planner.key, mean, cov)
+        b2, _ = planner.compute_xi_samples(planner.key, mean, cov)
+    finally:
+        planner.cache_normal_draws = old
+    assert torch.equal(a1, a2) and torch.equal(a1, b1) and torch.equal(b1, b2)
+    assert np.array_equal(np.asarray(k1), np.asarray(k2))
+
+
 def test_notebook_attributes_jit_step_and_vec_product(planner, oracle64):
     """mjx_planner.py:98,108: `vec_product` (vmapped outer product) and `jit_step` (one mjx.step of one environment),
     touched by mpc_planning.ipynb."""
