@@ -919,9 +919,11 @@ int cemk_set_horizon(cemk_handle* h, int T, const float* G, const float* Kpp, co
   CK(cudaMemcpy(h->d_K, kc, (nc * nc + nc * 5 + 3) * sizeof(float), cudaMemcpyHostToDevice));
   h->T = T;
   int smem = 0;
-  CEMK_FOR_NCOEF(nc, { smem = project_smem<NC>(T, 32 * PROJ_WARPS); CK(cudaFuncSetAttribute(k_project<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-                       CK(cudaFuncSetAttribute(k_project<NC>, cudaFuncAttributePreferredSharedMemoryCarveout, 100 * 3 * smem / (228 * 1024) + 8)); });
+  CEMK_FOR_NCOEF(nc, { smem = project_smem<NC>(T, 32 * PROJ_WARPS); });
   if (smem > 227 * 1024) return set_err(CEMK_ERR_ARG, "cemk_set_horizon: horizon too long for the projection kernel's shared memory");
+  const int carve = 100 * PROJ_MINB * smem / (228 * 1024) + 8;                       // room for PROJ_MINB CTAs per SM, in percent
+  CEMK_FOR_NCOEF(nc, { CK(cudaFuncSetAttribute(k_project<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                       CK(cudaFuncSetAttribute(k_project<NC>, cudaFuncAttributePreferredSharedMemoryCarveout, carve > 100 ? 100 : carve)); });
   return CEMK_OK;
 }
 

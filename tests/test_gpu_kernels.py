@@ -52,6 +52,20 @@ def test_projection_filter_and_bernstein(planner):
     np.testing.assert_allclose(thetadot.cpu().numpy().reshape(512, 6, 50)[:, 2, :], xf.cpu().numpy()[:, 22:33] @ pr.Pdot.T.astype(np.float32), atol=1e-4)
 
 
+@pytest.mark.parametrize("T,B", [(7, 3), (16, 1000), (100, 37), (400, 9)])
+def test_projection_filter_across_horizons_and_ragged_batches(T, B):
+    """k_project deals 8 problems x 4 time slices to a warp: horizons that are not a multiple of four, batches that leave the last
+    warp partly idle, a batch smaller than a warp's 8 problems / 6, and a long horizon (more shared memory per CTA)."""
+    from manipulator_mujoco_b200 import cem_planner
+    pl = cem_planner(num_dof=6, num_batch=B, num_steps=T, timestep=0.05, maxiter_cem=1, num_elite=0.5, w_pos=20.0, w_rot=3.0, w_col=80.0,
+                     maxiter_projection=10)
+    pr, z, xi, st, xif, td = planner_inputs(T, B, seed=T)
+    xf, thetadot = pl._project(xi, st, True)
+    scale = max(1.0, float(np.abs(xif).max()))
+    np.testing.assert_allclose(xf.cpu().numpy(), xif, rtol=0, atol=5e-5 * scale)
+    np.testing.assert_allclose(thetadot.cpu().numpy(), xif @ pr.A_thetadot.T, rtol=0, atol=5e-5 * max(1.0, float(np.abs(td).max())))
+
+
 @pytest.mark.parametrize("n", [1, 5, 100, 1000, 4096, 5000, 8192, 8193, 20000])   # <= 8192: counting-rank kernel, above: bitonic network
 def test_argsort_topk_is_stable_with_nan_last(planner, n):
     rng = np.random.default_rng(n)
