@@ -1,4 +1,7 @@
-# usage: bash tools/_finalN.sh N   (scratch driver of the multi-GPU measurement cycle; every command under its own timeout)
+#!/bin/bash
+# The multi-GPU leg of a measurement cycle on an N-GPU box:  gpurun --gpus N -- 'bash tools/scale_cycle.sh N'
+# bench.py under torchrun (weak-scaling line + the 65 536-sample leg) -> gpurun_out/f_scaleN.json; at N = 8 also the per-rank stage
+# times (tools/mg_profile.py), at N = 2 the sharded-vs-unsharded bit-identity test.  Every command runs under its own timeout.
 N=$1
 timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29571 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/f_scale$N.json 2> gpurun_out/f_scale$N.err; echo "bench rc $?"
 if [ "$N" = "8" ]; then timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29544 tools/mg_profile.py > gpurun_out/f_mgprof$N.txt 2>&1; echo "mgprof rc $?"; fi
