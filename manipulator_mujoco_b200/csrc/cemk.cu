@@ -63,6 +63,7 @@ struct cemk_handle {
   float* d_ovf;                    // contact spill area of every sample (same capacity as d_prevd)
   int force_rerun;               // debug option: recompute every sample with the all-in-shared-memory instantiation
   int cta_samples;                 // debug option "cta_samples": fixed number of samples per CTA (0 = see cemk_rollout_cost)
+  float* d_mc;                     // block sums of the blocked mean / covariance update (k_mc_partial -> k_mc_finish)
 };
 
 // ---------------------------------------------------------------------------------------------- rollout
@@ -835,6 +836,95 @@ __global__ void __launch_bounds__(MC_THREADS) k_mean_cov(int NVAR, int k, const 
   }
 }
 
+// Large elite sets (k >= MC_BLOCKED_MINK: the 8-GPU configurations, where every rank redoes the update over all k global
+// elites): k_mean_cov makes every one of its nvar CTAs stream the whole elite matrix twice (57 MB of L2 reads at k = 1638,
+// 35 us; 67 us at k = 3276).  Here the elites are cut into blocks of MC_EB; a CTA reads its block once and writes the block's
+// weighted sums about the shift a = mean_prev,
+//   S0 = sum w,  S1[j] = sum w (x_j - a_j),  S2[r][c] = sum w (x_r - a_r)(x_c - a_c)   (c <= r),
+// and a second launch adds the blocks in block order and forms, with delta = S1 / S0, the new mean m = (1 - am) a + am (a + delta)
+// and the covariance about m:  S2 / S0 - delta D^T - D delta^T + D D^T,  D = m - a.  Fixed summation order (block by block,
+// elite by elite) => bit-identical on every rank.  The shift keeps the single pass accurate: after the first iteration the
+// elites sit around mean_prev (|delta| below one standard deviation), and in the first one mean_prev is the sampler's mean.
+#define MC_EB 32
+#define MC_BLOCKED_MINK 1024
+#define MC_BLOCKED_MAXK 8192
+#define MC_PAD 16                       // the number of blocks is padded to a multiple (zero blocks): no remainder loop in the sums
+static int mc_blocks(int k) { return ((k + MC_EB - 1) / MC_EB + MC_PAD - 1) / MC_PAD * MC_PAD; }
+static size_t mc_stride(int nvar) { return 1 + (size_t)nvar + (size_t)nvar * (nvar + 1) / 2; }
+__global__ void __launch_bounds__(256) k_mc_partial(int NVAR, int k, const float* __restrict__ cost, const float* __restrict__ xi,
+                                                    const float* __restrict__ mean_prev, float lamda, float* __restrict__ part) {
+  __shared__ float red[256];
+  __shared__ float sw[MC_EB];
+  __shared__ float sd[MC_EB][MAXVAR + 1];          // x - a
+  __shared__ float swd[MC_EB][MAXVAR + 1];         // w (x - a)
+  const int tid = threadIdx.x, e0 = blockIdx.x * MC_EB, ne = k - e0 < MC_EB ? (k - e0 > 0 ? k - e0 : 0) : MC_EB;
+  const int npair = NVAR * (NVAR + 1) / 2;
+  float* P = part + (size_t)blockIdx.x * (1 + NVAR + npair);
+  if (ne == 0) {                                   // padding block
+    for (int e = tid; e < 1 + NVAR + npair; e += 256) P[e] = 0.f;
+    return;
+  }
+  float v = INFINITY;
+  for (int i = tid; i < k; i += 256) v = fminf(v, cost[i]);
+  red[tid] = v; __syncthreads();
+  for (int o = 128; o; o >>= 1) { if (tid < o) red[tid] = fminf(red[tid], red[tid + o]); __syncthreads(); }
+  const float cmin = red[0], il = __frcp_rn(lamda);
+  if (tid < MC_EB) sw[tid] = tid < ne ? precise_expf(-il * (cost[e0 + tid] - cmin)) : 0.f;
+  for (int idx = tid; idx < ne * NVAR; idx += 256) { const int e = idx / NVAR, j = idx - e * NVAR; sd[e][j] = xi[(size_t)(e0 + e) * NVAR + j] - mean_prev[j]; }
+  __syncthreads();
+  for (int idx = tid; idx < ne * NVAR; idx += 256) { const int e = idx / NVAR, j = idx - e * NVAR; swd[e][j] = sw[e] * sd[e][j]; }
+  __syncthreads();
+  if (tid == 0) { float t = 0.f; for (int e = 0; e < ne; ++e) t += sw[e]; P[0] = t; }
+  if (tid < NVAR) { float t = 0.f; for (int e = 0; e < ne; ++e) t += swd[e][tid]; P[1 + tid] = t; }
+  for (int p = tid; p < npair; p += 256) {
+    int r = (int)((sqrtf(8.f * (float)p + 1.f) - 1.f) * 0.5f);
+    while (r * (r + 1) / 2 > p) --r;
+    while ((r + 1) * (r + 2) / 2 <= p) ++r;
+    const int c = p - r * (r + 1) / 2;
+    float t = 0.f;
+#pragma unroll 8
+    for (int e = 0; e < ne; ++e) t += sd[e][r] * swd[e][c];
+    P[1 + NVAR + p] = t;
+  }
+}
+// grid = nvar CTAs (covariance row r = blockIdx.x, entries c <= r and their mirror images), 128 threads
+__global__ void __launch_bounds__(128) k_mc_finish(int NVAR, int nblk, const float* __restrict__ part, const float* __restrict__ mean_prev,
+                                                   const float* __restrict__ cov_prev, float am, float ac, float* __restrict__ mean_out,
+                                                   float* __restrict__ cov_out) {
+  __shared__ float sdelta[MAXVAR], sD[MAXVAR], sS2[MAXVAR], sW;
+  const int tid = threadIdx.x, r = blockIdx.x, npair = NVAR * (NVAR + 1) / 2;
+  const size_t stride = 1 + (size_t)NVAR + npair;
+  // one pass over the blocks: thread t < nvar adds S1[t] and S2[r][t]; thread 127 adds S0 (nvar <= 96)
+  {
+    const bool w = tid == 127, on = tid < NVAR, lo = on && tid <= r;
+    const float* p1 = part + (w ? 0 : 1 + (on ? tid : 0));
+    const float* p2 = part + 1 + NVAR + (size_t)r * (r + 1) / 2 + (lo ? tid : 0);
+    float s1 = 0.f, s2 = 0.f;
+    if (w || on) {
+#pragma unroll 16
+      for (int b = 0; b < nblk; ++b) { s1 += p1[b * stride]; s2 += p2[b * stride]; }
+    }
+    if (w) sW = s1;
+    if (on) { sdelta[tid] = s1; sS2[tid] = s2; }
+  }
+  __syncthreads();
+  const float W = sW;
+  if (tid < NVAR) {
+    const float a = mean_prev[tid], delta = __fdiv_rn(sdelta[tid], W);
+    const float mnew = (1.f - am) * a + am * (a + delta);
+    sdelta[tid] = delta; sD[tid] = mnew - a;
+    if (r == 0) mean_out[tid] = mnew;
+  }
+  __syncthreads();
+  if (tid <= r && tid < NVAR) {
+    const int c = tid;
+    const float cv = __fdiv_rn(sS2[c], W) - sdelta[r] * sD[c] - sD[r] * sdelta[c] + sD[r] * sD[c];
+    cov_out[r * NVAR + c] = (1.f - ac) * cov_prev[r * NVAR + c] + ac * cv + (r == c ? 0.0001f : 0.f);
+    if (c != r) cov_out[c * NVAR + r] = (1.f - ac) * cov_prev[c * NVAR + r] + ac * cv;
+  }
+}
+
+
 // ---------------------------------------------------------------------------------------------- calibration
 // FP32 FMA throughput of this GPU under the kernel's own conditions (register operands, 8 independent
 // chains per thread): the measured denominator of the rollout kernel's FP32 roofline.
@@ -877,6 +967,8 @@ int cemk_create(const void* kmodel, int kmodel_bytes, int device, cemk_handle** 
   CK(cudaFuncSetAttribute(k_rollout<KM_NC_FAST, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rollout_smem<KM_NC_FAST, 4>()));
   CK(cudaFuncSetAttribute(k_rollout<KM_NC_BIG, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)rollout_smem<KM_NC_BIG, 1>()));
+  h->d_mc = nullptr;
+  CK(cudaMalloc(&h->d_mc, sizeof(float) * mc_blocks(MC_BLOCKED_MAXK) * mc_stride(MAXVAR)));
   CK(cudaFuncSetAttribute(k_rank_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(unsigned long long) * RANK_MAXN)));
   CK(cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sample_smem(MAXVAR)));
   CK(cudaFuncSetAttribute(k_merge_lists<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(unsigned) * MERGE_MAXKEYS)));
@@ -886,7 +978,7 @@ int cemk_create(const void* kmodel, int kmodel_bytes, int device, cemk_handle** 
 int cemk_destroy(cemk_handle* h) {
   if (!h) return CEMK_OK;
   DevGuard guard(h->device);
-  cudaFree(h->d_model); cudaFree(h->d_G); cudaFree(h->d_K); cudaFree(h->d_flags); cudaFree(h->d_prevd); cudaFree(h->d_ovf);
+  cudaFree(h->d_model); cudaFree(h->d_G); cudaFree(h->d_K); cudaFree(h->d_flags); cudaFree(h->d_prevd); cudaFree(h->d_ovf); cudaFree(h->d_mc);
   delete h;
   return CEMK_OK;
 }
@@ -1160,6 +1252,14 @@ int cemk_mean_cov(cemk_handle* h, int k, const float* cost_elite, const float* x
   if (!h || !cost_elite || !xi_elite || !mean_prev || !cov_prev || !mean_out || !cov_out || k <= 0)
     return set_err(CEMK_ERR_ARG, "cemk_mean_cov: bad argument");
   DevGuard guard(h->device);
+  if (k >= MC_BLOCKED_MINK && k <= MC_BLOCKED_MAXK) {
+    const int nblk = mc_blocks(k);
+    k_mc_partial<<<nblk, 256, 0, (cudaStream_t)stream>>>(h->nvar, k, cost_elite, xi_elite, mean_prev, lamda, h->d_mc);
+    k_mc_finish<<<h->nvar, 128, 0, (cudaStream_t)stream>>>(h->nvar, nblk, h->d_mc, mean_prev, cov_prev, alpha_mean, alpha_cov, mean_out, cov_out);
+    h->launches += 2;
+    CK(cudaPeekAtLastError());
+    return CEMK_OK;
+  }
   k_mean_cov<<<h->nvar, MC_THREADS, 0, (cudaStream_t)stream>>>(h->nvar, k, cost_elite, xi_elite, mean_prev, cov_prev, lamda, alpha_mean, alpha_cov, mean_out, cov_out);
   h->launches += 1;
   CK(cudaPeekAtLastError());

@@ -103,6 +103,35 @@ def test_mean_cov(planner):
     np.testing.assert_allclose(cov.cpu().numpy(), rc, rtol=0, atol=5e-5)
 
 
+@pytest.mark.parametrize("k,case", [(1023, "far"), (1024, "first"), (1638, "far"), (1638, "near"), (3276, "near"), (3276, "first")])
+def test_mean_cov_large_elite_sets(planner, k, case):
+    """Elite sets of the multi-GPU configurations (k >= 1024 takes the blocked single-pass update about mean_prev; 1023 is the
+    last size of the two-pass kernel): against the float64 restatement of mjx_planner.py:326-335, with mean_prev far from the
+    elites, near them (later CEM iterations) and at the sampler's mean (first iteration); deterministic run to run."""
+    pr, *_ = planner_inputs(50, 8)
+    rng = np.random.default_rng(k)
+    ce = np.sort(rng.uniform(200, 260, k)).astype(np.float32)
+    if case == "far":
+        xe, mp_ = rng.normal(size=(k, 66)).astype(np.float32), rng.normal(size=66).astype(np.float32)
+    elif case == "near":
+        mp_ = (3 * rng.normal(size=66)).astype(np.float32)
+        xe = (mp_ + 0.3 * rng.normal(size=(k, 66))).astype(np.float32)
+    else:
+        mp_, xe = np.zeros(66, np.float32), (np.sqrt(10) * rng.normal(size=(k, 66))).astype(np.float32)
+    A = rng.normal(size=(66, 66)).astype(np.float32)
+    cp_ = (A @ A.T / 66 + 10 * np.eye(66)).astype(np.float32)
+    mean, cov = planner.compute_mean_cov(ce, mp_, cp_, xe)
+    mean2, cov2 = planner.compute_mean_cov(ce, mp_, cp_, xe)
+    assert torch.equal(mean, mean2) and torch.equal(cov, cov2)
+    rm, rc = pr.compute_mean_cov(ce.astype(np.float64), mp_.astype(np.float64), cp_.astype(np.float64), xe.astype(np.float64))
+    np.testing.assert_allclose(mean.cpu().numpy(), rm, rtol=0, atol=2e-5)
+    np.testing.assert_allclose(cov.cpu().numpy(), rc, rtol=0, atol=5e-5)
+    c = cov.cpu().numpy()
+    if k >= 1024:
+        # the elite part of the blocked update is exactly symmetric (one value written to both halves)
+        np.testing.assert_allclose(c - 0.4 * cp_, (c - 0.4 * cp_).T, rtol=0, atol=1e-5)
+
+
 def test_compute_cem_end_to_end_against_oracle_pipeline(oracle64):
     """One CEM iteration (C1-like config, T=16) through the public API vs the same pipeline assembled
     from the oracle pieces with the *same* normal draws: costs, elite set, new mean."""
