@@ -322,6 +322,24 @@ def test_normal_draw_cache_is_only_a_cache(planner):
     assert np.array_equal(np.asarray(k1), np.asarray(k2))
 
 
+def test_graph_replay_equals_eager_ticks_with_a_large_elite_set():
+    """compute_cem runs two eager ticks, captures the tick into a CUDA graph and replays it: every tick must return the same
+    tuple bit for bit (the reference restarts from the same key).  20 480 samples = 1024 elites, which takes the blocked
+    mean / covariance update (two launches on a library-owned workspace) and cemk_tick_record through capture and replay."""
+    from manipulator_mujoco_b200 import cem_planner
+    pl = cem_planner(num_dof=6, num_batch=20480, num_steps=16, timestep=0.05, maxiter_cem=2, num_elite=0.05, w_pos=20.0, w_rot=3.0, w_col=80.0,
+                     maxiter_projection=10)
+    assert pl.ellite_num == 1024
+    tp, tr = np.array([-0.3, -0.3, 0.5]), np.array([0.0, 1.0, 0.0, 0.0])
+    outs = [pl.compute_cem(np.zeros(66), Q0, np.zeros(6), np.zeros(6), tp, tr) for _ in range(4)]
+    assert pl._graph is not None
+    host = lambda a: a.cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            np.testing.assert_array_equal(host(a), host(b))
+    assert np.all(np.isfinite(outs[0][0])) and pl.overflow_samples == 0
+
+
 def test_notebook_attributes_jit_step_and_vec_product(planner, oracle64):
     """mjx_planner.py:98,108: `vec_product` (vmapped outer product) and `jit_step` (one mjx.step of one environment),
     touched by mpc_planning.ipynb."""
