@@ -1,12 +1,14 @@
 // cemk.cu -- sm_100a kernels + the C ABI declared in include/cemk.h.
 //
 // Kernels (one per stage of cem_planner.cem_iter, reference mjx_planner.py:337-362):
-//   k_chol66 / k_sample      compute_xi_samples            (:313-316)
+//   k_jax_normal / k_chol66 / k_sample            compute_xi_samples       (:313-316)
 //   k_project                compute_projection_filter + A_thetadot @ xi   (:181-249, :348)
 //   k_rollout                vmap(scan(mjx.step)) + compute_cost_batch     (:251-303)   <- hot kernel
 //   k_cost_batch             compute_cost_batch on materialised trajectories (:277-303)
-//   k_make_keys / k_bitonic* / k_finish_sort      compute_ellite_samples   (:306-310)
-//   k_mean_cov               compute_mean_cov                              (:326-335)
+//   k_rank_select (n <= 8192) | k_make_keys / k_bitonic* / k_finish_sort / k_pack_sorted     compute_ellite_samples   (:306-310)
+//   k_merge_lists            the same selection over the per-rank sorted lists of several GPUs
+//   k_mean_cov | k_mc_partial + k_mc_finish (k >= 1024)                    compute_mean_cov (:326-335)
+//   k_tick_record            what compute_cem keeps of an iteration        (:390-404)
 // The rollout core lives in rollout_core.h (shared with the CPU emulation used by the no-GPU tests).
 #include <cuda_runtime.h>
 #include <stdint.h>
