@@ -12,8 +12,7 @@ import ctypes as C
 
 import numpy as np
 
-from .mjcf import (GEOM_BOX, GEOM_CAPSULE, GEOM_PLANE, JNT_FREE, JNT_HINGE, ModelConsts, quat_mul,
-                   quat_normalize, quat_to_mat)
+from .mjcf import GEOM_BOX, GEOM_CAPSULE, GEOM_PLANE, JNT_FREE, JNT_HINGE, ModelConsts, quat_mul, quat_to_mat
 
 NL, NV, NQ, MAXCAP, MAXSBOX, MAXRPAIR, MAXBPAIR, MAXNEAR = 6, 12, 13, 12, 8, 160, 8, 96
 LANE_GROUP = 16          # lanes per sample in the rollout kernel (csrc/warp_dsl.h KW); one collider pass = 16 pair entries

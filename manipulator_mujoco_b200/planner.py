@@ -33,7 +33,7 @@ import torch
 
 from . import _lib, jax_prng, parallel
 from .bernstein import bernstein_coeff_ordern_new
-from .kmodel import KModel, build_kmodel
+from .kmodel import build_kmodel
 from .mjcf import ModelConsts, exclude_body_pairs, host_kinematics, load_model, quat_mul, quat_normalize
 
 _VP = C.c_void_p

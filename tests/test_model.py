@@ -8,7 +8,7 @@ import pytest
 
 from conftest import GOLDEN
 from manipulator_mujoco_b200 import kmodel as KM
-from manipulator_mujoco_b200.mjcf import compile_mjcf, host_kinematics, host_mass_matrix, load_model
+from manipulator_mujoco_b200.mjcf import compile_mjcf, host_kinematics, host_mass_matrix
 
 IDS = json.load(open(os.path.join(GOLDEN, "scene_ids.json")))
 REF_XML = "/root/reference/sampling_based_planner/ur5e_hande_mjx/scene.xml"
@@ -247,7 +247,6 @@ def test_dual_arm_scene_loads_and_is_refused_by_the_kernel():
     assert len(cyl) == 2
     np.testing.assert_allclose(md.actuator_gainprm[0], [2000, 0, 0]); np.testing.assert_allclose(md.actuator_biasprm[0], [0, -2000, -400])
     assert md.key_names == ["home"] and len(md.key_qpos[0]) == 12
-    t2 = md.body_id("table_2") if "table_2" in md.body_names else None
     # pairs with a cylinder have no slot count in the MJX table this package restates: listed, not guessed
     assert len(md.pair_unknown) > 0 and all(md.geom_type[g1] == GEOM_CYLINDER or md.geom_type[g2] == GEOM_CYLINDER for g1, g2 in md.pair_unknown)
     M, _, _ = host_mass_matrix(md, np.array(md.key_qpos[0]))

@@ -1,7 +1,7 @@
 """The step loop of a kernel in address order, from an ncu report captured with `--set full --import-source on`: which SASS
 instructions inside the loop's address span were executed (hot) and which never or rarely were (cold runs that still occupy
 instruction-cache lines between hot code).  usage: python tools/ncu_cold_runs.py report.ncu-rep <kernel name regex> path/to/libcemk.so"""
-import collections, csv, os, re, subprocess, sys, tempfile
+import csv, os, re, subprocess, sys, tempfile
 rep, kname, lib = sys.argv[1], sys.argv[2], sys.argv[3]
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
